@@ -1,0 +1,161 @@
+/*
+ * clbm.h -- C ABI of the B200-native multiphase lattice-Boltzmann time step.
+ *
+ * This is the drop-in boundary for the one hot line of every CooLBM case file
+ * in AmooMaD/Multiphase-LBM:
+ *
+ *     std::for_each(std::execution::par_unseq, lattice, lattice + dim.nelem, lbm);
+ *     *parity = 1 - *parity;
+ *
+ * (reference: "shan-chen single component model/apps/laplace2D.h":506-507,
+ *  "shan-chen single component model/apps/contactAngle2D.h":801-802,
+ *  "Phase field model/apps/rayleighTaylor2D.h":980-983,
+ *  "Phase field model/apps/laplace3D.h":943-946,
+ *  "Abbashub LBM/apps/PulsatileBloodFlow2D.h":764-789).
+ *
+ * The reference has no FFI of its own: the functor `lbm` is an aggregate of raw
+ * pointers (lattice, flag, parity) plus scalar model parameters passed by value.
+ * The entry points below carry exactly that aggregate across a C boundary:
+ * plain pointers, sizes and doubles; no C++ or torch types.
+ *
+ * Host arrays use the reference memory layout:
+ *   lattice[s*2*npop + p*npop + k*nelem + i],  s = population set (0: f, 1: g),
+ *   p = buffer selected by parity, k = direction, i = cell index,
+ *   i = y + ny*x (2-D, y fastest)  /  i = z + nz*(y + ny*x) (3-D, z fastest),
+ *   npop = Q*nelem;  flag[i] is uint8 {0: bounce_back, 1: bulk}.
+ *
+ * Every function returns 0 on success and a negative CLBM_E* code on failure;
+ * clbm_last_error() returns the message of the last failure on this thread.
+ * Nothing throws across the boundary.  There is no CPU fallback: without a
+ * CUDA device clbm_create fails with CLBM_ENODEVICE.
+ */
+#ifndef CLBM_H
+#define CLBM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLBM_ABI_VERSION 1
+
+/* ---- models (one per reference functor family) -------------------------- */
+#define CLBM_MODEL_SC_D2Q9    0 /* LBM_Laplace2D / LBM_contactAngle2D (Yuan-CS Shan-Chen) */
+#define CLBM_MODEL_SC_D3Q19   1 /* same physics on the D3Q19 set of PF/apps/laplace3D.h:31-55 */
+#define CLBM_MODEL_HCZ_D2Q9   2 /* LBM_rayleighTaylor2D (He-Chen-Zhang phase field) */
+#define CLBM_MODEL_HCZ_D3Q19  3 /* LBM_laplace3D */
+#define CLBM_MODEL_PULSATILE  4 /* LBM_PulsatileBloodFlow2D (pressure-based D2Q9 MRT) */
+
+/* Shan-Chen force variant */
+#define CLBM_SC_FORCE_LAPLACE 0 /* SC/apps/laplace2D.h:198-242: psi_w = psi(rho_w) on G1(rho_w); + gravity*rho in y */
+#define CLBM_SC_FORCE_CONTACT 1 /* SC/apps/contactAngle2D.h:248-293: psi_w on the centre node's G1 branch; F=0 if rho<=0; no gravity */
+
+/* error codes */
+#define CLBM_OK          0
+#define CLBM_EINVAL     -1
+#define CLBM_ENODEVICE  -2
+#define CLBM_ECUDA      -3
+#define CLBM_ENOMEM     -4
+#define CLBM_ESTATE     -5
+
+/* reductions, clbm_reduce(kind) */
+#define CLBM_REDUCE_MASS    0 /* totalMass_*: sum of rho (SC) or phi (HCZ) over non-solid nodes (SC/apps/laplace2D.h:382-393) */
+#define CLBM_REDUCE_ENERGY  1 /* computeEnergy_*: 0.5*sum_bulk(u.u)/nelem_global (SC/apps/laplace2D.h:368-380, PF/apps/rayleighTaylor2D.h:784-797) */
+#define CLBM_REDUCE_UMAX    2 /* max |u| over bulk nodes (spurious-current diagnostic) */
+
+/* built-in initial conditions, clbm_init_case(case_id) -- device-side equivalents of iniLattice + inigeom */
+#define CLBM_CASE_SC_LAPLACE2D     0 /* SC/apps/laplace2D.h:132-145,397-404   args: {rhol, rhog, Rdrop}              */
+#define CLBM_CASE_SC_CONTACT2D     1 /* SC/apps/contactAngle2D.h:126-137,442-455 args: {rhol, rhog, RR}              */
+#define CLBM_CASE_SC_DROPLET3D     2 /* composed C4 case: sessile droplet, walls y=0,ny-1  args: {rhol, rhog, RR, yc} */
+#define CLBM_CASE_SC_DROPLET3D_PER 3 /* fully periodic free droplet            args: {rhol, rhog, RR}                 */
+#define CLBM_CASE_HCZ_RT2D         4 /* PF/apps/rayleighTaylor2D.h:155-193,802-820   args: none                       */
+#define CLBM_CASE_HCZ_LAPLACE3D    5 /* PF/apps/laplace3D.h:170-213,830-849          args: none                       */
+
+typedef struct clbm_ctx clbm_ctx;
+
+/*
+ * Scalar members of the reference LBM_* aggregates.  Members a model does not
+ * use are ignored.  The lattice handed to one context is an x-slab
+ * [x_offset, x_offset+nx) of a global lattice nx_global wide (x is the slowest
+ * index, so a slab is a contiguous range of every population array); a
+ * single-GPU run has x_offset=0, nx_global=nx.
+ */
+typedef struct clbm_params {
+    int32_t abi_version;    /* CLBM_ABI_VERSION */
+    int32_t model;          /* CLBM_MODEL_* */
+    int32_t nx, ny, nz;     /* local slab extent; nz = 1 for D2Q9 */
+    int32_t nx_global;      /* global x extent (== nx on one GPU) */
+    int32_t x_offset;       /* global x of local column 0 */
+    int32_t sc_force;       /* CLBM_SC_FORCE_* */
+    int32_t device;         /* CUDA device ordinal, -1 = current */
+    int32_t fused;          /* 1: fused plane-marching kernels where available (default), 0: staged kernels */
+    /* common */
+    double omega;           /* BGK relaxation rate (all multiphase models) */
+    double gravity;         /* body force in +y */
+    /* Shan-Chen / Yuan-CS  (LBM_Laplace2D members, SC/apps/laplace2D.h:104-113) */
+    double rho_w, a, b, R, TT;
+    /* HCZ (LBM_rayleighTaylor2D members, PF/apps/rayleighTaylor2D.h:113-122) */
+    double phi_l, phi_g, rho_l, rho_g, kappa;
+} clbm_params;
+
+/* ---- life cycle ---------------------------------------------------------- */
+int  clbm_create(const clbm_params *params, clbm_ctx **out);
+int  clbm_destroy(clbm_ctx *ctx);
+const char *clbm_last_error(void);
+int  clbm_abi_version(void);
+
+/* ---- state transfer (reference layout, host memory) ---------------------- */
+/* replaces the host-side ownership of lattice/flag/parity: copies the parity-selected
+ * "in" buffer of every population set and the mask to the device. */
+int  clbm_upload(clbm_ctx *ctx, const double *lattice, const uint8_t *flag, int parity);
+/* writes the current populations back into lattice[] (buffer selected by the returned
+ * parity; the other buffer is left untouched) so unchanged host accessors keep working. */
+int  clbm_download_lattice(clbm_ctx *ctx, double *lattice, int *parity);
+/* macroscopic fields with the reference definitions; any pointer may be NULL.
+ *   SC : s0 = density, s1 = pressure_node, u = u_actual
+ *   HCZ: s0 = phi, s1 = total_P, s2 = total_rho, u = velocity
+ * non-bulk nodes: s0/s2 as computed from the (zero) populations, s1 = 0, u = 0. */
+int  clbm_download_fields(clbm_ctx *ctx, double *s0, double *s1, double *s2,
+                          double *ux, double *uy, double *uz, uint8_t *flag);
+/* device-side initial condition; args has the case-specific doubles listed above */
+int  clbm_init_case(clbm_ctx *ctx, int case_id, const double *args, int nargs);
+
+/* ---- the hot path --------------------------------------------------------- */
+/* nsteps times { for_each(par_unseq, lattice, lattice+nelem, lbm); parity = 1-parity; }.
+ * Asynchronous on the context's stream; any download/reduce synchronises. */
+int  clbm_step(clbm_ctx *ctx, int nsteps);
+int  clbm_sync(clbm_ctx *ctx);
+/* same, bracketed by CUDA events on the launching stream; *ms = device time of the nsteps */
+int  clbm_step_timed(clbm_ctx *ctx, int nsteps, float *ms);
+/* number of kernel launches issued by this context so far */
+int64_t clbm_launch_count(const clbm_ctx *ctx);
+/* per-kernel device time of one step (CUDA events around every launch).
+ * names/ms hold up to cap entries; returns the number of kernels or <0. */
+int  clbm_profile_step(clbm_ctx *ctx, const char **names, float *ms, int cap);
+
+/* ---- diagnostics ---------------------------------------------------------- */
+int  clbm_reduce(clbm_ctx *ctx, int kind, double *out);
+
+/* ---- x-slab ghost exchange (multi-GPU) ----------------------- */
+/* A slab step is  clbm_step_begin (boundary planes, packs the send buffers) ->
+ * caller moves send buffers to the neighbours' recv buffers (NCCL / P2P) ->
+ * clbm_step_end (unpack + interior).  Buffers are device memory owned by ctx.
+ * side: 0 = towards x-1 neighbour, 1 = towards x+1 neighbour.
+ * phase: 0 = moment halo (rho / phi ...), 1 = crossing populations. */
+int  clbm_halo_buffer(clbm_ctx *ctx, int phase, int side, int recv, void **dev_ptr, size_t *bytes);
+int  clbm_halo_pack(clbm_ctx *ctx, int phase);
+int  clbm_halo_unpack(clbm_ctx *ctx, int phase);
+/* one time step split around the two exchanges:
+ *   stage 0: moments of the local slab + pack phase 0
+ *   stage 1: unpack phase 0 + collide/stream + pack phase 1
+ *   stage 2: unpack phase 1, flip parity                                         */
+int  clbm_step_stage(clbm_ctx *ctx, int stage);
+/* raw stream handle (cudaStream_t) so the caller can order its copies after ours */
+void *clbm_stream(clbm_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLBM_H */

@@ -1,0 +1,102 @@
+"""clbm_params mirror (include/clbm.h) and the reference's derived lattice-unit parameters.
+
+The struct carries the scalar members of the reference LBM_* aggregates
+(SC/apps/laplace2D.h:104-114, PF/apps/rayleighTaylor2D.h:113-123).
+"""
+import ctypes
+
+ABI_VERSION = 1
+
+MODEL_SC_D2Q9, MODEL_SC_D3Q19, MODEL_HCZ_D2Q9, MODEL_HCZ_D3Q19, MODEL_PULSATILE = range(5)
+SC_FORCE_LAPLACE, SC_FORCE_CONTACT = 0, 1
+REDUCE_MASS, REDUCE_ENERGY, REDUCE_UMAX = 0, 1, 2
+(CASE_SC_LAPLACE2D, CASE_SC_CONTACT2D, CASE_SC_DROPLET3D, CASE_SC_DROPLET3D_PER,
+ CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D) = range(6)
+
+MODEL_Q = {MODEL_SC_D2Q9: 9, MODEL_SC_D3Q19: 19, MODEL_HCZ_D2Q9: 9, MODEL_HCZ_D3Q19: 19, MODEL_PULSATILE: 9}
+MODEL_SETS = {MODEL_SC_D2Q9: 1, MODEL_SC_D3Q19: 1, MODEL_HCZ_D2Q9: 2, MODEL_HCZ_D3Q19: 2, MODEL_PULSATILE: 1}
+# algorithmic bytes per lattice update: every population read once + written once + 1 mask byte
+MODEL_BYTES_PER_LU = {m: 2 * MODEL_SETS[m] * MODEL_Q[m] * 8 + 1 for m in MODEL_Q}
+
+
+class Params(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int32), ("model", ctypes.c_int32),
+        ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("nz", ctypes.c_int32),
+        ("nx_global", ctypes.c_int32), ("x_offset", ctypes.c_int32),
+        ("sc_force", ctypes.c_int32), ("device", ctypes.c_int32), ("fused", ctypes.c_int32),
+        ("omega", ctypes.c_double), ("gravity", ctypes.c_double),
+        ("rho_w", ctypes.c_double), ("a", ctypes.c_double), ("b", ctypes.c_double),
+        ("R", ctypes.c_double), ("TT", ctypes.c_double),
+        ("phi_l", ctypes.c_double), ("phi_g", ctypes.c_double),
+        ("rho_l", ctypes.c_double), ("rho_g", ctypes.c_double), ("kappa", ctypes.c_double),
+    ]
+
+    @property
+    def nelem(self):
+        return self.nx * self.ny * self.nz
+
+    @property
+    def Q(self):
+        return MODEL_Q[self.model]
+
+    @property
+    def sets(self):
+        return MODEL_SETS[self.model]
+
+    @property
+    def lattice_size(self):
+        """sizeOfLattice(): 2 buffers x sets x Q x nelem doubles (SC/apps/laplace2D.h:93)."""
+        return 2 * self.sets * self.Q * self.nelem
+
+    def copy(self, **kw):
+        q = Params.from_buffer_copy(bytes(self))
+        for k, v in kw.items():
+            setattr(q, k, v)
+        return q
+
+
+def lb_parameters(ulb, lref, Re):
+    """lbParameters_*: nu, omega, dx, dt (SC/apps/laplace2D.h:52-58)."""
+    nu = ulb * lref / Re
+    omega = 1.0 / (3.0 * nu + 0.5)
+    dx = 1.0 / lref
+    dt = dx * ulb
+    return nu, omega, dx, dt
+
+
+def make_params(model, nx, ny, nz=1, **kw):
+    p = Params()
+    p.abi_version = ABI_VERSION
+    p.model = model
+    p.nx, p.ny, p.nz = nx, ny, nz
+    p.nx_global, p.x_offset = nx, 0
+    p.device = -1
+    p.fused = 1
+    p.omega = 1.0
+    p.a, p.b, p.R = 1.0, 4.0, 1.0
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def sc_params(model, nx, ny, nz=1, *, omega=None, tau=None, ulb=0.01, N=None, Re=6.0, rho_w=0.12,
+              a=1.0, b=4.0, R=1.0, TT0=0.875, gravity=0.0, sc_force=SC_FORCE_LAPLACE, **kw):
+    """Shan-Chen parameter set; defaults = SC/apps/Config_Files/config_Laplace2D.txt.
+    TT = TT0 * Tc, Tc = 0.3773 a / (b R)  (SC/apps/laplace2D.h:468-470)."""
+    if omega is None:
+        omega = 1.0 / tau if tau is not None else lb_parameters(ulb, N if N else nx, Re)[1]
+    Tc = 0.3773 * a / (b * R)
+    return make_params(model, nx, ny, nz, omega=omega, rho_w=rho_w, a=a, b=b, R=R, TT=TT0 * Tc,
+                       gravity=gravity, sc_force=sc_force, **kw)
+
+
+def hcz_params(model, nx, ny, nz=1, *, omega=None, ulb=0.04, N=None, Re=3000.0, phi_l=0.251, phi_g=0.024,
+               rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-6.25e-6, **kw):
+    """HCZ parameter set; defaults = PF/apps/Config_Files/config_rayleighTaylor2D.txt."""
+    if omega is None:
+        omega = lb_parameters(ulb, N if N else nx, Re)[1]
+    return make_params(model, nx, ny, nz, omega=omega, phi_l=phi_l, phi_g=phi_g, rho_l=rho_l, rho_g=rho_g,
+                       a=a, b=b, kappa=kappa, gravity=gravity, **kw)

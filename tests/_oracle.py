@@ -1,0 +1,96 @@
+"""ctypes binding of oracle/_build/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+The oracle is the checker, never the product path: only tests/, smoke() and
+bench.py's cpu_baseline / --impl reference legs import this module.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+
+_lib = None
+
+
+def build(force=False):
+    src = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".c")]
+    src.append(os.path.join(ROOT, "include", "clbm.h"))
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(LIB)
+        dp = ctypes.POINTER(ctypes.c_double)
+        _lib.oracle_lattice_size.restype = ctypes.c_size_t
+        _lib.oracle_step.restype = ctypes.c_int
+        _lib.oracle_fields.restype = ctypes.c_int
+        _lib.oracle_init_case.restype = ctypes.c_int
+    return _lib
+
+
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+class OracleSim:
+    """Reference-layout host state advanced by the CPU oracle."""
+
+    def __init__(self, params):
+        self.p = params
+        self.lattice = np.zeros(params.lattice_size, dtype=np.float64)
+        self.flag = np.ones(params.nelem, dtype=np.uint8)
+        self.parity = ctypes.c_int(0)
+
+    def init_case(self, case_id, args=()):
+        a = np.asarray(args, dtype=np.float64)
+        rc = lib().oracle_init_case(ctypes.byref(self.p), int(case_id), _dptr(a), int(a.size), _dptr(self.lattice),
+                                    self.flag.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), ctypes.byref(self.parity))
+        assert rc == 0, "oracle_init_case failed"
+        return self
+
+    def step(self, n=1, threads=0):
+        rc = lib().oracle_step(ctypes.byref(self.p), _dptr(self.lattice),
+                               self.flag.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                               ctypes.byref(self.parity), int(n), int(threads))
+        assert rc == 0
+        return self
+
+    def in_pops(self):
+        """current ("in") populations as [sets, Q, nelem]"""
+        p = self.p
+        npop = p.Q * p.nelem
+        out = []
+        for s in range(p.sets):
+            off = s * 2 * npop + self.parity.value * npop
+            out.append(self.lattice[off:off + npop].reshape(p.Q, p.nelem))
+        return np.stack(out)
+
+    def fields(self):
+        n = self.p.nelem
+        names = ["s0", "s1", "s2", "ux", "uy", "uz"]
+        arrs = {k: np.zeros(n) for k in names}
+        rc = lib().oracle_fields(ctypes.byref(self.p), _dptr(self.lattice),
+                                 self.flag.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), self.parity.value,
+                                 *[_dptr(arrs[k]) for k in names])
+        assert rc == 0
+        return arrs
+
+
+def max_threads():
+    return lib().oracle_max_threads()
+
+
+def ref_binary(name):
+    """path of a prebuilt reference-harness binary (oracle/_ref), or None"""
+    path = os.path.join(REF_DIR, name)
+    return path if os.path.exists(path) else None
