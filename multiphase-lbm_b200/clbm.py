@@ -1,0 +1,200 @@
+"""ctypes binding of the clbm C ABI (include/clbm.h) -- the host-side mirror of the reference's
+LBM_* functor object: raw lattice / flag / parity on the host side, the time step on the device.
+
+There is no CPU fallback: if csrc/libclbm.so is missing or no CUDA device is present, creating a
+Lattice raises.  Build the library with `python -c "import __graft_entry__ as g; g.build()"` or
+`make -C multiphase-lbm_b200/csrc`.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import params as P
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libclbm.so")
+
+EXPORTS = [
+    "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_download_lattice",
+    "clbm_download_fields", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
+    "clbm_profile_step", "clbm_reduce", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
+    "clbm_stream",
+]
+
+_lib = None
+
+
+class ClbmError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen libclbm.so and declare the prototypes.  Fails loudly when the extension is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ClbmError("CUDA extension %s is missing: build it first (there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    vp, dp, u8p = ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint8)
+    lib.clbm_create.argtypes = [ctypes.POINTER(P.Params), ctypes.POINTER(vp)]
+    lib.clbm_destroy.argtypes = [vp]
+    lib.clbm_last_error.restype = ctypes.c_char_p
+    lib.clbm_upload.argtypes = [vp, vp, vp, ctypes.c_int]
+    lib.clbm_download_lattice.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int)]
+    lib.clbm_download_fields.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.clbm_init_case.argtypes = [vp, ctypes.c_int, dp, ctypes.c_int]
+    lib.clbm_step.argtypes = [vp, ctypes.c_int]
+    lib.clbm_sync.argtypes = [vp]
+    lib.clbm_step_timed.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+    lib.clbm_launch_count.argtypes = [vp]
+    lib.clbm_launch_count.restype = ctypes.c_int64
+    lib.clbm_profile_step.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    lib.clbm_reduce.argtypes = [vp, ctypes.c_int, dp]
+    lib.clbm_halo_buffer.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp),
+                                     ctypes.POINTER(ctypes.c_size_t)]
+    lib.clbm_halo_pack.argtypes = [vp, ctypes.c_int]
+    lib.clbm_halo_unpack.argtypes = [vp, ctypes.c_int]
+    lib.clbm_step_stage.argtypes = [vp, ctypes.c_int]
+    lib.clbm_stream.argtypes = [vp]
+    lib.clbm_stream.restype = vp
+    for name in EXPORTS:
+        getattr(lib, name)  # every declared symbol must resolve
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):   # torch tensor (pinned host memory)
+        return a.data_ptr()
+    return a
+
+
+class Lattice:
+    """Device-resident lattice of one x-slab; the counterpart of an `LBM_*` functor plus its arrays."""
+
+    def __init__(self, params):
+        self.lib = load_library()
+        self.p = params
+        h = ctypes.c_void_p()
+        self._h = None
+        self._check(self.lib.clbm_create(ctypes.byref(params), ctypes.byref(h)))
+        self._h = h
+
+    # -- plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise ClbmError("clbm error %d: %s" % (rc, self.lib.clbm_last_error().decode()))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.clbm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state transfer (reference layout)
+    def upload(self, lattice, flag, parity=0):
+        assert lattice.dtype == np.float64 if isinstance(lattice, np.ndarray) else True
+        self._check(self.lib.clbm_upload(self._h, _ptr(lattice), _ptr(flag), int(parity)))
+
+    def download_lattice(self, lattice=None):
+        if lattice is None:
+            lattice = np.zeros(self.p.lattice_size, dtype=np.float64)
+        par = ctypes.c_int(0)
+        self._check(self.lib.clbm_download_lattice(self._h, _ptr(lattice), ctypes.byref(par)))
+        return lattice, par.value
+
+    def in_pops(self):
+        """current populations as [sets, Q, nelem] (same view as tests/_oracle.OracleSim.in_pops)"""
+        lat, par = self.download_lattice()
+        p = self.p
+        npop = p.Q * p.nelem
+        return np.stack([lat[s * 2 * npop + par * npop: s * 2 * npop + (par + 1) * npop].reshape(p.Q, p.nelem)
+                         for s in range(p.sets)])
+
+    def fields(self, names=("s0", "s1", "s2", "ux", "uy", "uz"), out=None):
+        """macroscopic fields with the reference's definitions"""
+        n = self.p.nelem
+        order = ["s0", "s1", "s2", "ux", "uy", "uz"]
+        arrs = out or {k: np.zeros(n) for k in names}
+        ptrs = [_ptr(arrs[k]) if k in arrs else None for k in order]
+        self._check(self.lib.clbm_download_fields(self._h, *ptrs, None))
+        return arrs
+
+    def flags(self):
+        f = np.zeros(self.p.nelem, dtype=np.uint8)
+        self._check(self.lib.clbm_download_fields(self._h, None, None, None, None, None, None, _ptr(f)))
+        return f
+
+    def init_case(self, case_id, args=()):
+        a = np.asarray(args, dtype=np.float64)
+        self._check(self.lib.clbm_init_case(self._h, int(case_id), a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                            int(a.size)))
+        return self
+
+    # -- the hot path
+    def step(self, n=1):
+        self._check(self.lib.clbm_step(self._h, int(n)))
+        return self
+
+    def sync(self):
+        self._check(self.lib.clbm_sync(self._h))
+
+    def step_timed(self, n):
+        ms = ctypes.c_float(0)
+        self._check(self.lib.clbm_step_timed(self._h, int(n), ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self.lib.clbm_launch_count(self._h))
+
+    def profile_step(self):
+        cap = 64
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_float * cap)()
+        n = self.lib.clbm_profile_step(self._h, names, ms, cap)
+        if n < 0:
+            self._check(n)
+        return [(names[i].decode(), ms[i]) for i in range(n)]
+
+    def reduce(self, kind):
+        out = ctypes.c_double(0)
+        self._check(self.lib.clbm_reduce(self._h, int(kind), ctypes.byref(out)))
+        return out.value
+
+    # -- slab exchange
+    def halo_buffer(self, phase, side, recv):
+        ptr = ctypes.c_void_p()
+        nbytes = ctypes.c_size_t(0)
+        self._check(self.lib.clbm_halo_buffer(self._h, phase, side, int(recv), ctypes.byref(ptr), ctypes.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def halo_pack(self, phase):
+        self._check(self.lib.clbm_halo_pack(self._h, phase))
+
+    def halo_unpack(self, phase):
+        self._check(self.lib.clbm_halo_unpack(self._h, phase))
+
+    def step_stage(self, stage):
+        self._check(self.lib.clbm_step_stage(self._h, stage))
+
+    def stream(self):
+        return self.lib.clbm_stream(self._h)

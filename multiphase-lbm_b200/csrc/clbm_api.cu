@@ -1,0 +1,428 @@
+// clbm_api.cu -- the C ABI of include/clbm.h: context life cycle, state transfer between the
+// reference host layout and the device slab storage, the step loop, diagnostics, profiling.
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+#include "clbm_internal.h"
+
+namespace clbm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? CLBM_ENOMEM : CLBM_ECUDA;
+}
+
+LaunchScope::LaunchScope(clbm_ctx *ctx, const char *n) : c(ctx), name(n), a(nullptr), b(nullptr)
+{
+    c->launches++;
+    if (c->profiling) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+}
+LaunchScope::~LaunchScope()
+{
+    if (c->profiling) {
+        cudaEventRecord(b, c->stream);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        c->prof.push_back({name, ms});
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+}
+
+// per-model dispatch (kernels live in the per-model .cu files)
+int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz);
+int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
+int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
+int sc_psi_all(clbm_ctx *c);
+int sc_collide_all(clbm_ctx *c);
+int hcz2d_phi(clbm_ctx *c);
+int hcz2d_level1(clbm_ctx *c);
+int hcz2d_collide(clbm_ctx *c);
+int hcz3d_moments(clbm_ctx *c);
+int hcz3d_level1(clbm_ctx *c);
+int hcz3d_level2(clbm_ctx *c);
+int hcz3d_collide(clbm_ctx *c);
+
+static int model_step(clbm_ctx *c)
+{
+    switch (c->prm.model) {
+    case CLBM_MODEL_SC_D2Q9:
+    case CLBM_MODEL_SC_D3Q19: return sc_step(c);
+    case CLBM_MODEL_HCZ_D2Q9: return hcz2d_step(c);
+    case CLBM_MODEL_HCZ_D3Q19: return hcz3d_step(c);
+    }
+    set_error("model %d has no step", c->prm.model);
+    return CLBM_EINVAL;
+}
+
+int model_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz)
+{
+    switch (c->prm.model) {
+    case CLBM_MODEL_SC_D2Q9:
+    case CLBM_MODEL_SC_D3Q19: return sc_fields(c, s0, s1, ux, uy, uz);
+    case CLBM_MODEL_HCZ_D2Q9: return hcz2d_fields(c, s0, s1, s2, ux, uy, uz);
+    case CLBM_MODEL_HCZ_D3Q19: return hcz3d_fields(c, s0, s1, s2, ux, uy, uz);
+    }
+    return CLBM_EINVAL;
+}
+
+// slab protocol: see include/clbm.h (clbm_step_stage)
+int model_stage(clbm_ctx *c, int stage)
+{
+    int rc = 0;
+    const int m = c->prm.model;
+    if (stage == 0) {
+        if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = sc_psi_all(c);
+        else if (m == CLBM_MODEL_HCZ_D2Q9) rc = hcz2d_phi(c);
+        else if (m == CLBM_MODEL_HCZ_D3Q19) rc = hcz3d_moments(c);
+        else rc = CLBM_EINVAL;
+        if (rc) return rc;
+        return halo_pack(c, 0);
+    }
+    if (stage == 1) {
+        if ((rc = halo_unpack(c, 0))) return rc;
+        if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = sc_collide_all(c);
+        else if (m == CLBM_MODEL_HCZ_D2Q9) { if (!(rc = hcz2d_level1(c))) rc = hcz2d_collide(c); }
+        else if (m == CLBM_MODEL_HCZ_D3Q19) { if (!(rc = hcz3d_level1(c)) && !(rc = hcz3d_level2(c))) rc = hcz3d_collide(c); }
+        else rc = CLBM_EINVAL;
+        if (rc) return rc;
+        c->parity = 1 - c->parity;   // the freshly written buffer becomes "in"
+        return halo_pack(c, 1);
+    }
+    if (stage == 2) return halo_unpack(c, 1);
+    set_error("bad stage %d", stage);
+    return CLBM_EINVAL;
+}
+
+static int ensure_stage(clbm_ctx *c, size_t bytes)
+{
+    if (c->stage_bytes >= bytes) return 0;
+    if (c->stage) cudaFreeHost(c->stage);
+    c->stage = nullptr;
+    c->stage_bytes = 0;
+    CLBM_CUDA(cudaMallocHost(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+}  // namespace clbm
+
+using namespace clbm;
+
+extern "C" {
+
+const char *clbm_last_error(void) { return g_err; }
+int clbm_abi_version(void) { return CLBM_ABI_VERSION; }
+
+int clbm_create(const clbm_params *p, clbm_ctx **out)
+{
+    if (!p || !out) { set_error("null argument"); return CLBM_EINVAL; }
+    *out = nullptr;
+    if (p->abi_version != CLBM_ABI_VERSION) { set_error("ABI version %d != %d", p->abi_version, CLBM_ABI_VERSION); return CLBM_EINVAL; }
+    if (p->model < 0 || p->model > CLBM_MODEL_HCZ_D3Q19) { set_error("unsupported model %d", p->model); return CLBM_EINVAL; }
+    const bool is3d = p->model == CLBM_MODEL_SC_D3Q19 || p->model == CLBM_MODEL_HCZ_D3Q19;
+    if (p->nx < 1 || p->ny < 1 || p->nz < 1 || (!is3d && p->nz != 1)) { set_error("bad extent %d x %d x %d", p->nx, p->ny, p->nz); return CLBM_EINVAL; }
+    if (p->nx_global < p->nx || p->x_offset < 0 || p->x_offset + p->nx > p->nx_global) { set_error("bad slab [%d,%d) of %d", p->x_offset, p->x_offset + p->nx, p->nx_global); return CLBM_EINVAL; }
+    if (!(p->omega > 0.0)) { set_error("omega must be > 0"); return CLBM_EINVAL; }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device: this library has no CPU fallback");
+        return CLBM_ENODEVICE;
+    }
+    int dev = p->device;
+    if (dev < 0) CLBM_CUDA(cudaGetDevice(&dev));
+    CLBM_CUDA(cudaSetDevice(dev));
+
+    clbm_ctx *c = new (std::nothrow) clbm_ctx();
+    if (!c) return CLBM_ENOMEM;
+    memset((void *)&c->prm, 0, sizeof(c->prm));
+    c->prm = *p;
+    c->device = dev;
+    c->Q = is3d ? 19 : 9;
+    c->sets = (p->model == CLBM_MODEL_HCZ_D2Q9 || p->model == CLBM_MODEL_HCZ_D3Q19) ? 2 : 1;
+    c->multi = p->nx != p->nx_global;
+    c->parity = 0;
+    c->host_parity0 = 0;
+    c->steps_taken = 0;
+    c->launches = 0;
+    c->profiling = false;
+    c->stage = nullptr;
+    c->stage_bytes = 0;
+    c->nfld = 0;
+    for (auto &s : c->pop) for (auto &b : s) b = nullptr;
+    for (auto &f : c->fld) f = nullptr;
+    memset(c->halo, 0, sizeof(c->halo));
+    memset(c->halo_bytes, 0, sizeof(c->halo_bytes));
+    c->flag = nullptr; c->red_dev = nullptr; c->red_host = nullptr;
+
+    Geom &g = c->geo;
+    g.nx = p->nx; g.ny = p->ny; g.nz = p->nz;
+    g.G = (p->model == CLBM_MODEL_HCZ_D3Q19) ? 3 : (p->model == CLBM_MODEL_HCZ_D2Q9 ? 2 : 1);
+    g.wrapx = c->multi ? 0 : 1;
+    g.nx_global = p->nx_global; g.x_offset = p->x_offset;
+    g.plane = (long long)p->ny * p->nz;
+    g.ncs = (long long)(p->nx + 2 * g.G) * g.plane;
+    if (c->multi && p->nx < g.G) { set_error("slab thinner (%d) than the halo depth (%d)", p->nx, g.G); delete c; return CLBM_EINVAL; }
+
+    ModelParams &m = c->mp;
+    m.omega = p->omega; m.gravity = p->gravity;
+    m.rho_w = p->rho_w; m.a = p->a; m.b = p->b; m.R = p->R; m.TT = p->TT;
+    m.phi_l = p->phi_l; m.phi_g = p->phi_g; m.rho_l = p->rho_l; m.rho_g = p->rho_g; m.kappa = p->kappa;
+    m.sc_force = p->sc_force;
+
+    int rc = 0;
+    auto fail = [&](int code) { clbm_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream create failed"); delete c; return CLBM_ECUDA; }
+    cudaEventCreate(&c->ev0);
+    cudaEventCreate(&c->ev1);
+    const size_t popbytes = (size_t)c->Q * g.ncs * sizeof(double);
+    for (int s = 0; s < c->sets; ++s)
+        for (int b = 0; b < 2; ++b) {
+            if (cudaMalloc(&c->pop[s][b], popbytes) != cudaSuccess) { set_error("out of device memory allocating %zu bytes of populations", popbytes); return fail(CLBM_ENOMEM); }
+            cudaMemsetAsync(c->pop[s][b], 0, popbytes, c->stream);
+        }
+    if (cudaMalloc(&c->flag, (size_t)g.ncs) != cudaSuccess) { set_error("out of device memory (flag)"); return fail(CLBM_ENOMEM); }
+    cudaMemsetAsync(c->flag, CELL_BULK, (size_t)g.ncs, c->stream);
+    c->nfld = (p->model == CLBM_MODEL_HCZ_D3Q19) ? 8 : (p->model == CLBM_MODEL_HCZ_D2Q9 ? 5 : 1);
+    for (int i = 0; i < c->nfld; ++i) {
+        if (cudaMalloc(&c->fld[i], (size_t)g.ncs * sizeof(double)) != cudaSuccess) { set_error("out of device memory (field %d)", i); return fail(CLBM_ENOMEM); }
+        cudaMemsetAsync(c->fld[i], 0, (size_t)g.ncs * sizeof(double), c->stream);
+    }
+    if (cudaMalloc(&c->red_dev, 8 * sizeof(double)) != cudaSuccess || cudaMallocHost(&c->red_host, 8 * sizeof(double)) != cudaSuccess) {
+        set_error("out of memory (reduction scratch)");
+        return fail(CLBM_ENOMEM);
+    }
+    if (c->multi && (rc = halo_alloc(c))) return fail(rc);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { set_error("device initialisation failed"); return fail(CLBM_ECUDA); }
+    *out = c;
+    return CLBM_OK;
+}
+
+int clbm_destroy(clbm_ctx *c)
+{
+    if (!c) return CLBM_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &s : c->pop) for (auto &b : s) if (b) cudaFree(b);
+    for (auto &f : c->fld) if (f) cudaFree(f);
+    if (c->flag) cudaFree(c->flag);
+    if (c->red_dev) cudaFree(c->red_dev);
+    if (c->red_host) cudaFreeHost(c->red_host);
+    if (c->stage) cudaFreeHost(c->stage);
+    for (auto &ph : c->halo) for (auto &sd : ph) for (auto &b : sd) if (b) cudaFree(b);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return CLBM_OK;
+}
+
+int clbm_upload(clbm_ctx *c, const double *lattice, const uint8_t *flag, int parity)
+{
+    if (!c || !lattice || !flag || (parity != 0 && parity != 1)) { set_error("bad argument to clbm_upload"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    const Geom &g = c->geo;
+    const size_t nelem = (size_t)g.nx * g.plane, npop = (size_t)c->Q * nelem;
+    const size_t ghost = (size_t)g.G * g.plane;
+    // the device "in" buffer becomes buffer 0; the other one restarts from zero like the reference's
+    // value-initialised vector
+    c->parity = 0;
+    for (int s = 0; s < c->sets; ++s) {
+        CLBM_CUDA(cudaMemsetAsync(c->pop[s][1], 0, (size_t)c->Q * g.ncs * sizeof(double), c->stream));
+        const double *src = lattice + (size_t)s * 2 * npop + (size_t)parity * npop;
+        for (int k = 0; k < c->Q; ++k)
+            CLBM_CUDA(cudaMemcpyAsync(c->pop[s][0] + (size_t)k * g.ncs + ghost, src + (size_t)k * nelem, nelem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    CLBM_CUDA(cudaMemcpyAsync(c->flag + ghost, flag, nelem, cudaMemcpyHostToDevice, c->stream));
+    CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_parity0 = parity;   // download returns (uploaded parity + steps taken) & 1, like the reference's *parity
+    c->steps_taken = 0;
+    return CLBM_OK;
+}
+
+static int host_parity(const clbm_ctx *c) { return (int)((c->host_parity0 + c->steps_taken) & 1); }
+static void count_step(clbm_ctx *c) { c->steps_taken++; }
+
+int clbm_download_lattice(clbm_ctx *c, double *lattice, int *parity)
+{
+    if (!c || !lattice) { set_error("bad argument to clbm_download_lattice"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    const Geom &g = c->geo;
+    const size_t nelem = (size_t)g.nx * g.plane, npop = (size_t)c->Q * nelem;
+    const size_t ghost = (size_t)g.G * g.plane;
+    const int hp = host_parity(c);
+    for (int s = 0; s < c->sets; ++s) {
+        double *dst = lattice + (size_t)s * 2 * npop + (size_t)hp * npop;
+        for (int k = 0; k < c->Q; ++k)
+            CLBM_CUDA(cudaMemcpyAsync(dst + (size_t)k * nelem, c->pop[s][c->parity] + (size_t)k * g.ncs + ghost, nelem * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    if (parity) *parity = hp;
+    return CLBM_OK;
+}
+
+int clbm_download_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz, uint8_t *flag)
+{
+    if (!c) { set_error("null context"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    const Geom &g = c->geo;
+    const size_t nelem = (size_t)g.nx * g.plane;
+    double *host[6] = {s0, s1, s2, ux, uy, uz};
+    double *dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int nwant = 0;
+    for (auto h : host) nwant += h != nullptr;
+    if (nwant) {
+        double *tmp = nullptr;
+        CLBM_CUDA(cudaMalloc(&tmp, (size_t)nwant * nelem * sizeof(double)));
+        int j = 0;
+        for (int i = 0; i < 6; ++i) if (host[i]) dev[i] = tmp + (size_t)(j++) * nelem;
+        int rc = model_fields(c, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5]);
+        if (rc) { cudaFree(tmp); return rc; }
+        for (int i = 0; i < 6; ++i)
+            if (host[i]) {
+                cudaError_t e = cudaMemcpyAsync(host[i], dev[i], nelem * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+                if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(e, "field download", __FILE__, __LINE__); }
+            }
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        cudaFree(tmp);
+        if (e != cudaSuccess) return cuda_fail(e, "field download sync", __FILE__, __LINE__);
+    }
+    if (flag) {
+        CLBM_CUDA(cudaMemcpyAsync(flag, c->flag + (size_t)g.G * g.plane, nelem, cudaMemcpyDeviceToHost, c->stream));
+        CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return CLBM_OK;
+}
+
+int clbm_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)
+{
+    if (!c) { set_error("null context"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    int rc = model_init_case(c, case_id, args, nargs);
+    if (rc) return rc;
+    c->host_parity0 = 0;
+    c->steps_taken = 0;
+    CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    return CLBM_OK;
+}
+
+int clbm_step(clbm_ctx *c, int nsteps)
+{
+    if (!c || nsteps < 0) { set_error("bad argument to clbm_step"); return CLBM_EINVAL; }
+    if (c->multi) { set_error("clbm_step on an x-slab: drive it with clbm_step_stage + halo exchange"); return CLBM_ESTATE; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    for (int s = 0; s < nsteps; ++s) {
+        int rc = model_step(c);
+        if (rc) return rc;
+        count_step(c);
+    }
+    return CLBM_OK;
+}
+
+int clbm_step_stage(clbm_ctx *c, int stage)
+{
+    if (!c) { set_error("null context"); return CLBM_EINVAL; }
+    if (!c->multi) { set_error("clbm_step_stage needs an x-slab context (nx < nx_global)"); return CLBM_ESTATE; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    int rc = model_stage(c, stage);
+    if (rc) return rc;
+    if (stage == 1) count_step(c);
+    return CLBM_OK;
+}
+
+int clbm_sync(clbm_ctx *c)
+{
+    if (!c) { set_error("null context"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    return CLBM_OK;
+}
+
+int clbm_step_timed(clbm_ctx *c, int nsteps, float *ms)
+{
+    if (!c || !ms) { set_error("bad argument to clbm_step_timed"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    CLBM_CUDA(cudaEventRecord(c->ev0, c->stream));
+    int rc = clbm_step(c, nsteps);
+    if (rc) return rc;
+    CLBM_CUDA(cudaEventRecord(c->ev1, c->stream));
+    CLBM_CUDA(cudaEventSynchronize(c->ev1));
+    CLBM_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return CLBM_OK;
+}
+
+int64_t clbm_launch_count(const clbm_ctx *c) { return c ? c->launches : -1; }
+
+int clbm_profile_step(clbm_ctx *c, const char **names, float *ms, int cap)
+{
+    if (!c || !names || !ms || cap <= 0) { set_error("bad argument to clbm_profile_step"); return CLBM_EINVAL; }
+    if (c->multi) { set_error("profile a single-slab context"); return CLBM_ESTATE; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    c->prof.clear();
+    c->profiling = true;
+    int rc = model_step(c);
+    c->profiling = false;
+    if (rc) return rc;
+    count_step(c);
+    int n = 0;
+    for (auto &k : c->prof) {
+        if (n >= cap) break;
+        names[n] = k.name.c_str();   // static strings behind std::string copies owned by ctx->prof
+        ms[n] = k.ms;
+        ++n;
+    }
+    return n;
+}
+
+int clbm_reduce(clbm_ctx *c, int kind, double *out)
+{
+    if (!c || !out) { set_error("bad argument to clbm_reduce"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    return model_reduce(c, kind, out);
+}
+
+int clbm_halo_buffer(clbm_ctx *c, int phase, int side, int recv, void **dev_ptr, size_t *bytes)
+{
+    if (!c || phase < 0 || phase > 2 || side < 0 || side > 1 || recv < 0 || recv > 1 || !dev_ptr || !bytes) { set_error("bad argument to clbm_halo_buffer"); return CLBM_EINVAL; }
+    if (!c->multi) { set_error("no halo buffers on a single-slab context"); return CLBM_ESTATE; }
+    *dev_ptr = c->halo[phase][side][recv];
+    *bytes = c->halo_bytes[phase];
+    return CLBM_OK;
+}
+
+int clbm_halo_pack(clbm_ctx *c, int phase)
+{
+    if (!c || !c->multi) { set_error("halo pack needs an x-slab context"); return CLBM_ESTATE; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    return halo_pack(c, phase);
+}
+int clbm_halo_unpack(clbm_ctx *c, int phase)
+{
+    if (!c || !c->multi) { set_error("halo unpack needs an x-slab context"); return CLBM_ESTATE; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    return halo_unpack(c, phase);
+}
+
+void *clbm_stream(clbm_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+}  // extern "C"

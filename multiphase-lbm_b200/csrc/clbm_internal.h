@@ -1,0 +1,99 @@
+// clbm_internal.h -- context object behind the C ABI (include/clbm.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/clbm.h"
+#include "lattice.cuh"
+
+namespace clbm {
+
+// scalar model parameters handed to kernels by value
+struct ModelParams {
+    double omega, gravity;
+    double rho_w, a, b, R, TT;                    // Shan-Chen / Yuan-CS
+    double phi_l, phi_g, rho_l, rho_g, kappa;     // HCZ
+    int sc_force;
+};
+
+struct KernelTiming {
+    std::string name;
+    float ms;
+};
+
+}  // namespace clbm
+
+struct clbm_ctx {
+    clbm_params prm;
+    clbm::Geom geo;
+    clbm::ModelParams mp;
+    int Q, sets, device;
+    int parity;           // which device buffer is "in"
+    int host_parity0;     // parity value the host uploaded
+    long long steps_taken;
+    int multi;            // 1: x-slab of a wider lattice (ghost planes filled by exchange)
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int64_t launches;
+
+    // populations: pop[set][buffer], each Q * geo.ncs doubles
+    double *pop[2][2];
+    uint8_t *flag;        // geo.ncs
+    // moment / stage fields, geo.ncs doubles each (meaning depends on the model)
+    double *fld[12];
+    int nfld;
+    // reduction scratch
+    double *red_dev;
+    double *red_host;     // pinned
+    // halo buffers: [phase][side][send=0/recv=1]
+    void *halo[3][2][2];
+    size_t halo_bytes[3];
+    // staging for host<->device slab transfers (pinned), grown on demand
+    void *stage;
+    size_t stage_bytes;
+    // profiling
+    bool profiling;
+    std::vector<clbm::KernelTiming> prof;
+};
+
+namespace clbm {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define CLBM_CUDA(call)                                                        \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return clbm::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// RAII-ish helper that counts a launch and (when profiling) brackets it with events
+struct LaunchScope {
+    clbm_ctx *c;
+    const char *name;
+    cudaEvent_t a, b;
+    LaunchScope(clbm_ctx *ctx, const char *n);
+    ~LaunchScope();
+};
+
+// model steps (one full time step on ctx->stream, x-planes [0,nx)); defined per model
+int sc_step(clbm_ctx *c);
+int hcz2d_step(clbm_ctx *c);
+int hcz3d_step(clbm_ctx *c);
+// staged halves for the slab exchange protocol
+int model_stage(clbm_ctx *c, int stage);
+// macroscopic fields into device arrays of nx*ny*nz (no ghosts); NULL = skip
+int model_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
+int model_reduce(clbm_ctx *c, int kind, double *out);
+int model_init_case(clbm_ctx *c, int case_id, const double *args, int nargs);
+int halo_pack(clbm_ctx *c, int phase);
+int halo_unpack(clbm_ctx *c, int phase);
+int halo_alloc(clbm_ctx *c);
+
+inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+}  // namespace clbm

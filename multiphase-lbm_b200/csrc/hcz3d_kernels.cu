@@ -1,0 +1,282 @@
+// hcz3d_kernels.cu -- He-Chen-Zhang phase-field D3Q19 time step (PF/apps/laplace3D.h).
+//
+// laplace3D.h defines psi_rho = total_P - rho/3 where total_P itself needs grad(lap phi) and
+// grad(psi phi) (:318-336), so grad_psi_rho (:470-500) reaches radius 3 in phi; the reference
+// recomputes that whole chain at all 19 neighbours (2 kLUPS/core).  Here the levels
+// of SURVEY.md A.7 are materialised once per step:
+//   level 0  hcz3d_moments_kernel : phi, P_term, raw g momentum            (:216-258)
+//   level 1  hcz3d_level1_kernel  : lap phi (wall neighbours skipped, :370-393), psi(phi) (:268-275)
+//   level 2  hcz3d_level2_kernel  : u (:280-312 incl. the forcey-in-z quirk), total_P (:318-328),
+//                                   psi_rho = total_P - rho/3 (:330-336)
+//   level 3  hcz3d_collide_kernel : grad psi_rho (:470-500), collideBgk (:562-624), rest (:664-677),
+//                                   push stream (:539-559)
+// Wall fallback of the gradients: a bounce_back neighbour contributes the CENTRE value (:450-455).
+// Field slots: 0 phi, 1 P_term, 2-4 raw momentum, 5 lap phi, 6 psi(phi), 7 psi_rho
+#include "sc_cell.cuh"
+
+namespace clbm {
+
+using L19 = D3Q19;
+CLBM_D double hcz_rho_of_phi3(const ModelParams &mp, double phi)
+{
+    return mp.rho_g + ((phi - mp.phi_g) / (mp.phi_l - mp.phi_g)) * (mp.rho_l - mp.rho_g);
+}
+
+struct FieldPtrs8 { double *p[8]; };
+
+__global__ void __launch_bounds__(256)
+hcz3d_moments_kernel(const double *__restrict__ fin, const double *__restrict__ gin, FieldPtrs8 F, Geom g, int x0,
+                     long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const long long i = (long long)(x0 + g.G) * g.plane + t;
+    double f[19];
+#pragma unroll
+    for (int k = 0; k < 19; ++k) f[k] = fin[(size_t)k * g.ncs + i];
+    F.p[0][i] = Mom<L19>::sum(f);
+#pragma unroll
+    for (int k = 0; k < 19; ++k) f[k] = gin[(size_t)k * g.ncs + i];
+    double jx, jy, jz;
+    Mom<L19>::first(f, jx, jy, jz);
+    F.p[1][i] = Mom<L19>::sum(f);
+    F.p[2][i] = jx;
+    F.p[3][i] = jy;
+    F.p[4][i] = jz;
+}
+
+__global__ void __launch_bounds__(256)
+hcz3d_level1_kernel(const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g, ModelParams mp, int x0, long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const int x = x0 + (int)(t / g.plane);
+    const int r = (int)(t % g.plane);
+    const Nbr n = make_nbr(g, x, r / g.nz, r % g.nz);
+    const double *__restrict__ phi = F.p[0];
+    const double phi_c = phi[n.i];
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+        if (k == L19::REST) continue;
+        const long long nb = n.at<L19>(k);
+        if (flag[nb] != CELL_BB) sum += L19::t(k) * (phi[nb] - phi_c);
+    }
+    F.p[5][n.i] = 6.0 * sum;
+    F.p[6][n.i] = hcz_psi(phi_c, mp.a, mp.b);
+}
+
+struct Grad3 { double x, y, z; };
+
+CLBM_D Grad3 hcz3d_grad(const double *__restrict__ X, const uint8_t *__restrict__ flag, const Nbr &n)
+{
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+    const double xc = X[n.i];
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+        if (k == L19::REST) continue;
+        const long long nb = n.at<L19>(k);
+        const double v = (flag[nb] == CELL_BB) ? xc : X[nb];
+        if (L19::cx(k)) gx += L19::t(k) * L19::cx(k) * v;
+        if (L19::cy(k)) gy += L19::t(k) * L19::cy(k) * v;
+        if (L19::cz(k)) gz += L19::t(k) * L19::cz(k) * v;
+    }
+    return {3.0 * gx, 3.0 * gy, 3.0 * gz};
+}
+
+struct Hcz3dNode {
+    double phi, rho, P, u[3];
+    Grad3 glap, gpsiphi;
+};
+
+CLBM_D void hcz3d_node(const ModelParams &mp, const FieldPtrs8 &F, const uint8_t *flag, const Nbr &n, Hcz3dNode &o)
+{
+    o.phi = F.p[0][n.i];
+    o.rho = hcz_rho_of_phi3(mp, o.phi);
+    o.glap = hcz3d_grad(F.p[5], flag, n);
+    o.gpsiphi = hcz3d_grad(F.p[6], flag, n);
+    const double forcex = mp.kappa * o.phi * o.glap.x;
+    double forcey = mp.kappa * o.phi * o.glap.y;
+    forcey += mp.gravity * o.rho;
+    const double d = o.rho / 3.;
+    o.u[0] = (F.p[2][n.i] + forcex / 6.) / d;
+    o.u[1] = (F.p[3][n.i] + forcey / 6.) / d;
+    o.u[2] = (F.p[4][n.i] + forcey / 6.) / d;  // sic: forcey (laplace3D.h:304)
+    o.P = F.p[1][n.i] - 0.5 * (o.u[0] * o.gpsiphi.x + o.u[1] * o.gpsiphi.y + o.u[2] * o.gpsiphi.z);
+}
+
+__global__ void __launch_bounds__(256)
+hcz3d_level2_kernel(const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g, ModelParams mp, int x0, long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const int x = x0 + (int)(t / g.plane);
+    const int r = (int)(t % g.plane);
+    const Nbr n = make_nbr(g, x, r / g.nz, r % g.nz);
+    Hcz3dNode o;
+    hcz3d_node(mp, F, flag, n, o);
+    F.p[7][n.i] = o.P - o.rho / 3.0;
+}
+
+__global__ void __launch_bounds__(256)
+hcz3d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const double *__restrict__ gin,
+                     double *__restrict__ gout, const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g,
+                     ModelParams mp, int x0, long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const int x = x0 + (int)(t / g.plane);
+    const int r = (int)(t % g.plane);
+    const Nbr n = make_nbr(g, x, r / g.nz, r % g.nz);
+    if (flag[n.i] != CELL_BULK) return;
+
+    Hcz3dNode o;
+    hcz3d_node(mp, F, flag, n, o);
+    const Grad3 E = hcz3d_grad(F.p[7], flag, n);
+
+    const double omega = mp.omega, hw = 1. - 0.5 * omega;
+    const double phi = o.phi, rho = o.rho, P = o.P, u0 = o.u[0], u1 = o.u[1], u2 = o.u[2];
+    const double forcex = mp.kappa * phi * o.glap.x;
+    double forcey = mp.kappa * phi * o.glap.y;
+    const double forcez = mp.kappa * phi * o.glap.z;
+    forcey += mp.gravity * rho;
+    const double usqr = 1.5 * (u0 * u0 + u1 * u1 + u2 * u2);
+    const double inv_phi = 1.0 / phi, inv_rho = 1.0 / rho;
+
+    unsigned wall = 0;
+#pragma unroll
+    for (int k = 0; k < 19; ++k)
+        if (k != 9 && flag[n.at<L19>(k)] == CELL_BB) wall |= 1u << k;
+
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+        const double fk = fin[(size_t)k * g.ncs + n.i];
+        const double gk = gin[(size_t)k * g.ncs + n.i];
+        double pf, pg;
+        if (k == 9) {
+            const double eqf0 = phi * L19::t(9) * (1. - usqr);
+            const double eqg0 = L19::t(9) * (P - (rho / 3.0) * usqr);
+            const double fg0 = hw * -1 * (u0 * forcex + u1 * forcey + u2 * forcez) * eqf0 * inv_phi +
+                               hw * -1 * (u0 * -1 * E.x + u1 * -1 * E.y + u2 * -1 * E.z) * (eqf0 * inv_phi - L19::t(9));
+            const double ff0 = hw * -3. * eqf0 * (u0 * -1 * o.gpsiphi.x + u1 * -1 * o.gpsiphi.y + u2 * -1 * o.gpsiphi.z) * inv_rho;
+            pf = (1 - omega) * fk + omega * eqf0 + ff0;
+            pg = (1 - omega) * gk + omega * eqg0 + fg0;
+        } else {
+            // for k >= 10 the reference derives the equilibrium from the k-10 one (eq - 6 x t ck_u, :574,577);
+            // algebraically that is the same polynomial evaluated at c_k
+            const double ck_u = L19::cx(k) * u0 + L19::cy(k) * u1 + L19::cz(k) * u2;
+            const double poly = 3 * ck_u + 4.5 * ck_u * ck_u - usqr;
+            const double eqf = phi * L19::t(k) * (1 + poly);
+            const double eqg = L19::t(k) * (P + (rho / 3.0) * poly);
+            const double ex = L19::cx(k) - u0, ey = L19::cy(k) - u1, ez = L19::cz(k) - u2;
+            const double fg = hw * ((ex * forcex + ey * forcey + ez * forcez) * eqf * inv_phi) +
+                              hw * ((ex * -1 * E.x) + (ey * -1 * E.y) + (ez * -1 * E.z)) * (eqf * inv_phi - L19::t(k));
+            const double ff = hw * ((ex * -1 * o.gpsiphi.x) + (ey * -1 * o.gpsiphi.y) + (ez * -1 * o.gpsiphi.z)) * 3. * eqf * inv_rho;
+            pf = (1. - omega) * fk + omega * eqf + ff;
+            pg = (1. - omega) * gk + omega * eqg + fg;
+        }
+        if (k == 9) {
+            fout[(size_t)9 * g.ncs + n.i] = pf;
+            gout[(size_t)9 * g.ncs + n.i] = pg;
+        } else if (wall & (1u << k)) {
+            fout[(size_t)L19::opp(k) * g.ncs + n.i] = pf;
+            gout[(size_t)L19::opp(k) * g.ncs + n.i] = pg;
+        } else {
+            const long long nb = n.at<L19>(k);
+            fout[(size_t)k * g.ncs + nb] = pf;
+            gout[(size_t)k * g.ncs + nb] = pg;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hcz3d_fields_kernel(const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g, ModelParams mp, double *s0, double *s1,
+                    double *s2, double *ux, double *uy, double *uz, long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const int x = (int)(t / g.plane);
+    const int r = (int)(t % g.plane);
+    const Nbr n = make_nbr(g, x, r / g.nz, r % g.nz);
+    Hcz3dNode o;
+    hcz3d_node(mp, F, flag, n, o);
+    const bool bulk = flag[n.i] == CELL_BULK;
+    if (s0) s0[t] = o.phi;
+    if (s1) s1[t] = bulk ? o.P : 0.0;
+    if (s2) s2[t] = o.rho;
+    if (ux) ux[t] = bulk ? o.u[0] : 0.0;
+    if (uy) uy[t] = bulk ? o.u[1] : 0.0;
+    if (uz) uz[t] = bulk ? o.u[2] : 0.0;
+}
+
+// ---- host side ---------------------------------------------------------------------------
+static FieldPtrs8 fld8(clbm_ctx *c)
+{
+    FieldPtrs8 F;
+    for (int i = 0; i < 8; ++i) F.p[i] = c->fld[i];
+    return F;
+}
+
+int hcz3d_moments(clbm_ctx *c)
+{
+    const long long n = (long long)c->geo.nx * c->geo.plane;
+    LaunchScope ls(c, "hcz3d_moments");
+    hcz3d_moments_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[1][c->parity], fld8(c), c->geo, 0, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+int hcz3d_level1(clbm_ctx *c)
+{
+    const int x0 = c->multi ? -2 : 0, x1 = c->multi ? c->geo.nx + 2 : c->geo.nx;
+    const long long n = (long long)(x1 - x0) * c->geo.plane;
+    LaunchScope ls(c, "hcz3d_level1");
+    hcz3d_level1_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->flag, fld8(c), c->geo, c->mp, x0, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+int hcz3d_level2(clbm_ctx *c)
+{
+    const int x0 = c->multi ? -1 : 0, x1 = c->multi ? c->geo.nx + 1 : c->geo.nx;
+    const long long n = (long long)(x1 - x0) * c->geo.plane;
+    LaunchScope ls(c, "hcz3d_level2");
+    hcz3d_level2_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->flag, fld8(c), c->geo, c->mp, x0, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+int hcz3d_collide(clbm_ctx *c)
+{
+    const long long n = (long long)c->geo.nx * c->geo.plane;
+    LaunchScope ls(c, "hcz3d_collide_stream");
+    hcz3d_collide_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
+                                                                c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
+                                                                fld8(c), c->geo, c->mp, 0, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hcz3d_step(clbm_ctx *c)
+{
+    int rc;
+    if ((rc = hcz3d_moments(c))) return rc;
+    if ((rc = hcz3d_level1(c))) return rc;
+    if ((rc = hcz3d_level2(c))) return rc;
+    if ((rc = hcz3d_collide(c))) return rc;
+    c->parity = 1 - c->parity;
+    return 0;
+}
+
+int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz)
+{
+    int rc;
+    if (!c->multi) {
+        if ((rc = hcz3d_moments(c))) return rc;
+    }
+    if ((rc = hcz3d_level1(c))) return rc;
+    const long long n = (long long)c->geo.nx * c->geo.plane;
+    LaunchScope ls(c, "hcz3d_fields");
+    hcz3d_fields_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->flag, fld8(c), c->geo, c->mp, s0, s1, s2, ux, uy, uz, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace clbm

@@ -1,0 +1,152 @@
+// sc_kernels.cu -- Shan-Chen (Yuan-CS) time step, staged form:
+//   sc_psi_kernel     : rho = sum_k f_k, psi(rho) per node            (level 0/1 of SURVEY.md A.7)
+//   sc_collide_kernel : force from the psi stencil, BGK collision, push streaming with
+//                       half-way bounce-back (SC/apps/laplace2D.h:285-306, :260-270)
+// The fused plane-marching form lives in sc_fused.cu; both share sc_cell.cuh.
+#include "sc_cell.cuh"
+
+namespace clbm {
+
+template <class L>
+__global__ void __launch_bounds__(256)
+sc_psi_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, double *__restrict__ psi,
+              Geom g, ModelParams mp, int x0, long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const long long i = (long long)(x0 + g.G) * g.plane + t;
+    double f[L::Q];
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + i];
+    const double rho = Mom<L>::sum(f);
+    const ScEos eos{mp.R, mp.TT, mp.a};
+    psi[i] = (flag[i] == CELL_BB) ? 0.0 : eos.psi(rho);
+}
+
+template <class L>
+__global__ void __launch_bounds__(256)
+sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const uint8_t *__restrict__ flag,
+                  const double *__restrict__ psi, Geom g, ModelParams mp, int x0, long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const int x = x0 + (int)(t / g.plane);
+    const int r = (int)(t % g.plane);
+    const int y = r / g.nz, z = r % g.nz;
+    const Nbr n = make_nbr(g, x, y, z);
+    if (flag[n.i] != CELL_BULK) return;
+
+    double f[L::Q], out[L::Q];
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + n.i];
+
+    ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) {
+        if (k == L::REST) continue;  // c = 0: contributes nothing, and a bulk node is never its own wall
+        const long long nb = n.at<L>(k);
+        const bool w = flag[nb] == CELL_BB;
+        sc_force_add<L>(s, k, w, w ? 0.0 : psi[nb]);
+    }
+    sc_collide<L>(mp, f, s, out);
+
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) {
+        if (k == L::REST) { fout[(size_t)k * g.ncs + n.i] = out[k]; continue; }
+        if (s.wall & (1u << k)) fout[(size_t)L::opp(k) * g.ncs + n.i] = out[k];   // half-way bounce-back
+        else fout[(size_t)k * g.ncs + n.at<L>(k)] = out[k];
+    }
+}
+
+template <class L>
+__global__ void __launch_bounds__(256)
+sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, const double *__restrict__ psi,
+                 Geom g, ModelParams mp, double *s0, double *s1, double *ux, double *uy, double *uz, long long ncell)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell) return;
+    const int x = (int)(t / g.plane);
+    const int r = (int)(t % g.plane);
+    const int y = r / g.nz, z = r % g.nz;
+    const Nbr n = make_nbr(g, x, y, z);
+    double f[L::Q];
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + n.i];
+    double rho = Mom<L>::sum(f), pr = 0.0, u[3] = {0., 0., 0.};
+    if (flag[n.i] == CELL_BULK) {
+        ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
+#pragma unroll
+        for (int k = 0; k < L::Q; ++k) {
+            if (k == L::REST) continue;
+            const long long nb = n.at<L>(k);
+            const bool w = flag[nb] == CELL_BB;
+            sc_force_add<L>(s, k, w, w ? 0.0 : psi[nb]);
+        }
+        sc_outputs<L>(mp, f, s, rho, pr, u);
+    }
+    if (s0) s0[t] = rho;
+    if (s1) s1[t] = pr;
+    if (ux) ux[t] = u[0];
+    if (uy) uy[t] = u[1];
+    if (uz) uz[t] = u[2];
+}
+
+// ---- host side ---------------------------------------------------------------------------
+template <class L> static int sc_psi_range(clbm_ctx *c, int x0, int x1)
+{
+    const long long n = (long long)(x1 - x0) * c->geo.plane;
+    if (n <= 0) return 0;
+    LaunchScope ls(c, "sc_psi");
+    sc_psi_kernel<L><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, x0, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+template <class L> static int sc_collide_range(clbm_ctx *c, int x0, int x1)
+{
+    const long long n = (long long)(x1 - x0) * c->geo.plane;
+    if (n <= 0) return 0;
+    LaunchScope ls(c, "sc_collide_stream");
+    sc_collide_kernel<L><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
+                                                                 c->fld[0], c->geo, c->mp, x0, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sc_fused_step(clbm_ctx *c);  // sc_fused.cu
+
+int sc_psi_all(clbm_ctx *c)
+{
+    return c->Q == 9 ? sc_psi_range<D2Q9>(c, 0, c->geo.nx) : sc_psi_range<D3Q19>(c, 0, c->geo.nx);
+}
+int sc_collide_all(clbm_ctx *c)
+{
+    return c->Q == 9 ? sc_collide_range<D2Q9>(c, 0, c->geo.nx) : sc_collide_range<D3Q19>(c, 0, c->geo.nx);
+}
+
+int sc_step(clbm_ctx *c)
+{
+    if (c->prm.fused && !c->multi) return sc_fused_step(c);
+    int rc = sc_psi_all(c);
+    if (rc) return rc;
+    rc = sc_collide_all(c);
+    if (rc) return rc;
+    c->parity = 1 - c->parity;
+    return 0;
+}
+
+int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz)
+{
+    // psi of the current populations (ghost planes of psi must already be valid in slab mode)
+    int rc = sc_psi_all(c);
+    if (rc) return rc;
+    const long long n = (long long)c->geo.nx * c->geo.plane;
+    LaunchScope ls(c, "sc_fields");
+    if (c->Q == 9)
+        sc_fields_kernel<D2Q9><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, n);
+    else
+        sc_fields_kernel<D3Q19><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace clbm

@@ -1,0 +1,378 @@
+// support_kernels.cu -- everything around the step kernels: device-side initial conditions
+// (iniLattice + inigeom of each case), warp-shuffle reductions for the mass / energy diagnostics,
+// and the ghost-plane pack / unpack of the x-slab decomposition.
+#include "clbm_internal.h"
+#include "moments.cuh"
+
+namespace clbm {
+
+// ============================================================================================
+// initial conditions.  One thread per storage cell INCLUDING ghost planes so that ghost flags are
+// consistent with the global geometry from the start (global x = (x + x_offset) mod nx_global).
+// ============================================================================================
+struct CaseArgs { double a[8]; int n; };
+
+template <class L>
+__global__ void __launch_bounds__(256)
+init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, uint8_t *__restrict__ flag, Geom g, ModelParams mp,
+                 int case_id, CaseArgs A)
+{
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.ncs) return;
+    const int xs = (int)(s / g.plane);
+    const int r = (int)(s % g.plane);
+    const int iY = r / g.nz, iZ = r % g.nz;
+    int iX = xs - g.G + g.x_offset;
+    iX %= g.nx_global;
+    if (iX < 0) iX += g.nx_global;
+    const int nx = g.nx_global, ny = g.ny, nz = g.nz;
+
+    double vf = 0.0, vg = 0.0;   // f_k = vf * t_k, g_k = vg * t_k
+    bool wall = false;
+    switch (case_id) {
+    case CLBM_CASE_SC_LAPLACE2D: {   // SC/apps/laplace2D.h:132-145, 397-404
+        const double cx = double(nx) / 2.0, cy = double(ny) / 2.0, Rdrop = A.a[2];
+        const double dx = double(iX) - cx, dy = double(iY) - cy;
+        vf = (dx * dx + dy * dy <= Rdrop * Rdrop) ? A.a[0] : A.a[1];
+    } break;
+    case CLBM_CASE_SC_CONTACT2D: {   // SC/apps/contactAngle2D.h:126-137, 442-455
+        const int x_c = nx / 2, y_c = 5;
+        const double dx = double(iX) - double(x_c), dy = double(iY) - double(y_c);
+        vf = (dx * dx + dy * dy <= A.a[2] * A.a[2]) ? A.a[0] : A.a[1];
+        wall = (iY == 0 || iY == ny - 1);
+    } break;
+    case CLBM_CASE_SC_DROPLET3D:
+    case CLBM_CASE_SC_DROPLET3D_PER: {   // contactAngle2D geometry extruded to 3-D
+        const bool per = case_id == CLBM_CASE_SC_DROPLET3D_PER;
+        const double yc = per ? double(ny / 2) : (A.n > 3 ? A.a[3] : 5.0);
+        const double dx = double(iX) - double(nx / 2), dy = double(iY) - yc, dz = double(iZ) - double(nz / 2);
+        vf = (dx * dx + dy * dy + dz * dz <= A.a[2] * A.a[2]) ? A.a[0] : A.a[1];
+        wall = !per && (iY == 0 || iY == ny - 1);
+    } break;
+    case CLBM_CASE_HCZ_RT2D: {   // PF/apps/rayleighTaylor2D.h:155-193, 802-820
+        const double x = double(iX);
+        const double itf = (double(ny) / 2.0) + double(nx) * 0.1 * cos(2.0 * 3.14159265358979323846 * x / double(nx - 1));
+        const double w = 1.25, y = double(iY);
+        const double phi = 0.5 * (mp.phi_l + mp.phi_g) + 0.5 * (mp.phi_l - mp.phi_g) * tanh((y - itf) / (2.0 * w));
+        const double rho = mp.rho_g + ((phi - mp.phi_g) / (mp.phi_l - mp.phi_g)) * (mp.rho_l - mp.rho_g);
+        const double rt = mp.b * rho / 4.0, d = 1.0 - rt;
+        vf = phi;
+        vg = (rho / 3.0) * (1.0 + rt + rt * rt - rt * rt * rt) / (d * d * d) - mp.a * rho * rho;
+        wall = (iY == 0 || iY == ny - 1);
+    } break;
+    case CLBM_CASE_HCZ_LAPLACE3D: {   // PF/apps/laplace3D.h:170-213
+        const double xc = double(nx) / 2.0, yc = double(ny) / 2.0, zc = double(nz) / 2.0, R = 0.25 * nx;
+        const double dx = double(iX) - xc, dy = double(iY) - yc, dz = double(iZ) - zc;
+        const double delta = sqrt(dx * dx + dy * dy + dz * dz) - R;
+        const double rl = mp.b * mp.phi_l / 4.0, dl = 1.0 - rl;
+        const double pth_l = (mp.phi_l / 3.0) * (1 + rl + rl * rl - rl * rl * rl) / (dl * dl * dl) - mp.a * mp.phi_l * mp.phi_l;
+        const double rg = mp.b * mp.phi_g / 4.0, dg = 1.0 - rg;
+        const double pth_g = (mp.phi_g / 3.0) * (1 + rg + rg * rg - rg * rg * rg) / (dg * dg * dg) - mp.a * mp.phi_g * mp.phi_g;
+        const double w = 0.5 * (1.0 - tanh(delta / 1.0));
+        vf = mp.phi_g + w * (mp.phi_l - mp.phi_g);
+        vg = pth_g + w * (pth_l - pth_g);
+    } break;
+    default: break;
+    }
+    flag[s] = wall ? CELL_BB : CELL_BULK;
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) {
+        f[(size_t)k * g.ncs + s] = wall ? 0.0 : vf * L::t(k);
+        if (gpop) gpop[(size_t)k * g.ncs + s] = wall ? 0.0 : vg * L::t(k);
+    }
+}
+
+int model_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)
+{
+    const int m = c->prm.model;
+    const bool sc2 = m == CLBM_MODEL_SC_D2Q9, sc3 = m == CLBM_MODEL_SC_D3Q19;
+    const bool ok = (sc2 && (case_id == CLBM_CASE_SC_LAPLACE2D || case_id == CLBM_CASE_SC_CONTACT2D)) ||
+                    (sc3 && (case_id == CLBM_CASE_SC_DROPLET3D || case_id == CLBM_CASE_SC_DROPLET3D_PER)) ||
+                    (m == CLBM_MODEL_HCZ_D2Q9 && case_id == CLBM_CASE_HCZ_RT2D) ||
+                    (m == CLBM_MODEL_HCZ_D3Q19 && case_id == CLBM_CASE_HCZ_LAPLACE3D);
+    if (!ok) { set_error("case %d does not belong to model %d", case_id, m); return CLBM_EINVAL; }
+    if ((sc2 || sc3) && nargs < 3) { set_error("Shan-Chen droplet cases need {rhol, rhog, R}"); return CLBM_EINVAL; }
+    CaseArgs A;
+    A.n = nargs < 8 ? nargs : 8;
+    for (int i = 0; i < 8; ++i) A.a[i] = (args && i < A.n) ? args[i] : 0.0;
+    const Geom &g = c->geo;
+    c->parity = 0;
+    for (int s = 0; s < c->sets; ++s) CLBM_CUDA(cudaMemsetAsync(c->pop[s][1], 0, (size_t)c->Q * g.ncs * sizeof(double), c->stream));
+    LaunchScope ls(c, "init_case");
+    if (c->Q == 9)
+        init_case_kernel<D2Q9><<<grid_for(g.ncs, 256), 256, 0, c->stream>>>(c->pop[0][0], c->pop[1][0], c->flag, g, c->mp, case_id, A);
+    else
+        init_case_kernel<D3Q19><<<grid_for(g.ncs, 256), 256, 0, c->stream>>>(c->pop[0][0], c->pop[1][0], c->flag, g, c->mp, case_id, A);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ============================================================================================
+// diagnostics: deterministic two-stage reductions (warp shuffle -> block -> one final block)
+// ============================================================================================
+CLBM_D double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+CLBM_D double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+constexpr int RED_BLOCKS = 1184;   // 8 x 148 SMs
+constexpr int RED_THREADS = 256;
+
+// partial[b] = {mass, energy, umax} of block b
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_stage1(const double *__restrict__ s0, const double *__restrict__ ux, const double *__restrict__ uy,
+              const double *__restrict__ uz, const uint8_t *__restrict__ flag, long long n, double *__restrict__ partial)
+{
+    double m = 0.0, e = 0.0, um = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint8_t fl = flag[i];
+        if (fl != CELL_BB) m += s0[i];
+        if (fl == CELL_BULK) {
+            const double a = ux[i], b = uy[i], cc = uz[i];
+            const double q = a * a + b * b + cc * cc;
+            e += q;
+            um = fmax(um, q);
+        }
+    }
+    __shared__ double sm[3][RED_THREADS / 32];
+    m = warp_sum(m); e = warp_sum(e); um = warp_max(um);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm[0][w] = m; sm[1][w] = e; sm[2][w] = um; }
+    __syncthreads();
+    if (w == 0) {
+        m = l < RED_THREADS / 32 ? sm[0][l] : 0.0;
+        e = l < RED_THREADS / 32 ? sm[1][l] : 0.0;
+        um = l < RED_THREADS / 32 ? sm[2][l] : 0.0;
+        m = warp_sum(m); e = warp_sum(e); um = warp_max(um);
+        if (l == 0) { partial[3 * blockIdx.x + 0] = m; partial[3 * blockIdx.x + 1] = e; partial[3 * blockIdx.x + 2] = um; }
+    }
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_stage2(const double *__restrict__ partial, int nb, double *__restrict__ out)
+{
+    double m = 0.0, e = 0.0, um = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        m += partial[3 * i];
+        e += partial[3 * i + 1];
+        um = fmax(um, partial[3 * i + 2]);
+    }
+    __shared__ double sm[3][RED_THREADS / 32];
+    m = warp_sum(m); e = warp_sum(e); um = warp_max(um);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sm[0][w] = m; sm[1][w] = e; sm[2][w] = um; }
+    __syncthreads();
+    if (w == 0) {
+        m = l < RED_THREADS / 32 ? sm[0][l] : 0.0;
+        e = l < RED_THREADS / 32 ? sm[1][l] : 0.0;
+        um = l < RED_THREADS / 32 ? sm[2][l] : 0.0;
+        m = warp_sum(m); e = warp_sum(e); um = warp_max(um);
+        if (l == 0) { out[0] = m; out[1] = e; out[2] = um; }
+    }
+}
+
+__global__ void compact_flag_kernel(const uint8_t *__restrict__ flag, uint8_t *__restrict__ out, long long off, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = flag[off + i];
+}
+
+int model_reduce(clbm_ctx *c, int kind, double *out)
+{
+    if (kind < CLBM_REDUCE_MASS || kind > CLBM_REDUCE_UMAX) { set_error("bad reduction kind %d", kind); return CLBM_EINVAL; }
+    const Geom &g = c->geo;
+    const long long n = (long long)g.nx * g.plane;
+    double *tmp = nullptr, *partial = nullptr;
+    CLBM_CUDA(cudaMalloc(&tmp, (size_t)4 * n * sizeof(double)));
+    if (cudaMalloc(&partial, (size_t)3 * RED_BLOCKS * sizeof(double)) != cudaSuccess) { cudaFree(tmp); set_error("out of device memory (reduce)"); return CLBM_ENOMEM; }
+    int rc = model_fields(c, tmp, nullptr, nullptr, tmp + n, tmp + 2 * n, tmp + 3 * n);
+    if (!rc) {
+        {
+            LaunchScope ls(c, "reduce_stage1");
+            reduce_stage1<<<RED_BLOCKS, RED_THREADS, 0, c->stream>>>(tmp, tmp + n, tmp + 2 * n, tmp + 3 * n, c->flag + (size_t)g.G * g.plane, n, partial);
+        }
+        {
+            LaunchScope ls(c, "reduce_stage2");
+            reduce_stage2<<<1, RED_THREADS, 0, c->stream>>>(partial, RED_BLOCKS, c->red_dev);
+        }
+        cudaError_t e = cudaMemcpyAsync(c->red_host, c->red_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "reduce", __FILE__, __LINE__);
+    }
+    cudaFree(tmp);
+    cudaFree(partial);
+    if (rc) return rc;
+    const double nglob = (double)g.nx_global * (double)g.ny * (double)g.nz;
+    if (kind == CLBM_REDUCE_MASS) *out = c->red_host[0];
+    else if (kind == CLBM_REDUCE_ENERGY) *out = 0.5 * c->red_host[1] / nglob;   // this slab's share of 0.5*sum(u.u)/nelem
+    else *out = sqrt(c->red_host[2]);
+    return 0;
+}
+
+// ============================================================================================
+// x-slab ghost exchange.  side 0 = towards the x-1 neighbour, side 1 = towards x+1.
+//   phase 0 : moment halos before the collide  (SC: psi depth 1; HCZ2D: phi depth 2;
+//             HCZ3D: phi depth 3 + P_term and the raw momentum depth 1)
+//   phase 1 : populations that crossed the slab face into a ghost plane during the push
+//   phase 2 : node mask, depth G, once after upload
+// Planes are contiguous in storage (x slowest), so pack is a handful of D2D copies.
+// ============================================================================================
+static int n_cross(const clbm_ctx *c) { return c->Q == 9 ? 3 : 5; }
+static void cross_dirs(const clbm_ctx *c, int side, int *ks)
+{
+    // directions with c_x = -1 (side 0) / +1 (side 1)
+    if (c->Q == 9) { const int m[3] = {0, 2, 3}, p[3] = {5, 7, 8}; for (int i = 0; i < 3; ++i) ks[i] = side ? p[i] : m[i]; }
+    else { const int m[5] = {0, 3, 4, 5, 6}, p[5] = {10, 13, 14, 15, 16}; for (int i = 0; i < 5; ++i) ks[i] = side ? p[i] : m[i]; }
+}
+
+struct HaloField { int fld, depth; };
+static int phase0_fields(const clbm_ctx *c, HaloField *hf)
+{
+    switch (c->prm.model) {
+    case CLBM_MODEL_SC_D2Q9:
+    case CLBM_MODEL_SC_D3Q19: hf[0] = {0, 1}; return 1;
+    case CLBM_MODEL_HCZ_D2Q9: hf[0] = {0, 2}; return 1;
+    case CLBM_MODEL_HCZ_D3Q19: hf[0] = {0, 3}; hf[1] = {1, 1}; hf[2] = {2, 1}; hf[3] = {3, 1}; hf[4] = {4, 1}; return 5;
+    }
+    return 0;
+}
+
+int halo_alloc(clbm_ctx *c)
+{
+    const Geom &g = c->geo;
+    HaloField hf[8];
+    const int nf = phase0_fields(c, hf);
+    size_t planes0 = 0;
+    for (int i = 0; i < nf; ++i) planes0 += hf[i].depth;
+    c->halo_bytes[0] = planes0 * g.plane * sizeof(double);
+    c->halo_bytes[1] = (size_t)n_cross(c) * c->sets * g.plane * sizeof(double);
+    c->halo_bytes[2] = (size_t)g.G * g.plane;
+    for (int ph = 0; ph < 3; ++ph)
+        for (int side = 0; side < 2; ++side)
+            for (int r = 0; r < 2; ++r) {
+                if (cudaMalloc(&c->halo[ph][side][r], c->halo_bytes[ph]) != cudaSuccess) { set_error("out of device memory (halo buffers)"); return CLBM_ENOMEM; }
+                cudaMemsetAsync(c->halo[ph][side][r], 0, c->halo_bytes[ph], c->stream);
+            }
+    return 0;
+}
+
+int halo_pack(clbm_ctx *c, int phase)
+{
+    const Geom &g = c->geo;
+    const size_t pl = (size_t)g.plane;
+    c->launches += 0;
+    if (phase == 0) {
+        HaloField hf[8];
+        const int nf = phase0_fields(c, hf);
+        for (int side = 0; side < 2; ++side) {
+            double *dst = (double *)c->halo[0][side][0];
+            for (int i = 0; i < nf; ++i) {
+                const int d = hf[i].depth;
+                const int x0 = side ? g.nx - d : 0;
+                CLBM_CUDA(cudaMemcpyAsync(dst, c->fld[hf[i].fld] + (size_t)(x0 + g.G) * pl, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                dst += d * pl;
+            }
+        }
+        return 0;
+    }
+    if (phase == 1) {
+        int ks[5];
+        for (int side = 0; side < 2; ++side) {
+            cross_dirs(c, side, ks);
+            const int xg = side ? g.nx : -1;   // ghost plane the push wrote into
+            double *dst = (double *)c->halo[1][side][0];
+            for (int s = 0; s < c->sets; ++s)
+                for (int i = 0; i < n_cross(c); ++i) {
+                    CLBM_CUDA(cudaMemcpyAsync(dst, c->pop[s][c->parity] + (size_t)ks[i] * g.ncs + (size_t)(xg + g.G) * pl, pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                    dst += pl;
+                }
+        }
+        return 0;
+    }
+    if (phase == 2) {
+        for (int side = 0; side < 2; ++side) {
+            const int x0 = side ? g.nx - g.G : 0;
+            CLBM_CUDA(cudaMemcpyAsync(c->halo[2][side][0], c->flag + (size_t)(x0 + g.G) * pl, (size_t)g.G * pl, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        return 0;
+    }
+    set_error("bad halo phase %d", phase);
+    return CLBM_EINVAL;
+}
+
+// crossing populations land in the boundary plane only where the sender really wrote them:
+// the upstream node (in the neighbour's slab = our ghost plane) is fluid and the target is not a wall;
+// elsewhere the slot was filled locally by the target's own half-way bounce-back.
+template <class L>
+__global__ void __launch_bounds__(256)
+unpack_cross_kernel(double *__restrict__ pop, const double *__restrict__ recv, const uint8_t *__restrict__ flag, Geom g,
+                    int side, int slot, int k)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.plane) return;
+    const int y = (int)(r / g.nz), z = (int)(r % g.nz);
+    const int xb = side ? g.nx - 1 : 0;   // boundary plane that receives
+    const long long j = g.idx(xb, y, z);
+    if (flag[j] == CELL_BB) return;
+    const long long src = g.idx(xb - L::cx(k), g.wy(y - L::cy(k)), g.wz(z - L::cz(k)));
+    if (flag[src] == CELL_BB) return;
+    pop[(size_t)k * g.ncs + j] = recv[(size_t)slot * g.plane + r];
+}
+
+int halo_unpack(clbm_ctx *c, int phase)
+{
+    const Geom &g = c->geo;
+    const size_t pl = (size_t)g.plane;
+    if (phase == 0) {
+        HaloField hf[8];
+        const int nf = phase0_fields(c, hf);
+        for (int side = 0; side < 2; ++side) {
+            const double *src = (const double *)c->halo[0][side][1];
+            for (int i = 0; i < nf; ++i) {
+                const int d = hf[i].depth;
+                const int x0 = side ? g.nx : -d;   // ghost planes on that side
+                CLBM_CUDA(cudaMemcpyAsync(c->fld[hf[i].fld] + (size_t)(x0 + g.G) * pl, src, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                src += d * pl;
+            }
+        }
+        return 0;
+    }
+    if (phase == 1) {
+        int ks[5];
+        for (int side = 0; side < 2; ++side) {
+            // data received from the side-0 neighbour moves in +x (c_x = +1) into plane 0, and vice versa
+            cross_dirs(c, 1 - side, ks);
+            const double *src = (const double *)c->halo[1][side][1];
+            for (int s = 0; s < c->sets; ++s)
+                for (int i = 0; i < n_cross(c); ++i) {
+                    LaunchScope ls(c, "unpack_cross");
+                    const int slot = s * n_cross(c) + i;
+                    if (c->Q == 9)
+                        unpack_cross_kernel<D2Q9><<<grid_for(g.plane, 256), 256, 0, c->stream>>>(c->pop[s][c->parity], src, c->flag, g, side, slot, ks[i]);
+                    else
+                        unpack_cross_kernel<D3Q19><<<grid_for(g.plane, 256), 256, 0, c->stream>>>(c->pop[s][c->parity], src, c->flag, g, side, slot, ks[i]);
+                    CLBM_CUDA(cudaGetLastError());
+                }
+        }
+        return 0;
+    }
+    if (phase == 2) {
+        for (int side = 0; side < 2; ++side) {
+            const int x0 = side ? g.nx : -g.G;
+            CLBM_CUDA(cudaMemcpyAsync(c->flag + (size_t)(x0 + g.G) * pl, c->halo[2][side][1], (size_t)g.G * pl, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        return 0;
+    }
+    set_error("bad halo phase %d", phase);
+    return CLBM_EINVAL;
+}
+
+}  // namespace clbm

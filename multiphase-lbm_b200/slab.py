@@ -1,0 +1,174 @@
+"""x-slab decomposition of one lattice over several GPUs.
+
+x is the slowest index of the reference layout, so the slab [x0, x1) of every population array is a
+contiguous range; x is periodic in every multiphase case, so the slabs form a ring (rank R-1 <-> rank 0).
+One time step of a slab is
+
+    stage 0 : moments of the local planes, pack the moment halo          (clbm_step_stage(0))
+    exchange phase 0 with both neighbours
+    stage 1 : unpack, collide + push-stream, pack the crossing populations (clbm_step_stage(1))
+    exchange phase 1
+    stage 2 : unpack the crossing populations into the boundary planes     (clbm_step_stage(2))
+
+The exchange itself is plumbing: `LocalRing` moves the buffers between several contexts living in one
+process (single-GPU emulation of R ranks, used by the GPU tests), `DistRing` uses torch.distributed
+point-to-point operations (NCCL on GPUs; gloo in the CPU tests with host buffers).
+"""
+import numpy as np
+
+
+def slab_bounds(nx_global, nranks):
+    """[x0, x1) of every rank; the remainder goes to the first ranks."""
+    base, rem = divmod(nx_global, nranks)
+    out, x = [], 0
+    for r in range(nranks):
+        w = base + (1 if r < rem else 0)
+        out.append((x, x + w))
+        x += w
+    return out
+
+
+def slab_params(params, rank, nranks):
+    """clbm_params of rank's slab of a global lattice described by `params` (nx == nx_global)."""
+    x0, x1 = slab_bounds(params.nx_global, nranks)[rank]
+    return params.copy(nx=x1 - x0, x_offset=x0)
+
+
+def slice_host_state(params, lattice, flag, rank, nranks):
+    """cut the reference-layout host arrays of the global lattice down to one slab (same layout)."""
+    x0, x1 = slab_bounds(params.nx_global, nranks)[rank]
+    plane = params.ny * params.nz
+    ne_g = params.nx_global * plane
+    Q, sets = params.Q, params.sets
+    lat = lattice.reshape(sets, 2, Q, ne_g)[:, :, :, x0 * plane:x1 * plane]
+    return np.ascontiguousarray(lat).reshape(-1), np.ascontiguousarray(flag[x0 * plane:x1 * plane])
+
+
+class CudaBuffer:
+    """view of a raw device pointer for torch (CUDA array interface)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def as_torch(ptr, nbytes, device):
+    import torch
+    return torch.as_tensor(CudaBuffer(ptr, nbytes), device=device)
+
+
+class LocalRing:
+    """R slab contexts in one process; the exchange is a device-to-device copy per neighbour pair."""
+
+    def __init__(self, lattices):
+        import torch
+        self.lats = lattices
+        self.torch = torch
+        self.R = len(lattices)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self._views = {}
+
+    def _view(self, r, phase, side, recv):
+        key = (r, phase, side, recv)
+        if key not in self._views:
+            ptr, nb = self.lats[r].halo_buffer(phase, side, recv)
+            self._views[key] = as_torch(ptr, nb, self.dev)
+        return self._views[key]
+
+    def exchange(self, phase):
+        for lat in self.lats:
+            lat.sync()
+        for r in range(self.R):
+            left, right = (r - 1) % self.R, (r + 1) % self.R
+            # my side-0 send buffer travels to the left neighbour's side-1 recv buffer, and vice versa
+            self._view(left, phase, 1, True).copy_(self._view(r, phase, 0, False))
+            self._view(right, phase, 0, True).copy_(self._view(r, phase, 1, False))
+        self.torch.cuda.synchronize()
+
+    def exchange_flags(self):
+        for lat in self.lats:
+            lat.halo_pack(2)
+        self.exchange(2)
+        for lat in self.lats:
+            lat.halo_unpack(2)
+            lat.sync()
+
+    def step(self, n=1):
+        for _ in range(n):
+            for lat in self.lats:
+                lat.step_stage(0)
+            self.exchange(0)
+            for lat in self.lats:
+                lat.step_stage(1)
+            self.exchange(1)
+            for lat in self.lats:
+                lat.step_stage(2)
+
+    def refresh_moment_halo(self):
+        """make the moment ghosts valid for the current populations (needed before fields())"""
+        for lat in self.lats:
+            lat.step_stage(0)
+        self.exchange(0)
+        for lat in self.lats:
+            lat.halo_unpack(0)
+            lat.sync()
+
+
+def ring_exchange(dist, rank, nranks, send0, send1, recv0, recv1):
+    """One exchange phase with both ring neighbours through torch.distributed P2P ops.
+    send0 goes to rank-1 (arriving in its recv1), send1 to rank+1 (arriving in its recv0)."""
+    if nranks == 1:
+        recv1.copy_(send0)
+        recv0.copy_(send1)
+        return
+    left, right = (rank - 1) % nranks, (rank + 1) % nranks
+    ops = [dist.P2POp(dist.isend, send0, left), dist.P2POp(dist.isend, send1, right),
+           dist.P2POp(dist.irecv, recv1, right), dist.P2POp(dist.irecv, recv0, left)]
+    if nranks == 2:
+        # left == right: tag-less P2P matches in posting order; order the ops identically on both ranks
+        ops = [dist.P2POp(dist.isend, send0, left), dist.P2POp(dist.irecv, recv1, right),
+               dist.P2POp(dist.isend, send1, right), dist.P2POp(dist.irecv, recv0, left)]
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+class DistRing:
+    """one slab per process (rank), exchange over torch.distributed (NCCL)"""
+
+    def __init__(self, lattice, rank, nranks, device):
+        import torch
+        import torch.distributed as dist
+        self.lat, self.rank, self.R, self.dist, self.torch = lattice, rank, nranks, dist, torch
+        self.dev = device
+        self._v = {}
+        for phase in range(3):
+            for side in range(2):
+                for recv in (False, True):
+                    ptr, nb = lattice.halo_buffer(phase, side, recv)
+                    self._v[(phase, side, recv)] = as_torch(ptr, nb, device)
+
+    def exchange(self, phase):
+        self.lat.sync()
+        v = self._v
+        ring_exchange(self.dist, self.rank, self.R, v[(phase, 0, False)], v[(phase, 1, False)],
+                      v[(phase, 0, True)], v[(phase, 1, True)])
+        self.torch.cuda.current_stream().synchronize()
+
+    def exchange_flags(self):
+        self.lat.halo_pack(2)
+        self.exchange(2)
+        self.lat.halo_unpack(2)
+        self.lat.sync()
+
+    def step(self, n=1):
+        for _ in range(n):
+            self.lat.step_stage(0)
+            self.exchange(0)
+            self.lat.step_stage(1)
+            self.exchange(1)
+            self.lat.step_stage(2)
+
+    def refresh_moment_halo(self):
+        self.lat.step_stage(0)
+        self.exchange(0)
+        self.lat.halo_unpack(0)
+        self.lat.sync()

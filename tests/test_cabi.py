@@ -1,0 +1,64 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol include/clbm.h declares,
+rejects bad arguments, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import _cases
+
+pkg = _cases.pkg
+P = pkg.params
+ROOT = _cases.ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "clbm.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(clbm_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_header_symbols_all_exported():
+    lib = pkg.clbm.load_library()
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "libclbm.so does not export %s" % s
+    assert sorted(pkg.clbm.EXPORTS) == syms
+    assert lib.clbm_abi_version() == P.ABI_VERSION
+
+
+def test_params_struct_matches_header_layout():
+    # 10 int32 + 12 doubles, naturally aligned: must equal sizeof(clbm_params) on the C side
+    assert ctypes.sizeof(P.Params) == 10 * 4 + 12 * 8
+    assert P.Params.omega.offset == 40
+
+
+def test_bad_arguments_are_rejected_without_a_device_call():
+    lib = pkg.clbm.load_library()
+    h = ctypes.c_void_p()
+    bad = P.make_params(P.MODEL_SC_D2Q9, 8, 8)
+    bad.abi_version = 99
+    assert lib.clbm_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    assert b"ABI" in lib.clbm_last_error()
+    bad = P.make_params(P.MODEL_SC_D2Q9, 8, 8, nz=4)
+    assert lib.clbm_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    bad = P.make_params(7, 8, 8)
+    assert lib.clbm_create(ctypes.byref(bad), ctypes.byref(h)) == -1
+    assert lib.clbm_step(None, 1) == -1
+    assert lib.clbm_destroy(None) == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.clbm.ClbmError) as e:
+        pkg.clbm.Lattice(P.sc_params(P.MODEL_SC_D2Q9, 8, 8))
+    assert "no CUDA device" in str(e.value)
+
+
+def test_missing_extension_fails_loudly(tmp_path):
+    with pytest.raises(pkg.clbm.ClbmError):
+        pkg.clbm.load_library(str(tmp_path / "libclbm.so"))

@@ -1,0 +1,250 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI
+(ctypes -> libclbm.so); the CPU oracle is only the checker.
+
+Bar (BASELINE.json north_star): fp64 macroscopic fields within a relative L-inf of 1e-10
+(global-max normalisation) after up to 1000 steps; integer masks bit-exact.
+"""
+import numpy as np
+import pytest
+
+import _cases
+from _oracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+
+pkg = _cases.pkg
+P = pkg.params
+TOL = 1e-10
+
+
+def run_pair(prm, case, args, steps, fused=1):
+    ora = OracleSim(prm).init_case(case, args)
+    prm_gpu = prm.copy(fused=fused)
+    with pkg.clbm.Lattice(prm_gpu) as lat:
+        lat.upload(ora.lattice, ora.flag, 0)
+        lat.step(steps)
+        got = lat.fields()
+        pops = lat.in_pops()
+        flags = lat.flags()
+    ora.step(steps)
+    return ora, got, pops, flags
+
+
+def check_fields(ref, got, keys, tol=TOL):
+    for k in keys:
+        if np.max(np.abs(ref[k])) == 0.0:
+            assert np.max(np.abs(got[k])) < 1e-300, k
+            continue
+        err = _cases.rel_linf(got[k], ref[k])
+        assert err < tol, "field %s: rel Linf %.3e" % (k, err)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures produced by the untouched reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("name", _cases.golden_names())
+def test_golden_fixture(name, fused):
+    z, _ = _cases.load_golden(name)
+    prm, case, args, steps, fmap = _cases.golden_setup(name)
+    ora, got, pops, flags = run_pair(prm, case, args, steps, fused)
+    np.testing.assert_array_equal(flags, z["flag"])
+    for gname, slot in fmap.items():
+        ref = z[gname]
+        if np.max(np.abs(ref)) == 0.0:
+            continue
+        err = _cases.rel_linf(got[slot], ref)
+        assert err < TOL, "%s %s: rel Linf %.3e" % (name, gname, err)
+    assert _cases.rel_linf(pops, z["pops"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle comparisons at the north_star horizon (1000 steps) / BASELINE configs that the oracle finishes
+# ---------------------------------------------------------------------------------------------
+def test_sc_laplace2d_256_1000_steps():
+    """config 1: Shan-Chen static droplet D2Q9 256x256 BGK, shipped parameters, 1000 steps"""
+    prm = P.sc_params(P.MODEL_SC_D2Q9, 256, 256, ulb=0.01, N=256, Re=6.0)
+    ora, got, pops, _ = run_pair(prm, P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0), 1000)
+    check_fields(ora.fields(), got, ("s0", "s1", "ux", "uy"))
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_sc_contact2d_walls_1000_steps(fused):
+    prm = P.sc_params(P.MODEL_SC_D2Q9, 128, 64, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    ora, got, pops, flags = run_pair(prm, P.CASE_SC_CONTACT2D, (0.265, 0.038, 20.0), 1000, fused)
+    np.testing.assert_array_equal(flags, ora.flag)
+    check_fields(ora.fields(), got, ("s0", "s1", "ux", "uy"))
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_sc_d3q19_sessile_droplet(fused):
+    """config 4 physics at a size the oracle finishes: walls y=0,ny-1, contact-angle force"""
+    prm = P.sc_params(P.MODEL_SC_D3Q19, 40, 24, 36, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    ora, got, pops, flags = run_pair(prm, P.CASE_SC_DROPLET3D, (0.265, 0.038, 9.0, 5.0), 400, fused)
+    np.testing.assert_array_equal(flags, ora.flag)
+    check_fields(ora.fields(), got, ("s0", "s1", "ux", "uy", "uz"))
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_sc_d3q19_periodic_droplet_gravity(fused):
+    prm = P.sc_params(P.MODEL_SC_D3Q19, 24, 28, 32, omega=1.3, gravity=-2e-5, sc_force=P.SC_FORCE_LAPLACE)
+    ora, got, pops, _ = run_pair(prm, P.CASE_SC_DROPLET3D_PER, (0.265, 0.038, 7.0), 300, fused)
+    check_fields(ora.fields(), got, ("s0", "s1", "ux", "uy", "uz"))
+
+
+def test_hcz_rt2d_1000_steps():
+    """config 2 physics (HCZ Rayleigh-Taylor, shipped parameters) at N=64: 64x258, 1000 steps"""
+    prm = P.hcz_params(P.MODEL_HCZ_D2Q9, 64, 258, N=64)
+    ora, got, pops, flags = run_pair(prm, P.CASE_HCZ_RT2D, (), 1000)
+    np.testing.assert_array_equal(flags, ora.flag)
+    check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy"))
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+
+
+def test_hcz_rt2d_config2_full_size_100_steps():
+    """config 2 at its full size 256x1026 (the oracle needs ~seconds for 100 steps)"""
+    prm = P.hcz_params(P.MODEL_HCZ_D2Q9, 256, 1026, N=256)
+    ora, got, pops, _ = run_pair(prm, P.CASE_HCZ_RT2D, (), 100)
+    check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy"))
+
+
+def test_hcz_laplace3d_droplet():
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 24, 24, 24, ulb=0.01, N=24, Re=6.0, kappa=5e-4, gravity=0.0)
+    ora, got, pops, _ = run_pair(prm, P.CASE_HCZ_LAPLACE3D, (), 300)
+    check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy", "uz"))
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+
+
+def test_hcz_laplace3d_with_gravity_and_walls():
+    """exercise the centre-value wall fallback of the 3-D gradients (laplace3D.h:450-455) with a wall slab"""
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 16, 20, 12, omega=1.2, kappa=5e-4, gravity=-1e-5)
+    ora = OracleSim(prm).init_case(P.CASE_HCZ_LAPLACE3D, ())
+    # put bounce-back planes at y=0 and y=ny-1 and zero their populations like inigeom does
+    ne = prm.nelem
+    y = (np.arange(ne) // prm.nz) % prm.ny
+    wall = (y == 0) | (y == prm.ny - 1)
+    ora.flag[wall] = 0
+    lat4 = ora.lattice.reshape(2, 2, 19, ne)
+    lat4[:, :, :, wall] = 0.0
+    with pkg.clbm.Lattice(prm) as lat:
+        lat.upload(ora.lattice, ora.flag, 0)
+        lat.step(60)
+        got = lat.fields()
+    ora.step(60)
+    check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy", "uz"))
+
+
+# ---------------------------------------------------------------------------------------------
+# D3Q19 Shan-Chen has no reference functor ("parity unpinned"): pin it through the z-uniform
+# projection onto the D2Q9 reference model: 1/18+2/36 = 1/9, 1/3+2/18 = 4/9, ...
+# ---------------------------------------------------------------------------------------------
+def test_sc_d3q19_z_uniform_matches_d2q9_reference_model():
+    nx, ny, nz, steps = 48, 40, 4, 300
+    p2 = P.sc_params(P.MODEL_SC_D2Q9, nx, ny, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    p3 = P.sc_params(P.MODEL_SC_D3Q19, nx, ny, nz, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    o2 = OracleSim(p2).init_case(P.CASE_SC_CONTACT2D, (0.265, 0.038, 9.0))
+    rho2d = o2.fields()["s0"].reshape(nx, ny)
+    # z-uniform 3-D initial state with the same density field
+    T19 = np.array([1 / 18.] * 3 + [1 / 36.] * 6 + [1 / 3.] + [1 / 18.] * 3 + [1 / 36.] * 6)
+    rho3d = np.repeat(rho2d[:, :, None], nz, axis=2).reshape(-1)
+    lat3 = np.zeros(p3.lattice_size)
+    lat3[:19 * p3.nelem] = (T19[:, None] * rho3d[None, :]).reshape(-1)
+    flag3 = np.repeat(o2.flag.reshape(nx, ny)[:, :, None], nz, axis=2).reshape(-1).copy()
+    with pkg.clbm.Lattice(p3) as lat:
+        lat.upload(lat3, flag3, 0)
+        lat.step(steps)
+        got = lat.fields()
+    o2.step(steps)
+    ref = o2.fields()
+    for k in ("s0", "ux", "uy"):
+        g3 = got[k].reshape(nx, ny, nz)
+        assert np.max(np.abs(g3 - g3[:, :, :1])) <= 1e-13 * max(1.0, np.max(np.abs(g3)))   # stays z-uniform
+        assert _cases.rel_linf(g3[:, :, 0].reshape(-1), ref[k]) < 1e-9, k
+    assert np.max(np.abs(got["uz"])) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------
+# boundary behaviour of the C ABI itself
+# ---------------------------------------------------------------------------------------------
+def test_device_init_matches_oracle_init():
+    cases = [
+        (P.sc_params(P.MODEL_SC_D2Q9, 40, 36), P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0)),
+        (P.sc_params(P.MODEL_SC_D2Q9, 48, 24, sc_force=P.SC_FORCE_CONTACT), P.CASE_SC_CONTACT2D, (0.265, 0.038, 8.0)),
+        (P.sc_params(P.MODEL_SC_D3Q19, 20, 16, 12, sc_force=P.SC_FORCE_CONTACT), P.CASE_SC_DROPLET3D, (0.265, 0.038, 6.0, 5.0)),
+        (P.hcz_params(P.MODEL_HCZ_D2Q9, 24, 98, N=24), P.CASE_HCZ_RT2D, ()),
+        (P.hcz_params(P.MODEL_HCZ_D3Q19, 12, 12, 12, kappa=5e-4, gravity=0.0), P.CASE_HCZ_LAPLACE3D, ()),
+    ]
+    for prm, case, args in cases:
+        ora = OracleSim(prm).init_case(case, args)
+        with pkg.clbm.Lattice(prm) as lat:
+            lat.init_case(case, args)
+            np.testing.assert_array_equal(lat.flags(), ora.flag)
+            pops = lat.in_pops()
+        assert _cases.rel_linf(pops, ora.in_pops()) < 1e-14
+
+
+def test_upload_download_roundtrip_and_parity():
+    prm = P.hcz_params(P.MODEL_HCZ_D2Q9, 12, 18, N=12)
+    rng = np.random.default_rng(7)
+    lattice = rng.random(prm.lattice_size)
+    flag = np.ones(prm.nelem, dtype=np.uint8)
+    with pkg.clbm.Lattice(prm) as lat:
+        for parity in (0, 1):
+            lat.upload(lattice, flag, parity)
+            out = np.full(prm.lattice_size, -1.0)
+            got, par = lat.download_lattice(out)
+            assert par == parity
+            v_in = lattice.reshape(2, 2, 9, prm.nelem)[:, parity]
+            np.testing.assert_array_equal(got.reshape(2, 2, 9, prm.nelem)[:, parity], v_in)
+            # the other buffer of the host array is left untouched
+            assert np.all(got.reshape(2, 2, 9, prm.nelem)[:, 1 - parity] == -1.0)
+        # parity flips once per step, like `*parity = 1 - *parity`
+        ora = OracleSim(prm).init_case(P.CASE_HCZ_RT2D, ())
+        lat.upload(ora.lattice, ora.flag, 1 if False else 0)
+        lat.step(3)
+        _, par = lat.download_lattice()
+        assert par == 1
+
+
+def test_reductions_match_host_sums():
+    prm = P.sc_params(P.MODEL_SC_D2Q9, 64, 48, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    ora = OracleSim(prm).init_case(P.CASE_SC_CONTACT2D, (0.265, 0.038, 12.0))
+    with pkg.clbm.Lattice(prm) as lat:
+        lat.upload(ora.lattice, ora.flag, 0)
+        lat.step(50)
+        mass = lat.reduce(P.REDUCE_MASS)
+        energy = lat.reduce(P.REDUCE_ENERGY)
+        umax = lat.reduce(P.REDUCE_UMAX)
+    ora.step(50)
+    f = ora.fields()
+    bulk = ora.flag == 1
+    m_ref = np.sum(f["s0"][bulk])                      # totalMass_*: non-solid nodes
+    e_ref = 0.5 * np.sum(f["ux"][bulk] ** 2 + f["uy"][bulk] ** 2) / prm.nelem   # computeEnergy_*
+    assert abs(mass - m_ref) / m_ref < 1e-12
+    assert abs(energy - e_ref) / e_ref < 1e-9
+    assert abs(umax - np.sqrt(np.max(f["ux"] ** 2 + f["uy"] ** 2))) / umax < 1e-9
+
+
+def test_mass_is_conserved_over_a_long_run():
+    """size-independent property: half-way bounce-back + periodic push streaming conserve sum(rho) exactly
+    up to round-off, at any size"""
+    prm = P.sc_params(P.MODEL_SC_D3Q19, 64, 48, 64, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    with pkg.clbm.Lattice(prm) as lat:
+        lat.init_case(P.CASE_SC_DROPLET3D, (0.265, 0.038, 14.0, 5.0))
+        m0 = lat.reduce(P.REDUCE_MASS)
+        lat.step(200)
+        m1 = lat.reduce(P.REDUCE_MASS)
+    assert abs(m1 - m0) / m0 < 1e-12
+
+
+def test_error_paths():
+    prm = P.sc_params(P.MODEL_SC_D2Q9, 16, 16)
+    with pkg.clbm.Lattice(prm) as lat:
+        with pytest.raises(pkg.clbm.ClbmError):
+            lat.init_case(P.CASE_HCZ_RT2D, ())       # wrong model
+        with pytest.raises(pkg.clbm.ClbmError):
+            lat.step_stage(0)                        # not a slab context
+        with pytest.raises(pkg.clbm.ClbmError):
+            lat.reduce(17)
