@@ -135,6 +135,16 @@ int64_t clbm_launch_count(const clbm_ctx *ctx);
  * names/ms hold up to cap entries; returns the number of kernels or <0. */
 int  clbm_profile_step(clbm_ctx *ctx, const char **names, float *ms, int cap);
 
+/* average device time of the dominant kernel (the collide/stream sweep) over the launches issued since the
+ * last call to clbm_kernel_timing_begin: CUDA event pairs recorded around each launch on the launching
+ * stream.  At most cap_launches launches are sampled (the first ones).  *avg_ms <- mean, *count <- samples. */
+int  clbm_kernel_timing_begin(clbm_ctx *ctx, int cap_launches);
+int  clbm_kernel_timing_end(clbm_ctx *ctx, float *avg_ms, int *count, const char **kernel_name);
+
+/* pinned host memory for the reference-layout arrays (so uploads/downloads run at full PCIe speed) */
+int  clbm_alloc_host(size_t bytes, void **ptr);
+int  clbm_free_host(void *ptr);
+
 /* ---- diagnostics ---------------------------------------------------------- */
 int  clbm_reduce(clbm_ctx *ctx, int kind, double *out);
 

@@ -19,7 +19,7 @@ EXPORTS = [
     "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_download_lattice",
     "clbm_download_fields", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
-    "clbm_stream",
+    "clbm_stream", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
 ]
 
 _lib = None
@@ -58,6 +58,11 @@ def load_library(path=None):
     lib.clbm_halo_pack.argtypes = [vp, ctypes.c_int]
     lib.clbm_halo_unpack.argtypes = [vp, ctypes.c_int]
     lib.clbm_step_stage.argtypes = [vp, ctypes.c_int]
+    lib.clbm_kernel_timing_begin.argtypes = [vp, ctypes.c_int]
+    lib.clbm_kernel_timing_end.argtypes = [vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int),
+                                           ctypes.POINTER(ctypes.c_char_p)]
+    lib.clbm_alloc_host.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    lib.clbm_free_host.argtypes = [vp]
     lib.clbm_stream.argtypes = [vp]
     lib.clbm_stream.restype = vp
     for name in EXPORTS:
@@ -175,6 +180,14 @@ class Lattice:
             self._check(n)
         return [(names[i].decode(), ms[i]) for i in range(n)]
 
+    def kernel_timing_begin(self, cap=256):
+        self._check(self.lib.clbm_kernel_timing_begin(self._h, int(cap)))
+
+    def kernel_timing_end(self):
+        ms, n, name = ctypes.c_float(0), ctypes.c_int(0), ctypes.c_char_p()
+        self._check(self.lib.clbm_kernel_timing_end(self._h, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(name)))
+        return ms.value, n.value, (name.value or b"").decode()
+
     def reduce(self, kind):
         out = ctypes.c_double(0)
         self._check(self.lib.clbm_reduce(self._h, int(kind), ctypes.byref(out)))
@@ -198,3 +211,31 @@ class Lattice:
 
     def stream(self):
         return self.lib.clbm_stream(self._h)
+
+
+class PinnedArray:
+    """numpy view of pinned host memory allocated through the C ABI (clbm_alloc_host)"""
+
+    def __init__(self, n, dtype=np.float64):
+        lib = load_library()
+        self._lib = lib
+        self.nbytes = int(n) * np.dtype(dtype).itemsize
+        p = ctypes.c_void_p()
+        rc = lib.clbm_alloc_host(self.nbytes, ctypes.byref(p))
+        if rc != 0:
+            raise ClbmError("clbm_alloc_host(%d bytes) failed: %s" % (self.nbytes, lib.clbm_last_error().decode()))
+        self.ptr = p
+        buf = (ctypes.c_uint8 * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def free(self):
+        if self.ptr is not None:
+            self.array = None
+            self._lib.clbm_free_host(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

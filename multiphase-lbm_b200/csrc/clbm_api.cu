@@ -24,9 +24,19 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return e == cudaErrorMemoryAllocation ? CLBM_ENOMEM : CLBM_ECUDA;
 }
 
-LaunchScope::LaunchScope(clbm_ctx *ctx, const char *n) : c(ctx), name(n), a(nullptr), b(nullptr)
+LaunchScope::LaunchScope(clbm_ctx *ctx, const char *n, bool dominant) : c(ctx), name(n), a(nullptr), b(nullptr), timed(false)
 {
     c->launches++;
+    if (dominant && c->ktiming && (int)c->kev.size() < 2 * c->ktiming_cap) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        c->kev.push_back(e0);
+        c->kev.push_back(e1);
+        cudaEventRecord(e0, c->stream);
+        c->kname = n;
+        timed = true;
+    }
     if (c->profiling) {
         cudaEventCreate(&a);
         cudaEventCreate(&b);
@@ -35,6 +45,7 @@ LaunchScope::LaunchScope(clbm_ctx *ctx, const char *n) : c(ctx), name(n), a(null
 }
 LaunchScope::~LaunchScope()
 {
+    if (timed) cudaEventRecord(c->kev.back(), c->stream);
     if (c->profiling) {
         cudaEventRecord(b, c->stream);
         cudaEventSynchronize(b);
@@ -111,17 +122,6 @@ int model_stage(clbm_ctx *c, int stage)
     return CLBM_EINVAL;
 }
 
-static int ensure_stage(clbm_ctx *c, size_t bytes)
-{
-    if (c->stage_bytes >= bytes) return 0;
-    if (c->stage) cudaFreeHost(c->stage);
-    c->stage = nullptr;
-    c->stage_bytes = 0;
-    CLBM_CUDA(cudaMallocHost(&c->stage, bytes));
-    c->stage_bytes = bytes;
-    return 0;
-}
-
 }  // namespace clbm
 
 using namespace clbm;
@@ -164,6 +164,9 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->steps_taken = 0;
     c->launches = 0;
     c->profiling = false;
+    c->ktiming = false;
+    c->ktiming_cap = 0;
+    c->kname = "";
     c->stage = nullptr;
     c->stage_bytes = 0;
     c->nfld = 0;
@@ -392,6 +395,49 @@ int clbm_profile_step(clbm_ctx *c, const char **names, float *ms, int cap)
         ++n;
     }
     return n;
+}
+
+int clbm_kernel_timing_begin(clbm_ctx *c, int cap)
+{
+    if (!c || cap < 1) { set_error("bad argument to clbm_kernel_timing_begin"); return CLBM_EINVAL; }
+    for (auto e : c->kev) cudaEventDestroy(e);
+    c->kev.clear();
+    c->ktiming = true;
+    c->ktiming_cap = cap;
+    return CLBM_OK;
+}
+
+int clbm_kernel_timing_end(clbm_ctx *c, float *avg_ms, int *count, const char **kernel_name)
+{
+    if (!c || !avg_ms || !count) { set_error("bad argument to clbm_kernel_timing_end"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    c->ktiming = false;
+    double sum = 0.0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < c->kev.size(); i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->kev[i], c->kev[i + 1]) == cudaSuccess) { sum += ms; ++n; }
+    }
+    for (auto e : c->kev) cudaEventDestroy(e);
+    c->kev.clear();
+    *avg_ms = n ? (float)(sum / n) : 0.f;
+    *count = n;
+    if (kernel_name) *kernel_name = c->kname;
+    return CLBM_OK;
+}
+
+int clbm_alloc_host(size_t bytes, void **ptr)
+{
+    if (!ptr) { set_error("null argument"); return CLBM_EINVAL; }
+    *ptr = nullptr;
+    CLBM_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return CLBM_OK;
+}
+int clbm_free_host(void *ptr)
+{
+    if (ptr) CLBM_CUDA(cudaFreeHost(ptr));
+    return CLBM_OK;
 }
 
 int clbm_reduce(clbm_ctx *c, int kind, double *out)

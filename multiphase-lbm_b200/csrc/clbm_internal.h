@@ -55,6 +55,11 @@ struct clbm_ctx {
     // staging for host<->device slab transfers (pinned), grown on demand
     void *stage;
     size_t stage_bytes;
+    // dominant-kernel timing (event pairs around the collide/stream launches)
+    bool ktiming;
+    int ktiming_cap;
+    std::vector<cudaEvent_t> kev;
+    const char *kname;
     // profiling
     bool profiling;
     std::vector<clbm::KernelTiming> prof;
@@ -76,7 +81,8 @@ struct LaunchScope {
     clbm_ctx *c;
     const char *name;
     cudaEvent_t a, b;
-    LaunchScope(clbm_ctx *ctx, const char *n);
+    bool timed;
+    LaunchScope(clbm_ctx *ctx, const char *n, bool dominant = false);
     ~LaunchScope();
 };
 

@@ -246,7 +246,7 @@ int hcz3d_level2(clbm_ctx *c)
 int hcz3d_collide(clbm_ctx *c)
 {
     const long long n = (long long)c->geo.nx * c->geo.plane;
-    LaunchScope ls(c, "hcz3d_collide_stream");
+    LaunchScope ls(c, "hcz3d_collide_stream", true);
     hcz3d_collide_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
                                                                 c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
                                                                 fld8(c), c->geo, c->mp, 0, n);

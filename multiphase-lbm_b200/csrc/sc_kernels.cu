@@ -105,7 +105,7 @@ template <class L> static int sc_collide_range(clbm_ctx *c, int x0, int x1)
 {
     const long long n = (long long)(x1 - x0) * c->geo.plane;
     if (n <= 0) return 0;
-    LaunchScope ls(c, "sc_collide_stream");
+    LaunchScope ls(c, "sc_collide_stream", true);
     sc_collide_kernel<L><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
                                                                  c->fld[0], c->geo, c->mp, x0, n);
     CLBM_CUDA(cudaGetLastError());

@@ -211,7 +211,7 @@ static void sc_psi_field(const clbm_params *p, const sc_eos *e, int D, const dou
 /* one Shan-Chen step: operator() of SC/apps/laplace2D.h:285-306 / contactAngle2D.h:333-355 */
 static void sc_step(const clbm_params *p, int D, const double *fin, double *fout, const uint8_t *flag)
 {
-    const int Q = (D == 2) ? 9 : 19, H = (D == 2) ? 4 : 9;
+    const int H = (D == 2) ? 4 : 9;
     const int nx = p->nx, ny = p->ny, nz = p->nz;
     const size_t ne = (size_t)nx * ny * nz;
     const sc_eos e = {p->R, p->TT, p->a};
