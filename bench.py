@@ -36,7 +36,7 @@ WORKLOADS = {
     "c3_hcz_d2q9_slab": ("hcz2d", (256, 8194, 1), "HCZ D2Q9 Rayleigh-Taylor 2048x8194, one 256-column slab per GPU (BASELINE configs[2])"),
     "c2_hcz_d2q9_256": ("hcz2d", (256, 1026, 1), "HCZ D2Q9 Rayleigh-Taylor 256x1026 (BASELINE configs[1]; fits in L2)"),
     "c1_sc_d2q9_256": ("sc2d", (256, 256, 1), "Shan-Chen D2Q9 static droplet 256x256 (BASELINE configs[0]; fits in L2)"),
-    "sc_d2q9_8192": ("sc2d", (8192, 8192, 1), "Shan-Chen D2Q9 static droplet 8192x8192 (HBM-sized D2Q9)"),
+    "sc_d2q9_8192": ("sc2d_tau1", (8192, 8192, 1), "Shan-Chen D2Q9 static droplet 8192x8192 (HBM-sized D2Q9)"),
 }
 
 
@@ -46,6 +46,9 @@ def build_params(P, key, nx, ny, nz, nx_global, x_offset, fused):
         case, args = P.CASE_SC_DROPLET3D, (0.265, 0.038, 0.2 * ny, 5.0)
     elif key == "sc2d":
         prm = P.sc_params(P.MODEL_SC_D2Q9, nx, ny, 1, ulb=0.01, N=nx_global, Re=6.0)
+        case, args = P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0)
+    elif key == "sc2d_tau1":
+        prm = P.sc_params(P.MODEL_SC_D2Q9, nx, ny, 1, tau=1.0)
         case, args = P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0)
     elif key == "hcz3d":
         prm = P.hcz_params(P.MODEL_HCZ_D3Q19, nx, ny, nz, ulb=0.01, N=nx_global, Re=6.0, kappa=5e-4, gravity=0.0)
@@ -105,7 +108,7 @@ def measured_peak_gbs():
 def cpu_baseline(P, key, threads=0, target_s=12.0):
     """time the CPU oracle port on a bounded sample of the same workload (rank 0, N=1)"""
     from _oracle import OracleSim, max_threads
-    sample = {"sc3d": (96, 96, 96), "hcz3d": (64, 64, 64), "sc2d": (1024, 1024, 1), "hcz2d": (256, 1026, 1)}[key]
+    sample = {"sc3d": (96, 96, 96), "hcz3d": (64, 64, 64), "sc2d": (1024, 1024, 1), "sc2d_tau1": (1024, 1024, 1), "hcz2d": (256, 1026, 1)}[key]
     prm, case, args = build_params(P, key, *sample, sample[0], 0, 0)
     if key == "sc3d":
         args = (0.265, 0.038, 0.2 * sample[1], 5.0)
@@ -152,6 +155,7 @@ def reference_functor_baseline(key):
     """the UNTOUCHED reference functor (oracle/_ref harness binary), all host threads, small sample"""
     from _oracle import ref_binary
     spec = {"sc2d": ("ref_sc_laplace2d", ["nx=512", "ny=512", "steps=40"]),
+            "sc2d_tau1": ("ref_sc_laplace2d", ["nx=512", "ny=512", "steps=40", "omega=1.0"]),
             "hcz2d": ("ref_hcz_rt2d", ["nx=128", "ny=514", "steps=8"]),
             "hcz3d": ("ref_hcz_laplace3d", ["nx=16", "ny=16", "nz=16", "steps=2"])}.get(key)
     if not spec or not ref_binary(spec[0]):

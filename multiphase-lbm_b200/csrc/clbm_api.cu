@@ -1,5 +1,6 @@
 // clbm_api.cu -- the C ABI of include/clbm.h: context life cycle, state transfer between the
 // reference host layout and the device slab storage, the step loop, diagnostics, profiling.
+#include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <new>
@@ -190,6 +191,25 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     m.rho_w = p->rho_w; m.a = p->a; m.b = p->b; m.R = p->R; m.TT = p->TT;
     m.phi_l = p->phi_l; m.phi_g = p->phi_g; m.rho_l = p->rho_l; m.rho_g = p->rho_g; m.kappa = p->kappa;
     m.sc_force = p->sc_force;
+    m.tau = 1. / p->omega;
+    {
+        // wall pseudopotential: laplace2D.h:210 evaluates psi_yuan_from_rho(rho_w) (own branch G1(rho_w));
+        // contactAngle2D.h:259-262 re-evaluates it on the CENTRE node's branch G1c = +-1/3
+        const double cs2 = 1.0 / 3.0, rw = p->rho_w, dw = (1.0 - rw);
+        const double Zw = 1.0 + (4.0 * rw - 2.0 * rw * rw) / (dw * dw * dw);
+        if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
+            const double vp = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / cs2;
+            const double vn = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / -cs2;
+            m.psiw_pos = (vp > 0.0) ? sqrt(vp) : 0.0;
+            m.psiw_neg = (vn > 0.0) ? sqrt(vn) : 0.0;
+        } else {
+            const double Pw = rw * p->R * p->TT * Zw - p->a * rw * rw;
+            const double sw = p->R * p->TT * Zw - p->a * rw - cs2;
+            const double G1w = (sw > 0.0) ? cs2 : -cs2;
+            const double vw = 6.0 * (Pw - cs2 * rw) / G1w;
+            m.psiw_pos = m.psiw_neg = (vw > 0.0) ? sqrt(vw) : 0.0;
+        }
+    }
 
     int rc = 0;
     auto fail = [&](int code) { clbm_destroy(c); return code; };

@@ -18,6 +18,9 @@ struct ModelParams {
     double rho_w, a, b, R, TT;                    // Shan-Chen / Yuan-CS
     double phi_l, phi_g, rho_l, rho_g, kappa;     // HCZ
     int sc_force;
+    // derived on the host with the reference's expressions (clbm_create)
+    double tau;                  // 1/omega
+    double psiw_pos, psiw_neg;   // wall pseudopotential for G1 = +1/3 / -1/3 at the centre node
 };
 
 struct KernelTiming {

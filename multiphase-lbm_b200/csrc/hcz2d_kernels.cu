@@ -107,7 +107,7 @@ CLBM_D void hcz2d_node(const ModelParams &mp, const double *g9, const double *co
 
 struct FieldPtrs5 { const double *p[5]; };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 hcz2d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const double *__restrict__ gin,
                      double *__restrict__ gout, const uint8_t *__restrict__ flag, FieldPtrs5 F,
                      Geom g, ModelParams mp, int x0, long long ncell)

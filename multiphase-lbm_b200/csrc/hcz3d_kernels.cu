@@ -118,7 +118,7 @@ hcz3d_level2_kernel(const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g, Mode
     F.p[7][n.i] = o.P - o.rho / 3.0;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 hcz3d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const double *__restrict__ gin,
                      double *__restrict__ gout, const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g,
                      ModelParams mp, int x0, long long ncell)

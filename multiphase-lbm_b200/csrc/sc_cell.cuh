@@ -7,6 +7,12 @@
 //   collideBgk SC/apps/laplace2D.h:272-283 and the rest population :301-305
 // The D3Q19 form is the composition SURVEY.md 0.1/8c describes (D3Q19 set of
 // PF/apps/laplace3D.h:31-55 + the force/BGK of contactAngle2D.h).
+//
+// Arithmetic budget (the kernel is FP64-issue sensitive): per node ONE division for
+// Z(rho), ONE square root for psi and ONE reciprocal of rho.  The reference's  6(P - rho/3)/G1  with
+// G1 = +-1/3 becomes +-18 (P - rho/3); u + tau F/rho becomes (j + tau F)(1/rho); the wall
+// pseudopotential (a function of rho_w and the sign of G1 only) is precomputed on the host with the
+// reference's own expressions.  All of these differ from the reference by O(1 ulp).
 #pragma once
 #include "clbm_internal.h"
 #include "moments.cuh"
@@ -38,88 +44,112 @@ CLBM_D Nbr make_nbr(const Geom &g, int x, int y, int z)
     return n;
 }
 
+// psi(rho) and the sign of G1 with one division and one square root.
+//   Z = 1 + (4 rho - 2 rho^2)/(1-rho)^3 ; s = R T Z - a rho - 1/3 ; G1 = sign(s)/3
+//   psi = sqrt(6 (P - rho/3)/G1) = sqrt(+-18 (P - rho/3)),  P = rho R T Z - a rho^2   (0 where the radicand <= 0)
+CLBM_D double sc_psi_g1(const ModelParams &mp, double rho, bool &g1_pos)
+{
+    const double d = 1.0 - rho;
+    const double Zr = 1.0 + (4.0 * rho - 2.0 * rho * rho) / (d * d * d);
+    const double s = mp.R * mp.TT * Zr - mp.a * rho - (1.0 / 3.0);
+    g1_pos = s > 0.0;
+    const double P = rho * mp.R * mp.TT * Zr - mp.a * rho * rho;
+    const double q = P - (1.0 / 3.0) * rho;
+    const double val = g1_pos ? 18.0 * q : -18.0 * q;
+    return (val > 0.0) ? sqrt(val) : 0.0;
+}
+
 struct ScForceSums {
     double ff[3], bb[3];
     unsigned wall;  // bit k set: neighbour in direction k is a bounce_back node
 };
 
-// accumulate the k-th neighbour into the force sums (k is a compile-time constant after unrolling)
+// accumulate the k-th neighbour (k is a compile-time constant after unrolling).  Branch-free for the
+// fluid-fluid part; the wall sums are formed afterwards from the mask (rare).
 template <class L> CLBM_D void sc_force_add(ScForceSums &s, int k, bool is_wall, double psi_nb)
 {
     const double tk = L::t(k);
-    if (is_wall) {
-        s.wall |= 1u << k;
-        if (L::cx(k)) s.bb[0] += tk * L::cx(k);
-        if (L::cy(k)) s.bb[1] += tk * L::cy(k);
-        if (L::cz(k)) s.bb[2] += tk * L::cz(k);
-    } else {
-        if (L::cx(k)) s.ff[0] += tk * L::cx(k) * psi_nb;
-        if (L::cy(k)) s.ff[1] += tk * L::cy(k) * psi_nb;
-        if (L::cz(k)) s.ff[2] += tk * L::cz(k) * psi_nb;
+    const double v = is_wall ? 0.0 : psi_nb;
+    if (is_wall) s.wall |= 1u << k;
+    if (L::cx(k)) s.ff[0] += tk * L::cx(k) * v;
+    if (L::cy(k)) s.ff[1] += tk * L::cy(k) * v;
+    if (L::cz(k)) s.ff[2] += tk * L::cz(k) * v;
+}
+
+template <class L> CLBM_D void sc_wall_sums(ScForceSums &s)
+{
+    s.bb[0] = s.bb[1] = s.bb[2] = 0.0;
+    if (s.wall == 0u) return;
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) {
+        if (k == L::REST) continue;
+        if (s.wall & (1u << k)) {
+            if (L::cx(k)) s.bb[0] += L::t(k) * L::cx(k);
+            if (L::cy(k)) s.bb[1] += L::t(k) * L::cy(k);
+            if (L::cz(k)) s.bb[2] += L::t(k) * L::cz(k);
+        }
     }
 }
 
-// total force on the node; rho_c is the raw density (not clamped)
-template <class L> CLBM_D void sc_force(const ModelParams &mp, const ScForceSums &s, double rho_c, double F[3])
+// total force on the node; rho_c is the raw density (not clamped), psi_c / g1_pos its pseudopotential and branch
+template <class L>
+CLBM_D void sc_force(const ModelParams &mp, ScForceSums &s, double rho_c, double psi_c, bool g1_pos, double F[3])
 {
-    const ScEos eos{mp.R, mp.TT, mp.a};
-    const double Zc = eos.Z(rho_c);
-    const double G1 = eos.G1_of_Z(rho_c, Zc);
-    const double psi_c = eos.psi_of_Z(rho_c, Zc, G1);
+    sc_wall_sums<L>(s);
+    const double G1 = g1_pos ? (1.0 / 3.0) : -(1.0 / 3.0);
+    const double psi_w = g1_pos ? mp.psiw_pos : mp.psiw_neg;
+    const double a = -G1 * psi_c, b = -G1 * psi_c * psi_w;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) F[d] = a * s.ff[d] + b * s.bb[d];
     if (mp.sc_force == CLBM_SC_FORCE_CONTACT) {
-        if (rho_c <= 0.0) { F[0] = F[1] = F[2] = 0.0; return; }
-        const double Zw = eos.Z(mp.rho_w);
-        const double val_w = 6.0 * mp.rho_w * (mp.R * mp.TT * Zw - mp.a * mp.rho_w - (1.0 / 3.0)) / G1;
-        const double psi_w = (val_w > 0.0) ? sqrt(val_w) : 0.0;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) F[d] = -G1 * psi_c * s.ff[d] + (-G1 * psi_c * psi_w * s.bb[d]);
+        if (rho_c <= 0.0) F[0] = F[1] = F[2] = 0.0;
     } else {
-        const double psi_w = eos.psi(mp.rho_w);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) F[d] = -G1 * psi_c * s.ff[d] + (-G1 * psi_c * psi_w * s.bb[d]);
         F[1] += mp.gravity * rho_c;
     }
 }
 
 // BGK collision of all Q populations with the tau-shifted equilibrium velocity
-template <class L> CLBM_D void sc_collide(const ModelParams &mp, const double *f, const ScForceSums &s, double *out)
+template <class L>
+CLBM_D void sc_collide(const ModelParams &mp, const double *f, ScForceSums &s, double psi_c, bool g1_pos, double *out)
 {
     const double rho_raw = Mom<L>::sum(f);
     const double rho = fmax(rho_raw, 1e-14);
+    const double inv = 1.0 / rho;
     double jx, jy, jz, F[3];
     Mom<L>::first(f, jx, jy, jz);
-    sc_force<L>(mp, s, rho_raw, F);
-    const double omega = mp.omega, tau = 1.0 / omega;
-    const double ux = jx / rho + tau * F[0] / rho;
-    const double uy = jy / rho + tau * F[1] / rho;
-    const double uz = (L::D == 3) ? jz / rho + tau * F[2] / rho : 0.0;
-    const double usqr = 1.5 * (ux * ux + uy * uy + uz * uz);
+    sc_force<L>(mp, s, rho_raw, psi_c, g1_pos, F);
+    const double omega = mp.omega, om1 = 1.0 - omega, tau = mp.tau;
+    const double ux = (jx + tau * F[0]) * inv;
+    const double uy = (jy + tau * F[1]) * inv;
+    const double uz = (L::D == 3) ? (jz + tau * F[2]) * inv : 0.0;
+    const double base = 1.0 - 1.5 * (ux * ux + uy * uy + uz * uz);
+    const double A = omega * rho;
 #pragma unroll
     for (int k = 0; k < L::H; ++k) {
-        const double ck_u = L::cx(k) * ux + L::cy(k) * uy + L::cz(k) * uz;
-        const double eq = rho * L::t(k) * (1. + 3. * ck_u + 4.5 * ck_u * ck_u - usqr);
-        const double eqop = eq - 6.0 * rho * L::t(k) * ck_u;
-        out[k] = (1. - omega) * f[k] + omega * eq;
-        out[L::opp(k)] = (1. - omega) * f[L::opp(k)] + omega * eqop;
+        const double cu = L::cx(k) * ux + L::cy(k) * uy + L::cz(k) * uz;
+        const double even = A * L::t(k) * (base + 4.5 * cu * cu);
+        const double odd = A * L::t(k) * 3.0 * cu;
+        out[k] = om1 * f[k] + (even + odd);
+        out[L::opp(k)] = om1 * f[L::opp(k)] + (even - odd);
     }
-    out[L::REST] = (1. - omega) * f[L::REST] + omega * (rho * L::t(L::REST) * (1. - usqr));
+    out[L::REST] = om1 * f[L::REST] + A * L::t(L::REST) * base;
 }
 
 // output fields of one bulk node: pressure_node (laplace2D.h:308-315) and u_actual (:252-257)
 template <class L>
-CLBM_D void sc_outputs(const ModelParams &mp, const double *f, const ScForceSums &s, double &rho_raw, double &pr,
-                       double u[3])
+CLBM_D void sc_outputs(const ModelParams &mp, const double *f, ScForceSums &s, double &rho_raw, double &pr, double u[3])
 {
     rho_raw = Mom<L>::sum(f);
     const double rho = fmax(rho_raw, 1e-14);
     double jx, jy, jz, F[3];
     Mom<L>::first(f, jx, jy, jz);
-    sc_force<L>(mp, s, rho_raw, F);
+    bool g1_pos;
+    const double ps = sc_psi_g1(mp, rho_raw, g1_pos);
+    sc_force<L>(mp, s, rho_raw, ps, g1_pos, F);
     u[0] = jx / rho + 0.5 * F[0] / rho;
     u[1] = jy / rho + 0.5 * F[1] / rho;
     u[2] = (L::D == 3) ? jz / rho + 0.5 * F[2] / rho : 0.0;
-    const ScEos eos{mp.R, mp.TT, mp.a};
-    const double Zc = eos.Z(rho_raw), G1 = eos.G1_of_Z(rho_raw, Zc), ps = eos.psi_of_Z(rho_raw, Zc, G1);
+    const double G1 = g1_pos ? (1.0 / 3.0) : -(1.0 / 3.0);
     pr = (1.0 / 3.0) * rho_raw + (1.0 / 6.0) * G1 * ps * ps;
 }
 

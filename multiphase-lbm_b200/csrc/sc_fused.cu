@@ -1,18 +1,197 @@
-// sc_fused.cu -- fused plane-marching Shan-Chen step (placeholder: routes to the staged kernels
-// until the marching kernel lands).
-#include "clbm_internal.h"
+// sc_fused.cu -- fused plane-marching Shan-Chen time step: ONE kernel per step, every population
+// read once and written once from HBM.
+//
+// The staged form (sc_kernels.cu) reads the populations twice: once to build psi(rho), once to
+// collide.  Here a thread block owns a TY x TZ tile of the (y,z) plane and marches along x (the
+// slowest index).  While plane x is collided, the populations of plane x+1 are already in
+// registers: they were loaded to compute psi(x+1) into a 4-slot shared-memory ring of
+// (TY+2) x (TZ+2) psi planes with halos, and they are kept for the collision of the next
+// iteration.  Only the halo ring of each plane is read a second time (by the neighbouring
+// tile), which the L2 absorbs.  One __syncthreads per plane.
+//
+//   psi ring value < 0  <=>  bounce_back node (psi >= 0 everywhere else), so the ring also
+//   carries the node mask for the wall term and for the half-way bounce-back of the push.
+//
+// Physics per cell: sc_cell.cuh (force, tau-shifted BGK; SC/apps/laplace2D.h:198-306,
+// SC/apps/contactAngle2D.h:248-355).
+#include <cstdlib>
+
+#include "sc_cell.cuh"
 
 namespace clbm {
-int sc_psi_all(clbm_ctx *c);
-int sc_collide_all(clbm_ctx *c);
+
+template <class L, int TY, int TZ>
+struct FusedCfg {
+    static constexpr int NT = TY * TZ;
+    static constexpr int SY = TY + 2;
+    static constexpr int SZ = (L::D == 3) ? TZ + 2 : 1;
+    static constexpr int NHALO = (L::D == 3) ? 2 * SZ + 2 * TY : 2;
+    static_assert(L::D == 3 || TZ == 1, "D2Q9 tiles are one-dimensional");
+};
+
+template <class L> struct PopTable {
+    const double *in[L::Q];   // fin + k*ncs  (constant-bank operands: one IMAD.WIDE per address)
+    double *out[L::Q];        // fout + k*ncs
+};
+
+template <class L, int TY, int TZ, int MINB>
+__global__ void __launch_bounds__(TY *TZ, MINB)
+sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, Geom g, ModelParams mp, int xchunk)
+{
+    using C = FusedCfg<L, TY, TZ>;
+    __shared__ double psi_s[4][C::SY][C::SZ];
+
+    const int tid = threadIdx.x;
+    const int tz = tid % TZ, ty = tid / TZ;
+    const int y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
+    const int y = y0 + ty, z = z0 + tz;
+    const bool inside = (y < g.ny) && (z < g.nz);
+    const int xa = blockIdx.z * xchunk;
+    const int xb = min(g.nx, xa + xchunk);
+    const int plane = (int)g.plane, nz = g.nz, G = g.G;
+    // rows / columns of this tile that lie inside the lattice (partial tiles at the upper edges);
+    // the halo ring hugs them: rows sy = 0 and ty_n+1, columns sz = 0 and tz_n+1
+    const int ty_n = min(TY, g.ny - y0), tz_n = (L::D == 3) ? min(TZ, g.nz - z0) : 1;
+    const int nrow = tz_n + 2;
+    const int nhalo = (L::D == 3) ? 2 * nrow + 2 * ty_n : 2;
+    const int cz0 = (L::D == 3) ? tz + 1 : 0;
+    const int yz = y * nz + z;   // in-plane index of the own cell
+
+    // psi (or -1 for a wall) of storage plane xs into ring slot `slot`.  The thread's own populations stay in
+    // fk, its own psi / G1 branch in ps / gp (used when that plane is collided one iteration later).
+    auto fill = [&](int xs, int slot, double *fk, double &ps, bool &gp) {
+        if (inside) {
+            const int i = xs * plane + yz;
+#pragma unroll
+            for (int k = 0; k < L::Q; ++k) fk[k] = P.in[k][i];
+            double v = -1.0;
+            ps = 0.0;
+            gp = true;
+            if (flag[i] != CELL_BB) { ps = sc_psi_g1(mp, Mom<L>::sum(fk), gp); v = ps; }
+            psi_s[slot][ty + 1][cz0] = v;
+        }
+        for (int h = tid; h < nhalo; h += C::NT) {
+            int sy, sz;
+            if (L::D == 3) {
+                if (h < nrow) { sy = 0; sz = h; }
+                else if (h < 2 * nrow) { sy = ty_n + 1; sz = h - nrow; }
+                else { const int q = h - 2 * nrow; sy = 1 + (q >> 1); sz = (q & 1) ? tz_n + 1 : 0; }
+            } else { sy = h ? ty_n + 1 : 0; sz = 0; }
+            const int yy = g.wy(y0 + sy - 1), zz = (L::D == 3) ? g.wz(z0 + sz - 1) : 0;
+            const int i = xs * plane + yy * nz + zz;
+            double v = -1.0;
+            if (flag[i] != CELL_BB) {
+                double fh[L::Q];
+#pragma unroll
+                for (int k = 0; k < L::Q; ++k) fh[k] = P.in[k][i];
+                bool gph;
+                v = sc_psi_g1(mp, Mom<L>::sum(fh), gph);
+            }
+            psi_s[slot][sy][sz] = v;
+        }
+    };
+
+    double fc[L::Q], fn[L::Q];
+    double psc, psn;
+    bool gpc, gpn;
+    fill(g.wx(xa - 1) + G, (xa + 3) & 3, fn, psn, gpn);   // plane xa-1: only its psi ring is needed
+    fill(xa + G, xa & 3, fc, psc, gpc);
+
+    // in-plane neighbour offsets of this thread's column (x offsets change per plane)
+    const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
+    const int ozm = g.wz(z - 1) - z, ozp = g.wz(z + 1) - z;
+
+    for (int x = xa; x < xb; ++x) {
+        const int xp = g.wx(x + 1), xm = g.wx(x - 1);
+        fill(xp + G, (x + 1) & 3, fn, psn, gpn);
+        __syncthreads();
+
+        const int sm = (x + 3) & 3, s0 = x & 3, sp = (x + 1) & 3;
+        if (inside && psi_s[s0][ty + 1][cz0] >= 0.0) {
+            ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
+#pragma unroll
+            for (int k = 0; k < L::Q; ++k) {
+                if (k == L::REST) continue;
+                const int slot = L::cx(k) < 0 ? sm : (L::cx(k) > 0 ? sp : s0);
+                const double v = psi_s[slot][ty + 1 + L::cy(k)][cz0 + L::cz(k)];
+                sc_force_add<L>(s, k, v < 0.0, v);
+            }
+            double out[L::Q];
+            sc_collide<L>(mp, fc, s, psc, gpc, out);
+
+            const int i = (x + G) * plane + yz;
+            const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
+#pragma unroll
+            for (int k = 0; k < L::Q; ++k) {
+                if (k == L::REST) { P.out[k][i] = out[k]; continue; }
+                const int off = (L::cx(k) < 0 ? oxm : (L::cx(k) > 0 ? oxp : 0)) + (L::cy(k) < 0 ? oym : (L::cy(k) > 0 ? oyp : 0)) +
+                                (L::cz(k) < 0 ? ozm : (L::cz(k) > 0 ? ozp : 0));
+                if (s.wall & (1u << k)) P.out[L::opp(k)][i] = out[k];   // half-way bounce-back
+                else P.out[k][i + off] = out[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < L::Q; ++k) fc[k] = fn[k];
+        psc = psn;
+        gpc = gpn;
+    }
+}
+
+struct FusedChoice { int ty, tz; };
+
+template <class L, int TY, int TZ, int MINB>
+static int launch_fused(clbm_ctx *c)
+{
+    const Geom &g = c->geo;
+    const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
+    // enough blocks for >= 8 waves of 148 SMs where the lattice allows, chunks of at least 8 planes
+    int xchunk = g.nx;
+    const long long want = 8LL * 148 * MINB;
+    if ((long long)tiles < want) {
+        const long long nch = (want + tiles - 1) / tiles;
+        xchunk = (int)((g.nx + nch - 1) / nch);
+        if (xchunk < 8) xchunk = g.nx < 8 ? g.nx : 8;
+    }
+    if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+    dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
+    PopTable<L> P;
+    for (int k = 0; k < L::Q; ++k) {
+        P.in[k] = c->pop[0][c->parity] + (size_t)k * g.ncs;
+        P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+    }
+    LaunchScope ls(c, "sc_fused_collide_stream", true);
+    sc_fused_kernel<L, TY, TZ, MINB><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, g, c->mp, xchunk);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int sc_fused_step(clbm_ctx *c)
 {
-    int rc = sc_psi_all(c);
-    if (rc) return rc;
-    rc = sc_collide_all(c);
+    int rc;
+    int variant = 0;
+    if (const char *e = getenv("CLBM_SC_TILE")) variant = atoi(e);
+    if (c->Q == 9) {
+        switch (variant) {
+        case 1: rc = launch_fused<D2Q9, 256, 1, 2>(c); break;
+        case 2: rc = launch_fused<D2Q9, 64, 1, 8>(c); break;
+        default: rc = launch_fused<D2Q9, 128, 1, 4>(c); break;
+        }
+    } else {
+        switch (variant) {
+        case 1: rc = launch_fused<D3Q19, 8, 64, 1>(c); break;
+        case 2: rc = launch_fused<D3Q19, 8, 32, 2>(c); break;
+        case 3: rc = launch_fused<D3Q19, 16, 32, 1>(c); break;
+        case 4: rc = launch_fused<D3Q19, 2, 128, 2>(c); break;
+        case 5: rc = launch_fused<D3Q19, 6, 64, 1>(c); break;
+        case 6: rc = launch_fused<D3Q19, 4, 64, 1>(c); break;
+        case 7: rc = launch_fused<D3Q19, 3, 128, 1>(c); break;
+        case 8: rc = launch_fused<D3Q19, 4, 128, 1>(c); break;
+        default: rc = launch_fused<D3Q19, 4, 64, 2>(c); break;
+        }
+    }
     if (rc) return rc;
     c->parity = 1 - c->parity;
     return 0;
 }
+
 }  // namespace clbm

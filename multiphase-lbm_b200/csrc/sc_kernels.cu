@@ -18,13 +18,18 @@ sc_psi_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, 
     double f[L::Q];
 #pragma unroll
     for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + i];
-    const double rho = Mom<L>::sum(f);
-    const ScEos eos{mp.R, mp.TT, mp.a};
-    psi[i] = (flag[i] == CELL_BB) ? 0.0 : eos.psi(rho);
+    // |value| = psi(rho), sign bit = branch of G1 (set: G1 = -1/3); walls hold +0
+    double v = 0.0;
+    if (flag[i] != CELL_BB) {
+        bool g1_pos;
+        const double ps = sc_psi_g1(mp, Mom<L>::sum(f), g1_pos);
+        v = g1_pos ? ps : -ps;
+    }
+    psi[i] = v;
 }
 
 template <class L>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const uint8_t *__restrict__ flag,
                   const double *__restrict__ psi, Geom g, ModelParams mp, int x0, long long ncell)
 {
@@ -46,9 +51,10 @@ sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, con
         if (k == L::REST) continue;  // c = 0: contributes nothing, and a bulk node is never its own wall
         const long long nb = n.at<L>(k);
         const bool w = flag[nb] == CELL_BB;
-        sc_force_add<L>(s, k, w, w ? 0.0 : psi[nb]);
+        sc_force_add<L>(s, k, w, w ? 0.0 : fabs(psi[nb]));
     }
-    sc_collide<L>(mp, f, s, out);
+    const double pc = psi[n.i];
+    sc_collide<L>(mp, f, s, fabs(pc), !signbit(pc), out);
 
 #pragma unroll
     for (int k = 0; k < L::Q; ++k) {
@@ -80,7 +86,7 @@ sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ fla
             if (k == L::REST) continue;
             const long long nb = n.at<L>(k);
             const bool w = flag[nb] == CELL_BB;
-            sc_force_add<L>(s, k, w, w ? 0.0 : psi[nb]);
+            sc_force_add<L>(s, k, w, w ? 0.0 : fabs(psi[nb]));
         }
         sc_outputs<L>(mp, f, s, rho, pr, u);
     }
