@@ -165,11 +165,19 @@ static int launch_fused(clbm_ctx *c)
     return 0;
 }
 
+bool sc_tma_eligible(const clbm_ctx *c);            // sc_fused_tma.cu
+int sc_fused_tma_step(clbm_ctx *c, int variant);
+
 int sc_fused_step(clbm_ctx *c)
 {
     int rc;
-    int variant = 0;
+    // clbm_params.fused: 1 = default fused kernel, >1 = explicit tile variant (tuning / tests); env overrides
+    int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (const char *e = getenv("CLBM_SC_TILE")) variant = atoi(e);
+    // D3Q19 default: the TMA-staged kernel with 8 x 64 tiles (best of the sweep in profiles/README.md)
+    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 11;
+    if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
+    if (variant >= 10) variant = 0;
     if (c->Q == 9) {
         switch (variant) {
         case 1: rc = launch_fused<D2Q9, 256, 1, 2>(c); break;

@@ -1,0 +1,305 @@
+// sc_fused_tma.cu -- D3Q19 Shan-Chen fused step with TMA-staged population tiles (sm_100a).
+//
+// Same plane-marching scheme as sc_fused.cu (one launch per time step, every population read once and
+// written once from HBM), but the loads are taken off the instruction stream:
+//
+//   * one cp.async.bulk.tensor (TMA) per x-plane fetches the 19 x (TY+2) x (TZ+2) box "tile + halo ring,
+//     all directions" of the population tensor [k][x][y][z] into shared memory; completion is signalled
+//     on an mbarrier (expect_tx / complete_tx).  Two stages: the box of plane x+2 is in flight while
+//     plane x is collided, so HBM latency is hidden without holding a second population set in registers.
+//   * psi(rho) of plane x+1 (tile + halo) is computed straight from the staged box into a 4-slot ring of
+//     psi planes; the force stencil of plane x reads ring slots x-1, x, x+1.
+//   * the collision takes the 19 own populations of plane x from the stage (LDS), the post-collision
+//     values are pushed to the neighbours with plain coalesced stores (half-way bounce-back at walls).
+//
+// TMA cannot wrap, so halo cells that lie across a periodic y/z boundary (only on tiles touching the
+// lattice edge) are fetched with ordinary loads; out-of-bounds box elements are zero-filled and unused.
+// Physics per cell: sc_cell.cuh.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "sc_cell.cuh"
+
+namespace clbm {
+
+using L3 = D3Q19;
+
+CLBM_D uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+CLBM_D void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+CLBM_D void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+CLBM_D void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+CLBM_D void tma_load_4d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+struct OutTable { double *out[19]; };
+
+template <int TY, int TZ>
+struct TmaCfg {
+    static constexpr int NT = TY * TZ, SY = TY + 2, SZ = TZ + 2;
+    // the innermost TMA coordinate must be 16-byte aligned (odd z faults on sm_100a, tools/tma_probe.cu), so the
+    // box spans z0-2 .. z0+TZ+1: BZ = TZ+4 columns, of which column 0 and TZ+3 are padding
+    static constexpr int BZ = TZ + 4;
+    static constexpr int NH = 2 * SZ + 2 * TY;                 // halo ring cells
+    static constexpr int BOX = 19 * SY * BZ;                   // doubles per staged box
+    static_assert(TZ % 2 == 0, "box rows must be a multiple of 16 bytes");
+    static constexpr int STAGE_BYTES = ((BOX * 8 + 127) / 128) * 128;
+    static constexpr int RING_BYTES = 4 * SY * SZ * 8;
+    static constexpr int SMEM = 2 * STAGE_BYTES + RING_BYTES + 64;
+    static_assert(NH <= NT, "one halo cell per thread");
+};
+
+template <int TY, int TZ, int MINB>
+__global__ void __launch_bounds__(TY *TZ, MINB)
+sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, const uint8_t *__restrict__ flag,
+                    const double *__restrict__ fin, Geom g, ModelParams mp, int xchunk)
+{
+    using C = TmaCfg<TY, TZ>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *stage[2] = {reinterpret_cast<double *>(smem_raw), reinterpret_cast<double *>(smem_raw + C::STAGE_BYTES)};
+    double (*ring)[C::SY][C::SZ] = reinterpret_cast<double (*)[C::SY][C::SZ]>(smem_raw + 2 * C::STAGE_BYTES);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * C::STAGE_BYTES + C::RING_BYTES);
+
+    const int tid = threadIdx.x;
+    const int tz = tid % TZ, ty = tid / TZ;
+    const int y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
+    const int y = y0 + ty, z = z0 + tz;
+    const bool inside = (y < g.ny) && (z < g.nz);
+    const int xa = blockIdx.z * xchunk;
+    const int nplanes = min(g.nx, xa + xchunk) - xa;
+    const int plane = (int)g.plane, nz = g.nz, G = g.G;
+    const int ty_n = min(TY, g.ny - y0), tz_n = min(TZ, g.nz - z0);
+    const int nrow = tz_n + 2, nhalo = 2 * nrow + 2 * ty_n;
+    const int yz = y * nz + z;
+    const int own_s = (ty + 1) * C::BZ + (tz + 2);   // own cell inside a staged k-slab (box column = ring column + 1)
+
+    // this thread's halo cell (if any): position in the box, wrapped lattice position, whether TMA could not fetch it
+    const bool h_act = tid < nhalo;
+    int hsy = 0, hsz = 0;
+    if (h_act) {
+        if (tid < nrow) { hsy = 0; hsz = tid; }
+        else if (tid < 2 * nrow) { hsy = ty_n + 1; hsz = tid - nrow; }
+        else { const int q = tid - 2 * nrow; hsy = 1 + (q >> 1); hsz = (q & 1) ? tz_n + 1 : 0; }
+    }
+    const int hy_raw = y0 + hsy - 1, hz_raw = z0 + hsz - 1;
+    const bool h_wrapped = (hy_raw < 0) || (hy_raw >= g.ny) || (hz_raw < 0) || (hz_raw >= g.nz);
+    const int hyz = g.wy(hy_raw) * nz + g.wz(hz_raw);
+    const int h_s = hsy * C::BZ + (hsz + 1);
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // r = 0 .. nplanes+1 enumerates the planes xa-1 .. xa+nplanes; plane r lives in stage r&1, ring slot r&3
+    auto xs_of = [&](int r) { return g.wx(xa - 1 + r) + G; };   // storage plane
+    auto issue = [&](int r) {
+        mbar_expect_tx(&mbar[r & 1], (uint32_t)(C::BOX * 8));
+        tma_load_4d(stage[r & 1], &tmap, &mbar[r & 1], z0 - 2, y0 - 1, xs_of(r), 0);
+    };
+    double psn = 0.0;
+    bool gpn = true;
+    // psi of plane r (tile + halo ring) from its staged box into the ring; keeps the own psi / G1 branch
+    auto make_psi = [&](int r, uint8_t fl_own, uint8_t fl_halo) {
+        const double *st = stage[r & 1];
+        if (inside) {
+            double v = -1.0;
+            psn = 0.0;
+            gpn = true;
+            if (fl_own != CELL_BB) {
+                double f[19];
+#pragma unroll
+                for (int k = 0; k < 19; ++k) f[k] = st[k * (C::SY * C::BZ) + own_s];
+                psn = sc_psi_g1(mp, Mom<L3>::sum(f), gpn);
+                v = psn;
+            }
+            ring[r & 3][ty + 1][tz + 1] = v;
+        }
+        if (h_act) {
+            double v = -1.0;
+            if (fl_halo != CELL_BB) {
+                double f[19];
+                if (h_wrapped) {
+                    const int i = xs_of(r) * plane + hyz;
+#pragma unroll
+                    for (int k = 0; k < 19; ++k) f[k] = fin[(size_t)k * g.ncs + i];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 19; ++k) f[k] = st[k * (C::SY * C::BZ) + h_s];
+                }
+                bool gph;
+                v = sc_psi_g1(mp, Mom<L3>::sum(f), gph);
+            }
+            ring[r & 3][hsy][hsz] = v;
+        }
+    };
+    auto flags_of = [&](int r, uint8_t &fo, uint8_t &fh) {
+        const int xs = xs_of(r);
+        fo = inside ? flag[xs * plane + yz] : CELL_BB;
+        fh = h_act ? flag[xs * plane + hyz] : CELL_BB;
+    };
+
+    if (tid == 0) { issue(0); issue(1); }
+    uint8_t fo, fh;
+    flags_of(0, fo, fh);
+    mbar_wait(&mbar[0], 0);
+    make_psi(0, fo, fh);
+    flags_of(1, fo, fh);
+    mbar_wait(&mbar[1], 0);
+    make_psi(1, fo, fh);
+    double psc = psn;
+    bool gpc = gpn;
+    __syncthreads();
+    if (tid == 0 && nplanes + 1 >= 2) issue(2);
+
+    const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
+    const int ozm = g.wz(z - 1) - z, ozp = g.wz(z + 1) - z;
+
+    for (int r = 1; r <= nplanes; ++r) {
+        flags_of(r + 1, fo, fh);
+        mbar_wait(&mbar[(r + 1) & 1], ((r + 1) >> 1) & 1);
+        make_psi(r + 1, fo, fh);
+
+        // own populations of plane r out of its stage before the stage is recycled
+        double fc[19];
+        {
+            const double *st = stage[r & 1];
+#pragma unroll
+            for (int k = 0; k < 19; ++k) fc[k] = st[k * (C::SY * C::BZ) + own_s];
+        }
+        __syncthreads();
+        if (tid == 0 && r + 2 <= nplanes + 1) issue(r + 2);
+
+        const int sm = (r + 3) & 3, s0 = r & 3, sp = (r + 1) & 3;
+        if (inside && ring[s0][ty + 1][tz + 1] >= 0.0) {
+            ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
+#pragma unroll
+            for (int k = 0; k < 19; ++k) {
+                if (k == L3::REST) continue;
+                const int slot = L3::cx(k) < 0 ? sm : (L3::cx(k) > 0 ? sp : s0);
+                const double v = ring[slot][ty + 1 + L3::cy(k)][tz + 1 + L3::cz(k)];
+                sc_force_add<L3>(s, k, v < 0.0, v);
+            }
+            double out[19];
+            sc_collide<L3>(mp, fc, s, psc, gpc, out);
+
+            const int x = xa - 1 + r;
+            const int xp = g.wx(x + 1), xm = g.wx(x - 1);
+            const int i = (x + G) * plane + yz;
+            const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
+#pragma unroll
+            for (int k = 0; k < 19; ++k) {
+                if (k == L3::REST) { P.out[k][i] = out[k]; continue; }
+                const int off = (L3::cx(k) < 0 ? oxm : (L3::cx(k) > 0 ? oxp : 0)) + (L3::cy(k) < 0 ? oym : (L3::cy(k) > 0 ? oyp : 0)) +
+                                (L3::cz(k) < 0 ? ozm : (L3::cz(k) > 0 ? ozp : 0));
+                if (s.wall & (1u << k)) P.out[L3::opp(k)][i] = out[k];
+                else P.out[k][i + off] = out[k];
+            }
+        }
+        psc = psn;
+        gpc = gpn;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// can this lattice be described by a 16-byte-stride tensor map?
+bool sc_tma_eligible(const clbm_ctx *c)
+{
+    const Geom &g = c->geo;
+    return c->Q == 19 && (g.nz % 2 == 0) && g.ncs < (1LL << 31) && get_encode() != nullptr;
+}
+
+template <int TY, int TZ, int MINB>
+static int launch_tma(clbm_ctx *c)
+{
+    using C = TmaCfg<TY, TZ>;
+    const Geom &g = c->geo;
+    CUtensorMap tmap;
+    const cuuint64_t dims[4] = {(cuuint64_t)g.nz, (cuuint64_t)g.ny, (cuuint64_t)(g.nx + 2 * g.G), 19};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.nz * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.ncs * 8};
+    const cuuint32_t box[4] = {(cuuint32_t)C::BZ, (cuuint32_t)C::SY, 1, 19};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)c->pop[0][c->parity], dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
+
+    const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
+    int xchunk = g.nx;
+    const long long want = 6LL * 148 * MINB;
+    if ((long long)tiles < want) {
+        const long long nch = (want + tiles - 1) / tiles;
+        xchunk = (int)((g.nx + nch - 1) / nch);
+        if (xchunk < 16) xchunk = g.nx < 16 ? g.nx : 16;
+    }
+    if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+    dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
+    OutTable P;
+    for (int k = 0; k < 19; ++k) P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+    auto kern = sc_fused_tma_kernel<TY, TZ, MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    LaunchScope ls(c, "sc_fused_tma_collide_stream", true);
+    kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], g, c->mp, xchunk);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int sc_fused_tma_step(clbm_ctx *c, int variant)
+{
+    int rc;
+    switch (variant) {
+    case 11: rc = launch_tma<8, 64, 1>(c); break;
+    case 12: rc = launch_tma<16, 32, 1>(c); break;
+    case 13: rc = launch_tma<4, 64, 1>(c); break;
+    case 14: rc = launch_tma<4, 32, 3>(c); break;
+    case 15: rc = launch_tma<8, 16, 3>(c); break;
+    case 16: rc = launch_tma<8, 32, 1>(c); break;
+    default: rc = launch_tma<6, 32, 2>(c); break;
+    }
+    if (rc) return rc;
+    c->parity = 1 - c->parity;
+    return 0;
+}
+
+}  // namespace clbm

@@ -77,7 +77,7 @@ def test_sc_contact2d_walls_1000_steps(fused):
     check_fields(ora.fields(), got, ("s0", "s1", "ux", "uy"))
 
 
-@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("fused", [0, 1, 2, 5, 9, 10, 11, 12, 13, 14, 15, 16])
 def test_sc_d3q19_sessile_droplet(fused):
     """config 4 physics at a size the oracle finishes: walls y=0,ny-1, contact-angle force"""
     prm = P.sc_params(P.MODEL_SC_D3Q19, 40, 24, 36, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
@@ -87,7 +87,7 @@ def test_sc_d3q19_sessile_droplet(fused):
     assert _cases.rel_linf(pops, ora.in_pops()) < TOL
 
 
-@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("fused", [0, 1, 10, 13])
 def test_sc_d3q19_periodic_droplet_gravity(fused):
     prm = P.sc_params(P.MODEL_SC_D3Q19, 24, 28, 32, omega=1.3, gravity=-2e-5, sc_force=P.SC_FORCE_LAPLACE)
     ora, got, pops, _ = run_pair(prm, P.CASE_SC_DROPLET3D_PER, (0.265, 0.038, 7.0), 300, fused)
