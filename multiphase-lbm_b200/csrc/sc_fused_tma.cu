@@ -45,11 +45,17 @@ CLBM_D void mbar_wait(uint64_t *bar, uint32_t parity)
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-CLBM_D void tma_load_4d(void *dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2, int c3)
+CLBM_D double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+CLBM_D void tma_load_4d(uint32_t dst, const CUtensorMap *tmap, uint64_t *bar, int c0, int c1, int c2, int c3)
 {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+        ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
 struct OutTable { double *out[19]; };
@@ -76,7 +82,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
 {
     using C = TmaCfg<TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *stage[2] = {reinterpret_cast<double *>(smem_raw), reinterpret_cast<double *>(smem_raw + C::STAGE_BYTES)};
+    const uint32_t stage_a = smem_u32(smem_raw);   // shared-window address of stage 0 (stage 1 follows)
     double (*ring)[C::SY][C::SZ] = reinterpret_cast<double (*)[C::SY][C::SZ]>(smem_raw + 2 * C::STAGE_BYTES);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * C::STAGE_BYTES + C::RING_BYTES);
 
@@ -117,13 +123,13 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     auto xs_of = [&](int r) { return g.wx(xa - 1 + r) + G; };   // storage plane
     auto issue = [&](int r) {
         mbar_expect_tx(&mbar[r & 1], (uint32_t)(C::BOX * 8));
-        tma_load_4d(stage[r & 1], &tmap, &mbar[r & 1], z0 - 2, y0 - 1, xs_of(r), 0);
+        tma_load_4d(stage_a + (r & 1) * C::STAGE_BYTES, &tmap, &mbar[r & 1], z0 - 2, y0 - 1, xs_of(r), 0);
     };
     double psn = 0.0;
     bool gpn = true;
     // psi of plane r (tile + halo ring) from its staged box into the ring; keeps the own psi / G1 branch
     auto make_psi = [&](int r, uint8_t fl_own, uint8_t fl_halo) {
-        const double *st = stage[r & 1];
+        const uint32_t st = stage_a + (r & 1) * C::STAGE_BYTES;
         if (inside) {
             double v = -1.0;
             psn = 0.0;
@@ -131,7 +137,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
             if (fl_own != CELL_BB) {
                 double f[19];
 #pragma unroll
-                for (int k = 0; k < 19; ++k) f[k] = st[k * (C::SY * C::BZ) + own_s];
+                for (int k = 0; k < 19; ++k) f[k] = lds_f64(st + (k * (C::SY * C::BZ) + own_s) * 8);
                 psn = sc_psi_g1(mp, Mom<L3>::sum(f), gpn);
                 v = psn;
             }
@@ -147,7 +153,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
                     for (int k = 0; k < 19; ++k) f[k] = fin[(size_t)k * g.ncs + i];
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 19; ++k) f[k] = st[k * (C::SY * C::BZ) + h_s];
+                    for (int k = 0; k < 19; ++k) f[k] = lds_f64(st + (k * (C::SY * C::BZ) + h_s) * 8);
                 }
                 bool gph;
                 v = sc_psi_g1(mp, Mom<L3>::sum(f), gph);
@@ -171,6 +177,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     make_psi(1, fo, fh);
     double psc = psn;
     bool gpc = gpn;
+    flags_of(2, fo, fh);        // the node mask runs one plane ahead of its use so that its latency never shows
     __syncthreads();
     if (tid == 0 && nplanes + 1 >= 2) issue(2);
 
@@ -178,16 +185,17 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     const int ozm = g.wz(z - 1) - z, ozp = g.wz(z + 1) - z;
 
     for (int r = 1; r <= nplanes; ++r) {
-        flags_of(r + 1, fo, fh);
+        const uint8_t fo_now = fo, fh_now = fh;
+        if (r + 2 <= nplanes + 1) flags_of(r + 2, fo, fh);
         mbar_wait(&mbar[(r + 1) & 1], ((r + 1) >> 1) & 1);
-        make_psi(r + 1, fo, fh);
+        make_psi(r + 1, fo_now, fh_now);
 
         // own populations of plane r out of its stage before the stage is recycled
         double fc[19];
         {
-            const double *st = stage[r & 1];
+            const uint32_t st = stage_a + (r & 1) * C::STAGE_BYTES;
 #pragma unroll
-            for (int k = 0; k < 19; ++k) fc[k] = st[k * (C::SY * C::BZ) + own_s];
+            for (int k = 0; k < 19; ++k) fc[k] = lds_f64(st + (k * (C::SY * C::BZ) + own_s) * 8);
         }
         __syncthreads();
         if (tid == 0 && r + 2 <= nplanes + 1) issue(r + 2);
