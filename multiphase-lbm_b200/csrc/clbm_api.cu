@@ -63,7 +63,8 @@ int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, doubl
 int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int sc_psi_all(clbm_ctx *c);
-int sc_collide_all(clbm_ctx *c);
+int sc_psi_boundary(clbm_ctx *c);
+int sc_collide_slab(clbm_ctx *c);
 int hcz2d_phi(clbm_ctx *c);
 int hcz2d_level1(clbm_ctx *c);
 int hcz2d_collide(clbm_ctx *c);
@@ -101,7 +102,7 @@ int model_stage(clbm_ctx *c, int stage)
     int rc = 0;
     const int m = c->prm.model;
     if (stage == 0) {
-        if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = sc_psi_all(c);
+        if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = c->prm.fused ? sc_psi_boundary(c) : sc_psi_all(c);
         else if (m == CLBM_MODEL_HCZ_D2Q9) rc = hcz2d_phi(c);
         else if (m == CLBM_MODEL_HCZ_D3Q19) rc = hcz3d_moments(c);
         else rc = CLBM_EINVAL;
@@ -110,7 +111,7 @@ int model_stage(clbm_ctx *c, int stage)
     }
     if (stage == 1) {
         if ((rc = halo_unpack(c, 0))) return rc;
-        if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = sc_collide_all(c);
+        if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = sc_collide_slab(c);
         else if (m == CLBM_MODEL_HCZ_D2Q9) { if (!(rc = hcz2d_level1(c))) rc = hcz2d_collide(c); }
         else if (m == CLBM_MODEL_HCZ_D3Q19) { if (!(rc = hcz3d_level1(c)) && !(rc = hcz3d_level2(c))) rc = hcz3d_collide(c); }
         else rc = CLBM_EINVAL;

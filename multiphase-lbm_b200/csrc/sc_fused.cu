@@ -36,7 +36,8 @@ template <class L> struct PopTable {
 
 template <class L, int TY, int TZ, int MINB>
 __global__ void __launch_bounds__(TY *TZ, MINB)
-sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, Geom g, ModelParams mp, int xchunk)
+sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const double *__restrict__ psi_g, Geom g,
+                ModelParams mp, int xchunk)
 {
     using C = FusedCfg<L, TY, TZ>;
     __shared__ double psi_s[4][C::SY][C::SZ];
@@ -60,6 +61,25 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, Geom g, M
     // psi (or -1 for a wall) of storage plane xs into ring slot `slot`.  The thread's own populations stay in
     // fk, its own psi / G1 branch in ps / gp (used when that plane is collided one iteration later).
     auto fill = [&](int xs, int slot, double *fk, double &ps, bool &gp) {
+        if (!g.wrapx && (xs < G || xs >= g.nx + G)) {
+            // x-slab mode: ghost plane of the neighbour slab -> psi from the exchanged moment halo, mask from flag[]
+            if (inside) {
+                const int i = xs * plane + yz;
+                psi_s[slot][ty + 1][cz0] = (flag[i] == CELL_BB) ? -1.0 : fabs(psi_g[i]);
+            }
+            for (int h = tid; h < nhalo; h += C::NT) {
+                int sy, sz;
+                if (L::D == 3) {
+                    if (h < nrow) { sy = 0; sz = h; }
+                    else if (h < 2 * nrow) { sy = ty_n + 1; sz = h - nrow; }
+                    else { const int q = h - 2 * nrow; sy = 1 + (q >> 1); sz = (q & 1) ? tz_n + 1 : 0; }
+                } else { sy = h ? ty_n + 1 : 0; sz = 0; }
+                const int yy = g.wy(y0 + sy - 1), zz = (L::D == 3) ? g.wz(z0 + sz - 1) : 0;
+                const int i = xs * plane + yy * nz + zz;
+                psi_s[slot][sy][sz] = (flag[i] == CELL_BB) ? -1.0 : fabs(psi_g[i]);
+            }
+            return;
+        }
         if (inside) {
             const int i = xs * plane + yz;
 #pragma unroll
@@ -160,7 +180,7 @@ static int launch_fused(clbm_ctx *c)
         P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "sc_fused_collide_stream", true);
-    sc_fused_kernel<L, TY, TZ, MINB><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, g, c->mp, xchunk);
+    sc_fused_kernel<L, TY, TZ, MINB><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -168,7 +188,8 @@ static int launch_fused(clbm_ctx *c)
 bool sc_tma_eligible(const clbm_ctx *c);            // sc_fused_tma.cu
 int sc_fused_tma_step(clbm_ctx *c, int variant);
 
-int sc_fused_step(clbm_ctx *c)
+// one fused collide-stream sweep over the local planes; does NOT flip the parity
+int sc_fused_launch(clbm_ctx *c)
 {
     int rc;
     // clbm_params.fused: 1 = default fused kernel, >1 = explicit tile variant (tuning / tests); env overrides
@@ -197,6 +218,12 @@ int sc_fused_step(clbm_ctx *c)
         default: rc = launch_fused<D3Q19, 4, 64, 2>(c); break;
         }
     }
+    return rc;
+}
+
+int sc_fused_step(clbm_ctx *c)
+{
+    int rc = sc_fused_launch(c);
     if (rc) return rc;
     c->parity = 1 - c->parity;
     return 0;

@@ -78,7 +78,7 @@ struct TmaCfg {
 template <int TY, int TZ, int MINB>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, const uint8_t *__restrict__ flag,
-                    const double *__restrict__ fin, Geom g, ModelParams mp, int xchunk)
+                    const double *__restrict__ fin, const double *__restrict__ psi_g, Geom g, ModelParams mp, int xchunk)
 {
     using C = TmaCfg<TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -130,6 +130,15 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     // psi of plane r (tile + halo ring) from its staged box into the ring; keeps the own psi / G1 branch
     auto make_psi = [&](int r, uint8_t fl_own, uint8_t fl_halo) {
         const uint32_t st = stage_a + (r & 1) * C::STAGE_BYTES;
+        const int xg = xa - 1 + r;
+        if (!g.wrapx && (xg < 0 || xg >= g.nx)) {
+            // x-slab mode: planes -1 and nx belong to the neighbour slab; their psi arrived with the moment halo
+            // exchange (|value| = psi, see sc_psi_kernel) and their mask sits in the ghost planes of flag[]
+            const int xs = xg + G;
+            if (inside) ring[r & 3][ty + 1][tz + 1] = (fl_own == CELL_BB) ? -1.0 : fabs(psi_g[xs * plane + yz]);
+            if (h_act) ring[r & 3][hsy][hsz] = (fl_halo == CELL_BB) ? -1.0 : fabs(psi_g[xs * plane + hyz]);
+            return;
+        }
         if (inside) {
             double v = -1.0;
             psn = 0.0;
@@ -288,7 +297,7 @@ static int launch_tma(clbm_ctx *c)
         attr_set = true;
     }
     LaunchScope ls(c, "sc_fused_tma_collide_stream", true);
-    kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], g, c->mp, xchunk);
+    kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], c->fld[0], g, c->mp, xchunk);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -305,9 +314,7 @@ int sc_fused_tma_step(clbm_ctx *c, int variant)
     case 16: rc = launch_tma<8, 32, 1>(c); break;
     default: rc = launch_tma<6, 32, 2>(c); break;
     }
-    if (rc) return rc;
-    c->parity = 1 - c->parity;
-    return 0;
+    return rc;
 }
 
 }  // namespace clbm

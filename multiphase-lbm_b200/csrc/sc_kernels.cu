@@ -118,8 +118,26 @@ template <class L> static int sc_collide_range(clbm_ctx *c, int x0, int x1)
     return 0;
 }
 
-int sc_fused_step(clbm_ctx *c);  // sc_fused.cu
+int sc_fused_step(clbm_ctx *c);    // sc_fused.cu
+int sc_fused_launch(clbm_ctx *c);
+int sc_collide_all(clbm_ctx *c);
 
+// psi of the two boundary planes only (what the neighbours need as moment halo when the fused kernel runs)
+int sc_psi_boundary(clbm_ctx *c)
+{
+    const int nx = c->geo.nx;
+    int rc = c->Q == 9 ? sc_psi_range<D2Q9>(c, 0, 1) : sc_psi_range<D3Q19>(c, 0, 1);
+    if (rc || nx == 1) return rc;
+    return c->Q == 9 ? sc_psi_range<D2Q9>(c, nx - 1, nx) : sc_psi_range<D3Q19>(c, nx - 1, nx);
+}
+// collide + stream of the local planes in slab mode (ghost psi planes already unpacked); no parity flip
+int sc_collide_slab(clbm_ctx *c)
+{
+    if (c->prm.fused) return sc_fused_launch(c);
+    return sc_collide_all(c);
+}
+
+int sc_collide_all(clbm_ctx *c);
 int sc_psi_all(clbm_ctx *c)
 {
     return c->Q == 9 ? sc_psi_range<D2Q9>(c, 0, c->geo.nx) : sc_psi_range<D3Q19>(c, 0, c->geo.nx);

@@ -23,11 +23,14 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("fused", [0, 1, 2])
 @pytest.mark.parametrize("nranks", [2, 3, 4])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_slab_ring_matches_single_slab(name, nranks):
+def test_slab_ring_matches_single_slab(name, nranks, fused):
     mk, case, args, steps = CASES[name]
-    prm = mk().copy(fused=0)
+    if fused and not name.startswith("sc"):
+        pytest.skip("fused kernels exist for the Shan-Chen models only")
+    prm = mk().copy(fused=fused)
     ora = OracleSim(prm).init_case(case, args)
     with pkg.clbm.Lattice(prm) as single:
         single.upload(ora.lattice, ora.flag, 0)
@@ -59,7 +62,7 @@ def test_slab_ring_matches_single_slab(name, nranks):
 def test_slab_device_init_has_consistent_ghost_flags():
     prm = P.sc_params(P.MODEL_SC_D3Q19, 16, 12, 8, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
     args = (0.265, 0.038, 4.0, 5.0)
-    with pkg.clbm.Lattice(prm.copy(fused=0)) as single:
+    with pkg.clbm.Lattice(prm) as single:               # same kernel variant as the slabs: bit-identical
         single.init_case(P.CASE_SC_DROPLET3D, args)
         single.step(30)
         ref = single.in_pops()

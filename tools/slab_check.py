@@ -45,7 +45,7 @@ def main():
         lat.close()
         if rank == 0:
             full = torch.cat(parts, dim=2).cpu().numpy()
-            single = clbm.Lattice(prm.copy(fused=0, device=lr))
+            single = clbm.Lattice(prm.copy(device=lr))    # same kernel variant as the slabs
             single.init_case(case, args)
             single.step(steps)
             ref = single.in_pops()
