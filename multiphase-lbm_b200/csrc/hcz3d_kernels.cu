@@ -243,8 +243,12 @@ int hcz3d_level2(clbm_ctx *c)
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
+bool hcz3d_march_eligible(const clbm_ctx *c);   // hcz3d_march.cu
+int hcz3d_march_collide(clbm_ctx *c);
+
 int hcz3d_collide(clbm_ctx *c)
 {
+    if (c->prm.fused && hcz3d_march_eligible(c)) return hcz3d_march_collide(c);
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "hcz3d_collide_stream", true);
     hcz3d_collide_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],

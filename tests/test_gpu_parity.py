@@ -110,14 +110,16 @@ def test_hcz_rt2d_config2_full_size_100_steps():
     check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy"))
 
 
-def test_hcz_laplace3d_droplet():
+@pytest.mark.parametrize("fused", [0, 1, 2, 3, 4, 5, 6])
+def test_hcz_laplace3d_droplet(fused):
     prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 24, 24, 24, ulb=0.01, N=24, Re=6.0, kappa=5e-4, gravity=0.0)
-    ora, got, pops, _ = run_pair(prm, P.CASE_HCZ_LAPLACE3D, (), 300)
+    ora, got, pops, _ = run_pair(prm, P.CASE_HCZ_LAPLACE3D, (), 300, fused)
     check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy", "uz"))
     assert _cases.rel_linf(pops, ora.in_pops()) < TOL
 
 
-def test_hcz_laplace3d_with_gravity_and_walls():
+@pytest.mark.parametrize("fused", [0, 1])
+def test_hcz_laplace3d_with_gravity_and_walls(fused):
     """exercise the centre-value wall fallback of the 3-D gradients (laplace3D.h:450-455) with a wall slab"""
     prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 16, 20, 12, omega=1.2, kappa=5e-4, gravity=-1e-5)
     ora = OracleSim(prm).init_case(P.CASE_HCZ_LAPLACE3D, ())
@@ -128,7 +130,7 @@ def test_hcz_laplace3d_with_gravity_and_walls():
     ora.flag[wall] = 0
     lat4 = ora.lattice.reshape(2, 2, 19, ne)
     lat4[:, :, :, wall] = 0.0
-    with pkg.clbm.Lattice(prm) as lat:
+    with pkg.clbm.Lattice(prm.copy(fused=fused)) as lat:
         lat.upload(ora.lattice, ora.flag, 0)
         lat.step(60)
         got = lat.fields()
