@@ -65,13 +65,10 @@ int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
 int sc_psi_all(clbm_ctx *c);
 int sc_psi_boundary(clbm_ctx *c);
 int sc_collide_slab(clbm_ctx *c);
-int hcz2d_phi(clbm_ctx *c);
-int hcz2d_level1(clbm_ctx *c);
-int hcz2d_collide(clbm_ctx *c);
+int hcz2d_stage0(clbm_ctx *c);
+int hcz2d_stage1(clbm_ctx *c);
 int hcz3d_moments(clbm_ctx *c);
-int hcz3d_level1(clbm_ctx *c);
-int hcz3d_level2(clbm_ctx *c);
-int hcz3d_collide(clbm_ctx *c);
+int hcz3d_stage1(clbm_ctx *c);
 
 static int model_step(clbm_ctx *c)
 {
@@ -103,7 +100,7 @@ int model_stage(clbm_ctx *c, int stage)
     const int m = c->prm.model;
     if (stage == 0) {
         if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = c->prm.fused ? sc_psi_boundary(c) : sc_psi_all(c);
-        else if (m == CLBM_MODEL_HCZ_D2Q9) rc = hcz2d_phi(c);
+        else if (m == CLBM_MODEL_HCZ_D2Q9) rc = hcz2d_stage0(c);
         else if (m == CLBM_MODEL_HCZ_D3Q19) rc = hcz3d_moments(c);
         else rc = CLBM_EINVAL;
         if (rc) return rc;
@@ -112,8 +109,8 @@ int model_stage(clbm_ctx *c, int stage)
     if (stage == 1) {
         if ((rc = halo_unpack(c, 0))) return rc;
         if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = sc_collide_slab(c);
-        else if (m == CLBM_MODEL_HCZ_D2Q9) { if (!(rc = hcz2d_level1(c))) rc = hcz2d_collide(c); }
-        else if (m == CLBM_MODEL_HCZ_D3Q19) { if (!(rc = hcz3d_level1(c)) && !(rc = hcz3d_level2(c))) rc = hcz3d_collide(c); }
+        else if (m == CLBM_MODEL_HCZ_D2Q9) rc = hcz2d_stage1(c);
+        else if (m == CLBM_MODEL_HCZ_D3Q19) rc = hcz3d_stage1(c);
         else rc = CLBM_EINVAL;
         if (rc) return rc;
         c->parity = 1 - c->parity;   // the freshly written buffer becomes "in"

@@ -1,0 +1,280 @@
+// hcz2d_fused.cu -- He-Chen-Zhang D2Q9 time step as ONE column-marching kernel (PF/apps/rayleighTaylor2D.h).
+//
+// The staged path (hcz2d_kernels.cu) reads f twice and round-trips five scalar fields through HBM
+// (~410 B per lattice update against 289 algorithmic).  Here a CTA owns a segment of the y axis (y is the
+// fastest index, so a warp touches 256 contiguous bytes of every population array) and marches along x:
+//
+//   column x+2 : phi = sum_k f_k, then rho(phi), psi(phi), psi(rho)            -> 5-slot shared-memory rings
+//   column x+1 : lap(phi) with the wall mirror rule (:467-495)                 -> ring
+//   column x   : grad lap phi, grad psi(phi), grad psi(rho), grad rho from the rings (:341-446, :501-529),
+//                velocity (:316-337), total_P (:452-460), collideBgk of f and g (:552-606, rest :642-663),
+//                push stream with half-way bounce-back (:533-549)
+//
+// Every population is fetched from HBM once (the second read of f at collide time is two columns behind its
+// first read and hits L1/L2) and written once; no scalar field leaves the SM.
+//
+// Segments overlap by the stencil reach instead of having dedicated halo threads: a CTA of NT threads covers
+// NT consecutive rows, computes phi on all of them, lap(phi) on rows 1..NT-2 and collides rows 2..NT-3.
+// x-slab mode: phi of the ghost columns (-2,-1,nx,nx+1) comes from the exchanged moment halo (fld[0]).
+//
+// The per-node arithmetic is the staged kernel's, expression by expression, so fused == staged bit for bit.
+#include <cstdlib>
+
+#include "sc_cell.cuh"
+
+namespace clbm {
+
+using L9f = D2Q9;
+
+struct Hcz2dTables {
+    const double *fin[9];
+    const double *gin[9];
+    double *fout[9];
+    double *gout[9];
+};
+
+constexpr int HCZ2D_NS = 5;   // ring slots (columns x-2 .. x+2 are live at once)
+
+// k-th neighbour of ring position p with the mirror rule (a bounce_back neighbour is replaced by the opposite one)
+template <int NT>
+CLBM_D double ring_mirror(const double (*R)[NT], const uint8_t (*FL)[NT], int k, int sm, int s0, int sp, int p)
+{
+    const int slot = L9f::cx(k) < 0 ? sm : (L9f::cx(k) > 0 ? sp : s0);
+    if (FL[slot][p + L9f::cy(k)] == CELL_BB) {
+        const int oslot = L9f::cx(k) < 0 ? sp : (L9f::cx(k) > 0 ? sm : s0);
+        return R[oslot][p - L9f::cy(k)];
+    }
+    return R[slot][p + L9f::cy(k)];
+}
+
+template <int NT>
+CLBM_D void ring_grad(const double (*R)[NT], const uint8_t (*FL)[NT], unsigned wall, int sm, int s0, int sp, int p,
+                      double &gx, double &gy)
+{
+    double ax = 0.0, ay = 0.0;
+    if (wall == 0u) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (k == L9f::REST) continue;
+            const int slot = L9f::cx(k) < 0 ? sm : (L9f::cx(k) > 0 ? sp : s0);
+            const double v = R[slot][p + L9f::cy(k)];
+            if (L9f::cx(k)) ax += L9f::t(k) * L9f::cx(k) * v;
+            if (L9f::cy(k)) ay += L9f::t(k) * L9f::cy(k) * v;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (k == L9f::REST) continue;
+            const double v = ring_mirror<NT>(R, FL, k, sm, s0, sp, p);
+            if (L9f::cx(k)) ax += L9f::t(k) * L9f::cx(k) * v;
+            if (L9f::cy(k)) ay += L9f::t(k) * L9f::cy(k) * v;
+        }
+    }
+    gx = 3.0 * ax;
+    gy = 3.0 * ay;
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const double *__restrict__ phi_g, Geom g,
+                   ModelParams mp, int xchunk)
+{
+    constexpr int NS = HCZ2D_NS;
+    __shared__ double r_phi[NS][NT], r_rho[NS][NT], r_pp[NS][NT], r_pr[NS][NT], r_lap[NS][NT];
+    __shared__ uint8_t r_fl[NS][NT];
+
+    const int tid = threadIdx.x;
+    const int ny = g.ny, G = g.G;
+    const int yy = (int)blockIdx.x * (NT - 4) - 2 + tid;   // unwrapped row of this thread
+    const int yw = g.wy(yy);
+    const bool has_phi = yy <= ny + 1;
+    const bool has_lap = tid >= 1 && tid < NT - 1 && yy <= ny;
+    const bool own = tid >= 2 && tid < NT - 2 && yy < ny;
+    const int xa = blockIdx.y * xchunk;
+    const int xb = min(g.nx, xa + xchunk);
+
+    auto slot_of = [](int xg) { return (xg + 2 * NS) % NS; };
+    auto col_of = [&](int xg) { return (g.wx(xg) + G) * ny + yw; };   // storage index of (xg, this row)
+    auto is_ghost = [&](int xg) { return !g.wrapx && (xg < 0 || xg >= g.nx); };
+
+    // phi (and the scalars that depend on phi alone) of column xg into the rings
+    auto put_phi = [&](int xg, double phi, uint8_t fl) {
+        const int s = slot_of(xg);
+        const double rho = mp.rho_g + ((phi - mp.phi_g) / (mp.phi_l - mp.phi_g)) * (mp.rho_l - mp.rho_g);
+        r_phi[s][tid] = phi;
+        r_rho[s][tid] = rho;
+        r_pp[s][tid] = hcz_psi(phi, mp.a, mp.b);
+        r_pr[s][tid] = hcz_psi(rho, mp.a, mp.b);
+        r_fl[s][tid] = fl;
+    };
+    auto load_f = [&](int xg, double *f) {
+        const int i = col_of(xg);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) f[k] = P.fin[k][i];
+    };
+    auto fill_direct = [&](int xg) {
+        if (!has_phi) return;
+        const int i = col_of(xg);
+        if (is_ghost(xg)) { put_phi(xg, phi_g[i], flag[i]); return; }
+        double f[9];
+        load_f(xg, f);
+        put_phi(xg, Mom<L9f>::sum(f), flag[i]);
+    };
+    auto make_lap = [&](int xg) {
+        if (!has_lap) return;
+        const int s0 = slot_of(xg), sm = slot_of(xg - 1), sp = slot_of(xg + 1);
+        double sum = 0.0;
+        if (r_fl[s0][tid] == CELL_BULK) {
+            const double phi_c = r_phi[s0][tid];
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (k != L9f::REST) sum += L9f::t(k) * (ring_mirror<NT>(r_phi, r_fl, k, sm, s0, sp, tid) - phi_c);
+        }
+        r_lap[s0][tid] = 6.0 * sum;
+    };
+
+    // ---- prologue: phi of columns xa-2 .. xa+1, lap of columns xa-1, xa ----
+    fill_direct(xa - 2);
+    fill_direct(xa - 1);
+    fill_direct(xa);
+    fill_direct(xa + 1);
+    double fn[9];
+    uint8_t fln = CELL_BB;
+    bool ghost_n = is_ghost(xa + 2);
+    if (has_phi && !ghost_n) { load_f(xa + 2, fn); fln = flag[col_of(xa + 2)]; }
+    __syncthreads();
+    make_lap(xa - 1);
+    make_lap(xa);
+
+    const double omega = mp.omega, hw = 1. - 0.5 * omega;
+    const int oym = (g.wy(yy - 1) - yy), oyp = (g.wy(yy + 1) - yy);
+
+    for (int x = xa; x < xb; ++x) {
+        // 1. column x+2: phi from the prefetched populations (or the exchanged ghost field)
+        if (has_phi) {
+            if (ghost_n) { const int i = col_of(x + 2); put_phi(x + 2, phi_g[i], flag[i]); }
+            else put_phi(x + 2, Mom<L9f>::sum(fn), fln);
+        }
+        // prefetch column x+3 for the next iteration
+        ghost_n = is_ghost(x + 3);
+        if (x + 1 < xb && has_phi && !ghost_n) { load_f(x + 3, fn); fln = flag[col_of(x + 3)]; }
+        __syncthreads();
+        // 2. column x+1: lap(phi)
+        make_lap(x + 1);
+        __syncthreads();
+        // 3. column x: collide + push
+        const int s0 = slot_of(x), sm = slot_of(x - 1), sp = slot_of(x + 1);
+        if (!own || r_fl[s0][tid] != CELL_BULK) continue;
+
+        const int i = (x + G) * ny + yy;
+        double f[9], gg[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { gg[k] = P.gin[k][i]; f[k] = P.fin[k][i]; }
+
+        unsigned wall = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            if (k == 4) continue;
+            const int slot = L9f::cx(k) < 0 ? sm : (L9f::cx(k) > 0 ? sp : s0);
+            if (r_fl[slot][tid + L9f::cy(k)] == CELL_BB) wall |= 1u << k;
+        }
+        double glx, gly, grx, gry, Ex, Ey, gpx, gpy;
+        ring_grad<NT>(r_lap, r_fl, wall, sm, s0, sp, tid, glx, gly);
+        ring_grad<NT>(r_rho, r_fl, wall, sm, s0, sp, tid, grx, gry);
+        ring_grad<NT>(r_pr, r_fl, wall, sm, s0, sp, tid, Ex, Ey);
+        ring_grad<NT>(r_pp, r_fl, wall, sm, s0, sp, tid, gpx, gpy);
+
+        const double phi = r_phi[s0][tid], rho = r_rho[s0][tid];
+        double jx, jy, jz;
+        Mom<L9f>::first(gg, jx, jy, jz);
+        const double Pt = Mom<L9f>::sum(gg);
+        double forcex = mp.kappa * rho * glx;
+        double forcey = mp.kappa * rho * gly;
+        forcey += mp.gravity * rho;
+        const double u0 = (jx + forcex / 6.0) / (rho / 3.0);
+        const double u1 = (jy + forcey / 6.0) / (rho / 3.0);
+        const double Pp = Pt - 0.5 * (u0 * -grx / 3. + u1 * -gry / 3.);
+        const double usqr = 1.5 * (u0 * u0 + u1 * u1);
+        const double inv_phi = 1.0 / phi;
+
+        const int xp = g.wx(x + 1), xm = g.wx(x - 1);
+        const int oxm = (xm - x) * ny, oxp = (xp - x) * ny;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            double pf, pg;
+            if (k == 4) {
+                const double eqf0 = phi * L9f::t(4) * (1. - usqr);
+                const double eqg0 = L9f::t(4) * (Pp - (rho / 3.0) * usqr);
+                const double fg0 = hw * (-(u0 * forcex + u1 * forcey) * eqf0 * inv_phi +
+                                         ((u0 * -Ex + u1 * -Ey) * (eqf0 * inv_phi - L9f::t(4))));
+                const double ff0 = hw * (-3.0 * (u0 * -gpx + u1 * -gpy) * eqf0 * inv_phi);
+                pf = (1 - omega) * f[4] + omega * eqf0 + ff0;
+                pg = (1 - omega) * gg[4] + omega * eqg0 + fg0;
+                P.fout[4][i] = pf;
+                P.gout[4][i] = pg;
+                continue;
+            }
+            const double ck_u = L9f::cx(k) * u0 + L9f::cy(k) * u1;
+            const double poly = 3 * ck_u + 4.5 * ck_u * ck_u - usqr;
+            const double eqf = phi * L9f::t(k) * (1 + poly);
+            const double eqg = L9f::t(k) * (Pp + (rho / 3.0) * poly);
+            const double e_u_x = L9f::cx(k) - u0, e_u_y = L9f::cy(k) - u1;
+            const double fg = hw * ((e_u_x * forcex + e_u_y * forcey) * eqf * inv_phi) +
+                              hw * ((e_u_x * -Ex) + (e_u_y * -Ey)) * (eqf * inv_phi - L9f::t(k));
+            const double ff = hw * ((e_u_x * -gpx) + (e_u_y * -gpy)) * 3.0 * eqf * inv_phi;
+            pf = (1. - omega) * f[k] + omega * eqf + ff;
+            pg = (1. - omega) * gg[k] + omega * eqg + fg;
+            if (wall & (1u << k)) {
+                P.fout[L9f::opp(k)][i] = pf;
+                P.gout[L9f::opp(k)][i] = pg;
+            } else {
+                const int off = (L9f::cx(k) < 0 ? oxm : (L9f::cx(k) > 0 ? oxp : 0)) + (L9f::cy(k) < 0 ? oym : (L9f::cy(k) > 0 ? oyp : 0));
+                P.fout[k][i + off] = pf;
+                P.gout[k][i + off] = pg;
+            }
+        }
+    }
+}
+
+template <int NT, int MINB>
+static int launch_hcz2d_fused(clbm_ctx *c)
+{
+    const Geom &g = c->geo;
+    const int segs = (g.ny + (NT - 4) - 1) / (NT - 4);
+    int xchunk = g.nx;
+    const long long want = 4LL * 148 * MINB;
+    if ((long long)segs < want) {
+        const long long nch = (want + segs - 1) / segs;
+        xchunk = (int)((g.nx + nch - 1) / nch);
+        if (xchunk < 16) xchunk = g.nx < 16 ? g.nx : 16;
+    }
+    if (const char *e = getenv("CLBM_HCZ2D_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+    dim3 grid(segs, (g.nx + xchunk - 1) / xchunk);
+    Hcz2dTables P;
+    for (int k = 0; k < 9; ++k) {
+        P.fin[k] = c->pop[0][c->parity] + (size_t)k * g.ncs;
+        P.gin[k] = c->pop[1][c->parity] + (size_t)k * g.ncs;
+        P.fout[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+        P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
+    }
+    LaunchScope ls(c, "hcz2d_fused_collide_stream", true);
+    hcz2d_fused_kernel<NT, MINB><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool hcz2d_fused_eligible(const clbm_ctx *c) { return c->geo.ny >= 4 && c->geo.ncs < (1LL << 31); }
+
+int hcz2d_fused_launch(clbm_ctx *c)
+{
+    int variant = c->prm.fused > 1 ? c->prm.fused : 0;
+    if (const char *e = getenv("CLBM_HCZ2D_TILE")) variant = atoi(e);
+    switch (variant) {
+    case 2: return launch_hcz2d_fused<64, 8>(c);
+    case 3: return launch_hcz2d_fused<192, 2>(c);
+    case 4: return launch_hcz2d_fused<128, 3>(c);
+    default: return launch_hcz2d_fused<128, 4>(c);
+    }
+}
+
+}  // namespace clbm

@@ -249,9 +249,38 @@ int hcz2d_collide(clbm_ctx *c)
     return 0;
 }
 
+bool hcz2d_fused_eligible(const clbm_ctx *c);   // hcz2d_fused.cu
+int hcz2d_fused_launch(clbm_ctx *c);
+
+// slab protocol halves (clbm_step_stage): stage 0 makes the phi planes the neighbours need, stage 1 collides
+int hcz2d_stage0(clbm_ctx *c)
+{
+    const Geom &g = c->geo;
+    if (!(c->prm.fused && hcz2d_fused_eligible(c)) || g.nx < 4) return hcz2d_phi(c);
+    // fused path: only the two boundary columns on each side leave the SMs (the moment halo of depth 2)
+    for (int side = 0; side < 2; ++side) {
+        const int x0 = side ? g.nx - 2 : 0;
+        LaunchScope ls(c, "hcz2d_phi_boundary");
+        hcz2d_phi_kernel<<<grid_for(2 * g.plane, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->fld[0], g, x0, 2 * g.plane);
+        CLBM_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+int hcz2d_stage1(clbm_ctx *c)
+{
+    if (c->prm.fused && hcz2d_fused_eligible(c)) return hcz2d_fused_launch(c);
+    int rc = hcz2d_level1(c);
+    return rc ? rc : hcz2d_collide(c);
+}
+
 int hcz2d_step(clbm_ctx *c)
 {
     int rc;
+    if (c->prm.fused && hcz2d_fused_eligible(c)) {
+        if ((rc = hcz2d_fused_launch(c))) return rc;
+        c->parity = 1 - c->parity;
+        return 0;
+    }
     if ((rc = hcz2d_phi(c))) return rc;
     if ((rc = hcz2d_level1(c))) return rc;
     if ((rc = hcz2d_collide(c))) return rc;
@@ -262,9 +291,8 @@ int hcz2d_step(clbm_ctx *c)
 int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz)
 {
     int rc;
-    if (!c->multi) {  // slab mode: the caller ran stage 0 + exchange, so phi ghosts are valid already
-        if ((rc = hcz2d_phi(c))) return rc;
-    }
+    // phi of the local columns; in slab mode the caller ran stage 0 + exchange, so the phi ghosts are valid already
+    if ((rc = hcz2d_phi(c))) return rc;
     if ((rc = hcz2d_level1(c))) return rc;
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "hcz2d_fields");

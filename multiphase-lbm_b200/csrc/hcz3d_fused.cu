@@ -1,0 +1,382 @@
+// hcz3d_fused.cu -- HCZ D3Q19 (PF/apps/laplace3D.h): levels 1-3 and the collide/stream sweep in ONE plane-marching
+// kernel with TMA-staged populations (sm_100a).
+//
+// The step is two launches: hcz3d_moments_kernel (phi, P_term, raw g momentum: 304 B read + 40 B written per
+// node) and this kernel.  A CTA owns a TY x TZ (y,z) tile and marches along x.  Per iteration (collide plane x):
+//
+//   S1  phi, node mask of plane x+3 on the tile + halo 3          -> r_phi, r_fl rings   (prefetched one plane ahead)
+//   S2  lap(phi) (:370-393, wall neighbours skipped) and psi(phi) (:268-275) of plane x+2 on tile + halo 2
+//   S3  plane x+1 on tile + halo 1: grad lap(phi), grad psi(phi) (:435-536, wall -> centre value), velocity with the
+//       forcey-in-z quirk (:280-312), total_P (:318-328), psi_rho = total_P - rho/3 (:330-336)   -> r_pr ring;
+//       the owning thread keeps u, P, F, grad psi(phi) of its cell in registers for the collision one plane later
+//   S4  plane x: grad psi_rho from the ring, collideBgk of the 2 x 19 populations (:562-624, rest :664-677),
+//       push stream with half-way bounce-back (:539-559)
+//
+// The 38 populations of the tile's plane arrive by two cp.async.bulk.tensor (TMA) boxes [19][TY][TZ] per plane into a
+// two-stage shared-memory pipeline (mbarrier expect_tx/complete_tx), issued two planes ahead, so HBM latency is off
+// the instruction stream and no scalar field other than the five moments round-trips through HBM.
+// Traffic per node: 304 (moments pass) + ~45 (moment fields incl. halo re-reads, L2) + 608 (populations in/out).
+#include <cstdlib>
+
+#include "sc_cell.cuh"
+#include "tma.cuh"
+
+namespace clbm {
+
+using L19f = D3Q19;
+
+struct Hcz3dOut {
+    double *fout[19];
+    double *gout[19];
+};
+struct Hcz3dMom { const double *phi, *pt, *jx, *jy, *jz; };
+
+template <int TY, int TZ>
+struct Hcz3dCfg {
+    static constexpr int NT = TY * TZ;
+    static constexpr int Y3 = TY + 6, Z3 = TZ + 6, R3 = Y3 * Z3;   // tile + halo 3
+    static constexpr int Y2 = TY + 4, Z2 = TZ + 4, R2 = Y2 * Z2;   // tile + halo 2
+    static constexpr int Y1 = TY + 2, Z1 = TZ + 2;                 // tile + halo 1
+    static constexpr int NH1 = 2 * Z1 + 2 * TY;                    // cells of the halo-1 ring
+    static constexpr int N3 = (R3 + NT - 1) / NT;                  // S1 cells per thread
+    static constexpr int N2 = (R2 + NT - 1) / NT;                  // S2 cells per thread
+    static constexpr int SET_BYTES = 19 * NT * 8;
+    static constexpr int STAGE_BYTES = 2 * SET_BYTES;
+    static constexpr int OFF_PHI = 2 * STAGE_BYTES;
+    static constexpr int OFF_LAP = OFF_PHI + 4 * R3 * 8;
+    static constexpr int OFF_PP = OFF_LAP + 4 * R2 * 8;
+    static constexpr int OFF_PR = OFF_PP + 4 * R2 * 8;
+    static constexpr int OFF_FL = OFF_PR + 4 * Y1 * Z1 * 8;
+    static constexpr int OFF_BAR = ((OFF_FL + 8 * R3 + 15) / 16) * 16;
+    static constexpr int SMEM = OFF_BAR + 32;
+    static_assert(NH1 <= NT, "one halo-1 cell per thread");
+    static_assert(TZ % 2 == 0, "TMA rows must be a multiple of 16 bytes");
+    static_assert(SET_BYTES % 128 == 0, "stage alignment");
+};
+
+// 3 * sum_k t_k c_k X(nb), a bounce_back neighbour contributing the centre value; R is a ring of planes with row
+// length ZR, (a, b) the node's position in it
+template <int ZR>
+CLBM_D void grad19(const double *Rm, const double *R0, const double *Rp, int a, int b, unsigned wall, double g[3])
+{
+    const double xc = R0[a * ZR + b];
+    double gx = 0.0, gy = 0.0, gz = 0.0;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+        if (k == L19f::REST) continue;
+        const double *R = L19f::cx(k) < 0 ? Rm : (L19f::cx(k) > 0 ? Rp : R0);
+        double v = R[(a + L19f::cy(k)) * ZR + (b + L19f::cz(k))];
+        if (wall & (1u << k)) v = xc;
+        if (L19f::cx(k)) gx += L19f::t(k) * L19f::cx(k) * v;
+        if (L19f::cy(k)) gy += L19f::t(k) * L19f::cy(k) * v;
+        if (L19f::cz(k)) gz += L19f::t(k) * L19f::cz(k) * v;
+    }
+    g[0] = 3.0 * gx;
+    g[1] = 3.0 * gy;
+    g[2] = 3.0 * gz;
+}
+
+// bit k set: the k-th neighbour of (a, b) (halo-3 ring coordinates) is a bounce_back node
+template <int ZR>
+CLBM_D unsigned wall19(const uint8_t *Fm, const uint8_t *F0, const uint8_t *Fp, int a, int b)
+{
+    unsigned wall = 0;
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+        if (k == L19f::REST) continue;
+        const uint8_t *F = L19f::cx(k) < 0 ? Fm : (L19f::cx(k) > 0 ? Fp : F0);
+        if (F[(a + L19f::cy(k)) * ZR + (b + L19f::cz(k))] == CELL_BB) wall |= 1u << k;
+    }
+    return wall;
+}
+
+// what the collision of a node needs from level 2 (kept in registers by the owning thread)
+struct Hcz3dLocal {
+    double phi, rho, Fx, Fy, Fz, gp[3], u0, u1, u2, Pt;
+};
+
+template <int TY, int TZ>
+__global__ void __launch_bounds__(TY *TZ, 1)
+hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_g, const Hcz3dOut P,
+                   const Hcz3dMom M, const uint8_t *__restrict__ flag, Geom g, ModelParams mp, int xchunk)
+{
+    using C = Hcz3dCfg<TY, TZ>;
+    constexpr int NT = C::NT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t stage_a = smem_u32(smem_raw);
+    double *r_phi = reinterpret_cast<double *>(smem_raw + C::OFF_PHI);   // [4][Y3][Z3]
+    double *r_lap = reinterpret_cast<double *>(smem_raw + C::OFF_LAP);   // [4][Y2][Z2]
+    double *r_pp = reinterpret_cast<double *>(smem_raw + C::OFF_PP);     // [4][Y2][Z2]
+    double *r_pr = reinterpret_cast<double *>(smem_raw + C::OFF_PR);     // [4][Y1][Z1]
+    uint8_t *r_fl = smem_raw + C::OFF_FL;                                // [8][Y3][Z3]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
+
+    const int tid = threadIdx.x;
+    const int tz = tid % TZ, ty = tid / TZ;
+    const int y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
+    const int y = y0 + ty, z = z0 + tz;
+    const bool inside = (y < g.ny) && (z < g.nz);
+    const int xa = blockIdx.z * xchunk;
+    const int xb = min(g.nx, xa + xchunk);
+    const int plane = (int)g.plane, nz = g.nz, ny = g.ny, G = g.G;
+    const int yz = y * nz + z;
+    auto wrap = [](int v, int n) { v %= n; return v < 0 ? v + n : v; };
+    const int yz_w = wrap(y, ny) * nz + wrap(z, nz);   // periodic image of the own cell (ragged edge tiles)
+    auto xs_of = [&](int xg) { return g.wx(xg) + G; };   // storage plane of slab plane xg
+
+    // S1 cells of this thread (halo-3 region, row-major), as in-plane lattice offsets
+    int c3_yz[C::N3];
+#pragma unroll
+    for (int j = 0; j < C::N3; ++j) {
+        const int h = tid + j * NT;
+        const int sy = h / C::Z3, sz = h % C::Z3;
+        c3_yz[j] = (h < C::R3) ? wrap(y0 + sy - 3, ny) * nz + wrap(z0 + sz - 3, nz) : -1;
+    }
+    // halo-1 ring cell of this thread (S3), in halo-1 coordinates
+    const bool h_act = tid < C::NH1;
+    int h1y = 0, h1z = 0;
+    if (h_act) {
+        if (tid < C::Z1) { h1y = 0; h1z = tid; }
+        else if (tid < 2 * C::Z1) { h1y = C::Y1 - 1; h1z = tid - C::Z1; }
+        else { const int q = tid - 2 * C::Z1; h1y = 1 + (q >> 1); h1z = (q & 1) ? C::Z1 - 1 : 0; }
+    }
+    const int h1_yz = wrap(y0 + h1y - 1, ny) * nz + wrap(z0 + h1z - 1, nz);
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int x) {   // populations of plane x (both sets) into stage (x - xa) & 1
+        const int s = (x - xa) & 1;
+        mbar_expect_tx(&mbar[s], (uint32_t)C::STAGE_BYTES);
+        tma_load_4d(stage_a + s * C::STAGE_BYTES, &tmap_f, &mbar[s], z0, y0, x + G, 0);
+        tma_load_4d(stage_a + s * C::STAGE_BYTES + C::SET_BYTES, &tmap_g, &mbar[s], z0, y0, x + G, 0);
+    };
+    if (tid == 0) {
+        issue(xa);
+        if (xa + 1 < xb) issue(xa + 1);
+    }
+
+    // registers that run one plane ahead of their use
+    double phi_n[C::N3];
+    uint8_t fl_n[C::N3];
+    auto load_phi = [&](int xg) {
+        const int base = xs_of(xg) * plane;
+#pragma unroll
+        for (int j = 0; j < C::N3; ++j)
+            if (c3_yz[j] >= 0) { phi_n[j] = M.phi[base + c3_yz[j]]; fl_n[j] = flag[base + c3_yz[j]]; }
+    };
+    double mo_n[4] = {0., 0., 0., 0.}, mh_n[4] = {0., 0., 0., 0.}, mo_c[4], mh_c[4];
+    auto load_mom = [&](int xg) {
+        const int base = xs_of(xg) * plane;
+        mo_n[0] = M.pt[base + yz_w]; mo_n[1] = M.jx[base + yz_w]; mo_n[2] = M.jy[base + yz_w]; mo_n[3] = M.jz[base + yz_w];
+        if (h_act) { mh_n[0] = M.pt[base + h1_yz]; mh_n[1] = M.jx[base + h1_yz]; mh_n[2] = M.jy[base + h1_yz]; mh_n[3] = M.jz[base + h1_yz]; }
+    };
+
+    // level 2 of the node at halo-1 position (a1, b1) of plane p; stores psi_rho, returns the node's local set
+    auto level2 = [&](int p, int a1, int b1, const double *mo, Hcz3dLocal &o) {
+        const int a3 = a1 + 2, b3 = b1 + 2, a2 = a1 + 1, b2 = b1 + 1;
+        const uint8_t *Fm = r_fl + ((p - 1) & 7) * C::R3, *F0 = r_fl + (p & 7) * C::R3, *Fp = r_fl + ((p + 1) & 7) * C::R3;
+        const unsigned wall = wall19<C::Z3>(Fm, F0, Fp, a3, b3);
+        const int sm = ((p - 1) & 3) * C::R2, s0 = (p & 3) * C::R2, sp = ((p + 1) & 3) * C::R2;
+        double gl[3];
+        grad19<C::Z2>(r_lap + sm, r_lap + s0, r_lap + sp, a2, b2, wall, gl);
+        grad19<C::Z2>(r_pp + sm, r_pp + s0, r_pp + sp, a2, b2, wall, o.gp);
+        o.phi = r_phi[(p & 3) * C::R3 + a3 * C::Z3 + b3];
+        o.rho = mp.rho_g + ((o.phi - mp.phi_g) / (mp.phi_l - mp.phi_g)) * (mp.rho_l - mp.rho_g);
+        o.Fx = mp.kappa * o.phi * gl[0];
+        o.Fy = mp.kappa * o.phi * gl[1] + mp.gravity * o.rho;
+        o.Fz = mp.kappa * o.phi * gl[2];
+        const double inv_d = 3.0 / o.rho;          // 1 / (rho/3)
+        o.u0 = (mo[1] + o.Fx / 6.) * inv_d;
+        o.u1 = (mo[2] + o.Fy / 6.) * inv_d;
+        o.u2 = (mo[3] + o.Fy / 6.) * inv_d;        // sic: forcey (laplace3D.h:304)
+        o.Pt = mo[0] - 0.5 * (o.u0 * o.gp[0] + o.u1 * o.gp[1] + o.u2 * o.gp[2]);
+        r_pr[(p & 3) * (C::Y1 * C::Z1) + a1 * C::Z1 + b1] = o.Pt - o.rho / 3.0;
+    };
+
+    const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
+    const int ozm = g.wz(z - 1) - z, ozp = g.wz(z + 1) - z;
+    const double omega = mp.omega, om1 = 1. - omega, hw = 1. - 0.5 * omega;
+
+    Hcz3dLocal cur, nxt;
+    cur.phi = cur.rho = 1.0; cur.Fx = cur.Fy = cur.Fz = 0.0; cur.gp[0] = cur.gp[1] = cur.gp[2] = 0.0;
+    cur.u0 = cur.u1 = cur.u2 = cur.Pt = 0.0;
+    nxt = cur;
+
+    load_phi(xa - 3);
+    // x = plane being collided; the first six iterations only fill the pipeline (x < xa)
+    for (int x = xa - 6; x < xb; ++x) {
+        // ---- S1: phi / mask of plane x+3 from the registers, then prefetch the next plane's ----
+        {
+            double *dst = r_phi + ((x + 3) & 3) * C::R3;
+            uint8_t *dfl = r_fl + ((x + 3) & 7) * C::R3;
+#pragma unroll
+            for (int j = 0; j < C::N3; ++j)
+                if (c3_yz[j] >= 0) { dst[tid + j * NT] = phi_n[j]; dfl[tid + j * NT] = fl_n[j]; }
+        }
+        if (x + 1 < xb) load_phi(x + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { mo_c[j] = mo_n[j]; mh_c[j] = mh_n[j]; }
+        if (x + 2 >= xa - 1 && x + 1 < xb) load_mom(x + 2);   // consumed by S3 of the next iteration
+        __syncthreads();
+        if (tid == 0 && x - 1 >= xa && x + 1 < xb) issue(x + 1);   // stage of plane x-1 is free now
+
+        // ---- S2: lap(phi), psi(phi) of plane x+2 on tile + halo 2 ----
+        if (x + 2 >= xa - 2) {
+            const int p = x + 2;
+            const double *Pm = r_phi + ((p - 1) & 3) * C::R3, *P0 = r_phi + (p & 3) * C::R3, *Pp = r_phi + ((p + 1) & 3) * C::R3;
+            const uint8_t *Fm = r_fl + ((p - 1) & 7) * C::R3, *F0 = r_fl + (p & 7) * C::R3, *Fp = r_fl + ((p + 1) & 7) * C::R3;
+#pragma unroll
+            for (int j = 0; j < C::N2; ++j) {
+                const int h = tid + j * NT;
+                if (h >= C::R2) break;
+                const int a2 = h / C::Z2, b2 = h % C::Z2, a3 = a2 + 1, b3 = b2 + 1;
+                const double phi_c = P0[a3 * C::Z3 + b3];
+                double sum = 0.0;
+#pragma unroll
+                for (int k = 0; k < 19; ++k) {
+                    if (k == L19f::REST) continue;
+                    const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
+                    const uint8_t *F = L19f::cx(k) < 0 ? Fm : (L19f::cx(k) > 0 ? Fp : F0);
+                    const int q = (a3 + L19f::cy(k)) * C::Z3 + (b3 + L19f::cz(k));
+                    if (F[q] != CELL_BB) sum += L19f::t(k) * (R[q] - phi_c);
+                }
+                r_lap[(p & 3) * C::R2 + h] = 6.0 * sum;
+                r_pp[(p & 3) * C::R2 + h] = hcz_psi(phi_c, mp.a, mp.b);
+            }
+        }
+        __syncthreads();
+
+        // ---- S3: level 2 of plane x+1 on tile + halo 1 ----
+        if (x + 1 >= xa - 1) {
+            level2(x + 1, ty + 1, tz + 1, mo_c, nxt);   // also the periodic images in a ragged edge tile
+            if (h_act) { Hcz3dLocal tmp; level2(x + 1, h1y, h1z, mh_c, tmp); }
+        }
+        __syncthreads();
+
+        // ---- S4: collide + push plane x ----
+        if (x >= xa) {
+            const int r = x - xa;
+            mbar_wait(&mbar[r & 1], (r >> 1) & 1);
+            const uint8_t *Fm = r_fl + ((x - 1) & 7) * C::R3, *F0 = r_fl + (x & 7) * C::R3, *Fp = r_fl + ((x + 1) & 7) * C::R3;
+            if (inside && F0[(ty + 3) * C::Z3 + tz + 3] == CELL_BULK) {
+                const unsigned wall = wall19<C::Z3>(Fm, F0, Fp, ty + 3, tz + 3);
+                constexpr int R1 = C::Y1 * C::Z1;
+                double ge[3];
+                grad19<C::Z1>(r_pr + ((x - 1) & 3) * R1, r_pr + (x & 3) * R1, r_pr + ((x + 1) & 3) * R1, ty + 1, tz + 1, wall, ge);
+
+                const double phi = cur.phi, rho = cur.rho, Fx = cur.Fx, Fy = cur.Fy, Fz = cur.Fz;
+                const double u0 = cur.u0, u1 = cur.u1, u2 = cur.u2, Pt = cur.Pt;
+                const double usqr = 1.5 * (u0 * u0 + u1 * u1 + u2 * u2);
+                // (e_k - u).V = c_k.V - u.V for the three forcing vectors V = F, -E, -grad psi(phi)
+                const double uF = u0 * Fx + u1 * Fy + u2 * Fz;
+                const double uE = u0 * ge[0] + u1 * ge[1] + u2 * ge[2];
+                const double uG = u0 * cur.gp[0] + u1 * cur.gp[1] + u2 * cur.gp[2];
+                const double rho3 = rho / 3.0;
+                const double ffs = hw * 3.0 * phi / rho;   // ff = hw * C * 3 * eqf / rho,  eqf = phi * Gamma
+                const int xp = g.wx(x + 1), xm = g.wx(x - 1);
+                const int i = (x + G) * plane + yz;
+                const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
+                const uint32_t st = stage_a + (r & 1) * C::STAGE_BYTES + tid * 8;
+#pragma unroll
+                for (int k = 0; k < 19; ++k) {
+                    const double fk = lds_f64(st + k * (NT * 8));
+                    const double gk = lds_f64(st + C::SET_BYTES + k * (NT * 8));
+                    const double t = L19f::t(k);
+                    double pf, pg;
+                    if (k == 9) {
+                        const double Gam = t * (1. - usqr);                   // eqf0 / phi
+                        const double eqg0 = t * (Pt - rho3 * usqr);
+                        const double fg0 = hw * (-uF * Gam + uE * (Gam - t));
+                        const double ff0 = ffs * uG * Gam;
+                        pf = om1 * fk + omega * phi * Gam + ff0;
+                        pg = om1 * gk + omega * eqg0 + fg0;
+                        P.fout[k][i] = pf;
+                        P.gout[k][i] = pg;
+                        continue;
+                    }
+                    const double cu = L19f::cx(k) * u0 + L19f::cy(k) * u1 + L19f::cz(k) * u2;
+                    const double poly = 3. * cu + 4.5 * cu * cu - usqr;
+                    const double Gam = t * (1. + poly);                       // eqf / phi
+                    const double eqg = t * (Pt + rho3 * poly);
+                    const double cF = L19f::cx(k) * Fx + L19f::cy(k) * Fy + L19f::cz(k) * Fz;
+                    const double cE = L19f::cx(k) * ge[0] + L19f::cy(k) * ge[1] + L19f::cz(k) * ge[2];
+                    const double cG = L19f::cx(k) * cur.gp[0] + L19f::cy(k) * cur.gp[1] + L19f::cz(k) * cur.gp[2];
+                    const double fg = hw * ((cF - uF) * Gam - (cE - uE) * (Gam - t));
+                    const double ff = -ffs * (cG - uG) * Gam;
+                    pf = om1 * fk + omega * phi * Gam + ff;
+                    pg = om1 * gk + omega * eqg + fg;
+                    const int off = (L19f::cx(k) < 0 ? oxm : (L19f::cx(k) > 0 ? oxp : 0)) + (L19f::cy(k) < 0 ? oym : (L19f::cy(k) > 0 ? oyp : 0)) +
+                                    (L19f::cz(k) < 0 ? ozm : (L19f::cz(k) > 0 ? ozp : 0));
+                    if (wall & (1u << k)) { P.fout[L19f::opp(k)][i] = pf; P.gout[L19f::opp(k)][i] = pg; }
+                    else { P.fout[k][i + off] = pf; P.gout[k][i + off] = pg; }
+                }
+            }
+        }
+        cur = nxt;
+    }
+}
+
+bool hcz3d_fused_eligible(const clbm_ctx *c)
+{
+    const Geom &g = c->geo;
+    return (g.nz % 2 == 0) && g.nx >= 4 && g.ny >= 4 && g.nz >= 4 && g.ncs < (1LL << 31) && get_encode() != nullptr;
+}
+
+template <int TY, int TZ>
+static int launch_hcz3d_fused(clbm_ctx *c)
+{
+    using C = Hcz3dCfg<TY, TZ>;
+    const Geom &g = c->geo;
+    CUtensorMap tm[2];
+    const cuuint64_t dims[4] = {(cuuint64_t)g.nz, (cuuint64_t)g.ny, (cuuint64_t)(g.nx + 2 * g.G), 19};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.nz * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.ncs * 8};
+    const cuuint32_t box[4] = {(cuuint32_t)TZ, (cuuint32_t)TY, 1, 19};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int s = 0; s < 2; ++s) {
+        CUresult r = get_encode()(&tm[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)c->pop[s][c->parity], dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
+    }
+    const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
+    int xchunk = g.nx;
+    const long long want = 4LL * 148;
+    if ((long long)tiles < want) {
+        const long long nch = (want + tiles - 1) / tiles;
+        xchunk = (int)((g.nx + nch - 1) / nch);
+        if (xchunk < 32) xchunk = g.nx < 32 ? g.nx : 32;
+    }
+    if (const char *e = getenv("CLBM_HCZ_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+    dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
+    Hcz3dOut P;
+    for (int k = 0; k < 19; ++k) {
+        P.fout[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+        P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
+    }
+    const Hcz3dMom M = {c->fld[0], c->fld[1], c->fld[2], c->fld[3], c->fld[4]};
+    auto kern = hcz3d_fused_kernel<TY, TZ>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        attr_set = true;
+    }
+    LaunchScope ls(c, "hcz3d_fused_collide_stream", true);
+    kern<<<grid, C::NT, C::SMEM, c->stream>>>(tm[0], tm[1], P, M, c->flag, g, c->mp, xchunk);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int hcz3d_fused_launch(clbm_ctx *c, int variant)
+{
+    switch (variant) {
+    case 8: return launch_hcz3d_fused<16, 16>(c);
+    case 9: return launch_hcz3d_fused<4, 64>(c);
+    default: return launch_hcz3d_fused<8, 32>(c);
+    }
+}
+
+}  // namespace clbm

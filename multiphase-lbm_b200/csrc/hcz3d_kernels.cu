@@ -12,6 +12,8 @@
 //                                   push stream (:539-559)
 // Wall fallback of the gradients: a bounce_back neighbour contributes the CENTRE value (:450-455).
 // Field slots: 0 phi, 1 P_term, 2-4 raw momentum, 5 lap phi, 6 psi(phi), 7 psi_rho
+#include <cstdlib>
+
 #include "sc_cell.cuh"
 
 namespace clbm {
@@ -246,6 +248,32 @@ int hcz3d_level2(clbm_ctx *c)
 bool hcz3d_march_eligible(const clbm_ctx *c);   // hcz3d_march.cu
 int hcz3d_march_collide(clbm_ctx *c);
 
+int hcz3d_collide(clbm_ctx *c);
+bool hcz3d_fused_eligible(const clbm_ctx *c);   // hcz3d_fused.cu
+int hcz3d_fused_launch(clbm_ctx *c, int variant);
+
+// fused == 1 or >= 7: levels 1-3 + collide in one TMA-staged kernel; 2..6: march kernel tile variants
+static bool use_fused3d(const clbm_ctx *c)
+{
+    int v = c->prm.fused;
+    if (const char *e = getenv("CLBM_HCZ_TILE")) v = atoi(e);
+    return (v == 1 || v >= 7) && hcz3d_fused_eligible(c);
+}
+
+// everything after the moments: stage 1 of the slab protocol
+int hcz3d_stage1(clbm_ctx *c)
+{
+    if (use_fused3d(c)) {
+        int v = c->prm.fused;
+        if (const char *e = getenv("CLBM_HCZ_TILE")) v = atoi(e);
+        return hcz3d_fused_launch(c, v);
+    }
+    int rc;
+    if ((rc = hcz3d_level1(c))) return rc;
+    if ((rc = hcz3d_level2(c))) return rc;
+    return hcz3d_collide(c);
+}
+
 int hcz3d_collide(clbm_ctx *c)
 {
     if (c->prm.fused && hcz3d_march_eligible(c)) return hcz3d_march_collide(c);
@@ -262,9 +290,7 @@ int hcz3d_step(clbm_ctx *c)
 {
     int rc;
     if ((rc = hcz3d_moments(c))) return rc;
-    if ((rc = hcz3d_level1(c))) return rc;
-    if ((rc = hcz3d_level2(c))) return rc;
-    if ((rc = hcz3d_collide(c))) return rc;
+    if ((rc = hcz3d_stage1(c))) return rc;
     c->parity = 1 - c->parity;
     return 0;
 }

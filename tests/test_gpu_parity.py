@@ -103,6 +103,16 @@ def test_hcz_rt2d_1000_steps():
     assert _cases.rel_linf(pops, ora.in_pops()) < TOL
 
 
+@pytest.mark.parametrize("fused", [0, 1, 2, 3, 4])
+def test_hcz_rt2d_fused_variants(fused):
+    """every y-segment width of the column-marching kernel, with several segments and a ragged last one"""
+    prm = P.hcz_params(P.MODEL_HCZ_D2Q9, 40, 330, N=40)
+    ora, got, pops, flags = run_pair(prm, P.CASE_HCZ_RT2D, (), 200, fused)
+    np.testing.assert_array_equal(flags, ora.flag)
+    check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy"))
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+
+
 def test_hcz_rt2d_config2_full_size_100_steps():
     """config 2 at its full size 256x1026 (the oracle needs ~seconds for 100 steps)"""
     prm = P.hcz_params(P.MODEL_HCZ_D2Q9, 256, 1026, N=256)
@@ -110,7 +120,7 @@ def test_hcz_rt2d_config2_full_size_100_steps():
     check_fields(ora.fields(), got, ("s0", "s1", "s2", "ux", "uy"))
 
 
-@pytest.mark.parametrize("fused", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("fused", [0, 1, 2, 3, 4, 5, 6, 8, 9])
 def test_hcz_laplace3d_droplet(fused):
     prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 24, 24, 24, ulb=0.01, N=24, Re=6.0, kappa=5e-4, gravity=0.0)
     ora, got, pops, _ = run_pair(prm, P.CASE_HCZ_LAPLACE3D, (), 300, fused)
@@ -118,7 +128,7 @@ def test_hcz_laplace3d_droplet(fused):
     assert _cases.rel_linf(pops, ora.in_pops()) < TOL
 
 
-@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("fused", [0, 1, 2, 8, 9])
 def test_hcz_laplace3d_with_gravity_and_walls(fused):
     """exercise the centre-value wall fallback of the 3-D gradients (laplace3D.h:450-455) with a wall slab"""
     prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 16, 20, 12, omega=1.2, kappa=5e-4, gravity=-1e-5)

@@ -28,8 +28,6 @@ CASES = {
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_slab_ring_matches_single_slab(name, nranks, fused):
     mk, case, args, steps = CASES[name]
-    if fused and name == "hcz2d_rt":
-        pytest.skip("no fused kernel for HCZ D2Q9 yet")
     prm = mk().copy(fused=fused)
     ora = OracleSim(prm).init_case(case, args)
     with pkg.clbm.Lattice(prm) as single:
