@@ -56,17 +56,17 @@ struct Hcz3dCfg {
 
 // 3 * sum_k t_k c_k X(nb), a bounce_back neighbour contributing the centre value; R is a ring of planes with row
 // length ZR, (a, b) the node's position in it
-template <int ZR>
-CLBM_D void grad19(const double *Rm, const double *R0, const double *Rp, int a, int b, unsigned wall, double g[3])
+template <int ZR, bool WALLS>
+CLBM_D void grad19(const double *Rm, const double *R0, const double *Rp, int q, unsigned wall, double g[3])
 {
-    const double xc = R0[a * ZR + b];
+    const double xc = WALLS ? R0[q] : 0.0;
     double gx = 0.0, gy = 0.0, gz = 0.0;
 #pragma unroll
     for (int k = 0; k < 19; ++k) {
         if (k == L19f::REST) continue;
         const double *R = L19f::cx(k) < 0 ? Rm : (L19f::cx(k) > 0 ? Rp : R0);
-        double v = R[(a + L19f::cy(k)) * ZR + (b + L19f::cz(k))];
-        if (wall & (1u << k)) v = xc;
+        double v = R[q + L19f::cy(k) * ZR + L19f::cz(k)];
+        if (WALLS && (wall & (1u << k))) v = xc;
         if (L19f::cx(k)) gx += L19f::t(k) * L19f::cx(k) * v;
         if (L19f::cy(k)) gy += L19f::t(k) * L19f::cy(k) * v;
         if (L19f::cz(k)) gz += L19f::t(k) * L19f::cz(k) * v;
@@ -78,14 +78,14 @@ CLBM_D void grad19(const double *Rm, const double *R0, const double *Rp, int a, 
 
 // bit k set: the k-th neighbour of (a, b) (halo-3 ring coordinates) is a bounce_back node
 template <int ZR>
-CLBM_D unsigned wall19(const uint8_t *Fm, const uint8_t *F0, const uint8_t *Fp, int a, int b)
+CLBM_D unsigned wall19(const uint8_t *Fm, const uint8_t *F0, const uint8_t *Fp, int q)
 {
     unsigned wall = 0;
 #pragma unroll
     for (int k = 0; k < 19; ++k) {
         if (k == L19f::REST) continue;
         const uint8_t *F = L19f::cx(k) < 0 ? Fm : (L19f::cx(k) > 0 ? Fp : F0);
-        if (F[(a + L19f::cy(k)) * ZR + (b + L19f::cz(k))] == CELL_BB) wall |= 1u << k;
+        if (F[q + L19f::cy(k) * ZR + L19f::cz(k)] == CELL_BB) wall |= 1u << k;
     }
     return wall;
 }
@@ -176,15 +176,20 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     };
 
     // level 2 of the node at halo-1 position (a1, b1) of plane p; stores psi_rho, returns the node's local set
-    auto level2 = [&](int p, int a1, int b1, const double *mo, Hcz3dLocal &o) {
-        const int a3 = a1 + 2, b3 = b1 + 2, a2 = a1 + 1, b2 = b1 + 1;
-        const uint8_t *Fm = r_fl + ((p - 1) & 7) * C::R3, *F0 = r_fl + (p & 7) * C::R3, *Fp = r_fl + ((p + 1) & 7) * C::R3;
-        const unsigned wall = wall19<C::Z3>(Fm, F0, Fp, a3, b3);
+    auto level2 = [&](int p, int a1, int b1, const double *mo, Hcz3dLocal &o, bool walls) {
+        const int q3 = (a1 + 2) * C::Z3 + (b1 + 2), q2 = (a1 + 1) * C::Z2 + (b1 + 1);
         const int sm = ((p - 1) & 3) * C::R2, s0 = (p & 3) * C::R2, sp = ((p + 1) & 3) * C::R2;
         double gl[3];
-        grad19<C::Z2>(r_lap + sm, r_lap + s0, r_lap + sp, a2, b2, wall, gl);
-        grad19<C::Z2>(r_pp + sm, r_pp + s0, r_pp + sp, a2, b2, wall, o.gp);
-        o.phi = r_phi[(p & 3) * C::R3 + a3 * C::Z3 + b3];
+        if (walls) {
+            const uint8_t *Fm = r_fl + ((p - 1) & 7) * C::R3, *F0 = r_fl + (p & 7) * C::R3, *Fp = r_fl + ((p + 1) & 7) * C::R3;
+            const unsigned wall = wall19<C::Z3>(Fm, F0, Fp, q3);
+            grad19<C::Z2, true>(r_lap + sm, r_lap + s0, r_lap + sp, q2, wall, gl);
+            grad19<C::Z2, true>(r_pp + sm, r_pp + s0, r_pp + sp, q2, wall, o.gp);
+        } else {
+            grad19<C::Z2, false>(r_lap + sm, r_lap + s0, r_lap + sp, q2, 0u, gl);
+            grad19<C::Z2, false>(r_pp + sm, r_pp + s0, r_pp + sp, q2, 0u, o.gp);
+        }
+        o.phi = r_phi[(p & 3) * C::R3 + q3];
         o.rho = mp.rho_g + ((o.phi - mp.phi_g) / (mp.phi_l - mp.phi_g)) * (mp.rho_l - mp.rho_g);
         o.Fx = mp.kappa * o.phi * gl[0];
         o.Fy = mp.kappa * o.phi * gl[1] + mp.gravity * o.rho;
@@ -206,22 +211,38 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     cur.u0 = cur.u1 = cur.u2 = cur.Pt = 0.0;
     nxt = cur;
 
+    // S2 cells of this thread as ring offsets (halo-3 / halo-2 coordinates)
+    int c2_q3[C::N2], c2_q2[C::N2];
+#pragma unroll
+    for (int j = 0; j < C::N2; ++j) {
+        const int h = tid + j * NT;
+        const int a2 = h / C::Z2, b2 = h % C::Z2;
+        c2_q2[j] = (h < C::R2) ? h : -1;
+        c2_q3[j] = (a2 + 1) * C::Z3 + (b2 + 1);
+    }
+    unsigned wmask = 0;   // bit (p & 7): plane p has a bounce_back node inside this CTA's window (CTA-uniform)
+
     load_phi(xa - 3);
     // x = plane being collided; the first six iterations only fill the pipeline (x < xa)
     for (int x = xa - 6; x < xb; ++x) {
         // ---- S1: phi / mask of plane x+3 from the registers, then prefetch the next plane's ----
+        int anyw = 0;
         {
             double *dst = r_phi + ((x + 3) & 3) * C::R3;
             uint8_t *dfl = r_fl + ((x + 3) & 7) * C::R3;
 #pragma unroll
             for (int j = 0; j < C::N3; ++j)
-                if (c3_yz[j] >= 0) { dst[tid + j * NT] = phi_n[j]; dfl[tid + j * NT] = fl_n[j]; }
+                if (c3_yz[j] >= 0) { dst[tid + j * NT] = phi_n[j]; dfl[tid + j * NT] = fl_n[j]; anyw |= (fl_n[j] == CELL_BB); }
         }
         if (x + 1 < xb) load_phi(x + 4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { mo_c[j] = mo_n[j]; mh_c[j] = mh_n[j]; }
         if (x + 2 >= xa - 1 && x + 1 < xb) load_mom(x + 2);   // consumed by S3 of the next iteration
-        __syncthreads();
+        {
+            const unsigned bit = 1u << ((x + 3) & 7);
+            wmask = __syncthreads_or(anyw) ? (wmask | bit) : (wmask & ~bit);
+        }
+        auto walls_near = [&](int p) { return (wmask & ((1u << ((p - 1) & 7)) | (1u << (p & 7)) | (1u << ((p + 1) & 7)))) != 0u; };
         if (tid == 0 && x - 1 >= xa && x + 1 < xb) issue(x + 1);   // stage of plane x-1 is free now
 
         // ---- S2: lap(phi), psi(phi) of plane x+2 on tile + halo 2 ----
@@ -229,31 +250,41 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             const int p = x + 2;
             const double *Pm = r_phi + ((p - 1) & 3) * C::R3, *P0 = r_phi + (p & 3) * C::R3, *Pp = r_phi + ((p + 1) & 3) * C::R3;
             const uint8_t *Fm = r_fl + ((p - 1) & 7) * C::R3, *F0 = r_fl + (p & 7) * C::R3, *Fp = r_fl + ((p + 1) & 7) * C::R3;
+            const bool walls = walls_near(p);
 #pragma unroll
             for (int j = 0; j < C::N2; ++j) {
-                const int h = tid + j * NT;
-                if (h >= C::R2) break;
-                const int a2 = h / C::Z2, b2 = h % C::Z2, a3 = a2 + 1, b3 = b2 + 1;
-                const double phi_c = P0[a3 * C::Z3 + b3];
+                if (c2_q2[j] < 0) continue;
+                const int q3 = c2_q3[j];
+                const double phi_c = P0[q3];
                 double sum = 0.0;
+                if (walls) {
 #pragma unroll
-                for (int k = 0; k < 19; ++k) {
-                    if (k == L19f::REST) continue;
-                    const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
-                    const uint8_t *F = L19f::cx(k) < 0 ? Fm : (L19f::cx(k) > 0 ? Fp : F0);
-                    const int q = (a3 + L19f::cy(k)) * C::Z3 + (b3 + L19f::cz(k));
-                    if (F[q] != CELL_BB) sum += L19f::t(k) * (R[q] - phi_c);
+                    for (int k = 0; k < 19; ++k) {
+                        if (k == L19f::REST) continue;
+                        const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
+                        const uint8_t *F = L19f::cx(k) < 0 ? Fm : (L19f::cx(k) > 0 ? Fp : F0);
+                        const int q = q3 + L19f::cy(k) * C::Z3 + L19f::cz(k);
+                        if (F[q] != CELL_BB) sum += L19f::t(k) * (R[q] - phi_c);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 19; ++k) {
+                        if (k == L19f::REST) continue;
+                        const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
+                        sum += L19f::t(k) * (R[q3 + L19f::cy(k) * C::Z3 + L19f::cz(k)] - phi_c);
+                    }
                 }
-                r_lap[(p & 3) * C::R2 + h] = 6.0 * sum;
-                r_pp[(p & 3) * C::R2 + h] = hcz_psi(phi_c, mp.a, mp.b);
+                r_lap[(p & 3) * C::R2 + c2_q2[j]] = 6.0 * sum;
+                r_pp[(p & 3) * C::R2 + c2_q2[j]] = hcz_psi(phi_c, mp.a, mp.b);
             }
         }
         __syncthreads();
 
         // ---- S3: level 2 of plane x+1 on tile + halo 1 ----
         if (x + 1 >= xa - 1) {
-            level2(x + 1, ty + 1, tz + 1, mo_c, nxt);   // also the periodic images in a ragged edge tile
-            if (h_act) { Hcz3dLocal tmp; level2(x + 1, h1y, h1z, mh_c, tmp); }
+            const bool walls = walls_near(x + 1);
+            level2(x + 1, ty + 1, tz + 1, mo_c, nxt, walls);   // also the periodic images in a ragged edge tile
+            if (h_act) { Hcz3dLocal tmp; level2(x + 1, h1y, h1z, mh_c, tmp, walls); }
         }
         __syncthreads();
 
@@ -263,10 +294,16 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             mbar_wait(&mbar[r & 1], (r >> 1) & 1);
             const uint8_t *Fm = r_fl + ((x - 1) & 7) * C::R3, *F0 = r_fl + (x & 7) * C::R3, *Fp = r_fl + ((x + 1) & 7) * C::R3;
             if (inside && F0[(ty + 3) * C::Z3 + tz + 3] == CELL_BULK) {
-                const unsigned wall = wall19<C::Z3>(Fm, F0, Fp, ty + 3, tz + 3);
                 constexpr int R1 = C::Y1 * C::Z1;
+                const int q1 = (ty + 1) * C::Z1 + tz + 1;
+                unsigned wall = 0;
                 double ge[3];
-                grad19<C::Z1>(r_pr + ((x - 1) & 3) * R1, r_pr + (x & 3) * R1, r_pr + ((x + 1) & 3) * R1, ty + 1, tz + 1, wall, ge);
+                if (walls_near(x)) {
+                    wall = wall19<C::Z3>(Fm, F0, Fp, (ty + 3) * C::Z3 + tz + 3);
+                    grad19<C::Z1, true>(r_pr + ((x - 1) & 3) * R1, r_pr + (x & 3) * R1, r_pr + ((x + 1) & 3) * R1, q1, wall, ge);
+                } else {
+                    grad19<C::Z1, false>(r_pr + ((x - 1) & 3) * R1, r_pr + (x & 3) * R1, r_pr + ((x + 1) & 3) * R1, q1, 0u, ge);
+                }
 
                 const double phi = cur.phi, rho = cur.rho, Fx = cur.Fx, Fy = cur.Fy, Fz = cur.Fz;
                 const double u0 = cur.u0, u1 = cur.u1, u2 = cur.u2, Pt = cur.Pt;

@@ -94,3 +94,58 @@ def ref_binary(name):
     """path of a prebuilt reference-harness binary (oracle/_ref), or None"""
     path = os.path.join(REF_DIR, name)
     return path if os.path.exists(path) else None
+
+
+class PulsatileOracle:
+    """oracle/pulsatile_oracle.c: CPU restatement of AB/apps/PulsatileBloodFlow2D.h (test infrastructure)."""
+
+    def __init__(self, N=64, tau=0.75, alpha=0.01, p0_in=0.20, p0_out=0.19, is_severed=1, deformable=1):
+        L = lib()
+        L.pulsatile_create.restype = ctypes.c_void_p
+        L.pulsatile_create.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_int, ctypes.c_int]
+        L.pulsatile_lattice.restype = ctypes.POINTER(ctypes.c_double)
+        for f in ("pulsatile_step", "pulsatile_get", "pulsatile_destroy", "pulsatile_nx", "pulsatile_ny",
+                  "pulsatile_parity", "pulsatile_tf", "pulsatile_fresh", "pulsatile_lattice"):
+            getattr(L, f).argtypes = None
+        self.h = ctypes.c_void_p(L.pulsatile_create(N, tau, alpha, p0_in, p0_out, is_severed, deformable))
+        if not self.h:
+            raise RuntimeError("Initial wall location out of bounds.")
+        self.nx, self.ny = L.pulsatile_nx(self.h), L.pulsatile_ny(self.h)
+        self.nelem = self.nx * self.ny
+        self.tf = L.pulsatile_tf(self.h)
+
+    def step(self, n=1):
+        lib().pulsatile_step(self.h, int(n))
+        return self
+
+    def fields(self):
+        ne = self.nelem
+        out = {"P": np.zeros(ne), "Ux": np.zeros(ne), "Uy": np.zeros(ne), "flag": np.zeros(ne, dtype=np.uint8),
+               "yr1": np.zeros(self.nx), "yr2": np.zeros(self.nx)}
+        lib().pulsatile_get(self.h, _dptr(out["P"]), _dptr(out["Ux"]), _dptr(out["Uy"]),
+                            out["flag"].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _dptr(out["yr1"]), _dptr(out["yr2"]))
+        return out
+
+    def lattice(self):
+        return np.ctypeslib.as_array(lib().pulsatile_lattice(self.h), shape=(2 * 9 * self.nelem,)).copy()
+
+    @property
+    def parity(self):
+        return lib().pulsatile_parity(self.h)
+
+    def close(self):
+        if self.h:
+            lib().pulsatile_destroy(self.h)
+            self.h = None
+
+
+def pulsatile_write_vtk(nx, ny, P, Ux, Uy, flag, time_iter, path):
+    """the reference's legacy-VTK text (AB/apps/PulsatileBloodFlow2D.h:680-706) of the given arrays"""
+    L = lib()
+    L.pulsatile_write_vtk.argtypes = None
+    rc = L.pulsatile_write_vtk(int(nx), int(ny), _dptr(np.ascontiguousarray(P)), _dptr(np.ascontiguousarray(Ux)),
+                               _dptr(np.ascontiguousarray(Uy)),
+                               np.ascontiguousarray(flag).ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), int(time_iter),
+                               path.encode())
+    assert rc == 0
