@@ -29,7 +29,20 @@ P = pkg.params
 
 
 def golden_names(prefix=""):
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith(prefix))
+    """multiphase fixtures (clbm_oracle.c); the Pulsatile fixtures have their own loader (pulsatile_golden_names)"""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN)
+                  if f.endswith(".npz") and f.startswith(prefix) and not f.startswith("pulsatile_"))
+
+
+def pulsatile_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("pulsatile_"))
+
+
+def load_pulsatile_golden(name):
+    """-> (npz, N, dump steps, keyword arguments of the run)"""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(bytes(z["params"]).decode())
+    return z, meta["N"], meta["dumps"], meta["kw"]
 
 
 def load_golden(name):
