@@ -165,6 +165,57 @@ int  clbm_step_stage(clbm_ctx *ctx, int stage);
 /* raw stream handle (cudaStream_t) so the caller can order its copies after ours */
 void *clbm_stream(clbm_ctx *ctx);
 
+/* ---- compliant-vessel case (CLBM_MODEL_PULSATILE) ---------------------------------------------------
+ * Replaces the whole iteration body of PulsatileBloodFlow2D() ("Abbashub LBM/apps/PulsatileBloodFlow2D.h":764-790):
+ *     for_each(par_unseq, lattice, lattice + nelem, lbm);   // MRT_Collision           :533-541, :672-676
+ *     lbm.Boundary_Conditions();                            // Bouzidi_quadratic x2     :543-601
+ *     lbm.Streaming();                                      // in-place pull            :603-616
+ *     lbm.Inlet_ZouHe(t); lbm.Outlet_ZouHe(t);              //                          :618-669
+ *     lbm.Macroscopic_Properties_g();                       //                          :216-230
+ *     if (deformable) lbm.Calculate_Pressure_and_Move_Walls(t);  // + Fobj / border / fresh nodes  :233-498
+ *     *parity = 1 - *parity;
+ * The functor there owns P, Ux, Uy, yr1, yr2, Fobj and the border lists besides lattice/flag/parity, so this
+ * model has its own context type.  Host arrays use the reference layout: lattice[p*9*nelem + k*nelem + i],
+ * i = y + ny*x, nx = 1 + 10*(N-2), ny = N; flag uint8 {0 bounce_back, 1 bulk}.  Results are bit-identical to the
+ * reference's (the device code is built without FMA contraction).                                            */
+typedef struct clbm_pulsatile clbm_pulsatile;
+typedef struct clbm_pulsatile_params {
+    int32_t abi_version;    /* CLBM_ABI_VERSION */
+    int32_t N;              /* ny = N, nx = 1 + 10*(N-2)  (AB:721-722) */
+    int32_t device;         /* CUDA device ordinal, -1 = current */
+    int32_t is_severed;     /* AB:105, :153-155, :741 */
+    int32_t deformable;     /* AB:104, :740 */
+    int32_t t_beat;         /* <= 0: max(1, nx)  (AB:749) */
+    double tau;             /* s8 = 1/tau, s5 = 1  (AB:99-102, :742-744) */
+    double alpha;           /* wall compliance  (AB:106, :745) */
+    double p0_in, p0_out;   /* AB:746-747 (both 0: 0.20 / 0.19; severed: 0.02 / 0) */
+} clbm_pulsatile_params;
+
+/* Setup_Simulation_Parameters, Initialize_Yr_and_Vw_and_p, Initialize_Fobj_for_Vessel_Walls,
+ * Find_or_Update_Boundary_Nodes, Initialize_P_U_g (AB:751-757), state resident on the device.
+ * CLBM_EINVAL with "Initial wall location out of bounds." where the reference throws runtime_error (AB:181). */
+int  clbm_pulsatile_create(const clbm_pulsatile_params *params, clbm_pulsatile **out);
+int  clbm_pulsatile_destroy(clbm_pulsatile *ctx);
+/* nx, ny, tf = t_beat + 2*t_propagation (AB:759), iterations done, current parity; any pointer may be NULL */
+int  clbm_pulsatile_info(const clbm_pulsatile *ctx, int *nx, int *ny, int *tf, int *t_iter, int *parity);
+/* nsteps iterations of the loop body above (asynchronous; sync/download report device-side failures) */
+int  clbm_pulsatile_step(clbm_pulsatile *ctx, int nsteps);
+int  clbm_pulsatile_step_timed(clbm_pulsatile *ctx, int nsteps, float *ms);
+int  clbm_pulsatile_sync(clbm_pulsatile *ctx);
+int64_t clbm_pulsatile_launch_count(const clbm_pulsatile *ctx);
+/* device time per iteration (event pair around the kernels of each of the first cap_steps iterations) */
+int  clbm_pulsatile_kernel_timing_begin(clbm_pulsatile *ctx, int cap_steps);
+int  clbm_pulsatile_kernel_timing_end(clbm_pulsatile *ctx, float *avg_ms, int *count);
+/* the functor's stored fields (what saveVtkFields_PulsatileBloodFlow2D prints, AB:680-706) and the wall positions */
+int  clbm_pulsatile_download_fields(clbm_pulsatile *ctx, double *P, double *Ux, double *Uy, uint8_t *flag,
+                                    double *yr1, double *yr2);
+/* both lattice buffers (2*9*nelem doubles) and the parity */
+int  clbm_pulsatile_download_lattice(clbm_pulsatile *ctx, double *lattice, int *parity);
+/* hand over a host state built by the reference's own set-up code (both buffers, all functor fields) */
+int  clbm_pulsatile_upload(clbm_pulsatile *ctx, const double *lattice, const uint8_t *flag, const double *P,
+                           const double *Ux, const double *Uy, const double *yr1, const double *yr2,
+                           int parity, int t_iter);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,10 @@ EXPORTS = [
     "clbm_download_fields", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
     "clbm_stream", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
+    "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
+    "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
+    "clbm_pulsatile_kernel_timing_begin", "clbm_pulsatile_kernel_timing_end", "clbm_pulsatile_download_fields",
+    "clbm_pulsatile_download_lattice", "clbm_pulsatile_upload",
 ]
 
 _lib = None
@@ -65,6 +69,20 @@ def load_library(path=None):
     lib.clbm_free_host.argtypes = [vp]
     lib.clbm_stream.argtypes = [vp]
     lib.clbm_stream.restype = vp
+    ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
+    lib.clbm_pulsatile_create.argtypes = [ctypes.POINTER(P.PulsatileParams), ctypes.POINTER(vp)]
+    lib.clbm_pulsatile_destroy.argtypes = [vp]
+    lib.clbm_pulsatile_info.argtypes = [vp, ip, ip, ip, ip, ip]
+    lib.clbm_pulsatile_step.argtypes = [vp, ctypes.c_int]
+    lib.clbm_pulsatile_step_timed.argtypes = [vp, ctypes.c_int, fp]
+    lib.clbm_pulsatile_sync.argtypes = [vp]
+    lib.clbm_pulsatile_launch_count.argtypes = [vp]
+    lib.clbm_pulsatile_launch_count.restype = ctypes.c_int64
+    lib.clbm_pulsatile_kernel_timing_begin.argtypes = [vp, ctypes.c_int]
+    lib.clbm_pulsatile_kernel_timing_end.argtypes = [vp, fp, ip]
+    lib.clbm_pulsatile_download_fields.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.clbm_pulsatile_download_lattice.argtypes = [vp, vp, ip]
+    lib.clbm_pulsatile_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
     for name in EXPORTS:
         getattr(lib, name)  # every declared symbol must resolve
     _lib = lib
@@ -239,3 +257,93 @@ class PinnedArray:
             self.free()
         except Exception:
             pass
+
+
+class Pulsatile:
+    """Device-resident compliant-vessel case: the counterpart of `LBM_PulsatileBloodFlow2D` and its arrays
+    (AB/apps/PulsatileBloodFlow2D.h); `step(n)` is n iterations of the reference loop body :764-790."""
+
+    def __init__(self, N=64, tau=0.75, alpha=0.01, p0_in=0.20, p0_out=0.19, is_severed=1, deformable=1, device=-1):
+        self.lib = load_library()
+        self.p = P.pulsatile_params(N, tau, alpha, p0_in, p0_out, is_severed, deformable, device)
+        h = ctypes.c_void_p()
+        self._h = None
+        self._check(self.lib.clbm_pulsatile_create(ctypes.byref(self.p), ctypes.byref(h)))
+        self._h = h
+        v = [ctypes.c_int() for _ in range(3)]
+        self._check(self.lib.clbm_pulsatile_info(self._h, ctypes.byref(v[0]), ctypes.byref(v[1]), ctypes.byref(v[2]), None, None))
+        self.nx, self.ny, self.tf = (x.value for x in v)
+        self.nelem = self.nx * self.ny
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ClbmError("clbm error %d: %s" % (rc, self.lib.clbm_last_error().decode()))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.clbm_pulsatile_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, n=1):
+        self._check(self.lib.clbm_pulsatile_step(self._h, int(n)))
+        return self
+
+    def step_timed(self, n):
+        ms = ctypes.c_float()
+        self._check(self.lib.clbm_pulsatile_step_timed(self._h, int(n), ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._check(self.lib.clbm_pulsatile_sync(self._h))
+
+    def launch_count(self):
+        return int(self.lib.clbm_pulsatile_launch_count(self._h))
+
+    def kernel_timing_begin(self, cap):
+        self._check(self.lib.clbm_pulsatile_kernel_timing_begin(self._h, int(cap)))
+
+    def kernel_timing_end(self):
+        ms, n = ctypes.c_float(), ctypes.c_int()
+        self._check(self.lib.clbm_pulsatile_kernel_timing_end(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def parity(self):
+        v = ctypes.c_int()
+        self._check(self.lib.clbm_pulsatile_info(self._h, None, None, None, None, ctypes.byref(v)))
+        return v.value
+
+    @property
+    def t_iter(self):
+        v = ctypes.c_int()
+        self._check(self.lib.clbm_pulsatile_info(self._h, None, None, None, ctypes.byref(v), None))
+        return v.value
+
+    def fields(self, out=None):
+        ne = self.nelem
+        o = out or {"P": np.empty(ne), "Ux": np.empty(ne), "Uy": np.empty(ne), "flag": np.empty(ne, dtype=np.uint8),
+                    "yr1": np.empty(self.nx), "yr2": np.empty(self.nx)}
+        self._check(self.lib.clbm_pulsatile_download_fields(self._h, *[_ptr(o.get(k)) for k in ("P", "Ux", "Uy", "flag", "yr1", "yr2")]))
+        return o
+
+    def lattice(self):
+        a = np.empty(2 * 9 * self.nelem)
+        par = ctypes.c_int()
+        self._check(self.lib.clbm_pulsatile_download_lattice(self._h, _ptr(a), ctypes.byref(par)))
+        return a, par.value
+
+    def upload(self, lattice, flag, Pf, Ux, Uy, yr1, yr2, parity, t_iter):
+        self._check(self.lib.clbm_pulsatile_upload(self._h, _ptr(lattice), _ptr(flag), _ptr(Pf), _ptr(Ux), _ptr(Uy), _ptr(yr1),
+                                                   _ptr(yr2), int(parity), int(t_iter)))

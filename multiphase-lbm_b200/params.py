@@ -100,3 +100,26 @@ def hcz_params(model, nx, ny, nz=1, *, omega=None, ulb=0.04, N=None, Re=3000.0, 
         omega = lb_parameters(ulb, N if N else nx, Re)[1]
     return make_params(model, nx, ny, nz, omega=omega, phi_l=phi_l, phi_g=phi_g, rho_l=rho_l, rho_g=rho_g,
                        a=a, b=b, kappa=kappa, gravity=gravity, **kw)
+
+
+class PulsatileParams(ctypes.Structure):
+    """clbm_pulsatile_params mirror (include/clbm.h): the user-set members of LBM_PulsatileBloodFlow2D
+    (AB/apps/PulsatileBloodFlow2D.h:740-749)."""
+    _fields_ = [
+        ("abi_version", ctypes.c_int32), ("N", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("is_severed", ctypes.c_int32), ("deformable", ctypes.c_int32), ("t_beat", ctypes.c_int32),
+        ("tau", ctypes.c_double), ("alpha", ctypes.c_double), ("p0_in", ctypes.c_double), ("p0_out", ctypes.c_double),
+    ]
+
+
+def pulsatile_params(N=64, tau=0.75, alpha=0.01, p0_in=0.20, p0_out=0.19, is_severed=1, deformable=1, device=-1):
+    """defaults = the values hard-coded in PulsatileBloodFlow2D() (AB/apps/PulsatileBloodFlow2D.h:721, :740-749)"""
+    p = PulsatileParams()
+    p.abi_version = ABI_VERSION
+    p.N, p.device, p.is_severed, p.deformable, p.t_beat = N, device, int(is_severed), int(deformable), 0
+    p.tau, p.alpha, p.p0_in, p.p0_out = tau, alpha, p0_in, p0_out
+    return p
+
+
+# Pulsatile: 145 B/LU as the other single-set D2Q9 paths; the reference also stores P, Ux, Uy every step (169)
+PULSATILE_BYTES_PER_LU = 169
