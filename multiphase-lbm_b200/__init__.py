@@ -6,4 +6,4 @@ The directory name carries a hyphen (it is the project name), so import it throu
 """
 from . import params  # noqa: F401
 from .params import *  # noqa: F401,F403
-from . import clbm, slab  # noqa: F401,E402
+from . import clbm, slab, pulsatile_cases  # noqa: F401,E402

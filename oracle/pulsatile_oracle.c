@@ -606,6 +606,28 @@ void pulsatile_step(pulsatile *p, int n)
     }
 }
 
+/* replace the whole functor state (host arrays in the reference layout) and rebuild what the reference derives from the
+ * wall positions: Fobj + mask (AB:275-285) and the border lists (AB:294-382).  Used to start from states other than
+ * Initialize_P_U_g, e.g. the open vessel at rest of bench.py / tests. */
+int pulsatile_set_state(pulsatile *p, const double *lattice, const double *P, const double *Ux, const double *Uy,
+                        const double *yr1, const double *yr2, int parity, int t_iter)
+{
+    memcpy(p->lattice, lattice, 2 * p->npop * sizeof(double));
+    memcpy(p->P, P, p->nelem * sizeof(double));
+    memcpy(p->Ux, Ux, p->nelem * sizeof(double));
+    memcpy(p->Uy, Uy, p->nelem * sizeof(double));
+    memcpy(p->yr1, yr1, p->nx * sizeof(double));
+    memcpy(p->yr2, yr2, p->nx * sizeof(double));
+    memcpy(p->y1new, yr1, p->nx * sizeof(double));
+    memcpy(p->y2new, yr2, p->nx * sizeof(double));
+    p->parity = parity;
+    p->t_iter = t_iter;
+    init_fobj(p);
+    update_boundary_bottom(p);
+    update_boundary_top(p);
+    return 0;
+}
+
 int pulsatile_nx(const pulsatile *p) { return p->nx; }
 int pulsatile_ny(const pulsatile *p) { return p->ny; }
 int pulsatile_parity(const pulsatile *p) { return p->parity; }

@@ -130,6 +130,14 @@ class PulsatileOracle:
     def lattice(self):
         return np.ctypeslib.as_array(lib().pulsatile_lattice(self.h), shape=(2 * 9 * self.nelem,)).copy()
 
+    def set_state(self, lattice, P, Ux, Uy, yr1, yr2, parity=0, t_iter=0):
+        L = lib()
+        L.pulsatile_set_state.argtypes = None
+        c = [np.ascontiguousarray(a, dtype=np.float64) for a in (lattice, P, Ux, Uy, yr1, yr2)]
+        assert c[0].size == 2 * 9 * self.nelem and c[1].size == self.nelem and c[4].size == self.nx
+        L.pulsatile_set_state(self.h, *[_dptr(a) for a in c], int(parity), int(t_iter))
+        return self
+
     @property
     def parity(self):
         return lib().pulsatile_parity(self.h)
