@@ -119,6 +119,9 @@ int  clbm_download_lattice(clbm_ctx *ctx, double *lattice, int *parity);
  * non-bulk nodes: s0/s2 as computed from the (zero) populations, s1 = 0, u = 0. */
 int  clbm_download_fields(clbm_ctx *ctx, double *s0, double *s1, double *s2,
                           double *ux, double *uy, double *uz, uint8_t *flag);
+/* Shan-Chen only: the interaction force `force(f0)` the reference's VTK writers print
+ * (SC/apps/laplace2D.h:198-242, :356-364; contactAngle2D.h:248-293, :399-408); 0 at non-bulk nodes; NULL = skip */
+int  clbm_download_force(clbm_ctx *ctx, double *fx, double *fy, double *fz);
 /* device-side initial condition; args has the case-specific doubles listed above */
 int  clbm_init_case(clbm_ctx *ctx, int case_id, const double *args, int nargs);
 

@@ -67,6 +67,21 @@ inline LbParameters lb_parameters(double ulb, int lref, double Re)
     return p;
 }
 
+// clbm_params with the library defaults (single slab on the current device, fused kernels)
+inline clbm_params default_params(int model, int nx, int ny, int nz)
+{
+    clbm_params p{};
+    p.abi_version = CLBM_ABI_VERSION;
+    p.model = model;
+    p.nx = nx; p.ny = ny; p.nz = nz;
+    p.nx_global = nx; p.x_offset = 0;
+    p.device = -1;
+    p.fused = 1;
+    p.omega = 1.0;
+    p.a = 1.0; p.b = 4.0; p.R = 1.0;
+    return p;
+}
+
 inline void check(int rc)
 {
     if (rc != CLBM_OK) throw std::runtime_error(std::string("clbm: ") + clbm_last_error());
@@ -117,7 +132,8 @@ public:
         os << "POINT_DATA " << (size_t)nx * ny * nz << "\n";
     }
     // value(i) with i = z + nz*(y + ny*x); loop order of the reference writers: z descending (3-D), y outer, x inner
-    template <class V> void scalars(const char *name, const char *type, V value)
+    // plane_blank: a blank line after every z plane even in 2-D (the PF writers' Flag block, PF/apps/rayleighTaylor2D.h:763-780)
+    template <class V> void scalars(const char *name, const char *type, V value, bool plane_blank = false)
     {
         os << "SCALARS " << name << " " << type << " 1\nLOOKUP_TABLE default\n";
         for (int z = nz - 1; z >= 0; --z) {
@@ -125,7 +141,7 @@ public:
                 for (int x = 0; x < nx; ++x) os << value((size_t)z + (size_t)nz * (y + (size_t)ny * x)) << " ";
                 os << "\n";
             }
-            if (nz > 1) os << "\n";
+            if (nz > 1 || plane_blank) os << "\n";
         }
         os << "\n";
     }
@@ -146,19 +162,22 @@ public:
 struct Stopwatch {
     std::chrono::high_resolution_clock::time_point t0 = std::chrono::high_resolution_clock::now();
     int iters = 0;
-    void report(size_t nelem, const char *l1 = "result: ", const char *l2 = "result: ") const
+    // "result: <s> seconds / result: <v> MLUPS" (SC/apps/laplace2D.h:79-86); the PF / AB drivers print
+    // "Runtime: ... / Throughput: ..." (PF/apps/laplace3D.h:101-112, AB/apps/PulsatileBloodFlow2D.h:711-717)
+    void report(size_t nelem, const char *l1 = "result: ", const char *l2 = "result: ", const char *unit1 = " seconds\n") const
     {
         auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::high_resolution_clock::now() - t0).count();
         double mlups = (double)(nelem * (size_t)iters) / (double)us;
-        std::cout << l1 << us / 1e6 << " seconds" << std::endl;
+        std::cout << l1 << us / 1e6 << unit1;
         std::cout << l2 << std::setprecision(4) << mlups << " MLUPS" << std::endl;
     }
 };
 
-inline void progress_line(int time_iter, double dt, double max_t)
+inline void progress_line(int time_iter, double dt, double max_t, bool flush = false)
 {
     std::cout << "Saving profiles at iteration " << time_iter << ", t = " << std::setprecision(4) << time_iter * dt
               << std::setprecision(3) << " [" << time_iter * dt / max_t * 100. << "%]\n";
+    if (flush) std::cout.flush();
 }
 
 // runs `steps_total` device steps, stopping at every multiple of the output frequencies for the callback

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libclbm.so")
 
 EXPORTS = [
     "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_download_lattice",
-    "clbm_download_fields", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
+    "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
     "clbm_stream", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
@@ -49,6 +49,7 @@ def load_library(path=None):
     lib.clbm_upload.argtypes = [vp, vp, vp, ctypes.c_int]
     lib.clbm_download_lattice.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int)]
     lib.clbm_download_fields.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.clbm_download_force.argtypes = [vp, vp, vp, vp]
     lib.clbm_init_case.argtypes = [vp, ctypes.c_int, dp, ctypes.c_int]
     lib.clbm_step.argtypes = [vp, ctypes.c_int]
     lib.clbm_sync.argtypes = [vp]
@@ -161,6 +162,13 @@ class Lattice:
         ptrs = [_ptr(arrs[k]) if k in arrs else None for k in order]
         self._check(self.lib.clbm_download_fields(self._h, *ptrs, None))
         return arrs
+
+    def force(self):
+        """Shan-Chen interaction force of every node (the VECTORS Force of the reference's VTK files)"""
+        n = self.p.nelem
+        f = [np.zeros(n) for _ in range(3)]
+        self._check(self.lib.clbm_download_force(self._h, *[_ptr(a) for a in f]))
+        return f
 
     def flags(self):
         f = np.zeros(self.p.nelem, dtype=np.uint8)

@@ -60,6 +60,7 @@ LaunchScope::~LaunchScope()
 
 // per-model dispatch (kernels live in the per-model .cu files)
 int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz);
+int sc_force_field(clbm_ctx *c, double *fx, double *fy, double *fz);
 int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int sc_psi_all(clbm_ctx *c);
@@ -331,6 +332,30 @@ int clbm_download_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double
         CLBM_CUDA(cudaStreamSynchronize(c->stream));
     }
     return CLBM_OK;
+}
+
+int clbm_download_force(clbm_ctx *c, double *fx, double *fy, double *fz)
+{
+    if (!c) { set_error("null context"); return CLBM_EINVAL; }
+    if (c->prm.model != CLBM_MODEL_SC_D2Q9 && c->prm.model != CLBM_MODEL_SC_D3Q19) {
+        set_error("clbm_download_force: Shan-Chen models only");
+        return CLBM_EINVAL;
+    }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    const size_t nelem = (size_t)c->geo.nx * c->geo.plane;
+    double *host[3] = {fx, fy, fz}, *dev[3] = {nullptr, nullptr, nullptr}, *tmp = nullptr;
+    CLBM_CUDA(cudaMalloc(&tmp, 3 * nelem * sizeof(double)));
+    for (int i = 0; i < 3; ++i) if (host[i]) dev[i] = tmp + (size_t)i * nelem;
+    int rc = sc_force_field(c, dev[0], dev[1], dev[2]);
+    for (int i = 0; i < 3 && !rc; ++i)
+        if (host[i] && cudaMemcpyAsync(host[i], dev[i], nelem * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) {
+            set_error("force download failed");
+            rc = CLBM_ECUDA;
+        }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    if (!rc && e != cudaSuccess) return cuda_fail(e, "force download sync", __FILE__, __LINE__);
+    return rc;
 }
 
 int clbm_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)

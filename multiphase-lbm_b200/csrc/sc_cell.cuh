@@ -137,11 +137,11 @@ CLBM_D void sc_collide(const ModelParams &mp, const double *f, ScForceSums &s, d
 
 // output fields of one bulk node: pressure_node (laplace2D.h:308-315) and u_actual (:252-257)
 template <class L>
-CLBM_D void sc_outputs(const ModelParams &mp, const double *f, ScForceSums &s, double &rho_raw, double &pr, double u[3])
+CLBM_D void sc_outputs(const ModelParams &mp, const double *f, ScForceSums &s, double &rho_raw, double &pr, double u[3], double F[3])
 {
     rho_raw = Mom<L>::sum(f);
     const double rho = fmax(rho_raw, 1e-14);
-    double jx, jy, jz, F[3];
+    double jx, jy, jz;
     Mom<L>::first(f, jx, jy, jz);
     bool g1_pos;
     const double ps = sc_psi_g1(mp, rho_raw, g1_pos);

@@ -67,7 +67,8 @@ sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, con
 template <class L>
 __global__ void __launch_bounds__(256)
 sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, const double *__restrict__ psi,
-                 Geom g, ModelParams mp, double *s0, double *s1, double *ux, double *uy, double *uz, long long ncell)
+                 Geom g, ModelParams mp, double *s0, double *s1, double *ux, double *uy, double *uz, double *fx, double *fy,
+                 double *fz, long long ncell)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ncell) return;
@@ -78,7 +79,7 @@ sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ fla
     double f[L::Q];
 #pragma unroll
     for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + n.i];
-    double rho = Mom<L>::sum(f), pr = 0.0, u[3] = {0., 0., 0.};
+    double rho = Mom<L>::sum(f), pr = 0.0, u[3] = {0., 0., 0.}, F[3] = {0., 0., 0.};
     if (flag[n.i] == CELL_BULK) {
         ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
 #pragma unroll
@@ -88,13 +89,16 @@ sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ fla
             const bool w = flag[nb] == CELL_BB;
             sc_force_add<L>(s, k, w, w ? 0.0 : fabs(psi[nb]));
         }
-        sc_outputs<L>(mp, f, s, rho, pr, u);
+        sc_outputs<L>(mp, f, s, rho, pr, u, F);
     }
     if (s0) s0[t] = rho;
     if (s1) s1[t] = pr;
     if (ux) ux[t] = u[0];
     if (uy) uy[t] = u[1];
     if (uz) uz[t] = u[2];
+    if (fx) fx[t] = F[0];
+    if (fy) fy[t] = F[1];
+    if (fz) fz[t] = F[2];
 }
 
 // ---- host side ---------------------------------------------------------------------------
@@ -158,7 +162,7 @@ int sc_step(clbm_ctx *c)
     return 0;
 }
 
-int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz)
+static int sc_fields_all(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz, double *fx, double *fy, double *fz)
 {
     // psi of the current populations (ghost planes of psi must already be valid in slab mode)
     int rc = sc_psi_all(c);
@@ -166,11 +170,21 @@ int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, doubl
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "sc_fields");
     if (c->Q == 9)
-        sc_fields_kernel<D2Q9><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, n);
+        sc_fields_kernel<D2Q9><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, fx, fy, fz, n);
     else
-        sc_fields_kernel<D3Q19><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, n);
+        sc_fields_kernel<D3Q19><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, fx, fy, fz, n);
     CLBM_CUDA(cudaGetLastError());
     return 0;
+}
+
+int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz)
+{
+    return sc_fields_all(c, s0, s1, ux, uy, uz, nullptr, nullptr, nullptr);
+}
+// `force` of every node (SC/apps/laplace2D.h:198-242, contactAngle2D.h:248-293), 0 at non-bulk nodes
+int sc_force_field(clbm_ctx *c, double *fx, double *fy, double *fz)
+{
+    return sc_fields_all(c, nullptr, nullptr, nullptr, nullptr, nullptr, fx, fy, fz);
 }
 
 }  // namespace clbm

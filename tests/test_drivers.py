@@ -1,0 +1,78 @@
+"""The C++17 case drivers (multiphase-lbm_b200/apps, built by __graft_entry__.build()): CPU-side checks of the reference's
+error behaviour, and on the GPU the full PulsatileBloodFlow2D run reproducing the reference's shipped VTK files byte
+for byte plus a short Laplace2D run checked against the oracle."""
+import hashlib
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _cases
+from _oracle import OracleSim
+
+APPS = os.path.join(_cases.ROOT, "multiphase-lbm_b200", "apps")
+EXE = os.path.join(APPS, "build", "COOLBM")
+P = _cases.P
+
+
+def _exe():
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-s", "-C", APPS])
+    return EXE
+
+
+def test_driver_missing_config_throws_like_reference(tmp_path):
+    r = subprocess.run([_exe(), "laplace2D", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert 'Config file not found. It should be named "config_Laplace2D.txt" in Files_Config.' in r.stderr
+
+
+def test_driver_unknown_problem():
+    r = subprocess.run([_exe(), "noSuchCase"], capture_output=True, text=True)
+    assert r.returncode == 2
+
+
+def test_driver_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([_exe(), "laplace2D", os.path.join(APPS, "Config_Files")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_driver_pulsatile_reproduces_shipped_vtk(tmp_path):
+    hashes = json.load(open(os.path.join(_cases.GOLDEN, "pulsatile_vtk_sha256.json")))
+    r = subprocess.run([_exe(), "PulsatileBloodFlow2D"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "t=2754 / 2765" in r.stdout and "MLUPS" in r.stdout
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".vtk"))
+    assert files == sorted(hashes)
+    for f in files:
+        assert hashlib.sha256(open(tmp_path / f, "rb").read()).hexdigest() == hashes[f], f
+
+
+@pytest.mark.gpu
+def test_driver_laplace2d_matches_oracle(tmp_path):
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    (cfg / "config_Laplace2D.txt").write_text(
+        "# first line is skipped\nTT0 0.875\na 1.0\nb 4.0\nR 1.0\nrho_w 0.12\nrhol 0.265\nrhog 0.038\nN 48\nulb 0.01\nRe 6\n"
+        "max_t 0.0626\nout_freq 100\nvtk_freq 300\ngravity 0.0\n")
+    r = subprocess.run([_exe(), "laplace2D", str(cfg)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "Laplace 2D problem" in r.stdout and re.search(r"result: [0-9.e+-]+ MLUPS", r.stdout)
+    # dt = ulb / N -> max_time_iter = int(0.0626 * 4800) = 300 steps; the VTK of iteration 300 is not written (loop ends at 299)
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".vtk")) == ["sol_0000000.vtk"]
+    mass = np.loadtxt(tmp_path / "mass.dat")
+    assert mass.shape == (3, 2) and abs(mass[-1, 1] - mass[0, 1]) / mass[0, 1] < 1e-12
+    prm = P.sc_params(P.MODEL_SC_D2Q9, 48, 48, ulb=0.01, N=48, Re=6.0)
+    ora = OracleSim(prm).init_case(P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0))
+    ora.step(200)
+    u = ora.fields()
+    e_ref = 0.5 * np.sum(u["ux"] ** 2 + u["uy"] ** 2) / (48 * 48) * (1 / 48.) ** 2 / (0.01 / 48.) ** 2
+    e_drv = np.loadtxt(tmp_path / "energy.dat")[2, 1]
+    assert abs(e_drv - e_ref) <= 2e-8 * abs(e_ref) + 1e-30     # energy.dat holds 8 significant digits

@@ -260,3 +260,34 @@ def test_error_paths():
             lat.step_stage(0)                        # not a slab context
         with pytest.raises(pkg.clbm.ClbmError):
             lat.reduce(17)
+
+
+@pytest.mark.parametrize("model,case,args,dims,force", [
+    (P.MODEL_SC_D2Q9, P.CASE_SC_CONTACT2D, (0.265, 0.038, 8.0), (48, 24, 1), P.SC_FORCE_CONTACT),
+    (P.MODEL_SC_D2Q9, P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0), (40, 40, 1), P.SC_FORCE_LAPLACE),
+    (P.MODEL_SC_D3Q19, P.CASE_SC_DROPLET3D, (0.265, 0.038, 5.0, 5.0), (16, 12, 20), P.SC_FORCE_CONTACT),
+])
+def test_sc_force_field_download(model, case, args, dims, force):
+    """clbm_download_force (the VECTORS Force of the reference VTK writers): the oracle exposes u_actual = u + F/(2 rho),
+    so F must equal 2 (rho u_actual - j) with j the first moment of the populations"""
+    prm = P.sc_params(model, *dims, tau=1.0, rho_w=0.2, sc_force=force, gravity=-1e-5 if force == P.SC_FORCE_LAPLACE else 0.0)
+    ora = OracleSim(prm).init_case(case, args)
+    with pkg.clbm.Lattice(prm) as lat:
+        lat.upload(ora.lattice, ora.flag, 0)
+        lat.step(50)
+        F = lat.force()
+    ora.step(50)
+    ref, pops = ora.fields(), ora.in_pops()[0]
+    if prm.Q == 9:
+        C = np.array([(-1, 0, 0), (0, -1, 0), (-1, -1, 0), (-1, 1, 0), (0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (1, -1, 0)])
+    else:
+        h = [(-1, 0, 0), (0, -1, 0), (0, 0, -1), (-1, -1, 0), (-1, 1, 0), (-1, 0, -1), (-1, 0, 1), (0, -1, -1), (0, -1, 1)]
+        C = np.array(h + [(0, 0, 0)] + [tuple(-v for v in c) for c in h])
+    bulk = ora.flag == 1
+    scale = None
+    for d, key in enumerate(("ux", "uy", "uz")):
+        j = (pops * C[:, d][:, None]).sum(axis=0)
+        Fref = np.where(bulk, 2.0 * (np.maximum(ref["s0"], 1e-14) * ref[key] - j), 0.0)
+        scale = scale or max(np.max(np.abs(Fref)), 1e-30)
+        assert np.max(np.abs(F[d] - Fref)) < 1e-8 * scale, key
+    assert scale > 1e-6
