@@ -254,13 +254,11 @@ def main():
     if ring is None:
         ms = lat.step_timed(a.steps)              # CUDA events on the library's launching stream
     else:
-        t0 = time.perf_counter()
-        ev0.record()
+        ev0 = ring.record_event()                 # CUDA events on the library's launching stream (NCCL is ordered on it)
         ring.step(a.steps)
-        lat.sync()
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3    # slab steps interleave two streams + NCCL: host clock around a full sync
+        ev1 = ring.record_event()
+        ev1.synchronize()
+        ms = ev0.elapsed_time(ev1)
     barrier()
     kms, kcount, kname = lat.kernel_timing_end()
     launches = lat.launch_count() - l0

@@ -167,6 +167,17 @@ int  clbm_halo_unpack(clbm_ctx *ctx, int phase);
 int  clbm_step_stage(clbm_ctx *ctx, int stage);
 /* raw stream handle (cudaStream_t) so the caller can order its copies after ours */
 void *clbm_stream(clbm_ctx *ctx);
+/* Overlap protocol (SURVEY.md 8e "boundary planes first on a high-priority stream -> start exchange -> interior on
+ * the main stream -> join"), available when clbm_overlap_supported() returns 1:
+ *   stage 10: boundary stream: moments of the boundary planes + pack phase 0;  launching stream: collide/stream of
+ *             the interior planes [1, nx-1), which need nothing from the neighbours
+ *   (caller exchanges phase 0 ON THE BOUNDARY STREAM)
+ *   stage 11: boundary stream: unpack phase 0, collide/stream of planes 0 and nx-1, pack phase 1
+ *   (caller exchanges phase 1 on the boundary stream)
+ *   stage 12: boundary stream: unpack phase 1; the launching stream then waits for the boundary stream
+ * clbm_boundary_stream returns that stream (cudaStream_t), NULL when the protocol is not available. */
+int  clbm_overlap_supported(const clbm_ctx *ctx);
+void *clbm_boundary_stream(clbm_ctx *ctx);
 
 /* ---- compliant-vessel case (CLBM_MODEL_PULSATILE) ---------------------------------------------------
  * Replaces the whole iteration body of PulsatileBloodFlow2D() ("Abbashub LBM/apps/PulsatileBloodFlow2D.h":764-790):

@@ -19,7 +19,7 @@ EXPORTS = [
     "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_download_lattice",
     "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
-    "clbm_stream", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
+    "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
     "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
     "clbm_pulsatile_kernel_timing_begin", "clbm_pulsatile_kernel_timing_end", "clbm_pulsatile_download_fields",
@@ -70,6 +70,9 @@ def load_library(path=None):
     lib.clbm_free_host.argtypes = [vp]
     lib.clbm_stream.argtypes = [vp]
     lib.clbm_stream.restype = vp
+    lib.clbm_boundary_stream.argtypes = [vp]
+    lib.clbm_boundary_stream.restype = vp
+    lib.clbm_overlap_supported.argtypes = [vp]
     ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
     lib.clbm_pulsatile_create.argtypes = [ctypes.POINTER(P.PulsatileParams), ctypes.POINTER(vp)]
     lib.clbm_pulsatile_destroy.argtypes = [vp]
@@ -237,6 +240,12 @@ class Lattice:
 
     def stream(self):
         return self.lib.clbm_stream(self._h)
+
+    def overlap_supported(self):
+        return bool(self.lib.clbm_overlap_supported(self._h))
+
+    def boundary_stream(self):
+        return self.lib.clbm_boundary_stream(self._h)
 
 
 class PinnedArray:

@@ -65,6 +65,8 @@ int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int sc_psi_all(clbm_ctx *c);
 int sc_psi_boundary(clbm_ctx *c);
+bool sc_range_supported(const clbm_ctx *c);
+int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end);
 int sc_collide_slab(clbm_ctx *c);
 int hcz2d_stage0(clbm_ctx *c);
 int hcz2d_stage1(clbm_ctx *c);
@@ -94,6 +96,70 @@ int model_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
     return CLBM_EINVAL;
 }
 
+static bool overlap_supported(const clbm_ctx *c)
+{
+    const int m = c->prm.model;
+    return c->multi && c->geo.nx >= 3 && (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) && sc_range_supported(c);
+}
+
+static int ensure_boundary_stream(clbm_ctx *c)
+{
+    if (c->stream_b) return 0;
+    int lo = 0, hi = 0;
+    CLBM_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CLBM_CUDA(cudaStreamCreateWithPriority(&c->stream_b, cudaStreamNonBlocking, hi));
+    CLBM_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CLBM_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
+    return 0;
+}
+
+// while alive, the boundary stream is the context's launching stream
+struct BoundaryStream {
+    clbm_ctx *c;
+    cudaStream_t saved;
+    explicit BoundaryStream(clbm_ctx *ctx) : c(ctx), saved(ctx->stream) { c->stream = c->stream_b; }
+    ~BoundaryStream() { c->stream = saved; }
+};
+
+// Overlap protocol of one slab step (stages 10, 11, 12; include/clbm.h): the interior planes [1, nx-1) need nothing
+// from the neighbours (their psi stencil reads the slab's own populations), so they are collided on the launching
+// stream while the boundary stream moves the moment halo, collides the two boundary planes and moves the crossing
+// populations.  Interior and boundary launches write disjoint (node, direction) slots of the out buffer.
+static int overlap_stage(clbm_ctx *c, int stage)
+{
+    if (!overlap_supported(c)) { set_error("overlap protocol not available for this context (use stages 0-2)"); return CLBM_ESTATE; }
+    int rc;
+    const int nx = c->geo.nx;
+    if ((rc = ensure_boundary_stream(c))) return rc;
+    if (stage == 10) {
+        {   // the boundary planes of the "in" buffer were completed by the previous step's interior launch too
+            CLBM_CUDA(cudaStreamWaitEvent(c->stream_b, c->ev_main, 0));
+            BoundaryStream bs(c);
+            if ((rc = sc_psi_boundary(c))) return rc;
+            if ((rc = halo_pack(c, 0))) return rc;
+        }
+        if ((rc = sc_collide_range_fused(c, 1, nx - 1))) return rc;
+        CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
+        return 0;
+    }
+    if (stage == 11) {
+        BoundaryStream bs(c);
+        if ((rc = halo_unpack(c, 0))) return rc;
+        if ((rc = sc_collide_range_fused(c, 0, 1))) return rc;
+        if ((rc = sc_collide_range_fused(c, nx - 1, nx))) return rc;
+        c->parity = 1 - c->parity;
+        return halo_pack(c, 1);
+    }
+    {
+        BoundaryStream bs(c);
+        if ((rc = halo_unpack(c, 1))) return rc;
+    }
+    CLBM_CUDA(cudaEventRecord(c->ev_b, c->stream_b));
+    CLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+    return 0;
+}
+
 // slab protocol: see include/clbm.h (clbm_step_stage)
 int model_stage(clbm_ctx *c, int stage)
 {
@@ -118,6 +184,7 @@ int model_stage(clbm_ctx *c, int stage)
         return halo_pack(c, 1);
     }
     if (stage == 2) return halo_unpack(c, 1);
+    if (stage >= 10 && stage <= 12) return overlap_stage(c, stage);
     set_error("bad stage %d", stage);
     return CLBM_EINVAL;
 }
@@ -252,6 +319,12 @@ int clbm_destroy(clbm_ctx *c)
     for (auto &ph : c->halo) for (auto &sd : ph) for (auto &b : sd) if (b) cudaFree(b);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream_b) {
+        cudaStreamSynchronize(c->stream_b);
+        cudaStreamDestroy(c->stream_b);
+        cudaEventDestroy(c->ev_main);
+        cudaEventDestroy(c->ev_b);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return CLBM_OK;
@@ -390,14 +463,17 @@ int clbm_step_stage(clbm_ctx *c, int stage)
     CLBM_CUDA(cudaSetDevice(c->device));
     int rc = model_stage(c, stage);
     if (rc) return rc;
-    if (stage == 1) count_step(c);
+    if (stage == 1 || stage == 11) count_step(c);
     return CLBM_OK;
 }
+
+int clbm_overlap_supported(const clbm_ctx *c) { return c && overlap_supported(c) ? 1 : 0; }
 
 int clbm_sync(clbm_ctx *c)
 {
     if (!c) { set_error("null context"); return CLBM_EINVAL; }
     CLBM_CUDA(cudaSetDevice(c->device));
+    if (c->stream_b) CLBM_CUDA(cudaStreamSynchronize(c->stream_b));
     CLBM_CUDA(cudaStreamSynchronize(c->stream));
     return CLBM_OK;
 }
@@ -513,5 +589,12 @@ int clbm_halo_unpack(clbm_ctx *c, int phase)
 }
 
 void *clbm_stream(clbm_ctx *c) { return c ? (void *)c->stream : nullptr; }
+void *clbm_boundary_stream(clbm_ctx *c)
+{
+    if (!c || !overlap_supported(c)) return nullptr;
+    cudaSetDevice(c->device);
+    if (ensure_boundary_stream(c)) return nullptr;
+    return (void *)c->stream_b;
+}
 
 }  // extern "C"

@@ -39,7 +39,9 @@ struct clbm_ctx {
     int host_parity0;     // parity value the host uploaded
     long long steps_taken;
     int multi;            // 1: x-slab of a wider lattice (ghost planes filled by exchange)
-    cudaStream_t stream;
+    cudaStream_t stream;      // launching stream (all work of a single slab; the interior of an overlapped slab step)
+    cudaStream_t stream_b;    // boundary stream of the overlap protocol (high priority): boundary planes, pack/unpack, exchange
+    cudaEvent_t ev_main, ev_b;   // interior done / boundary + exchange done (cross-stream ordering between steps)
     cudaEvent_t ev0, ev1;
     int64_t launches;
 

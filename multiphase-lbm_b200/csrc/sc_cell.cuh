@@ -109,10 +109,10 @@ CLBM_D void sc_force(const ModelParams &mp, ScForceSums &s, double rho_c, double
 }
 
 // BGK collision of all Q populations with the tau-shifted equilibrium velocity
+// rho_raw = Mom<L>::sum(f), already known to the caller
 template <class L>
-CLBM_D void sc_collide(const ModelParams &mp, const double *f, ScForceSums &s, double psi_c, bool g1_pos, double *out)
+CLBM_D void sc_collide_rho(const ModelParams &mp, const double *f, ScForceSums &s, double rho_raw, double psi_c, bool g1_pos, double *out)
 {
-    const double rho_raw = Mom<L>::sum(f);
     const double rho = fmax(rho_raw, 1e-14);
     const double inv = 1.0 / rho;
     double jx, jy, jz, F[3];
@@ -133,6 +133,12 @@ CLBM_D void sc_collide(const ModelParams &mp, const double *f, ScForceSums &s, d
         out[L::opp(k)] = om1 * f[L::opp(k)] + (even - odd);
     }
     out[L::REST] = om1 * f[L::REST] + A * L::t(L::REST) * base;
+}
+
+template <class L>
+CLBM_D void sc_collide(const ModelParams &mp, const double *f, ScForceSums &s, double psi_c, bool g1_pos, double *out)
+{
+    sc_collide_rho<L>(mp, f, s, Mom<L>::sum(f), psi_c, g1_pos, out);
 }
 
 // output fields of one bulk node: pressure_node (laplace2D.h:308-315) and u_actual (:252-257)

@@ -187,15 +187,29 @@ static int launch_fused(clbm_ctx *c)
 
 bool sc_tma_eligible(const clbm_ctx *c);            // sc_fused_tma.cu
 int sc_fused_tma_step(clbm_ctx *c, int variant);
+int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end);
 
 // one fused collide-stream sweep over the local planes; does NOT flip the parity
-int sc_fused_launch(clbm_ctx *c)
+// tile variant of the TMA kernel this context would run, 0 when it runs one of the register-pipelined kernels
+static int sc_tma_variant(const clbm_ctx *c)
 {
-    int rc;
     // clbm_params.fused: 1 = default fused kernel, >1 = explicit tile variant (tuning / tests); env overrides
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (const char *e = getenv("CLBM_SC_TILE")) variant = atoi(e);
     // D3Q19 default: the TMA-staged kernel with 8 x 64 tiles (best of the sweep in profiles/README.md)
+    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 11;
+    return (variant >= 10 && sc_tma_eligible(c)) ? variant : 0;
+}
+
+// x-range launches (overlap protocol of the slab exchange) exist for the TMA kernel
+bool sc_range_supported(const clbm_ctx *c) { return c->prm.fused && sc_tma_variant(c) != 0; }
+int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end) { return sc_fused_tma_range(c, sc_tma_variant(c), x_begin, x_end); }
+
+int sc_fused_launch(clbm_ctx *c)
+{
+    int rc;
+    int variant = c->prm.fused > 1 ? c->prm.fused : 0;
+    if (const char *e = getenv("CLBM_SC_TILE")) variant = atoi(e);
     if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 11;
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;

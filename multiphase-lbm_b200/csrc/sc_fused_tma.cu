@@ -46,7 +46,8 @@ struct TmaCfg {
 template <int TY, int TZ, int MINB>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, const uint8_t *__restrict__ flag,
-                    const double *__restrict__ fin, const double *__restrict__ psi_g, Geom g, ModelParams mp, int xchunk)
+                    const double *__restrict__ fin, const double *__restrict__ psi_g, Geom g, ModelParams mp, int xchunk,
+                    int x_begin, int x_end)
 {
     using C = TmaCfg<TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -59,8 +60,8 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     const int y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
     const int y = y0 + ty, z = z0 + tz;
     const bool inside = (y < g.ny) && (z < g.nz);
-    const int xa = blockIdx.z * xchunk;
-    const int nplanes = min(g.nx, xa + xchunk) - xa;
+    const int xa = x_begin + blockIdx.z * xchunk;        // this CTA collides planes [xa, xa + nplanes) of [x_begin, x_end)
+    const int nplanes = min(x_end, xa + xchunk) - xa;
     const int plane = (int)g.plane, nz = g.nz, G = g.G;
     const int ty_n = min(TY, g.ny - y0), tz_n = min(TZ, g.nz - z0);
     const int nrow = tz_n + 2, nhalo = 2 * nrow + 2 * ty_n;
@@ -93,7 +94,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
         mbar_expect_tx(&mbar[r & 1], (uint32_t)(C::BOX * 8));
         tma_load_4d(stage_a + (r & 1) * C::STAGE_BYTES, &tmap, &mbar[r & 1], z0 - 2, y0 - 1, xs_of(r), 0);
     };
-    double psn = 0.0;
+    double psn = 0.0, rhn = 0.0;
     bool gpn = true;
     // psi of plane r (tile + halo ring) from its staged box into the ring; keeps the own psi / G1 branch
     auto make_psi = [&](int r, uint8_t fl_own, uint8_t fl_halo) {
@@ -110,12 +111,14 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
         if (inside) {
             double v = -1.0;
             psn = 0.0;
+            rhn = 0.0;
             gpn = true;
             if (fl_own != CELL_BB) {
                 double f[19];
 #pragma unroll
                 for (int k = 0; k < 19; ++k) f[k] = lds_f64(st + (k * (C::SY * C::BZ) + own_s) * 8);
-                psn = sc_psi_g1(mp, Mom<L3>::sum(f), gpn);
+                rhn = Mom<L3>::sum(f);
+                psn = sc_psi_g1(mp, rhn, gpn);
                 v = psn;
             }
             ring[r & 3][ty + 1][tz + 1] = v;
@@ -146,16 +149,24 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
 
     if (tid == 0) { issue(0); issue(1); }
     uint8_t fo, fh;
+    // wmask bit (r & 3): plane r has a bounce_back node inside this CTA's tile + halo ring (CTA-uniform).  Planes
+    // without walls around take the branch-free force sums and unconditional pushes below.
+    unsigned wmask = 0;
+    auto has_wall = [&](uint8_t fl_own, uint8_t fl_halo) { return (int)((inside && fl_own == CELL_BB) || (h_act && fl_halo == CELL_BB)); };
     flags_of(0, fo, fh);
+    int w0 = has_wall(fo, fh);
     mbar_wait(&mbar[0], 0);
     make_psi(0, fo, fh);
     flags_of(1, fo, fh);
+    const int w1 = has_wall(fo, fh);
     mbar_wait(&mbar[1], 0);
     make_psi(1, fo, fh);
-    double psc = psn;
+    double psc = psn, rhc = rhn;
     bool gpc = gpn;
     flags_of(2, fo, fh);        // the node mask runs one plane ahead of its use so that its latency never shows
-    __syncthreads();
+    w0 = __syncthreads_or(w0 | (w1 << 1));
+    wmask = (unsigned)w0 & 3u;   // an OR over both prologue planes: conservative (bit set where either plane has a wall)
+    if (wmask) wmask = 3u;
     if (tid == 0 && nplanes + 1 >= 2) issue(2);
 
     const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
@@ -174,11 +185,40 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
 #pragma unroll
             for (int k = 0; k < 19; ++k) fc[k] = lds_f64(st + (k * (C::SY * C::BZ) + own_s) * 8);
         }
-        __syncthreads();
+        {
+            const unsigned bit = 1u << ((r + 1) & 3);
+            wmask = __syncthreads_or(has_wall(fo_now, fh_now)) ? (wmask | bit) : (wmask & ~bit);
+        }
         if (tid == 0 && r + 2 <= nplanes + 1) issue(r + 2);
 
         const int sm = (r + 3) & 3, s0 = r & 3, sp = (r + 1) & 3;
-        if (inside && ring[s0][ty + 1][tz + 1] >= 0.0) {
+        const bool walls = (wmask & ((1u << sm) | (1u << s0) | (1u << sp))) != 0u;
+        if (!walls) {
+            if (inside) {
+                // no bounce_back node within reach: every neighbour is fluid, every push goes to the neighbour
+                ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
+#pragma unroll
+                for (int k = 0; k < 19; ++k) {
+                    if (k == L3::REST) continue;
+                    const int slot = L3::cx(k) < 0 ? sm : (L3::cx(k) > 0 ? sp : s0);
+                    const double v = ring[slot][ty + 1 + L3::cy(k)][tz + 1 + L3::cz(k)];
+                    if (L3::cx(k)) s.ff[0] += L3::t(k) * L3::cx(k) * v;
+                    if (L3::cy(k)) s.ff[1] += L3::t(k) * L3::cy(k) * v;
+                    if (L3::cz(k)) s.ff[2] += L3::t(k) * L3::cz(k) * v;
+                }
+                double out[19];
+                sc_collide_rho<L3>(mp, fc, s, rhc, psc, gpc, out);
+                const int x = xa - 1 + r;
+                const int i = (x + G) * plane + yz;
+                const int oxm = (g.wx(x - 1) - x) * plane, oxp = (g.wx(x + 1) - x) * plane;
+#pragma unroll
+                for (int k = 0; k < 19; ++k) {
+                    const int off = (L3::cx(k) < 0 ? oxm : (L3::cx(k) > 0 ? oxp : 0)) + (L3::cy(k) < 0 ? oym : (L3::cy(k) > 0 ? oyp : 0)) +
+                                    (L3::cz(k) < 0 ? ozm : (L3::cz(k) > 0 ? ozp : 0));
+                    P.out[k][i + off] = out[k];
+                }
+            }
+        } else if (inside && ring[s0][ty + 1][tz + 1] >= 0.0) {
             ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
 #pragma unroll
             for (int k = 0; k < 19; ++k) {
@@ -188,7 +228,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
                 sc_force_add<L3>(s, k, v < 0.0, v);
             }
             double out[19];
-            sc_collide<L3>(mp, fc, s, psc, gpc, out);
+            sc_collide_rho<L3>(mp, fc, s, rhc, psc, gpc, out);
 
             const int x = xa - 1 + r;
             const int xp = g.wx(x + 1), xm = g.wx(x - 1);
@@ -204,6 +244,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
             }
         }
         psc = psn;
+        rhc = rhn;
         gpc = gpn;
     }
 }
@@ -216,7 +257,7 @@ bool sc_tma_eligible(const clbm_ctx *c)
 }
 
 template <int TY, int TZ, int MINB>
-static int launch_tma(clbm_ctx *c)
+static int launch_tma(clbm_ctx *c, int x_begin, int x_end)
 {
     using C = TmaCfg<TY, TZ>;
     const Geom &g = c->geo;
@@ -231,15 +272,17 @@ static int launch_tma(clbm_ctx *c)
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
 
     const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
-    int xchunk = g.nx;
+    const int nxr = x_end - x_begin;
+    if (nxr <= 0) return 0;
+    int xchunk = nxr;
     const long long want = 6LL * 148 * MINB;
     if ((long long)tiles < want) {
         const long long nch = (want + tiles - 1) / tiles;
-        xchunk = (int)((g.nx + nch - 1) / nch);
-        if (xchunk < 16) xchunk = g.nx < 16 ? g.nx : 16;
+        xchunk = (int)((nxr + nch - 1) / nch);
+        if (xchunk < 16) xchunk = nxr < 16 ? nxr : 16;
     }
-    if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
-    dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
+    if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < nxr ? v : nxr; }
+    dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (nxr + xchunk - 1) / xchunk);
     OutTable P;
     for (int k = 0; k < 19; ++k) P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     auto kern = sc_fused_tma_kernel<TY, TZ, MINB>;
@@ -248,25 +291,28 @@ static int launch_tma(clbm_ctx *c)
         CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
-    LaunchScope ls(c, "sc_fused_tma_collide_stream", true);
-    kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], c->fld[0], g, c->mp, xchunk);
+    LaunchScope ls(c, "sc_fused_tma_collide_stream", nxr * 2 >= g.nx);   // the boundary-plane launches of the overlap protocol are not the dominant kernel
+    kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], c->fld[0], g, c->mp, xchunk, x_begin, x_end);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
 
-int sc_fused_tma_step(clbm_ctx *c, int variant)
+// collide + push of the planes [x_begin, x_end) of the slab
+int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end)
 {
     int rc;
     switch (variant) {
-    case 11: rc = launch_tma<8, 64, 1>(c); break;
-    case 12: rc = launch_tma<16, 32, 1>(c); break;
-    case 13: rc = launch_tma<4, 64, 1>(c); break;
-    case 14: rc = launch_tma<4, 32, 3>(c); break;
-    case 15: rc = launch_tma<8, 16, 3>(c); break;
-    case 16: rc = launch_tma<8, 32, 1>(c); break;
-    default: rc = launch_tma<6, 32, 2>(c); break;
+    case 11: rc = launch_tma<8, 64, 1>(c, x_begin, x_end); break;
+    case 12: rc = launch_tma<16, 32, 1>(c, x_begin, x_end); break;
+    case 13: rc = launch_tma<4, 64, 1>(c, x_begin, x_end); break;
+    case 14: rc = launch_tma<4, 32, 3>(c, x_begin, x_end); break;
+    case 15: rc = launch_tma<8, 16, 3>(c, x_begin, x_end); break;
+    case 16: rc = launch_tma<8, 32, 1>(c, x_begin, x_end); break;
+    default: rc = launch_tma<6, 32, 2>(c, x_begin, x_end); break;
     }
     return rc;
 }
+
+int sc_fused_tma_step(clbm_ctx *c, int variant) { return sc_fused_tma_range(c, variant, 0, c->geo.nx); }
 
 }  // namespace clbm

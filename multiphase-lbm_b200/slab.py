@@ -92,16 +92,21 @@ class LocalRing:
             lat.halo_unpack(2)
             lat.sync()
 
-    def step(self, n=1):
+    def step(self, n=1, overlap=None):
+        """overlap: use the boundary-first protocol (stages 10-12) where the contexts support it; here the exchange is
+        still a synchronous copy, so this only checks the protocol's results, not its timing"""
+        if overlap is None:
+            overlap = all(lat.overlap_supported() for lat in self.lats)
+        s0, s1, s2 = (10, 11, 12) if overlap else (0, 1, 2)
         for _ in range(n):
             for lat in self.lats:
-                lat.step_stage(0)
+                lat.step_stage(s0)
             self.exchange(0)
             for lat in self.lats:
-                lat.step_stage(1)
+                lat.step_stage(s1)
             self.exchange(1)
             for lat in self.lats:
-                lat.step_stage(2)
+                lat.step_stage(s2)
 
     def refresh_moment_halo(self):
         """make the moment ghosts valid for the current populations (needed before fields())"""
@@ -132,7 +137,12 @@ def ring_exchange(dist, rank, nranks, send0, send1, recv0, recv1):
 
 
 class DistRing:
-    """one slab per process (rank), exchange over torch.distributed (NCCL)"""
+    """one slab per process (rank), exchange over torch.distributed (NCCL send/recv over NVLink).
+
+    The library's launching stream is made torch's current stream (torch.cuda.ExternalStream) for the duration of
+    every ring call, so the NCCL operations are ordered after the pack kernels and before the unpack kernels on the
+    DEVICE: `req.wait()` on an NCCL work object makes the current stream wait, not the host.  A slab step therefore
+    never synchronises with the host; the step loop runs ahead of the GPU like the single-slab one."""
 
     def __init__(self, lattice, rank, nranks, device):
         import torch
@@ -145,13 +155,26 @@ class DistRing:
                 for recv in (False, True):
                     ptr, nb = lattice.halo_buffer(phase, side, recv)
                     self._v[(phase, side, recv)] = as_torch(ptr, nb, device)
+        self.stream = torch.cuda.ExternalStream(lattice.stream(), device=device) if device.type == "cuda" else None
+        # boundary-first overlap protocol (clbm_step_stage 10-12): the exchanges run on the library's boundary stream
+        self.overlap = device.type == "cuda" and lattice.overlap_supported()
+        self.stream_b = torch.cuda.ExternalStream(lattice.boundary_stream(), device=device) if self.overlap else None
 
-    def exchange(self, phase):
-        self.lat.sync()
+    def _on_stream(self):
+        import contextlib
+        return self.torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def exchange(self, phase, boundary=False):
         v = self._v
-        ring_exchange(self.dist, self.rank, self.R, v[(phase, 0, False)], v[(phase, 1, False)],
-                      v[(phase, 0, True)], v[(phase, 1, True)])
-        self.torch.cuda.current_stream().synchronize()
+        with (self.torch.cuda.stream(self.stream_b) if boundary else self._on_stream()):
+            ring_exchange(self.dist, self.rank, self.R, v[(phase, 0, False)], v[(phase, 1, False)],
+                          v[(phase, 0, True)], v[(phase, 1, True)])
+
+    def record_event(self):
+        """CUDA event on the launching stream (device-side timing of slab steps)"""
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(self.stream)
+        return ev
 
     def exchange_flags(self):
         self.lat.halo_pack(2)
@@ -159,13 +182,22 @@ class DistRing:
         self.lat.halo_unpack(2)
         self.lat.sync()
 
-    def step(self, n=1):
-        for _ in range(n):
-            self.lat.step_stage(0)
-            self.exchange(0)
-            self.lat.step_stage(1)
-            self.exchange(1)
-            self.lat.step_stage(2)
+    def step(self, n=1, overlap=None):
+        if self.overlap if overlap is None else (overlap and self.overlap):
+            for _ in range(n):
+                self.lat.step_stage(10)         # boundary moments + pack | interior collide on the launching stream
+                self.exchange(0, boundary=True)
+                self.lat.step_stage(11)         # unpack, boundary planes, pack
+                self.exchange(1, boundary=True)
+                self.lat.step_stage(12)         # unpack, join
+            return
+        with self._on_stream():
+            for _ in range(n):
+                self.lat.step_stage(0)
+                self.exchange(0)
+                self.lat.step_stage(1)
+                self.exchange(1)
+                self.lat.step_stage(2)
 
     def refresh_moment_halo(self):
         self.lat.step_stage(0)

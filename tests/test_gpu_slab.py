@@ -73,3 +73,29 @@ def test_slab_device_init_has_consistent_ghost_flags():
     for lat in lats:
         lat.close()
     np.testing.assert_array_equal(pops, ref)
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_overlap_protocol_is_bit_identical(nranks):
+    """boundary-first overlap protocol (clbm_step_stage 10-12: interior planes on the launching stream, boundary planes
+    + both exchanges on the boundary stream) against the sequential protocol (stages 0-2) and the single slab"""
+    prm = P.sc_params(P.MODEL_SC_D3Q19, 32, 24, 36, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    args = (0.265, 0.038, 8.0, 5.0)
+    with pkg.clbm.Lattice(prm) as single:
+        single.init_case(P.CASE_SC_DROPLET3D, args)
+        single.step(50)
+        ref = single.in_pops()
+    out = {}
+    for overlap in (False, True):
+        lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, nranks)) for r in range(nranks)]
+        assert all(lat.overlap_supported() for lat in lats)
+        for lat in lats:
+            lat.init_case(P.CASE_SC_DROPLET3D, args)
+        ring = slab.LocalRing(lats)
+        ring.step(25, overlap=overlap)
+        ring.step(25, overlap=not overlap)      # the two protocols can be mixed between steps
+        out[overlap] = np.concatenate([lat.in_pops() for lat in lats], axis=2)
+        for lat in lats:
+            lat.close()
+    np.testing.assert_array_equal(out[False], ref)
+    np.testing.assert_array_equal(out[True], ref)
