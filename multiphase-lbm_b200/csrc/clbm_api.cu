@@ -258,6 +258,8 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     m.phi_l = p->phi_l; m.phi_g = p->phi_g; m.rho_l = p->rho_l; m.rho_g = p->rho_g; m.kappa = p->kappa;
     m.sc_force = p->sc_force;
     m.tau = 1. / p->omega;
+    m.inv_dphi = (p->phi_l != p->phi_g) ? 1.0 / (p->phi_l - p->phi_g) : 0.0;
+    m.drho = p->rho_l - p->rho_g;
     {
         // wall pseudopotential: laplace2D.h:210 evaluates psi_yuan_from_rho(rho_w) (own branch G1(rho_w));
         // contactAngle2D.h:259-262 re-evaluates it on the CENTRE node's branch G1c = +-1/3

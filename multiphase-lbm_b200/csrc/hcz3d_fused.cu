@@ -60,20 +60,28 @@ template <int ZR, bool WALLS>
 CLBM_D void grad19(const double *Rm, const double *R0, const double *Rp, int q, unsigned wall, double g[3])
 {
     const double xc = WALLS ? R0[q] : 0.0;
-    double gx = 0.0, gy = 0.0, gz = 0.0;
+    // opposite directions are paired first (the weights are equal), then the pair differences are accumulated in two
+    // interleaved chains per component: a third of the FMAs of the plain k = 0..18 sum and short dependency chains
+    // (the kernel runs 8 warps per SM, so FP64 latency has to be hidden inside the thread)
+    double gx[2] = {0.0, 0.0}, gy[2] = {0.0, 0.0}, gz[2] = {0.0, 0.0};
+    int nx_ = 0, ny_ = 0, nz_ = 0;
 #pragma unroll
-    for (int k = 0; k < 19; ++k) {
-        if (k == L19f::REST) continue;
-        const double *R = L19f::cx(k) < 0 ? Rm : (L19f::cx(k) > 0 ? Rp : R0);
-        double v = R[q + L19f::cy(k) * ZR + L19f::cz(k)];
-        if (WALLS && (wall & (1u << k))) v = xc;
-        if (L19f::cx(k)) gx += L19f::t(k) * L19f::cx(k) * v;
-        if (L19f::cy(k)) gy += L19f::t(k) * L19f::cy(k) * v;
-        if (L19f::cz(k)) gz += L19f::t(k) * L19f::cz(k) * v;
+    for (int k = 0; k < 9; ++k) {
+        const int ko = L19f::opp(k);
+        const double *Ra = L19f::cx(k) < 0 ? Rm : (L19f::cx(k) > 0 ? Rp : R0);
+        const double *Rb = L19f::cx(ko) < 0 ? Rm : (L19f::cx(ko) > 0 ? Rp : R0);
+        double va = Ra[q + L19f::cy(k) * ZR + L19f::cz(k)];
+        double vb = Rb[q + L19f::cy(ko) * ZR + L19f::cz(ko)];
+        if (WALLS && (wall & (1u << k))) va = xc;
+        if (WALLS && (wall & (1u << ko))) vb = xc;
+        const double d = L19f::t(k) * (va - vb);
+        if (L19f::cx(k)) { gx[nx_ & 1] += L19f::cx(k) * d; ++nx_; }
+        if (L19f::cy(k)) { gy[ny_ & 1] += L19f::cy(k) * d; ++ny_; }
+        if (L19f::cz(k)) { gz[nz_ & 1] += L19f::cz(k) * d; ++nz_; }
     }
-    g[0] = 3.0 * gx;
-    g[1] = 3.0 * gy;
-    g[2] = 3.0 * gz;
+    g[0] = 3.0 * (gx[0] + gx[1]);
+    g[1] = 3.0 * (gy[0] + gy[1]);
+    g[2] = 3.0 * (gz[0] + gz[1]);
 }
 
 // bit k set: the k-th neighbour of (a, b) (halo-3 ring coordinates) is a bounce_back node
@@ -190,16 +198,16 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             grad19<C::Z2, false>(r_pp + sm, r_pp + s0, r_pp + sp, q2, 0u, o.gp);
         }
         o.phi = r_phi[(p & 3) * C::R3 + q3];
-        o.rho = mp.rho_g + ((o.phi - mp.phi_g) / (mp.phi_l - mp.phi_g)) * (mp.rho_l - mp.rho_g);
+        o.rho = mp.rho_g + ((o.phi - mp.phi_g) * mp.inv_dphi) * mp.drho;
         o.Fx = mp.kappa * o.phi * gl[0];
         o.Fy = mp.kappa * o.phi * gl[1] + mp.gravity * o.rho;
         o.Fz = mp.kappa * o.phi * gl[2];
         const double inv_d = 3.0 / o.rho;          // 1 / (rho/3)
-        o.u0 = (mo[1] + o.Fx / 6.) * inv_d;
-        o.u1 = (mo[2] + o.Fy / 6.) * inv_d;
-        o.u2 = (mo[3] + o.Fy / 6.) * inv_d;        // sic: forcey (laplace3D.h:304)
+        o.u0 = (mo[1] + o.Fx * (1. / 6.)) * inv_d;
+        o.u1 = (mo[2] + o.Fy * (1. / 6.)) * inv_d;
+        o.u2 = (mo[3] + o.Fy * (1. / 6.)) * inv_d;   // sic: forcey (laplace3D.h:304)
         o.Pt = mo[0] - 0.5 * (o.u0 * o.gp[0] + o.u1 * o.gp[1] + o.u2 * o.gp[2]);
-        r_pr[(p & 3) * (C::Y1 * C::Z1) + a1 * C::Z1 + b1] = o.Pt - o.rho / 3.0;
+        r_pr[(p & 3) * (C::Y1 * C::Z1) + a1 * C::Z1 + b1] = o.Pt - o.rho * (1. / 3.);
     };
 
     const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
@@ -267,15 +275,23 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                         if (F[q] != CELL_BB) sum += L19f::t(k) * (R[q] - phi_c);
                     }
                 } else {
+                    // no wall in reach: sum_k t_k (phi_nb - phi_c) = (1/18) S_axis + (1/36) S_diag - (2/3) phi_c with the
+                    // neighbour values added in four independent chains
+                    double sa[2] = {0.0, 0.0}, sd[2] = {0.0, 0.0};
+                    int na = 0, nd = 0;
 #pragma unroll
                     for (int k = 0; k < 19; ++k) {
                         if (k == L19f::REST) continue;
                         const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
-                        sum += L19f::t(k) * (R[q3 + L19f::cy(k) * C::Z3 + L19f::cz(k)] - phi_c);
+                        const double v = R[q3 + L19f::cy(k) * C::Z3 + L19f::cz(k)];
+                        const bool axis = (L19f::cx(k) != 0) + (L19f::cy(k) != 0) + (L19f::cz(k) != 0) == 1;
+                        if (axis) { sa[na & 1] += v; ++na; }
+                        else { sd[nd & 1] += v; ++nd; }
                     }
+                    sum = (1. / 18.) * (sa[0] + sa[1]) + (1. / 36.) * (sd[0] + sd[1]) - (2. / 3.) * phi_c;
                 }
                 r_lap[(p & 3) * C::R2 + c2_q2[j]] = 6.0 * sum;
-                r_pp[(p & 3) * C::R2 + c2_q2[j]] = hcz_psi(phi_c, mp.a, mp.b);
+                r_pp[(p & 3) * C::R2 + c2_q2[j]] = hcz_psi1(phi_c, mp.a, mp.b);
             }
         }
         __syncthreads();
@@ -312,7 +328,7 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const double uF = u0 * Fx + u1 * Fy + u2 * Fz;
                 const double uE = u0 * ge[0] + u1 * ge[1] + u2 * ge[2];
                 const double uG = u0 * cur.gp[0] + u1 * cur.gp[1] + u2 * cur.gp[2];
-                const double rho3 = rho / 3.0;
+                const double rho3 = rho * (1. / 3.);
                 const double ffs = hw * 3.0 * phi / rho;   // ff = hw * C * 3 * eqf / rho,  eqf = phi * Gamma
                 const int xp = g.wx(x + 1), xm = g.wx(x - 1);
                 const int i = (x + G) * plane + yz;
