@@ -106,6 +106,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md, MEASURED_PEAKS.json absent)"
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed `ncu --set full`
+    capture of this same workload and lattice (profiles/ncu_traffic.json, written by profiles/update_traffic.py);
+    None when no capture of this configuration exists"""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        e = json.load(open(path)).get(key)
+        return (e["traffic"], "profiles/" + e["report"].replace(".ncu-rep", "") + " (ncu --set full, one launch)") if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def cpu_baseline(P, key, threads=0, target_s=12.0):
     """time the CPU oracle port on a bounded sample of the same workload (rank 0, N=1)"""
     from _oracle import OracleSim, max_threads
@@ -277,8 +289,12 @@ def main():
     blu = P.MODEL_BYTES_PER_LU[prm.model]
     peak, peak_src = measured_peak_gbs()
     achieved = (blu * prm.nelem / (kms * 1e-3) / 1e9) if kms > 0 else None
+    tkey = a.workload if (a.workload != "c3_hcz_d2q9_slab" and not a.size and world == 1) else \
+        ("c3_hcz_d2q9_2048x8194" if (key == "hcz2d" and (nxl, ny) == (2048, 8194) and world == 1) else None)
+    traffic, traffic_src = ncu_traffic(tkey) if tkey else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": blu * prm.nelem,
                 "kernel": kname, "kernel_ms": kms, "kernel_launches_sampled": kcount,
                 "algorithmic_bytes_per_lu": blu, "lattice_updates_per_launch": prm.nelem, "peak_source": peak_src,
                 "step_frac_of_peak": blu * nelem_total / world * a.steps / (ms * 1e-3) / 1e9 / peak}
@@ -396,8 +412,10 @@ def run_pulsatile(a, rank, world, local_rank):
     blu = P.PULSATILE_BYTES_PER_LU
     peak, peak_src = measured_peak_gbs()
     achieved = blu * nelem / (kms * 1e-3) / 1e9 if kms > 0 else None
+    traffic, traffic_src = ncu_traffic("c5_pulsatile_1024") if (N == 1024 and world == 1) else (None, None)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                "traffic": None, "kernel": "pulsatile iteration (collide + bouzidi x2 + stream/ZouHe/moments + walls + fobj + seed)",
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": blu * nelem,
+                "kernel": "pulsatile iteration (collide + bouzidi x2 + stream/ZouHe/moments + walls + fobj + seed)",
                 "state_finite": bool(np.isfinite(sim.fields()["P"]).all()),
                 "kernel_ms": kms, "kernel_launches_sampled": kcount, "algorithmic_bytes_per_lu": blu,
                 "lattice_updates_per_launch": nelem, "peak_source": peak_src}

@@ -266,9 +266,15 @@ static int launch_tma(clbm_ctx *c, int x_begin, int x_end)
     const cuuint64_t strides[3] = {(cuuint64_t)g.nz * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.ncs * 8};
     const cuuint32_t box[4] = {(cuuint32_t)C::BZ, (cuuint32_t)C::SY, 1, 19};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
+    // box rows are 544 B starting 16 B before a 512-B boundary: 256-B promotion over-fetches a third of every row
+    // (ncu at 512^3: 31.6 GB read for 20.4 GB of populations); 64 B measured best (profiles/README.md)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+    if (const char *e = getenv("CLBM_TMA_PROMO")) {
+        const int v = atoi(e);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo));
+    }
     CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)c->pop[0][c->parity], dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
 
     const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
