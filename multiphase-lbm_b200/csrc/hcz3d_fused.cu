@@ -396,9 +396,10 @@ static int launch_hcz3d_fused(clbm_ctx *c)
         if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
     }
     const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
-    int xchunk = g.nx;
+    // every chunk pays a 6-plane pipeline fill, so chunks stay long here (128 planes measured best at 512^3)
+    int xchunk = g.nx < 128 ? g.nx : 128;
     const long long want = 4LL * 148;
-    if ((long long)tiles < want) {
+    if ((long long)tiles * ((g.nx + xchunk - 1) / xchunk) < want) {
         const long long nch = (want + tiles - 1) / tiles;
         xchunk = (int)((g.nx + nch - 1) / nch);
         if (xchunk < 32) xchunk = g.nx < 32 ? g.nx : 32;

@@ -43,7 +43,12 @@ struct TmaCfg {
     static_assert(NH <= NT, "one halo cell per thread");
 };
 
-template <int TY, int TZ, int MINB>
+// CY > 1: the kernel is launched in thread-block clusters of CY tiles along y that cross a cluster barrier once per
+// plane.  Nothing is exchanged through it -- it only keeps y-neighbouring tiles on the same plane, so that the halo
+// rows they share (box rows y0-1 / y0+TY of one tile are own rows of the next) are fetched from HBM once and hit in
+// L2 the second time.  Without it tiles drift apart by several planes and the rows are evicted in between (ncu at
+// 512^3: 31.6 GB read for 20.4 GB of populations).
+template <int TY, int TZ, int MINB, int CY>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, const uint8_t *__restrict__ flag,
                     const double *__restrict__ fin, const double *__restrict__ psi_g, Geom g, ModelParams mp, int xchunk,
@@ -189,6 +194,10 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
             const unsigned bit = 1u << ((r + 1) & 3);
             wmask = __syncthreads_or(has_wall(fo_now, fh_now)) ? (wmask | bit) : (wmask & ~bit);
         }
+        if (CY > 1) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
         if (tid == 0 && r + 2 <= nplanes + 1) issue(r + 2);
 
         const int sm = (r + 3) & 3, s0 = r & 3, sp = (r + 1) & 3;
@@ -256,8 +265,8 @@ bool sc_tma_eligible(const clbm_ctx *c)
     return c->Q == 19 && (g.nz % 2 == 0) && g.ncs < (1LL << 31) && get_encode() != nullptr;
 }
 
-template <int TY, int TZ, int MINB>
-static int launch_tma(clbm_ctx *c, int x_begin, int x_end)
+template <int TY, int TZ, int MINB, int CY>
+static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end)
 {
     using C = TmaCfg<TY, TZ>;
     const Geom &g = c->geo;
@@ -280,27 +289,57 @@ static int launch_tma(clbm_ctx *c, int x_begin, int x_end)
     const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
     const int nxr = x_end - x_begin;
     if (nxr <= 0) return 0;
-    int xchunk = nxr;
-    const long long want = 6LL * 148 * MINB;
-    if ((long long)tiles < want) {
-        const long long nch = (want + tiles - 1) / tiles;
-        xchunk = (int)((nxr + nch - 1) / nch);
-        if (xchunk < 16) xchunk = nxr < 16 ? nxr : 16;
-    }
+    // Short x-chunks keep the CTAs that are resident at the same time on neighbouring planes, so the halo rows that
+    // y/z-neighbouring tiles share are still in L2 when the second tile asks for them: at 512^3 chunks of 20-24 planes
+    // give 16.3 GLUPS against 14.8 for 256-plane chunks, although every chunk re-reads two prologue planes (sweep in
+    // profiles/README.md).  (tiles is only used to keep at least one full wave of CTAs.)
+    int xchunk = nxr < 24 ? nxr : 24;
+    if ((long long)tiles * ((nxr + xchunk - 1) / xchunk) < 148LL * MINB && nxr > 8) xchunk = 8;
     if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < nxr ? v : nxr; }
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (nxr + xchunk - 1) / xchunk);
     OutTable P;
     for (int k = 0; k < 19; ++k) P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
-    auto kern = sc_fused_tma_kernel<TY, TZ, MINB>;
+    auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY>;
     static bool attr_set = false;
     if (!attr_set) {
         CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         attr_set = true;
     }
     LaunchScope ls(c, "sc_fused_tma_collide_stream", nxr * 2 >= g.nx);   // the boundary-plane launches of the overlap protocol are not the dominant kernel
-    kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], c->fld[0], g, c->mp, xchunk, x_begin, x_end);
+    if (CY == 1) {
+        kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], c->fld[0], g, c->mp, xchunk, x_begin, x_end);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(TY * TZ, 1, 1);
+        cfg.dynamicSmemBytes = C::SMEM;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 1;
+        at[0].val.clusterDim.y = CY;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const uint8_t *fl = c->flag;
+        const double *fin = c->pop[0][c->parity], *psi = c->fld[0];
+        CLBM_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, P, fl, fin, psi, g, c->mp, xchunk, x_begin, x_end));
+    }
     CLBM_CUDA(cudaGetLastError());
     return 0;
+}
+
+// lock-step clusters along y are an experiment (CLBM_SC_CLUSTER = 2 / 4): measured SLOWER at 512^3 (12.8 / 11.8 vs 14.8
+// GLUPS) -- waiting for the slower partner costs more than the shared halo rows save -- so the default is 1
+template <int TY, int TZ, int MINB>
+static int launch_tma(clbm_ctx *c, int x_begin, int x_end)
+{
+    int cy = 1;
+    if (const char *e = getenv("CLBM_SC_CLUSTER")) cy = atoi(e);
+    const int ytiles = (c->geo.ny + TY - 1) / TY;
+    if (MINB == 1 && cy >= 4 && ytiles % 4 == 0) return launch_tma_c<TY, TZ, MINB, 4>(c, x_begin, x_end);
+    if (MINB == 1 && cy >= 2 && ytiles % 2 == 0) return launch_tma_c<TY, TZ, MINB, 2>(c, x_begin, x_end);
+    return launch_tma_c<TY, TZ, MINB, 1>(c, x_begin, x_end);
 }
 
 // collide + push of the planes [x_begin, x_end) of the slab
