@@ -193,41 +193,21 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         double forcex = mp.kappa * rho * glx;
         double forcey = mp.kappa * rho * gly;
         forcey += mp.gravity * rho;
-        // two divisions per node (3/rho, 1/phi); every division by a constant is a multiplication by its reciprocal
+        // one division per node here (3/rho); every division by a constant is a multiplication by its reciprocal
         const double inv_r3 = 3.0 / rho, rho3 = rho * (1.0 / 3.0);
         const double u0 = (jx + forcex * (1.0 / 6.0)) * inv_r3;
         const double u1 = (jy + forcey * (1.0 / 6.0)) * inv_r3;
         const double Pp = Pt - 0.5 * ((u0 * -grx + u1 * -gry) * (1.0 / 3.0));
         const double usqr = 1.5 * (u0 * u0 + u1 * u1);
-        const double inv_phi = 1.0 / phi;
 
         const int xp = g.wx(x + 1), xm = g.wx(x - 1);
         const int oxm = (xm - x) * ny, oxp = (xp - x) * ny;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            double pf, pg;
-            if (k == 4) {
-                const double eqf0 = phi * L9f::t(4) * (1. - usqr);
-                const double eqg0 = L9f::t(4) * (Pp - rho3 * usqr);
-                const double fg0 = hw * (-(u0 * forcex + u1 * forcey) * eqf0 * inv_phi +
-                                         ((u0 * -Ex + u1 * -Ey) * (eqf0 * inv_phi - L9f::t(4))));
-                const double ff0 = hw * (-3.0 * (u0 * -gpx + u1 * -gpy) * eqf0 * inv_phi);
-                pf = (1 - omega) * f[4] + omega * eqf0 + ff0;
-                pg = (1 - omega) * gg[4] + omega * eqg0 + fg0;
-                P.fout[4][i] = pf;
-                P.gout[4][i] = pg;
-                continue;
-            }
-            const double ck_u = L9f::cx(k) * u0 + L9f::cy(k) * u1;
-            const double poly = 3 * ck_u + 4.5 * ck_u * ck_u - usqr;
-            const double eqf = phi * L9f::t(k) * (1 + poly);
-            const double eqg = L9f::t(k) * (Pp + rho3 * poly);
-            const double e_u_x = L9f::cx(k) - u0, e_u_y = L9f::cy(k) - u1;
-            const double fg = hw * ((e_u_x * forcex + e_u_y * forcey) * eqf * inv_phi) +
-                              hw * ((e_u_x * -Ex) + (e_u_y * -Ey)) * (eqf * inv_phi - L9f::t(k));
-            const double ff = hw * ((e_u_x * -gpx) + (e_u_y * -gpy)) * 3.0 * eqf * inv_phi;
-            pf = (1. - omega) * f[k] + omega * eqf + ff;
-            pg = (1. - omega) * gg[k] + omega * eqg + fg;
+        // eqf / phi = t_k (1 + poly) =: Gamma, so neither eqf nor 1/phi is formed; opposite directions share c.u, c.F, c.E,
+        // c.G up to the sign and are collided in pairs (even part once, odd part added / subtracted).
+        // Forcing vectors as the reference writes them: F (forcex, forcey), -E (grad psi(rho)), -grad psi(phi).
+        const double uF = u0 * forcex + u1 * forcey, uE = u0 * Ex + u1 * Ey, uG = u0 * gpx + u1 * gpy;
+        const double om1 = 1. - omega, op = omega * phi, hw3 = 3.0 * hw;
+        auto push = [&](int k, double pf, double pg) {
             if (wall & (1u << k)) {
                 P.fout[L9f::opp(k)][i] = pf;
                 P.gout[L9f::opp(k)][i] = pg;
@@ -236,6 +216,35 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
                 P.fout[k][i + off] = pf;
                 P.gout[k][i + off] = pg;
             }
+        };
+        {   // rest population (:642-663)
+            const double t = L9f::t(4);
+            const double Gam = t * (1. - usqr);
+            const double eqg0 = t * (Pp - rho3 * usqr);
+            const double fg0 = hw * (-uF * Gam - uE * (Gam - t));      // (u.(-E)) as the reference writes it
+            const double ff0 = hw3 * uG * Gam;
+            P.fout[4][i] = om1 * f[4] + op * Gam + ff0;
+            P.gout[4][i] = om1 * gg[4] + omega * eqg0 + fg0;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ko = L9f::opp(k);
+            const double t = L9f::t(k);
+            const double cu = L9f::cx(k) * u0 + L9f::cy(k) * u1;
+            const double cF = L9f::cx(k) * forcex + L9f::cy(k) * forcey;
+            const double cE = L9f::cx(k) * Ex + L9f::cy(k) * Ey;
+            const double cG = L9f::cx(k) * gpx + L9f::cy(k) * gpy;
+            const double ev = 4.5 * cu * cu - usqr, od = 3. * cu;
+            const double Ge = t * (1. + ev), Go = t * od;
+            const double qe = t * (Pp + rho3 * ev), qo = rho3 * Go;
+            const double Gp = Ge + Go, Gm = Ge - Go;
+            // fg = hw [ (e-u).F Gam + (e-u).(-E) (Gam - t) ],  ff = hw (e-u).(-grad psi(phi)) 3 Gam
+            const double fgp = hw * ((cF - uF) * Gp - (cE - uE) * (Gp - t));
+            const double fgm = hw * ((-cF - uF) * Gm + (cE + uE) * (Gm - t));
+            const double ffp = -hw3 * (cG - uG) * Gp;
+            const double ffm = hw3 * (cG + uG) * Gm;
+            push(k, om1 * f[k] + op * Gp + ffp, om1 * gg[k] + omega * (qe + qo) + fgp);
+            push(ko, om1 * f[ko] + op * Gm + ffm, om1 * gg[ko] + omega * (qe - qo) + fgm);
         }
     }
 }
