@@ -12,6 +12,8 @@
 // the neighbouring population array; those reads are reproduced literally.
 //
 // Kernels (one time step, AB:764-790):
+//   puls_fused     collide of all fluid nodes + pull stream + moments of the INTERIOR fluid nodes in one column-marching
+//                  pass (default; CLBM_PULS_FUSED=0 selects the two-pass form puls_collide + puls_stream on all nodes)
 //   puls_collide   MRT_Collision (AB:533-541) on fluid nodes: out = in - M^-1 S M (in - geq(P, Ux, Uy))
 //   puls_bouzidi   border-node discovery (AB:294-382) + Bouzidi_quadratic (AB:553-601), one thread per column, one launch per wall;
 //                  the Delta arrays are recomputed from the wall positions instead of being stored
@@ -21,8 +23,10 @@
 //                  per column; Fobj (AB:275-285) is a pure function of the wall positions and is never stored
 //   puls_seed      Seed_From_Nearest_Fluid (AB:418-458) for fresh nodes of a stretch that opens up, in sweep order
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "clbm_internal.h"
@@ -53,15 +57,29 @@ __host__ __device__ constexpr int eyI(int I) { constexpr int v[9] = {0, 0, 1, 0,
 __host__ __device__ constexpr int jbI(int I) { constexpr int v[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6}; return v[I]; }
 __host__ __device__ constexpr int kfromI(int I) { constexpr int v[9] = {4, 5, 6, 0, 1, 7, 3, 2, 8}; return v[I]; }
 
-// AB:501-507
+// AB:501-507.  Rho0 is 1 in the reference (hsize = 1, AB:97-98): Rho0 / 3.0 is then the constant RN(1/3) and no division runs.
 __host__ __device__ inline void equilibrium_g(double Rho0, double P, double U, double V, double geq[9])
 {
     const double U2 = U * U + V * V;
+    const double r3 = (Rho0 == 1.0) ? (1.0 / 3.0) : Rho0 / 3.0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
         const double eU = ckx(k) * U + cky(k) * V;
-        geq[k] = tk(k) * (P + Rho0 / 3.0 * (eU * (3.0 + 4.5 * eU) - 1.5 * U2));
+        geq[k] = tk(k) * (P + r3 * (eU * (3.0 + 4.5 * eU) - 1.5 * U2));
     }
+}
+
+// x / C for a small integer constant C, CORRECTLY ROUNDED like the IEEE division it replaces, in three instructions
+// (Markstein: q0 = RN(x r), rem = x - C q0 exactly by FMA, q = RN(q0 + rem r), r = RN(1/C)); an IEEE FP64 division is a
+// ~30-instruction sequence with a branch, and reconvert() has ten of them per node.  Checked against x / C on 3e8
+// operands per constant (multiples, neighbours of multiples, random mantissas over 1900 binades): no mismatch.  Valid
+// for normal quotients, which populations always are (0, Inf, NaN behave like the division).
+template <int C> __device__ __forceinline__ double divc(double x)
+{
+    constexpr double r = 1.0 / C;
+    const double q0 = __dmul_rn(x, r);
+    const double rem = __fma_rn(-(double)C, q0, x);
+    return __fma_rn(rem, r, q0);
 }
 
 // AB:509-531: the moment transform is written for I-ordered input but receives k-ordered arrays
@@ -79,16 +97,22 @@ __device__ __forceinline__ void convert(const double IN[9], double OUT[9])
 }
 __device__ __forceinline__ void reconvert(const double IN[9], double OUT[9])
 {
-    const double C0 = IN[0] / 9.0, C7 = IN[7] / 4.0, C8 = IN[8] / 4.0;
-    OUT[0] = C0 - (IN[1] - IN[2]) / 9.0;
-    OUT[1] = C0 - (IN[1] + 2 * IN[2]) / 36.0 + (IN[3] - IN[4]) / 6.0 + C7;
-    OUT[2] = C0 - (IN[1] + 2 * IN[2]) / 36.0 + (IN[5] - IN[6]) / 6.0 - C7;
-    OUT[3] = C0 - (IN[1] + 2 * IN[2]) / 36.0 - (IN[3] - IN[4]) / 6.0 + C7;
-    OUT[4] = C0 - (IN[1] + 2 * IN[2]) / 36.0 - (IN[5] - IN[6]) / 6.0 - C7;
-    OUT[5] = C0 + (IN[2] + 2 * IN[1]) / 36.0 + (IN[3] + IN[5]) / 6.0 + (IN[4] + IN[6]) / 12.0 + C8;
-    OUT[6] = C0 + (IN[2] + 2 * IN[1]) / 36.0 - (IN[3] - IN[5]) / 6.0 - (IN[4] - IN[6]) / 12.0 - C8;
-    OUT[7] = C0 + (IN[2] + 2 * IN[1]) / 36.0 - (IN[3] + IN[5]) / 6.0 - (IN[4] + IN[6]) / 12.0 + C8;
-    OUT[8] = C0 + (IN[2] + 2 * IN[1]) / 36.0 + (IN[3] - IN[5]) / 6.0 + (IN[4] - IN[6]) / 12.0 - C8;
+    // the reference's expressions with every "/ c" evaluated by divc<c> (same correctly rounded value) and the repeated
+    // quotients named once (the compiler would do the same CSE on the division form)
+    const double C0 = divc<9>(IN[0]), C7 = IN[7] / 4.0, C8 = IN[8] / 4.0;
+    const double a36 = divc<36>(IN[1] + 2 * IN[2]), b36 = divc<36>(IN[2] + 2 * IN[1]);
+    const double d34 = divc<6>(IN[3] - IN[4]), d56 = divc<6>(IN[5] - IN[6]);
+    const double s35 = divc<6>(IN[3] + IN[5]), d35 = divc<6>(IN[3] - IN[5]);
+    const double s46 = divc<12>(IN[4] + IN[6]), d46 = divc<12>(IN[4] - IN[6]);
+    OUT[0] = C0 - divc<9>(IN[1] - IN[2]);
+    OUT[1] = C0 - a36 + d34 + C7;
+    OUT[2] = C0 - a36 + d56 - C7;
+    OUT[3] = C0 - a36 - d34 + C7;
+    OUT[4] = C0 - a36 - d56 - C7;
+    OUT[5] = C0 + b36 + s35 + s46 + C8;
+    OUT[6] = C0 + b36 - d35 - d46 - C8;
+    OUT[7] = C0 + b36 - s35 - s46 + C8;
+    OUT[8] = C0 + b36 + d35 + d46 - C8;
 }
 
 // Fobj in the reference's padded coordinates (Xp = X+1 in [1, nx], Yp = Y+1 in [0, ny+1]) as the pure function of the
@@ -100,17 +124,11 @@ __host__ __device__ inline double fobj(const double *yr1, const double *yr2, con
     return (Y <= g.Y0 ? (yr1[X] - g.c) : (yr2[X] - g.c)) / (Y - g.c);
 }
 
-// ---- collide ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) puls_collide(const double *__restrict__ A, double *__restrict__ B,
-                                                    const uint8_t *__restrict__ flag, const double *__restrict__ P,
-                                                    const double *__restrict__ Ux, const double *__restrict__ Uy, Geo g, Par mp)
+// MRT_Collision of one node held in registers (shared by puls_collide and puls_fused: identical operations)
+__device__ __forceinline__ void mrt_post(const Par &mp, const double gin[9], double P, double Ux, double Uy, double post[9])
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.nelem || flag[i] == 0) return;
-    double gin[9], geq[9], tmp[9], m[9], dpost[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) gin[k] = A[k * g.nelem + i];
-    equilibrium_g(mp.Rho0, P[i], Ux[i], Uy[i], geq);
+    double geq[9], tmp[9], m[9], dpost[9];
+    equilibrium_g(mp.Rho0, P, Ux, Uy, geq);
 #pragma unroll
     for (int k = 0; k < 9; ++k) tmp[k] = gin[k] - geq[k];
     convert(tmp, m);
@@ -118,7 +136,142 @@ __global__ void __launch_bounds__(256) puls_collide(const double *__restrict__ A
     for (int q = 0; q < 9; ++q) m[q] *= mp.S[q];
     reconvert(m, dpost);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) B[k * g.nelem + i] = gin[k] - dpost[k];
+    for (int k = 0; k < 9; ++k) post[k] = gin[k] - dpost[k];
+}
+
+// ---- collide ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) puls_collide(const double *__restrict__ A, double *__restrict__ B,
+                                                    const uint8_t *__restrict__ flag, const double *__restrict__ P,
+                                                    const double *__restrict__ Ux, const double *__restrict__ Uy, Geo g, Par mp)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.nelem || flag[i] == 0) return;
+    double gin[9], post[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gin[k] = A[k * g.nelem + i];
+    mrt_post(mp, gin, P[i], Ux[i], Uy[i], post);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) B[k * g.nelem + i] = post[k];
+}
+
+// ---- fused collide + pull stream + moments for INTERIOR fluid nodes ---------------------------------------
+// An interior node is a fluid node off the lattice rim (1 <= X <= nx-2, 1 <= Y <= ny-2) whose eight neighbours are all
+// fluid: every population it pulls is a plain post-collision value -- no Bouzidi value, no stale solid-node value, no
+// Zou/He column, no flat-index spill.  For those nodes (almost all of them) the reference's
+//     collide -> [Bouzidi] -> pull -> [Zou/He] -> moments
+// is done here in one pass: a CTA owns NT-2 consecutive rows and marches along x with a 3-column shared-memory ring of
+// post-collision populations; column x+1 is collided (and written to the out buffer, which the NEXT iteration's
+// collision reads un-streamed -- SURVEY.md B.1), then column x is streamed out of the ring and its P, Ux, Uy are
+// written.  The streamed populations of an interior node are NOT written to the in buffer: the reference overwrites
+// them with the next post-collision values before anything reads them, except (a) a fresh node being seeded from
+// nodes >= 3 links away and (b) a lattice download -- both re-create them on demand (interior_streamed below).
+// Everything else (solid nodes, fluid nodes next to a solid node, the rim) goes through puls_stream after the Bouzidi
+// kernels, exactly as in the unfused path.  P, Ux, Uy are double buffered: the collision of a halo row / column reads
+// the old values while its owner may already have written the new ones.
+// Traffic per interior node: 9 + 3 doubles read, 9 + 3 written (192 B) instead of 336 B for collide + stream.
+template <int NT>
+__global__ void __launch_bounds__(NT) puls_fused(const double *__restrict__ A, double *__restrict__ B, const uint8_t *__restrict__ flag,
+                                                 const double *__restrict__ P, const double *__restrict__ Ux,
+                                                 const double *__restrict__ Uy, double *__restrict__ Pn, double *__restrict__ Uxn,
+                                                 double *__restrict__ Uyn, uint8_t *__restrict__ intr, Geo g, Par mp, int xchunk)
+{
+    __shared__ double R[3][9][NT];
+    __shared__ uint8_t F[3][NT];
+    const int tid = threadIdx.x;
+    const int Y = (int)blockIdx.x * (NT - 2) - 1 + tid;          // rows tid = 0 and NT-1 are halo rows
+    const bool row_ok = Y >= 0 && Y < g.ny;
+    const bool own = tid >= 1 && tid < NT - 1 && row_ok;
+    const int xa = blockIdx.y * xchunk, xb = min(g.nx, xa + xchunk);
+    auto slot_of = [](int X) { return (X + 3) % 3; };
+    // the 12 inputs of a column's collision are loaded ONE COLUMN AHEAD into registers, so a thread always has loads in
+    // flight while it computes, waits at the barriers and streams (the kernel is bound by memory-level parallelism, not
+    // by instruction issue: without the prefetch it moved 3.9 TB/s)
+    double nin[12];
+    uint8_t nfl = 0;
+    auto fetch_col = [&](int X) {
+        nfl = 0;
+        if (row_ok && X >= 0 && X < g.nx) nfl = flag[Y + (long long)g.ny * X];
+        if (!nfl) return;
+        const long long i = Y + (long long)g.ny * X;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) nin[k] = A[k * g.nelem + i];
+        nin[9] = P[i]; nin[10] = Ux[i]; nin[11] = Uy[i];
+    };
+    // collides column X from the prefetched registers, then prefetches column X + 1
+    auto collide_col = [&](int X, bool write, bool more) {
+        const int s = slot_of(X);
+        const uint8_t fl = nfl;
+        double gin[9], post[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gin[k] = nin[k];
+        const double p0 = nin[9], u0 = nin[10], v0 = nin[11];
+        if (more) fetch_col(X + 1);
+        F[s][tid] = fl;
+        if (!fl) return;
+        mrt_post(mp, gin, p0, u0, v0, post);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[s][k][tid] = post[k];
+        if (write && own) {
+            const long long i = Y + (long long)g.ny * X;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) B[k * g.nelem + i] = post[k];
+        }
+    };
+    fetch_col(xa - 1);
+    collide_col(xa - 1, false, true);
+    collide_col(xa, true, true);
+    for (int X = xa; X < xb; ++X) {
+        collide_col(X + 1, X + 1 < xb, X + 1 < xb);
+        __syncthreads();
+        if (own) {
+            const int sm = slot_of(X - 1), s0 = slot_of(X), sp = slot_of(X + 1);
+            const bool interior = X >= 1 && X <= g.nx - 2 && Y >= 1 && Y <= g.ny - 2 &&
+                                  (F[sm][tid - 1] & F[sm][tid] & F[sm][tid + 1] & F[s0][tid - 1] & F[s0][tid] & F[s0][tid + 1] &
+                                   F[sp][tid - 1] & F[sp][tid] & F[sp][tid + 1]) != 0;
+            intr[Y + (long long)g.ny * X] = interior ? 1 : 0;      // puls_stream skips these nodes (one coalesced byte per node)
+            if (interior) {
+                double gk[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gk[k] = R[ckx(k) > 0 ? sm : (ckx(k) < 0 ? sp : s0)][k][tid - cky(k)];   // source (X - cx, Y - cy)
+                double pp = 0.0, ux = 0.0, uy = 0.0;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) pp += gk[k];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) { ux += gk[k] * ckx(k); uy += gk[k] * cky(k); }
+                const long long i = Y + (long long)g.ny * X;
+                Pn[i] = pp;
+                Uxn[i] = (mp.Rho0 == 1.0) ? 3.0 * ux : 3.0 * ux / mp.Rho0;
+                Uyn[i] = (mp.Rho0 == 1.0) ? 3.0 * uy : 3.0 * uy / mp.Rho0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// streamed ("gin" after Streaming) population k of a node that was interior when the last step ran; B = that step's out buffer
+__device__ __forceinline__ double interior_streamed(const double *__restrict__ B, const Geo &g, int X, int Y, int k)
+{
+    return B[k * g.nelem + (Y - cky(k)) + (long long)g.ny * (X - ckx(k))];
+}
+// the same predicate from the wall positions the step ran with (the mask array has moved on by the time it is asked)
+__device__ inline bool interior_by_walls(const double *yr1o, const double *yr2o, const Geo &g, int X, int Y)
+{
+    if (X < 1 || X > g.nx - 2 || Y < 1 || Y > g.ny - 2) return false;
+    for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy)
+            if (fobj(yr1o, yr2o, g, X + dx + 1, Y + dy + 1) < 1.0) return false;
+    return true;
+}
+// writes the skipped streamed populations of the last step's interior nodes into its in buffer (lattice download)
+__global__ void __launch_bounds__(256) puls_materialise(double *__restrict__ A, const double *__restrict__ B, const double *__restrict__ yr1o,
+                                                        const double *__restrict__ yr2o, Geo g)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.nelem) return;
+    const int X = (int)(i / g.ny), Y = (int)(i % g.ny);
+    if (!interior_by_walls(yr1o, yr2o, g, X, Y)) return;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) A[k * g.nelem + i] = interior_streamed(B, g, X, Y, k);
 }
 
 // ---- Bouzidi ---------------------------------------------------------------------------------------
@@ -228,10 +381,11 @@ __global__ void __launch_bounds__(128) puls_bouzidi(double *__restrict__ B, cons
 __global__ void __launch_bounds__(256) puls_stream(double *__restrict__ lat, long long bin, long long bout, const uint8_t *__restrict__ flag,
                                                    double *__restrict__ P, double *__restrict__ Ux, double *__restrict__ Uy,
                                                    const double *__restrict__ yr1, const double *__restrict__ yr2, Geo g, Par mp,
-                                                   double Pin, double Pout)
+                                                   double Pin, double Pout, const uint8_t *__restrict__ intr)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.nelem) return;
+    if (intr && intr[i]) return;                                     // done by puls_fused
     const int X = (int)(i / g.ny), Y = (int)(i % g.ny);
     const double *B = lat + bout;
     double gk[9];
@@ -289,8 +443,8 @@ __global__ void __launch_bounds__(256) puls_stream(double *__restrict__ lat, lon
 #pragma unroll
         for (int k = 1; k < 9; ++k) { ux += gk[k] * ckx(k); uy += gk[k] * cky(k); }
         P[i] = pp;
-        Ux[i] = 3.0 * ux / Rho0;
-        Uy[i] = 3.0 * uy / Rho0;
+        Ux[i] = (Rho0 == 1.0) ? 3.0 * ux : 3.0 * ux / Rho0;
+        Uy[i] = (Rho0 == 1.0) ? 3.0 * uy : 3.0 * uy / Rho0;
     }
 }
 
@@ -423,7 +577,8 @@ __global__ void __launch_bounds__(32) puls_seed(double *__restrict__ A, const ui
                                                 double *__restrict__ Ux, double *__restrict__ Uy, const double *__restrict__ yr1,
                                                 const double *__restrict__ yr2, const double *__restrict__ yr1o,
                                                 const double *__restrict__ yr2o, Geo g, Par mp, const double *__restrict__ pre,
-                                                int *__restrict__ seed_count, int *__restrict__ seed_list, int seed_cap)
+                                                int *__restrict__ seed_count, int *__restrict__ seed_list, int seed_cap,
+                                                const double *__restrict__ B, int fused)
 {
     int n = *seed_count;
     if (n == 0) return;
@@ -447,7 +602,11 @@ __global__ void __launch_bounds__(32) puls_seed(double *__restrict__ A, const ui
             const int idn = Yn + ny * Xn;
             if (flag[idn] == 0) return;
             const bool later_fresh = idn > id && fobj(yr1o, yr2o, g, Xn + 1, Yn + 1) < 1 && fobj(yr1, yr2, g, Xn + 1, Yn + 1) >= 1;
-            if (lane < 9) acc += later_fresh ? pre[pre_slot(Xn, Yn, g) + lane] : A[lane * g.nelem + idn];
+            // fused step: an interior node's streamed populations were never stored -- pull them from the out buffer
+            const bool skipped = fused && interior_by_walls(yr1o, yr2o, g, Xn, Yn);
+            if (lane < 9)
+                acc += later_fresh ? pre[pre_slot(Xn, Yn, g) + lane]
+                                   : (skipped ? interior_streamed(B, g, Xn, Yn, lane) : A[lane * g.nelem + idn]);
             ++cnt;
         };
         constexpr int dx[8] = {1, -1, 0, 0, 1, 1, -1, -1}, dy[8] = {0, 0, 1, -1, 1, -1, 1, -1};
@@ -507,6 +666,10 @@ struct clbm_pulsatile {
     double *lat;          // 2*npop + 1 doubles
     uint8_t *flag;
     double *P, *Ux, *Uy, *yr1, *yr2, *yr1o, *yr2o;
+    uint8_t *intr;            // fused step: 1 where puls_fused streamed the node (interior), written every step
+    double *P2, *Ux2, *Uy2;   // fused step: the set the running step writes (swapped with P, Ux, Uy afterwards)
+    int fused;                // 1: puls_fused + puls_stream on the remaining nodes (default), 0: puls_collide + puls_stream
+    bool in_complete;         // the last step's in buffer holds the streamed populations of ALL nodes (see puls_materialise)
     int *err_dev, *err_host;
     double *pre;          // pre-fill populations of this step's fresh nodes
     int *seed_count, *seed_list, seed_cap;
@@ -597,7 +760,21 @@ int one_step(clbm_pulsatile *c)
         c->kev.push_back(e);
         cudaEventRecord(e, c->stream);
     }
-    puls_collide<<<nb, 256, 0, c->stream>>>(A, B, c->flag, c->P, c->Ux, c->Uy, g, c->mp);
+    double *Pw = c->fused ? c->P2 : c->P, *Uxw = c->fused ? c->Ux2 : c->Ux, *Uyw = c->fused ? c->Uy2 : c->Uy;   // this step's P, Ux, Uy
+    if (c->fused) {
+        int xchunk = g.nx < 64 ? g.nx : 64, nt = 128;
+        if (const char *e = getenv("CLBM_PULS_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+        if (const char *e = getenv("CLBM_PULS_NT")) nt = atoi(e);
+        if (nt == 64) {
+            dim3 grid((g.ny + 62 - 1) / 62, (g.nx + xchunk - 1) / xchunk);
+            puls_fused<64><<<grid, 64, 0, c->stream>>>(A, B, c->flag, c->P, c->Ux, c->Uy, Pw, Uxw, Uyw, c->intr, g, c->mp, xchunk);
+        } else {
+            dim3 grid((g.ny + 126 - 1) / 126, (g.nx + xchunk - 1) / xchunk);
+            puls_fused<128><<<grid, 128, 0, c->stream>>>(A, B, c->flag, c->P, c->Ux, c->Uy, Pw, Uxw, Uyw, c->intr, g, c->mp, xchunk);
+        }
+    } else {
+        puls_collide<<<nb, 256, 0, c->stream>>>(A, B, c->flag, c->P, c->Ux, c->Uy, g, c->mp);
+    }
     puls_bouzidi<<<grid_for(g.nx, 128), 128, 0, c->stream>>>(B, c->yr1, c->yr2, g, 0);
     puls_bouzidi<<<grid_for(g.nx, 128), 128, 0, c->stream>>>(B, c->yr1, c->yr2, g, 1);
     // Zou/He boundary pressures of this iteration (AB:620-622, :646-650): sin() on the host, like the reference
@@ -606,16 +783,22 @@ int one_step(clbm_pulsatile *c)
     double Pout = c->p0_out;
     if (t >= c->t_start + c->t_prop) Pout = c->p0_out + c->p_osc * sin(c->omega * (t + 1 - c->t_start - c->t_prop));
     if (t > c->t_sever) Pout = 0;
-    puls_stream<<<nb, 256, 0, c->stream>>>(c->lat, (long long)c->parity * g.npop, (long long)(1 - c->parity) * g.npop, c->flag, c->P, c->Ux,
-                                           c->Uy, c->yr1, c->yr2, g, c->mp, Pin, Pout);
+    puls_stream<<<nb, 256, 0, c->stream>>>(c->lat, (long long)c->parity * g.npop, (long long)(1 - c->parity) * g.npop, c->flag, Pw, Uxw,
+                                           Uyw, c->yr1, c->yr2, g, c->mp, Pin, Pout, c->fused ? c->intr : nullptr);
     c->launches += 4;
     if (c->prm.deformable) {
-        puls_walls<<<grid_for(g.nx, 128), 128, 0, c->stream>>>(c->P, c->yr1, c->yr2, c->yr1o, c->yr2o, g, c->mp);
-        puls_fobj<<<grid_for(g.nx, 128), 128, 0, c->stream>>>(A, c->flag, c->P, c->Ux, c->Uy, c->yr1, c->yr2, c->yr1o, c->yr2o, g, c->mp,
+        puls_walls<<<grid_for(g.nx, 128), 128, 0, c->stream>>>(Pw, c->yr1, c->yr2, c->yr1o, c->yr2o, g, c->mp);
+        puls_fobj<<<grid_for(g.nx, 128), 128, 0, c->stream>>>(A, c->flag, Pw, Uxw, Uyw, c->yr1, c->yr2, c->yr1o, c->yr2o, g, c->mp,
                                                              c->pre, c->seed_count, c->seed_list, c->seed_cap, c->err_dev);
-        puls_seed<<<1, 32, 0, c->stream>>>(A, c->flag, c->P, c->Ux, c->Uy, c->yr1, c->yr2, c->yr1o, c->yr2o, g, c->mp, c->pre,
-                                           c->seed_count, c->seed_list, c->seed_cap);
+        puls_seed<<<1, 32, 0, c->stream>>>(A, c->flag, Pw, Uxw, Uyw, c->yr1, c->yr2, c->yr1o, c->yr2o, g, c->mp, c->pre,
+                                           c->seed_count, c->seed_list, c->seed_cap, B, c->fused);
         c->launches += 3;
+    }
+    if (c->fused) {
+        std::swap(c->P, c->P2);
+        std::swap(c->Ux, c->Ux2);
+        std::swap(c->Uy, c->Uy2);
+        c->in_complete = false;
     }
     if (sample) {
         cudaEvent_t e;
@@ -685,7 +868,11 @@ int clbm_pulsatile_create(const clbm_pulsatile_params *p, clbm_pulsatile **out)
     const size_t nd = (size_t)g.nelem * sizeof(double);
     if ((e = cudaMalloc(&c->lat, (2 * (size_t)g.npop + 1) * sizeof(double))) != cudaSuccess) return fail(e, "cudaMalloc lattice");
     if ((e = cudaMalloc(&c->flag, (size_t)g.nelem)) != cudaSuccess) return fail(e, "cudaMalloc flag");
-    double **fl[3] = {&c->P, &c->Ux, &c->Uy};
+    if ((e = cudaMalloc(&c->intr, (size_t)g.nelem)) != cudaSuccess) return fail(e, "cudaMalloc intr");
+    c->fused = 1;
+    if (const char *e = getenv("CLBM_PULS_FUSED")) c->fused = atoi(e) != 0;
+    c->in_complete = true;
+    double **fl[6] = {&c->P, &c->Ux, &c->Uy, &c->P2, &c->Ux2, &c->Uy2};
     for (auto f : fl) if ((e = cudaMalloc(f, nd)) != cudaSuccess) return fail(e, "cudaMalloc field");
     double **wl[4] = {&c->yr1, &c->yr2, &c->yr1o, &c->yr2o};
     for (auto w : wl) if ((e = cudaMalloc(w, g.nx * sizeof(double))) != cudaSuccess) return fail(e, "cudaMalloc wall");
@@ -718,6 +905,7 @@ int clbm_pulsatile_destroy(clbm_pulsatile *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->lat); cudaFree(c->flag); cudaFree(c->P); cudaFree(c->Ux); cudaFree(c->Uy);
+    cudaFree(c->P2); cudaFree(c->Ux2); cudaFree(c->Uy2); cudaFree(c->intr);
     cudaFree(c->yr1); cudaFree(c->yr2); cudaFree(c->yr1o); cudaFree(c->yr2o); cudaFree(c->err_dev);
     cudaFree(c->pre); cudaFree(c->seed_count); cudaFree(c->seed_list);
     if (c->err_host) cudaFreeHost(c->err_host);
@@ -821,6 +1009,14 @@ int clbm_pulsatile_download_lattice(clbm_pulsatile *c, double *lattice, int *par
 {
     if (!c || !lattice) { set_error("bad argument"); return CLBM_EINVAL; }
     CLBM_CUDA(cudaSetDevice(c->device));
+    if (!c->in_complete) {
+        // the last step's in buffer is the one the parity flip turned into the out buffer
+        double *A = c->lat + (long long)(1 - c->parity) * c->g.npop, *B = c->lat + (long long)c->parity * c->g.npop;
+        puls_materialise<<<grid_for(c->g.nelem, 256), 256, 0, c->stream>>>(A, B, c->yr1o, c->yr2o, c->g);
+        CLBM_CUDA(cudaGetLastError());
+        c->launches += 1;
+        c->in_complete = true;
+    }
     CLBM_CUDA(cudaMemcpyAsync(lattice, c->lat, 2 * (size_t)c->g.npop * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (parity) *parity = c->parity;
     return check_device_error(c);
@@ -842,7 +1038,10 @@ int clbm_pulsatile_upload(clbm_pulsatile *c, const double *lattice, const uint8_
     CLBM_CUDA(cudaMemcpyAsync(c->Uy, Uy, nd, cudaMemcpyHostToDevice, c->stream));
     CLBM_CUDA(cudaMemcpyAsync(c->yr1, yr1, c->g.nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CLBM_CUDA(cudaMemcpyAsync(c->yr2, yr2, c->g.nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CLBM_CUDA(cudaMemcpyAsync(c->yr1o, yr1, c->g.nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CLBM_CUDA(cudaMemcpyAsync(c->yr2o, yr2, c->g.nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    c->in_complete = true;
     c->parity = parity;
     c->t_iter = t_iter;
     return CLBM_OK;
