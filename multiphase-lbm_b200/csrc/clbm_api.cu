@@ -66,7 +66,7 @@ int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
 int sc_psi_all(clbm_ctx *c);
 int sc_psi_boundary(clbm_ctx *c);
 bool sc_range_supported(const clbm_ctx *c);
-int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end);
+int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end);
 int sc_collide_slab(clbm_ctx *c);
 int hcz2d_stage0(clbm_ctx *c);
 int hcz2d_stage1(clbm_ctx *c);
@@ -138,16 +138,19 @@ static int overlap_stage(clbm_ctx *c, int stage)
             BoundaryStream bs(c);
             if ((rc = sc_psi_boundary(c))) return rc;
             if ((rc = halo_pack(c, 0))) return rc;
+            // the interior launch fills every SM for the rest of the step: let these two small kernels through first
+            // (they run in ~20 us on the idle GPU; behind the interior's first wave they took 350 us)
+            CLBM_CUDA(cudaEventRecord(c->ev_b, c->stream_b));
         }
-        if ((rc = sc_collide_range_fused(c, 1, nx - 1))) return rc;
+        CLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+        if ((rc = sc_collide_range_fused(c, 1, nx - 1, 0, 0))) return rc;
         CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
         return 0;
     }
     if (stage == 11) {
         BoundaryStream bs(c);
         if ((rc = halo_unpack(c, 0))) return rc;
-        if ((rc = sc_collide_range_fused(c, 0, 1))) return rc;
-        if ((rc = sc_collide_range_fused(c, nx - 1, nx))) return rc;
+        if ((rc = sc_collide_range_fused(c, 0, 1, nx - 1, nx))) return rc;   // both boundary planes in one launch
         c->parity = 1 - c->parity;
         return halo_pack(c, 1);
     }

@@ -189,7 +189,7 @@ static int launch_fused(clbm_ctx *c)
 
 bool sc_tma_eligible(const clbm_ctx *c);            // sc_fused_tma.cu
 int sc_fused_tma_step(clbm_ctx *c, int variant);
-int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end);
+int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_begin, int x2_end);
 
 // one fused collide-stream sweep over the local planes; does NOT flip the parity
 // tile variant of the TMA kernel this context would run, 0 when it runs one of the register-pipelined kernels
@@ -205,7 +205,10 @@ static int sc_tma_variant(const clbm_ctx *c)
 
 // x-range launches (overlap protocol of the slab exchange) exist for the TMA kernel
 bool sc_range_supported(const clbm_ctx *c) { return c->prm.fused && sc_tma_variant(c) != 0; }
-int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end) { return sc_fused_tma_range(c, sc_tma_variant(c), x_begin, x_end); }
+int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
+{
+    return sc_fused_tma_range(c, sc_tma_variant(c), x_begin, x_end, x2_begin, x2_end);
+}
 
 int sc_fused_launch(clbm_ctx *c)
 {

@@ -52,7 +52,7 @@ template <int TY, int TZ, int MINB, int CY>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, const uint8_t *__restrict__ flag,
                     const double *__restrict__ fin, const double *__restrict__ psi_g, Geom g, ModelParams mp, int xchunk,
-                    int x_begin, int x_end)
+                    int x_begin, int x_end, int nch1, int x2_begin, int x2_end)
 {
     using C = TmaCfg<TY, TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -65,8 +65,11 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     const int y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
     const int y = y0 + ty, z = z0 + tz;
     const bool inside = (y < g.ny) && (z < g.nz);
-    const int xa = x_begin + blockIdx.z * xchunk;        // this CTA collides planes [xa, xa + nplanes) of [x_begin, x_end)
-    const int nplanes = min(x_end, xa + xchunk) - xa;
+    // this CTA collides planes [xa, xa + nplanes) of [x_begin, x_end) -- or, for blockIdx.z >= nch1, of the second range
+    // [x2_begin, x2_end) (the two boundary planes of the overlap protocol share one launch)
+    const bool second = (int)blockIdx.z >= nch1;
+    const int xa = second ? x2_begin + ((int)blockIdx.z - nch1) * xchunk : x_begin + (int)blockIdx.z * xchunk;
+    const int nplanes = min(second ? x2_end : x_end, xa + xchunk) - xa;
     const int plane = (int)g.plane, nz = g.nz, G = g.G;
     const int ty_n = min(TY, g.ny - y0), tz_n = min(TZ, g.nz - z0);
     const int nrow = tz_n + 2, nhalo = 2 * nrow + 2 * ty_n;
@@ -266,7 +269,7 @@ bool sc_tma_eligible(const clbm_ctx *c)
 }
 
 template <int TY, int TZ, int MINB, int CY>
-static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end)
+static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
     using C = TmaCfg<TY, TZ>;
     const Geom &g = c->geo;
@@ -296,7 +299,8 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end)
     int xchunk = nxr < 24 ? nxr : 24;
     if ((long long)tiles * ((nxr + xchunk - 1) / xchunk) < 148LL * MINB && nxr > 8) xchunk = 8;
     if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < nxr ? v : nxr; }
-    dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (nxr + xchunk - 1) / xchunk);
+    const int nch1 = (nxr + xchunk - 1) / xchunk, nch2 = x2_end > x2_begin ? (x2_end - x2_begin + xchunk - 1) / xchunk : 0;
+    dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, nch1 + nch2);
     OutTable P;
     for (int k = 0; k < 19; ++k) P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY>;
@@ -307,7 +311,7 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end)
     }
     LaunchScope ls(c, "sc_fused_tma_collide_stream", nxr * 2 >= g.nx);   // the boundary-plane launches of the overlap protocol are not the dominant kernel
     if (CY == 1) {
-        kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], c->fld[0], g, c->mp, xchunk, x_begin, x_end);
+        kern<<<grid, TY * TZ, C::SMEM, c->stream>>>(tmap, P, c->flag, c->pop[0][c->parity], c->fld[0], g, c->mp, xchunk, x_begin, x_end, nch1, x2_begin, x2_end);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
@@ -323,7 +327,7 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end)
         cfg.numAttrs = 1;
         const uint8_t *fl = c->flag;
         const double *fin = c->pop[0][c->parity], *psi = c->fld[0];
-        CLBM_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, P, fl, fin, psi, g, c->mp, xchunk, x_begin, x_end));
+        CLBM_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, P, fl, fin, psi, g, c->mp, xchunk, x_begin, x_end, nch1, x2_begin, x2_end));
     }
     CLBM_CUDA(cudaGetLastError());
     return 0;
@@ -332,32 +336,32 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end)
 // lock-step clusters along y are an experiment (CLBM_SC_CLUSTER = 2 / 4): measured SLOWER at 512^3 (12.8 / 11.8 vs 14.8
 // GLUPS) -- waiting for the slower partner costs more than the shared halo rows save -- so the default is 1
 template <int TY, int TZ, int MINB>
-static int launch_tma(clbm_ctx *c, int x_begin, int x_end)
+static int launch_tma(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
     int cy = 1;
     if (const char *e = getenv("CLBM_SC_CLUSTER")) cy = atoi(e);
     const int ytiles = (c->geo.ny + TY - 1) / TY;
-    if (MINB == 1 && cy >= 4 && ytiles % 4 == 0) return launch_tma_c<TY, TZ, MINB, 4>(c, x_begin, x_end);
-    if (MINB == 1 && cy >= 2 && ytiles % 2 == 0) return launch_tma_c<TY, TZ, MINB, 2>(c, x_begin, x_end);
-    return launch_tma_c<TY, TZ, MINB, 1>(c, x_begin, x_end);
+    if (MINB == 1 && cy >= 4 && ytiles % 4 == 0) return launch_tma_c<TY, TZ, MINB, 4>(c, x_begin, x_end, x2_begin, x2_end);
+    if (MINB == 1 && cy >= 2 && ytiles % 2 == 0) return launch_tma_c<TY, TZ, MINB, 2>(c, x_begin, x_end, x2_begin, x2_end);
+    return launch_tma_c<TY, TZ, MINB, 1>(c, x_begin, x_end, x2_begin, x2_end);
 }
 
-// collide + push of the planes [x_begin, x_end) of the slab
-int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end)
+// collide + push of the planes [x_begin, x_end) and [x2_begin, x2_end) of the slab in one launch
+int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_begin, int x2_end)
 {
     int rc;
     switch (variant) {
-    case 11: rc = launch_tma<8, 64, 1>(c, x_begin, x_end); break;
-    case 12: rc = launch_tma<16, 32, 1>(c, x_begin, x_end); break;
-    case 13: rc = launch_tma<4, 64, 1>(c, x_begin, x_end); break;
-    case 14: rc = launch_tma<4, 32, 3>(c, x_begin, x_end); break;
-    case 15: rc = launch_tma<8, 16, 3>(c, x_begin, x_end); break;
-    case 16: rc = launch_tma<8, 32, 1>(c, x_begin, x_end); break;
-    default: rc = launch_tma<6, 32, 2>(c, x_begin, x_end); break;
+    case 11: rc = launch_tma<8, 64, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 12: rc = launch_tma<16, 32, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 13: rc = launch_tma<4, 64, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 14: rc = launch_tma<4, 32, 3>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 15: rc = launch_tma<8, 16, 3>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 16: rc = launch_tma<8, 32, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
+    default: rc = launch_tma<6, 32, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
     }
     return rc;
 }
 
-int sc_fused_tma_step(clbm_ctx *c, int variant) { return sc_fused_tma_range(c, variant, 0, c->geo.nx); }
+int sc_fused_tma_step(clbm_ctx *c, int variant) { return sc_fused_tma_range(c, variant, 0, c->geo.nx, 0, 0); }
 
 }  // namespace clbm

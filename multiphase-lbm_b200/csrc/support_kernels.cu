@@ -264,6 +264,59 @@ int halo_alloc(clbm_ctx *c)
     return 0;
 }
 
+// One launch for all (side, set, direction) slots: blockIdx.y enumerates them.
+struct CrossTable {
+    double *pop[2];              // population set s of the current "in" buffer
+    const double *recv[2];       // receive buffer of side 0 / 1
+    double *send[2];             // send buffer of side 0 / 1
+    int ks[2][5];                // crossing directions sent towards side 0 / 1 (ks[1 - side] arrive from side)
+    int ncross, sets;
+};
+
+template <class L>
+__global__ void __launch_bounds__(256)
+unpack_cross_kernel(CrossTable T, const uint8_t *__restrict__ flag, Geom g)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.plane) return;
+    const int per_side = T.ncross * T.sets;
+    const int side = blockIdx.y / per_side, slot = blockIdx.y % per_side;
+    const int s = slot / T.ncross, k = T.ks[1 - side][slot % T.ncross];
+    const int y = (int)(r / g.nz), z = (int)(r % g.nz);
+    const int xb = side ? g.nx - 1 : 0;   // boundary plane that receives
+    const long long j = g.idx(xb, y, z);
+    if (flag[j] == CELL_BB) return;
+    const long long src = g.idx(xb - L::cx(k), g.wy(y - L::cy(k)), g.wz(z - L::cz(k)));
+    if (flag[src] == CELL_BB) return;
+    T.pop[s][(size_t)k * g.ncs + j] = T.recv[side][(size_t)slot * g.plane + r];
+}
+
+// ghost-plane populations (what the push wrote across the slab face) -> send buffers, all slots in one launch
+__global__ void __launch_bounds__(256) pack_cross_kernel(CrossTable T, Geom g)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= g.plane) return;
+    const int per_side = T.ncross * T.sets;
+    const int side = blockIdx.y / per_side, slot = blockIdx.y % per_side;
+    const int s = slot / T.ncross, k = T.ks[side][slot % T.ncross];
+    const int xg = side ? g.nx : -1;
+    T.send[side][(size_t)slot * g.plane + r] = T.pop[s][(size_t)k * g.ncs + (size_t)(xg + g.G) * g.plane + r];
+}
+
+static CrossTable cross_table(clbm_ctx *c)
+{
+    CrossTable T;
+    T.ncross = n_cross(c);
+    T.sets = c->sets;
+    for (int s = 0; s < 2; ++s) T.pop[s] = c->pop[s < c->sets ? s : 0][c->parity];
+    for (int side = 0; side < 2; ++side) {
+        T.recv[side] = (const double *)c->halo[1][side][1];
+        T.send[side] = (double *)c->halo[1][side][0];
+        cross_dirs(c, side, T.ks[side]);
+    }
+    return T;
+}
+
 int halo_pack(clbm_ctx *c, int phase)
 {
     const Geom &g = c->geo;
@@ -284,17 +337,11 @@ int halo_pack(clbm_ctx *c, int phase)
         return 0;
     }
     if (phase == 1) {
-        int ks[5];
-        for (int side = 0; side < 2; ++side) {
-            cross_dirs(c, side, ks);
-            const int xg = side ? g.nx : -1;   // ghost plane the push wrote into
-            double *dst = (double *)c->halo[1][side][0];
-            for (int s = 0; s < c->sets; ++s)
-                for (int i = 0; i < n_cross(c); ++i) {
-                    CLBM_CUDA(cudaMemcpyAsync(dst, c->pop[s][c->parity] + (size_t)ks[i] * g.ncs + (size_t)(xg + g.G) * pl, pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-                    dst += pl;
-                }
-        }
+        LaunchScope ls(c, "pack_cross");
+        const CrossTable T = cross_table(c);
+        dim3 grid(grid_for(g.plane, 256), 2 * T.ncross * T.sets);
+        pack_cross_kernel<<<grid, 256, 0, c->stream>>>(T, g);
+        CLBM_CUDA(cudaGetLastError());
         return 0;
     }
     if (phase == 2) {
@@ -311,22 +358,6 @@ int halo_pack(clbm_ctx *c, int phase)
 // crossing populations land in the boundary plane only where the sender really wrote them:
 // the upstream node (in the neighbour's slab = our ghost plane) is fluid and the target is not a wall;
 // elsewhere the slot was filled locally by the target's own half-way bounce-back.
-template <class L>
-__global__ void __launch_bounds__(256)
-unpack_cross_kernel(double *__restrict__ pop, const double *__restrict__ recv, const uint8_t *__restrict__ flag, Geom g,
-                    int side, int slot, int k)
-{
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= g.plane) return;
-    const int y = (int)(r / g.nz), z = (int)(r % g.nz);
-    const int xb = side ? g.nx - 1 : 0;   // boundary plane that receives
-    const long long j = g.idx(xb, y, z);
-    if (flag[j] == CELL_BB) return;
-    const long long src = g.idx(xb - L::cx(k), g.wy(y - L::cy(k)), g.wz(z - L::cz(k)));
-    if (flag[src] == CELL_BB) return;
-    pop[(size_t)k * g.ncs + j] = recv[(size_t)slot * g.plane + r];
-}
-
 int halo_unpack(clbm_ctx *c, int phase)
 {
     const Geom &g = c->geo;
@@ -346,22 +377,13 @@ int halo_unpack(clbm_ctx *c, int phase)
         return 0;
     }
     if (phase == 1) {
-        int ks[5];
-        for (int side = 0; side < 2; ++side) {
-            // data received from the side-0 neighbour moves in +x (c_x = +1) into plane 0, and vice versa
-            cross_dirs(c, 1 - side, ks);
-            const double *src = (const double *)c->halo[1][side][1];
-            for (int s = 0; s < c->sets; ++s)
-                for (int i = 0; i < n_cross(c); ++i) {
-                    LaunchScope ls(c, "unpack_cross");
-                    const int slot = s * n_cross(c) + i;
-                    if (c->Q == 9)
-                        unpack_cross_kernel<D2Q9><<<grid_for(g.plane, 256), 256, 0, c->stream>>>(c->pop[s][c->parity], src, c->flag, g, side, slot, ks[i]);
-                    else
-                        unpack_cross_kernel<D3Q19><<<grid_for(g.plane, 256), 256, 0, c->stream>>>(c->pop[s][c->parity], src, c->flag, g, side, slot, ks[i]);
-                    CLBM_CUDA(cudaGetLastError());
-                }
-        }
+        // data received from the side-0 neighbour moves in +x (c_x = +1) into plane 0, and vice versa
+        LaunchScope ls(c, "unpack_cross");
+        const CrossTable T = cross_table(c);
+        dim3 grid(grid_for(g.plane, 256), 2 * T.ncross * T.sets);
+        if (c->Q == 9) unpack_cross_kernel<D2Q9><<<grid, 256, 0, c->stream>>>(T, c->flag, g);
+        else unpack_cross_kernel<D3Q19><<<grid, 256, 0, c->stream>>>(T, c->flag, g);
+        CLBM_CUDA(cudaGetLastError());
         return 0;
     }
     if (phase == 2) {

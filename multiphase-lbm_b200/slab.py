@@ -118,7 +118,7 @@ class LocalRing:
             lat.sync()
 
 
-def ring_exchange(dist, rank, nranks, send0, send1, recv0, recv1):
+def ring_exchange(dist, rank, nranks, send0, send1, recv0, recv1, group=None):
     """One exchange phase with both ring neighbours through torch.distributed P2P ops.
     send0 goes to rank-1 (arriving in its recv1), send1 to rank+1 (arriving in its recv0)."""
     if nranks == 1:
@@ -126,12 +126,12 @@ def ring_exchange(dist, rank, nranks, send0, send1, recv0, recv1):
         recv0.copy_(send1)
         return
     left, right = (rank - 1) % nranks, (rank + 1) % nranks
-    ops = [dist.P2POp(dist.isend, send0, left), dist.P2POp(dist.isend, send1, right),
-           dist.P2POp(dist.irecv, recv1, right), dist.P2POp(dist.irecv, recv0, left)]
+    ops = [dist.P2POp(dist.isend, send0, left, group), dist.P2POp(dist.isend, send1, right, group),
+           dist.P2POp(dist.irecv, recv1, right, group), dist.P2POp(dist.irecv, recv0, left, group)]
     if nranks == 2:
         # left == right: tag-less P2P matches in posting order; order the ops identically on both ranks
-        ops = [dist.P2POp(dist.isend, send0, left), dist.P2POp(dist.irecv, recv1, right),
-               dist.P2POp(dist.isend, send1, right), dist.P2POp(dist.irecv, recv0, left)]
+        ops = [dist.P2POp(dist.isend, send0, left, group), dist.P2POp(dist.irecv, recv1, right, group),
+               dist.P2POp(dist.isend, send1, right, group), dist.P2POp(dist.irecv, recv0, left, group)]
     for req in dist.batch_isend_irecv(ops):
         req.wait()
 
@@ -159,6 +159,16 @@ class DistRing:
         # boundary-first overlap protocol (clbm_step_stage 10-12): the exchanges run on the library's boundary stream
         self.overlap = device.type == "cuda" and lattice.overlap_supported()
         self.stream_b = torch.cuda.ExternalStream(lattice.boundary_stream(), device=device) if self.overlap else None
+        # The NCCL kernels run on the process group's own stream.  With the default (normal-priority) stream they queue
+        # behind the thousands of pending CTAs of the interior launch and the "overlapped" exchange only starts when the
+        # interior kernel drains; a group whose NCCL streams are high priority gets the next SM slot that frees up.
+        self.group = None
+        if self.overlap and nranks > 1:
+            try:
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                self.group = dist.new_group(list(range(nranks)), pg_options=opts)
+            except Exception:   # noqa: BLE001  (gloo / older torch: keep the default group)
+                self.group = None
 
     def _on_stream(self):
         import contextlib
@@ -168,7 +178,7 @@ class DistRing:
         v = self._v
         with (self.torch.cuda.stream(self.stream_b) if boundary else self._on_stream()):
             ring_exchange(self.dist, self.rank, self.R, v[(phase, 0, False)], v[(phase, 1, False)],
-                          v[(phase, 0, True)], v[(phase, 1, True)])
+                          v[(phase, 0, True)], v[(phase, 1, True)], group=self.group if boundary else None)
 
     def record_event(self):
         """CUDA event on the launching stream (device-side timing of slab steps)"""
