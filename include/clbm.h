@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CLBM_ABI_VERSION 1
+#define CLBM_ABI_VERSION 2
 
 /* ---- models (one per reference functor family) -------------------------- */
 #define CLBM_MODEL_SC_D2Q9    0 /* LBM_Laplace2D / LBM_contactAngle2D (Yuan-CS Shan-Chen) */
@@ -51,6 +51,8 @@ extern "C" {
 /* Shan-Chen force variant */
 #define CLBM_SC_FORCE_LAPLACE 0 /* SC/apps/laplace2D.h:198-242: psi_w = psi(rho_w) on G1(rho_w); + gravity*rho in y */
 #define CLBM_SC_FORCE_CONTACT 1 /* SC/apps/contactAngle2D.h:248-293: psi_w on the centre node's G1 branch; F=0 if rho<=0; no gravity */
+#define CLBM_SC_FORCE_CONSTG  2 /* SC/apps/twoLayeredFlow2D.h:183-261: constant coupling G, psi = sqrt(2 (rho/3 - P_eos - p_shift) / (|G|/3)),
+                                   psi_w = psi(rho_w), F=0 if rho<=0, uniform body force (gx, gy) added to F; pressure_node = P_eos */
 
 /* error codes */
 #define CLBM_OK          0
@@ -72,6 +74,7 @@ extern "C" {
 #define CLBM_CASE_SC_DROPLET3D_PER 3 /* fully periodic free droplet            args: {rhol, rhog, RR}                 */
 #define CLBM_CASE_HCZ_RT2D         4 /* PF/apps/rayleighTaylor2D.h:155-193,802-820   args: none                       */
 #define CLBM_CASE_HCZ_LAPLACE3D    5 /* PF/apps/laplace3D.h:170-213,830-849          args: none                       */
+#define CLBM_CASE_SC_LAYERED2D     6 /* SC/apps/twoLayeredFlow2D.h:325-346,441-454 args: {rhol, rhog, h_lower, w_int}  */
 
 typedef struct clbm_ctx clbm_ctx;
 
@@ -98,6 +101,8 @@ typedef struct clbm_params {
     double rho_w, a, b, R, TT;
     /* HCZ (LBM_rayleighTaylor2D members, PF/apps/rayleighTaylor2D.h:113-122) */
     double phi_l, phi_g, rho_l, rho_g, kappa;
+    /* Shan-Chen constant-G variant (LBM members of SC/apps/twoLayeredFlow2D.h:150-153) */
+    double gx, gy, G, p_shift;
 } clbm_params;
 
 /* ---- life cycle ---------------------------------------------------------- */

@@ -207,6 +207,7 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     *out = nullptr;
     if (p->abi_version != CLBM_ABI_VERSION) { set_error("ABI version %d != %d", p->abi_version, CLBM_ABI_VERSION); return CLBM_EINVAL; }
     if (p->model < 0 || p->model > CLBM_MODEL_HCZ_D3Q19) { set_error("unsupported model %d", p->model); return CLBM_EINVAL; }
+    if (p->sc_force == CLBM_SC_FORCE_CONSTG && p->G == 0.0) { set_error("constant-G Shan-Chen needs G != 0"); return CLBM_EINVAL; }
     const bool is3d = p->model == CLBM_MODEL_SC_D3Q19 || p->model == CLBM_MODEL_HCZ_D3Q19;
     if (p->nx < 1 || p->ny < 1 || p->nz < 1 || (!is3d && p->nz != 1)) { set_error("bad extent %d x %d x %d", p->nx, p->ny, p->nz); return CLBM_EINVAL; }
     if (p->nx_global < p->nx || p->x_offset < 0 || p->x_offset + p->nx > p->nx_global) { set_error("bad slab [%d,%d) of %d", p->x_offset, p->x_offset + p->nx, p->nx_global); return CLBM_EINVAL; }
@@ -268,7 +269,14 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
         // contactAngle2D.h:259-262 re-evaluates it on the CENTRE node's branch G1c = +-1/3
         const double cs2 = 1.0 / 3.0, rw = p->rho_w, dw = (1.0 - rw);
         const double Zw = 1.0 + (4.0 * rw - 2.0 * rw * rw) / (dw * dw * dw);
-        if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
+        m.gx = p->gx; m.gy = p->gy; m.G = p->G; m.p_shift = p->p_shift;
+        m.kpsi = (p->G != 0.0) ? 2.0 / (fabs(p->G) * cs2) : 0.0;
+        if (p->sc_force == CLBM_SC_FORCE_CONSTG) {
+            // psi_w = psi_from_rho(rho_w) with the same constant-G mapping (twoLayeredFlow2D.h:226)
+            const double Pw = rw * p->R * p->TT * Zw - p->a * rw * rw + p->p_shift;
+            const double Sw = cs2 * rw - Pw;
+            m.psiw_pos = m.psiw_neg = (Sw <= 0.0) ? 0.0 : sqrt(2.0 * Sw / (fabs(p->G) * cs2));
+        } else if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
             const double vp = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / cs2;
             const double vn = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / -cs2;
             m.psiw_pos = (vp > 0.0) ? sqrt(vp) : 0.0;

@@ -51,6 +51,12 @@ CLBM_D double sc_psi_g1(const ModelParams &mp, double rho, bool &g1_pos)
 {
     const double d = 1.0 - rho;
     const double Zr = 1.0 + (4.0 * rho - 2.0 * rho * rho) / (d * d * d);
+    if (mp.sc_force == CLBM_SC_FORCE_CONSTG) {
+        // constant-G mapping (SC/apps/twoLayeredFlow2D.h:183-188): psi^2 = 2 (cs2 rho - (P_eos + p_shift)) / (|G| cs2)
+        g1_pos = true;
+        const double S = (1.0 / 3.0) * rho - (rho * mp.R * mp.TT * Zr - mp.a * rho * rho + mp.p_shift);
+        return (S > 0.0) ? sqrt(mp.kpsi * S) : 0.0;
+    }
     const double s = mp.R * mp.TT * Zr - mp.a * rho - (1.0 / 3.0);
     g1_pos = s > 0.0;
     const double P = rho * mp.R * mp.TT * Zr - mp.a * rho * rho;
@@ -96,12 +102,16 @@ template <class L>
 CLBM_D void sc_force(const ModelParams &mp, ScForceSums &s, double rho_c, double psi_c, bool g1_pos, double F[3])
 {
     sc_wall_sums<L>(s);
-    const double G1 = g1_pos ? (1.0 / 3.0) : -(1.0 / 3.0);
+    const double G1 = (mp.sc_force == CLBM_SC_FORCE_CONSTG) ? mp.G : (g1_pos ? (1.0 / 3.0) : -(1.0 / 3.0));
     const double psi_w = g1_pos ? mp.psiw_pos : mp.psiw_neg;
     const double a = -G1 * psi_c, b = -G1 * psi_c * psi_w;
 #pragma unroll
     for (int d = 0; d < 3; ++d) F[d] = a * s.ff[d] + b * s.bb[d];
-    if (mp.sc_force == CLBM_SC_FORCE_CONTACT) {
+    if (mp.sc_force == CLBM_SC_FORCE_CONSTG) {
+        // twoLayeredFlow2D.h:224, :256-258: no force on an empty node, else the uniform body force is added as is
+        if (rho_c <= 0.0) F[0] = F[1] = F[2] = 0.0;
+        else { F[0] += mp.gx; F[1] += mp.gy; }
+    } else if (mp.sc_force == CLBM_SC_FORCE_CONTACT) {
         if (rho_c <= 0.0) F[0] = F[1] = F[2] = 0.0;
     } else {
         F[1] += mp.gravity * rho_c;
@@ -157,6 +167,10 @@ CLBM_D void sc_outputs(const ModelParams &mp, const double *f, ScForceSums &s, d
     u[2] = (L::D == 3) ? jz / rho + 0.5 * F[2] / rho : 0.0;
     const double G1 = g1_pos ? (1.0 / 3.0) : -(1.0 / 3.0);
     pr = (1.0 / 3.0) * rho_raw + (1.0 / 6.0) * G1 * ps * ps;
+    if (mp.sc_force == CLBM_SC_FORCE_CONSTG) {   // pressure_node = thermodynamic EOS pressure (twoLayeredFlow2D.h:191-194)
+        const double d = 1.0 - rho_raw;
+        pr = rho_raw * mp.R * mp.TT * (1.0 + (4.0 * rho_raw - 2.0 * rho_raw * rho_raw) / (d * d * d)) - mp.a * rho_raw * rho_raw;
+    }
 }
 
 }  // namespace clbm

@@ -41,6 +41,19 @@ init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, uint8_t *__r
         vf = (dx * dx + dy * dy <= A.a[2] * A.a[2]) ? A.a[0] : A.a[1];
         wall = (iY == 0 || iY == ny - 1);
     } break;
+    case CLBM_CASE_SC_LAYERED2D: {   // SC/apps/twoLayeredFlow2D.h:325-346, 441-454   args {rhol, rhog, h_lower, w_int}
+        const double H = double(ny - 1);
+        const double hl = A.a[2] < 0.0 ? 0.0 : (A.a[2] > 0.5 ? 0.5 : A.a[2]);
+        const double y_low = hl * H, y_high = H - y_low;
+        const int wi = (int)A.a[3];
+        const double w = double(wi > 1 ? wi : 1), yy = double(iY);
+        const double s_bottom = 0.5 * (1.0 - tanh((yy - y_low) / w));
+        const double s_top = 0.5 * (1.0 + tanh((yy - y_high) / w));
+        double s_liq = s_bottom + s_top;
+        s_liq = s_liq < 0.0 ? 0.0 : (s_liq > 1.0 ? 1.0 : s_liq);
+        vf = s_liq * A.a[1] + (1.0 - s_liq) * A.a[0];   // "liquid" (rhog in the reference's naming) at the walls
+        wall = (iY == 0 || iY == ny - 1);
+    } break;
     case CLBM_CASE_SC_DROPLET3D:
     case CLBM_CASE_SC_DROPLET3D_PER: {   // contactAngle2D geometry extruded to 3-D
         const bool per = case_id == CLBM_CASE_SC_DROPLET3D_PER;
@@ -86,7 +99,7 @@ int model_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)
 {
     const int m = c->prm.model;
     const bool sc2 = m == CLBM_MODEL_SC_D2Q9, sc3 = m == CLBM_MODEL_SC_D3Q19;
-    const bool ok = (sc2 && (case_id == CLBM_CASE_SC_LAPLACE2D || case_id == CLBM_CASE_SC_CONTACT2D)) ||
+    const bool ok = (sc2 && (case_id == CLBM_CASE_SC_LAPLACE2D || case_id == CLBM_CASE_SC_CONTACT2D || case_id == CLBM_CASE_SC_LAYERED2D)) ||
                     (sc3 && (case_id == CLBM_CASE_SC_DROPLET3D || case_id == CLBM_CASE_SC_DROPLET3D_PER)) ||
                     (m == CLBM_MODEL_HCZ_D2Q9 && case_id == CLBM_CASE_HCZ_RT2D) ||
                     (m == CLBM_MODEL_HCZ_D3Q19 && case_id == CLBM_CASE_HCZ_LAPLACE3D);

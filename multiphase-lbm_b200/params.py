@@ -5,13 +5,13 @@ The struct carries the scalar members of the reference LBM_* aggregates
 """
 import ctypes
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 MODEL_SC_D2Q9, MODEL_SC_D3Q19, MODEL_HCZ_D2Q9, MODEL_HCZ_D3Q19, MODEL_PULSATILE = range(5)
-SC_FORCE_LAPLACE, SC_FORCE_CONTACT = 0, 1
+SC_FORCE_LAPLACE, SC_FORCE_CONTACT, SC_FORCE_CONSTG = 0, 1, 2
 REDUCE_MASS, REDUCE_ENERGY, REDUCE_UMAX = 0, 1, 2
 (CASE_SC_LAPLACE2D, CASE_SC_CONTACT2D, CASE_SC_DROPLET3D, CASE_SC_DROPLET3D_PER,
- CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D) = range(6)
+ CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D, CASE_SC_LAYERED2D) = range(7)
 
 MODEL_Q = {MODEL_SC_D2Q9: 9, MODEL_SC_D3Q19: 19, MODEL_HCZ_D2Q9: 9, MODEL_HCZ_D3Q19: 19, MODEL_PULSATILE: 9}
 MODEL_SETS = {MODEL_SC_D2Q9: 1, MODEL_SC_D3Q19: 1, MODEL_HCZ_D2Q9: 2, MODEL_HCZ_D3Q19: 2, MODEL_PULSATILE: 1}
@@ -30,6 +30,7 @@ class Params(ctypes.Structure):
         ("R", ctypes.c_double), ("TT", ctypes.c_double),
         ("phi_l", ctypes.c_double), ("phi_g", ctypes.c_double),
         ("rho_l", ctypes.c_double), ("rho_g", ctypes.c_double), ("kappa", ctypes.c_double),
+        ("gx", ctypes.c_double), ("gy", ctypes.c_double), ("G", ctypes.c_double), ("p_shift", ctypes.c_double),
     ]
 
     @property
@@ -75,6 +76,7 @@ def make_params(model, nx, ny, nz=1, **kw):
     p.fused = 1
     p.omega = 1.0
     p.a, p.b, p.R = 1.0, 4.0, 1.0
+    p.G = -1.0
     for k, v in kw.items():
         if not hasattr(p, k):
             raise AttributeError(k)
@@ -123,3 +125,27 @@ def pulsatile_params(N=64, tau=0.75, alpha=0.01, p0_in=0.20, p0_out=0.19, is_sev
 
 # Pulsatile: 145 B/LU as the other single-set D2Q9 paths; the reference also stores P, Ux, Uy every step (169)
 PULSATILE_BYTES_PER_LU = 169
+
+
+def sc_p_shift(rhog, rhol, a, b, R, TT):
+    """p_shift of the constant-G variant: the smallest shift that keeps rho/3 - (P_eos + p_shift) >= 0 on [rhog, rhol],
+    sampled at 601 points, plus 1e-12 (SC/apps/twoLayeredFlow2D.h:535-546)."""
+    worst = -1e30
+    Ns = 600
+    for s in range(Ns + 1):
+        r = rhog + (rhol - rhog) * (float(s) / Ns)
+        d = 1.0 - r
+        Z = 1.0 + (4.0 * r - 2.0 * r * r) / (d * d * d)
+        S = (1.0 / 3.0) * r - (r * R * TT * Z - a * r * r)
+        worst = max(worst, -S)
+    return max(0.0, worst) + 1e-12
+
+
+def sc_layered_params(nx, ny, *, omega=None, tau=None, ulb=0.1, N=None, Re=60.0, rhol=0.21, rhog=0.067, rho_w=0.067, a=1.0, b=4.0,
+                      R=1.0, TT0=0.95, gx=1e-8, gy=0.0, G=-1.0, **kw):
+    """constant-G Shan-Chen parameter set; defaults = SC/apps/Config_Files/config_twoLayeredFlow2D.txt"""
+    p = sc_params(MODEL_SC_D2Q9, nx, ny, omega=omega, tau=tau, ulb=ulb, N=N if N else ny - 1, Re=Re, rho_w=rho_w, a=a, b=b, R=R,
+                  TT0=TT0, sc_force=SC_FORCE_CONSTG, **kw)
+    p.gx, p.gy, p.G = gx, gy, G
+    p.p_shift = sc_p_shift(rhog, rhol, a, b, R, p.TT)
+    return p

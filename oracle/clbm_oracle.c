@@ -93,6 +93,20 @@ static double sc_psi(const sc_eos *e, double rho)
     return (val > 0.0) ? sqrt(val) : 0.0;
 }
 
+/* constant-G mapping of SC/apps/twoLayeredFlow2D.h:183-188: psi^2 = 2 (cs2 rho - (P_eos + p_shift)) / (|G| cs2) */
+static double sc_psi_constg(const sc_eos *e, double rho, double G, double p_shift)
+{
+    const double P = sc_P(e, rho) + p_shift;
+    const double S = sc_cs2() * rho - P;
+    if (S <= 0.0) return 0.0;
+    return sqrt(2.0 * S / (fabs(G) * sc_cs2()));
+}
+/* psi of the variant selected by p->sc_force */
+static double sc_psi_of(const clbm_params *p, const sc_eos *e, double rho)
+{
+    return p->sc_force == CLBM_SC_FORCE_CONSTG ? sc_psi_constg(e, rho, p->G, p->p_shift) : sc_psi(e, rho);
+}
+
 /* density / raw momentum of one node from the "in" buffer */
 static double sc2_density(const double *fin, size_t ne, size_t i)
 { /* SC/apps/laplace2D.h:148-154 */
@@ -150,7 +164,12 @@ static void sc_force(const clbm_params *p, const sc_eos *e, int D, const double 
     double G1, psi_c, psi_w;
     Fout[0] = Fout[1] = Fout[2] = 0.0;
 
-    if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
+    if (p->sc_force == CLBM_SC_FORCE_CONSTG) {      /* SC/apps/twoLayeredFlow2D.h:218-261 */
+        if (rho_c <= 0.0) return;
+        G1 = p->G;
+        psi_c = sc_psi_constg(e, rho_c, p->G, p->p_shift);
+        psi_w = sc_psi_constg(e, p->rho_w, p->G, p->p_shift);
+    } else if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
         if (rho_c <= 0.0) return;
         G1 = sc_G1(e, rho_c);
         psi_c = sc_psi(e, rho_c);
@@ -183,7 +202,11 @@ static void sc_force(const clbm_params *p, const sc_eos *e, int D, const double 
             sum_ff[2] += tk * cz * psi_nb;
         }
     }
-    if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
+    if (p->sc_force == CLBM_SC_FORCE_CONSTG) {
+        for (int d = 0; d < 3; ++d) Fout[d] = -G1 * psi_c * sum_ff[d] + (-G1 * psi_c * psi_w * sum_bb[d]);
+        Fout[0] += p->gx;
+        Fout[1] += p->gy;
+    } else if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
         for (int d = 0; d < 3; ++d) Fout[d] = -G1 * psi_c * sum_ff[d] + (-G1 * psi_c * psi_w * sum_bb[d]);
     } else {
         for (int d = 0; d < 3; ++d) {
@@ -204,7 +227,7 @@ static void sc_psi_field(const clbm_params *p, const sc_eos *e, int D, const dou
         size_t i = (size_t)ii;
         double r = (D == 2) ? sc2_density(fin, ne, i) : sc3_density(fin, ne, i);
         rho[i] = r;
-        psi[i] = (flag[i] == BB) ? 0.0 : sc_psi(e, r);
+        psi[i] = (flag[i] == BB) ? 0.0 : sc_psi_of(p, e, r);
     }
 }
 
@@ -292,7 +315,9 @@ static void sc_fields(const clbm_params *p, int D, const double *fin, const uint
             if (uz) uz[i] = 0.0;
             continue;
         }
-        if (s1) {
+        if (s1 && p->sc_force == CLBM_SC_FORCE_CONSTG) {
+            s1[i] = sc_P(&e, r);       /* pressure_node = thermodynamic EOS pressure (twoLayeredFlow2D.h:191-194) */
+        } else if (s1) {
             double ps = sc_psi(&e, r), G1 = sc_G1(&e, r);
             if (p->sc_force == CLBM_SC_FORCE_CONTACT) s1[i] = sc_cs2() * r + (G1 / 6.0) * ps * ps;
             else s1[i] = (1.0 / 3.0) * r + (1.0 / 6.0) * G1 * ps * ps;
@@ -794,6 +819,24 @@ int oracle_init_case(const clbm_params *p, int case_id, const double *args, int 
             int x_c = nx / 2, y_c = 5;
             double dx = (double)iX - (double)x_c, dy = (double)iY - (double)y_c;
             double rho = (dx * dx + dy * dy <= args[2] * args[2]) ? args[0] : args[1];
+            for (int k = 0; k < 9; ++k) f[(size_t)k * ne + i] = rho * T9[k];
+            wall = (iY == 0 || iY == ny - 1);
+        } break;
+        case CLBM_CASE_SC_LAYERED2D: { /* SC/apps/twoLayeredFlow2D.h:325-346 (iniLattice_layers), :441-454 (inigeom) */
+            if (nargs < 4) return -1;
+            const double rhol = args[0], rhog = args[1], h_lower = args[2];
+            const int w_int = (int)args[3];
+            const double H = (double)(ny - 1);
+            const double y_low = (h_lower < 0.0 ? 0.0 : (h_lower > 0.5 ? 0.5 : h_lower)) * H;
+            const double y_high = H - y_low;
+            const double w = (double)(w_int > 1 ? w_int : 1);
+            const double yy = (double)iY;
+            const double s_bottom = 0.5 * (1.0 - tanh((yy - y_low) / w));
+            const double s_top = 0.5 * (1.0 + tanh((yy - y_high) / w));
+            double s_liq = s_bottom + s_top;
+            s_liq = s_liq < 0.0 ? 0.0 : (s_liq > 1.0 ? 1.0 : s_liq);
+            const double s_gas = 1.0 - s_liq;
+            const double rho = s_liq * rhog + s_gas * rhol;
             for (int k = 0; k < 9; ++k) f[(size_t)k * ne + i] = rho * T9[k];
             wall = (iY == 0 || iY == ny - 1);
         } break;

@@ -65,6 +65,11 @@ def golden_setup(name):
                         TT0=kw["TT0"], gravity=0.0, sc_force=P.SC_FORCE_CONTACT)
         return p, P.CASE_SC_CONTACT2D, (kw["rhol"], kw["rhog"], kw["RR"]), kw["steps"], \
             {"rho": "s0", "pressure": "s1", "ux": "ux", "uy": "uy"}
+    if name.startswith("sc_layered2d"):
+        p = P.sc_layered_params(nx, ny, omega=kw["omega"], rhol=kw["rhol"], rhog=kw["rhog"], rho_w=kw["rho_w"], a=kw["a"], b=kw["b"],
+                                R=kw["R"], TT0=kw["TT0"], gx=kw["gx"], gy=kw["gy"], G=kw["G"])
+        return p, P.CASE_SC_LAYERED2D, (kw["rhol"], kw["rhog"], kw["h_lower"], float(kw["w_int"])), kw["steps"], \
+            {"rho": "s0", "pressure": "s1", "ux": "ux", "uy": "uy"}
     if name.startswith("hcz_rt2d"):
         p = P.hcz_params(P.MODEL_HCZ_D2Q9, nx, ny, omega=kw["omega"], phi_l=kw["phi_l"], phi_g=kw["phi_g"],
                          rho_l=kw["rho_l"], rho_g=kw["rho_g"], a=kw["a"], b=kw["b"], kappa=kw["kappa"], gravity=kw["gravity"])

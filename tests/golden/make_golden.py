@@ -30,6 +30,12 @@ CASES = {
     "sc_contact2d_48x24_s200": ("ref_sc_contact2d", dict(nx=48, ny=24, steps=200, omega=1.0, rhol=0.265, rhog=0.038,
                                 rho_w=0.2, a=1.0, b=4.0, R=1.0, TT0=0.875, RR=8.0),
                                 1, 9, ["rho", "pressure", "ux", "uy"]),
+    "sc_layered2d_10x41_s300": ("ref_sc_layered2d", dict(nx=10, ny=41, steps=300, omega=1.0, rhol=0.21, rhog=0.067, rho_w=0.067,
+                                a=1.0, b=4.0, R=1.0, TT0=0.95, gx=1e-6, gy=0.0, G=-1.0, h_lower=0.3, w_int=4),
+                                1, 9, ["rho", "pressure", "ux", "uy"]),
+    "sc_layered2d_12x33_s200": ("ref_sc_layered2d", dict(nx=12, ny=33, steps=200, omega=1.25, rhol=0.247, rhog=0.0405, rho_w=0.06,
+                                a=1.0, b=4.0, R=1.0, TT0=0.9, gx=2e-6, gy=-1e-7, G=-1.3, h_lower=0.25, w_int=2),
+                                1, 9, ["rho", "pressure", "ux", "uy"]),
     "hcz_rt2d_16x66_s40": ("ref_hcz_rt2d", dict(nx=16, ny=66, steps=40, omega=1.9598595172738, phi_l=0.251, phi_g=0.024,
                            rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-6.25e-6),
                            2, 9, ["phi", "P", "rho", "ux", "uy"]),

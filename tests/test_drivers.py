@@ -76,3 +76,29 @@ def test_driver_laplace2d_matches_oracle(tmp_path):
     e_ref = 0.5 * np.sum(u["ux"] ** 2 + u["uy"] ** 2) / (48 * 48) * (1 / 48.) ** 2 / (0.01 / 48.) ** 2
     e_drv = np.loadtxt(tmp_path / "energy.dat")[2, 1]
     assert abs(e_drv - e_ref) <= 2e-8 * abs(e_ref) + 1e-30     # energy.dat holds 8 significant digits
+
+
+@pytest.mark.gpu
+def test_driver_two_layered_flow_matches_oracle(tmp_path):
+    """COOLBM twoLayeredFlow2D (the SC reference's default problem) against the oracle: mass log and energy log"""
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    (cfg / "config_twoLayeredFlow2D.txt").write_text(
+        "N 40\nulb 0.1\nRe 60\nmax_t 1.0001   # 400 steps\nout_freq 200\nvtk_freq 200\na 1.0\nb 4.0\nR 1.0\nTT0 0.95\nrhol 0.21\n"
+        "rhog 0.067\nrho_w 0.067\nh_lower 0.30\nw_int 4\ngx 1e-6\ngy 0.0\n")
+    r = subprocess.run([_exe(), "twoLayeredFlow2D", str(cfg)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "Two-Layered Flow 2-D" in r.stdout and "p_shift = " in r.stdout and "MLUPS" in r.stdout
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".vtk")) == ["sol_0000000.vtk", "sol_0000200.vtk"]
+    vtk = open(tmp_path / "sol_0000200.vtk").read()
+    assert all(tag in vtk for tag in ("SCALARS Density", "SCALARS Pressure", "VECTORS Force", "VECTORS Velocity"))
+    prm = P.sc_layered_params(10, 41, ulb=0.1, N=40, Re=60.0, gx=1e-6)
+    ora = OracleSim(prm).init_case(P.CASE_SC_LAYERED2D, (0.21, 0.067, 0.30, 4.0))
+    ora.step(200)
+    u = ora.fields()
+    bulk = ora.flag == 1
+    e_ref = 0.5 * np.sum((u["ux"] ** 2 + u["uy"] ** 2)[bulk]) / (10 * 41) * (1 / 40.) ** 2 / (0.1 / 40.) ** 2
+    e_drv = np.loadtxt(tmp_path / "energy.dat")[1, 1]
+    assert abs(e_drv - e_ref) <= 2e-9 * abs(e_ref) + 1e-30
+    m_drv = np.loadtxt(tmp_path / "mass.dat")[1, 1]
+    assert abs(m_drv - np.sum(u["s0"][bulk])) <= 1e-12 * m_drv

@@ -291,3 +291,16 @@ def test_sc_force_field_download(model, case, args, dims, force):
         scale = scale or max(np.max(np.abs(Fref)), 1e-30)
         assert np.max(np.abs(F[d] - Fref)) < 1e-8 * scale, key
     assert scale > 1e-6
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_sc_layered2d_constant_g_1000_steps(fused):
+    """SC/apps/twoLayeredFlow2D.h (the SC reference's default problem): constant-G psi mapping with p_shift, uniform
+    body force, walls y = 0, ny-1; 10 x 101 lattice of the shipped config, 1000 steps"""
+    prm = P.sc_layered_params(10, 101, ulb=0.1, N=100, Re=60.0, gx=1e-6)
+    ora, got, pops, flags = run_pair(prm, P.CASE_SC_LAYERED2D, (0.21, 0.067, 0.30, 4.0), 1000, fused=fused)
+    np.testing.assert_array_equal(flags, ora.flag)
+    ref = ora.fields()
+    check_fields(ref, got, ("s0", "s1", "ux", "uy"))
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+    assert np.max(np.abs(ref["ux"])) > 1e-7      # the body force drives a flow
