@@ -31,11 +31,21 @@ P = pkg.params
 def golden_names(prefix=""):
     """multiphase fixtures (clbm_oracle.c); the Pulsatile fixtures have their own loader (pulsatile_golden_names)"""
     return sorted(f[:-4] for f in os.listdir(GOLDEN)
-                  if f.endswith(".npz") and f.startswith(prefix) and not f.startswith("pulsatile_"))
+                  if f.endswith(".npz") and f.startswith(prefix) and not f.startswith(("pulsatile_", "yl2d_")))
 
 
 def pulsatile_golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("pulsatile_"))
+
+
+def yl2d_golden_names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("yl2d_"))
+
+
+def load_yl2d_golden(name):
+    """-> (npz, keyword arguments of the run incl. nx, ny, steps)"""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return z, json.loads(bytes(z["params"]).decode())
 
 
 def load_pulsatile_golden(name):

@@ -157,3 +157,38 @@ def pulsatile_write_vtk(nx, ny, P, Ux, Uy, flag, time_iter, path):
                                np.ascontiguousarray(flag).ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), int(time_iter),
                                path.encode())
     assert rc == 0
+
+
+class YL2DOracle:
+    """oracle/yl2d_oracle.c: CPU restatement of AB/apps/Young_Laplace2D.h (test infrastructure)."""
+
+    def __init__(self, nx=32, ny=32, Sigma=0.01, W=4.0, M=0.02, RhoL=0.001, RhoH=1.0, tau=0.8):
+        L = lib()
+        L.yl2d_create.restype = ctypes.c_void_p
+        L.yl2d_create.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 6
+        L.yl2d_lattice.restype = ctypes.POINTER(ctypes.c_double)
+        for f in ("yl2d_step", "yl2d_get", "yl2d_destroy", "yl2d_parity", "yl2d_lattice"):
+            getattr(L, f).argtypes = None
+        self.h = ctypes.c_void_p(L.yl2d_create(nx, ny, Sigma, W, M, RhoL, RhoH, tau))
+        self.nx, self.ny, self.nelem = nx, ny, nx * ny
+
+    def step(self, n=1):
+        lib().yl2d_step(self.h, int(n))
+        return self
+
+    def fields(self):
+        out = {k: np.zeros(self.nelem) for k in ("C", "P", "Rho", "Ux", "Uy")}
+        lib().yl2d_get(self.h, *[_dptr(out[k]) for k in ("C", "P", "Rho", "Ux", "Uy")])
+        return out
+
+    def lattice(self):
+        return np.ctypeslib.as_array(lib().yl2d_lattice(self.h), shape=(4 * 9 * self.nelem,)).copy()
+
+    @property
+    def parity(self):
+        return lib().yl2d_parity(self.h)
+
+    def close(self):
+        if self.h:
+            lib().yl2d_destroy(self.h)
+            self.h = None
