@@ -37,6 +37,7 @@ WORKLOADS = {
     "c2_hcz_d2q9_256": ("hcz2d", (256, 1026, 1), "HCZ D2Q9 Rayleigh-Taylor 256x1026 (BASELINE configs[1]; fits in L2)"),
     "c1_sc_d2q9_256": ("sc2d", (256, 256, 1), "Shan-Chen D2Q9 static droplet 256x256 (BASELINE configs[0]; fits in L2)"),
     "sc_d2q9_8192": ("sc2d_tau1", (8192, 8192, 1), "Shan-Chen D2Q9 static droplet 8192x8192 (HBM-sized D2Q9)"),
+    "yl2d_8192": ("yl2d", (8192, 8192, 1), "Young-Laplace conservative phase-field bubble D2Q9 BGK, 8192 x 8192 periodic (AB reference default problem, HBM-sized)"),
     "c5_pulsatile_1024": ("pulsatile", (10221, 1024, 1), "PulsatileBloodFlow2D compliant vessel D2Q9 MRT, Zou/He pulsatile pressure BCs, N=1024 (BASELINE configs[4])"),
 }
 
@@ -203,6 +204,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if WORKLOADS[a.workload][0] == "pulsatile":
         run_pulsatile(a, rank, world, local_rank)
+        return
+    if WORKLOADS[a.workload][0] == "yl2d":
+        run_yl2d(a, rank, world, local_rank)
         return
     if a.impl == "reference":
         run_reference_arm(a, rank)
@@ -461,6 +465,121 @@ def run_pulsatile(a, rank, world, local_rank):
                                      "parallelism": "replicas only x%d (global per-column wall recurrence)" % world,
                                      "initial_state": "open vessel at rest, margin 6 rows (pulsatile_cases.open_vessel_at_rest), uploaded through the C ABI",
                                      "l2_policy": "working set %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (2 * 9 * nelem * 8 / 1e9)},
+                          "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def yl2d_cpu_baseline(N=512, target_s=10.0):
+    """the UNTOUCHED reference header (oracle/_ref/ref_yl2d; collide is par_unseq on the serial PSTL backend, update_fields is
+    serial in the reference) on a bounded sample; the oracle port when the prebuilt binary is absent"""
+    from _oracle import YL2DOracle, ref_binary
+    exe = ref_binary("ref_yl2d")
+    steps = int(max(10, target_s * 4.0e6 / (N * N)))
+    if exe:
+        out = subprocess.check_output([exe, "nx=%d" % N, "ny=%d" % N, "steps=%d" % steps], timeout=900).decode()
+        r = json.loads(out.strip().splitlines()[-1])
+        return {"value": r["mlups"], "unit": "MLUPS", "cores": 1, "kind": "reference",
+                "sample": "%d x %d, %d iterations of the reference loop body, reference header compiled unmodified" % (N, N, steps)}
+    o = YL2DOracle(N, N)
+    t0 = time.perf_counter(); o.step(steps); dt = time.perf_counter() - t0
+    return {"value": N * N * steps / dt / 1e6, "unit": "MLUPS", "cores": 1, "kind": "port",
+            "sample": "%d x %d, %d iterations, oracle/yl2d_oracle.c" % (N, N, steps)}
+
+
+def run_yl2d(a, rank, world, local_rank):
+    """Young-Laplace bubble (AB reference default problem): periodic, shards like the other multiphase cases, but this
+    round runs replicas only (no slab protocol for this model yet)."""
+    metric = "fp64 MLUPS (D2Q9 conservative phase field)"
+    N = 8192
+    if a.size:
+        N = int(a.size.split("x")[0])
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb = yl2d_cpu_baseline(512, target_s=8.0 * max(1, min(a.steps, 3)))
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "MLUPS", "n_gpus": a.gpus, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": a.workload, "description": WORKLOADS[a.workload][2]},
+                          "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pkg = entry.load_package()
+    P, clbm = pkg.params, pkg.clbm
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sim = clbm.YoungLaplace(N, device=local_rank)
+    nelem = sim.nelem
+    sim.step(a.warmup)
+    sim.sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = sim.launch_count()
+    barrier()
+    ms = sim.step_timed(a.steps)
+    barrier()
+    launches = sim.launch_count() - l0
+    clocks = sampler.summary() if sampler else None
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches = float(tmax[0]), int(tsum[1])
+    value = nelem * world * a.steps / (ms * 1e-3) / 1e6
+    blu = P.YL2D_BYTES_PER_LU
+    peak, peak_src = measured_peak_gbs()
+    achieved = blu * nelem * a.steps / (ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "yl2d iteration (yl2d_phi + yl2d_step)", "kernel_ms": ms / a.steps, "algorithmic_bytes_per_lu": blu,
+                "lattice_updates_per_launch": nelem, "peak_source": peak_src}
+    e2e = None
+    if not a.no_e2e:
+        lat, par = sim.lattice()
+        f = sim.fields()
+        pins = {"lat": clbm.PinnedArray(lat.size), "Ux": clbm.PinnedArray(nelem), "Uy": clbm.PinnedArray(nelem)}
+        pins["lat"].array[:] = lat
+        pins["Ux"].array[:] = f["Ux"]
+        pins["Uy"].array[:] = f["Uy"]
+        del lat
+        out = {k: clbm.PinnedArray(nelem) for k in ("C", "P", "Ux", "Uy")}
+        outd = {k: v.array for k, v in out.items()}
+        barrier()
+        t0 = time.perf_counter()
+        sim.upload(pins["lat"].array, pins["Ux"].array, pins["Uy"].array, par)
+        sim.step(a.steps)
+        sim.fields(out=outd)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        e2e = {"value": nelem * world * a.steps / dt / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": (36 + 2) * nelem * 8 * world / a.steps,
+               "d2h_bytes_per_step": 4 * nelem * 8 * world / a.steps, "seconds": dt, "finite": bool(np.isfinite(outd["C"]).all()),
+               "note": "upload of all four population buffers + Ux, Uy from pinned host memory + %d iterations + download of C, P, Ux, Uy" % a.steps}
+        for v in list(pins.values()) + list(out.values()):
+            v.free()
+    cb = yl2d_cpu_baseline() if rank == 0 and world == 1 and not a.no_cpu else None
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic",
+                          "config": {"workload": a.workload, "description": WORKLOADS[a.workload][2], "lattice_per_gpu": [N, N, 1],
+                                     "parallelism": "replicas only x%d" % world,
+                                     "l2_policy": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (36 * nelem * 8 / 1e9)},
                           "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
     sim.close()
     if world > 1:

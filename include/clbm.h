@@ -235,6 +235,37 @@ int  clbm_pulsatile_upload(clbm_pulsatile *ctx, const double *lattice, const uin
                            const double *Ux, const double *Uy, const double *yr1, const double *yr2,
                            int parity, int t_iter);
 
+/* ---- Young-Laplace case (conservative phase field, AB/apps/Young_Laplace2D.h) ---------------------------------
+ * Replaces the iteration body of Young_Laplace2D() ("Abbashub LBM/apps/Young_Laplace2D.h":555-565):
+ *     for_each(par_unseq, cell_index.begin(), cell_index.end(), [&](int i){ lbm.collide_stream_at(i); });   // :217-290
+ *     *parity = 1 - *parity;
+ *     lbm.update_fields();                                                                                    // :297-370
+ * Host arrays use the reference layout: lattice[h_in | h_out | g_in | g_out] (4*9*nelem doubles, in/out selected by
+ * parity, :104-107), i = y + ny*x; fully periodic.  The functor's ten stored fields are not kept on the device; the
+ * ones a driver prints (C, P, Rho, Ux, Uy) are evaluated on download with update_fields' definitions.        */
+typedef struct clbm_yl2d clbm_yl2d;
+typedef struct clbm_yl2d_params {
+    int32_t abi_version;    /* CLBM_ABI_VERSION */
+    int32_t nx, ny;         /* the driver uses N x N (AB:497) */
+    int32_t device;         /* CUDA device ordinal, -1 = current */
+    double Sigma, W, M;     /* surface tension, interface thickness, mobility (AB:85-87) */
+    double RhoL, RhoH, tau; /* light / heavy density, hydrodynamic relaxation time (AB:83-84, :88) */
+} clbm_yl2d_params;
+/* parameters + iniCell on every node (AB:512-521); the first step performs the driver's initial update_fields */
+int  clbm_yl2d_create(const clbm_yl2d_params *params, clbm_yl2d **out);
+int  clbm_yl2d_destroy(clbm_yl2d *ctx);
+int  clbm_yl2d_step(clbm_yl2d *ctx, int nsteps);
+int  clbm_yl2d_step_timed(clbm_yl2d *ctx, int nsteps, float *ms);
+int  clbm_yl2d_sync(clbm_yl2d *ctx);
+int64_t clbm_yl2d_launch_count(const clbm_yl2d *ctx);
+/* C (phi), P (p*), Rho, Ux, Uy as update_fields leaves them (what saveVtkFields_Young_Laplace2D prints, AB:374-421) */
+int  clbm_yl2d_download_fields(clbm_yl2d *ctx, double *C, double *P, double *Rho, double *Ux, double *Uy);
+int  clbm_yl2d_download_lattice(clbm_yl2d *ctx, double *lattice, int *parity);
+/* hand over a state built by the reference's own code: populations + the velocity update_fields computed for them */
+int  clbm_yl2d_upload(clbm_yl2d *ctx, const double *lattice, const double *Ux, const double *Uy, int parity);
+/* CLBM_REDUCE_MASS: totalMass_Young_Laplace2D (AB:436-445); CLBM_REDUCE_ENERGY: computeEnergy_Young_Laplace2D (:425-435) */
+int  clbm_yl2d_reduce(clbm_yl2d *ctx, int kind, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -145,6 +145,19 @@ public:
         }
         os << "\n";
     }
+    // "u v 0" per node with a blank line after every row (the AB writers, AB/apps/Young_Laplace2D.h:406-412)
+    template <class V> void vectors_rows(const char *name, V value)
+    {
+        os << "VECTORS " << name << " float\n";
+        for (int y = 0; y < ny; ++y) {
+            for (int x = 0; x < nx; ++x) {
+                auto v = value((size_t)y + (size_t)ny * x);
+                os << v[0] << " " << v[1] << " 0\n";
+            }
+            os << "\n";
+        }
+        os << "\n";
+    }
     template <class V> void vectors(const char *name, V value)
     {
         os << "VECTORS " << name << " float\n";

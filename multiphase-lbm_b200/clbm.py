@@ -24,6 +24,8 @@ EXPORTS = [
     "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
     "clbm_pulsatile_kernel_timing_begin", "clbm_pulsatile_kernel_timing_end", "clbm_pulsatile_download_fields",
     "clbm_pulsatile_download_lattice", "clbm_pulsatile_upload",
+    "clbm_yl2d_create", "clbm_yl2d_destroy", "clbm_yl2d_step", "clbm_yl2d_step_timed", "clbm_yl2d_sync",
+    "clbm_yl2d_launch_count", "clbm_yl2d_download_fields", "clbm_yl2d_download_lattice", "clbm_yl2d_upload", "clbm_yl2d_reduce",
 ]
 
 _lib = None
@@ -87,6 +89,17 @@ def load_library(path=None):
     lib.clbm_pulsatile_download_fields.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.clbm_pulsatile_download_lattice.argtypes = [vp, vp, ip]
     lib.clbm_pulsatile_upload.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int]
+    lib.clbm_yl2d_create.argtypes = [ctypes.POINTER(P.YL2DParams), ctypes.POINTER(vp)]
+    lib.clbm_yl2d_destroy.argtypes = [vp]
+    lib.clbm_yl2d_step.argtypes = [vp, ctypes.c_int]
+    lib.clbm_yl2d_step_timed.argtypes = [vp, ctypes.c_int, fp]
+    lib.clbm_yl2d_sync.argtypes = [vp]
+    lib.clbm_yl2d_launch_count.argtypes = [vp]
+    lib.clbm_yl2d_launch_count.restype = ctypes.c_int64
+    lib.clbm_yl2d_download_fields.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.clbm_yl2d_download_lattice.argtypes = [vp, vp, ip]
+    lib.clbm_yl2d_upload.argtypes = [vp, vp, vp, vp, ctypes.c_int]
+    lib.clbm_yl2d_reduce.argtypes = [vp, ctypes.c_int, dp]
     for name in EXPORTS:
         getattr(lib, name)  # every declared symbol must resolve
     _lib = lib
@@ -364,3 +377,73 @@ class Pulsatile:
     def upload(self, lattice, flag, Pf, Ux, Uy, yr1, yr2, parity, t_iter):
         self._check(self.lib.clbm_pulsatile_upload(self._h, _ptr(lattice), _ptr(flag), _ptr(Pf), _ptr(Ux), _ptr(Uy), _ptr(yr1),
                                                    _ptr(yr2), int(parity), int(t_iter)))
+
+
+class YoungLaplace:
+    """Device-resident Young-Laplace case: the counterpart of `LBM_Young_Laplace2D` (AB/apps/Young_Laplace2D.h);
+    `step(n)` is n iterations of the reference loop body :555-565 (collide_stream_at, parity flip, update_fields)."""
+
+    def __init__(self, nx=128, ny=None, Sigma=0.01, W=4.0, M=0.02, RhoL=0.001, RhoH=1.0, tau=0.8, device=-1):
+        self.lib = load_library()
+        self.p = P.yl2d_params(nx, ny if ny else nx, Sigma, W, M, RhoL, RhoH, tau, device)
+        self.nx, self.ny = self.p.nx, self.p.ny
+        self.nelem = self.nx * self.ny
+        h = ctypes.c_void_p()
+        self._h = None
+        self._check(self.lib.clbm_yl2d_create(ctypes.byref(self.p), ctypes.byref(h)))
+        self._h = h
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ClbmError("clbm error %d: %s" % (rc, self.lib.clbm_last_error().decode()))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.clbm_yl2d_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, n=1):
+        self._check(self.lib.clbm_yl2d_step(self._h, int(n)))
+        return self
+
+    def step_timed(self, n):
+        ms = ctypes.c_float()
+        self._check(self.lib.clbm_yl2d_step_timed(self._h, int(n), ctypes.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._check(self.lib.clbm_yl2d_sync(self._h))
+
+    def launch_count(self):
+        return int(self.lib.clbm_yl2d_launch_count(self._h))
+
+    def fields(self, out=None):
+        o = out or {k: np.empty(self.nelem) for k in ("C", "P", "Rho", "Ux", "Uy")}
+        self._check(self.lib.clbm_yl2d_download_fields(self._h, *[_ptr(o.get(k)) for k in ("C", "P", "Rho", "Ux", "Uy")]))
+        return o
+
+    def lattice(self):
+        a = np.empty(36 * self.nelem)
+        par = ctypes.c_int()
+        self._check(self.lib.clbm_yl2d_download_lattice(self._h, _ptr(a), ctypes.byref(par)))
+        return a, par.value
+
+    def upload(self, lattice, Ux, Uy, parity):
+        self._check(self.lib.clbm_yl2d_upload(self._h, _ptr(lattice), _ptr(Ux), _ptr(Uy), int(parity)))
+
+    def reduce(self, kind):
+        v = ctypes.c_double()
+        self._check(self.lib.clbm_yl2d_reduce(self._h, int(kind), ctypes.byref(v)))
+        return v.value

@@ -149,3 +149,24 @@ def sc_layered_params(nx, ny, *, omega=None, tau=None, ulb=0.1, N=None, Re=60.0,
     p.gx, p.gy, p.G = gx, gy, G
     p.p_shift = sc_p_shift(rhog, rhol, a, b, R, p.TT)
     return p
+
+
+class YL2DParams(ctypes.Structure):
+    """clbm_yl2d_params mirror (include/clbm.h): the config keys of Young_Laplace2D() (AB/apps/Young_Laplace2D.h:465-494)."""
+    _fields_ = [
+        ("abi_version", ctypes.c_int32), ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("Sigma", ctypes.c_double), ("W", ctypes.c_double), ("M", ctypes.c_double),
+        ("RhoL", ctypes.c_double), ("RhoH", ctypes.c_double), ("tau", ctypes.c_double),
+    ]
+
+
+def yl2d_params(nx=128, ny=128, Sigma=0.01, W=4.0, M=0.02, RhoL=0.001, RhoH=1.0, tau=0.8, device=-1):
+    """defaults = AB/apps/Config_Files/config_laplace2D.txt"""
+    p = YL2DParams()
+    p.abi_version, p.nx, p.ny, p.device = ABI_VERSION, nx, ny, device
+    p.Sigma, p.W, p.M, p.RhoL, p.RhoH, p.tau = Sigma, W, M, RhoL, RhoH, tau
+    return p
+
+
+# Young-Laplace: two population sets read + written once, plus the stored velocity (2 doubles read + written)
+YL2D_BYTES_PER_LU = 4 * 9 * 8 + 4 * 8

@@ -102,3 +102,29 @@ def test_driver_two_layered_flow_matches_oracle(tmp_path):
     assert abs(e_drv - e_ref) <= 2e-9 * abs(e_ref) + 1e-30
     m_drv = np.loadtxt(tmp_path / "mass.dat")[1, 1]
     assert abs(m_drv - np.sum(u["s0"][bulk])) <= 1e-12 * m_drv
+
+
+@pytest.mark.gpu
+def test_driver_young_laplace_matches_reference_writer(tmp_path):
+    """COOLBM Young_Laplace2D (the AB reference's default problem): logs against the oracle, VTK layout of AB:374-421"""
+    from _oracle import YL2DOracle
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    (cfg / "config_laplace2D.txt").write_text("# test\nN 48\ntf 200\nout_freq 100\nvtk_freq 200\nSigma 0.01\nW 4.0\nM 0.02\nRhoL 0.001\nRhoH 1.0\ntau 0.8\n")
+    r = subprocess.run([_exe(), "Young_Laplace2D", str(cfg)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "it =     200   [100.0%]" in r.stdout and "Throughput:" in r.stdout
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".vtk")) == ["sol_0000000.vtk", "sol_0000200.vtk"]
+    o = YL2DOracle(48, 48).step(200)
+    f = o.fields()
+    mass = np.loadtxt(tmp_path / "mass.dat")
+    assert mass.shape == (3, 2) and abs(mass[2, 1] - f["Rho"].sum()) < 1e-11 * f["Rho"].sum()
+    e_ref = 0.5 * np.sum(f["Ux"] ** 2 + f["Uy"] ** 2) / (48 * 48)
+    assert abs(np.loadtxt(tmp_path / "energy.dat")[2, 1] - e_ref) <= 2e-8 * e_ref
+    # the phi block of the VTK file: 48 rows of 48 floats printed like `os << float(x)`
+    lines = open(tmp_path / "sol_0000200.vtk").read().split("\n")
+    k = lines.index("SCALARS phi float 1")
+    row0 = np.array(lines[k + 2].split(), dtype=np.float64)
+    ref_row0 = np.array([float("%g" % np.float32(f["C"][0 + 48 * x])) for x in range(48)])
+    np.testing.assert_array_equal(row0, ref_row0)
+    o.close()
