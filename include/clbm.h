@@ -54,6 +54,11 @@ extern "C" {
 #define CLBM_SC_FORCE_CONSTG  2 /* SC/apps/twoLayeredFlow2D.h:183-261: constant coupling G, psi = sqrt(2 (rho/3 - P_eos - p_shift) / (|G|/3)),
                                    psi_w = psi(rho_w), F=0 if rho<=0, uniform body force (gx, gy) added to F; pressure_node = P_eos */
 
+/* HCZ D2Q9 force variant, carried in the same `sc_force` member */
+#define CLBM_HCZ_FORCE_GRAVITY 0 /* PF/apps/rayleighTaylor2D.h:316-337: F = kappa rho grad lap phi, + gravity*rho in y */
+#define CLBM_HCZ_FORCE_LAYERED 1 /* PF/apps/twoLayeredFlow2D.h:310-330: F_x = kappa rho (grad lap phi)_x + rho*gx + gx_const, no y drive;
+                                    the rest population uses grad lap RHO instead (:595-598) */
+
 /* error codes */
 #define CLBM_OK          0
 #define CLBM_EINVAL     -1
@@ -75,6 +80,7 @@ extern "C" {
 #define CLBM_CASE_HCZ_RT2D         4 /* PF/apps/rayleighTaylor2D.h:155-193,802-820   args: none                       */
 #define CLBM_CASE_HCZ_LAPLACE3D    5 /* PF/apps/laplace3D.h:170-213,830-849          args: none                       */
 #define CLBM_CASE_SC_LAYERED2D     6 /* SC/apps/twoLayeredFlow2D.h:325-346,441-454 args: {rhol, rhog, h_lower, w_int}  */
+#define CLBM_CASE_HCZ_LAYERED2D    7 /* PF/apps/twoLayeredFlow2D.h:148-196,737-757 args: {h_lower, w_int}              */
 
 typedef struct clbm_ctx clbm_ctx;
 
@@ -103,6 +109,8 @@ typedef struct clbm_params {
     double phi_l, phi_g, rho_l, rho_g, kappa;
     /* Shan-Chen constant-G variant (LBM members of SC/apps/twoLayeredFlow2D.h:150-153) */
     double gx, gy, G, p_shift;
+    /* HCZ layered variant (LBM_twoLayeredPF2D members gx, Gx_const, PF/apps/twoLayeredFlow2D.h:127-128); gx is shared */
+    double gx_const;
 } clbm_params;
 
 /* ---- life cycle ---------------------------------------------------------- */

@@ -1,7 +1,7 @@
 // COOLBM.cpp -- case selector of the B200 drivers.  The reference hard-codes `string problem = "...";` in
 // apps/COOLBM.cpp and is rebuilt per case (SC/apps/COOLBM.cpp:66-84, PF/apps/COOLBM.cpp, AB/apps/COOLBM.cpp:118-150);
 // here the same names select the case at run time:
-//     COOLBM <problem> [config_dir]        problem in {laplace2D, contactAngle2D, twoLayeredFlow2D, droplet3D, rayleighTaylor2D, laplace3D, Young_Laplace2D,
+//     COOLBM <problem> [config_dir]        problem in {laplace2D, contactAngle2D, twoLayeredFlow2D, droplet3D, rayleighTaylor2D, laplace3D, twoLayeredPF2D, Young_Laplace2D,
 //                                          PulsatileBloodFlow2D [N] [max_iter] [vtk 0/1]}
 // config_dir defaults to ../apps/Config_Files, the path the reference drivers open relative to their build directory.
 #include <array>
@@ -13,6 +13,7 @@
 #include "laplace3D.h"
 #include "rayleighTaylor2D.h"
 #include "twoLayeredFlow2D.h"
+#include "twoLayeredPF2D.h"
 
 std::string problem = "laplace2D";
 
@@ -31,6 +32,7 @@ int main(int argc, char **argv)
         else if (problem == "droplet3D") coolbm::droplet3D(dir);
         else if (problem == "twoLayeredFlow2D") coolbm::twoLayeredFlow2D(dir);
         else if (problem == "Young_Laplace2D") coolbm::Young_Laplace2D(dir);
+        else if (problem == "twoLayeredPF2D") coolbm::twoLayeredPF2D(dir);
         else if (problem == "rayleighTaylor2D") coolbm::rayleighTaylor2D(dir);
         else if (problem == "laplace3D") coolbm::laplace3D(dir);
         else { std::cerr << "unknown problem \"" << problem << "\"\n"; return 2; }

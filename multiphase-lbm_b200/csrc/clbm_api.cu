@@ -269,7 +269,7 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
         // contactAngle2D.h:259-262 re-evaluates it on the CENTRE node's branch G1c = +-1/3
         const double cs2 = 1.0 / 3.0, rw = p->rho_w, dw = (1.0 - rw);
         const double Zw = 1.0 + (4.0 * rw - 2.0 * rw * rw) / (dw * dw * dw);
-        m.gx = p->gx; m.gy = p->gy; m.G = p->G; m.p_shift = p->p_shift;
+        m.gx = p->gx; m.gy = p->gy; m.G = p->G; m.p_shift = p->p_shift; m.gx_const = p->gx_const;
         m.kpsi = (p->G != 0.0) ? 2.0 / (fabs(p->G) * cs2) : 0.0;
         if (p->sc_force == CLBM_SC_FORCE_CONSTG) {
             // psi_w = psi_from_rho(rho_w) with the same constant-G mapping (twoLayeredFlow2D.h:226)

@@ -22,6 +22,7 @@ struct ModelParams {
     double tau;                  // 1/omega
     double psiw_pos, psiw_neg;   // wall pseudopotential for G1 = +1/3 / -1/3 at the centre node
     double gx, gy, G, p_shift;   // Shan-Chen constant-G variant (SC/apps/twoLayeredFlow2D.h:150-153)
+    double gx_const;             // HCZ layered variant: constant x force (PF/apps/twoLayeredFlow2D.h:128); sc_force carries the variant
     double kpsi;                 // 2 / (|G| cs2): psi = sqrt(kpsi * (rho/3 - P_eos - p_shift))
     double inv_dphi, drho;       // HCZ total_rho: rho = rho_g + (phi - phi_g) * inv_dphi * drho, inv_dphi = 1/(phi_l - phi_g)
 };

@@ -190,9 +190,8 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         double jx, jy, jz;
         Mom<L9f>::first(gg, jx, jy, jz);
         const double Pt = Mom<L9f>::sum(gg);
-        double forcex = mp.kappa * rho * glx;
-        double forcey = mp.kappa * rho * gly;
-        forcey += mp.gravity * rho;
+        double forcex, forcey;
+        hcz2d_force(mp, rho, glx, gly, forcex, forcey);
         // one division per node here (3/rho); every division by a constant is a multiplication by its reciprocal
         const double inv_r3 = 3.0 / rho, rho3 = rho * (1.0 / 3.0);
         const double u0 = (jx + forcex * (1.0 / 6.0)) * inv_r3;
@@ -221,7 +220,15 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
             const double t = L9f::t(4);
             const double Gam = t * (1. - usqr);
             const double eqg0 = t * (Pp - rho3 * usqr);
-            const double fg0 = hw * (-uF * Gam - uE * (Gam - t));      // (u.(-E)) as the reference writes it
+            // the layered variant drives the rest population with grad lap rho = slope * grad lap phi (twoLayeredFlow2D.h:595-598)
+            double uF0 = uF;
+            if (mp.sc_force == CLBM_HCZ_FORCE_LAYERED) {
+                const double slope = mp.drho * mp.inv_dphi;
+                double fx0, fy0;
+                hcz2d_force(mp, rho, slope * glx, slope * gly, fx0, fy0);
+                uF0 = u0 * fx0 + u1 * fy0;
+            }
+            const double fg0 = hw * (-uF0 * Gam - uE * (Gam - t));     // (u.(-E)) as the reference writes it
             const double ff0 = hw3 * uG * Gam;
             P.fout[4][i] = om1 * f[4] + op * Gam + ff0;
             P.gout[4][i] = om1 * gg[4] + omega * eqg0 + fg0;

@@ -96,9 +96,8 @@ CLBM_D void hcz2d_node(const ModelParams &mp, const double *g9, const double *co
     double jx, jy, jz;
     Mom<L9>::first(g9, jx, jy, jz);
     const double Pt = Mom<L9>::sum(g9);
-    double forcex = mp.kappa * o.rho * o.glap.x;
-    double forcey = mp.kappa * o.rho * o.glap.y;
-    forcey += mp.gravity * o.rho;
+    double forcex, forcey;
+    hcz2d_force(mp, o.rho, o.glap.x, o.glap.y, forcex, forcey);
     o.ux = (jx + forcex / 6.0) / (o.rho / 3.0);
     o.uy = (jy + forcey / 6.0) / (o.rho / 3.0);
     const Grad2 grho = hcz2d_grad(fld[4], flag, n);
@@ -133,9 +132,12 @@ hcz2d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, 
     const double omega = mp.omega, hw = 1. - 0.5 * omega;
     const double u0 = o.ux, u1 = o.uy, phi = o.phi, rho = o.rho, P = o.P;
     const double usqr = 1.5 * (u0 * u0 + u1 * u1);
-    double forcex = mp.kappa * rho * o.glap.x;
-    double forcey = mp.kappa * rho * o.glap.y;
-    forcey += mp.gravity * rho;
+    double forcex, forcey, forcex0, forcey0;
+    hcz2d_force(mp, rho, o.glap.x, o.glap.y, forcex, forcey);
+    // the layered variant drives its REST population with grad lap rho (PF/apps/twoLayeredFlow2D.h:595-598);
+    // rho is an affine function of phi, so grad lap rho = (rho_l - rho_g)/(phi_l - phi_g) * grad lap phi, mirror rule included
+    const double slope = (mp.sc_force == CLBM_HCZ_FORCE_LAYERED) ? mp.drho * mp.inv_dphi : 1.0;
+    hcz2d_force(mp, rho, slope * o.glap.x, slope * o.glap.y, forcex0, forcey0);
     const double Ex = o.gpsirho.x, Ey = o.gpsirho.y;
     const double inv_phi = 1.0 / phi;
 
@@ -150,7 +152,7 @@ hcz2d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, 
         if (k == 4) {
             const double eqf0 = phi * L9::t(4) * (1. - usqr);
             const double eqg0 = L9::t(4) * (P - (rho / 3.0) * usqr);
-            const double fg0 = hw * (-(u0 * forcex + u1 * forcey) * eqf0 * inv_phi +
+            const double fg0 = hw * (-(u0 * forcex0 + u1 * forcey0) * eqf0 * inv_phi +
                                      ((u0 * -Ex + u1 * -Ey) * (eqf0 * inv_phi - L9::t(4))));
             const double ff0 = hw * (-3.0 * (u0 * -o.gpsiphi.x + u1 * -o.gpsiphi.y) * eqf0 * inv_phi);
             pf = (1 - omega) * f[4] + omega * eqf0 + ff0;

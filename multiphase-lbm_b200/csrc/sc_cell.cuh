@@ -173,4 +173,14 @@ CLBM_D void sc_outputs(const ModelParams &mp, const double *f, ScForceSums &s, d
     }
 }
 
+// Driving force of the two HCZ D2Q9 variants from kappa rho grad(lap X): PF/apps/rayleighTaylor2D.h:325-327 (gravity in y)
+// and PF/apps/twoLayeredFlow2D.h:316-317 (rho gx + Gx_const in x, nothing in y)
+CLBM_D void hcz2d_force(const ModelParams &mp, double rho, double glx, double gly, double &forcex, double &forcey)
+{
+    forcex = mp.kappa * rho * glx;
+    forcey = mp.kappa * rho * gly;
+    if (mp.sc_force == CLBM_HCZ_FORCE_LAYERED) forcex += rho * mp.gx + mp.gx_const;
+    else forcey += mp.gravity * rho;
+}
+
 }  // namespace clbm

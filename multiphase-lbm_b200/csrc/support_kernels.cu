@@ -14,8 +14,8 @@ struct CaseArgs { double a[8]; int n; };
 
 template <class L>
 __global__ void __launch_bounds__(256)
-init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, uint8_t *__restrict__ flag, Geom g, ModelParams mp,
-                 int case_id, CaseArgs A)
+init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, double *__restrict__ f1, double *__restrict__ g1,
+                 uint8_t *__restrict__ flag, Geom g, ModelParams mp, int case_id, CaseArgs A)
 {
     const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= g.ncs) return;
@@ -28,7 +28,7 @@ init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, uint8_t *__r
     const int nx = g.nx_global, ny = g.ny, nz = g.nz;
 
     double vf = 0.0, vg = 0.0;   // f_k = vf * t_k, g_k = vg * t_k
-    bool wall = false;
+    bool wall = false, both = false;
     switch (case_id) {
     case CLBM_CASE_SC_LAPLACE2D: {   // SC/apps/laplace2D.h:132-145, 397-404
         const double cx = double(nx) / 2.0, cy = double(ny) / 2.0, Rdrop = A.a[2];
@@ -73,6 +73,22 @@ init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, uint8_t *__r
         vg = (rho / 3.0) * (1.0 + rt + rt * rt - rt * rt * rt) / (d * d * d) - mp.a * rho * rho;
         wall = (iY == 0 || iY == ny - 1);
     } break;
+    case CLBM_CASE_HCZ_LAYERED2D: {   // PF/apps/twoLayeredFlow2D.h:148-196, 737-757   args {h_lower, w_int}
+        const double H = double(ny - 1);
+        const double hl = A.a[0] < 0.0 ? 0.0 : (A.a[0] > 0.5 ? 0.5 : A.a[0]);
+        const double y_low = hl * H, y_high = H - y_low;
+        const int wi = (int)A.a[1];
+        const double w = double(wi > 1 ? wi : 1), yy = double(iY);
+        double s_liq = 0.5 * (1.0 - tanh((yy - y_low) / w)) + 0.5 * (1.0 + tanh((yy - y_high) / w));
+        s_liq = s_liq < 0.0 ? 0.0 : (s_liq > 1.0 ? 1.0 : s_liq);
+        const double s_gas = 1.0 - s_liq;
+        const double rho = s_liq * mp.rho_g + s_gas * mp.rho_l;
+        const double rt = mp.b * rho / 4.0, d = 1.0 - rt;
+        vf = s_liq * mp.phi_g + s_gas * mp.phi_l;
+        vg = (rho / 3.0) * (1.0 + rt + rt * rt - rt * rt * rt) / (d * d * d) - mp.a * rho * rho;
+        wall = (iY == 0 || iY == ny - 1);
+        both = true;    // the reference fills fout / gout too (:189-190) and inigeom zeroes only the parity-0 buffer of walls
+    } break;
     case CLBM_CASE_HCZ_LAPLACE3D: {   // PF/apps/laplace3D.h:170-213
         const double xc = double(nx) / 2.0, yc = double(ny) / 2.0, zc = double(nz) / 2.0, R = 0.25 * nx;
         const double dx = double(iX) - xc, dy = double(iY) - yc, dz = double(iZ) - zc;
@@ -92,6 +108,8 @@ init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, uint8_t *__r
     for (int k = 0; k < L::Q; ++k) {
         f[(size_t)k * g.ncs + s] = wall ? 0.0 : vf * L::t(k);
         if (gpop) gpop[(size_t)k * g.ncs + s] = wall ? 0.0 : vg * L::t(k);
+        if (both && f1) f1[(size_t)k * g.ncs + s] = vf * L::t(k);
+        if (both && g1) g1[(size_t)k * g.ncs + s] = vg * L::t(k);
     }
 }
 
@@ -101,7 +119,7 @@ int model_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)
     const bool sc2 = m == CLBM_MODEL_SC_D2Q9, sc3 = m == CLBM_MODEL_SC_D3Q19;
     const bool ok = (sc2 && (case_id == CLBM_CASE_SC_LAPLACE2D || case_id == CLBM_CASE_SC_CONTACT2D || case_id == CLBM_CASE_SC_LAYERED2D)) ||
                     (sc3 && (case_id == CLBM_CASE_SC_DROPLET3D || case_id == CLBM_CASE_SC_DROPLET3D_PER)) ||
-                    (m == CLBM_MODEL_HCZ_D2Q9 && case_id == CLBM_CASE_HCZ_RT2D) ||
+                    (m == CLBM_MODEL_HCZ_D2Q9 && (case_id == CLBM_CASE_HCZ_RT2D || case_id == CLBM_CASE_HCZ_LAYERED2D)) ||
                     (m == CLBM_MODEL_HCZ_D3Q19 && case_id == CLBM_CASE_HCZ_LAPLACE3D);
     if (!ok) { set_error("case %d does not belong to model %d", case_id, m); return CLBM_EINVAL; }
     if ((sc2 || sc3) && nargs < 3) { set_error("Shan-Chen droplet cases need {rhol, rhog, R}"); return CLBM_EINVAL; }
@@ -113,9 +131,9 @@ int model_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)
     for (int s = 0; s < c->sets; ++s) CLBM_CUDA(cudaMemsetAsync(c->pop[s][1], 0, (size_t)c->Q * g.ncs * sizeof(double), c->stream));
     LaunchScope ls(c, "init_case");
     if (c->Q == 9)
-        init_case_kernel<D2Q9><<<grid_for(g.ncs, 256), 256, 0, c->stream>>>(c->pop[0][0], c->pop[1][0], c->flag, g, c->mp, case_id, A);
+        init_case_kernel<D2Q9><<<grid_for(g.ncs, 256), 256, 0, c->stream>>>(c->pop[0][0], c->pop[1][0], c->pop[0][1], c->pop[1][1], c->flag, g, c->mp, case_id, A);
     else
-        init_case_kernel<D3Q19><<<grid_for(g.ncs, 256), 256, 0, c->stream>>>(c->pop[0][0], c->pop[1][0], c->flag, g, c->mp, case_id, A);
+        init_case_kernel<D3Q19><<<grid_for(g.ncs, 256), 256, 0, c->stream>>>(c->pop[0][0], c->pop[1][0], c->pop[0][1], c->pop[1][1], c->flag, g, c->mp, case_id, A);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -9,9 +9,10 @@ ABI_VERSION = 2
 
 MODEL_SC_D2Q9, MODEL_SC_D3Q19, MODEL_HCZ_D2Q9, MODEL_HCZ_D3Q19, MODEL_PULSATILE = range(5)
 SC_FORCE_LAPLACE, SC_FORCE_CONTACT, SC_FORCE_CONSTG = 0, 1, 2
+HCZ_FORCE_GRAVITY, HCZ_FORCE_LAYERED = 0, 1
 REDUCE_MASS, REDUCE_ENERGY, REDUCE_UMAX = 0, 1, 2
 (CASE_SC_LAPLACE2D, CASE_SC_CONTACT2D, CASE_SC_DROPLET3D, CASE_SC_DROPLET3D_PER,
- CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D, CASE_SC_LAYERED2D) = range(7)
+ CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D, CASE_SC_LAYERED2D, CASE_HCZ_LAYERED2D) = range(8)
 
 MODEL_Q = {MODEL_SC_D2Q9: 9, MODEL_SC_D3Q19: 19, MODEL_HCZ_D2Q9: 9, MODEL_HCZ_D3Q19: 19, MODEL_PULSATILE: 9}
 MODEL_SETS = {MODEL_SC_D2Q9: 1, MODEL_SC_D3Q19: 1, MODEL_HCZ_D2Q9: 2, MODEL_HCZ_D3Q19: 2, MODEL_PULSATILE: 1}
@@ -31,6 +32,7 @@ class Params(ctypes.Structure):
         ("phi_l", ctypes.c_double), ("phi_g", ctypes.c_double),
         ("rho_l", ctypes.c_double), ("rho_g", ctypes.c_double), ("kappa", ctypes.c_double),
         ("gx", ctypes.c_double), ("gy", ctypes.c_double), ("G", ctypes.c_double), ("p_shift", ctypes.c_double),
+        ("gx_const", ctypes.c_double),
     ]
 
     @property
@@ -170,3 +172,14 @@ def yl2d_params(nx=128, ny=128, Sigma=0.01, W=4.0, M=0.02, RhoL=0.001, RhoH=1.0,
 
 # Young-Laplace: two population sets read + written once, plus the stored velocity (2 doubles read + written)
 YL2D_BYTES_PER_LU = 4 * 9 * 8 + 4 * 8
+
+
+def hcz_layered_params(nx, ny, *, omega=None, tau=None, ulb=0.1, N=None, Re=60.0, phi_l=0.251, phi_g=0.024, rho_l=0.12, rho_g=0.04,
+                       a=4.0, b=4.0, kappa=0.001, gx=0.0, gx_const=1e-8, **kw):
+    """HCZ two-layered channel flow; defaults = PF/apps/Config_Files/config_twoLayeredFlow2D.txt"""
+    if omega is None:
+        omega = 1.0 / tau if tau is not None else lb_parameters(ulb, N if N else ny - 1, Re)[1]
+    p = make_params(MODEL_HCZ_D2Q9, nx, ny, omega=omega, phi_l=phi_l, phi_g=phi_g, rho_l=rho_l, rho_g=rho_g, a=a, b=b, kappa=kappa,
+                    gravity=0.0, sc_force=HCZ_FORCE_LAYERED, **kw)
+    p.gx, p.gx_const = gx, gx_const
+    return p

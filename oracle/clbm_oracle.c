@@ -335,7 +335,7 @@ static void sc_fields(const clbm_params *p, int D, const double *fin, const uint
  * HCZ D2Q9 -- PF/apps/rayleighTaylor2D.h
  * ======================================================================== */
 typedef struct {
-    double *phi, *Pt, *ur0, *ur1, *rho, *psiphi, *psirho, *lap;
+    double *phi, *Pt, *ur0, *ur1, *rho, *psiphi, *psirho, *lap, *laprho;
 } hcz2_f;
 
 static double hcz_pth_minus(double x, double a, double b)
@@ -378,6 +378,7 @@ static void hcz2_fieldsets(const clbm_params *p, const double *fin, const double
     const size_t ne = (size_t)nx * ny;
     F->phi = scratch(0, ne); F->Pt = scratch(1, ne); F->ur0 = scratch(2, ne); F->ur1 = scratch(3, ne);
     F->rho = scratch(4, ne); F->psiphi = scratch(5, ne); F->psirho = scratch(6, ne); F->lap = scratch(7, ne);
+    F->laprho = scratch(8, ne);
 #pragma omp parallel for schedule(static)
     for (long long ii = 0; ii < (long long)ne; ++ii) {
         size_t i = (size_t)ii;
@@ -411,6 +412,32 @@ static void hcz2_fieldsets(const clbm_params *p, const double *fin, const double
         for (int k = 0; k < 9; ++k) sum += T9[k] * (F->phi[hcz2_nb(p, flag, iX, iY, k)] - phi_c);
         F->lap[i] = 6.0 * sum;
     }
+    /* laplacian_rho (PF/apps/twoLayeredFlow2D.h:245-272): only the layered variant's rest population reads it */
+    if (p->sc_force == CLBM_HCZ_FORCE_LAYERED) {
+#pragma omp parallel for schedule(static)
+        for (long long ii = 0; ii < (long long)ne; ++ii) {
+            size_t i = (size_t)ii;
+            if (flag[i] != BULK) { F->laprho[i] = 0.0; continue; }
+            int iX = (int)(i / ny), iY = (int)(i % ny);
+            double rho_c = F->rho[i], sum = 0.0;
+            for (int k = 0; k < 9; ++k) sum += T9[k] * (F->rho[hcz2_nb(p, flag, iX, iY, k)] - rho_c);
+            F->laprho[i] = 6.0 * sum;
+        }
+    }
+}
+
+/* the driving force of the two HCZ D2Q9 variants from kappa rho grad(lap X): rayleighTaylor2D.h:325-327 (gravity in y)
+ * and twoLayeredFlow2D.h:316-317 (rho gx + Gx_const in x) */
+static void hcz2_force(const clbm_params *p, double rho, const double glap[2], double *forcex, double *forcey)
+{
+    if (p->sc_force == CLBM_HCZ_FORCE_LAYERED) {
+        *forcex = p->kappa * rho * glap[0] + rho * p->gx + p->gx_const;
+        *forcey = p->kappa * rho * glap[1];
+    } else {
+        *forcex = p->kappa * rho * glap[0];
+        *forcey = p->kappa * rho * glap[1];
+        *forcey += p->gravity * rho;
+    }
 }
 
 /* velocity :316-337 and total_P :452-460 of one bulk node */
@@ -421,9 +448,8 @@ static void hcz2_uP(const clbm_params *p, const uint8_t *flag, const hcz2_f *F, 
     hcz2_grad(p, flag, F->lap, iX, iY, glap_phi);
     u[0] = F->ur0[i];
     u[1] = F->ur1[i];
-    double forcex = p->kappa * rho * glap_phi[0];
-    double forcey = p->kappa * rho * glap_phi[1];
-    forcey += p->gravity * rho;
+    double forcex, forcey;
+    hcz2_force(p, rho, glap_phi, &forcex, &forcey);
     u[0] += forcex / 6.0;
     u[1] += forcey / 6.0;
     u[0] /= (rho / 3.0);
@@ -440,7 +466,7 @@ static void hcz2_step(const clbm_params *p, const double *fin, double *fout, con
 {
     const int nx = p->nx, ny = p->ny;
     const size_t ne = (size_t)nx * ny;
-    const double omega = p->omega, kappa = p->kappa, gravity = p->gravity;
+    const double omega = p->omega;
     hcz2_f F;
     hcz2_fieldsets(p, fin, gin, flag, &F);
 
@@ -466,9 +492,8 @@ static void hcz2_step(const clbm_params *p, const double *fin, double *fout, con
             double eqg_op = T9[ko] * (P + (rho / 3.0) * (3 * ck_u_op + 4.5 * ck_u_op * ck_u_op - usqr));
             double e_u_x = C9[k][0] - u[0], e_u_x_op = C9[ko][0] - u[0];
             double e_u_y = C9[k][1] - u[1], e_u_y_op = C9[ko][1] - u[1];
-            double forcex = kappa * rho * glap_phi[0];
-            double forcey = kappa * rho * glap_phi[1];
-            forcey += gravity * rho;
+            double forcex, forcey;
+            hcz2_force(p, rho, glap_phi, &forcex, &forcey);
             double Ex = gpsi_rho[0], Ey = gpsi_rho[1];
             double fg = (1. - 0.5 * omega) * ((e_u_x * forcex + e_u_y * forcey) * eqf / phi)
                       + (1. - 0.5 * omega) * ((e_u_x * -Ex) + (e_u_y * -Ey)) * (eqf / phi - T9[k]);
@@ -494,9 +519,14 @@ static void hcz2_step(const clbm_params *p, const double *fin, double *fout, con
             int k = 4;
             double eqf0 = phi * T9[k] * (1. - usqr);
             double eqg0 = T9[k] * (P - (rho / 3.0) * usqr);
-            double forcex = kappa * rho * glap_phi[0];
-            double forcey = kappa * rho * glap_phi[1];
-            forcey += gravity * rho;
+            double forcex, forcey;
+            if (p->sc_force == CLBM_HCZ_FORCE_LAYERED) { /* rest population: grad lap RHO (twoLayeredFlow2D.h:595-598, B.9) */
+                double glap_rho[2];
+                hcz2_grad(p, flag, F.laprho, iX, iY, glap_rho);
+                hcz2_force(p, rho, glap_rho, &forcex, &forcey);
+            } else {
+                hcz2_force(p, rho, glap_phi, &forcex, &forcey);
+            }
             double Ex = gpsi_rho[0], Ey = gpsi_rho[1];
             double fg0 = (1. - 0.5 * omega) *
                          (-(u[0] * forcex + u[1] * forcey) * eqf0 / phi + ((u[0] * -Ex + u[1] * -Ey) * (eqf0 / phi - T9[k])));
@@ -859,6 +889,31 @@ int oracle_init_case(const clbm_params *p, int case_id, const double *args, int 
             double rt_rho = p->b * rho / 4.0;
             double p_rho = (rho / 3.0) * (1.0 + rt_rho + rt_rho * rt_rho - rt_rho * rt_rho * rt_rho) / pow(1.0 - rt_rho, 3) - p->a * rho * rho;
             for (int k = 0; k < 9; ++k) { f[(size_t)k * ne + i] = phi * T9[k]; g[(size_t)k * ne + i] = p_rho * T9[k]; }
+            wall = (iY == 0 || iY == ny - 1);
+        } break;
+        case CLBM_CASE_HCZ_LAYERED2D: { /* PF/apps/twoLayeredFlow2D.h:148-196 (iniLattice_layers: BOTH buffers), :737-757 (inigeom) */
+            if (nargs < 2) return -1;
+            const double h_lower = args[0];
+            const int w_int = (int)args[1];
+            const double H = (double)(ny - 1);
+            const double y_low = (h_lower < 0.0 ? 0.0 : (h_lower > 0.5 ? 0.5 : h_lower)) * H, y_high = H - y_low;
+            const double w = (double)(w_int > 1 ? w_int : 1), yy = (double)iY;
+            const double s_bottom = 0.5 * (1.0 - tanh((yy - y_low) / w));
+            const double s_top = 0.5 * (1.0 + tanh((yy - y_high) / w));
+            double s_liq = s_bottom + s_top;
+            s_liq = s_liq < 0.0 ? 0.0 : (s_liq > 1.0 ? 1.0 : s_liq);
+            const double s_gas = 1.0 - s_liq;
+            const double phi = s_liq * p->phi_g + s_gas * p->phi_l;
+            const double rho = s_liq * p->rho_g + s_gas * p->rho_l;
+            const double rt = p->b * rho / 4.0;
+            const double denom = pow(1.0 - rt, 3);
+            const double p_rho = (rho / 3.0) * (1.0 + rt + rt * rt - rt * rt * rt) / denom - p->a * rho * rho;
+            for (int k = 0; k < 9; ++k) {
+                f[(size_t)k * ne + i] = phi * T9[k];
+                g[(size_t)k * ne + i] = p_rho * T9[k];
+                f[npop + (size_t)k * ne + i] = phi * T9[k];      /* fout = fin, gout = gin (:189-190); inigeom only */
+                g[npop + (size_t)k * ne + i] = p_rho * T9[k];    /* zeroes the parity-0 buffer of the wall nodes     */
+            }
             wall = (iY == 0 || iY == ny - 1);
         } break;
         case CLBM_CASE_HCZ_LAPLACE3D: { /* PF/apps/laplace3D.h:170-213 */

@@ -42,6 +42,12 @@ CASES = {
     "hcz_rt2d_24x50_s25": ("ref_hcz_rt2d", dict(nx=24, ny=50, steps=25, omega=1.7, phi_l=0.251, phi_g=0.024,
                            rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-2e-5),
                            2, 9, ["phi", "P", "rho", "ux", "uy"]),
+    "hcz_layered2d_10x41_s60": ("ref_hcz_layered2d", dict(nx=10, ny=41, steps=60, omega=1.0, phi_l=0.251, phi_g=0.024, rho_l=0.12,
+                                rho_g=0.04, a=4.0, b=4.0, kappa=0.001, gx=0.0, gx_const=1e-6, h_lower=0.3, w_int=2),
+                                2, 9, ["phi", "P", "rho", "ux", "uy"]),
+    "hcz_layered2d_12x29_s45": ("ref_hcz_layered2d", dict(nx=12, ny=29, steps=45, omega=1.4, phi_l=0.251, phi_g=0.024, rho_l=0.12,
+                                rho_g=0.04, a=4.0, b=4.0, kappa=0.004, gx=2e-6, gx_const=5e-7, h_lower=0.25, w_int=3),
+                                2, 9, ["phi", "P", "rho", "ux", "uy"]),
     "hcz_laplace3d_8x8x8_s4": ("ref_hcz_laplace3d", dict(nx=8, ny=8, nz=8, steps=4, omega=0.5617977528089888,
                                phi_l=0.251, phi_g=0.024, rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=5e-4, gravity=0.0),
                                2, 19, ["phi", "P", "rho", "ux", "uy", "uz"]),

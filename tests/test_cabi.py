@@ -30,8 +30,8 @@ def test_header_symbols_all_exported():
 
 
 def test_params_struct_matches_header_layout():
-    # 10 int32 + 16 doubles, naturally aligned: must equal sizeof(clbm_params) on the C side
-    assert ctypes.sizeof(P.Params) == 10 * 4 + 16 * 8
+    # 10 int32 + 17 doubles, naturally aligned: must equal sizeof(clbm_params) on the C side
+    assert ctypes.sizeof(P.Params) == 10 * 4 + 17 * 8
     assert P.Params.omega.offset == 40
 
 

@@ -49,13 +49,21 @@ def test_golden_fixture(name, fused):
     prm, case, args, steps, fmap = _cases.golden_setup(name)
     ora, got, pops, flags = run_pair(prm, case, args, steps, fused)
     np.testing.assert_array_equal(flags, z["flag"])
+    # the reference's layered HCZ init also fills the OUT buffer, and clbm_upload hands over the in buffer only: the (never
+    # read) populations of bounce_back nodes, and phi / rho evaluated on them, differ after an odd number of steps --
+    # compare bulk nodes there (test_hcz_layered2d_1000_steps covers all nodes through the device-side init)
+    sel = (z["flag"] == 1) if name.startswith("hcz_layered2d") else slice(None)
     for gname, slot in fmap.items():
-        ref = z[gname]
+        ref = z[gname][sel]
         if np.max(np.abs(ref)) == 0.0:
             continue
-        err = _cases.rel_linf(got[slot], ref)
+        err = _cases.rel_linf(got[slot][sel], ref)
         assert err < TOL, "%s %s: rel Linf %.3e" % (name, gname, err)
-    assert _cases.rel_linf(pops, z["pops"]) < TOL
+    ref_pops = z["pops"]
+    if name.startswith("hcz_layered2d"):
+        bulk = z["flag"] == 1
+        pops, ref_pops = pops[..., bulk], ref_pops[..., bulk]
+    assert _cases.rel_linf(pops, ref_pops) < TOL
 
 
 # ---------------------------------------------------------------------------------------------
@@ -304,3 +312,23 @@ def test_sc_layered2d_constant_g_1000_steps(fused):
     check_fields(ref, got, ("s0", "s1", "ux", "uy"))
     assert _cases.rel_linf(pops, ora.in_pops()) < TOL
     assert np.max(np.abs(ref["ux"])) > 1e-7      # the body force drives a flow
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_hcz_layered2d_1000_steps(fused):
+    """PF/apps/twoLayeredFlow2D.h: HCZ two-layered channel flow (x body force, rest population driven by grad lap rho),
+    10 x 101 lattice of the shipped config, device-side initial condition (both buffers, like the reference), 1000 steps"""
+    prm = P.hcz_layered_params(10, 101, ulb=0.1, N=100, Re=60.0, gx=1e-7, gx_const=1e-6).copy(fused=fused)
+    args = (0.3, 2.0)
+    ora = OracleSim(prm).init_case(P.CASE_HCZ_LAYERED2D, args)
+    with pkg.clbm.Lattice(prm) as lat:
+        lat.init_case(P.CASE_HCZ_LAYERED2D, args)
+        np.testing.assert_array_equal(lat.flags(), ora.flag)
+        assert _cases.rel_linf(lat.in_pops(), ora.in_pops()) < 1e-14
+        lat.step(1001)                      # odd: the in buffer is now the one only the device-side init can have filled at the walls
+        got, pops = lat.fields(), lat.in_pops()
+    ora.step(1001)
+    ref = ora.fields()
+    check_fields(ref, got, ("s0", "s1", "s2", "ux", "uy"))
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+    assert np.max(np.abs(ref["ux"])) > 1e-6
