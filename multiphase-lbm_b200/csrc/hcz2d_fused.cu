@@ -193,7 +193,7 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         double forcex, forcey;
         hcz2d_force(mp, rho, glx, gly, forcex, forcey);
         // one division per node here (3/rho); every division by a constant is a multiplication by its reciprocal
-        const double inv_r3 = 3.0 / rho, rho3 = rho * (1.0 / 3.0);
+        const double inv_r3 = 3.0 * fast_rcp(rho), rho3 = rho * (1.0 / 3.0);
         const double u0 = (jx + forcex * (1.0 / 6.0)) * inv_r3;
         const double u1 = (jy + forcey * (1.0 / 6.0)) * inv_r3;
         const double Pp = Pt - 0.5 * ((u0 * -grx + u1 * -gry) * (1.0 / 3.0));

@@ -202,7 +202,7 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         o.Fx = mp.kappa * o.phi * gl[0];
         o.Fy = mp.kappa * o.phi * gl[1] + mp.gravity * o.rho;
         o.Fz = mp.kappa * o.phi * gl[2];
-        const double inv_d = 3.0 / o.rho;          // 1 / (rho/3)
+        const double inv_d = 3.0 * fast_rcp(o.rho);   // 1 / (rho/3)
         o.u0 = (mo[1] + o.Fx * (1. / 6.)) * inv_d;
         o.u1 = (mo[2] + o.Fy * (1. / 6.)) * inv_d;
         o.u2 = (mo[3] + o.Fy * (1. / 6.)) * inv_d;   // sic: forcey (laplace3D.h:304)
@@ -329,7 +329,7 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const double uE = u0 * ge[0] + u1 * ge[1] + u2 * ge[2];
                 const double uG = u0 * cur.gp[0] + u1 * cur.gp[1] + u2 * cur.gp[2];
                 const double rho3 = rho * (1. / 3.);
-                const double ffs = hw * 3.0 * phi / rho;   // ff = hw * C * 3 * eqf / rho,  eqf = phi * Gamma
+                const double ffs = hw * 3.0 * phi * fast_rcp(rho);   // ff = hw * C * 3 * eqf / rho,  eqf = phi * Gamma
                 const int xp = g.wx(x + 1), xm = g.wx(x - 1);
                 const int i = (x + G) * plane + yz;
                 const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;

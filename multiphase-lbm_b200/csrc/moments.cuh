@@ -73,6 +73,28 @@ struct ScEos {
     }
 };
 
+// ---- fast FP64 reciprocal / square root for the kernels that are checked at 1e-10 (NOT for the bit-exact paths) --------
+// An IEEE FP64 division or square root is a 25-35 instruction sequence with a slow-path branch.  The hardware seeds
+// (rcp.approx / rsqrt.approx, ~2^-22 relative) refined by two Newton steps in FMA arithmetic are accurate to 1-2 ulp in
+// about 8 instructions.  Arguments must be normal and positive where a square root is taken (callers guard).
+CLBM_D double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+CLBM_D double fast_sqrt(double x)      // x > 1e-290
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-0.5 * x * y, y, 1.5);           // y ~ x^-1/2
+    y = y * fma(-0.5 * x * y, y, 1.5);
+    const double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);       // one correction of s ~ x^1/2
+}
+
 // ---- HCZ Carnahan-Starling "psi" = p_th(x) - x/3 (PF/apps/rayleighTaylor2D.h:237-242, 374-379) ----
 CLBM_D double hcz_psi(double x, double a, double b)
 {
@@ -89,7 +111,7 @@ CLBM_D double hcz_psi1(double x, double a, double b)
     const double rt = b * x * 0.25;
     const double d = 1.0 - rt;
     const double x3 = x * (1.0 / 3.0);
-    return x3 * ((1.0 + rt + rt * rt - rt * rt * rt) / (d * d * d)) - a * x * x - x3;
+    return x3 * ((1.0 + rt + rt * rt - rt * rt * rt) * fast_rcp(d * d * d)) - a * x * x - x3;
 }
 
 }  // namespace clbm

@@ -50,19 +50,20 @@ CLBM_D Nbr make_nbr(const Geom &g, int x, int y, int z)
 CLBM_D double sc_psi_g1(const ModelParams &mp, double rho, bool &g1_pos)
 {
     const double d = 1.0 - rho;
-    const double Zr = 1.0 + (4.0 * rho - 2.0 * rho * rho) / (d * d * d);
+    const double Zr = 1.0 + (4.0 * rho - 2.0 * rho * rho) * fast_rcp(d * d * d);
     if (mp.sc_force == CLBM_SC_FORCE_CONSTG) {
         // constant-G mapping (SC/apps/twoLayeredFlow2D.h:183-188): psi^2 = 2 (cs2 rho - (P_eos + p_shift)) / (|G| cs2)
         g1_pos = true;
         const double S = (1.0 / 3.0) * rho - (rho * mp.R * mp.TT * Zr - mp.a * rho * rho + mp.p_shift);
-        return (S > 0.0) ? sqrt(mp.kpsi * S) : 0.0;
+        const double v = mp.kpsi * S;
+        return (v > 1e-280) ? fast_sqrt(v) : ((v > 0.0) ? sqrt(v) : 0.0);
     }
     const double s = mp.R * mp.TT * Zr - mp.a * rho - (1.0 / 3.0);
     g1_pos = s > 0.0;
     const double P = rho * mp.R * mp.TT * Zr - mp.a * rho * rho;
     const double q = P - (1.0 / 3.0) * rho;
     const double val = g1_pos ? 18.0 * q : -18.0 * q;
-    return (val > 0.0) ? sqrt(val) : 0.0;
+    return (val > 1e-280) ? fast_sqrt(val) : ((val > 0.0) ? sqrt(val) : 0.0);
 }
 
 struct ScForceSums {
@@ -124,7 +125,7 @@ template <class L>
 CLBM_D void sc_collide_rho(const ModelParams &mp, const double *f, ScForceSums &s, double rho_raw, double psi_c, bool g1_pos, double *out)
 {
     const double rho = fmax(rho_raw, 1e-14);
-    const double inv = 1.0 / rho;
+    const double inv = fast_rcp(rho);
     double jx, jy, jz, F[3];
     Mom<L>::first(f, jx, jy, jz);
     sc_force<L>(mp, s, rho_raw, psi_c, g1_pos, F);
