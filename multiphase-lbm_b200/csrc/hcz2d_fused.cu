@@ -264,7 +264,9 @@ static int launch_hcz2d_fused(clbm_ctx *c)
     // short x-chunks keep concurrently resident CTAs on neighbouring columns (L2 locality of the overlapping segment
     // rows): 48-64 columns measured best at 2048 x 8194 (14.1 vs 12.5 GLUPS at 128 and 9.6 at 512)
     int xchunk = g.nx < 48 ? g.nx : 48;
-    (void)segs;
+    // small lattices (BASELINE configs[1], 256 x 1026): shorter chunks until there are two CTAs per SM slot
+    const long long want = 2LL * 148 * MINB;
+    while (xchunk > 8 && (long long)segs * ((g.nx + xchunk - 1) / xchunk) < want) xchunk /= 2;
     if (const char *e = getenv("CLBM_HCZ2D_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
     dim3 grid(segs, (g.nx + xchunk - 1) / xchunk);
     Hcz2dTables P;

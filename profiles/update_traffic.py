@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Extract dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from `ncu --set full`
 captures (gpurun_out/*.ncu-rep) into profiles/ncu_traffic.json, which bench.py quotes as roofline.traffic.
-usage: python profiles/update_traffic.py workload=report.ncu-rep[:kernel-regex] ..."""
+usage: python profiles/update_traffic.py workload=report.ncu-rep[:kernel-regex[:max-launches]] ..."""
 import csv, io, json, os, re, subprocess, sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -27,12 +27,16 @@ def main():
     table = json.load(open(OUT)) if os.path.exists(OUT) else {}
     for arg in sys.argv[1:]:
         wl, spec = arg.split("=", 1)
-        rep, _, rx = spec.partition(":")
+        rep, _, rest = spec.partition(":")
+        rx, _, mx = rest.partition(":")
+        mx = int(mx) if mx else 10 ** 9
         tot_r = tot_w = 0.0
         names, grid = [], None
         for d in rows_of(rep):
             if rx and not re.search(rx, d["Kernel Name"]):
                 continue
+            if len(names) >= mx:
+                break
             tot_r += val(d, "dram__bytes_read.sum")
             tot_w += val(d, "dram__bytes_write.sum")
             names.append(d["Kernel Name"].split("(")[0])
