@@ -84,6 +84,10 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
     constexpr int NS = HCZ2D_NS;
     __shared__ double r_phi[NS][NT], r_rho[NS][NT], r_pp[NS][NT], r_pr[NS][NT], r_lap[NS][NT];
     __shared__ uint8_t r_fl[NS][NT];
+    // the 9 g populations the collision of column x consumes are copied global -> shared one column ahead with cp.async
+    // (no registers, no stall at the point of use: long_scoreboard was the second stall reason); a thread only ever reads
+    // the slots it filled itself, so the copies need no barrier, only cp.async.wait_group
+    __shared__ double st_g[2][9][NT];     // g only: the second read of f hits L1/L2 (it was read two columns earlier for phi)
 
     const int tid = threadIdx.x;
     const int ny = g.ny, G = g.G;
@@ -150,8 +154,21 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
 
     const double omega = mp.omega, hw = 1. - 0.5 * omega;
     const int oym = (g.wy(yy - 1) - yy), oyp = (g.wy(yy + 1) - yy);
+    auto stage_pops = [&](int xg) {     // own row of column xg (always a real column of this slab) into slot xg & 1
+        if (own) {
+            const int i = (xg + G) * ny + yy;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&st_g[xg & 1][k][tid])), "l"(P.gin[k] + i) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage_pops(xa);
 
     for (int x = xa; x < xb; ++x) {
+        if (x + 1 < xb) stage_pops(x + 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per iteration so wait_group 1 means "column x is here"
         // 1. column x+2: phi from the prefetched populations (or the exchanged ghost field)
         if (has_phi) {
             if (ghost_n) { const int i = col_of(x + 2); put_phi(x + 2, phi_g[i], flag[i]); }
@@ -170,8 +187,9 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
 
         const int i = (x + G) * ny + yy;
         double f[9], gg[9];
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { gg[k] = P.gin[k][i]; f[k] = P.fin[k][i]; }
+        for (int k = 0; k < 9; ++k) { gg[k] = st_g[x & 1][k][tid]; f[k] = P.fin[k][i]; }
 
         unsigned wall = 0;
 #pragma unroll
@@ -290,9 +308,9 @@ int hcz2d_fused_launch(clbm_ctx *c)
     if (const char *e = getenv("CLBM_HCZ2D_TILE")) variant = atoi(e);
     switch (variant) {
     case 2: return launch_hcz2d_fused<64, 8>(c);
-    case 3: return launch_hcz2d_fused<192, 2>(c);
-    case 4: return launch_hcz2d_fused<128, 4>(c);
-    default: return launch_hcz2d_fused<128, 3>(c);   // 168 registers, no spills: best of the sweep at 2048 x 8194
+    case 3: return launch_hcz2d_fused<96, 4>(c);
+    case 4: return launch_hcz2d_fused<128, 3>(c);
+    default: return launch_hcz2d_fused<128, 4>(c);   // 128 registers, 16 warps per SM: best of the sweep at 2048 x 8194 with the cp.async staging
     }
 }
 
