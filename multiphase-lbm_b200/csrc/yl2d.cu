@@ -18,6 +18,7 @@
 // far from the interface) by ~100x per 50 iterations until they saturate near 1e-5, so no FMA-contracted build can
 // hold 1e-10 for 1000 iterations (measured).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -83,15 +84,11 @@ __device__ __forceinline__ void viscous_force(const Par &p, double dcdx, double 
 // what update_fields (AB:297-370) leaves at one node
 struct Node { double C, Rho, P, Ux, Uy, dCx, dCy, mu, ni, nj, den, rden; };   // den = Rho + 1e-30, rden = RN(1 / den)
 
-// update_fields at node (X, Y) from phi (3x3, periodic), the g populations of the node and the previous velocity
-__device__ __forceinline__ void update_node(const Par &p, const Geo &g, const double *__restrict__ C, int X, int Y, const double gin[9],
-                                            double Uo, double Vo, bool keep_u, Node &n)
+// update_fields (AB:297-370) at one node from the 3x3 neighbourhood of phi, the g populations of the node and the previous velocity
+__device__ __forceinline__ void node_from_stencil(const Par &p, double cC, double cE, double cW, double cN, double cS, double cNE,
+                                                  double cNW, double cSE, double cSW, const double gin[9], double Uo, double Vo,
+                                                  bool keep_u, Node &n)
 {
-    const int xm = X == 0 ? g.nx - 1 : X - 1, xp = X == g.nx - 1 ? 0 : X + 1;
-    const int ym = Y == 0 ? g.ny - 1 : Y - 1, yp = Y == g.ny - 1 ? 0 : Y + 1;
-    auto at = [&](int x, int y) { return C[y + (long long)g.ny * x]; };
-    const double cC = at(X, Y), cE = at(xp, Y), cW = at(xm, Y), cN = at(X, yp), cS = at(X, ym);
-    const double cNE = at(xp, yp), cNW = at(xm, yp), cSE = at(xp, ym), cSW = at(xm, ym);
     n.C = cC;
     n.Rho = p.Rhol + cC * (p.Rhoh - p.Rhol);
     n.dCx = divc<3>(cE - cW) + divc<12>(cSE + cNE - cSW - cNW);
@@ -123,6 +120,46 @@ __device__ __forceinline__ void update_node(const Par &p, const Geo &g, const do
     n.Uy = my + divr(0.5 * Fy, n.den, n.rden);
 }
 
+__device__ __forceinline__ void update_node(const Par &p, const Geo &g, const double *__restrict__ C, int X, int Y, const double gin[9],
+                                            double Uo, double Vo, bool keep_u, Node &n)
+{
+    const int xm = X == 0 ? g.nx - 1 : X - 1, xp = X == g.nx - 1 ? 0 : X + 1;
+    const int ym = Y == 0 ? g.ny - 1 : Y - 1, yp = Y == g.ny - 1 ? 0 : Y + 1;
+    auto at = [&](int x, int y) { return C[y + (long long)g.ny * x]; };
+    node_from_stencil(p, at(X, Y), at(xp, Y), at(xm, Y), at(X, yp), at(X, ym), at(xp, yp), at(xm, yp), at(xp, ym), at(xm, ym), gin, Uo, Vo,
+                      keep_u, n);
+}
+
+// collide_stream_at (AB:217-290) of one node whose fields are in n
+__device__ __forceinline__ void collide_push(const Par &p, const Geo &g, int X, int Y, long long i, const Node &n, const double hk[9],
+                                             const double gin[9], double *__restrict__ hout, double *__restrict__ gout)
+{
+    double GaWa[9];
+    gawa(n.Ux, n.Uy, GaWa);
+    const double shape = divr(1.0 - 4.0 * (n.C - 0.5) * (n.C - 0.5), p.W, p.rW);
+    const double FpX = -n.P * p.dRho3 * n.dCx, FpY = -n.P * p.dRho3 * n.dCy;
+    double gneq[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gneq[k] = gin[k] - (n.P * tk(k) + GaWa[k]);
+    double FmX, FmY;
+    viscous_force(p, n.dCx, n.dCy, gneq, FmX, FmY);
+    const double Fx = n.mu * n.dCx + FpX + FmX, Fy = n.mu * n.dCy + FpY + FmY;
+    const int xm = X == 0 ? g.nx - 1 : X - 1, xp = X == g.nx - 1 ? 0 : X + 1;
+    const int ym = Y == 0 ? g.ny - 1 : Y - 1, yp = Y == g.ny - 1 ? 0 : Y + 1;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double hlp_h = tk(k) * (shape * (ckx(k) * n.ni + cky(k) * n.nj));
+        const double heq = n.C * (tk(k) + GaWa[k]) - 0.5 * hlp_h;
+        const double hlp_g = divr(3.0 * tk(k) * (ckx(k) * Fx + cky(k) * Fy), n.den, n.rden);
+        const double geq = (n.P * tk(k) + GaWa[k]) - 0.5 * hlp_g;
+        const double ho = (1.0 - p.wc) * hk[k] + p.wc * heq + hlp_h;
+        const double go = (1.0 - p.s8) * gin[k] + p.s8 * geq + hlp_g;
+        const long long nb = (ckx(k) < 0 ? xm : (ckx(k) > 0 ? xp : X)) * (long long)g.ny + (cky(k) < 0 ? ym : (cky(k) > 0 ? yp : Y));
+        hout[k * g.ne + nb] = ho;
+        gout[k * g.ne + nb] = go;
+    }
+}
+
 __global__ void __launch_bounds__(256) yl2d_phi(const double *__restrict__ hin, double *__restrict__ C, Geo g)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,30 +185,68 @@ __global__ void __launch_bounds__(256) yl2d_step(const double *__restrict__ hin,
     update_node(p, g, C, X, Y, gin, Ux[i], Uy[i], keep_u != 0, n);
     Ux[i] = n.Ux;
     Uy[i] = n.Uy;
+    collide_push(p, g, X, Y, i, n, hk, gin, hout, gout);
+}
 
-    double GaWa[9];
-    gawa(n.Ux, n.Uy, GaWa);
-    const double shape = divr(1.0 - 4.0 * (n.C - 0.5) * (n.C - 0.5), p.W, p.rW);
-    const double FpX = -n.P * p.dRho3 * n.dCx, FpY = -n.P * p.dRho3 * n.dCy;
-    double gneq[9];
+// Fused form of yl2d_phi + yl2d_step: a CTA owns NT-2 consecutive rows and marches along x with a 3-column shared-memory
+// ring of phi; the h populations are loaded once (two columns ahead, in registers) and serve both phi and the collision
+// one column later, so the separate phi pass (9 reads + 1 write per node) disappears.  Arithmetic is yl2d_step's, operation
+// for operation (same update_node / collision code), hence still bit-identical to the reference.
+template <int NT>
+__global__ void __launch_bounds__(NT) yl2d_fused(const double *__restrict__ hin, double *__restrict__ hout, const double *__restrict__ gin_,
+                                                 double *__restrict__ gout, double *__restrict__ Ux, double *__restrict__ Uy, Geo g, Par p,
+                                                 int keep_u, int xchunk)
+{
+    __shared__ double Cr[3][NT];
+    const int tid = threadIdx.x;
+    const int Yraw = (int)blockIdx.x * (NT - 2) - 1 + tid;
+    const bool row_ok = Yraw >= -1 && Yraw <= g.ny;                      // rows -1 and ny are the periodic images
+    const int Y = Yraw < 0 ? Yraw + g.ny : (Yraw >= g.ny ? Yraw - g.ny : Yraw);
+    const bool own = tid >= 1 && tid < NT - 1 && Yraw < g.ny;
+    const int xa = blockIdx.y * xchunk, xb = min(g.nx, xa + xchunk);
+    auto wrapx = [&](int X) { return X < 0 ? X + g.nx : (X >= g.nx ? X - g.nx : X); };
+    auto load_h = [&](int X, double h[9]) {
+        if (!row_ok) return;
+        const long long i = Y + (long long)g.ny * wrapx(X);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) gneq[k] = gin[k] - (n.P * tk(k) + GaWa[k]);
-    double FmX, FmY;
-    viscous_force(p, n.dCx, n.dCy, gneq, FmX, FmY);
-    const double Fx = n.mu * n.dCx + FpX + FmX, Fy = n.mu * n.dCy + FpY + FmY;
-    const int xm = X == 0 ? g.nx - 1 : X - 1, xp = X == g.nx - 1 ? 0 : X + 1;
-    const int ym = Y == 0 ? g.ny - 1 : Y - 1, yp = Y == g.ny - 1 ? 0 : Y + 1;
+        for (int k = 0; k < 9; ++k) h[k] = hin[k * g.ne + i];
+    };
+    auto put_phi = [&](int X, const double h[9]) {
+        double phi = 0.0;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const double hlp_h = tk(k) * (shape * (ckx(k) * n.ni + cky(k) * n.nj));
-        const double heq = n.C * (tk(k) + GaWa[k]) - 0.5 * hlp_h;
-        const double hlp_g = divr(3.0 * tk(k) * (ckx(k) * Fx + cky(k) * Fy), n.den, n.rden);
-        const double geq = (n.P * tk(k) + GaWa[k]) - 0.5 * hlp_g;
-        const double ho = (1.0 - p.wc) * hk[k] + p.wc * heq + hlp_h;
-        const double go = (1.0 - p.s8) * gin[k] + p.s8 * geq + hlp_g;
-        const long long nb = (ckx(k) < 0 ? xm : (ckx(k) > 0 ? xp : X)) * (long long)g.ny + (cky(k) < 0 ? ym : (cky(k) > 0 ? yp : Y));
-        hout[k * g.ne + nb] = ho;
-        gout[k * g.ne + nb] = go;
+        for (int k = 0; k < 9; ++k) phi += h[k];
+        Cr[(X + 3) % 3][tid] = phi;
+    };
+    double hc[9], hn[9], hp[9];          // columns X, X+1, X+2 (prefetch)
+    load_h(xa - 1, hp);
+    put_phi(xa - 1, hp);
+    load_h(xa, hc);
+    put_phi(xa, hc);
+    load_h(xa + 1, hn);
+    for (int X = xa; X < xb; ++X) {
+        if (X + 1 < xb) load_h(X + 2, hp);          // in flight while this column is processed
+        put_phi(X + 1, hn);
+        __syncthreads();
+        if (own) {
+            const long long i = Y + (long long)g.ny * X;
+            double gin[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) gin[k] = gin_[k * g.ne + i];
+            // update_fields at this node with phi from the ring (same expressions as update_node)
+            const int sm = (X + 2) % 3, s0 = X % 3, sp = (X + 1) % 3;
+            Node n;
+            {
+                const double cC = Cr[s0][tid], cE = Cr[sp][tid], cW = Cr[sm][tid], cN = Cr[s0][tid + 1], cS = Cr[s0][tid - 1];
+                const double cNE = Cr[sp][tid + 1], cNW = Cr[sm][tid + 1], cSE = Cr[sp][tid - 1], cSW = Cr[sm][tid - 1];
+                node_from_stencil(p, cC, cE, cW, cN, cS, cNE, cNW, cSE, cSW, gin, Ux[i], Uy[i], keep_u != 0, n);
+            }
+            Ux[i] = n.Ux;
+            Uy[i] = n.Uy;
+            collide_push(p, g, X, Y, i, n, hc, gin, hout, gout);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { hc[k] = hn[k]; hn[k] = hp[k]; }
+        __syncthreads();
     }
 }
 
@@ -269,12 +344,22 @@ double *g_out(clbm_yl2d *c) { return c->lat + (size_t)18 * c->g.ne + (size_t)(1 
 
 int one_step(clbm_yl2d *c)
 {
-    const int nb = grid_for(c->g.ne, 256);
-    yl2d_phi<<<nb, 256, 0, c->stream>>>(h_in(c), c->C, c->g);
-    yl2d_step<<<nb, 256, 0, c->stream>>>(h_in(c), h_out(c), g_in(c), g_out(c), c->C, c->Ux, c->Uy, c->g, c->p, c->keep_u);
+    static const int fused = getenv("CLBM_YL2D_FUSED") ? atoi(getenv("CLBM_YL2D_FUSED")) : 1;
+    if (fused && c->g.ny >= 3) {
+        constexpr int NT = 128;
+        int xchunk = c->g.nx < 32 ? c->g.nx : 32;
+        if (const char *e = getenv("CLBM_YL2D_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < c->g.nx ? v : c->g.nx; }
+        dim3 grid((c->g.ny + (NT - 2) - 1) / (NT - 2), (c->g.nx + xchunk - 1) / xchunk);
+        yl2d_fused<NT><<<grid, NT, 0, c->stream>>>(h_in(c), h_out(c), g_in(c), g_out(c), c->Ux, c->Uy, c->g, c->p, c->keep_u, xchunk);
+        c->launches += 1;
+    } else {
+        const int nb = grid_for(c->g.ne, 256);
+        yl2d_phi<<<nb, 256, 0, c->stream>>>(h_in(c), c->C, c->g);
+        yl2d_step<<<nb, 256, 0, c->stream>>>(h_in(c), h_out(c), g_in(c), g_out(c), c->C, c->Ux, c->Uy, c->g, c->p, c->keep_u);
+        c->launches += 2;
+    }
     c->keep_u = 0;
     c->parity = 1 - c->parity;
-    c->launches += 2;
     c->steps++;
     CLBM_CUDA(cudaGetLastError());
     return CLBM_OK;
