@@ -99,3 +99,23 @@ def test_overlap_protocol_is_bit_identical(nranks):
             lat.close()
     np.testing.assert_array_equal(out[False], ref)
     np.testing.assert_array_equal(out[True], ref)
+
+
+def test_full_plane_slabs_match_single_slab():
+    """four slabs of 8 planes at the production plane size 512 x 512 (real tile grid, TMA boxes, 24-plane chunk logic) against
+    the single 32 x 512 x 512 slab, bit for bit, with the overlap protocol"""
+    prm = P.sc_params(P.MODEL_SC_D3Q19, 32, 512, 512, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    args = (0.265, 0.038, 12.0, 5.0)
+    with pkg.clbm.Lattice(prm) as single:
+        single.init_case(P.CASE_SC_DROPLET3D, args)
+        single.step(6)
+        ref = single.in_pops()
+    lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, 4)) for r in range(4)]
+    for lat in lats:
+        lat.init_case(P.CASE_SC_DROPLET3D, args)
+    ring = slab.LocalRing(lats)
+    ring.step(6)
+    pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
+    for lat in lats:
+        lat.close()
+    np.testing.assert_array_equal(pops, ref)
