@@ -17,6 +17,7 @@
 // the instruction stream and no scalar field other than the five moments round-trips through HBM.
 // Traffic per node: 304 (moments pass) + ~45 (moment fields incl. halo re-reads, L2) + 608 (populations in/out).
 #include <cstdlib>
+#include <type_traits>
 
 #include "sc_cell.cuh"
 #include "tma.cuh"
@@ -104,7 +105,7 @@ struct Hcz3dLocal {
 };
 
 template <int TY, int TZ>
-__global__ void __launch_bounds__(TY *TZ, 1)
+__global__ void __launch_bounds__(TY *TZ, (TY * TZ <= 128) ? 2 : 1)
 hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_g, const Hcz3dOut P,
                    const Hcz3dMom M, const uint8_t *__restrict__ flag, Geom g, ModelParams mp, int xchunk)
 {
@@ -148,6 +149,8 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         else if (tid < 2 * C::Z1) { h1y = C::Y1 - 1; h1z = tid - C::Z1; }
         else { const int q = tid - 2 * C::Z1; h1y = 1 + (q >> 1); h1z = (q & 1) ? C::Z1 - 1 : 0; }
     }
+    const bool h_warp = (tid >> 5) <= ((C::NH1 - 1) >> 5);
+    if (h_warp && !h_act) { h1y = ty + 1; h1z = tz + 1; }
     const int h1_yz = wrap(y0 + h1y - 1, ny) * nz + wrap(z0 + h1z - 1, nz);
 
     if (tid == 0) {
@@ -180,23 +183,22 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     auto load_mom = [&](int xg) {
         const int base = xs_of(xg) * plane;
         mo_n[0] = M.pt[base + yz_w]; mo_n[1] = M.jx[base + yz_w]; mo_n[2] = M.jy[base + yz_w]; mo_n[3] = M.jz[base + yz_w];
-        if (h_act) { mh_n[0] = M.pt[base + h1_yz]; mh_n[1] = M.jx[base + h1_yz]; mh_n[2] = M.jy[base + h1_yz]; mh_n[3] = M.jz[base + h1_yz]; }
+        if (h_warp) { mh_n[0] = M.pt[base + h1_yz]; mh_n[1] = M.jx[base + h1_yz]; mh_n[2] = M.jy[base + h1_yz]; mh_n[3] = M.jz[base + h1_yz]; }
     };
 
     // level 2 of the node at halo-1 position (a1, b1) of plane p; stores psi_rho, returns the node's local set
-    auto level2 = [&](int p, int a1, int b1, const double *mo, Hcz3dLocal &o, bool walls) {
+    auto level2 = [&](auto wtag, int p, int a1, int b1, const double *mo, Hcz3dLocal &o) -> double {
+        constexpr bool W = decltype(wtag)::value;
         const int q3 = (a1 + 2) * C::Z3 + (b1 + 2), q2 = (a1 + 1) * C::Z2 + (b1 + 1);
         const int sm = ((p - 1) & 3) * C::R2, s0 = (p & 3) * C::R2, sp = ((p + 1) & 3) * C::R2;
         double gl[3];
-        if (walls) {
+        unsigned wall = 0;
+        if constexpr (W) {
             const uint8_t *Fm = r_fl + ((p - 1) & 7) * C::R3, *F0 = r_fl + (p & 7) * C::R3, *Fp = r_fl + ((p + 1) & 7) * C::R3;
-            const unsigned wall = wall19<C::Z3>(Fm, F0, Fp, q3);
-            grad19<C::Z2, true>(r_lap + sm, r_lap + s0, r_lap + sp, q2, wall, gl);
-            grad19<C::Z2, true>(r_pp + sm, r_pp + s0, r_pp + sp, q2, wall, o.gp);
-        } else {
-            grad19<C::Z2, false>(r_lap + sm, r_lap + s0, r_lap + sp, q2, 0u, gl);
-            grad19<C::Z2, false>(r_pp + sm, r_pp + s0, r_pp + sp, q2, 0u, o.gp);
+            wall = wall19<C::Z3>(Fm, F0, Fp, q3);
         }
+        grad19<C::Z2, W>(r_lap + sm, r_lap + s0, r_lap + sp, q2, wall, gl);
+        grad19<C::Z2, W>(r_pp + sm, r_pp + s0, r_pp + sp, q2, wall, o.gp);
         o.phi = r_phi[(p & 3) * C::R3 + q3];
         o.rho = mp.rho_g + ((o.phi - mp.phi_g) * mp.inv_dphi) * mp.drho;
         o.Fx = mp.kappa * o.phi * gl[0];
@@ -207,7 +209,8 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         o.u1 = (mo[2] + o.Fy * (1. / 6.)) * inv_d;
         o.u2 = (mo[3] + o.Fy * (1. / 6.)) * inv_d;   // sic: forcey (laplace3D.h:304)
         o.Pt = mo[0] - 0.5 * (o.u0 * o.gp[0] + o.u1 * o.gp[1] + o.u2 * o.gp[2]);
-        r_pr[(p & 3) * (C::Y1 * C::Z1) + a1 * C::Z1 + b1] = o.Pt - o.rho * (1. / 3.);
+        return o.Pt - o.rho * (1. / 3.);   // psi_rho; the caller stores it (after all its evaluations: the loads of one
+                                           // evaluation must not wait behind the store of the previous one)
     };
 
     const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
@@ -229,6 +232,74 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         c2_q3[j] = (a2 + 1) * C::Z3 + (b2 + 1);
     }
     unsigned wmask = 0;   // bit (p & 7): plane p has a bounce_back node inside this CTA's window (CTA-uniform)
+
+    // S4 of the own node: grad psi_rho, the 2 x 19 collisions, push.  Two instantiations: with walls in reach the
+    // destination of every population is selected without a branch (bounce-back: opposite slot of the own node), the
+    // wall-free one has no mask work at all; straight-line code in both, so the scheduler can overlap the FP64
+    // chains of neighbouring directions (8 warps per SM: latency has to be hidden inside the thread)
+    auto collide = [&](auto wtag, int x, const double *sf, const uint8_t *Fm, const uint8_t *F0, const uint8_t *Fp) {
+        constexpr bool W = decltype(wtag)::value;
+        constexpr int R1 = C::Y1 * C::Z1;
+        const int q1 = (ty + 1) * C::Z1 + tz + 1;
+        unsigned wall = 0;
+        double ge[3];
+        if constexpr (W) wall = wall19<C::Z3>(Fm, F0, Fp, (ty + 3) * C::Z3 + tz + 3);
+        grad19<C::Z1, W>(r_pr + ((x - 1) & 3) * R1, r_pr + (x & 3) * R1, r_pr + ((x + 1) & 3) * R1, q1, wall, ge);
+
+        const double phi = cur.phi, rho = cur.rho;
+        const double u0 = cur.u0, u1 = cur.u1, u2 = cur.u2, Pt = cur.Pt;
+        const double usqr = 1.5 * (u0 * u0 + u1 * u1 + u2 * u2);
+        // The two forcing terms, regrouped around Gamma_k = eqf_k / phi = t_k (1 + poly_k):
+        //   fg_k = hw [ (c_k - u).F Gamma_k + (c_k - u).(-E) (Gamma_k - t_k) ] = Gamma_k (c_k - u).D + t_k (c_k - u).Eh
+        //   ff_k = hw (c_k - u).(-grad psi(phi)) 3 eqf_k / rho                 = Gamma_k (c_k - u).Gv
+        // with the per-node vectors D = hw (F - E), Eh = hw E, Gv = -(3 hw phi / rho) grad psi(phi)
+        const double ffs = -hw * 3.0 * phi * fast_rcp(rho);
+        const double D0 = hw * (cur.Fx - ge[0]), D1 = hw * (cur.Fy - ge[1]), D2 = hw * (cur.Fz - ge[2]);
+        const double E0 = hw * ge[0], E1 = hw * ge[1], E2 = hw * ge[2];
+        const double G0 = ffs * cur.gp[0], G1 = ffs * cur.gp[1], G2 = ffs * cur.gp[2];
+        const double uD = u0 * D0 + u1 * D1 + u2 * D2;
+        const double uE = u0 * E0 + u1 * E1 + u2 * E2;
+        const double opg = omega * phi - (u0 * G0 + u1 * G1 + u2 * G2);   // omega phi - u.Gv
+        const double rho3 = rho * (1. / 3.);
+        const int xp = g.wx(x + 1), xm = g.wx(x - 1);
+        const int i = (x + G) * plane + yz;
+        const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
+#pragma unroll
+        for (int k = 0; k < 19; ++k) {
+            const double fk = sf[k * NT];
+            const double gk = sf[(19 + k) * NT];
+            const double t = L19f::t(k);
+            double pf, pg;
+            if (k == 9) {
+                const double Gam = t * (1. - usqr);                   // eqf0 / phi
+                pf = om1 * fk + Gam * opg;
+                pg = om1 * gk + (omega * t) * (Pt - rho3 * usqr) - (Gam * uD + t * uE);
+                P.fout[k][i] = pf;
+                P.gout[k][i] = pg;
+                continue;
+            }
+            const double cu = L19f::cx(k) * u0 + L19f::cy(k) * u1 + L19f::cz(k) * u2;
+            const double poly = 3. * cu + 4.5 * cu * cu - usqr;
+            const double Gam = t * (1. + poly);                       // eqf / phi
+            const double cD = L19f::cx(k) * D0 + L19f::cy(k) * D1 + L19f::cz(k) * D2;
+            const double cE = L19f::cx(k) * E0 + L19f::cy(k) * E1 + L19f::cz(k) * E2;
+            const double cG = L19f::cx(k) * G0 + L19f::cy(k) * G1 + L19f::cz(k) * G2;
+            pf = om1 * fk + Gam * (opg + cG);
+            pg = om1 * gk + (omega * t) * (Pt + rho3 * poly) + (Gam * (cD - uD) + t * (cE - uE));
+            const int off = (L19f::cx(k) < 0 ? oxm : (L19f::cx(k) > 0 ? oxp : 0)) + (L19f::cy(k) < 0 ? oym : (L19f::cy(k) > 0 ? oyp : 0)) +
+                            (L19f::cz(k) < 0 ? ozm : (L19f::cz(k) > 0 ? ozp : 0));
+            if constexpr (W) {
+                const bool bb = (wall >> k) & 1u;
+                double *df = bb ? P.fout[L19f::opp(k)] + i : P.fout[k] + (i + off);
+                double *dg = bb ? P.gout[L19f::opp(k)] + i : P.gout[k] + (i + off);
+                *df = pf;
+                *dg = pg;
+            } else {
+                P.fout[k][i + off] = pf;
+                P.gout[k][i + off] = pg;
+            }
+        }
+    };
 
     load_phi(xa - 3);
     // x = plane being collided; the first six iterations only fill the pipeline (x < xa)
@@ -299,8 +370,21 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         // ---- S3: level 2 of plane x+1 on tile + halo 1 ----
         if (x + 1 >= xa - 1) {
             const bool walls = walls_near(x + 1);
-            level2(x + 1, ty + 1, tz + 1, mo_c, nxt, walls);   // also the periodic images in a ragged edge tile
-            if (h_act) { Hcz3dLocal tmp; level2(x + 1, h1y, h1z, mh_c, tmp, walls); }
+            // the halo-1 ring belongs to the first warps; they evaluate both nodes in one basic block so that the two
+            // independent dependency chains overlap (lanes past the ring repeat their own node, the stores coincide)
+            auto s3 = [&](auto wtag) {
+                double *pr = r_pr + ((x + 1) & 3) * (C::Y1 * C::Z1);
+                if (h_warp) {
+                    Hcz3dLocal tmp;
+                    const double a = level2(wtag, x + 1, ty + 1, tz + 1, mo_c, nxt);
+                    const double b = level2(wtag, x + 1, h1y, h1z, mh_c, tmp);
+                    pr[(ty + 1) * C::Z1 + tz + 1] = a;
+                    pr[h1y * C::Z1 + h1z] = b;
+                } else {
+                    pr[(ty + 1) * C::Z1 + tz + 1] = level2(wtag, x + 1, ty + 1, tz + 1, mo_c, nxt);   // also the periodic images in a ragged edge tile
+                }
+            };
+            if (walls) s3(std::true_type{}); else s3(std::false_type{});
         }
         __syncthreads();
 
@@ -310,63 +394,9 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             mbar_wait(&mbar[r & 1], (r >> 1) & 1);
             const uint8_t *Fm = r_fl + ((x - 1) & 7) * C::R3, *F0 = r_fl + (x & 7) * C::R3, *Fp = r_fl + ((x + 1) & 7) * C::R3;
             if (inside && F0[(ty + 3) * C::Z3 + tz + 3] == CELL_BULK) {
-                constexpr int R1 = C::Y1 * C::Z1;
-                const int q1 = (ty + 1) * C::Z1 + tz + 1;
-                unsigned wall = 0;
-                double ge[3];
-                if (walls_near(x)) {
-                    wall = wall19<C::Z3>(Fm, F0, Fp, (ty + 3) * C::Z3 + tz + 3);
-                    grad19<C::Z1, true>(r_pr + ((x - 1) & 3) * R1, r_pr + (x & 3) * R1, r_pr + ((x + 1) & 3) * R1, q1, wall, ge);
-                } else {
-                    grad19<C::Z1, false>(r_pr + ((x - 1) & 3) * R1, r_pr + (x & 3) * R1, r_pr + ((x + 1) & 3) * R1, q1, 0u, ge);
-                }
-
-                const double phi = cur.phi, rho = cur.rho, Fx = cur.Fx, Fy = cur.Fy, Fz = cur.Fz;
-                const double u0 = cur.u0, u1 = cur.u1, u2 = cur.u2, Pt = cur.Pt;
-                const double usqr = 1.5 * (u0 * u0 + u1 * u1 + u2 * u2);
-                // (e_k - u).V = c_k.V - u.V for the three forcing vectors V = F, -E, -grad psi(phi)
-                const double uF = u0 * Fx + u1 * Fy + u2 * Fz;
-                const double uE = u0 * ge[0] + u1 * ge[1] + u2 * ge[2];
-                const double uG = u0 * cur.gp[0] + u1 * cur.gp[1] + u2 * cur.gp[2];
-                const double rho3 = rho * (1. / 3.);
-                const double ffs = hw * 3.0 * phi * fast_rcp(rho);   // ff = hw * C * 3 * eqf / rho,  eqf = phi * Gamma
-                const int xp = g.wx(x + 1), xm = g.wx(x - 1);
-                const int i = (x + G) * plane + yz;
-                const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
-                const uint32_t st = stage_a + (r & 1) * C::STAGE_BYTES + tid * 8;
-#pragma unroll
-                for (int k = 0; k < 19; ++k) {
-                    const double fk = lds_f64(st + k * (NT * 8));
-                    const double gk = lds_f64(st + C::SET_BYTES + k * (NT * 8));
-                    const double t = L19f::t(k);
-                    double pf, pg;
-                    if (k == 9) {
-                        const double Gam = t * (1. - usqr);                   // eqf0 / phi
-                        const double eqg0 = t * (Pt - rho3 * usqr);
-                        const double fg0 = hw * (-uF * Gam + uE * (Gam - t));
-                        const double ff0 = ffs * uG * Gam;
-                        pf = om1 * fk + omega * phi * Gam + ff0;
-                        pg = om1 * gk + omega * eqg0 + fg0;
-                        P.fout[k][i] = pf;
-                        P.gout[k][i] = pg;
-                        continue;
-                    }
-                    const double cu = L19f::cx(k) * u0 + L19f::cy(k) * u1 + L19f::cz(k) * u2;
-                    const double poly = 3. * cu + 4.5 * cu * cu - usqr;
-                    const double Gam = t * (1. + poly);                       // eqf / phi
-                    const double eqg = t * (Pt + rho3 * poly);
-                    const double cF = L19f::cx(k) * Fx + L19f::cy(k) * Fy + L19f::cz(k) * Fz;
-                    const double cE = L19f::cx(k) * ge[0] + L19f::cy(k) * ge[1] + L19f::cz(k) * ge[2];
-                    const double cG = L19f::cx(k) * cur.gp[0] + L19f::cy(k) * cur.gp[1] + L19f::cz(k) * cur.gp[2];
-                    const double fg = hw * ((cF - uF) * Gam - (cE - uE) * (Gam - t));
-                    const double ff = -ffs * (cG - uG) * Gam;
-                    pf = om1 * fk + omega * phi * Gam + ff;
-                    pg = om1 * gk + omega * eqg + fg;
-                    const int off = (L19f::cx(k) < 0 ? oxm : (L19f::cx(k) > 0 ? oxp : 0)) + (L19f::cy(k) < 0 ? oym : (L19f::cy(k) > 0 ? oyp : 0)) +
-                                    (L19f::cz(k) < 0 ? ozm : (L19f::cz(k) > 0 ? ozp : 0));
-                    if (wall & (1u << k)) { P.fout[L19f::opp(k)][i] = pf; P.gout[L19f::opp(k)][i] = pg; }
-                    else { P.fout[k][i + off] = pf; P.gout[k][i + off] = pg; }
-                }
+                const double *sf = reinterpret_cast<const double *>(smem_raw + (r & 1) * C::STAGE_BYTES) + tid;
+                if (walls_near(x)) collide(std::true_type{}, x, sf, Fm, F0, Fp);
+                else collide(std::false_type{}, x, sf, Fm, F0, Fp);
             }
         }
         cur = nxt;
@@ -429,6 +459,7 @@ int hcz3d_fused_launch(clbm_ctx *c, int variant)
     switch (variant) {
     case 8: return launch_hcz3d_fused<16, 16>(c);
     case 9: return launch_hcz3d_fused<4, 64>(c);
+    case 10: return launch_hcz3d_fused<8, 16>(c);   // two 128-thread CTAs per SM
     default: return launch_hcz3d_fused<8, 32>(c);
     }
 }
