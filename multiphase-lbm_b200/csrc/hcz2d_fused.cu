@@ -222,8 +222,22 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         // eqf / phi = t_k (1 + poly) =: Gamma, so neither eqf nor 1/phi is formed; opposite directions share c.u, c.F, c.E,
         // c.G up to the sign and are collided in pairs (even part once, odd part added / subtracted).
         // Forcing vectors as the reference writes them: F (forcex, forcey), -E (grad psi(rho)), -grad psi(phi).
+        // The two forcing terms regrouped around Gamma_k (reference form: fg = hw [ (e-u).F Gam + (e-u).(-E) (Gam - t) ],
+        // ff = hw (e-u).(-grad psi(phi)) 3 Gam):
+        //   fg_k = Gamma_k (c_k - u).D + t_k (c_k - u).Eh,   ff_k = Gamma_k (c_k - u).Gv
+        // with the per-node vectors D = hw (F - E), Eh = hw E, Gv = -3 hw grad psi(phi); everything is written as explicit
+        // FMAs (the kernel is FP64-issue bound and the compiler does not re-associate)
         const double uF = u0 * forcex + u1 * forcey, uE = u0 * Ex + u1 * Ey, uG = u0 * gpx + u1 * gpy;
         const double om1 = 1. - omega, op = omega * phi, hw3 = 3.0 * hw;
+        const double D0 = hw * (forcex - Ex), D1 = hw * (forcey - Ey);
+        const double E0 = hw * Ex, E1 = hw * Ey;
+        const double G0 = -hw3 * gpx, G1 = -hw3 * gpy;
+        const double uD = u0 * D0 + u1 * D1, uEh = u0 * E0 + u1 * E1;
+        const double opg = op - (u0 * G0 + u1 * G1);                   // omega phi - u.Gv
+        const double orho3 = omega * rho3;
+        // omega t_k (Pp + rho/3 ev_k) = A + B ev_k with one (A, B) pair per weight class
+        const double Aa = (omega * (1. / 9.)) * Pp, Ba = (omega * (1. / 9.)) * rho3;
+        const double Ad = (omega * (1. / 36.)) * Pp, Bd = (omega * (1. / 36.)) * rho3;
         auto push = [&](int k, double pf, double pg) {
             if (wall & (1u << k)) {
                 P.fout[L9f::opp(k)][i] = pf;
@@ -253,23 +267,24 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            // opposite directions share c.u, c.D, c.Eh, c.Gv up to the sign and are collided in pairs
             const int ko = L9f::opp(k);
             const double t = L9f::t(k);
-            const double cu = L9f::cx(k) * u0 + L9f::cy(k) * u1;
-            const double cF = L9f::cx(k) * forcex + L9f::cy(k) * forcey;
-            const double cE = L9f::cx(k) * Ex + L9f::cy(k) * Ey;
-            const double cG = L9f::cx(k) * gpx + L9f::cy(k) * gpy;
-            const double ev = 4.5 * cu * cu - usqr, od = 3. * cu;
-            const double Ge = t * (1. + ev), Go = t * od;
-            const double qe = t * (Pp + rho3 * ev), qo = rho3 * Go;
+            const bool axis = (L9f::cx(k) != 0) + (L9f::cy(k) != 0) == 1;
+            const double cu = cdot<L9f>(k, u0, u1, 0.0);
+            const double cD = cdot<L9f>(k, D0, D1, 0.0);
+            const double cE = cdot<L9f>(k, E0, E1, 0.0);
+            const double cG = cdot<L9f>(k, G0, G1, 0.0);
+            const double ev = fma(4.5 * cu, cu, -usqr);
+            const double Ge = fma(t, ev, t), Go = (3. * t) * cu;
             const double Gp = Ge + Go, Gm = Ge - Go;
-            // fg = hw [ (e-u).F Gam + (e-u).(-E) (Gam - t) ],  ff = hw (e-u).(-grad psi(phi)) 3 Gam
-            const double fgp = hw * ((cF - uF) * Gp - (cE - uE) * (Gp - t));
-            const double fgm = hw * ((-cF - uF) * Gm + (cE + uE) * (Gm - t));
-            const double ffp = -hw3 * (cG - uG) * Gp;
-            const double ffm = hw3 * (cG + uG) * Gm;
-            push(k, om1 * f[k] + op * Gp + ffp, om1 * gg[k] + omega * (qe + qo) + fgp);
-            push(ko, om1 * f[ko] + op * Gm + ffm, om1 * gg[ko] + omega * (qe - qo) + fgm);
+            const double we = fma(axis ? Ba : Bd, ev, axis ? Aa : Ad), wo = orho3 * Go;
+            const double pfp = fma(Gp, opg + cG, om1 * f[k]);
+            const double pfm = fma(Gm, opg - cG, om1 * f[ko]);
+            const double pgp = fma(t, cE - uEh, fma(Gp, cD - uD, fma(om1, gg[k], we + wo)));
+            const double pgm = fma(t, -cE - uEh, fma(Gm, -cD - uD, fma(om1, gg[ko], we - wo)));
+            push(k, pfp, pgp);
+            push(ko, pfm, pgm);
         }
     }
 }

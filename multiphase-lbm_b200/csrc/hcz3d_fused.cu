@@ -261,6 +261,9 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         const double uE = u0 * E0 + u1 * E1 + u2 * E2;
         const double opg = omega * phi - (u0 * G0 + u1 * G1 + u2 * G2);   // omega phi - u.Gv
         const double rho3 = rho * (1. / 3.);
+        // omega t_k (Pt + rho/3 poly_k) = A + B poly_k with one (A, B) pair per weight class
+        const double Aa = (omega * (1. / 18.)) * Pt, Ba = (omega * (1. / 18.)) * rho3;
+        const double Ad = (omega * (1. / 36.)) * Pt, Bd = (omega * (1. / 36.)) * rho3;
         const int xp = g.wx(x + 1), xm = g.wx(x - 1);
         const int i = (x + G) * plane + yz;
         const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
@@ -271,21 +274,22 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             const double t = L19f::t(k);
             double pf, pg;
             if (k == 9) {
-                const double Gam = t * (1. - usqr);                   // eqf0 / phi
-                pf = om1 * fk + Gam * opg;
-                pg = om1 * gk + (omega * t) * (Pt - rho3 * usqr) - (Gam * uD + t * uE);
+                const double Gam = fma(-t, usqr, t);                  // eqf0 / phi = t (1 - usqr)
+                pf = fma(Gam, opg, om1 * fk);
+                pg = fma(om1, gk, (omega * t) * fma(-rho3, usqr, Pt)) - fma(Gam, uD, t * uE);
                 P.fout[k][i] = pf;
                 P.gout[k][i] = pg;
                 continue;
             }
-            const double cu = L19f::cx(k) * u0 + L19f::cy(k) * u1 + L19f::cz(k) * u2;
-            const double poly = 3. * cu + 4.5 * cu * cu - usqr;
-            const double Gam = t * (1. + poly);                       // eqf / phi
-            const double cD = L19f::cx(k) * D0 + L19f::cy(k) * D1 + L19f::cz(k) * D2;
-            const double cE = L19f::cx(k) * E0 + L19f::cy(k) * E1 + L19f::cz(k) * E2;
-            const double cG = L19f::cx(k) * G0 + L19f::cy(k) * G1 + L19f::cz(k) * G2;
-            pf = om1 * fk + Gam * (opg + cG);
-            pg = om1 * gk + (omega * t) * (Pt + rho3 * poly) + (Gam * (cD - uD) + t * (cE - uE));
+            const bool axis = (L19f::cx(k) != 0) + (L19f::cy(k) != 0) + (L19f::cz(k) != 0) == 1;
+            const double cu = cdot<L19f>(k, u0, u1, u2);
+            const double poly = fma(cu, fma(4.5, cu, 3.0), -usqr);    // 3 cu + 4.5 cu^2 - usqr
+            const double Gam = fma(t, poly, t);                       // eqf / phi = t (1 + poly)
+            const double dD = cdot<L19f>(k, D0, D1, D2) - uD;
+            const double dE = cdot<L19f>(k, E0, E1, E2) - uE;
+            const double dG = cdot<L19f>(k, G0, G1, G2) + opg;
+            pf = fma(Gam, dG, om1 * fk);
+            pg = fma(t, dE, fma(Gam, dD, fma(om1, gk, fma(axis ? Ba : Bd, poly, axis ? Aa : Ad))));
             const int off = (L19f::cx(k) < 0 ? oxm : (L19f::cx(k) > 0 ? oxp : 0)) + (L19f::cy(k) < 0 ? oym : (L19f::cy(k) > 0 ? oyp : 0)) +
                             (L19f::cz(k) < 0 ? ozm : (L19f::cz(k) > 0 ? ozp : 0));
             if constexpr (W) {

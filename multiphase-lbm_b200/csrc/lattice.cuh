@@ -85,6 +85,19 @@ struct Geom {
     }
 };
 
+// c_k . a without multiplications and without the zero components: 0 * a cannot be folded under IEEE rules, so the plain
+// c_x a_0 + c_y a_1 + c_z a_2 costs three FP64 operations whatever c_k is; k is a constant after unrolling
+template <class L>
+CLBM_HD double cdot(int k, double a0, double a1, double a2)
+{
+    double s = 0.0;
+    bool have = false;
+    if (L::cx(k) != 0) { s = L::cx(k) > 0 ? a0 : -a0; have = true; }
+    if (L::cy(k) != 0) { const double v = L::cy(k) > 0 ? a1 : -a1; s = have ? s + v : v; have = true; }
+    if (L::cz(k) != 0) { const double v = L::cz(k) > 0 ? a2 : -a2; s = have ? s + v : v; }
+    return s;
+}
+
 constexpr uint8_t CELL_BB = 0;    // CellType::bounce_back
 constexpr uint8_t CELL_BULK = 1;  // CellType::bulk
 

@@ -137,7 +137,7 @@ CLBM_D void sc_collide_rho(const ModelParams &mp, const double *f, ScForceSums &
     const double A = omega * rho;
 #pragma unroll
     for (int k = 0; k < L::H; ++k) {
-        const double cu = L::cx(k) * ux + L::cy(k) * uy + L::cz(k) * uz;
+        const double cu = cdot<L>(k, ux, uy, uz);
         const double even = A * L::t(k) * (base + 4.5 * cu * cu);
         const double odd = A * L::t(k) * 3.0 * cu;
         out[k] = om1 * f[k] + (even + odd);
