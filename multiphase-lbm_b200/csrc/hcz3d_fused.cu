@@ -223,12 +223,16 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     nxt = cur;
 
     // S2 cells of this thread as ring offsets (halo-3 / halo-2 coordinates)
+    // (a lane past the region in a partly active warp repeats its first cell, so that every round is warp-uniform)
     int c2_q3[C::N2], c2_q2[C::N2];
+    bool c2_on[C::N2];
 #pragma unroll
     for (int j = 0; j < C::N2; ++j) {
-        const int h = tid + j * NT;
+        int h = tid + j * NT;
+        c2_on[j] = ((tid & ~31) + j * NT) < C::R2;   // warp-uniform
+        if (h >= C::R2) h = tid;
         const int a2 = h / C::Z2, b2 = h % C::Z2;
-        c2_q2[j] = (h < C::R2) ? h : -1;
+        c2_q2[j] = h;
         c2_q3[j] = (a2 + 1) * C::Z3 + (b2 + 1);
     }
     unsigned wmask = 0;   // bit (p & 7): plane p has a bounce_back node inside this CTA's window (CTA-uniform)
@@ -333,41 +337,53 @@ hcz3d_fused_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             const int p = x + 2;
             const double *Pm = r_phi + ((p - 1) & 3) * C::R3, *P0 = r_phi + (p & 3) * C::R3, *Pp = r_phi + ((p + 1) & 3) * C::R3;
             const uint8_t *Fm = r_fl + ((p - 1) & 7) * C::R3, *F0 = r_fl + (p & 7) * C::R3, *Fp = r_fl + ((p + 1) & 7) * C::R3;
-            const bool walls = walls_near(p);
+            // all cells of the thread are evaluated before the first store (the loads of one cell must not wait behind the
+            // stores of the previous one), in a walls / wall-free instantiation
+            auto s2 = [&](auto wtag) {
+                constexpr bool W = decltype(wtag)::value;
+                double lap_v[C::N2], pp_v[C::N2];
 #pragma unroll
-            for (int j = 0; j < C::N2; ++j) {
-                if (c2_q2[j] < 0) continue;
-                const int q3 = c2_q3[j];
-                const double phi_c = P0[q3];
-                double sum = 0.0;
-                if (walls) {
+                for (int j = 0; j < C::N2; ++j) {
+                    if (!c2_on[j]) continue;
+                    const int q3 = c2_q3[j];
+                    const double phi_c = P0[q3];
+                    double sum = 0.0;
+                    if constexpr (W) {
 #pragma unroll
-                    for (int k = 0; k < 19; ++k) {
-                        if (k == L19f::REST) continue;
-                        const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
-                        const uint8_t *F = L19f::cx(k) < 0 ? Fm : (L19f::cx(k) > 0 ? Fp : F0);
-                        const int q = q3 + L19f::cy(k) * C::Z3 + L19f::cz(k);
-                        if (F[q] != CELL_BB) sum += L19f::t(k) * (R[q] - phi_c);
+                        for (int k = 0; k < 19; ++k) {
+                            if (k == L19f::REST) continue;
+                            const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
+                            const uint8_t *F = L19f::cx(k) < 0 ? Fm : (L19f::cx(k) > 0 ? Fp : F0);
+                            const int q = q3 + L19f::cy(k) * C::Z3 + L19f::cz(k);
+                            if (F[q] != CELL_BB) sum += L19f::t(k) * (R[q] - phi_c);
+                        }
+                    } else {
+                        // no wall in reach: sum_k t_k (phi_nb - phi_c) = (1/18) S_axis + (1/36) S_diag - (2/3) phi_c with the
+                        // neighbour values added in four independent chains
+                        double sa[2] = {0.0, 0.0}, sd[2] = {0.0, 0.0};
+                        int na = 0, nd = 0;
+#pragma unroll
+                        for (int k = 0; k < 19; ++k) {
+                            if (k == L19f::REST) continue;
+                            const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
+                            const double v = R[q3 + L19f::cy(k) * C::Z3 + L19f::cz(k)];
+                            const bool axis = (L19f::cx(k) != 0) + (L19f::cy(k) != 0) + (L19f::cz(k) != 0) == 1;
+                            if (axis) { sa[na & 1] += v; ++na; }
+                            else { sd[nd & 1] += v; ++nd; }
+                        }
+                        sum = (1. / 18.) * (sa[0] + sa[1]) + (1. / 36.) * (sd[0] + sd[1]) - (2. / 3.) * phi_c;
                     }
-                } else {
-                    // no wall in reach: sum_k t_k (phi_nb - phi_c) = (1/18) S_axis + (1/36) S_diag - (2/3) phi_c with the
-                    // neighbour values added in four independent chains
-                    double sa[2] = {0.0, 0.0}, sd[2] = {0.0, 0.0};
-                    int na = 0, nd = 0;
-#pragma unroll
-                    for (int k = 0; k < 19; ++k) {
-                        if (k == L19f::REST) continue;
-                        const double *R = L19f::cx(k) < 0 ? Pm : (L19f::cx(k) > 0 ? Pp : P0);
-                        const double v = R[q3 + L19f::cy(k) * C::Z3 + L19f::cz(k)];
-                        const bool axis = (L19f::cx(k) != 0) + (L19f::cy(k) != 0) + (L19f::cz(k) != 0) == 1;
-                        if (axis) { sa[na & 1] += v; ++na; }
-                        else { sd[nd & 1] += v; ++nd; }
-                    }
-                    sum = (1. / 18.) * (sa[0] + sa[1]) + (1. / 36.) * (sd[0] + sd[1]) - (2. / 3.) * phi_c;
+                    lap_v[j] = 6.0 * sum;
+                    pp_v[j] = hcz_psi1(phi_c, mp.a, mp.b);
                 }
-                r_lap[(p & 3) * C::R2 + c2_q2[j]] = 6.0 * sum;
-                r_pp[(p & 3) * C::R2 + c2_q2[j]] = hcz_psi1(phi_c, mp.a, mp.b);
-            }
+#pragma unroll
+                for (int j = 0; j < C::N2; ++j) {
+                    if (!c2_on[j]) continue;
+                    r_lap[(p & 3) * C::R2 + c2_q2[j]] = lap_v[j];
+                    r_pp[(p & 3) * C::R2 + c2_q2[j]] = pp_v[j];
+                }
+            };
+            if (walls_near(p)) s2(std::true_type{}); else s2(std::false_type{});
         }
         __syncthreads();
 
