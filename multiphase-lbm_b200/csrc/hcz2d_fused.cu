@@ -21,6 +21,7 @@
 // quotients shared (4 FP64 divisions per node instead of 13; they were a third of the instruction stream): fused and
 // staged agree to O(1 ulp) per step, both within 1e-10 of the oracle.
 #include <cstdlib>
+#include <type_traits>
 
 #include "sc_cell.cuh"
 
@@ -55,13 +56,15 @@ CLBM_D void ring_grad(const double (*R)[NT], const uint8_t (*FL)[NT], unsigned w
 {
     double ax = 0.0, ay = 0.0;
     if (wall == 0u) {
+        // opposite directions first (equal weights): half the FMAs and chains of three instead of six
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (k == L9f::REST) continue;
+        for (int k = 0; k < 4; ++k) {
+            const int ko = L9f::opp(k);
             const int slot = L9f::cx(k) < 0 ? sm : (L9f::cx(k) > 0 ? sp : s0);
-            const double v = R[slot][p + L9f::cy(k)];
-            if (L9f::cx(k)) ax += L9f::t(k) * L9f::cx(k) * v;
-            if (L9f::cy(k)) ay += L9f::t(k) * L9f::cy(k) * v;
+            const int oslot = L9f::cx(ko) < 0 ? sm : (L9f::cx(ko) > 0 ? sp : s0);
+            const double d = R[slot][p + L9f::cy(k)] - R[oslot][p + L9f::cy(ko)];
+            if (L9f::cx(k)) ax += (L9f::t(k) * L9f::cx(k)) * d;
+            if (L9f::cy(k)) ay += (L9f::t(k) * L9f::cy(k)) * d;
         }
     } else {
 #pragma unroll
@@ -118,37 +121,51 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
 #pragma unroll
         for (int k = 0; k < 9; ++k) f[k] = P.fin[k][i];
     };
-    auto fill_direct = [&](int xg) {
-        if (!has_phi) return;
+    auto fill_direct = [&](int xg) -> bool {   // true: the cell is a bounce_back node
+        if (!has_phi) return false;
         const int i = col_of(xg);
-        if (is_ghost(xg)) { put_phi(xg, phi_g[i], flag[i]); return; }
+        const uint8_t fl = flag[i];
+        if (is_ghost(xg)) { put_phi(xg, phi_g[i], fl); return fl == CELL_BB; }
         double f[9];
         load_f(xg, f);
-        put_phi(xg, Mom<L9f>::sum(f), flag[i]);
+        put_phi(xg, Mom<L9f>::sum(f), fl);
+        return fl == CELL_BB;
     };
+    // Walls are rare (two rows of the whole lattice in the shipped cases), so every stencil phase exists twice: the general
+    // one with the mirror rule per neighbour, and a straight-line one for windows without a bounce_back node.  The choice
+    // is CTA-uniform: bit (xg & 7) of wmask says "column xg has a bounce_back node on this CTA's rows".
+    unsigned wmask = 0;
+    auto walls_near = [&](int xg) { return (wmask & ((1u << ((xg - 1) & 7)) | (1u << (xg & 7)) | (1u << ((xg + 1) & 7)))) != 0u; };
     auto make_lap = [&](int xg) {
         if (!has_lap) return;
         const int s0 = slot_of(xg), sm = slot_of(xg - 1), sp = slot_of(xg + 1);
         double sum = 0.0;
-        if (r_fl[s0][tid] == CELL_BULK) {
-            const double phi_c = r_phi[s0][tid];
+        if (walls_near(xg)) {
+            if (r_fl[s0][tid] == CELL_BULK) {
+                const double phi_c = r_phi[s0][tid];
 #pragma unroll
-            for (int k = 0; k < 9; ++k)
-                if (k != L9f::REST) sum += L9f::t(k) * (ring_mirror<NT>(r_phi, r_fl, k, sm, s0, sp, tid) - phi_c);
+                for (int k = 0; k < 9; ++k)
+                    if (k != L9f::REST) sum += L9f::t(k) * (ring_mirror<NT>(r_phi, r_fl, k, sm, s0, sp, tid) - phi_c);
+            }
+        } else {
+            // sum_k t_k (phi_nb - phi_c) = (1/9) S_axis + (1/36) S_diag - (5/9) phi_c
+            const double sa = (r_phi[sm][tid] + r_phi[sp][tid]) + (r_phi[s0][tid - 1] + r_phi[s0][tid + 1]);
+            const double sd = (r_phi[sm][tid - 1] + r_phi[sp][tid + 1]) + (r_phi[sm][tid + 1] + r_phi[sp][tid - 1]);
+            sum = fma(1. / 9., sa, fma(1. / 36., sd, (-5. / 9.) * r_phi[s0][tid]));
         }
         r_lap[s0][tid] = 6.0 * sum;
     };
 
     // ---- prologue: phi of columns xa-2 .. xa+1, lap of columns xa-1, xa ----
-    fill_direct(xa - 2);
-    fill_direct(xa - 1);
-    fill_direct(xa);
-    fill_direct(xa + 1);
+    int pw = fill_direct(xa - 2);
+    pw |= (int)fill_direct(xa - 1);
+    pw |= (int)fill_direct(xa);
+    pw |= (int)fill_direct(xa + 1);
     double fn[9];
-    uint8_t fln = CELL_BB;
+    uint8_t fln = CELL_BULK;
     bool ghost_n = is_ghost(xa + 2);
     if (has_phi && !ghost_n) { load_f(xa + 2, fn); fln = flag[col_of(xa + 2)]; }
-    __syncthreads();
+    if (__syncthreads_or(pw)) wmask = 0xffu;   // conservative for the four prologue columns; the ring corrects itself as it advances
     make_lap(xa - 1);
     make_lap(xa);
 
@@ -170,14 +187,19 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         if (x + 1 < xb) stage_pops(x + 1);
         else asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per iteration so wait_group 1 means "column x is here"
         // 1. column x+2: phi from the prefetched populations (or the exchanged ghost field)
+        int anyw = 0;
         if (has_phi) {
-            if (ghost_n) { const int i = col_of(x + 2); put_phi(x + 2, phi_g[i], flag[i]); }
+            if (ghost_n) { const int i = col_of(x + 2); fln = flag[i]; put_phi(x + 2, phi_g[i], fln); }
             else put_phi(x + 2, Mom<L9f>::sum(fn), fln);
+            anyw = fln == CELL_BB;
         }
         // prefetch column x+3 for the next iteration
         ghost_n = is_ghost(x + 3);
         if (x + 1 < xb && has_phi && !ghost_n) { load_f(x + 3, fn); fln = flag[col_of(x + 3)]; }
-        __syncthreads();
+        {
+            const unsigned bit = 1u << ((x + 2) & 7);
+            wmask = __syncthreads_or(anyw) ? (wmask | bit) : (wmask & ~bit);
+        }
         // 2. column x+1: lap(phi)
         make_lap(x + 1);
         __syncthreads();
@@ -185,6 +207,8 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         const int s0 = slot_of(x), sm = slot_of(x - 1), sp = slot_of(x + 1);
         if (!own || r_fl[s0][tid] != CELL_BULK) continue;
 
+        auto collide = [&](auto wtag) {
+        constexpr bool W = decltype(wtag)::value;
         const int i = (x + G) * ny + yy;
         double f[9], gg[9];
         asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -192,11 +216,13 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         for (int k = 0; k < 9; ++k) { gg[k] = st_g[x & 1][k][tid]; f[k] = P.fin[k][i]; }
 
         unsigned wall = 0;
+        if constexpr (W) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            if (k == 4) continue;
-            const int slot = L9f::cx(k) < 0 ? sm : (L9f::cx(k) > 0 ? sp : s0);
-            if (r_fl[slot][tid + L9f::cy(k)] == CELL_BB) wall |= 1u << k;
+            for (int k = 0; k < 9; ++k) {
+                if (k == 4) continue;
+                const int slot = L9f::cx(k) < 0 ? sm : (L9f::cx(k) > 0 ? sp : s0);
+                if (r_fl[slot][tid + L9f::cy(k)] == CELL_BB) wall |= 1u << k;
+            }
         }
         double glx, gly, grx, gry, Ex, Ey, gpx, gpy;
         ring_grad<NT>(r_lap, r_fl, wall, sm, s0, sp, tid, glx, gly);
@@ -239,7 +265,7 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         const double Aa = (omega * (1. / 9.)) * Pp, Ba = (omega * (1. / 9.)) * rho3;
         const double Ad = (omega * (1. / 36.)) * Pp, Bd = (omega * (1. / 36.)) * rho3;
         auto push = [&](int k, double pf, double pg) {
-            if (wall & (1u << k)) {
+            if (W && (wall & (1u << k))) {
                 P.fout[L9f::opp(k)][i] = pf;
                 P.gout[L9f::opp(k)][i] = pg;
             } else {
@@ -286,6 +312,8 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
             push(k, pfp, pgp);
             push(ko, pfm, pgm);
         }
+        };
+        if (walls_near(x)) collide(std::true_type{}); else collide(std::false_type{});
     }
 }
 
