@@ -53,6 +53,9 @@ extern "C" {
 #define CLBM_SC_FORCE_CONTACT 1 /* SC/apps/contactAngle2D.h:248-293: psi_w on the centre node's G1 branch; F=0 if rho<=0; no gravity */
 #define CLBM_SC_FORCE_CONSTG  2 /* SC/apps/twoLayeredFlow2D.h:183-261: constant coupling G, psi = sqrt(2 (rho/3 - P_eos - p_shift) / (|G|/3)),
                                    psi_w = psi(rho_w), F=0 if rho<=0, uniform body force (gx, gy) added to F; pressure_node = P_eos */
+#define CLBM_SC_FORCE_EXPGUO  3 /* SC/apps/RayleighTaylor2D.h (D2Q9 only): psi = 1 - exp(-rho) (:194-196), constant coupling G (the header's `g`),
+                                   a bounce_back neighbour contributes the psi of the OPPOSITE neighbour (:246-262), + gravity*rho in y (:286);
+                                   velocity shift u + F/(2 rho) (:343-351) and Guo's forcing term in the collision (:370-436); no wall force */
 
 /* HCZ D2Q9 force variant, carried in the same `sc_force` member */
 #define CLBM_HCZ_FORCE_GRAVITY 0 /* PF/apps/rayleighTaylor2D.h:316-337: F = kappa rho grad lap phi, + gravity*rho in y */
@@ -81,6 +84,7 @@ extern "C" {
 #define CLBM_CASE_HCZ_LAPLACE3D    5 /* PF/apps/laplace3D.h:170-213,830-849          args: none                       */
 #define CLBM_CASE_SC_LAYERED2D     6 /* SC/apps/twoLayeredFlow2D.h:325-346,441-454 args: {rhol, rhog, h_lower, w_int}  */
 #define CLBM_CASE_HCZ_LAYERED2D    7 /* PF/apps/twoLayeredFlow2D.h:148-196,737-757 args: {h_lower, w_int}              */
+#define CLBM_CASE_SC_RT2D          8 /* SC/apps/RayleighTaylor2D.h:134-158,526-541  args: {rhol, rhog}                  */
 
 typedef struct clbm_ctx clbm_ctx;
 

@@ -8,11 +8,11 @@ import ctypes
 ABI_VERSION = 2
 
 MODEL_SC_D2Q9, MODEL_SC_D3Q19, MODEL_HCZ_D2Q9, MODEL_HCZ_D3Q19, MODEL_PULSATILE = range(5)
-SC_FORCE_LAPLACE, SC_FORCE_CONTACT, SC_FORCE_CONSTG = 0, 1, 2
+SC_FORCE_LAPLACE, SC_FORCE_CONTACT, SC_FORCE_CONSTG, SC_FORCE_EXPGUO = 0, 1, 2, 3
 HCZ_FORCE_GRAVITY, HCZ_FORCE_LAYERED = 0, 1
 REDUCE_MASS, REDUCE_ENERGY, REDUCE_UMAX = 0, 1, 2
 (CASE_SC_LAPLACE2D, CASE_SC_CONTACT2D, CASE_SC_DROPLET3D, CASE_SC_DROPLET3D_PER,
- CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D, CASE_SC_LAYERED2D, CASE_HCZ_LAYERED2D) = range(8)
+ CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D, CASE_SC_LAYERED2D, CASE_HCZ_LAYERED2D, CASE_SC_RT2D) = range(9)
 
 MODEL_Q = {MODEL_SC_D2Q9: 9, MODEL_SC_D3Q19: 19, MODEL_HCZ_D2Q9: 9, MODEL_HCZ_D3Q19: 19, MODEL_PULSATILE: 9}
 MODEL_SETS = {MODEL_SC_D2Q9: 1, MODEL_SC_D3Q19: 1, MODEL_HCZ_D2Q9: 2, MODEL_HCZ_D3Q19: 2, MODEL_PULSATILE: 1}
@@ -150,6 +150,17 @@ def sc_layered_params(nx, ny, *, omega=None, tau=None, ulb=0.1, N=None, Re=60.0,
                   TT0=TT0, sc_force=SC_FORCE_CONSTG, **kw)
     p.gx, p.gy, p.G = gx, gy, G
     p.p_shift = sc_p_shift(rhog, rhol, a, b, R, p.TT)
+    return p
+
+
+def sc_rt_params(nx, ny=None, *, omega=None, tau=None, ulb=0.04, N=None, Re=30.72, g=-5.0, gravity=-1.25e-5, rho_w=0.2, a=1.0, b=4.0, **kw):
+    """Shan-Chen Rayleigh-Taylor parameter set (psi = 1 - exp(-rho), Guo forcing); defaults =
+    SC/apps/Config_Files/config_RayleighTaylor2D.txt; the lattice is N x (4N + 2) (SC/apps/RayleighTaylor2D.h:603)"""
+    if ny is None:
+        ny = 4 * nx + 2
+    p = sc_params(MODEL_SC_D2Q9, nx, ny, omega=omega, tau=tau, ulb=ulb, N=N if N else nx, Re=Re, rho_w=rho_w, a=a, b=b,
+                  gravity=gravity, sc_force=SC_FORCE_EXPGUO, **kw)
+    p.G = g
     return p
 
 

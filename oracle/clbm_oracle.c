@@ -19,7 +19,7 @@
  * (SURVEY.md A.5); we keep IEEE double operations exactly as written.
  *
  * Parity status:
- *   SC D2Q9 (laplace2D.h, contactAngle2D.h), HCZ D2Q9 (rayleighTaylor2D.h),
+ *   SC D2Q9 (laplace2D.h, contactAngle2D.h, twoLayeredFlow2D.h, RayleighTaylor2D.h), HCZ D2Q9 (rayleighTaylor2D.h, twoLayeredFlow2D.h),
  *   HCZ D3Q19 (laplace3D.h): PINNED against the reference functor (golden fixtures).
  *   SC D3Q19: the reference has no such functor -> "parity unpinned" against the
  *   reference; pinned indirectly by the z-uniform D3Q19 == D2Q9 consistency test.
@@ -328,6 +328,177 @@ static void sc_fields(const clbm_params *p, int D, const double *fin, const uint
         if (ux) ux[i] = u[0] + 0.5 * F[0] / rho;
         if (uy) uy[i] = u[1] + 0.5 * F[1] / rho;
         if (uz) uz[i] = (D == 3) ? u[2] + 0.5 * F[2] / rho : 0.0;
+    }
+}
+
+/* ===========================================================================
+ * Shan-Chen Rayleigh-Taylor variant (CLBM_SC_FORCE_EXPGUO) -- SC/apps/RayleighTaylor2D.h
+ * psi = 1 - exp(-rho) (:194-196), constant coupling g, mirrored psi at wall neighbours
+ * (:246-262), Guo forcing with the half-force velocity (:343-351, :370-436).  D2Q9 only.
+ * ======================================================================== */
+static double scrt_psi(double dens) { return 1 - exp(-dens); }
+
+static double scrt_density(const double *fin, size_t ne, size_t i) { return sc2_density(fin, ne, i); } /* :172-183 */
+
+static void scrt_ucommon(const double *fin, size_t ne, size_t i, double rho, double u[2])
+{ /* :186-206 -- no clamp of rho */
+    double X_M1 = fin[0 * ne + i] + fin[2 * ne + i] + fin[3 * ne + i];
+    double X_P1 = fin[5 * ne + i] + fin[7 * ne + i] + fin[8 * ne + i];
+    double Y_M1 = fin[1 * ne + i] + fin[2 * ne + i] + fin[8 * ne + i];
+    double Y_P1 = fin[3 * ne + i] + fin[6 * ne + i] + fin[7 * ne + i];
+    u[0] = X_P1 - X_M1;
+    u[1] = Y_P1 - Y_M1;
+    u[0] /= rho;
+    u[1] /= rho;
+}
+static double scrt_Peos(const clbm_params *p, double rho)
+{ /* :200-208 */
+    double rt = p->b * rho / 4;
+    return (rho / 3.) * (1. + rt + rt * rt - rt * rt * rt) / ((1 - rt) * (1 - rt) * (1 - rt)) - p->a * rho * rho;
+}
+/* force_ff :236-289 ; psi[] holds scrt_psi(density) of EVERY node (wall nodes have density 0 -> psi 0) */
+static void scrt_force_ff(const clbm_params *p, const double *psi, const uint8_t *flag, double rho_c, size_t i, int iX, int iY, double F[2])
+{
+    const int nx = p->nx, ny = p->ny;
+    double fx = 0.0, fy = 0.0;
+    const double psi_c = psi[i];
+    for (int k = 0; k < 9; ++k) {
+        int XX = (iX + C9[k][0] + nx) % nx;
+        int YY = iY + C9[k][1];
+        size_t nb = (size_t)YY + (size_t)ny * XX;
+        if (flag[nb] == BB) {
+            int XXX = (iX - C9[k][0] + nx) % nx;
+            int YYY = iY - C9[k][1];
+            size_t nbb = (size_t)YYY + (size_t)ny * XXX;
+            double psi_nb = psi[nbb];
+            fx += T9[k] * C9[k][0] * psi_nb;
+            fy += T9[k] * C9[k][1] * psi_nb;
+        } else {
+            double psi_nb = psi[nb];
+            fx += T9[k] * C9[k][0] * psi_nb;
+            fy += T9[k] * C9[k][1] * psi_nb;
+        }
+    }
+    fx *= -p->G * psi_c;
+    fy *= -p->G * psi_c;
+    fy += p->gravity * rho_c;
+    F[0] = fx;
+    F[1] = fy;
+}
+/* force_fw :294-340 -- multiplied by 0. in the reference; kept literally (it only decides the sign of a zero) */
+static void scrt_force_fw(const clbm_params *p, const double *psi, const uint8_t *flag, size_t i, int iX, int iY, double F[2])
+{
+    const int nx = p->nx, ny = p->ny;
+    double fx = 0.0, fy = 0.0;
+    const double psi_c = psi[i];
+    for (int k = 0; k < 9; ++k) {
+        int XX = (iX + C9[k][0] + nx) % nx;
+        int YY = iY + C9[k][1];
+        size_t nb = (size_t)YY + (size_t)ny * XX;
+        if (flag[nb] == BB) {
+            double psi_nb = psi[nb];
+            fx += T9[k] * C9[k][0] * psi_nb;
+            fy += T9[k] * C9[k][1] * psi_nb;
+        }
+    }
+    fx *= -p->G * psi_c * 0.;
+    fy *= -p->G * psi_c * 0.;
+    F[0] = fx;
+    F[1] = fy;
+}
+static void scrt_psi_field(const double *fin, size_t ne, double *psi, double *rho)
+{
+#pragma omp parallel for schedule(static)
+    for (long long ii = 0; ii < (long long)ne; ++ii) {
+        rho[ii] = scrt_density(fin, ne, (size_t)ii);
+        psi[ii] = scrt_psi(rho[ii]);
+    }
+}
+/* u_eq :343-351 */
+static void scrt_ueq(const double u[2], const double FF[2], const double FW[2], double rho, double ueq[2])
+{
+    ueq[0] = u[0] + (FF[0] + FW[0]) / (2 * rho);
+    ueq[1] = u[1] + (FF[1] + FW[1]) / (2 * rho);
+}
+/* operator() :407-436 with collideBgk :370-405 and stream :354-367 */
+static void scrt_step(const clbm_params *p, const double *fin, double *fout, const uint8_t *flag)
+{
+    const int nx = p->nx, ny = p->ny;
+    const size_t ne = (size_t)nx * ny;
+    const double omega = p->omega;
+    double *psi = scratch(0, ne), *rhoa = scratch(1, ne);
+    scrt_psi_field(fin, ne, psi, rhoa);
+#pragma omp parallel for schedule(static)
+    for (long long ii = 0; ii < (long long)ne; ++ii) {
+        size_t i = (size_t)ii;
+        if (flag[i] != BULK) continue;
+        int iX = (int)(i / (size_t)ny), iY = (int)(i % (size_t)ny);
+        double rho = rhoa[i], u[2], FF[2], FW[2], ueq[2];
+        scrt_ucommon(fin, ne, i, rho, u);
+        scrt_force_ff(p, psi, flag, rho, i, iX, iY, FF);
+        scrt_force_fw(p, psi, flag, i, iX, iY, FW);
+        scrt_ueq(u, FF, FW, rho, ueq);
+        double usqreq = 1.5 * (ueq[0] * ueq[0] + ueq[1] * ueq[1]);
+        for (int k = 0; k < 4; ++k) {
+            const int ko = OPP9[k];
+            double F_x = FF[0], F_y = FF[1];
+            double e_u_x = C9[k][0] - ueq[0];
+            double e_u_x_op = C9[ko][0] - ueq[0];
+            double e_u_y = C9[k][1] - ueq[1];
+            double e_u_y_op = C9[ko][1] - ueq[1];
+            double ck_ueq = C9[k][0] * ueq[0] + C9[k][1] * ueq[1];
+            double eq_f = rho * T9[k] * (1. + 3. * ck_ueq + 4.5 * ck_ueq * ck_ueq - usqreq);
+            double eq_fopp = eq_f - 6. * rho * T9[k] * ck_ueq;
+            double total_F = T9[k] * (1 - 0.5 * omega) * ((3 * e_u_x + 9 * ck_ueq * C9[k][0]) * F_x + (3 * e_u_y + 9 * ck_ueq * C9[k][1]) * F_y);
+            double total_Fopp = T9[k] * (1 - 0.5 * omega) * ((3 * e_u_x_op - 9 * ck_ueq * C9[ko][0]) * F_x + (3 * e_u_y_op - 9 * ck_ueq * C9[ko][1]) * F_y);
+            double pop_out = (1. - omega) * fin[(size_t)k * ne + i] + omega * eq_f + total_F;
+            double pop_out_opp = (1. - omega) * fin[(size_t)ko * ne + i] + omega * eq_fopp + total_Fopp;
+            {
+                int x2 = (iX + C9[k][0] + nx) % nx, y2 = iY + C9[k][1];
+                size_t nb = (size_t)y2 + (size_t)ny * x2;
+                if (flag[nb] == BB) fout[(size_t)ko * ne + i] = pop_out; else fout[(size_t)k * ne + nb] = pop_out;
+            }
+            {
+                int x2 = (iX + C9[ko][0] + nx) % nx, y2 = iY + C9[ko][1];
+                size_t nb = (size_t)y2 + (size_t)ny * x2;
+                if (flag[nb] == BB) fout[(size_t)k * ne + i] = pop_out_opp; else fout[(size_t)ko * ne + nb] = pop_out_opp;
+            }
+        }
+        {
+            const int k = 4;
+            double eq_f = rho * T9[k] * (1. - usqreq);
+            double total_F_center = T9[k] * (1 - 0.5 * omega) * ((-3. * ueq[0] * (FW[0] + FF[0])) + (-3. * ueq[1] * (FW[1] + FF[1])));
+            fout[(size_t)k * ne + i] = (1. - omega) * fin[(size_t)k * ne + i] + omega * eq_f + total_F_center;
+        }
+    }
+}
+/* output fields: density, P_eos, u_eq (the velocity computeEnergy_RayleighTaylor2D :503-516 sums), force_ff */
+static void scrt_fields(const clbm_params *p, const double *fin, const uint8_t *flag, double *s0, double *s1, double *ux, double *uy,
+                        double *uz, double *fx, double *fy)
+{
+    const int nx = p->nx, ny = p->ny;
+    const size_t ne = (size_t)nx * ny;
+    double *psi = scratch(0, ne), *rhoa = scratch(1, ne);
+    scrt_psi_field(fin, ne, psi, rhoa);
+#pragma omp parallel for schedule(static)
+    for (long long ii = 0; ii < (long long)ne; ++ii) {
+        size_t i = (size_t)ii;
+        int iX = (int)(i / (size_t)ny), iY = (int)(i % (size_t)ny);
+        double r = rhoa[i], u[2] = {0., 0.}, FF[2] = {0., 0.}, FW[2], ueq[2] = {0., 0.}, pr = 0.0;
+        if (flag[i] == BULK) {
+            pr = scrt_Peos(p, r);
+            scrt_ucommon(fin, ne, i, r, u);
+            scrt_force_ff(p, psi, flag, r, i, iX, iY, FF);
+            scrt_force_fw(p, psi, flag, i, iX, iY, FW);
+            scrt_ueq(u, FF, FW, r, ueq);
+        }
+        if (s0) s0[i] = r;
+        if (s1) s1[i] = pr;
+        if (ux) ux[i] = ueq[0];
+        if (uy) uy[i] = ueq[1];
+        if (uz) uz[i] = 0.0;
+        if (fx) fx[i] = FF[0];
+        if (fy) fy[i] = FF[1];
     }
 }
 
@@ -793,7 +964,9 @@ int oracle_step(const clbm_params *p, double *lattice, const uint8_t *flag, int 
         double *fin = lattice + (size_t)(*parity) * npop, *fout = lattice + (size_t)(1 - *parity) * npop;
         double *gin = fin + 2 * npop, *gout = fout + 2 * npop;
         switch (p->model) {
-        case CLBM_MODEL_SC_D2Q9: sc_step(p, 2, fin, fout, flag); break;
+        case CLBM_MODEL_SC_D2Q9:
+            if (p->sc_force == CLBM_SC_FORCE_EXPGUO) scrt_step(p, fin, fout, flag); else sc_step(p, 2, fin, fout, flag);
+            break;
         case CLBM_MODEL_SC_D3Q19: sc_step(p, 3, fin, fout, flag); break;
         case CLBM_MODEL_HCZ_D2Q9: hcz2_step(p, fin, fout, gin, gout, flag); break;
         case CLBM_MODEL_HCZ_D3Q19: hcz3_step(p, fin, fout, gin, gout, flag); break;
@@ -810,7 +983,10 @@ int oracle_fields(const clbm_params *p, const double *lattice, const uint8_t *fl
     const size_t ne = (size_t)p->nx * p->ny * p->nz, npop = (size_t)model_Q(p->model) * ne;
     const double *fin = lattice + (size_t)parity * npop, *gin = fin + 2 * npop;
     switch (p->model) {
-    case CLBM_MODEL_SC_D2Q9: sc_fields(p, 2, fin, flag, s0, s1, ux, uy, uz); break;
+    case CLBM_MODEL_SC_D2Q9:
+        if (p->sc_force == CLBM_SC_FORCE_EXPGUO) scrt_fields(p, fin, flag, s0, s1, ux, uy, uz, NULL, NULL);
+        else sc_fields(p, 2, fin, flag, s0, s1, ux, uy, uz);
+        break;
     case CLBM_MODEL_SC_D3Q19: sc_fields(p, 3, fin, flag, s0, s1, ux, uy, uz); break;
     case CLBM_MODEL_HCZ_D2Q9:
         hcz2_fields(p, fin, gin, flag, s0, s1, s2, ux, uy);
@@ -818,6 +994,33 @@ int oracle_fields(const clbm_params *p, const double *lattice, const uint8_t *fl
         break;
     case CLBM_MODEL_HCZ_D3Q19: hcz3_fields(p, fin, gin, flag, s0, s1, s2, ux, uy, uz); break;
     default: return -1;
+    }
+    return 0;
+}
+
+/* interaction force of every node (0 at non-bulk nodes): force_ff of the Rayleigh-Taylor variant, `force` otherwise */
+int oracle_force(const clbm_params *p, const double *lattice, const uint8_t *flag, int parity, double *fx, double *fy, double *fz)
+{
+    const size_t ne = (size_t)p->nx * p->ny * p->nz, npop = (size_t)model_Q(p->model) * ne;
+    const double *fin = lattice + (size_t)parity * npop;
+    if (p->model != CLBM_MODEL_SC_D2Q9 && p->model != CLBM_MODEL_SC_D3Q19) return -1;
+    if (p->sc_force == CLBM_SC_FORCE_EXPGUO) {
+        if (p->model != CLBM_MODEL_SC_D2Q9) return -1;
+        scrt_fields(p, fin, flag, NULL, NULL, NULL, NULL, NULL, fx, fy);
+        if (fz) memset(fz, 0, ne * sizeof(double));
+        return 0;
+    }
+    const int D = p->model == CLBM_MODEL_SC_D2Q9 ? 2 : 3;
+    const sc_eos e = {p->R, p->TT, p->a};
+    double *psi = scratch(0, ne), *rhoa = scratch(1, ne);
+    sc_psi_field(p, &e, D, fin, flag, psi, rhoa);
+    for (size_t i = 0; i < ne; ++i) {
+        int iX = (int)(i / ((size_t)p->ny * p->nz)), rem = (int)(i % ((size_t)p->ny * p->nz)), iY = rem / p->nz, iZ = rem % p->nz;
+        double F[3] = {0., 0., 0.};
+        if (flag[i] == BULK) sc_force(p, &e, D, psi, flag, rhoa[i], iX, iY, iZ, F);
+        if (fx) fx[i] = F[0];
+        if (fy) fy[i] = F[1];
+        if (fz) fz[i] = F[2];
     }
     return 0;
 }
@@ -867,6 +1070,16 @@ int oracle_init_case(const clbm_params *p, int case_id, const double *args, int 
             s_liq = s_liq < 0.0 ? 0.0 : (s_liq > 1.0 ? 1.0 : s_liq);
             const double s_gas = 1.0 - s_liq;
             const double rho = s_liq * rhog + s_gas * rhol;
+            for (int k = 0; k < 9; ++k) f[(size_t)k * ne + i] = rho * T9[k];
+            wall = (iY == 0 || iY == ny - 1);
+        } break;
+        case CLBM_CASE_SC_RT2D: { /* SC/apps/RayleighTaylor2D.h:134-158 (iniLattice), :526-541 (inigeom) */
+            if (nargs < 2) return -1;
+            const double rhol = args[0], rhog = args[1];
+            double x = (double)iX;
+            double interface = ((double)ny / 2.0) + ((double)nx) * 0.1 * cos(2.0 * M_PI * x / ((double)(nx - 1)));
+            double w = 2.5, y = (double)iY;
+            double rho = 0.5 * (rhol + rhog) + 0.5 * (rhol - rhog) * tanh((y - interface) / (2.0 * w));
             for (int k = 0; k < 9; ++k) f[(size_t)k * ne + i] = rho * T9[k];
             wall = (iY == 0 || iY == ny - 1);
         } break;

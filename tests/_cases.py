@@ -80,6 +80,10 @@ def golden_setup(name):
                                 R=kw["R"], TT0=kw["TT0"], gx=kw["gx"], gy=kw["gy"], G=kw["G"])
         return p, P.CASE_SC_LAYERED2D, (kw["rhol"], kw["rhog"], kw["h_lower"], float(kw["w_int"])), kw["steps"], \
             {"rho": "s0", "pressure": "s1", "ux": "ux", "uy": "uy"}
+    if name.startswith("sc_rt2d"):
+        p = P.sc_rt_params(nx, ny, omega=kw["omega"], g=kw["g"], gravity=kw["gravity"], rho_w=kw["rhow"], a=kw["a"], b=kw["b"])
+        return p, P.CASE_SC_RT2D, (kw["rhol"], kw["rhog"]), kw["steps"], \
+            {"rho": "s0", "pressure": "s1", "ux": "ux", "uy": "uy"}
     if name.startswith("hcz_layered2d"):
         p = P.hcz_layered_params(nx, ny, omega=kw["omega"], phi_l=kw["phi_l"], phi_g=kw["phi_g"], rho_l=kw["rho_l"], rho_g=kw["rho_g"],
                                  a=kw["a"], b=kw["b"], kappa=kw["kappa"], gx=kw["gx"], gx_const=kw["gx_const"])

@@ -35,6 +35,7 @@ def lib():
         _lib.oracle_step.restype = ctypes.c_int
         _lib.oracle_fields.restype = ctypes.c_int
         _lib.oracle_init_case.restype = ctypes.c_int
+        _lib.oracle_force.restype = ctypes.c_int
     return _lib
 
 
@@ -82,6 +83,16 @@ class OracleSim:
         rc = lib().oracle_fields(ctypes.byref(self.p), _dptr(self.lattice),
                                  self.flag.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), self.parity.value,
                                  *[_dptr(arrs[k]) for k in names])
+        assert rc == 0
+        return arrs
+
+    def force(self):
+        """interaction force of the Shan-Chen models (0 at non-bulk nodes): {"fx", "fy", "fz"}"""
+        n = self.p.nelem
+        arrs = {k: np.zeros(n) for k in ("fx", "fy", "fz")}
+        rc = lib().oracle_force(ctypes.byref(self.p), _dptr(self.lattice),
+                                self.flag.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), self.parity.value,
+                                *[_dptr(arrs[k]) for k in ("fx", "fy", "fz")])
         assert rc == 0
         return arrs
 

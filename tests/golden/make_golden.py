@@ -36,6 +36,10 @@ CASES = {
     "sc_layered2d_12x33_s200": ("ref_sc_layered2d", dict(nx=12, ny=33, steps=200, omega=1.25, rhol=0.247, rhog=0.0405, rho_w=0.06,
                                 a=1.0, b=4.0, R=1.0, TT0=0.9, gx=2e-6, gy=-1e-7, G=-1.3, h_lower=0.25, w_int=2),
                                 1, 9, ["rho", "pressure", "ux", "uy"]),
+    "sc_rt2d_16x66_s300": ("ref_sc_rt2d", dict(nx=16, ny=66, steps=300, omega=1.0, rhol=1.2, rhog=0.4, rhow=0.2, g=-5.0, a=1.0, b=4.0,
+                           gravity=-1.25e-5), 1, 9, ["rho", "pressure", "ux", "uy", "fx", "fy"]),
+    "sc_rt2d_20x42_s150": ("ref_sc_rt2d", dict(nx=20, ny=42, steps=150, omega=1.3, rhol=1.5, rhog=0.3, rhow=0.2, g=-4.5, a=1.0, b=4.0,
+                           gravity=-5e-5), 1, 9, ["rho", "pressure", "ux", "uy", "fx", "fy"]),
     "hcz_rt2d_16x66_s40": ("ref_hcz_rt2d", dict(nx=16, ny=66, steps=40, omega=1.9598595172738, phi_l=0.251, phi_g=0.024,
                            rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-6.25e-6),
                            2, 9, ["phi", "P", "rho", "ux", "uy"]),

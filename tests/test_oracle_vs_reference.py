@@ -27,6 +27,10 @@ def test_oracle_bit_exact_vs_reference(name):
     f = sim.fields()
     for gname, slot in fmap.items():
         np.testing.assert_array_equal(f[slot], z[gname], err_msg="%s field %s" % (name, gname))
+    if "fx" in z.files:     # fixtures that also hold the reference's force_ff (SC/apps/RayleighTaylor2D.h:236-289)
+        F = sim.force()
+        np.testing.assert_array_equal(F["fx"], z["fx"])
+        np.testing.assert_array_equal(F["fy"], z["fy"])
 
 
 @pytest.mark.parametrize("name", NAMES[:1] + NAMES[-1:])
