@@ -7,6 +7,7 @@
 #include <array>
 
 #include "PulsatileBloodFlow2D.h"
+#include "RayleighTaylor2D.h"
 #include "Young_Laplace2D.h"
 #include "contactAngle2D.h"
 #include "laplace2D.h"
@@ -34,6 +35,7 @@ int main(int argc, char **argv)
         else if (problem == "Young_Laplace2D") coolbm::Young_Laplace2D(dir);
         else if (problem == "twoLayeredPF2D") coolbm::twoLayeredPF2D(dir);
         else if (problem == "rayleighTaylor2D") coolbm::rayleighTaylor2D(dir);
+        else if (problem == "RayleighTaylor2D") coolbm::RayleighTaylor2D(dir);   // the Shan-Chen one (capital R, as in SC/apps)
         else if (problem == "laplace3D") coolbm::laplace3D(dir);
         else { std::cerr << "unknown problem \"" << problem << "\"\n"; return 2; }
     } catch (const std::exception &e) {

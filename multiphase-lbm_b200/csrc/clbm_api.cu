@@ -208,6 +208,14 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     if (p->abi_version != CLBM_ABI_VERSION) { set_error("ABI version %d != %d", p->abi_version, CLBM_ABI_VERSION); return CLBM_EINVAL; }
     if (p->model < 0 || p->model > CLBM_MODEL_HCZ_D3Q19) { set_error("unsupported model %d", p->model); return CLBM_EINVAL; }
     if (p->sc_force == CLBM_SC_FORCE_CONSTG && p->G == 0.0) { set_error("constant-G Shan-Chen needs G != 0"); return CLBM_EINVAL; }
+    if ((p->model == CLBM_MODEL_SC_D2Q9 || p->model == CLBM_MODEL_SC_D3Q19) && (p->sc_force < 0 || p->sc_force > CLBM_SC_FORCE_EXPGUO)) {
+        set_error("unknown Shan-Chen force variant %d", p->sc_force);
+        return CLBM_EINVAL;
+    }
+    if (p->model == CLBM_MODEL_SC_D3Q19 && p->sc_force == CLBM_SC_FORCE_EXPGUO) {
+        set_error("the psi = 1 - exp(-rho) / Guo variant (SC/apps/RayleighTaylor2D.h) is D2Q9 only");
+        return CLBM_EINVAL;
+    }
     const bool is3d = p->model == CLBM_MODEL_SC_D3Q19 || p->model == CLBM_MODEL_HCZ_D3Q19;
     if (p->nx < 1 || p->ny < 1 || p->nz < 1 || (!is3d && p->nz != 1)) { set_error("bad extent %d x %d x %d", p->nx, p->ny, p->nz); return CLBM_EINVAL; }
     if (p->nx_global < p->nx || p->x_offset < 0 || p->x_offset + p->nx > p->nx_global) { set_error("bad slab [%d,%d) of %d", p->x_offset, p->x_offset + p->nx, p->nx_global); return CLBM_EINVAL; }
@@ -256,39 +264,7 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     g.ncs = (long long)(p->nx + 2 * g.G) * g.plane;
     if (c->multi && p->nx < g.G) { set_error("slab thinner (%d) than the halo depth (%d)", p->nx, g.G); delete c; return CLBM_EINVAL; }
 
-    ModelParams &m = c->mp;
-    m.omega = p->omega; m.gravity = p->gravity;
-    m.rho_w = p->rho_w; m.a = p->a; m.b = p->b; m.R = p->R; m.TT = p->TT;
-    m.phi_l = p->phi_l; m.phi_g = p->phi_g; m.rho_l = p->rho_l; m.rho_g = p->rho_g; m.kappa = p->kappa;
-    m.sc_force = p->sc_force;
-    m.tau = 1. / p->omega;
-    m.inv_dphi = (p->phi_l != p->phi_g) ? 1.0 / (p->phi_l - p->phi_g) : 0.0;
-    m.drho = p->rho_l - p->rho_g;
-    {
-        // wall pseudopotential: laplace2D.h:210 evaluates psi_yuan_from_rho(rho_w) (own branch G1(rho_w));
-        // contactAngle2D.h:259-262 re-evaluates it on the CENTRE node's branch G1c = +-1/3
-        const double cs2 = 1.0 / 3.0, rw = p->rho_w, dw = (1.0 - rw);
-        const double Zw = 1.0 + (4.0 * rw - 2.0 * rw * rw) / (dw * dw * dw);
-        m.gx = p->gx; m.gy = p->gy; m.G = p->G; m.p_shift = p->p_shift; m.gx_const = p->gx_const;
-        m.kpsi = (p->G != 0.0) ? 2.0 / (fabs(p->G) * cs2) : 0.0;
-        if (p->sc_force == CLBM_SC_FORCE_CONSTG) {
-            // psi_w = psi_from_rho(rho_w) with the same constant-G mapping (twoLayeredFlow2D.h:226)
-            const double Pw = rw * p->R * p->TT * Zw - p->a * rw * rw + p->p_shift;
-            const double Sw = cs2 * rw - Pw;
-            m.psiw_pos = m.psiw_neg = (Sw <= 0.0) ? 0.0 : sqrt(2.0 * Sw / (fabs(p->G) * cs2));
-        } else if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
-            const double vp = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / cs2;
-            const double vn = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / -cs2;
-            m.psiw_pos = (vp > 0.0) ? sqrt(vp) : 0.0;
-            m.psiw_neg = (vn > 0.0) ? sqrt(vn) : 0.0;
-        } else {
-            const double Pw = rw * p->R * p->TT * Zw - p->a * rw * rw;
-            const double sw = p->R * p->TT * Zw - p->a * rw - cs2;
-            const double G1w = (sw > 0.0) ? cs2 : -cs2;
-            const double vw = 6.0 * (Pw - cs2 * rw) / G1w;
-            m.psiw_pos = m.psiw_neg = (vw > 0.0) ? sqrt(vw) : 0.0;
-        }
-    }
+    derive_model_params(p, c->mp);
 
     int rc = 0;
     auto fail = [&](int code) { clbm_destroy(c); return code; };

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -26,6 +27,43 @@ struct ModelParams {
     double kpsi;                 // 2 / (|G| cs2): psi = sqrt(kpsi * (rho/3 - P_eos - p_shift))
     double inv_dphi, drho;       // HCZ total_rho: rho = rho_g + (phi - phi_g) * inv_dphi * drho, inv_dphi = 1/(phi_l - phi_g)
 };
+
+// scalar parameters of the kernels from the C-ABI parameter block, derived with the reference's own expressions
+inline void derive_model_params(const clbm_params *p, ModelParams &m)
+{
+    m.omega = p->omega; m.gravity = p->gravity;
+    m.rho_w = p->rho_w; m.a = p->a; m.b = p->b; m.R = p->R; m.TT = p->TT;
+    m.phi_l = p->phi_l; m.phi_g = p->phi_g; m.rho_l = p->rho_l; m.rho_g = p->rho_g; m.kappa = p->kappa;
+    m.sc_force = p->sc_force;
+    m.tau = 1. / p->omega;
+    m.inv_dphi = (p->phi_l != p->phi_g) ? 1.0 / (p->phi_l - p->phi_g) : 0.0;
+    m.drho = p->rho_l - p->rho_g;
+    {
+        // wall pseudopotential: laplace2D.h:210 evaluates psi_yuan_from_rho(rho_w) (own branch G1(rho_w));
+        // contactAngle2D.h:259-262 re-evaluates it on the CENTRE node's branch G1c = +-1/3
+        const double cs2 = 1.0 / 3.0, rw = p->rho_w, dw = (1.0 - rw);
+        const double Zw = 1.0 + (4.0 * rw - 2.0 * rw * rw) / (dw * dw * dw);
+        m.gx = p->gx; m.gy = p->gy; m.G = p->G; m.p_shift = p->p_shift; m.gx_const = p->gx_const;
+        m.kpsi = (p->G != 0.0) ? 2.0 / (fabs(p->G) * cs2) : 0.0;
+        if (p->sc_force == CLBM_SC_FORCE_CONSTG) {
+            // psi_w = psi_from_rho(rho_w) with the same constant-G mapping (twoLayeredFlow2D.h:226)
+            const double Pw = rw * p->R * p->TT * Zw - p->a * rw * rw + p->p_shift;
+            const double Sw = cs2 * rw - Pw;
+            m.psiw_pos = m.psiw_neg = (Sw <= 0.0) ? 0.0 : sqrt(2.0 * Sw / (fabs(p->G) * cs2));
+        } else if (p->sc_force == CLBM_SC_FORCE_CONTACT) {
+            const double vp = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / cs2;
+            const double vn = 6.0 * rw * (p->R * p->TT * Zw - p->a * rw - cs2) / -cs2;
+            m.psiw_pos = (vp > 0.0) ? sqrt(vp) : 0.0;
+            m.psiw_neg = (vn > 0.0) ? sqrt(vn) : 0.0;
+        } else {
+            const double Pw = rw * p->R * p->TT * Zw - p->a * rw * rw;
+            const double sw = p->R * p->TT * Zw - p->a * rw - cs2;
+            const double G1w = (sw > 0.0) ? cs2 : -cs2;
+            const double vw = 6.0 * (Pw - cs2 * rw) / G1w;
+            m.psiw_pos = m.psiw_neg = (vw > 0.0) ? sqrt(vw) : 0.0;
+        }
+    }
+}
 
 struct KernelTiming {
     std::string name;

@@ -10,7 +10,13 @@
 #include <cstdint>
 
 #define CLBM_HD __host__ __device__ __forceinline__
+#ifdef CLBM_HOST_CHECK
+// tests/host_check only (test infrastructure, never part of libclbm.so): the per-cell device functions are also compiled
+// for the host so that their arithmetic can be checked against the oracle on a machine without a GPU
+#define CLBM_D __host__ __device__ inline
+#else
 #define CLBM_D __device__ __forceinline__
+#endif
 
 namespace clbm {
 

@@ -79,20 +79,28 @@ struct ScEos {
 // about 8 instructions.  Arguments must be normal and positive where a square root is taken (callers guard).
 CLBM_D double fast_rcp(double x)
 {
+#if defined(CLBM_HOST_CHECK) && !defined(__CUDA_ARCH__)
+    return 1.0 / x;
+#else
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     r = fma(fma(-x, r, 1.0), r, r);
     r = fma(fma(-x, r, 1.0), r, r);
     return r;
+#endif
 }
 CLBM_D double fast_sqrt(double x)      // x > 1e-290
 {
+#if defined(CLBM_HOST_CHECK) && !defined(__CUDA_ARCH__)
+    return sqrt(x);
+#else
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     y = y * fma(-0.5 * x * y, y, 1.5);           // y ~ x^-1/2
     y = y * fma(-0.5 * x * y, y, 1.5);
     const double s = x * y;
     return fma(fma(-s, s, x), 0.5 * y, s);       // one correction of s ~ x^1/2
+#endif
 }
 
 // ---- HCZ Carnahan-Starling "psi" = p_th(x) - x/3 (PF/apps/rayleighTaylor2D.h:237-242, 374-379) ----

@@ -174,6 +174,90 @@ CLBM_D void sc_outputs(const ModelParams &mp, const double *f, ScForceSums &s, d
     }
 }
 
+// ---- Rayleigh-Taylor variant (CLBM_SC_FORCE_EXPGUO): SC/apps/RayleighTaylor2D.h ----------------------------------------
+// A compile-time variant (template flag GUO of the kernels), so that the Yuan-CS instantiations above are untouched.
+//   psi = 1 - exp(-rho)                                   :194-196
+//   force_ff = -g psi_c sum_k t_k c_k psi(nb), a bounce_back neighbour contributing the psi of the OPPOSITE neighbour
+//              (the callers gather that value), + gravity rho in y            :236-289   (force_fw is multiplied by 0: :336-337)
+//   u_eq = u + F/(2 rho)                                  :343-351
+//   collideBgk with Guo's forcing term                    :370-405, rest population :424-433
+CLBM_D double scrt_psi(double rho) { return 1.0 - exp(-rho); }
+
+template <class L>
+CLBM_D void scrt_force(const ModelParams &mp, const ScForceSums &s, double rho_c, double psi_c, double F[3])
+{
+    const double a = -mp.G * psi_c;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) F[d] = a * s.ff[d];
+    F[1] += mp.gravity * rho_c;
+}
+
+// omega eq_k + (1 - omega/2) t_k [3 (c_k - u) + 9 (c_k.u) c_k].F  split into the part even in c_k,
+//   t_k [A (1 - 1.5 u^2 + 4.5 (c.u)^2) + B (9 (c.u)(c.F) - 3 u.F)],   and the odd part  t_k [3 A (c.u) + 3 B (c.F)],
+// A = omega rho, B = 1 - omega/2: the pair (k, opp k) shares both.
+template <class L>
+CLBM_D void scrt_collide(const ModelParams &mp, const double *f, const ScForceSums &s, double rho_raw, double psi_c, double *out)
+{
+    const double rho = fmax(rho_raw, 1e-14);
+    const double inv = fast_rcp(rho);
+    double jx, jy, jz, F[3];
+    Mom<L>::first(f, jx, jy, jz);
+    scrt_force<L>(mp, s, rho_raw, psi_c, F);
+    const double omega = mp.omega, om1 = 1.0 - omega;
+    const double ux = (jx + 0.5 * F[0]) * inv;
+    const double uy = (jy + 0.5 * F[1]) * inv;
+    const double uz = (L::D == 3) ? (jz + 0.5 * F[2]) * inv : 0.0;
+    const double base = 1.0 - 1.5 * (ux * ux + uy * uy + uz * uz);
+    const double A = omega * rho, B = 1.0 - 0.5 * omega;
+    const double uF3 = 3.0 * B * ((L::D == 3) ? (ux * F[0] + uy * F[1] + uz * F[2]) : (ux * F[0] + uy * F[1]));
+    const double A3 = 3.0 * A, B3 = 3.0 * B, B9 = 9.0 * B;
+#pragma unroll
+    for (int k = 0; k < L::H; ++k) {
+        const double cu = cdot<L>(k, ux, uy, uz);
+        const double cF = cdot<L>(k, F[0], F[1], F[2]);
+        const double even = L::t(k) * (A * (base + 4.5 * cu * cu) + (B9 * cu * cF - uF3));
+        const double odd = L::t(k) * (A3 * cu + B3 * cF);
+        out[k] = om1 * f[k] + (even + odd);
+        out[L::opp(k)] = om1 * f[L::opp(k)] + (even - odd);
+    }
+    out[L::REST] = om1 * f[L::REST] + L::t(L::REST) * (A * base - uF3);
+}
+
+// output fields of one bulk node: density, P_eos (:200-208, the Carnahan-Starling pressure with rt = b rho / 4),
+// u_eq (what computeEnergy_RayleighTaylor2D :503-516 sums) and force_ff
+template <class L>
+CLBM_D void scrt_outputs(const ModelParams &mp, const double *f, const ScForceSums &s, double &rho_raw, double &pr, double u[3], double F[3])
+{
+    rho_raw = Mom<L>::sum(f);
+    double jx, jy, jz;
+    Mom<L>::first(f, jx, jy, jz);
+    scrt_force<L>(mp, s, rho_raw, scrt_psi(rho_raw), F);
+    u[0] = jx / rho_raw + F[0] / (2.0 * rho_raw);
+    u[1] = jy / rho_raw + F[1] / (2.0 * rho_raw);
+    u[2] = (L::D == 3) ? jz / rho_raw + F[2] / (2.0 * rho_raw) : 0.0;
+    const double rt = mp.b * rho_raw / 4.0, d = 1.0 - rt;
+    pr = (rho_raw / 3.0) * (1.0 + rt + rt * rt - rt * rt * rt) / (d * d * d) - mp.a * rho_raw * rho_raw;
+}
+
+// neighbour sums of the force; GUO: a bounce_back neighbour contributes the psi of the opposite neighbour
+// (SC/apps/RayleighTaylor2D.h:246-262) instead of the wall-adhesion term
+template <class L, bool GUO>
+CLBM_D void sc_gather_force(ScForceSums &s, const Nbr &n, const uint8_t *__restrict__ flag, const double *__restrict__ psi)
+{
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) {
+        if (k == L::REST) continue;  // c = 0: contributes nothing, and a bulk node is never its own wall
+        const long long nb = n.at<L>(k);
+        const bool w = flag[nb] == CELL_BB;
+        if constexpr (GUO) {
+            if (w) s.wall |= 1u << k;
+            sc_force_add<L>(s, k, false, fabs(psi[w ? n.at<L>(L::opp(k)) : nb]));
+        } else {
+            sc_force_add<L>(s, k, w, w ? 0.0 : fabs(psi[nb]));
+        }
+    }
+}
+
 // Driving force of the two HCZ D2Q9 variants from kappa rho grad(lap X): PF/apps/rayleighTaylor2D.h:325-327 (gravity in y)
 // and PF/apps/twoLayeredFlow2D.h:316-317 (rho gx + Gx_const in x, nothing in y)
 CLBM_D void hcz2d_force(const ModelParams &mp, double rho, double glx, double gly, double &forcex, double &forcey)

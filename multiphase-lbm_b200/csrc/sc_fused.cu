@@ -34,7 +34,9 @@ template <class L> struct PopTable {
     double *out[L::Q];        // fout + k*ncs
 };
 
-template <class L, int TY, int TZ, int MINB>
+// GUO = true: the Rayleigh-Taylor variant (SC/apps/RayleighTaylor2D.h; psi = 1 - exp(-rho), a wall neighbour
+// contributes the psi of the opposite neighbour, Guo forcing) -- a compile-time flag, the Yuan-CS code is unchanged.
+template <class L, int TY, int TZ, int MINB, bool GUO = false>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const double *__restrict__ psi_g, Geom g,
                 ModelParams mp, int xchunk)
@@ -87,7 +89,11 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
             double v = -1.0;
             ps = 0.0;
             gp = true;
-            if (flag[i] != CELL_BB) { ps = sc_psi_g1(mp, Mom<L>::sum(fk), gp); v = ps; }
+            if (flag[i] != CELL_BB) {
+                if constexpr (GUO) ps = scrt_psi(Mom<L>::sum(fk));
+                else ps = sc_psi_g1(mp, Mom<L>::sum(fk), gp);
+                v = ps;
+            }
             psi_s[slot][ty + 1][cz0] = v;
         }
         for (int h = tid; h < nhalo; h += C::NT) {
@@ -105,7 +111,8 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
 #pragma unroll
                 for (int k = 0; k < L::Q; ++k) fh[k] = P.in[k][i];
                 bool gph;
-                v = sc_psi_g1(mp, Mom<L>::sum(fh), gph);
+                if constexpr (GUO) v = scrt_psi(Mom<L>::sum(fh));
+                else v = sc_psi_g1(mp, Mom<L>::sum(fh), gph);
             }
             psi_s[slot][sy][sz] = v;
         }
@@ -134,10 +141,19 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
                 if (k == L::REST) continue;
                 const int slot = L::cx(k) < 0 ? sm : (L::cx(k) > 0 ? sp : s0);
                 const double v = psi_s[slot][ty + 1 + L::cy(k)][cz0 + L::cz(k)];
-                sc_force_add<L>(s, k, v < 0.0, v);
+                if constexpr (GUO) {
+                    // wall neighbour: psi of the opposite neighbour (RayleighTaylor2D.h:246-262); a wall there too holds psi = 0
+                    const int oslot = L::cx(k) < 0 ? sp : (L::cx(k) > 0 ? sm : s0);
+                    const double vo = psi_s[oslot][ty + 1 - L::cy(k)][cz0 - L::cz(k)];
+                    if (v < 0.0) s.wall |= 1u << k;
+                    sc_force_add<L>(s, k, false, v < 0.0 ? fmax(vo, 0.0) : v);
+                } else {
+                    sc_force_add<L>(s, k, v < 0.0, v);
+                }
             }
             double out[L::Q];
-            sc_collide<L>(mp, fc, s, psc, gpc, out);
+            if constexpr (GUO) scrt_collide<L>(mp, fc, s, Mom<L>::sum(fc), psc, out);
+            else sc_collide<L>(mp, fc, s, psc, gpc, out);
 
             const int i = (x + G) * plane + yz;
             const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
@@ -159,7 +175,7 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
 
 struct FusedChoice { int ty, tz; };
 
-template <class L, int TY, int TZ, int MINB>
+template <class L, int TY, int TZ, int MINB, bool GUO = false>
 static int launch_fused(clbm_ctx *c)
 {
     const Geom &g = c->geo;
@@ -182,7 +198,7 @@ static int launch_fused(clbm_ctx *c)
         P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "sc_fused_collide_stream", true);
-    sc_fused_kernel<L, TY, TZ, MINB><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
+    sc_fused_kernel<L, TY, TZ, MINB, GUO><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -218,6 +234,7 @@ int sc_fused_launch(clbm_ctx *c)
     if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 11;
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;
+    if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO) return launch_fused<D2Q9, 128, 1, 4, true>(c);   // D2Q9 only (clbm_create)
     if (c->Q == 9) {
         switch (variant) {
         case 1: rc = launch_fused<D2Q9, 256, 1, 2>(c); break;

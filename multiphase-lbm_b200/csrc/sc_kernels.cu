@@ -7,7 +7,7 @@
 
 namespace clbm {
 
-template <class L>
+template <class L, bool GUO = false>
 __global__ void __launch_bounds__(256)
 sc_psi_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, double *__restrict__ psi,
               Geom g, ModelParams mp, int x0, long long ncell)
@@ -21,14 +21,20 @@ sc_psi_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, 
     // |value| = psi(rho), sign bit = branch of G1 (set: G1 = -1/3); walls hold +0
     double v = 0.0;
     if (flag[i] != CELL_BB) {
-        bool g1_pos;
-        const double ps = sc_psi_g1(mp, Mom<L>::sum(f), g1_pos);
-        v = g1_pos ? ps : -ps;
+        if constexpr (GUO) {
+            // Rayleigh-Taylor variant: psi = 1 - exp(-rho) >= 0, no G1 branch; wall nodes carry zero populations in the
+            // reference (inigeom zeroes them, nothing writes them), i.e. psi(wall) = 0, which is what +0 stands for here
+            v = scrt_psi(Mom<L>::sum(f));
+        } else {
+            bool g1_pos;
+            const double ps = sc_psi_g1(mp, Mom<L>::sum(f), g1_pos);
+            v = g1_pos ? ps : -ps;
+        }
     }
     psi[i] = v;
 }
 
-template <class L>
+template <class L, bool GUO = false>
 __global__ void __launch_bounds__(256, 2)
 sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const uint8_t *__restrict__ flag,
                   const double *__restrict__ psi, Geom g, ModelParams mp, int x0, long long ncell)
@@ -46,15 +52,10 @@ sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, con
     for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + n.i];
 
     ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
-#pragma unroll
-    for (int k = 0; k < L::Q; ++k) {
-        if (k == L::REST) continue;  // c = 0: contributes nothing, and a bulk node is never its own wall
-        const long long nb = n.at<L>(k);
-        const bool w = flag[nb] == CELL_BB;
-        sc_force_add<L>(s, k, w, w ? 0.0 : fabs(psi[nb]));
-    }
+    sc_gather_force<L, GUO>(s, n, flag, psi);
     const double pc = psi[n.i];
-    sc_collide<L>(mp, f, s, fabs(pc), !signbit(pc), out);
+    if constexpr (GUO) scrt_collide<L>(mp, f, s, Mom<L>::sum(f), pc, out);
+    else sc_collide<L>(mp, f, s, fabs(pc), !signbit(pc), out);
 
 #pragma unroll
     for (int k = 0; k < L::Q; ++k) {
@@ -64,7 +65,7 @@ sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, con
     }
 }
 
-template <class L>
+template <class L, bool GUO = false>
 __global__ void __launch_bounds__(256)
 sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, const double *__restrict__ psi,
                  Geom g, ModelParams mp, double *s0, double *s1, double *ux, double *uy, double *uz, double *fx, double *fy,
@@ -82,14 +83,9 @@ sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ fla
     double rho = Mom<L>::sum(f), pr = 0.0, u[3] = {0., 0., 0.}, F[3] = {0., 0., 0.};
     if (flag[n.i] == CELL_BULK) {
         ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
-#pragma unroll
-        for (int k = 0; k < L::Q; ++k) {
-            if (k == L::REST) continue;
-            const long long nb = n.at<L>(k);
-            const bool w = flag[nb] == CELL_BB;
-            sc_force_add<L>(s, k, w, w ? 0.0 : fabs(psi[nb]));
-        }
-        sc_outputs<L>(mp, f, s, rho, pr, u, F);
+        sc_gather_force<L, GUO>(s, n, flag, psi);
+        if constexpr (GUO) scrt_outputs<L>(mp, f, s, rho, pr, u, F);
+        else sc_outputs<L>(mp, f, s, rho, pr, u, F);
     }
     if (s0) s0[t] = rho;
     if (s1) s1[t] = pr;
@@ -102,12 +98,15 @@ sc_fields_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ fla
 }
 
 // ---- host side ---------------------------------------------------------------------------
+// Rayleigh-Taylor variant (psi = 1 - exp(-rho), Guo forcing): D2Q9 only, enforced by clbm_create
+static bool is_guo(const clbm_ctx *c) { return c->mp.sc_force == CLBM_SC_FORCE_EXPGUO; }
 template <class L> static int sc_psi_range(clbm_ctx *c, int x0, int x1)
 {
     const long long n = (long long)(x1 - x0) * c->geo.plane;
     if (n <= 0) return 0;
     LaunchScope ls(c, "sc_psi");
-    sc_psi_kernel<L><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, x0, n);
+    if (L::D == 2 && is_guo(c)) sc_psi_kernel<D2Q9, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, x0, n);
+    else sc_psi_kernel<L><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, x0, n);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -116,8 +115,12 @@ template <class L> static int sc_collide_range(clbm_ctx *c, int x0, int x1)
     const long long n = (long long)(x1 - x0) * c->geo.plane;
     if (n <= 0) return 0;
     LaunchScope ls(c, "sc_collide_stream", true);
-    sc_collide_kernel<L><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
-                                                                 c->fld[0], c->geo, c->mp, x0, n);
+    if (L::D == 2 && is_guo(c))
+        sc_collide_kernel<D2Q9, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
+                                                                              c->fld[0], c->geo, c->mp, x0, n);
+    else
+        sc_collide_kernel<L><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
+                                                                     c->fld[0], c->geo, c->mp, x0, n);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -169,7 +172,9 @@ static int sc_fields_all(clbm_ctx *c, double *s0, double *s1, double *ux, double
     if (rc) return rc;
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "sc_fields");
-    if (c->Q == 9)
+    if (c->Q == 9 && is_guo(c))
+        sc_fields_kernel<D2Q9, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, fx, fy, fz, n);
+    else if (c->Q == 9)
         sc_fields_kernel<D2Q9><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, fx, fy, fz, n);
     else
         sc_fields_kernel<D3Q19><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], c->geo, c->mp, s0, s1, ux, uy, uz, fx, fy, fz, n);

@@ -54,6 +54,13 @@ init_case_kernel(double *__restrict__ f, double *__restrict__ gpop, double *__re
         vf = s_liq * A.a[1] + (1.0 - s_liq) * A.a[0];   // "liquid" (rhog in the reference's naming) at the walls
         wall = (iY == 0 || iY == ny - 1);
     } break;
+    case CLBM_CASE_SC_RT2D: {   // SC/apps/RayleighTaylor2D.h:134-158, 526-541   args {rhol, rhog}
+        const double x = double(iX);
+        const double itf = (double(ny) / 2.0) + double(nx) * 0.1 * cos(2.0 * 3.14159265358979323846 * x / double(nx - 1));
+        const double w = 2.5, y = double(iY);
+        vf = 0.5 * (A.a[0] + A.a[1]) + 0.5 * (A.a[0] - A.a[1]) * tanh((y - itf) / (2.0 * w));
+        wall = (iY == 0 || iY == ny - 1);
+    } break;
     case CLBM_CASE_SC_DROPLET3D:
     case CLBM_CASE_SC_DROPLET3D_PER: {   // contactAngle2D geometry extruded to 3-D
         const bool per = case_id == CLBM_CASE_SC_DROPLET3D_PER;
@@ -117,12 +124,14 @@ int model_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)
 {
     const int m = c->prm.model;
     const bool sc2 = m == CLBM_MODEL_SC_D2Q9, sc3 = m == CLBM_MODEL_SC_D3Q19;
-    const bool ok = (sc2 && (case_id == CLBM_CASE_SC_LAPLACE2D || case_id == CLBM_CASE_SC_CONTACT2D || case_id == CLBM_CASE_SC_LAYERED2D)) ||
+    const bool ok = (sc2 && (case_id == CLBM_CASE_SC_LAPLACE2D || case_id == CLBM_CASE_SC_CONTACT2D || case_id == CLBM_CASE_SC_LAYERED2D ||
+                            case_id == CLBM_CASE_SC_RT2D)) ||
                     (sc3 && (case_id == CLBM_CASE_SC_DROPLET3D || case_id == CLBM_CASE_SC_DROPLET3D_PER)) ||
                     (m == CLBM_MODEL_HCZ_D2Q9 && (case_id == CLBM_CASE_HCZ_RT2D || case_id == CLBM_CASE_HCZ_LAYERED2D)) ||
                     (m == CLBM_MODEL_HCZ_D3Q19 && case_id == CLBM_CASE_HCZ_LAPLACE3D);
     if (!ok) { set_error("case %d does not belong to model %d", case_id, m); return CLBM_EINVAL; }
-    if ((sc2 || sc3) && nargs < 3) { set_error("Shan-Chen droplet cases need {rhol, rhog, R}"); return CLBM_EINVAL; }
+    if (case_id == CLBM_CASE_SC_RT2D && nargs < 2) { set_error("the Shan-Chen Rayleigh-Taylor case needs {rhol, rhog}"); return CLBM_EINVAL; }
+    if ((sc2 || sc3) && case_id != CLBM_CASE_SC_RT2D && nargs < 3) { set_error("Shan-Chen droplet cases need {rhol, rhog, R}"); return CLBM_EINVAL; }
     CaseArgs A;
     A.n = nargs < 8 ? nargs : 8;
     for (int i = 0; i < 8; ++i) A.a[i] = (args && i < A.n) ? args[i] : 0.0;

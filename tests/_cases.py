@@ -108,3 +108,12 @@ def rel_linf(a, b):
     den = np.max(np.abs(b))
     num = np.max(np.abs(a - b))
     return num / den if den > 0 else num
+
+
+def rel_linf_vec(a_comps, b_comps):
+    """relative L-inf of a VECTOR field: max over components of |a-b|, normalised by the largest |b| over ALL components.
+    Used where one component decays to cancellation level (the x force / x velocity of the Shan-Chen Rayleigh-Taylor case
+    drop to 1e-6 while y stays O(0.1)): a per-component norm would then measure round-off against round-off."""
+    den = max(float(np.max(np.abs(np.asarray(b)))) for b in b_comps)
+    num = max(float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) for a, b in zip(a_comps, b_comps))
+    return num / den if den > 0 else num

@@ -136,6 +136,7 @@ def test_driver_young_laplace_matches_reference_writer(tmp_path):
     ("twoLayeredFlow2D", ["ny     = 101", "TT0 (reduced)=0.95", "rho_w=0.067", "p_shift = "]),
     ("droplet3D", ["N      = 256", "tau    = 1"]),
     ("rayleighTaylor2D", ["ny     = 1026", "omega  = 1.95986"]),
+    ("RayleighTaylor2D", ["Rayleigh Taylor 2D problem", "ny     = 514", "omega  = 1\n", "nu     = 0.166667"]),
     ("twoLayeredPF2D", ["ny     = 101", "w_int   = 2", "Gx_const= 1e-08"]),
     ("laplace3D", ["nz     = 128", "omega  = 0.877193"]),
 ])

@@ -1,0 +1,123 @@
+"""GPU parity of the Shan-Chen Rayleigh-Taylor variant (SC/apps/RayleighTaylor2D.h: psi = 1 - exp(-rho), mirrored psi at
+wall neighbours, Guo forcing; CLBM_SC_FORCE_EXPGUO) -- through the C ABI, the CPU oracle is only the checker.
+
+Bar: 1e-10 relative L-inf.  Scalars and populations use the global-max norm; velocity and force are normalised as VECTOR
+fields (largest component, _cases.rel_linf_vec): in this case the x components decay to ~1e-6 while y stays O(0.1), so a
+per-component norm would measure round-off against round-off.  Masks bit-exact.
+"""
+import numpy as np
+import pytest
+
+import _cases
+from _cases import rel_linf, rel_linf_vec
+from _oracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+
+pkg = _cases.pkg
+P = pkg.params
+TOL = 1e-10
+
+
+def _run(prm, args, steps, fused, device_init=False):
+    ora = OracleSim(prm).init_case(P.CASE_SC_RT2D, args)
+    with pkg.clbm.Lattice(prm.copy(fused=fused)) as lat:
+        if device_init:
+            lat.init_case(P.CASE_SC_RT2D, args)
+        else:
+            lat.upload(ora.lattice, ora.flag, 0)
+        lat.step(steps)
+        got, pops, flags, F = lat.fields(), lat.in_pops(), lat.flags(), lat.force()
+        energy, mass = lat.reduce(P.REDUCE_ENERGY), lat.reduce(P.REDUCE_MASS)
+    ora.step(steps)
+    return ora, got, pops, flags, F, energy, mass
+
+
+def _check(ora, got, pops, flags, F, ref=None, refF=None):
+    ref = ref or ora.fields()
+    refF = refF or ora.force()
+    np.testing.assert_array_equal(flags, ora.flag)
+    for k in ("s0", "s1"):
+        assert rel_linf(got[k], ref[k]) < TOL, k
+    assert rel_linf_vec([got["ux"], got["uy"]], [ref["ux"], ref["uy"]]) < TOL
+    assert rel_linf_vec([F[0], F[1]], [refF["fx"], refF["fy"]]) < TOL
+    assert np.max(np.abs(got["uz"])) == 0.0
+    assert rel_linf(pops, ora.in_pops()) < TOL
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("name", _cases.golden_names("sc_rt2d"))
+def test_sc_rt2d_golden_fixture(name, fused):
+    """fixtures dumped by the untouched reference header (populations, density, P_eos, u_eq, force_ff)"""
+    z, _ = _cases.load_golden(name)
+    prm, case, args, steps, _ = _cases.golden_setup(name)
+    ora, got, pops, flags, F, _, _ = _run(prm, args, steps, fused)
+    np.testing.assert_array_equal(flags, z["flag"])
+    _check(ora, got, pops, flags, F, ref={"s0": z["rho"], "s1": z["pressure"], "ux": z["ux"], "uy": z["uy"]},
+           refF={"fx": z["fx"], "fy": z["fy"]})
+    assert rel_linf(pops, z["pops"]) < TOL
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_sc_rt2d_1000_steps(fused):
+    """shipped parameters (config_RayleighTaylor2D.txt: omega = 1, g = -5, gravity = -1.25e-5) on 64 x 258, 1000 steps,
+    device-side initial condition"""
+    prm = P.sc_rt_params(64, omega=1.0)
+    ora, got, pops, flags, F, energy, mass = _run(prm, (1.2, 0.4), 1000, fused, device_init=True)
+    _check(ora, got, pops, flags, F)
+    ref = ora.fields()
+    bulk = ora.flag == 1
+    e_ref = 0.5 * np.sum((ref["ux"] ** 2 + ref["uy"] ** 2)[bulk]) / prm.nelem
+    assert abs(energy - e_ref) <= 1e-10 * e_ref
+    assert abs(mass - ref["s0"][bulk].sum()) <= 1e-12 * mass
+
+
+def test_sc_rt2d_odd_sizes_and_chunks():
+    """partial tiles of the fused kernel (ny not a multiple of 128) and more than one x-chunk"""
+    prm = P.sc_rt_params(70, 150, omega=1.4, g=-4.5, gravity=-5e-5)
+    ora, got, pops, flags, F, _, _ = _run(prm, (1.5, 0.3), 200, 1)
+    _check(ora, got, pops, flags, F)
+
+
+def test_sc_rt2d_mass_conservation_large():
+    """size-independent property at a lattice the oracle does not run: bounce-back walls + periodic x conserve mass"""
+    prm = P.sc_rt_params(512, omega=1.0)
+    with pkg.clbm.Lattice(prm) as lat:
+        lat.init_case(P.CASE_SC_RT2D, (1.2, 0.4))
+        m0 = lat.reduce(P.REDUCE_MASS)
+        lat.step(500)
+        m1 = lat.reduce(P.REDUCE_MASS)
+    assert abs(m1 - m0) <= 1e-11 * m0
+
+
+def test_sc_rt2d_rejected_on_d3q19():
+    prm = P.sc_params(P.MODEL_SC_D3Q19, 8, 8, 8, sc_force=P.SC_FORCE_EXPGUO)
+    with pytest.raises(pkg.clbm.ClbmError):
+        pkg.clbm.Lattice(prm)
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_sc_rt2d_slab_ring_matches_single_slab(nranks, fused):
+    """x-slab decomposition (psi halo of depth 1, crossing populations): bit-identical to the single slab"""
+    slab = pkg.slab
+    prm = P.sc_rt_params(24, 50, omega=1.2).copy(fused=fused)
+    args, steps = (1.2, 0.4), 80
+    ora = OracleSim(prm).init_case(P.CASE_SC_RT2D, args)
+    with pkg.clbm.Lattice(prm) as single:
+        single.upload(ora.lattice, ora.flag, 0)
+        single.step(steps)
+        ref_pops = single.in_pops()
+    lats = []
+    for r in range(nranks):
+        lat = pkg.clbm.Lattice(slab.slab_params(prm, r, nranks))
+        l, f = slab.slice_host_state(prm, ora.lattice, ora.flag, r, nranks)
+        lat.upload(l, f, 0)
+        lats.append(lat)
+    ring = slab.LocalRing(lats)
+    ring.exchange_flags()
+    ring.step(steps)
+    pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
+    for lat in lats:
+        lat.close()
+    np.testing.assert_array_equal(pops, ref_pops)

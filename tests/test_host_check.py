@@ -1,0 +1,114 @@
+"""Per-cell Shan-Chen device functions (csrc/sc_cell.cuh) compiled for the HOST and checked against the oracle.
+
+Test infrastructure for containers without a GPU (tests/host_check/sc_cell_host.cu): the same psi / force / collision /
+output functions the kernels inline, driven by the two loops of the staged kernels.  It does not replace the `-m gpu`
+parity tests (kernel indexing, shared-memory staging, fused pipelines); it catches arithmetic slips in a variant before
+GPU time is spent on it.  Tolerance: 1e-10 relative L-inf (global-max normalisation), the bar of the GPU tests.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import _cases
+from _cases import P, rel_linf, rel_linf_vec
+from _oracle import OracleSim
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_check", "sc_cell_host.cu")
+LIB = os.path.join(HERE, "host_check", "_build", "libsc_cell_host.so")
+CSRC = os.path.join(_cases.ROOT, "multiphase-lbm_b200", "csrc")
+TOL = 1e-10
+
+pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists(LIB), reason="nvcc not available")
+
+
+def _lib():
+    deps = [SRC, os.path.join(_cases.ROOT, "include", "clbm.h")] + \
+           [os.path.join(CSRC, f) for f in ("sc_cell.cuh", "moments.cuh", "lattice.cuh", "clbm_internal.h")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        subprocess.check_call(["nvcc", "-std=c++17", "-O2", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared", "-o", LIB, SRC])
+    L = ctypes.CDLL(LIB)
+    L.host_check_sc_step.restype = ctypes.c_int
+    L.host_check_sc_fields.restype = ctypes.c_int
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+class HostSim:
+    def __init__(self, osim):
+        self.p = osim.p
+        self.lattice = osim.lattice.copy()
+        self.flag = osim.flag.copy()
+        self.parity = ctypes.c_int(osim.parity.value)
+
+    def step(self, n):
+        rc = _lib().host_check_sc_step(ctypes.byref(self.p), _dp(self.lattice), self.flag.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                       ctypes.byref(self.parity), int(n))
+        assert rc == 0
+        return self
+
+    def in_pops(self):
+        npop = self.p.Q * self.p.nelem
+        off = self.parity.value * npop
+        return self.lattice[off:off + npop]
+
+    def fields(self):
+        names = ["s0", "s1", "ux", "uy", "uz", "fx", "fy", "fz"]
+        arrs = {k: np.zeros(self.p.nelem) for k in names}
+        ptrs = (ctypes.POINTER(ctypes.c_double) * 8)(*[_dp(arrs[k]) for k in names])
+        rc = _lib().host_check_sc_fields(ctypes.byref(self.p), _dp(self.lattice), self.flag.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                                         self.parity.value, ptrs)
+        assert rc == 0
+        return arrs
+
+
+def _compare(p, case_id, args, steps, vec_norm=False):
+    o = OracleSim(p).init_case(case_id, args)
+    h = HostSim(o)
+    o.step(steps)
+    h.step(steps)
+    assert h.parity.value == o.parity.value
+    npop = p.Q * p.nelem
+    ref = o.lattice[o.parity.value * npop:(o.parity.value + 1) * npop]
+    assert rel_linf(h.in_pops(), ref) < TOL
+    fo, fh = o.fields(), h.fields()
+    for k in ("s0", "s1"):
+        assert rel_linf(fh[k], fo[k]) < TOL, k
+    Fo = o.force()
+    if vec_norm:
+        assert rel_linf_vec([fh[k] for k in ("ux", "uy", "uz")], [fo[k] for k in ("ux", "uy", "uz")]) < TOL
+        assert rel_linf_vec([fh[k] for k in ("fx", "fy", "fz")], [Fo[k] for k in ("fx", "fy", "fz")]) < TOL
+    else:
+        for k in ("ux", "uy", "uz"):
+            assert rel_linf(fh[k], fo[k]) < TOL, k
+        for k in ("fx", "fy", "fz"):
+            assert rel_linf(fh[k], Fo[k]) < TOL, k
+    return fo
+
+
+@pytest.mark.parametrize("name", _cases.golden_names("sc_"))
+def test_host_cell_functions_vs_oracle_on_golden_cases(name):
+    """every Shan-Chen fixture (Laplace, contact angle, constant-G layered, Rayleigh-Taylor/Guo): same case, same step count"""
+    p, case_id, args, steps, _ = _cases.golden_setup(name)
+    _compare(p, case_id, args, steps)
+
+
+def test_host_cell_functions_sc_rt_1000_steps():
+    """SC/apps/RayleighTaylor2D.h at the shipped parameters (omega = 1, g = -5, gravity = -1.25e-5), 1000 steps"""
+    p = P.sc_rt_params(24, 98, omega=1.0)
+    f = _compare(p, P.CASE_SC_RT2D, (1.2, 0.4), 1000, vec_norm=True)   # x components decay to 1e-6: see rel_linf_vec
+    assert np.max(np.abs(f["uy"])) > 1e-6
+
+
+def test_host_cell_functions_sc_d3q19_walls():
+    p = P.sc_params(P.MODEL_SC_D3Q19, 12, 10, 8, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    _compare(p, P.CASE_SC_DROPLET3D, (0.265, 0.038, 3.0, 4.0), 50)
