@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define CLBM_ABI_VERSION 2
+#define CLBM_ABI_VERSION 3 /* 3: + CLBM_SC_FORCE_EXPGUO, CLBM_CASE_SC_RT2D, clbm_diag_* (the struct layouts are those of version 2) */
 
 /* ---- models (one per reference functor family) -------------------------- */
 #define CLBM_MODEL_SC_D2Q9    0 /* LBM_Laplace2D / LBM_contactAngle2D (Yuan-CS Shan-Chen) */
@@ -167,6 +167,16 @@ int  clbm_free_host(void *ptr);
 
 /* ---- diagnostics ---------------------------------------------------------- */
 int  clbm_reduce(clbm_ctx *ctx, int kind, double *out);
+/* calculateContactAngle's scans (SC/apps/contactAngle2D.h:465-529) on the device, Shan-Chen D2Q9, single slab:
+ *   base_y = first non-solid row at x = 0 from y = 2 up (:473-476; >= ny-1: "no fluid row found", base = height = 0),
+ *   base   = length of the run of rho > rho_cut on row base_y around x = nx/2 (:489-497),
+ *   height = length of the run of fluid nodes with rho > rho_cut on column nx/2 from base_y up (:499-505).
+ * The caller forms theta = atan((b/2)/(R-h)), R = (4h^2+b^2)/(8h) (:513-517).  NULL outputs are skipped. */
+int  clbm_diag_contact_angle(clbm_ctx *ctx, double rho_cut, int *base_y, int *base, int *height);
+/* findInterfaceHeights' scans (PF/apps/rayleighTaylor2D.h:668-708) on the device, HCZ D2Q9, single slab: the largest y in
+ * [1, ny-2] with phi <= phi_mid on column x = 0 (the reference stores it in `bubble_y`) and on column x = nx/2 (`spike_y`);
+ * 0 when the column has none (the reference initialises both ints from +-0.05). */
+int  clbm_diag_interface_heights(clbm_ctx *ctx, double phi_mid, int *y_at_x0, int *y_at_xmid);
 
 /* ---- x-slab ghost exchange (multi-GPU) ----------------------- */
 /* A slab step is  clbm_step_begin (boundary planes, packs the send buffers) ->

@@ -1,6 +1,6 @@
 // contactAngle2D.h -- Shan-Chen droplet on a wetting wall (2N x N, walls y = 0, ny-1) on the B200 library.
 // Driver surface of SC/apps/contactAngle2D.h:644-806 (contactAngle2D()) incl. the base/height contact-angle
-// measurement (:465-529) evaluated on the downloaded density field.
+// measurement (:465-529), whose scans run on the device.
 #pragma once
 #include <cmath>
 
@@ -8,26 +8,14 @@
 
 namespace coolbm {
 
-// base/height method on rho (i = y + ny*x), threshold 0.5 (rho_l + rho_g)
-inline void calculate_contact_angle(const DeviceLattice::Fields &f, int nx, int ny, double rho_l, double rho_g)
+// base/height method, threshold 0.5 (rho_l + rho_g): the three scans run on the device (clbm_diag_contact_angle), the
+// circle geometry and the log lines are those of calculateContactAngle (:507-528)
+inline void calculate_contact_angle(DeviceLattice &lat, int ny, double rho_l, double rho_g)
 {
-    const double rho_cut = 0.5 * (rho_l + rho_g), PI = 3.14159265358979323846;
-    auto at = [ny](int x, int y) { return (size_t)y + (size_t)ny * x; };
-    int base_y = 2;
-    while (base_y < ny && f.flag[at(0, base_y)] == 0) ++base_y;
+    const double PI = 3.14159265358979323846;
+    int base_y = 0, base = 0, height = 0;
+    check(clbm_diag_contact_angle(lat.ctx, 0.5 * (rho_l + rho_g), &base_y, &base, &height));
     if (base_y >= ny - 1) { std::cout << "ContactAngle: no fluid row found above wall.\n"; return; }
-    auto rho_base = [&](int x) { return f.s0[at((x % nx + nx) % nx, base_y)]; };
-    const int xmid = nx / 2;
-    int left = xmid, right = xmid;
-    while (left > 0 && rho_base(left - 1) > rho_cut) --left;
-    while (right < nx - 1 && rho_base(right + 1) > rho_cut) ++right;
-    const int base = std::max(0, right - left + 1);
-    int height = 0;
-    for (int y = base_y; y < ny; ++y) {
-        if (f.flag[at(xmid, y)] == 0) break;
-        if (f.s0[at(xmid, y)] > rho_cut) ++height;
-        else break;
-    }
     if (height <= 0 || base <= 1) {
         std::cout << "ContactAngle: droplet not detected (Base=" << base << ", Height=" << height << ")\n";
         return;
@@ -75,7 +63,7 @@ inline void contactAngle2D(const std::string &config_dir)
         if (vtk) save_vtk_sc(lat, time_iter, dx);
         if (!out) return;
         progress_line(time_iter, dt, max_t);
-        calculate_contact_angle(lat.fields(false, false), nx, ny, rhol, rhog);
+        calculate_contact_angle(lat, ny, rhol, rhog);
         const double M = lat.reduce(CLBM_REDUCE_MASS);
         if (M0 < 0.0) M0 = M;
         std::cout << std::setprecision(12) << "[Mass] M=" << M << "   \xCE\x94M/M0=" << std::setprecision(6) << (M - M0) / M0 * 100.0 << "%\n";

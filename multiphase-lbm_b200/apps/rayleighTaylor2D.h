@@ -31,16 +31,11 @@ struct HczConfig {
     }
 };
 
-// PF/apps/rayleighTaylor2D.h:668-708 on the downloaded phi field (the x = 0 scan feeds "bubble", x = nx/2 feeds "spike")
-inline void find_interface_heights(const std::vector<double> &phi, int nx, int ny, double phi_l, double phi_g, int &spike_y, int &bubble_y)
+// PF/apps/rayleighTaylor2D.h:668-708, scanned on the device (clbm_diag_interface_heights): no field download for two integers.
+// The reference stores the x = 0 scan in `bubble_y` and the x = nx/2 scan in `spike_y`; kept.
+inline void find_interface_heights(DeviceLattice &lat, double phi_l, double phi_g, int &spike_y, int &bubble_y)
 {
-    const double phi_mid = 0.5 * (phi_l + phi_g);
-    spike_y = 0;
-    bubble_y = 0;
-    for (int y = ny - 2; y >= 1; --y)
-        if (phi[(size_t)y + (size_t)ny * 0] <= phi_mid) { bubble_y = y; break; }
-    for (int y = ny - 2; y >= 1; --y)
-        if (phi[(size_t)y + (size_t)ny * (nx / 2)] <= phi_mid) { spike_y = y; break; }
+    check(clbm_diag_interface_heights(lat.ctx, 0.5 * (phi_l + phi_g), &bubble_y, &spike_y));
 }
 
 inline void rayleighTaylor2D(const std::string &config_dir)
@@ -58,9 +53,8 @@ inline void rayleighTaylor2D(const std::string &config_dir)
     std::ofstream efile("energy.dat"), posfile("spike_bubble_position.dat"), velfile("spike_bubble_velocity.dat");
     const double dx = lb.dx, dt = lb.dt;
     run_loop(lat, static_cast<int>(c.max_t / dt), c.out_freq, c.vtk_freq, sw, [&](int time_iter, bool vtk, bool out) {
-        DeviceLattice::Fields f;
-        if (vtk || out) f = lat.fields(false, false);
         if (vtk) {
+            const DeviceLattice::Fields f = lat.fields(false, false);
             VtkWriter w(time_iter, nx, ny, 1, 1.0 / nx);   // the reference calls the writer without dx
             w.scalars("phi", "float", [&](size_t i) { return f.s0[i]; });
             w.scalars("density", "float", [&](size_t i) { return f.s2[i]; });
@@ -72,7 +66,7 @@ inline void rayleighTaylor2D(const std::string &config_dir)
         std::cout << "Average energy: " << std::setprecision(8) << energy << std::endl;
         efile << std::setw(10) << time_iter * dt << std::setw(16) << std::setprecision(8) << energy << std::endl;
         int spike_y, bubble_y;
-        find_interface_heights(f.s0, nx, ny, c.phi_l, c.phi_g, spike_y, bubble_y);
+        find_interface_heights(lat, c.phi_l, c.phi_g, spike_y, bubble_y);
         posfile << std::setw(10) << time_iter * dt << std::setw(16) << (spike_y < 0 ? -1.0 : spike_y * dx) << std::setw(16)
                 << (bubble_y < 0 ? -1.0 : bubble_y * dx) << "\n";
     });

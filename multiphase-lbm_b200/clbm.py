@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libclbm.so")
 EXPORTS = [
     "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_download_lattice",
     "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
-    "clbm_profile_step", "clbm_reduce", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
+    "clbm_profile_step", "clbm_reduce", "clbm_diag_contact_angle", "clbm_diag_interface_heights", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
     "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
     "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
@@ -60,6 +60,8 @@ def load_library(path=None):
     lib.clbm_launch_count.restype = ctypes.c_int64
     lib.clbm_profile_step.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.clbm_reduce.argtypes = [vp, ctypes.c_int, dp]
+    lib.clbm_diag_contact_angle.argtypes = [vp, ctypes.c_double] + [ctypes.POINTER(ctypes.c_int)] * 3
+    lib.clbm_diag_interface_heights.argtypes = [vp, ctypes.c_double] + [ctypes.POINTER(ctypes.c_int)] * 2
     lib.clbm_halo_buffer.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp),
                                      ctypes.POINTER(ctypes.c_size_t)]
     lib.clbm_halo_pack.argtypes = [vp, ctypes.c_int]
@@ -234,6 +236,18 @@ class Lattice:
         out = ctypes.c_double(0)
         self._check(self.lib.clbm_reduce(self._h, int(kind), ctypes.byref(out)))
         return out.value
+
+    def contact_angle_scan(self, rho_cut):
+        """device-side scans of calculateContactAngle (SC/apps/contactAngle2D.h:465-529) -> (base_y, base, height)"""
+        v = [ctypes.c_int(0) for _ in range(3)]
+        self._check(self.lib.clbm_diag_contact_angle(self._h, ctypes.c_double(rho_cut), *[ctypes.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def interface_heights(self, phi_mid):
+        """device-side scans of findInterfaceHeights (PF/apps/rayleighTaylor2D.h:668-708) -> (y at x = 0, y at x = nx/2)"""
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self.lib.clbm_diag_interface_heights(self._h, ctypes.c_double(phi_mid), ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     # -- slab exchange
     def halo_buffer(self, phase, side, recv):

@@ -61,6 +61,8 @@ LaunchScope::~LaunchScope()
 // per-model dispatch (kernels live in the per-model .cu files)
 int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz);
 int sc_force_field(clbm_ctx *c, double *fx, double *fy, double *fz);
+int diag_contact_angle(clbm_ctx *c, double rho_cut, int *base_y, int *base, int *height);          // diag_kernels.cu
+int diag_interface_heights(clbm_ctx *c, double phi_mid, int *y_x0, int *y_xmid);
 int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int sc_psi_all(clbm_ctx *c);
@@ -553,6 +555,20 @@ int clbm_reduce(clbm_ctx *c, int kind, double *out)
     if (!c || !out) { set_error("bad argument to clbm_reduce"); return CLBM_EINVAL; }
     CLBM_CUDA(cudaSetDevice(c->device));
     return model_reduce(c, kind, out);
+}
+
+int clbm_diag_contact_angle(clbm_ctx *c, double rho_cut, int *base_y, int *base, int *height)
+{
+    if (!c) { set_error("bad argument to clbm_diag_contact_angle"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    return diag_contact_angle(c, rho_cut, base_y, base, height);
+}
+
+int clbm_diag_interface_heights(clbm_ctx *c, double phi_mid, int *y_at_x0, int *y_at_xmid)
+{
+    if (!c) { set_error("bad argument to clbm_diag_interface_heights"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    return diag_interface_heights(c, phi_mid, y_at_x0, y_at_xmid);
 }
 
 int clbm_halo_buffer(clbm_ctx *c, int phase, int side, int recv, void **dev_ptr, size_t *bytes)

@@ -5,7 +5,7 @@ The struct carries the scalar members of the reference LBM_* aggregates
 """
 import ctypes
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 MODEL_SC_D2Q9, MODEL_SC_D3Q19, MODEL_HCZ_D2Q9, MODEL_HCZ_D3Q19, MODEL_PULSATILE = range(5)
 SC_FORCE_LAPLACE, SC_FORCE_CONTACT, SC_FORCE_CONSTG, SC_FORCE_EXPGUO = 0, 1, 2, 3
