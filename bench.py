@@ -37,6 +37,7 @@ WORKLOADS = {
     "c2_hcz_d2q9_256": ("hcz2d", (256, 1026, 1), "HCZ D2Q9 Rayleigh-Taylor 256x1026 (BASELINE configs[1]; fits in L2)"),
     "c1_sc_d2q9_256": ("sc2d", (256, 256, 1), "Shan-Chen D2Q9 static droplet 256x256 (BASELINE configs[0]; fits in L2)"),
     "sc_d2q9_8192": ("sc2d_tau1", (8192, 8192, 1), "Shan-Chen D2Q9 static droplet 8192x8192 (HBM-sized D2Q9)"),
+    "sc_rt2d_2048": ("sc_rt2d", (2048, 8194, 1), "Shan-Chen Rayleigh-Taylor D2Q9 (psi = 1 - exp(-rho), Guo forcing; SC/apps/RayleighTaylor2D.h) 2048x8194, walls y=0,ny-1"),
     "yl2d_8192": ("yl2d", (8192, 8192, 1), "Young-Laplace conservative phase-field bubble D2Q9 BGK, 8192 x 8192 periodic (AB reference default problem, HBM-sized)"),
     "c5_pulsatile_1024": ("pulsatile", (10221, 1024, 1), "PulsatileBloodFlow2D compliant vessel D2Q9 MRT, Zou/He pulsatile pressure BCs, N=1024 (BASELINE configs[4])"),
 }
@@ -52,6 +53,9 @@ def build_params(P, key, nx, ny, nz, nx_global, x_offset, fused):
     elif key == "sc2d_tau1":
         prm = P.sc_params(P.MODEL_SC_D2Q9, nx, ny, 1, tau=1.0)
         case, args = P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0)
+    elif key == "sc_rt2d":
+        prm = P.sc_rt_params(nx, ny, omega=1.0)
+        case, args = P.CASE_SC_RT2D, (1.2, 0.4)
     elif key == "hcz3d":
         prm = P.hcz_params(P.MODEL_HCZ_D3Q19, nx, ny, nz, ulb=0.01, N=nx_global, Re=6.0, kappa=5e-4, gravity=0.0)
         case, args = P.CASE_HCZ_LAPLACE3D, ()
@@ -122,7 +126,8 @@ def ncu_traffic(key):
 def cpu_baseline(P, key, threads=0, target_s=12.0):
     """time the CPU oracle port on a bounded sample of the same workload (rank 0, N=1)"""
     from _oracle import OracleSim, max_threads
-    sample = {"sc3d": (96, 96, 96), "hcz3d": (64, 64, 64), "sc2d": (1024, 1024, 1), "sc2d_tau1": (1024, 1024, 1), "hcz2d": (256, 1026, 1)}[key]
+    sample = {"sc3d": (96, 96, 96), "hcz3d": (64, 64, 64), "sc2d": (1024, 1024, 1), "sc2d_tau1": (1024, 1024, 1), "hcz2d": (256, 1026, 1),
+              "sc_rt2d": (256, 1026, 1)}[key]
     prm, case, args = build_params(P, key, *sample, sample[0], 0, 0)
     if key == "sc3d":
         args = (0.265, 0.038, 0.2 * sample[1], 5.0)
@@ -171,6 +176,7 @@ def reference_functor_baseline(key):
     spec = {"sc2d": ("ref_sc_laplace2d", ["nx=512", "ny=512", "steps=40"]),
             "sc2d_tau1": ("ref_sc_laplace2d", ["nx=512", "ny=512", "steps=40", "omega=1.0"]),
             "hcz2d": ("ref_hcz_rt2d", ["nx=128", "ny=514", "steps=8"]),
+            "sc_rt2d": ("ref_sc_rt2d", ["nx=256", "ny=1026", "steps=40", "omega=1.0"]),
             "hcz3d": ("ref_hcz_laplace3d", ["nx=16", "ny=16", "nz=16", "steps=2"])}.get(key)
     if not spec or not ref_binary(spec[0]):
         return None
