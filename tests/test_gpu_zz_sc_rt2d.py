@@ -87,11 +87,11 @@ def _ulp_sensitivity(prm, args, steps):
 
 
 @pytest.mark.parametrize("fused", [0, 1])
-def test_sc_rt2d_300_steps(fused):
+def test_sc_rt2d_200_steps(fused):
     """shipped parameters (config_RayleighTaylor2D.txt: omega = 1, g = -5, gravity = -1.25e-5) on 64 x 258, device-side
-    initial condition, 1e-10 on every field"""
+    initial condition, 200 steps (past the start-up transient, before the amplification documented below), 1e-10 on every field"""
     prm = P.sc_rt_params(64, omega=1.0)
-    ora, got, pops, flags, F, energy, mass = _run(prm, (1.2, 0.4), 300, fused, device_init=True)
+    ora, got, pops, flags, F, energy, mass = _run(prm, (1.2, 0.4), 200, fused, device_init=True)
     _check(ora, got, pops, flags, F)
     ref = ora.fields()
     bulk = ora.flag == 1
