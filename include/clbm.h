@@ -57,6 +57,11 @@ extern "C" {
                                    a bounce_back neighbour contributes the psi of the OPPOSITE neighbour (:246-262), + gravity*rho in y (:286);
                                    velocity shift u + F/(2 rho) (:343-351) and Guo's forcing term in the collision (:370-436); no wall force */
 
+/* collision operator, `collision` member */
+#define CLBM_COLLISION_BGK 0
+#define CLBM_COLLISION_MRT 1 /* HCZ D2Q9 only; BASELINE.json configs[1-2] ask for MRT, the reference functor is BGK:
+                                parity of this operator is UNPINNED against the reference, pinned to BGK at S = omega I */
+
 /* HCZ D2Q9 force variant, carried in the same `sc_force` member */
 #define CLBM_HCZ_FORCE_GRAVITY 0 /* PF/apps/rayleighTaylor2D.h:316-337: F = kappa rho grad lap phi, + gravity*rho in y */
 #define CLBM_HCZ_FORCE_LAYERED 1 /* PF/apps/twoLayeredFlow2D.h:310-330: F_x = kappa rho (grad lap phi)_x + rho*gx + gx_const, no y drive;
@@ -115,6 +120,13 @@ typedef struct clbm_params {
     double gx, gy, G, p_shift;
     /* HCZ layered variant (LBM_twoLayeredPF2D members gx, Gx_const, PF/apps/twoLayeredFlow2D.h:127-128); gx is shared */
     double gx_const;
+    /* collision operator (appended in ABI version 3; zero-initialised = BGK, the only operator the reference's SC / HCZ
+     * functors have).  CLBM_COLLISION_MRT, HCZ D2Q9 only: relaxation in the moment basis of CooLBM_MRT_combustion.cpp:313-323
+     * (rho, e, eps, jx, qx, jy, qy, pxx, pxy), rates S = (omega, s_e, s_eps, omega, s_q, omega, s_q, omega, omega) for BOTH
+     * population sets, forcing term relaxed with (I - S/2) (the form of :2441, :2466).  s_e = s_eps = s_q = omega is BGK. */
+    double s_e, s_eps, s_q;
+    int32_t collision;      /* CLBM_COLLISION_* */
+    int32_t reserved0;
 } clbm_params;
 
 /* ---- life cycle ---------------------------------------------------------- */

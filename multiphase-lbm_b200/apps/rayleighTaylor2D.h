@@ -17,8 +17,14 @@ inline void print_hcz_parameters(const char *title, int N, int nx, int ny, int n
 struct HczConfig {
     double Re = 0, ulb = 0, max_t = 0, phi_l = 0, phi_g = 0, rho_l = 0, rho_g = 0, a = 0, b = 0, kappa = 0, gravity = 0;
     int N = 0, out_freq = 0, vtk_freq = 0;
+    // optional keys of this library, absent from the reference's files: `collision MRT` selects the moment-space operator
+    // (include/clbm.h, CLBM_COLLISION_MRT; HCZ D2Q9 only), s_e / s_eps / s_q its free rates (default: omega, i.e. BGK)
+    bool mrt = false;
+    double s_e = -1, s_eps = -1, s_q = -1;
     explicit HczConfig(Config cfg)
     {
+        if (cfg.has("collision")) { cfg.used["collision"] = true; mrt = cfg.kv["collision"] == "MRT" || cfg.kv["collision"] == "mrt" || cfg.kv["collision"] == "1"; }
+        s_e = cfg.d("s_e", -1); s_eps = cfg.d("s_eps", -1); s_q = cfg.d("s_q", -1);
         Re = cfg.d("Re", 0); ulb = cfg.d("ulb", 0); N = cfg.i("N", 0); max_t = cfg.d("max_t", 0); out_freq = cfg.i("out_freq", 0);
         vtk_freq = cfg.i("vtk_freq", 0); phi_l = cfg.d("phi_l", 0); phi_g = cfg.d("phi_g", 0); rho_l = cfg.d("rho_l", 0);
         rho_g = cfg.d("rho_g", 0); a = cfg.d("a", 0); b = cfg.d("b", 0); kappa = cfg.d("kappa", 0); gravity = cfg.d("gravity", 0);
@@ -28,6 +34,11 @@ struct HczConfig {
     {
         p.omega = omega; p.gravity = gravity; p.phi_l = phi_l; p.phi_g = phi_g; p.rho_l = rho_l; p.rho_g = rho_g;
         p.a = a; p.b = b; p.kappa = kappa;
+        if (mrt && p.model == CLBM_MODEL_HCZ_D2Q9) {
+            p.collision = CLBM_COLLISION_MRT;
+            p.s_e = s_e > 0 ? s_e : omega; p.s_eps = s_eps > 0 ? s_eps : omega; p.s_q = s_q > 0 ? s_q : omega;
+            std::cout << "collision = MRT  s_e = " << p.s_e << "  s_eps = " << p.s_eps << "  s_q = " << p.s_q << "  (s_nu = omega)\n";
+        }
     }
 };
 

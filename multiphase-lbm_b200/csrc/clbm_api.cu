@@ -214,6 +214,15 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
         set_error("unknown Shan-Chen force variant %d", p->sc_force);
         return CLBM_EINVAL;
     }
+    if (p->collision != CLBM_COLLISION_BGK) {
+        if (p->collision != CLBM_COLLISION_MRT || p->model != CLBM_MODEL_HCZ_D2Q9) {
+            set_error("collision operator %d: only BGK (0) everywhere and MRT (1) for HCZ D2Q9 exist", p->collision);
+            return CLBM_EINVAL;
+        }
+        const double r[3] = {p->s_e, p->s_eps, p->s_q};
+        for (double v : r)
+            if (!(v > 0.0 && v < 2.0)) { set_error("MRT rates s_e, s_eps, s_q must lie in (0, 2): got %g %g %g", r[0], r[1], r[2]); return CLBM_EINVAL; }
+    }
     if (p->model == CLBM_MODEL_SC_D3Q19 && p->sc_force == CLBM_SC_FORCE_EXPGUO) {
         set_error("the psi = 1 - exp(-rho) / Guo variant (SC/apps/RayleighTaylor2D.h) is D2Q9 only");
         return CLBM_EINVAL;

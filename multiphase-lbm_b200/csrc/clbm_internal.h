@@ -26,6 +26,7 @@ struct ModelParams {
     double gx_const;             // HCZ layered variant: constant x force (PF/apps/twoLayeredFlow2D.h:128); sc_force carries the variant
     double kpsi;                 // 2 / (|G| cs2): psi = sqrt(kpsi * (rho/3 - P_eos - p_shift))
     double inv_dphi, drho;       // HCZ total_rho: rho = rho_g + (phi - phi_g) * inv_dphi * drho, inv_dphi = 1/(phi_l - phi_g)
+    double s_e, s_eps, s_q;      // MRT rates of the non-hydrodynamic moments (CLBM_COLLISION_MRT, HCZ D2Q9; mrt.cuh)
 };
 
 // scalar parameters of the kernels from the C-ABI parameter block, derived with the reference's own expressions
@@ -38,6 +39,7 @@ inline void derive_model_params(const clbm_params *p, ModelParams &m)
     m.tau = 1. / p->omega;
     m.inv_dphi = (p->phi_l != p->phi_g) ? 1.0 / (p->phi_l - p->phi_g) : 0.0;
     m.drho = p->rho_l - p->rho_g;
+    m.s_e = p->s_e; m.s_eps = p->s_eps; m.s_q = p->s_q;
     {
         // wall pseudopotential: laplace2D.h:210 evaluates psi_yuan_from_rho(rho_w) (own branch G1(rho_w));
         // contactAngle2D.h:259-262 re-evaluates it on the CENTRE node's branch G1c = +-1/3

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include "mrt.cuh"
 #include "sc_cell.cuh"
 
 namespace clbm {
@@ -79,7 +80,9 @@ CLBM_D void ring_grad(const double (*R)[NT], const uint8_t (*FL)[NT], unsigned w
     gy = 3.0 * ay;
 }
 
-template <int NT, int MINB>
+// MRT = true: CLBM_COLLISION_MRT (include/clbm.h, mrt.cuh) -- a compile-time variant of the collide phase only; the BGK
+// instantiations are unchanged.
+template <int NT, int MINB, bool MRT = false>
 __global__ void __launch_bounds__(NT, MINB)
 hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const double *__restrict__ phi_g, Geom g,
                    ModelParams mp, int xchunk)
@@ -274,6 +277,51 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
                 P.gout[k][i + off] = pg;
             }
         };
+        if constexpr (MRT) {
+            // out = in + F - M^-1 S M (in - eq + F/2), F = the forcing terms below without their (1 - omega/2) factor; with
+            // Gamma_k = eqf_k / phi = t_k (1 + poly_k):  Ff_k = 3 Gamma_k (c_k - u).(-grad psi(phi)),
+            // Fg_k = Gamma_k (c_k - u).F + (Gamma_k - t_k) (c_k - u).(-E); rest population as the reference writes it
+            // (u.(-E), layered variant's own force: SURVEY.md B.8, B.9).  One population set at a time (registers).
+            const MrtRates S = {omega, mp.s_e, mp.s_eps, mp.s_q, omega};
+            double uF0 = uF;
+            if (mp.sc_force == CLBM_HCZ_FORCE_LAYERED) {
+                const double slope = mp.drho * mp.inv_dphi;
+                double fx0, fy0;
+                hcz2d_force(mp, rho, slope * glx, slope * gly, fx0, fy0);
+                uF0 = u0 * fx0 + u1 * fy0;
+            }
+            double sv[9], vv[9], wv[9], of[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double cu = cdot<L9f>(k, u0, u1, 0.0);
+                const double Gam = L9f::t(k) * (1. + (3.0 * cu + 4.5 * cu * cu - usqr));
+                const double Ff = (k == 4) ? 3.0 * uG * Gam : -3.0 * (cdot<L9f>(k, gpx, gpy, 0.0) - uG) * Gam;
+                sv[k] = f[k] + Ff;
+                vv[k] = f[k] - phi * Gam + 0.5 * Ff;
+            }
+            mrt9_relax(vv, S, wv);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) of[k] = sv[k] - wv[k];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double t = L9f::t(k);
+                const double cu = cdot<L9f>(k, u0, u1, 0.0);
+                const double poly = 3.0 * cu + 4.5 * cu * cu - usqr;
+                const double Gam = t * (1. + poly);
+                const double eqg = t * (Pp + rho3 * poly);
+                const double Fg = (k == 4) ? (-uF0 * Gam - uE * (Gam - t))
+                                           : (Gam * (cdot<L9f>(k, forcex, forcey, 0.0) - uF) - (Gam - t) * (cdot<L9f>(k, Ex, Ey, 0.0) - uE));
+                sv[k] = gg[k] + Fg;
+                vv[k] = gg[k] - eqg + 0.5 * Fg;
+            }
+            mrt9_relax(vv, S, wv);
+            P.fout[4][i] = of[4];
+            P.gout[4][i] = sv[4] - wv[4];
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (k != 4) push(k, of[k], sv[k] - wv[k]);
+            return;
+        }
         {   // rest population (:642-663)
             const double t = L9f::t(4);
             const double Gam = t * (1. - usqr);
@@ -317,7 +365,7 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
     }
 }
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool MRT = false>
 static int launch_hcz2d_fused(clbm_ctx *c)
 {
     const Geom &g = c->geo;
@@ -338,7 +386,7 @@ static int launch_hcz2d_fused(clbm_ctx *c)
         P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "hcz2d_fused_collide_stream", true);
-    hcz2d_fused_kernel<NT, MINB><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
+    hcz2d_fused_kernel<NT, MINB, MRT><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -349,6 +397,7 @@ int hcz2d_fused_launch(clbm_ctx *c)
 {
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (const char *e = getenv("CLBM_HCZ2D_TILE")) variant = atoi(e);
+    if (c->prm.collision == CLBM_COLLISION_MRT) return launch_hcz2d_fused<128, 3, true>(c);   // 168 registers: no spills
     switch (variant) {
     case 2: return launch_hcz2d_fused<64, 8>(c);
     case 3: return launch_hcz2d_fused<96, 4>(c);

@@ -9,6 +9,7 @@
 //                                  velocity (:316-337), total_P (:452-460), collideBgk (:552-606),
 //                                  rest population (:642-663), push stream with bounce-back (:533-549)
 // Field slots: fld[0]=phi  fld[1]=lap phi  fld[2]=psi(phi)  fld[3]=psi(rho)  fld[4]=rho
+#include "mrt.cuh"
 #include "sc_cell.cuh"
 
 namespace clbm {
@@ -106,6 +107,9 @@ CLBM_D void hcz2d_node(const ModelParams &mp, const double *g9, const double *co
 
 struct FieldPtrs5 { const double *p[5]; };
 
+// MRT = true: CLBM_COLLISION_MRT (include/clbm.h): out = in + F - M^-1 S M (in - eq + F/2) with the equilibria and the
+// forcing terms of collideBgk, the forcing without its (1 - omega/2) factor (mrt.cuh; S = omega I is collideBgk again)
+template <bool MRT>
 __global__ void __launch_bounds__(256, 2)
 hcz2d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const double *__restrict__ gin,
                      double *__restrict__ gout, const uint8_t *__restrict__ flag, FieldPtrs5 F,
@@ -146,17 +150,42 @@ hcz2d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, 
     for (int k = 0; k < 9; ++k)
         if (k != 4 && flag[n.at<L9>(k)] == CELL_BB) wall |= 1u << k;
 
+    double pf[9], pg[9];
+    if constexpr (MRT) {
+        double Ff[9], Fg[9], vf[9], vg[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double ck_u = L9::cx(k) * u0 + L9::cy(k) * u1;
+            const double poly = 3 * ck_u + 4.5 * ck_u * ck_u - usqr;      // k = 4: -usqr
+            const double eqf = phi * L9::t(k) * (1 + poly);
+            const double eqg = L9::t(k) * (P + (rho / 3.0) * poly);
+            const double e_u_x = L9::cx(k) - u0, e_u_y = L9::cy(k) - u1;
+            if (k == 4) {   // rest population: the layered variant's own force and the reference's (u.(-E)) sign
+                Fg[k] = -(u0 * forcex0 + u1 * forcey0) * eqf * inv_phi + ((u0 * -Ex + u1 * -Ey) * (eqf * inv_phi - L9::t(4)));
+            } else {
+                Fg[k] = (e_u_x * forcex + e_u_y * forcey) * eqf * inv_phi + ((e_u_x * -Ex) + (e_u_y * -Ey)) * (eqf * inv_phi - L9::t(k));
+            }
+            Ff[k] = ((e_u_x * -o.gpsiphi.x) + (e_u_y * -o.gpsiphi.y)) * 3.0 * eqf * inv_phi;
+            vf[k] = f[k] - eqf + 0.5 * Ff[k];
+            vg[k] = gg[k] - eqg + 0.5 * Fg[k];
+        }
+        const MrtRates S = {omega, mp.s_e, mp.s_eps, mp.s_q, omega};
+        double wf[9], wg[9];
+        mrt9_relax(vf, S, wf);
+        mrt9_relax(vg, S, wg);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { pf[k] = f[k] + Ff[k] - wf[k]; pg[k] = gg[k] + Fg[k] - wg[k]; }
+    } else {
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-        double pf, pg;
         if (k == 4) {
             const double eqf0 = phi * L9::t(4) * (1. - usqr);
             const double eqg0 = L9::t(4) * (P - (rho / 3.0) * usqr);
             const double fg0 = hw * (-(u0 * forcex0 + u1 * forcey0) * eqf0 * inv_phi +
                                      ((u0 * -Ex + u1 * -Ey) * (eqf0 * inv_phi - L9::t(4))));
             const double ff0 = hw * (-3.0 * (u0 * -o.gpsiphi.x + u1 * -o.gpsiphi.y) * eqf0 * inv_phi);
-            pf = (1 - omega) * f[4] + omega * eqf0 + ff0;
-            pg = (1 - omega) * gg[4] + omega * eqg0 + fg0;
+            pf[k] = (1 - omega) * f[4] + omega * eqf0 + ff0;
+            pg[k] = (1 - omega) * gg[4] + omega * eqg0 + fg0;
         } else {
             const double ck_u = L9::cx(k) * u0 + L9::cy(k) * u1;
             const double poly = 3 * ck_u + 4.5 * ck_u * ck_u - usqr;
@@ -167,19 +196,23 @@ hcz2d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, 
             const double fg = hw * ((e_u_x * forcex + e_u_y * forcey) * eqf * inv_phi) +
                               hw * ((e_u_x * -Ex) + (e_u_y * -Ey)) * (eqf * inv_phi - L9::t(k));
             const double ff = hw * ((e_u_x * -o.gpsiphi.x) + (e_u_y * -o.gpsiphi.y)) * 3.0 * eqf * inv_phi;
-            pf = (1. - omega) * f[k] + omega * eqf + ff;
-            pg = (1. - omega) * gg[k] + omega * eqg + fg;
+            pf[k] = (1. - omega) * f[k] + omega * eqf + ff;
+            pg[k] = (1. - omega) * gg[k] + omega * eqg + fg;
         }
+    }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
         if (k == 4) {
-            fout[(size_t)4 * g.ncs + n.i] = pf;
-            gout[(size_t)4 * g.ncs + n.i] = pg;
+            fout[(size_t)4 * g.ncs + n.i] = pf[k];
+            gout[(size_t)4 * g.ncs + n.i] = pg[k];
         } else if (wall & (1u << k)) {
-            fout[(size_t)L9::opp(k) * g.ncs + n.i] = pf;
-            gout[(size_t)L9::opp(k) * g.ncs + n.i] = pg;
+            fout[(size_t)L9::opp(k) * g.ncs + n.i] = pf[k];
+            gout[(size_t)L9::opp(k) * g.ncs + n.i] = pg[k];
         } else {
             const long long nb = n.at<L9>(k);
-            fout[(size_t)k * g.ncs + nb] = pf;
-            gout[(size_t)k * g.ncs + nb] = pg;
+            fout[(size_t)k * g.ncs + nb] = pf[k];
+            gout[(size_t)k * g.ncs + nb] = pg[k];
         }
     }
 }
@@ -244,9 +277,14 @@ int hcz2d_collide(clbm_ctx *c)
 {
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "hcz2d_collide_stream", true);
-    hcz2d_collide_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
-                                                                c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
-                                                                fld5(c), c->geo, c->mp, 0, n);
+    if (c->prm.collision == CLBM_COLLISION_MRT)
+        hcz2d_collide_kernel<true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
+                                                                          c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
+                                                                          fld5(c), c->geo, c->mp, 0, n);
+    else
+        hcz2d_collide_kernel<false><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
+                                                                           c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
+                                                                           fld5(c), c->geo, c->mp, 0, n);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }

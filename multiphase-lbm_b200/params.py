@@ -10,6 +10,7 @@ ABI_VERSION = 3
 MODEL_SC_D2Q9, MODEL_SC_D3Q19, MODEL_HCZ_D2Q9, MODEL_HCZ_D3Q19, MODEL_PULSATILE = range(5)
 SC_FORCE_LAPLACE, SC_FORCE_CONTACT, SC_FORCE_CONSTG, SC_FORCE_EXPGUO = 0, 1, 2, 3
 HCZ_FORCE_GRAVITY, HCZ_FORCE_LAYERED = 0, 1
+COLLISION_BGK, COLLISION_MRT = 0, 1
 REDUCE_MASS, REDUCE_ENERGY, REDUCE_UMAX = 0, 1, 2
 (CASE_SC_LAPLACE2D, CASE_SC_CONTACT2D, CASE_SC_DROPLET3D, CASE_SC_DROPLET3D_PER,
  CASE_HCZ_RT2D, CASE_HCZ_LAPLACE3D, CASE_SC_LAYERED2D, CASE_HCZ_LAYERED2D, CASE_SC_RT2D) = range(9)
@@ -33,6 +34,8 @@ class Params(ctypes.Structure):
         ("rho_l", ctypes.c_double), ("rho_g", ctypes.c_double), ("kappa", ctypes.c_double),
         ("gx", ctypes.c_double), ("gy", ctypes.c_double), ("G", ctypes.c_double), ("p_shift", ctypes.c_double),
         ("gx_const", ctypes.c_double),
+        ("s_e", ctypes.c_double), ("s_eps", ctypes.c_double), ("s_q", ctypes.c_double),
+        ("collision", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
     @property
@@ -104,6 +107,17 @@ def hcz_params(model, nx, ny, nz=1, *, omega=None, ulb=0.04, N=None, Re=3000.0, 
         omega = lb_parameters(ulb, N if N else nx, Re)[1]
     return make_params(model, nx, ny, nz, omega=omega, phi_l=phi_l, phi_g=phi_g, rho_l=rho_l, rho_g=rho_g,
                        a=a, b=b, kappa=kappa, gravity=gravity, **kw)
+
+
+def hcz_mrt_params(nx, ny, *, s_e=None, s_eps=None, s_q=None, **kw):
+    """HCZ D2Q9 with the MRT collision operator (include/clbm.h, CLBM_COLLISION_MRT); a rate left at None equals omega,
+    so hcz_mrt_params(nx, ny) is the BGK operator evaluated in moment space"""
+    p = hcz_params(MODEL_HCZ_D2Q9, nx, ny, **kw)
+    p.collision = COLLISION_MRT
+    p.s_e = p.omega if s_e is None else s_e
+    p.s_eps = p.omega if s_eps is None else s_eps
+    p.s_q = p.omega if s_q is None else s_q
+    return p
 
 
 class PulsatileParams(ctypes.Structure):

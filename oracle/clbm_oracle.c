@@ -611,6 +611,44 @@ static void hcz2_force(const clbm_params *p, double rho, const double glap[2], d
     }
 }
 
+/* ---- MRT relaxation in the moment basis of CooLBM_MRT_combustion.cpp:313-323 (rho, e, eps, jx, qx, jy, qy, pxx, pxy), written for
+ * the k-ordering of the SC / PF case headers: row j of M evaluated at c_k.  The rows are mutually orthogonal, so
+ * M^-1 = M^T diag(1/|row|^2) (the M_inv table of :326-336).  w = M^-1 S M v.  PARITY UNPINNED: the reference's SC / HCZ functors
+ * are BGK; this operator is pinned to them only at S = omega I. */
+static void mrt9_rows(double M[9][9], double norm2[9])
+{
+    for (int k = 0; k < 9; ++k) {
+        const double cx = C9[k][0], cy = C9[k][1], c2 = cx * cx + cy * cy;
+        M[0][k] = 1.0;
+        M[1][k] = -4.0 + 3.0 * c2;
+        M[2][k] = 4.0 - 10.5 * c2 + 4.5 * c2 * c2;
+        M[3][k] = cx;
+        M[4][k] = (-5.0 + 3.0 * c2) * cx;
+        M[5][k] = cy;
+        M[6][k] = (-5.0 + 3.0 * c2) * cy;
+        M[7][k] = cx * cx - cy * cy;
+        M[8][k] = cx * cy;
+    }
+    for (int j = 0; j < 9; ++j) {
+        norm2[j] = 0.0;
+        for (int k = 0; k < 9; ++k) norm2[j] += M[j][k] * M[j][k];
+    }
+}
+static void mrt9_relax(const double v[9], const double S[9], double w[9])
+{
+    double M[9][9], n2[9], m[9];
+    mrt9_rows(M, n2);                                            /* 81 exact small-integer products: cheap next to the rest */
+    for (int j = 0; j < 9; ++j) {
+        m[j] = 0.0;
+        for (int k = 0; k < 9; ++k) m[j] += M[j][k] * v[k];      /* moment space (:2431-2436) */
+        m[j] = S[j] * m[j];                                      /* collision in moment space (:2440-2442) */
+    }
+    for (int k = 0; k < 9; ++k) {
+        w[k] = 0.0;
+        for (int j = 0; j < 9; ++j) w[k] += M[j][k] / n2[j] * m[j];   /* back to population space (:2445-2449) */
+    }
+}
+
 /* velocity :316-337 and total_P :452-460 of one bulk node */
 static void hcz2_uP(const clbm_params *p, const uint8_t *flag, const hcz2_f *F, size_t i, int iX, int iY,
                     double u[2], double *Ptot, double glap_phi[2])
@@ -652,6 +690,47 @@ static void hcz2_step(const clbm_params *p, const double *fin, double *fout, con
         hcz2_grad(p, flag, F.psirho, iX, iY, gpsi_rho);
         hcz2_grad(p, flag, F.psiphi, iX, iY, gpsi_phi);
         double usqr = 1.5 * (u[0] * u[0] + u[1] * u[1]);
+
+        if (p->collision == CLBM_COLLISION_MRT) {
+            /* the same equilibria and forcing terms as collideBgk below, without the (1 - omega/2) factor:
+             *   out = in + F - M^-1 S M (in - eq + F/2),   S = (omega, s_e, s_eps, omega, s_q, omega, s_q, omega, omega)
+             * (relaxation :2440-2442, forcing relaxed with (I - S/2) :2466; S = omega I gives collideBgk back) */
+            const double S[9] = {omega, p->s_e, p->s_eps, omega, p->s_q, omega, p->s_q, omega, omega};
+            double Ff[9], Fg[9], vf[9], vg[9], wf[9], wg[9];
+            double Ex = gpsi_rho[0], Ey = gpsi_rho[1];
+            for (int k = 0; k < 9; ++k) {
+                double ck_u = C9[k][0] * u[0] + C9[k][1] * u[1];
+                double eqf = phi * T9[k] * (1 + 3 * ck_u + 4.5 * ck_u * ck_u - usqr);
+                double eqg = T9[k] * (P + (rho / 3.0) * (3 * ck_u + 4.5 * ck_u * ck_u - usqr));
+                double e_u_x = C9[k][0] - u[0], e_u_y = C9[k][1] - u[1];
+                double forcex, forcey;
+                if (k == 4 && p->sc_force == CLBM_HCZ_FORCE_LAYERED) {   /* rest population: grad lap RHO (B.9) */
+                    double glap_rho[2];
+                    hcz2_grad(p, flag, F.laprho, iX, iY, glap_rho);
+                    hcz2_force(p, rho, glap_rho, &forcex, &forcey);
+                } else {
+                    hcz2_force(p, rho, glap_phi, &forcex, &forcey);
+                }
+                Fg[k] = (e_u_x * forcex + e_u_y * forcey) * eqf / phi + ((e_u_x * -Ex) + (e_u_y * -Ey)) * (eqf / phi - T9[k]);
+                if (k == 4)   /* the reference writes the rest term with (u.(-E)), not ((0-u).(-E)) (:654-656): kept */
+                    Fg[k] = -(u[0] * forcex + u[1] * forcey) * eqf / phi + ((u[0] * -Ex + u[1] * -Ey) * (eqf / phi - T9[k]));
+                Ff[k] = ((e_u_x * -gpsi_phi[0]) + (e_u_y * -gpsi_phi[1])) * 3.0 * eqf / phi;
+                vf[k] = fin[(size_t)k * ne + i] - eqf + 0.5 * Ff[k];
+                vg[k] = gin[(size_t)k * ne + i] - eqg + 0.5 * Fg[k];
+            }
+            mrt9_relax(vf, S, wf);
+            mrt9_relax(vg, S, wg);
+            for (int k = 0; k < 9; ++k) {
+                double pf = fin[(size_t)k * ne + i] + Ff[k] - wf[k];
+                double pg = gin[(size_t)k * ne + i] + Fg[k] - wg[k];
+                if (k == 4) { fout[(size_t)k * ne + i] = pf; gout[(size_t)k * ne + i] = pg; continue; }
+                int XX = (iX + C9[k][0] + nx) % nx, YY = iY + C9[k][1];
+                size_t nb = (size_t)YY + (size_t)ny * XX;
+                if (flag[nb] == BB) { fout[(size_t)OPP9[k] * ne + i] = pf; gout[(size_t)OPP9[k] * ne + i] = pg; }
+                else { fout[(size_t)k * ne + nb] = pf; gout[(size_t)k * ne + nb] = pg; }
+            }
+            continue;
+        }
 
         for (int k = 0; k < 4; ++k) { /* collideBgk :552-606 */
             const int ko = OPP9[k];

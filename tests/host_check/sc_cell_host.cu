@@ -11,6 +11,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../multiphase-lbm_b200/csrc/mrt.cuh"
 #include "../../multiphase-lbm_b200/csrc/sc_cell.cuh"
 
 using namespace clbm;
@@ -127,4 +128,11 @@ extern "C" int host_check_sc_fields(const clbm_params *p, const double *lattice,
     else if (guo) fields<D2Q9, true>(g, mp, fin, flag, psi.data(), out);
     else fields<D2Q9, false>(g, mp, fin, flag, psi.data(), out);
     return 0;
+}
+
+// w = M^-1 S M v of csrc/mrt.cuh (the factorised form the HCZ D2Q9 MRT kernels inline); rates = {s_c, s_e, s_eps, s_q, s_nu}
+extern "C" void host_check_mrt9(const double *v, const double *rates, double *w)
+{
+    const MrtRates S = {rates[0], rates[1], rates[2], rates[3], rates[4]};
+    mrt9_relax(v, S, w);
 }

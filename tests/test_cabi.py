@@ -30,8 +30,9 @@ def test_header_symbols_all_exported():
 
 
 def test_params_struct_matches_header_layout():
-    # 10 int32 + 17 doubles, naturally aligned: must equal sizeof(clbm_params) on the C side
-    assert ctypes.sizeof(P.Params) == 10 * 4 + 17 * 8
+    # 10 int32 + 17 doubles (ABI 2) + 3 doubles + 2 int32 (appended in ABI 3), naturally aligned: sizeof(clbm_params) on the C side
+    assert ctypes.sizeof(P.Params) == 10 * 4 + 17 * 8 + 3 * 8 + 2 * 4
+    assert P.Params.s_e.offset == 10 * 4 + 17 * 8 and P.Params.collision.offset == 10 * 4 + 20 * 8
     assert P.Params.omega.offset == 40
 
 

@@ -28,7 +28,7 @@ pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exi
 
 def _lib():
     deps = [SRC, os.path.join(_cases.ROOT, "include", "clbm.h")] + \
-           [os.path.join(CSRC, f) for f in ("sc_cell.cuh", "moments.cuh", "lattice.cuh", "clbm_internal.h")]
+           [os.path.join(CSRC, f) for f in ("sc_cell.cuh", "moments.cuh", "lattice.cuh", "clbm_internal.h", "mrt.cuh")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         subprocess.check_call(["nvcc", "-std=c++17", "-O2", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
@@ -112,3 +112,34 @@ def test_host_cell_functions_sc_rt_1000_steps():
 def test_host_cell_functions_sc_d3q19_walls():
     p = P.sc_params(P.MODEL_SC_D3Q19, 12, 10, 8, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
     _compare(p, P.CASE_SC_DROPLET3D, (0.265, 0.038, 3.0, 4.0), 50)
+
+
+def test_mrt9_factorised_form_equals_the_matrix_form():
+    """csrc/mrt.cuh against M^-1 S M built from the moment rows of CooLBM_MRT_combustion.cpp:313-323 in the k-ordering of the
+    case headers; S = omega I must be omega times the identity"""
+    c = np.array([(-1, 0), (0, -1), (-1, -1), (-1, 1), (0, 0), (1, 0), (0, 1), (1, 1), (1, -1)], dtype=np.float64)
+    cx, cy = c[:, 0], c[:, 1]
+    c2 = cx * cx + cy * cy
+    M = np.stack([np.ones(9), -4 + 3 * c2, 4 - 10.5 * c2 + 4.5 * c2 * c2, cx, (-5 + 3 * c2) * cx, cy, (-5 + 3 * c2) * cy,
+                  cx * cx - cy * cy, cx * cy])
+    # the same matrix as the reference's table (rest first, E, N, W, S, NE, NW, SW, SE), permuted
+    ref_order = [(0, 0), (1, 0), (0, 1), (-1, 0), (0, -1), (1, 1), (-1, 1), (-1, -1), (1, -1)]
+    Mref = np.array([[1, 1, 1, 1, 1, 1, 1, 1, 1], [-4, -1, -1, -1, -1, 2, 2, 2, 2], [4, -2, -2, -2, -2, 1, 1, 1, 1],
+                     [0, 1, 0, -1, 0, 1, -1, -1, 1], [0, -2, 0, 2, 0, 1, -1, -1, 1], [0, 0, 1, 0, -1, 1, 1, -1, -1],
+                     [0, 0, -2, 0, 2, 1, 1, -1, -1], [0, 1, -1, 1, -1, 0, 0, 0, 0], [0, 0, 0, 0, 0, 1, -1, 1, -1]], dtype=np.float64)
+    perm = [ref_order.index((int(a), int(b))) for a, b in c]
+    np.testing.assert_array_equal(M, Mref[:, perm])
+    Minv = np.linalg.inv(M)
+    L = _lib()
+    rng = np.random.default_rng(1)
+    for rates in ([1.3, 1.3, 1.3, 1.3, 1.3], [1.7, 1.1, 1.2, 0.9, 1.7], [1.0, 0.5, 1.9, 1.4, 1.96]):
+        s_c, s_e, s_eps, s_q, s_nu = rates
+        S = np.diag([s_c, s_e, s_eps, s_c, s_q, s_c, s_q, s_nu, s_nu])
+        A = Minv @ S @ M
+        for _ in range(20):
+            v = rng.standard_normal(9)
+            w = np.zeros(9)
+            L.host_check_mrt9(_dp(v), _dp(np.asarray(rates, dtype=np.float64)), _dp(w))
+            assert np.max(np.abs(w - A @ v)) < 5e-15 * np.max(np.abs(v))
+            if len(set(rates)) == 1:
+                assert np.max(np.abs(w - rates[0] * v)) < 5e-15 * np.max(np.abs(v))
