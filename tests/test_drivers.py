@@ -150,3 +150,20 @@ def test_driver_parses_shipped_config(problem, expect):
     assert r.returncode == 1 and "no CUDA device" in r.stderr
     for e in expect:
         assert e in r.stdout, (problem, e, r.stdout)
+
+
+def test_driver_accepts_the_mrt_keys(tmp_path):
+    """`collision MRT` + rates are optional keys of this library's HCZ D2Q9 drivers (absent from the reference's files); checked
+    on the banner printed before the device is touched"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("would run the case on a GPU box (covered by tests/test_gpu_zx_hcz_mrt.py)")
+    cfg = tmp_path / "cfg"
+    cfg.mkdir()
+    (cfg / "config_rayleighTaylor2D.txt").write_text(
+        "# skipped\nRe 3000\nulb 0.04\nN 32\nmax_t 0.1\nout_freq 100\nvtk_freq 0\nphi_l 0.251\nphi_g 0.024\nrho_l 0.12\nrho_g 0.04\n"
+        "a 4\nb 4\nkappa 0.01\ngravity -6.25e-6\ncollision MRT\ns_e 1.8\n")
+    r = subprocess.run([_exe(), "rayleighTaylor2D", str(cfg)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr
+    assert "collision = MRT  s_e = 1.8  s_eps = 1.99489  s_q = 1.99489" in r.stdout
+    assert "unknown parameter" not in r.stderr
