@@ -72,6 +72,8 @@ int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end, int x2_begin, in
 int sc_collide_slab(clbm_ctx *c);
 int hcz2d_stage0(clbm_ctx *c);
 int hcz2d_stage1(clbm_ctx *c);
+bool hcz2d_fused_eligible(const clbm_ctx *c);                      // hcz2d_fused.cu
+int hcz2d_fused_range(clbm_ctx *c, int x_begin, int x_end);
 int hcz3d_moments(clbm_ctx *c);
 int hcz3d_stage1(clbm_ctx *c);
 
@@ -98,10 +100,26 @@ int model_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
     return CLBM_EINVAL;
 }
 
+// The overlap protocol needs x-range launches of the collide kernel: the TMA Shan-Chen kernel and the fused HCZ D2Q9 kernel
+// have them.  D = number of boundary planes per side whose stencils reach into the neighbour slab (= the halo depth of the
+// moment exchange: psi depth 1, phi depth 2).
 static bool overlap_supported(const clbm_ctx *c)
 {
     const int m = c->prm.model;
-    return c->multi && c->geo.nx >= 3 && (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) && sc_range_supported(c);
+    if (!c->multi) return false;
+    if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) return c->geo.nx >= 3 && sc_range_supported(c);
+    if (m == CLBM_MODEL_HCZ_D2Q9) return c->geo.nx >= 4 && c->prm.fused && hcz2d_fused_eligible(c);
+    return false;
+}
+static int overlap_depth(const clbm_ctx *c) { return c->prm.model == CLBM_MODEL_HCZ_D2Q9 ? 2 : 1; }
+static int overlap_moments(clbm_ctx *c) { return c->prm.model == CLBM_MODEL_HCZ_D2Q9 ? hcz2d_stage0(c) : sc_psi_boundary(c); }
+// collide + push of [x_begin, x_end) and, when non-empty, [x2_begin, x2_end)
+static int overlap_collide(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
+{
+    if (c->prm.model != CLBM_MODEL_HCZ_D2Q9) return sc_collide_range_fused(c, x_begin, x_end, x2_begin, x2_end);
+    int rc = hcz2d_fused_range(c, x_begin, x_end);
+    if (rc || x2_end <= x2_begin) return rc;
+    return hcz2d_fused_range(c, x2_begin, x2_end);
 }
 
 static int ensure_boundary_stream(clbm_ctx *c)
@@ -124,35 +142,36 @@ struct BoundaryStream {
     ~BoundaryStream() { c->stream = saved; }
 };
 
-// Overlap protocol of one slab step (stages 10, 11, 12; include/clbm.h): the interior planes [1, nx-1) need nothing
-// from the neighbours (their psi stencil reads the slab's own populations), so they are collided on the launching
-// stream while the boundary stream moves the moment halo, collides the two boundary planes and moves the crossing
-// populations.  Interior and boundary launches write disjoint (node, direction) slots of the out buffer.
+// Overlap protocol of one slab step (stages 10, 11, 12; include/clbm.h): the interior planes [D, nx-D) need nothing
+// from the neighbours (their stencils read the slab's own populations: D = 1 for the psi stencil, 2 for the phi chain of
+// HCZ D2Q9), so they are collided on the launching stream while the boundary stream moves the moment halo, collides the
+// 2 D boundary planes and moves the crossing populations.  Interior and boundary launches write disjoint (node, direction)
+// slots of the out buffer.
 static int overlap_stage(clbm_ctx *c, int stage)
 {
     if (!overlap_supported(c)) { set_error("overlap protocol not available for this context (use stages 0-2)"); return CLBM_ESTATE; }
     int rc;
-    const int nx = c->geo.nx;
+    const int nx = c->geo.nx, D = overlap_depth(c);
     if ((rc = ensure_boundary_stream(c))) return rc;
     if (stage == 10) {
         {   // the boundary planes of the "in" buffer were completed by the previous step's interior launch too
             CLBM_CUDA(cudaStreamWaitEvent(c->stream_b, c->ev_main, 0));
             BoundaryStream bs(c);
-            if ((rc = sc_psi_boundary(c))) return rc;
+            if ((rc = overlap_moments(c))) return rc;
             if ((rc = halo_pack(c, 0))) return rc;
             // the interior launch fills every SM for the rest of the step: let these two small kernels through first
             // (they run in ~20 us on the idle GPU; behind the interior's first wave they took 350 us)
             CLBM_CUDA(cudaEventRecord(c->ev_b, c->stream_b));
         }
         CLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
-        if ((rc = sc_collide_range_fused(c, 1, nx - 1, 0, 0))) return rc;
+        if ((rc = overlap_collide(c, D, nx - D, 0, 0))) return rc;
         CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
         return 0;
     }
     if (stage == 11) {
         BoundaryStream bs(c);
         if ((rc = halo_unpack(c, 0))) return rc;
-        if ((rc = sc_collide_range_fused(c, 0, 1, nx - 1, nx))) return rc;   // both boundary planes in one launch
+        if ((rc = overlap_collide(c, 0, D, nx - D, nx))) return rc;   // SC: both boundary planes in one launch
         c->parity = 1 - c->parity;
         return halo_pack(c, 1);
     }

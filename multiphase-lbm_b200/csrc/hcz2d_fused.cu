@@ -85,7 +85,7 @@ CLBM_D void ring_grad(const double (*R)[NT], const uint8_t (*FL)[NT], unsigned w
 template <int NT, int MINB, bool MRT = false>
 __global__ void __launch_bounds__(NT, MINB)
 hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const double *__restrict__ phi_g, Geom g,
-                   ModelParams mp, int xchunk)
+                   ModelParams mp, int xchunk, int x_begin, int x_end)
 {
     constexpr int NS = HCZ2D_NS;
     __shared__ double r_phi[NS][NT], r_rho[NS][NT], r_pp[NS][NT], r_pr[NS][NT], r_lap[NS][NT];
@@ -102,8 +102,10 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
     const bool has_phi = yy <= ny + 1;
     const bool has_lap = tid >= 1 && tid < NT - 1 && yy <= ny;
     const bool own = tid >= 2 && tid < NT - 2 && yy < ny;
-    const int xa = blockIdx.y * xchunk;
-    const int xb = min(g.nx, xa + xchunk);
+    // columns [x_begin, x_end) of the slab: the whole slab, or one of the ranges of the overlap protocol (boundary columns /
+    // interior) -- a column is collided by exactly one launch, and a (node, direction) slot is written by exactly one column
+    const int xa = x_begin + blockIdx.y * xchunk;
+    const int xb = min(x_end, xa + xchunk);
 
     auto slot_of = [](int xg) { return (xg + 2 * NS) % NS; };
     auto col_of = [&](int xg) { return (g.wx(xg) + G) * ny + yw; };   // storage index of (xg, this row)
@@ -366,18 +368,20 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
 }
 
 template <int NT, int MINB, bool MRT = false>
-static int launch_hcz2d_fused(clbm_ctx *c)
+static int launch_hcz2d_fused(clbm_ctx *c, int x_begin, int x_end)
 {
     const Geom &g = c->geo;
+    const int ncol = x_end - x_begin;
+    if (ncol <= 0) return 0;
     const int segs = (g.ny + (NT - 4) - 1) / (NT - 4);
     // short x-chunks keep concurrently resident CTAs on neighbouring columns (L2 locality of the overlapping segment
     // rows): 48-64 columns measured best at 2048 x 8194 (14.1 vs 12.5 GLUPS at 128 and 9.6 at 512)
-    int xchunk = g.nx < 48 ? g.nx : 48;
+    int xchunk = ncol < 48 ? ncol : 48;
     // small lattices (BASELINE configs[1], 256 x 1026): shorter chunks until there are two CTAs per SM slot
     const long long want = 2LL * 148 * MINB;
-    while (xchunk > 8 && (long long)segs * ((g.nx + xchunk - 1) / xchunk) < want) xchunk /= 2;
-    if (const char *e = getenv("CLBM_HCZ2D_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
-    dim3 grid(segs, (g.nx + xchunk - 1) / xchunk);
+    while (xchunk > 8 && (long long)segs * ((ncol + xchunk - 1) / xchunk) < want) xchunk /= 2;
+    if (const char *e = getenv("CLBM_HCZ2D_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < ncol ? v : ncol; }
+    dim3 grid(segs, (ncol + xchunk - 1) / xchunk);
     Hcz2dTables P;
     for (int k = 0; k < 9; ++k) {
         P.fin[k] = c->pop[0][c->parity] + (size_t)k * g.ncs;
@@ -386,24 +390,27 @@ static int launch_hcz2d_fused(clbm_ctx *c)
         P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "hcz2d_fused_collide_stream", true);
-    hcz2d_fused_kernel<NT, MINB, MRT><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
+    hcz2d_fused_kernel<NT, MINB, MRT><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk, x_begin, x_end);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
 
 bool hcz2d_fused_eligible(const clbm_ctx *c) { return c->geo.ny >= 4 && c->geo.ncs < (1LL << 31); }
 
-int hcz2d_fused_launch(clbm_ctx *c)
+// collide + push of the columns [x_begin, x_end) of this slab (the whole slab, or a range of the overlap protocol)
+int hcz2d_fused_range(clbm_ctx *c, int x_begin, int x_end)
 {
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (const char *e = getenv("CLBM_HCZ2D_TILE")) variant = atoi(e);
-    if (c->prm.collision == CLBM_COLLISION_MRT) return launch_hcz2d_fused<128, 3, true>(c);   // 168 registers: no spills
+    if (c->prm.collision == CLBM_COLLISION_MRT) return launch_hcz2d_fused<128, 3, true>(c, x_begin, x_end);   // 168 registers: no spills
     switch (variant) {
-    case 2: return launch_hcz2d_fused<64, 8>(c);
-    case 3: return launch_hcz2d_fused<96, 4>(c);
-    case 4: return launch_hcz2d_fused<128, 3>(c);
-    default: return launch_hcz2d_fused<128, 4>(c);   // 128 registers, 16 warps per SM: best of the sweep at 2048 x 8194 with the cp.async staging
+    case 2: return launch_hcz2d_fused<64, 8>(c, x_begin, x_end);
+    case 3: return launch_hcz2d_fused<96, 4>(c, x_begin, x_end);
+    case 4: return launch_hcz2d_fused<128, 3>(c, x_begin, x_end);
+    default: return launch_hcz2d_fused<128, 4>(c, x_begin, x_end);   // 128 registers, 16 warps per SM: best of the sweep at 2048 x 8194 with the cp.async staging
     }
 }
+
+int hcz2d_fused_launch(clbm_ctx *c) { return hcz2d_fused_range(c, 0, c->geo.nx); }
 
 }  // namespace clbm
