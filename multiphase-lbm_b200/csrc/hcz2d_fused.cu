@@ -389,7 +389,7 @@ static int launch_hcz2d_fused(clbm_ctx *c, int x_begin, int x_end)
         P.fout[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
         P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
     }
-    LaunchScope ls(c, "hcz2d_fused_collide_stream", true);
+    LaunchScope ls(c, "hcz2d_fused_collide_stream", ncol * 2 >= g.nx);   // the boundary-column launches of the overlap protocol are not the dominant kernel
     hcz2d_fused_kernel<NT, MINB, MRT><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk, x_begin, x_end);
     CLBM_CUDA(cudaGetLastError());
     return 0;
