@@ -218,6 +218,17 @@ void *clbm_stream(clbm_ctx *ctx);
 int  clbm_overlap_supported(const clbm_ctx *ctx);
 void *clbm_boundary_stream(clbm_ctx *ctx);
 
+/* ---- the ring driven from the library (one process per GPU, NCCL send/recv on the library's own streams) ----
+ * The caller only transports a 128-byte ncclUniqueId once: rank 0 calls clbm_comm_unique_id, broadcasts the bytes by any
+ * means (MPI, torch.distributed, a file), every rank calls clbm_comm_init on its slab context.  clbm_slab_step(ctx, n)
+ * then runs n slab steps -- stages, both ghost exchanges, the overlap protocol where clbm_overlap_supported() -- without
+ * returning to the caller and without a host synchronisation; every rank must call it with the same n.  NCCL is
+ * resolved at run time (libnccl.so.2), libclbm.so does not link it.  nranks >= 2 (a single slab needs no ring). */
+int  clbm_comm_unique_id(void *id128);
+int  clbm_comm_init(clbm_ctx *ctx, const void *id128, int rank, int nranks);
+int  clbm_slab_step(clbm_ctx *ctx, int nsteps);
+int  clbm_comm_destroy(clbm_ctx *ctx);
+
 /* ---- compliant-vessel case (CLBM_MODEL_PULSATILE) ---------------------------------------------------
  * Replaces the whole iteration body of PulsatileBloodFlow2D() ("Abbashub LBM/apps/PulsatileBloodFlow2D.h":764-790):
  *     for_each(par_unseq, lattice, lattice + nelem, lbm);   // MRT_Collision           :533-541, :672-676

@@ -19,7 +19,7 @@ EXPORTS = [
     "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_download_lattice",
     "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_diag_contact_angle", "clbm_diag_interface_heights", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
-    "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
+    "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_comm_unique_id", "clbm_comm_init", "clbm_slab_step", "clbm_comm_destroy", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
     "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
     "clbm_pulsatile_kernel_timing_begin", "clbm_pulsatile_kernel_timing_end", "clbm_pulsatile_download_fields",
@@ -77,6 +77,10 @@ def load_library(path=None):
     lib.clbm_boundary_stream.argtypes = [vp]
     lib.clbm_boundary_stream.restype = vp
     lib.clbm_overlap_supported.argtypes = [vp]
+    lib.clbm_comm_unique_id.argtypes = [vp]
+    lib.clbm_comm_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    lib.clbm_slab_step.argtypes = [vp, ctypes.c_int]
+    lib.clbm_comm_destroy.argtypes = [vp]
     ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
     lib.clbm_pulsatile_create.argtypes = [ctypes.POINTER(P.PulsatileParams), ctypes.POINTER(vp)]
     lib.clbm_pulsatile_destroy.argtypes = [vp]
@@ -267,6 +271,21 @@ class Lattice:
 
     def stream(self):
         return self.lib.clbm_stream(self._h)
+
+    # -- the ring driven from the library (slab_comm.cu)
+    def comm_unique_id(self):
+        """128 bytes of a fresh ncclUniqueId (rank 0 calls this and broadcasts the bytes)"""
+        buf = ctypes.create_string_buffer(128)
+        self._check(self.lib.clbm_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, id128, rank, nranks):
+        assert len(id128) == 128
+        self._check(self.lib.clbm_comm_init(self._h, ctypes.c_char_p(id128), int(rank), int(nranks)))
+
+    def slab_step(self, n=1):
+        """n slab steps (stages + both ghost exchanges) inside the library; every rank calls it with the same n"""
+        self._check(self.lib.clbm_slab_step(self._h, int(n)))
 
     def overlap_supported(self):
         return bool(self.lib.clbm_overlap_supported(self._h))

@@ -278,6 +278,9 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->kname = "";
     c->stage = nullptr;
     c->stage_bytes = 0;
+    c->comm = nullptr;
+    c->comm_rank = 0;
+    c->comm_size = 0;
     c->nfld = 0;
     for (auto &s : c->pop) for (auto &b : s) b = nullptr;
     for (auto &f : c->fld) f = nullptr;
@@ -328,6 +331,7 @@ int clbm_destroy(clbm_ctx *c)
 {
     if (!c) return CLBM_OK;
     cudaSetDevice(c->device);
+    clbm_comm_destroy(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &s : c->pop) for (auto &b : s) if (b) cudaFree(b);
     for (auto &f : c->fld) if (f) cudaFree(f);

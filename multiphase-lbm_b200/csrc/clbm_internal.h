@@ -101,6 +101,9 @@ struct clbm_ctx {
     // halo buffers: [phase][side][send=0/recv=1]
     void *halo[3][2][2];
     size_t halo_bytes[3];
+    // library-driven ring (slab_comm.cu): ncclComm_t of this rank, its rank and the ring size (0 = no communicator)
+    void *comm;
+    int comm_rank, comm_size;
     // staging for host<->device slab transfers (pinned), grown on demand
     void *stage;
     size_t stage_bytes;

@@ -14,6 +14,8 @@ The exchange itself is plumbing: `LocalRing` moves the buffers between several c
 process (single-GPU emulation of R ranks, used by the GPU tests), `DistRing` uses torch.distributed
 point-to-point operations (NCCL on GPUs; gloo in the CPU tests with host buffers).
 """
+import os
+
 import numpy as np
 
 
@@ -144,10 +146,17 @@ class DistRing:
     DEVICE: `req.wait()` on an NCCL work object makes the current stream wait, not the host.  A slab step therefore
     never synchronises with the host; the step loop runs ahead of the GPU like the single-slab one."""
 
-    def __init__(self, lattice, rank, nranks, device):
+    def __init__(self, lattice, rank, nranks, device, native=None):
         import torch
         import torch.distributed as dist
         self.lat, self.rank, self.R, self.dist, self.torch = lattice, rank, nranks, dist, torch
+        # native ring (csrc/slab_comm.cu): the step loop, the stages and the ncclSend/ncclRecv groups all run inside the
+        # library; torch.distributed only carries the 128-byte ncclUniqueId once.  Opt-in (CLBM_SLAB_NATIVE=1) until it has
+        # been measured on a multi-GPU box: it exists because a slab step of BASELINE configs[2] (256 columns per GPU, a
+        # 0.17 ms kernel) is host-launch bound when the five calls per step are issued from Python.
+        if native is None:
+            native = os.environ.get("CLBM_SLAB_NATIVE", "0") == "1"
+        self.native = bool(native) and device.type == "cuda" and nranks > 1
         self.dev = device
         self._v = {}
         for phase in range(3):
@@ -192,7 +201,22 @@ class DistRing:
         self.lat.halo_unpack(2)
         self.lat.sync()
 
+    def _init_native(self):
+        torch, dist = self.torch, self.dist
+        t = torch.zeros(128, dtype=torch.uint8, device=self.dev)
+        if self.rank == 0:
+            t.copy_(torch.frombuffer(bytearray(self.lat.comm_unique_id()), dtype=torch.uint8))
+        if self.R > 1:
+            dist.broadcast(t, 0)
+        self.lat.comm_init(bytes(t.cpu().numpy().tobytes()), self.rank, self.R)
+        self._native_ready = True
+
     def step(self, n=1, overlap=None):
+        if self.native and overlap is None:
+            if not getattr(self, "_native_ready", False):
+                self._init_native()
+            self.lat.slab_step(n)
+            return
         if self.overlap if overlap is None else (overlap and self.overlap):
             for _ in range(n):
                 self.lat.step_stage(10)         # boundary moments + pack | interior collide on the launching stream

@@ -63,3 +63,20 @@ def test_no_cpu_fallback():
 def test_missing_extension_fails_loudly(tmp_path):
     with pytest.raises(pkg.clbm.ClbmError):
         pkg.clbm.load_library(str(tmp_path / "libclbm.so"))
+
+
+def test_library_driven_ring_entry_points_fail_cleanly():
+    """clbm_comm_* / clbm_slab_step (csrc/slab_comm.cu): NCCL is resolved at run time, bad arguments are rejected before any
+    device or NCCL call, nothing crashes in a container without a GPU"""
+    lib = pkg.clbm.load_library()
+    buf = ctypes.create_string_buffer(128)
+    rc = lib.clbm_comm_unique_id(buf)
+    assert rc in (0, -5, -3)                 # ok, or "NCCL not found" / an NCCL error, reported through clbm_last_error
+    if rc == 0:
+        assert any(b != 0 for b in buf.raw)
+    else:
+        assert lib.clbm_last_error()
+    assert lib.clbm_comm_unique_id(None) == -1
+    assert lib.clbm_slab_step(None, 1) == -1
+    assert lib.clbm_comm_init(None, buf, 0, 2) == -1
+    assert lib.clbm_comm_destroy(None) == 0

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Multi-GPU slab check (run under torchrun, one rank per GPU):
 every rank advances its x-slab over NCCL (DistRing); rank 0 also advances the whole lattice on its own GPU and
-compares the gathered populations bit-for-bit.   torchrun --nproc-per-node N tools/slab_check.py"""
+compares the gathered populations bit-for-bit.   torchrun --nproc-per-node N tools/slab_check.py [--native]
+--native: the ring driven from the library (clbm_slab_step, csrc/slab_comm.cu) instead of slab.DistRing's Python loop;
+also prints the device time per step of both so that the host-overhead difference is visible."""
 import os
 import sys
 
@@ -35,7 +37,7 @@ def main():
         sp.device = lr
         lat = clbm.Lattice(sp)
         lat.init_case(case, args)
-        ring = slab.DistRing(lat, rank, world, dev)
+        ring = slab.DistRing(lat, rank, world, dev, native="--native" in sys.argv)
         ring.step(steps)
         pops = torch.from_numpy(lat.in_pops()).to(dev)          # [sets, Q, nelem_local]
         sizes = [b[1] - b[0] for b in slab.slab_bounds(prm.nx_global, world)]
