@@ -377,9 +377,11 @@ static int launch_hcz2d_fused(clbm_ctx *c, int x_begin, int x_end)
     // short x-chunks keep concurrently resident CTAs on neighbouring columns (L2 locality of the overlapping segment
     // rows): 48-64 columns measured best at 2048 x 8194 (14.1 vs 12.5 GLUPS at 128 and 9.6 at 512)
     int xchunk = ncol < 48 ? ncol : 48;
-    // small lattices (BASELINE configs[1], 256 x 1026): shorter chunks until there are two CTAs per SM slot
+    // small lattices (BASELINE configs[1], 256 x 1026) are L2 resident and latency bound: shorter chunks until there are two
+    // CTAs per SM slot, down to 4 columns (tools/small_lattice_chunks.py at 256 x 1026, bit-identical populations: 29.9 us per
+    // step at 8 columns, 24.5 at 4, 26.4 at 2, 31.9 at 1 -- the 4-column prologue of this kernel costs more than the SC one)
     const long long want = 2LL * 148 * MINB;
-    while (xchunk > 8 && (long long)segs * ((ncol + xchunk - 1) / xchunk) < want) xchunk /= 2;
+    while (xchunk > 4 && (long long)segs * ((ncol + xchunk - 1) / xchunk) < want) xchunk = xchunk / 2 > 4 ? xchunk / 2 : 4;
     if (const char *e = getenv("CLBM_HCZ2D_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < ncol ? v : ncol; }
     dim3 grid(segs, (ncol + xchunk - 1) / xchunk);
     Hcz2dTables P;

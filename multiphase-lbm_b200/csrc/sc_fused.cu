@@ -188,7 +188,12 @@ static int launch_fused(clbm_ctx *c)
     if ((long long)tiles * ((g.nx + xchunk - 1) / xchunk) < want) {
         const long long nch = (want + tiles - 1) / tiles;
         xchunk = (int)((g.nx + nch - 1) / nch);
-        if (xchunk < 8) xchunk = g.nx < 8 ? g.nx : 8;
+        // Lattices this small are L2 resident and LATENCY bound: a CTA marches its chunk serially, so shorter chunks mean
+        // more CTAs in flight; the extra prologue planes are L2 hits.  D2Q9 single slab, measured at 256 x 256
+        // (tools/small_lattice_chunks.py, bit-identical populations): 18.4 us per step at 8 columns, 12.3 at 4, 10.1 at 2,
+        // 8.2 at 1 (the staged kernels: 10.2).  Other paths keep the 8-plane floor they were measured with.
+        const int floor_ = (L::D == 2 && !c->multi) ? 1 : 8;
+        if (xchunk < floor_) xchunk = g.nx < floor_ ? g.nx : floor_;
     }
     if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
