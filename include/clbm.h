@@ -39,7 +39,8 @@
 extern "C" {
 #endif
 
-#define CLBM_ABI_VERSION 3 /* 3: + CLBM_SC_FORCE_EXPGUO, CLBM_CASE_SC_RT2D, clbm_diag_* (the struct layouts are those of version 2) */
+#define CLBM_ABI_VERSION 3 /* 3: + CLBM_SC_FORCE_EXPGUO, CLBM_CASE_SC_RT2D, clbm_diag_*, clbm_comm_* / clbm_slab_step; clbm_params grew at
+                              its END (s_e, s_eps, s_q, collision, reserved0): a version-2 block zero-extended is a valid BGK block */
 
 /* ---- models (one per reference functor family) -------------------------- */
 #define CLBM_MODEL_SC_D2Q9    0 /* LBM_Laplace2D / LBM_contactAngle2D (Yuan-CS Shan-Chen) */
