@@ -60,7 +60,7 @@ extern "C" {
 
 /* collision operator, `collision` member */
 #define CLBM_COLLISION_BGK 0
-#define CLBM_COLLISION_MRT 1 /* HCZ D2Q9 only; BASELINE.json configs[1-2] ask for MRT, the reference functor is BGK:
+#define CLBM_COLLISION_MRT 1 /* HCZ D2Q9 and Yuan-CS Shan-Chen D2Q9 (not CLBM_SC_FORCE_EXPGUO); BASELINE.json configs[1-2] ask for MRT, the reference functor is BGK:
                                 parity of this operator is UNPINNED against the reference, pinned to BGK at S = omega I */
 
 /* HCZ D2Q9 force variant, carried in the same `sc_force` member */
@@ -122,9 +122,10 @@ typedef struct clbm_params {
     /* HCZ layered variant (LBM_twoLayeredPF2D members gx, Gx_const, PF/apps/twoLayeredFlow2D.h:127-128); gx is shared */
     double gx_const;
     /* collision operator (appended in ABI version 3; zero-initialised = BGK, the only operator the reference's SC / HCZ
-     * functors have).  CLBM_COLLISION_MRT, HCZ D2Q9 only: relaxation in the moment basis of CooLBM_MRT_combustion.cpp:313-323
+     * functors have).  CLBM_COLLISION_MRT, HCZ D2Q9 and Shan-Chen D2Q9: relaxation in the moment basis of CooLBM_MRT_combustion.cpp:313-323
      * (rho, e, eps, jx, qx, jy, qy, pxx, pxy), rates S = (omega, s_e, s_eps, omega, s_q, omega, s_q, omega, omega) for BOTH
-     * population sets, forcing term relaxed with (I - S/2) (the form of :2441, :2466).  s_e = s_eps = s_q = omega is BGK. */
+     * population sets, HCZ forcing term relaxed with (I - S/2) (the form of :2441, :2466); Shan-Chen keeps its tau-shifted
+     * equilibrium velocity (tau = 1/omega) and relaxes f - f_eq.  s_e = s_eps = s_q = omega is BGK. */
     double s_e, s_eps, s_q;
     int32_t collision;      /* CLBM_COLLISION_* */
     int32_t reserved0;

@@ -57,6 +57,21 @@ struct Config {
     }
 };
 
+// Optional keys of this library, absent from the reference's config files: `collision MRT` selects the moment-space
+// collision operator (include/clbm.h, CLBM_COLLISION_MRT: HCZ D2Q9 and Yuan-CS Shan-Chen D2Q9), `s_e`, `s_eps`, `s_q` are
+// its free rates (default: omega, which is the BGK operator evaluated in moment space).
+inline void apply_collision_keys(Config &cfg, clbm_params &p, double omega)
+{
+    if (!cfg.has("collision")) return;
+    cfg.used["collision"] = true;
+    const std::string v = cfg.kv["collision"];
+    if (!(v == "MRT" || v == "mrt" || v == "1")) return;
+    const double s_e = cfg.d("s_e", -1), s_eps = cfg.d("s_eps", -1), s_q = cfg.d("s_q", -1);
+    p.collision = CLBM_COLLISION_MRT;
+    p.s_e = s_e > 0 ? s_e : omega; p.s_eps = s_eps > 0 ? s_eps : omega; p.s_q = s_q > 0 ? s_q : omega;
+    std::cout << "collision = MRT  s_e = " << p.s_e << "  s_eps = " << p.s_eps << "  s_q = " << p.s_q << "  (s_nu = omega)\n";
+}
+
 struct LbParameters { double nu, omega, dx, dt; };
 inline LbParameters lb_parameters(double ulb, int lref, double Re)
 {

@@ -48,6 +48,7 @@ inline void contactAngle2D(const std::string &config_dir)
     const double Tc = 0.3773 * a / (b * R);
     prm.omega = omega; prm.gravity = gravity; prm.rho_w = rho_w; prm.a = a; prm.b = b; prm.R = R; prm.TT = TT0 * Tc;
     prm.sc_force = CLBM_SC_FORCE_CONTACT;
+    apply_collision_keys(cfg, prm, omega);
     std::cout << std::setprecision(6) << "CS params: a=" << a << " b=" << b << " R=" << R << "\n"
               << "TT0 (reduced)=" << TT0 << "  Tc=" << Tc << "  TT (abs)=" << prm.TT << "\n"
               << "rho_l=" << rhol << "  rho_g=" << rhog << "  rho_w=" << rho_w << "  RR=" << RR << "\n"

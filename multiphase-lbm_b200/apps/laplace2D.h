@@ -49,6 +49,7 @@ inline void Laplace2D(const std::string &config_dir)
     prm.omega = omega; prm.gravity = gravity; prm.rho_w = rho_w; prm.a = a; prm.b = b; prm.R = R;
     prm.TT = TT0 * (0.3773 * a / (b * R));          // Yuan: TT = TT0 * Tc
     prm.sc_force = CLBM_SC_FORCE_LAPLACE;
+    apply_collision_keys(cfg, prm, omega);
     DeviceLattice lat(prm);
     lat.init_case(CLBM_CASE_SC_LAPLACE2D, {rhol, rhog, 10.0});   // iniLattice + inigeom (periodic everywhere)
 

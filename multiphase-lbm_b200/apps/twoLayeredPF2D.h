@@ -29,16 +29,7 @@ inline void twoLayeredPF2D(const std::string &config_dir)
     clbm_params prm = default_params(CLBM_MODEL_HCZ_D2Q9, nx, ny, 1);
     prm.omega = omega; prm.phi_l = phi_l; prm.phi_g = phi_g; prm.rho_l = rho_l; prm.rho_g = rho_g; prm.a = a; prm.b = b; prm.kappa = kappa;
     prm.sc_force = CLBM_HCZ_FORCE_LAYERED; prm.gx = gx; prm.gx_const = Gx_const;
-    if (cfg.has("collision")) {   // optional key of this library (include/clbm.h, CLBM_COLLISION_MRT); rates default to omega = BGK
-        cfg.used["collision"] = true;
-        const std::string v = cfg.kv["collision"];
-        if (v == "MRT" || v == "mrt" || v == "1") {
-            const double s_e = cfg.d("s_e", -1), s_eps = cfg.d("s_eps", -1), s_q = cfg.d("s_q", -1);
-            prm.collision = CLBM_COLLISION_MRT;
-            prm.s_e = s_e > 0 ? s_e : omega; prm.s_eps = s_eps > 0 ? s_eps : omega; prm.s_q = s_q > 0 ? s_q : omega;
-            std::cout << "collision = MRT  s_e = " << prm.s_e << "  s_eps = " << prm.s_eps << "  s_q = " << prm.s_q << "  (s_nu = omega)\n";
-        }
-    }
+    apply_collision_keys(cfg, prm, omega);
     DeviceLattice lat(prm);
     lat.init_case(CLBM_CASE_HCZ_LAYERED2D, {h_lower, (double)w_int});
 

@@ -234,8 +234,9 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
         return CLBM_EINVAL;
     }
     if (p->collision != CLBM_COLLISION_BGK) {
-        if (p->collision != CLBM_COLLISION_MRT || p->model != CLBM_MODEL_HCZ_D2Q9) {
-            set_error("collision operator %d: only BGK (0) everywhere and MRT (1) for HCZ D2Q9 exist", p->collision);
+        const bool sc2_yuan = p->model == CLBM_MODEL_SC_D2Q9 && p->sc_force != CLBM_SC_FORCE_EXPGUO;
+        if (p->collision != CLBM_COLLISION_MRT || !(p->model == CLBM_MODEL_HCZ_D2Q9 || sc2_yuan)) {
+            set_error("collision operator %d: only BGK (0) everywhere and MRT (1) for HCZ D2Q9 and Yuan-CS Shan-Chen D2Q9 exist", p->collision);
             return CLBM_EINVAL;
         }
         const double r[3] = {p->s_e, p->s_eps, p->s_q};

@@ -16,6 +16,7 @@
 #pragma once
 #include "clbm_internal.h"
 #include "moments.cuh"
+#include "mrt.cuh"
 
 namespace clbm {
 
@@ -150,6 +151,34 @@ template <class L>
 CLBM_D void sc_collide(const ModelParams &mp, const double *f, ScForceSums &s, double psi_c, bool g1_pos, double *out)
 {
     sc_collide_rho<L>(mp, f, s, Mom<L>::sum(f), psi_c, g1_pos, out);
+}
+
+// MRT relaxation of the Yuan-CS Shan-Chen collision (clbm_params.collision = CLBM_COLLISION_MRT, D2Q9): the same tau-shifted
+// equilibrium velocity u + tau F / rho with tau = 1/omega as sc_collide_rho, relaxed in the moment basis of mrt.cuh:
+//   out = f - M^-1 S M (f - eq),   S = (omega, s_e, s_eps, omega, s_q, omega, s_q, omega, omega);  S = omega I is BGK.
+// The reference's Shan-Chen functors are BGK only: parity of this operator is unpinned against the reference.
+template <class L>
+CLBM_D void sc_collide_mrt(const ModelParams &mp, const double *f, ScForceSums &s, double rho_raw, double psi_c, bool g1_pos, double *out)
+{
+    static_assert(L::Q == 9, "the MRT operator exists for D2Q9");
+    const double rho = fmax(rho_raw, 1e-14);
+    const double inv = fast_rcp(rho);
+    double jx, jy, jz, F[3];
+    Mom<L>::first(f, jx, jy, jz);
+    sc_force<L>(mp, s, rho_raw, psi_c, g1_pos, F);
+    const double ux = (jx + mp.tau * F[0]) * inv;
+    const double uy = (jy + mp.tau * F[1]) * inv;
+    const double base = 1.0 - 1.5 * (ux * ux + uy * uy);
+    double v[9], w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double cu = cdot<L>(k, ux, uy, 0.0);
+        v[k] = f[k] - rho * L::t(k) * (base + 3.0 * cu + 4.5 * cu * cu);
+    }
+    const MrtRates S = {mp.omega, mp.s_e, mp.s_eps, mp.s_q, mp.omega};
+    mrt9_relax(v, S, w);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k] = f[k] - w[k];
 }
 
 // output fields of one bulk node: pressure_node (laplace2D.h:308-315) and u_actual (:252-257)

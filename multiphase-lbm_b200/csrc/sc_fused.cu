@@ -36,7 +36,8 @@ template <class L> struct PopTable {
 
 // GUO = true: the Rayleigh-Taylor variant (SC/apps/RayleighTaylor2D.h; psi = 1 - exp(-rho), a wall neighbour
 // contributes the psi of the opposite neighbour, Guo forcing) -- a compile-time flag, the Yuan-CS code is unchanged.
-template <class L, int TY, int TZ, int MINB, bool GUO = false>
+// MRT = true: CLBM_COLLISION_MRT for D2Q9 (sc_collide_mrt), likewise a compile-time flag.
+template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const double *__restrict__ psi_g, Geom g,
                 ModelParams mp, int xchunk)
@@ -153,6 +154,7 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
             }
             double out[L::Q];
             if constexpr (GUO) scrt_collide<L>(mp, fc, s, Mom<L>::sum(fc), psc, out);
+            else if constexpr (MRT) sc_collide_mrt<L>(mp, fc, s, Mom<L>::sum(fc), psc, gpc, out);
             else sc_collide<L>(mp, fc, s, psc, gpc, out);
 
             const int i = (x + G) * plane + yz;
@@ -175,7 +177,7 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
 
 struct FusedChoice { int ty, tz; };
 
-template <class L, int TY, int TZ, int MINB, bool GUO = false>
+template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false>
 static int launch_fused(clbm_ctx *c)
 {
     const Geom &g = c->geo;
@@ -203,7 +205,7 @@ static int launch_fused(clbm_ctx *c)
         P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "sc_fused_collide_stream", true);
-    sc_fused_kernel<L, TY, TZ, MINB, GUO><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
+    sc_fused_kernel<L, TY, TZ, MINB, GUO, MRT><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -240,6 +242,7 @@ int sc_fused_launch(clbm_ctx *c)
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;
     if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO) return launch_fused<D2Q9, 128, 1, 4, true>(c);   // D2Q9 only (clbm_create)
+    if (c->prm.collision == CLBM_COLLISION_MRT) return launch_fused<D2Q9, 128, 1, 3, false, true>(c);   // D2Q9 only (clbm_create)
     if (c->Q == 9) {
         switch (variant) {
         case 1: rc = launch_fused<D2Q9, 256, 1, 2>(c); break;

@@ -34,7 +34,7 @@ sc_psi_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, 
     psi[i] = v;
 }
 
-template <class L, bool GUO = false>
+template <class L, bool GUO = false, bool MRT = false>
 __global__ void __launch_bounds__(256, 2)
 sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const uint8_t *__restrict__ flag,
                   const double *__restrict__ psi, Geom g, ModelParams mp, int x0, long long ncell)
@@ -55,6 +55,7 @@ sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, con
     sc_gather_force<L, GUO>(s, n, flag, psi);
     const double pc = psi[n.i];
     if constexpr (GUO) scrt_collide<L>(mp, f, s, Mom<L>::sum(f), pc, out);
+    else if constexpr (MRT) sc_collide_mrt<L>(mp, f, s, Mom<L>::sum(f), fabs(pc), !signbit(pc), out);
     else sc_collide<L>(mp, f, s, fabs(pc), !signbit(pc), out);
 
 #pragma unroll
@@ -115,7 +116,10 @@ template <class L> static int sc_collide_range(clbm_ctx *c, int x0, int x1)
     const long long n = (long long)(x1 - x0) * c->geo.plane;
     if (n <= 0) return 0;
     LaunchScope ls(c, "sc_collide_stream", true);
-    if (L::D == 2 && is_guo(c))
+    if (L::D == 2 && c->prm.collision == CLBM_COLLISION_MRT)
+        sc_collide_kernel<D2Q9, false, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
+                                                                                     c->fld[0], c->geo, c->mp, x0, n);
+    else if (L::D == 2 && is_guo(c))
         sc_collide_kernel<D2Q9, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
                                                                               c->fld[0], c->geo, c->mp, x0, n);
     else

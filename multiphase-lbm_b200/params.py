@@ -120,6 +120,16 @@ def hcz_mrt_params(nx, ny, *, s_e=None, s_eps=None, s_q=None, **kw):
     return p
 
 
+def sc_mrt_params(nx, ny, *, s_e=None, s_eps=None, s_q=None, **kw):
+    """Yuan-CS Shan-Chen D2Q9 with the MRT collision operator (CLBM_COLLISION_MRT); a rate left at None equals omega"""
+    p = sc_params(MODEL_SC_D2Q9, nx, ny, **kw)
+    p.collision = COLLISION_MRT
+    p.s_e = p.omega if s_e is None else s_e
+    p.s_eps = p.omega if s_eps is None else s_eps
+    p.s_q = p.omega if s_q is None else s_q
+    return p
+
+
 class PulsatileParams(ctypes.Structure):
     """clbm_pulsatile_params mirror (include/clbm.h): the user-set members of LBM_PulsatileBloodFlow2D
     (AB/apps/PulsatileBloodFlow2D.h:740-749)."""

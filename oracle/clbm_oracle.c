@@ -231,6 +231,8 @@ static void sc_psi_field(const clbm_params *p, const sc_eos *e, int D, const dou
     }
 }
 
+static void mrt9_relax(const double v[9], const double S[9], double w[9]);   /* defined with the HCZ D2Q9 model below */
+
 /* one Shan-Chen step: operator() of SC/apps/laplace2D.h:285-306 / contactAngle2D.h:333-355 */
 static void sc_step(const clbm_params *p, int D, const double *fin, double *fout, const uint8_t *flag)
 {
@@ -259,6 +261,26 @@ static void sc_step(const clbm_params *p, int D, const double *fin, double *fout
         double usqr = (D == 2) ? 1.5 * (ueq[0] * ueq[0] + ueq[1] * ueq[1])
                                : 1.5 * (ueq[0] * ueq[0] + ueq[1] * ueq[1] + ueq[2] * ueq[2]);
 
+        if (D == 2 && p->collision == CLBM_COLLISION_MRT) {
+            /* MRT relaxation of the same equilibrium (tau-shifted velocity, tau = 1/omega): out = f - M^-1 S M (f - eq),
+             * S = (omega, s_e, s_eps, omega, s_q, omega, s_q, omega, omega) in the moment basis of
+             * CooLBM_MRT_combustion.cpp:313-347; S = omega I is collideBgk.  No reference implementation: parity unpinned. */
+            const double S[9] = {omega, p->s_e, p->s_eps, omega, p->s_q, omega, p->s_q, omega, omega};
+            double v[9], w[9];
+            for (int k = 0; k < 9; ++k) {
+                const double ck_u = C9[k][0] * ueq[0] + C9[k][1] * ueq[1];
+                v[k] = fin[(size_t)k * ne + i] - rho * T9[k] * (1. + 3. * ck_u + 4.5 * ck_u * ck_u - usqr);
+            }
+            mrt9_relax(v, S, w);
+            for (int k = 0; k < 9; ++k) {
+                const double pop_out = fin[(size_t)k * ne + i] - w[k];
+                if (k == 4) { fout[(size_t)k * ne + i] = pop_out; continue; }
+                int x2 = (iX + C9[k][0] + nx) % nx, y2 = (iY + C9[k][1] + ny) % ny;
+                size_t nb = (size_t)y2 + (size_t)ny * x2;
+                if (flag[nb] == BB) fout[(size_t)OPP9[k] * ne + i] = pop_out; else fout[(size_t)k * ne + nb] = pop_out;
+            }
+            continue;
+        }
         for (int k = 0; k < H; ++k) {
             int cx, cy, cz, ko;
             double tk;

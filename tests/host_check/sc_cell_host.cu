@@ -44,7 +44,7 @@ void psi_field(const Geom &g, const ModelParams &mp, const double *fin, const ui
     }
 }
 
-template <class L, bool GUO>
+template <class L, bool GUO, bool MRT = false>
 void step(const Geom &g, const ModelParams &mp, const double *fin, double *fout, const uint8_t *flag, double *psi)
 {
     psi_field<L, GUO>(g, mp, fin, flag, psi);
@@ -57,7 +57,8 @@ void step(const Geom &g, const ModelParams &mp, const double *fin, double *fout,
         ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
         sc_gather_force<L, GUO>(s, n, flag, psi);
         const double pc = psi[n.i];
-        if (GUO) scrt_collide<L>(mp, f, s, Mom<L>::sum(f), pc, out);
+        if constexpr (GUO) scrt_collide<L>(mp, f, s, Mom<L>::sum(f), pc, out);
+        else if constexpr (MRT) sc_collide_mrt<L>(mp, f, s, Mom<L>::sum(f), fabs(pc), !std::signbit(pc), out);
         else sc_collide<L>(mp, f, s, fabs(pc), !std::signbit(pc), out);
         for (int k = 0; k < L::Q; ++k) {
             if (k == L::REST) { fout[(size_t)k * g.ncs + n.i] = out[k]; continue; }
@@ -106,6 +107,7 @@ extern "C" int host_check_sc_step(const clbm_params *p, double *lattice, const u
         double *fout = lattice + (size_t)(1 - *parity) * npop;
         if (p->model == CLBM_MODEL_SC_D3Q19) step<D3Q19, false>(g, mp, fin, fout, flag, psi.data());
         else if (guo) step<D2Q9, true>(g, mp, fin, fout, flag, psi.data());
+        else if (p->collision == CLBM_COLLISION_MRT) step<D2Q9, false, true>(g, mp, fin, fout, flag, psi.data());
         else step<D2Q9, false>(g, mp, fin, fout, flag, psi.data());
         *parity = 1 - *parity;
     }

@@ -143,3 +143,28 @@ def test_mrt9_factorised_form_equals_the_matrix_form():
             assert np.max(np.abs(w - A @ v)) < 5e-15 * np.max(np.abs(v))
             if len(set(rates)) == 1:
                 assert np.max(np.abs(w - rates[0] * v)) < 5e-15 * np.max(np.abs(v))
+
+
+@pytest.mark.parametrize("case", ["laplace", "contact", "layered"])
+def test_host_cell_functions_sc_mrt(case):
+    """CLBM_COLLISION_MRT for Yuan-CS Shan-Chen D2Q9: the device's sc_collide_mrt (factorised M^-1 S M) against the oracle's
+    matrix form at free rates, and the oracle at S = omega I against its own BGK branch (pinned to the reference)"""
+    if case == "laplace":
+        mk = lambda **k: P.sc_params(P.MODEL_SC_D2Q9, 48, 40, omega=1.2, gravity=-1e-5, **k)
+        cid, args, steps = P.CASE_SC_LAPLACE2D, (0.265, 0.038, 10.0), 300
+    elif case == "contact":
+        mk = lambda **k: P.sc_params(P.MODEL_SC_D2Q9, 48, 24, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT, **k)
+        cid, args, steps = P.CASE_SC_CONTACT2D, (0.265, 0.038, 8.0), 300
+    else:
+        mk = lambda **k: P.sc_layered_params(10, 41, omega=1.1, gx=1e-6, **k)
+        cid, args, steps = P.CASE_SC_LAYERED2D, (0.21, 0.067, 0.3, 4.0), 300
+    bgk = mk()
+    same = bgk.copy(collision=P.COLLISION_MRT, s_e=bgk.omega, s_eps=bgk.omega, s_q=bgk.omega)
+    a = OracleSim(bgk).init_case(cid, args).step(steps)
+    b = OracleSim(same).init_case(cid, args).step(steps)
+    assert rel_linf(b.in_pops(), a.in_pops()) < 1e-12
+    free = bgk.copy(collision=P.COLLISION_MRT, s_e=min(1.9, bgk.omega + 0.3), s_eps=max(0.5, bgk.omega - 0.2), s_q=1.4)
+    f = _compare(free, cid, args, steps)
+    assert np.isfinite(f["ux"]).all()
+    c = OracleSim(free).init_case(cid, args).step(steps)
+    assert rel_linf(c.in_pops(), a.in_pops()) > 1e-8        # the free rates do change the solution
