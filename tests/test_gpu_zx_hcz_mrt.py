@@ -107,7 +107,7 @@ def test_mrt_slab_ring_matches_single_slab(fused):
 
 
 def test_mrt_is_rejected_where_it_does_not_exist():
-    for prm in (P.sc_params(P.MODEL_SC_D2Q9, 16, 16).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=1.0),
+    for prm in (P.sc_params(P.MODEL_SC_D3Q19, 8, 8, 8).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=1.0),
                 P.hcz_params(P.MODEL_HCZ_D3Q19, 8, 8, 8).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=1.0),
                 P.hcz_mrt_params(16, 66, s_e=2.5), P.hcz_mrt_params(16, 66, s_q=0.0).copy(s_q=0.0)):
         with pytest.raises(pkg.clbm.ClbmError):
