@@ -16,6 +16,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstring>
+
 #include "clbm_internal.h"
 
 namespace clbm {
