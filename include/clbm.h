@@ -138,9 +138,15 @@ const char *clbm_last_error(void);
 int  clbm_abi_version(void);
 
 /* ---- state transfer (reference layout, host memory) ---------------------- */
-/* replaces the host-side ownership of lattice/flag/parity: copies the parity-selected
- * "in" buffer of every population set and the mask to the device. */
+/* replaces the host-side ownership of lattice/flag/parity: copies the parity-selected "in" buffer of every population
+ * set, the bounce_back-node values of the other buffer and the mask to the device. */
 int  clbm_upload(clbm_ctx *ctx, const double *lattice, const uint8_t *flag, int parity);
+/* the same with a say on the buffer the parity does NOT select.  Every slot of a bulk node is rewritten by each step, so that
+ * buffer matters only at bounce_back nodes, which keep their initial values for ever: clbm_upload (other_buffer = 1) hands
+ * those node values over too -- the reference's layered HCZ init fills both buffers ("Phase field model/apps/
+ * twoLayeredFlow2D.h":184-187) -- so that clbm_download_lattice later returns the reference's host array at EVERY node.
+ * other_buffer = 0: lattice[] holds valid data only in the selected buffer (the other half may not even be mapped). */
+int  clbm_upload2(clbm_ctx *ctx, const double *lattice, const uint8_t *flag, int parity, int other_buffer);
 /* writes the current populations back into lattice[] (buffer selected by the returned
  * parity; the other buffer is left untouched) so unchanged host accessors keep working. */
 int  clbm_download_lattice(clbm_ctx *ctx, double *lattice, int *parity);
@@ -230,6 +236,28 @@ int  clbm_comm_unique_id(void *id128);
 int  clbm_comm_init(clbm_ctx *ctx, const void *id128, int rank, int nranks);
 int  clbm_slab_step(clbm_ctx *ctx, int nsteps);
 int  clbm_comm_destroy(clbm_ctx *ctx);
+
+/* ---- the ring over CUDA peer memory (the GPUs of one node: NVLink / NVSwitch) -- the default transport -------------
+ * All halo blocks of a context live in one device allocation (the "mailbox").  clbm_peer_export writes an opaque
+ * CLBM_PEER_HANDLE_BYTES-byte handle of it (a cudaIpcMemHandle plus the layout); the caller moves the handles of the two
+ * ring neighbours to every rank by any means (torch.distributed all_gather, MPI, a file) and calls clbm_peer_connect
+ * (left = the rank owning x_offset - 1, right = the rank owning x_offset + nx, periodic; a ring of two passes the same
+ * handle twice).  From then on the pack of a halo phase writes straight into the neighbour's receive block and an exchange
+ * is a flag store + a flag wait on the device; clbm_slab_step replays two captured steps per CUDA graph launch
+ * (CLBM_SLAB_GRAPH=0 turns the capture off).  All ranks must pass a barrier between clbm_peer_connect and the first
+ * clbm_slab_step / clbm_slab_exchange.  A wait that sees no signal for CLBM_PEER_TIMEOUT_MS (default 20000) gives up and
+ * the next clbm_sync reports CLBM_ESTATE instead of hanging the GPU.
+ * clbm_peer_connect_local is the same for contexts living in ONE process (tests; several GPUs driven by one process). */
+#define CLBM_PEER_HANDLE_BYTES 128
+int  clbm_peer_export(clbm_ctx *ctx, void *handle);
+int  clbm_peer_connect(clbm_ctx *ctx, const void *left_handle, const void *right_handle);
+int  clbm_peer_connect_local(clbm_ctx *ctx, clbm_ctx *left, clbm_ctx *right);
+int  clbm_peer_disconnect(clbm_ctx *ctx);
+/* 0: no ring, 1: NCCL ring (clbm_comm_init), 2: peer-memory ring */
+int  clbm_ring_kind(const clbm_ctx *ctx);
+/* pack + exchange + unpack of ONE halo phase on the launching stream, through whichever ring the context has
+ * (phase 2: the node mask after clbm_upload; phase 0 after stage 0: the moment ghosts a field download needs) */
+int  clbm_slab_exchange(clbm_ctx *ctx, int phase);
 
 /* ---- compliant-vessel case (CLBM_MODEL_PULSATILE) ---------------------------------------------------
  * Replaces the whole iteration body of PulsatileBloodFlow2D() ("Abbashub LBM/apps/PulsatileBloodFlow2D.h":764-790):

@@ -16,10 +16,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libclbm.so")
 
 EXPORTS = [
-    "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_download_lattice",
+    "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_upload2", "clbm_download_lattice",
     "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_diag_contact_angle", "clbm_diag_interface_heights", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
-    "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_comm_unique_id", "clbm_comm_init", "clbm_slab_step", "clbm_comm_destroy", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
+    "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_comm_unique_id", "clbm_comm_init", "clbm_slab_step", "clbm_comm_destroy",
+    "clbm_peer_export", "clbm_peer_connect", "clbm_peer_connect_local", "clbm_peer_disconnect", "clbm_ring_kind", "clbm_slab_exchange", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
     "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
     "clbm_pulsatile_kernel_timing_begin", "clbm_pulsatile_kernel_timing_end", "clbm_pulsatile_download_fields",
@@ -49,6 +50,7 @@ def load_library(path=None):
     lib.clbm_destroy.argtypes = [vp]
     lib.clbm_last_error.restype = ctypes.c_char_p
     lib.clbm_upload.argtypes = [vp, vp, vp, ctypes.c_int]
+    lib.clbm_upload2.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int]
     lib.clbm_download_lattice.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_int)]
     lib.clbm_download_fields.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.clbm_download_force.argtypes = [vp, vp, vp, vp]
@@ -81,6 +83,12 @@ def load_library(path=None):
     lib.clbm_comm_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
     lib.clbm_slab_step.argtypes = [vp, ctypes.c_int]
     lib.clbm_comm_destroy.argtypes = [vp]
+    lib.clbm_peer_export.argtypes = [vp, vp]
+    lib.clbm_peer_connect.argtypes = [vp, vp, vp]
+    lib.clbm_peer_connect_local.argtypes = [vp, vp, vp]
+    lib.clbm_peer_disconnect.argtypes = [vp]
+    lib.clbm_ring_kind.argtypes = [vp]
+    lib.clbm_slab_exchange.argtypes = [vp, ctypes.c_int]
     ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
     lib.clbm_pulsatile_create.argtypes = [ctypes.POINTER(P.PulsatileParams), ctypes.POINTER(vp)]
     lib.clbm_pulsatile_destroy.argtypes = [vp]
@@ -157,9 +165,10 @@ class Lattice:
         self.close()
 
     # -- state transfer (reference layout)
-    def upload(self, lattice, flag, parity=0):
+    def upload(self, lattice, flag, parity=0, other_buffer=True):
+        """other_buffer=False: `lattice` holds valid data only in the buffer `parity` selects (clbm_upload2)"""
         assert lattice.dtype == np.float64 if isinstance(lattice, np.ndarray) else True
-        self._check(self.lib.clbm_upload(self._h, _ptr(lattice), _ptr(flag), int(parity)))
+        self._check(self.lib.clbm_upload2(self._h, _ptr(lattice), _ptr(flag), int(parity), 1 if other_buffer else 0))
 
     def download_lattice(self, lattice=None):
         if lattice is None:
@@ -286,6 +295,31 @@ class Lattice:
     def slab_step(self, n=1):
         """n slab steps (stages + both ghost exchanges) inside the library; every rank calls it with the same n"""
         self._check(self.lib.clbm_slab_step(self._h, int(n)))
+
+    PEER_HANDLE_BYTES = 128
+
+    def peer_export(self):
+        """opaque handle of this slab's halo mailbox (clbm_peer_export) -> bytes"""
+        buf = ctypes.create_string_buffer(self.PEER_HANDLE_BYTES)
+        self._check(self.lib.clbm_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, left_handle, right_handle):
+        """map the ring neighbours' mailboxes (handles from their peer_export, other processes of this node)"""
+        self._check(self.lib.clbm_peer_connect(self._h, ctypes.c_char_p(left_handle), ctypes.c_char_p(right_handle)))
+
+    def peer_connect_local(self, left, right):
+        """the same for neighbours that are Lattice objects of this process"""
+        self._check(self.lib.clbm_peer_connect_local(self._h, left._h, right._h))
+
+    def peer_disconnect(self):
+        self._check(self.lib.clbm_peer_disconnect(self._h))
+
+    def ring_kind(self):
+        return int(self.lib.clbm_ring_kind(self._h))
+
+    def slab_exchange(self, phase):
+        self._check(self.lib.clbm_slab_exchange(self._h, int(phase)))
 
     def overlap_supported(self):
         return bool(self.lib.clbm_overlap_supported(self._h))

@@ -1,9 +1,13 @@
 // clbm_api.cu -- the C ABI of include/clbm.h: context life cycle, state transfer between the
 // reference host layout and the device slab storage, the step loop, diagnostics, profiling.
+#include <sched.h>
+
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "clbm_internal.h"
 
@@ -154,7 +158,10 @@ static int overlap_stage(clbm_ctx *c, int stage)
     const int nx = c->geo.nx, D = overlap_depth(c);
     if ((rc = ensure_boundary_stream(c))) return rc;
     if (stage == 10) {
-        {   // the boundary planes of the "in" buffer were completed by the previous step's interior launch too
+        {   // the boundary planes of the "in" buffer were completed by the launching stream: by the previous step's interior
+            // launch, or -- after a step of the sequential protocol, an upload or a device-side init -- by whatever that stream
+            // ran last.  Recording here (not only after the interior launch) orders ALL of it before the boundary stream.
+            CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
             CLBM_CUDA(cudaStreamWaitEvent(c->stream_b, c->ev_main, 0));
             BoundaryStream bs(c);
             if ((rc = overlap_moments(c))) return rc;
@@ -212,6 +219,57 @@ int model_stage(clbm_ctx *c, int stage)
     set_error("bad stage %d", stage);
     return CLBM_EINVAL;
 }
+
+// device scratch of the field / force downloads: allocated once at the largest size asked for and kept with the context
+// (a cudaMalloc + cudaFree pair per call is a device-wide synchronisation and milliseconds at 512^3)
+int field_scratch(clbm_ctx *c, size_t bytes, double **out)
+{
+    if (c->scratch_bytes < bytes) {
+        if (c->scratch) { CLBM_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->scratch); c->scratch = nullptr; c->scratch_bytes = 0; }
+        if (cudaMalloc(&c->scratch, bytes) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (%zu bytes of field scratch)", bytes); return CLBM_ENOMEM; }
+        c->scratch_bytes = bytes;
+    }
+    *out = c->scratch;
+    return 0;
+}
+
+// while alive, the calling thread is restricted to the CPUs of the NUMA node the current CUDA device hangs off
+struct NumaPin {
+    cpu_set_t old;
+    bool active = false;
+    NumaPin()
+    {
+        int dev = 0;
+        char bus[32] = "", path[128], buf[4096];
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) { cudaGetLastError(); return; }
+        for (char *q = bus; *q; ++q) *q = (char)tolower(*q);
+        snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+        FILE *f = fopen(path, "r");
+        int node = -1;
+        if (f) { if (fscanf(f, "%d", &node) != 1) node = -1; fclose(f); }
+        if (node < 0) return;
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+        f = fopen(path, "r");
+        if (!f) return;
+        const bool got = fgets(buf, sizeof(buf), f) != nullptr;
+        fclose(f);
+        if (!got) return;
+        cpu_set_t want, allowed;
+        CPU_ZERO(&want);
+        for (char *tok = strtok(buf, ",\n"); tok; tok = strtok(nullptr, ",\n")) {   // "0-15,32-47"
+            int a = 0, b = 0;
+            const int n = sscanf(tok, "%d-%d", &a, &b);
+            if (n == 1) b = a;
+            if (n >= 1) for (int i = a; i <= b && i < CPU_SETSIZE; ++i) CPU_SET(i, &want);
+        }
+        if (sched_getaffinity(0, sizeof(old), &old) != 0) return;
+        CPU_AND(&allowed, &want, &old);
+        if (CPU_COUNT(&allowed) == 0) return;
+        active = sched_setaffinity(0, sizeof(allowed), &allowed) == 0;
+    }
+    void restore() { if (active) { sched_setaffinity(0, sizeof(old), &old); active = false; } }
+    ~NumaPin() { restore(); }
+};
 
 }  // namespace clbm
 
@@ -279,10 +337,22 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->kname = "";
     c->stage = nullptr;
     c->stage_bytes = 0;
+    c->mailbox = nullptr;
+    c->mailbox_bytes = c->mailbox_flags_off = 0;
+    c->peer_mode = 0;
+    c->peer_base[0] = c->peer_base[1] = nullptr;
+    c->peer_err = nullptr;
+    c->slab_graph[0] = c->slab_graph[1] = nullptr;
+    c->slab_graph_launches[0] = c->slab_graph_launches[1] = 0;
+    c->slab_graph_failed = 0;
     c->comm = nullptr;
     c->comm_rank = 0;
     c->comm_size = 0;
     c->nfld = 0;
+    c->scratch = nullptr;
+    c->scratch_bytes = 0;
+    c->stream_u = nullptr;
+    read_env_knobs(c->env);
     for (auto &s : c->pop) for (auto &b : s) b = nullptr;
     for (auto &f : c->fld) f = nullptr;
     memset(c->halo, 0, sizeof(c->halo));
@@ -333,6 +403,7 @@ int clbm_destroy(clbm_ctx *c)
     if (!c) return CLBM_OK;
     cudaSetDevice(c->device);
     clbm_comm_destroy(c);
+    clbm_peer_disconnect(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &s : c->pop) for (auto &b : s) if (b) cudaFree(b);
     for (auto &f : c->fld) if (f) cudaFree(f);
@@ -340,7 +411,8 @@ int clbm_destroy(clbm_ctx *c)
     if (c->red_dev) cudaFree(c->red_dev);
     if (c->red_host) cudaFreeHost(c->red_host);
     if (c->stage) cudaFreeHost(c->stage);
-    for (auto &ph : c->halo) for (auto &sd : ph) for (auto &b : sd) if (b) cudaFree(b);
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->mailbox) cudaFree(c->mailbox);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream_b) {
@@ -349,12 +421,15 @@ int clbm_destroy(clbm_ctx *c)
         cudaEventDestroy(c->ev_main);
         cudaEventDestroy(c->ev_b);
     }
+    if (c->stream_u) cudaStreamDestroy(c->stream_u);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return CLBM_OK;
 }
 
-int clbm_upload(clbm_ctx *c, const double *lattice, const uint8_t *flag, int parity)
+int clbm_upload(clbm_ctx *c, const double *lattice, const uint8_t *flag, int parity) { return clbm_upload2(c, lattice, flag, parity, 1); }
+
+int clbm_upload2(clbm_ctx *c, const double *lattice, const uint8_t *flag, int parity, int other_buffer)
 {
     if (!c || !lattice || !flag || (parity != 0 && parity != 1)) { set_error("bad argument to clbm_upload"); return CLBM_EINVAL; }
     CLBM_CUDA(cudaSetDevice(c->device));
@@ -364,13 +439,59 @@ int clbm_upload(clbm_ctx *c, const double *lattice, const uint8_t *flag, int par
     // the device "in" buffer becomes buffer 0; the other one restarts from zero like the reference's
     // value-initialised vector
     c->parity = 0;
+    // the population arrays alternate between two streams so that two host-to-device copies are in flight at a time (one
+    // stream keeps a single DMA engine busy and leaves the link idle between the 19 / 38 copies)
+    if (!c->stream_u) CLBM_CUDA(cudaStreamCreateWithFlags(&c->stream_u, cudaStreamNonBlocking));
+    int turn = 0;
     for (int s = 0; s < c->sets; ++s) {
         CLBM_CUDA(cudaMemsetAsync(c->pop[s][1], 0, (size_t)c->Q * g.ncs * sizeof(double), c->stream));
         const double *src = lattice + (size_t)s * 2 * npop + (size_t)parity * npop;
         for (int k = 0; k < c->Q; ++k)
-            CLBM_CUDA(cudaMemcpyAsync(c->pop[s][0] + (size_t)k * g.ncs + ghost, src + (size_t)k * nelem, nelem * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            CLBM_CUDA(cudaMemcpyAsync(c->pop[s][0] + (size_t)k * g.ncs + ghost, src + (size_t)k * nelem, nelem * sizeof(double), cudaMemcpyHostToDevice,
+                                      (turn++ & 1) ? c->stream_u : c->stream));
     }
     CLBM_CUDA(cudaMemcpyAsync(c->flag + ghost, flag, nelem, cudaMemcpyHostToDevice, c->stream));
+    CLBM_CUDA(cudaStreamSynchronize(c->stream_u));
+    // The buffer the caller did not select: every slot of a bulk node is rewritten by each step, so only bounce_back nodes
+    // keep their initial values there.  The reference's inits leave them zero, except the layered HCZ one that fills both
+    // buffers (PF/apps/twoLayeredFlow2D.h:184-187): hand those node values over as well, so a later
+    // clbm_download_lattice returns what the reference's host array would hold at EVERY node.
+    if (other_buffer) {
+        std::vector<long long> widx;
+        // CellType has two values: memchr finds the bounce_back (0) bytes at memory speed
+        for (const uint8_t *q = flag, *end = flag + nelem; q < end && (q = (const uint8_t *)memchr(q, CELL_BB, (size_t)(end - q))); ++q)
+            widx.push_back((long long)(ghost + (size_t)(q - flag)));
+        const size_t nn = widx.size();
+        if (nn) {
+            std::vector<double> vals((size_t)c->sets * c->Q * nn);
+            bool any = false;
+            for (int s = 0; s < c->sets; ++s)
+                for (int k = 0; k < c->Q; ++k) {
+                    const double *src = lattice + (size_t)s * 2 * npop + (size_t)(1 - parity) * npop + (size_t)k * nelem;
+                    double *dst = vals.data() + ((size_t)s * c->Q + k) * nn;
+                    for (size_t j = 0; j < nn; ++j) { dst[j] = src[widx[j] - (long long)ghost]; any |= dst[j] != 0.0; }
+                }
+            if (any) {
+                long long *idx_dev = nullptr;
+                double *vals_dev = nullptr;
+                if (cudaMalloc(&idx_dev, nn * sizeof(long long)) != cudaSuccess || cudaMalloc(&vals_dev, vals.size() * sizeof(double)) != cudaSuccess) {
+                    cudaGetLastError();
+                    if (idx_dev) cudaFree(idx_dev);
+                    set_error("out of device memory (bounce_back node hand-over)");
+                    return CLBM_ENOMEM;
+                }
+                int rc = 0;
+                if (cudaMemcpyAsync(idx_dev, widx.data(), nn * sizeof(long long), cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                    cudaMemcpyAsync(vals_dev, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+                    rc = CLBM_ECUDA;
+                if (!rc) rc = scatter_node_pops(c, 1, idx_dev, vals_dev, (long long)nn);
+                cudaStreamSynchronize(c->stream);
+                cudaFree(idx_dev);
+                cudaFree(vals_dev);
+                if (rc) { set_error("bounce_back node hand-over failed"); return rc; }
+            }
+        }
+    }
     CLBM_CUDA(cudaStreamSynchronize(c->stream));
     c->host_parity0 = parity;   // download returns (uploaded parity + steps taken) & 1, like the reference's *parity
     c->steps_taken = 0;
@@ -410,19 +531,16 @@ int clbm_download_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double
     for (auto h : host) nwant += h != nullptr;
     if (nwant) {
         double *tmp = nullptr;
-        CLBM_CUDA(cudaMalloc(&tmp, (size_t)nwant * nelem * sizeof(double)));
+        if (int rc = field_scratch(c, (size_t)nwant * nelem * sizeof(double), &tmp)) return rc;
         int j = 0;
         for (int i = 0; i < 6; ++i) if (host[i]) dev[i] = tmp + (size_t)(j++) * nelem;
         int rc = model_fields(c, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5]);
-        if (rc) { cudaFree(tmp); return rc; }
+        if (rc) return rc;
         for (int i = 0; i < 6; ++i)
-            if (host[i]) {
-                cudaError_t e = cudaMemcpyAsync(host[i], dev[i], nelem * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-                if (e != cudaSuccess) { cudaFree(tmp); return cuda_fail(e, "field download", __FILE__, __LINE__); }
-            }
-        cudaError_t e = cudaStreamSynchronize(c->stream);
-        cudaFree(tmp);
-        if (e != cudaSuccess) return cuda_fail(e, "field download sync", __FILE__, __LINE__);
+            if (host[i]) CLBM_CUDA(cudaMemcpyAsync(host[i], dev[i], nelem * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        if (flag) CLBM_CUDA(cudaMemcpyAsync(flag, c->flag + (size_t)g.G * g.plane, nelem, cudaMemcpyDeviceToHost, c->stream));
+        CLBM_CUDA(cudaStreamSynchronize(c->stream));
+        return CLBM_OK;
     }
     if (flag) {
         CLBM_CUDA(cudaMemcpyAsync(flag, c->flag + (size_t)g.G * g.plane, nelem, cudaMemcpyDeviceToHost, c->stream));
@@ -441,7 +559,7 @@ int clbm_download_force(clbm_ctx *c, double *fx, double *fy, double *fz)
     CLBM_CUDA(cudaSetDevice(c->device));
     const size_t nelem = (size_t)c->geo.nx * c->geo.plane;
     double *host[3] = {fx, fy, fz}, *dev[3] = {nullptr, nullptr, nullptr}, *tmp = nullptr;
-    CLBM_CUDA(cudaMalloc(&tmp, 3 * nelem * sizeof(double)));
+    if (int rc = field_scratch(c, 3 * nelem * sizeof(double), &tmp)) return rc;
     for (int i = 0; i < 3; ++i) if (host[i]) dev[i] = tmp + (size_t)i * nelem;
     int rc = sc_force_field(c, dev[0], dev[1], dev[2]);
     for (int i = 0; i < 3 && !rc; ++i)
@@ -450,7 +568,6 @@ int clbm_download_force(clbm_ctx *c, double *fx, double *fy, double *fz)
             rc = CLBM_ECUDA;
         }
     cudaError_t e = cudaStreamSynchronize(c->stream);
-    cudaFree(tmp);
     if (!rc && e != cudaSuccess) return cuda_fail(e, "force download sync", __FILE__, __LINE__);
     return rc;
 }
@@ -499,6 +616,10 @@ int clbm_sync(clbm_ctx *c)
     CLBM_CUDA(cudaSetDevice(c->device));
     if (c->stream_b) CLBM_CUDA(cudaStreamSynchronize(c->stream_b));
     CLBM_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->peer_err && *c->peer_err) {
+        set_error("peer-memory ring: the wait for halo phase %d saw no signal from a neighbour within the time-out", *c->peer_err - 1);
+        return CLBM_ESTATE;
+    }
     return CLBM_OK;
 }
 
@@ -574,7 +695,12 @@ int clbm_alloc_host(size_t bytes, void **ptr)
 {
     if (!ptr) { set_error("null argument"); return CLBM_EINVAL; }
     *ptr = nullptr;
-    CLBM_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    // pinned pages are placed where the allocating thread runs: allocate from a CPU of the current GPU's NUMA node, so that
+    // uploads do not cross the socket interconnect (best effort: a box without NUMA information allocates as before)
+    NumaPin pin;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+    pin.restore();
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
     return CLBM_OK;
 }
 int clbm_free_host(void *ptr)

@@ -2,9 +2,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -72,6 +74,51 @@ struct KernelTiming {
     float ms;
 };
 
+// tuning knobs from the environment, read ONCE per context in clbm_create (-1 = not set): the launch paths never call getenv
+struct EnvKnobs {
+    int sc_xchunk, sc_tile, sc_cluster, tma_promo;
+    int hcz_tile, hcz_xchunk, hcz2d_tile, hcz2d_xchunk;
+    int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
+    int slab_graph;    // 0: never capture the slab step in a CUDA graph
+    int persist;       // 0: never use the persistent multi-step kernels of the L2-resident lattices
+};
+inline int env_int(const char *name, int unset = -1)
+{
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : unset;
+}
+inline void read_env_knobs(EnvKnobs &k)
+{
+    k.sc_xchunk = env_int("CLBM_SC_XCHUNK");
+    k.sc_tile = env_int("CLBM_SC_TILE");
+    k.sc_cluster = env_int("CLBM_SC_CLUSTER");
+    k.tma_promo = env_int("CLBM_TMA_PROMO");
+    k.hcz_tile = env_int("CLBM_HCZ_TILE");
+    k.hcz_xchunk = env_int("CLBM_HCZ_XCHUNK");
+    k.hcz2d_tile = env_int("CLBM_HCZ2D_TILE");
+    k.hcz2d_xchunk = env_int("CLBM_HCZ2D_XCHUNK");
+    k.hcz3d_sweep = env_int("CLBM_HCZ3D_SWEEP");
+    k.slab_graph = env_int("CLBM_SLAB_GRAPH");
+    k.persist = env_int("CLBM_PERSIST");
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE property of a kernel: one bit per device ordinal,
+// so a second device used by the same process gets its own call (a per-process flag left it unset there)
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0ull};
+    bool need(int dev) const { return dev < 0 || dev >= 64 || !((done.load(std::memory_order_acquire) >> dev) & 1ull); }
+    void mark(int dev) { if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release); }
+};
+
+// an encoded tensor map, cached per (buffer, box shape, L2 promotion): encoding costs microseconds of host time per launch,
+// which is what a slab step at strong-scaling sizes does not have
+struct TmapEntry {
+    const void *base;
+    unsigned box[4];
+    int promo;
+    alignas(64) unsigned char map[128];   // CUtensorMap
+};
+
 }  // namespace clbm
 
 struct clbm_ctx {
@@ -84,6 +131,7 @@ struct clbm_ctx {
     long long steps_taken;
     int multi;            // 1: x-slab of a wider lattice (ghost planes filled by exchange)
     cudaStream_t stream;      // launching stream (all work of a single slab; the interior of an overlapped slab step)
+    cudaStream_t stream_u;    // second stream of clbm_upload (two host-to-device copies in flight)
     cudaStream_t stream_b;    // boundary stream of the overlap protocol (high priority): boundary planes, pack/unpack, exchange
     cudaEvent_t ev_main, ev_b;   // interior done / boundary + exchange done (cross-stream ordering between steps)
     cudaEvent_t ev0, ev1;
@@ -101,9 +149,19 @@ struct clbm_ctx {
     // halo buffers: [phase][side][send=0/recv=1]
     void *halo[3][2][2];
     size_t halo_bytes[3];
+    void *mailbox;              // the one allocation behind halo[][][] + a page of flag words (support_kernels.cu: halo_alloc)
+    size_t mailbox_bytes, mailbox_flags_off;
     // library-driven ring (slab_comm.cu): ncclComm_t of this rank, its rank and the ring size (0 = no communicator)
     void *comm;
     int comm_rank, comm_size;
+    // peer-memory ring (slab_comm.cu): 0 = none, 1 = neighbours' mailboxes mapped through CUDA IPC (one process per GPU),
+    // 2 = neighbours are contexts of this process.  peer_base[side] = mailbox of the neighbour on that side.
+    int peer_mode;
+    void *peer_base[2];
+    int *peer_err;              // pinned + mapped: a wait kernel that timed out writes its phase + 1 here
+    void *slab_graph[2];        // cudaGraphExec_t of two consecutive slab steps starting at parity 0 / 1
+    int64_t slab_graph_launches[2];   // kernels one replay launches (counted while capturing)
+    int slab_graph_failed;
     // staging for host<->device slab transfers (pinned), grown on demand
     void *stage;
     size_t stage_bytes;
@@ -115,6 +173,11 @@ struct clbm_ctx {
     // profiling
     bool profiling;
     std::vector<clbm::KernelTiming> prof;
+    clbm::EnvKnobs env;
+    std::vector<clbm::TmapEntry> tmaps;
+    // persistent device scratch of clbm_download_fields / clbm_download_force (grown on demand, freed in clbm_destroy)
+    double *scratch;
+    size_t scratch_bytes;
 };
 
 namespace clbm {
@@ -150,7 +213,11 @@ int model_reduce(clbm_ctx *c, int kind, double *out);
 int model_init_case(clbm_ctx *c, int case_id, const double *args, int nargs);
 int halo_pack(clbm_ctx *c, int phase);
 int halo_unpack(clbm_ctx *c, int phase);
+int field_scratch(clbm_ctx *c, size_t bytes, double **out);   // persistent device scratch of the downloads / reductions
 int halo_alloc(clbm_ctx *c);
+size_t halo_block_offset(const clbm_ctx *c, int phase, int side, int recv);
+void *halo_send_ptr(const clbm_ctx *c, int phase, int side);
+int scatter_node_pops(clbm_ctx *c, int buffer, const long long *idx_dev, const double *vals_dev, long long nn);
 
 inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 

@@ -382,7 +382,7 @@ static int launch_hcz2d_fused(clbm_ctx *c, int x_begin, int x_end)
     // step at 8 columns, 24.5 at 4, 26.4 at 2, 31.9 at 1 -- the 4-column prologue of this kernel costs more than the SC one)
     const long long want = 2LL * 148 * MINB;
     while (xchunk > 4 && (long long)segs * ((ncol + xchunk - 1) / xchunk) < want) xchunk = xchunk / 2 > 4 ? xchunk / 2 : 4;
-    if (const char *e = getenv("CLBM_HCZ2D_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < ncol ? v : ncol; }
+    if (c->env.hcz2d_xchunk > 0) xchunk = c->env.hcz2d_xchunk < ncol ? c->env.hcz2d_xchunk : ncol;
     dim3 grid(segs, (ncol + xchunk - 1) / xchunk);
     Hcz2dTables P;
     for (int k = 0; k < 9; ++k) {
@@ -403,7 +403,7 @@ bool hcz2d_fused_eligible(const clbm_ctx *c) { return c->geo.ny >= 4 && c->geo.n
 int hcz2d_fused_range(clbm_ctx *c, int x_begin, int x_end)
 {
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
-    if (const char *e = getenv("CLBM_HCZ2D_TILE")) variant = atoi(e);
+    if (c->env.hcz2d_tile >= 0) variant = c->env.hcz2d_tile;
     if (c->prm.collision == CLBM_COLLISION_MRT) return launch_hcz2d_fused<128, 3, true>(c, x_begin, x_end);   // 168 registers: no spills
     switch (variant) {
     case 2: return launch_hcz2d_fused<64, 8>(c, x_begin, x_end);

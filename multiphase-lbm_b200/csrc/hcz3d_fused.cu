@@ -435,16 +435,9 @@ static int launch_hcz3d_fused(clbm_ctx *c)
     using C = Hcz3dCfg<TY, TZ>;
     const Geom &g = c->geo;
     CUtensorMap tm[2];
-    const cuuint64_t dims[4] = {(cuuint64_t)g.nz, (cuuint64_t)g.ny, (cuuint64_t)(g.nx + 2 * g.G), 19};
-    const cuuint64_t strides[3] = {(cuuint64_t)g.nz * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.ncs * 8};
     const cuuint32_t box[4] = {(cuuint32_t)TZ, (cuuint32_t)TY, 1, 19};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    for (int s = 0; s < 2; ++s) {
-        CUresult r = get_encode()(&tm[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)c->pop[s][c->parity], dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
-    }
+    for (int s = 0; s < 2; ++s)
+        if (int rc = cached_tmap(c, c->pop[s][c->parity], box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, &tm[s])) return rc;
     const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
     // every chunk pays a 6-plane pipeline fill, so chunks stay long here (128 planes measured best at 512^3)
     int xchunk = g.nx < 128 ? g.nx : 128;
@@ -454,7 +447,7 @@ static int launch_hcz3d_fused(clbm_ctx *c)
         xchunk = (int)((g.nx + nch - 1) / nch);
         if (xchunk < 32) xchunk = g.nx < 32 ? g.nx : 32;
     }
-    if (const char *e = getenv("CLBM_HCZ_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+    if (c->env.hcz_xchunk > 0) xchunk = c->env.hcz_xchunk < g.nx ? c->env.hcz_xchunk : g.nx;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
     Hcz3dOut P;
     for (int k = 0; k < 19; ++k) {
@@ -463,10 +456,10 @@ static int launch_hcz3d_fused(clbm_ctx *c)
     }
     const Hcz3dMom M = {c->fld[0], c->fld[1], c->fld[2], c->fld[3], c->fld[4]};
     auto kern = hcz3d_fused_kernel<TY, TZ>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr;
+    if (attr.need(c->device)) {
         CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
+        attr.mark(c->device);
     }
     LaunchScope ls(c, "hcz3d_fused_collide_stream", true);
     kern<<<grid, C::NT, C::SMEM, c->stream>>>(tm[0], tm[1], P, M, c->flag, g, c->mp, xchunk);

@@ -256,7 +256,7 @@ int hcz3d_fused_launch(clbm_ctx *c, int variant);
 static bool use_fused3d(const clbm_ctx *c)
 {
     int v = c->prm.fused;
-    if (const char *e = getenv("CLBM_HCZ_TILE")) v = atoi(e);
+    if (c->env.hcz_tile >= 0) v = c->env.hcz_tile;
     return (v == 1 || v >= 7) && hcz3d_fused_eligible(c);
 }
 
@@ -265,7 +265,7 @@ int hcz3d_stage1(clbm_ctx *c)
 {
     if (use_fused3d(c)) {
         int v = c->prm.fused;
-        if (const char *e = getenv("CLBM_HCZ_TILE")) v = atoi(e);
+        if (c->env.hcz_tile >= 0) v = c->env.hcz_tile;
         return hcz3d_fused_launch(c, v);
     }
     int rc;

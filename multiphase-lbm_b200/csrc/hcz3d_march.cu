@@ -173,7 +173,7 @@ static int launch_march(clbm_ctx *c)
         xchunk = (int)((g.nx + nch - 1) / nch);
         if (xchunk < 8) xchunk = g.nx < 8 ? g.nx : 8;
     }
-    if (const char *e = getenv("CLBM_HCZ_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+    if (c->env.hcz_xchunk > 0) xchunk = c->env.hcz_xchunk < g.nx ? c->env.hcz_xchunk : g.nx;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
     HczTables P;
     for (int k = 0; k < 19; ++k) {
@@ -195,7 +195,7 @@ bool hcz3d_march_eligible(const clbm_ctx *c) { return c->geo.ncs < (1LL << 31); 
 int hcz3d_march_collide(clbm_ctx *c)
 {
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
-    if (const char *e = getenv("CLBM_HCZ_TILE")) variant = atoi(e);
+    if (c->env.hcz_tile >= 0) variant = c->env.hcz_tile;
     switch (variant) {
     case 2: return launch_march<8, 32, 2>(c);
     case 3: return launch_march<4, 64, 1>(c);

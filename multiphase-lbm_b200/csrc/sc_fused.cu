@@ -197,7 +197,7 @@ static int launch_fused(clbm_ctx *c)
         const int floor_ = (L::D == 2 && !c->multi) ? 1 : 8;
         if (xchunk < floor_) xchunk = g.nx < floor_ ? g.nx : floor_;
     }
-    if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
+    if (c->env.sc_xchunk > 0) xchunk = c->env.sc_xchunk < g.nx ? c->env.sc_xchunk : g.nx;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
     PopTable<L> P;
     for (int k = 0; k < L::Q; ++k) {
@@ -220,7 +220,7 @@ static int sc_tma_variant(const clbm_ctx *c)
 {
     // clbm_params.fused: 1 = default fused kernel, >1 = explicit tile variant (tuning / tests); env overrides
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
-    if (const char *e = getenv("CLBM_SC_TILE")) variant = atoi(e);
+    if (c->env.sc_tile >= 0) variant = c->env.sc_tile;
     // D3Q19 default: the TMA-staged kernel with 8 x 64 tiles (best of the sweep in profiles/README.md)
     if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 11;
     return (variant >= 10 && sc_tma_eligible(c)) ? variant : 0;
@@ -237,7 +237,7 @@ int sc_fused_launch(clbm_ctx *c)
 {
     int rc;
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
-    if (const char *e = getenv("CLBM_SC_TILE")) variant = atoi(e);
+    if (c->env.sc_tile >= 0) variant = c->env.sc_tile;
     if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 11;
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;

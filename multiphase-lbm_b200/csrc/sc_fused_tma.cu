@@ -274,20 +274,15 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
     using C = TmaCfg<TY, TZ>;
     const Geom &g = c->geo;
     CUtensorMap tmap;
-    const cuuint64_t dims[4] = {(cuuint64_t)g.nz, (cuuint64_t)g.ny, (cuuint64_t)(g.nx + 2 * g.G), 19};
-    const cuuint64_t strides[3] = {(cuuint64_t)g.nz * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.ncs * 8};
     const cuuint32_t box[4] = {(cuuint32_t)C::BZ, (cuuint32_t)C::SY, 1, 19};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
     // box rows are 544 B starting 16 B before a 512-B boundary: 256-B promotion over-fetches a third of every row
     // (ncu at 512^3: 31.6 GB read for 20.4 GB of populations); 64 B measured best (profiles/README.md)
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
-    if (const char *e = getenv("CLBM_TMA_PROMO")) {
-        const int v = atoi(e);
+    if (c->env.tma_promo >= 0) {
+        const int v = c->env.tma_promo;
         promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : (v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : promo));
     }
-    CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)c->pop[0][c->parity], dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
+    if (int rc = cached_tmap(c, c->pop[0][c->parity], box, promo, &tmap)) return rc;
 
     const int tiles = ((g.ny + TY - 1) / TY) * ((g.nz + TZ - 1) / TZ);
     const int nxr = x_end - x_begin;
@@ -298,16 +293,16 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
     // profiles/README.md).  (tiles is only used to keep at least one full wave of CTAs.)
     int xchunk = nxr < 24 ? nxr : 24;
     if ((long long)tiles * ((nxr + xchunk - 1) / xchunk) < 148LL * MINB && nxr > 8) xchunk = 8;
-    if (const char *e = getenv("CLBM_SC_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < nxr ? v : nxr; }
+    if (c->env.sc_xchunk > 0) xchunk = c->env.sc_xchunk < nxr ? c->env.sc_xchunk : nxr;
     const int nch1 = (nxr + xchunk - 1) / xchunk, nch2 = x2_end > x2_begin ? (x2_end - x2_begin + xchunk - 1) / xchunk : 0;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, nch1 + nch2);
     OutTable P;
     for (int k = 0; k < 19; ++k) P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr;
+    if (attr.need(c->device)) {
         CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr_set = true;
+        attr.mark(c->device);
     }
     LaunchScope ls(c, "sc_fused_tma_collide_stream", nxr * 2 >= g.nx);   // the boundary-plane launches of the overlap protocol are not the dominant kernel
     if (CY == 1) {
@@ -338,8 +333,7 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
 template <int TY, int TZ, int MINB>
 static int launch_tma(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
-    int cy = 1;
-    if (const char *e = getenv("CLBM_SC_CLUSTER")) cy = atoi(e);
+    const int cy = c->env.sc_cluster > 0 ? c->env.sc_cluster : 1;
     const int ytiles = (c->geo.ny + TY - 1) / TY;
     if (MINB == 1 && cy >= 4 && ytiles % 4 == 0) return launch_tma_c<TY, TZ, MINB, 4>(c, x_begin, x_end, x2_begin, x2_end);
     if (MINB == 1 && cy >= 2 && ytiles % 2 == 0) return launch_tma_c<TY, TZ, MINB, 2>(c, x_begin, x_end, x2_begin, x2_end);

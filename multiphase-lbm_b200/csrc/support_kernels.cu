@@ -230,10 +230,12 @@ int model_reduce(clbm_ctx *c, int kind, double *out)
     if (kind < CLBM_REDUCE_MASS || kind > CLBM_REDUCE_UMAX) { set_error("bad reduction kind %d", kind); return CLBM_EINVAL; }
     const Geom &g = c->geo;
     const long long n = (long long)g.nx * g.plane;
-    double *tmp = nullptr, *partial = nullptr;
-    CLBM_CUDA(cudaMalloc(&tmp, (size_t)4 * n * sizeof(double)));
-    if (cudaMalloc(&partial, (size_t)3 * RED_BLOCKS * sizeof(double)) != cudaSuccess) { cudaFree(tmp); set_error("out of device memory (reduce)"); return CLBM_ENOMEM; }
-    int rc = model_fields(c, tmp, nullptr, nullptr, tmp + n, tmp + 2 * n, tmp + 3 * n);
+    // four field arrays + the per-block partial sums, in the context's persistent scratch (no allocation per call)
+    double *tmp = nullptr;
+    int rc = field_scratch(c, ((size_t)4 * n + (size_t)3 * RED_BLOCKS) * sizeof(double), &tmp);
+    if (rc) return rc;
+    double *partial = tmp + (size_t)4 * n;
+    rc = model_fields(c, tmp, nullptr, nullptr, tmp + n, tmp + 2 * n, tmp + 3 * n);
     if (!rc) {
         {
             LaunchScope ls(c, "reduce_stage1");
@@ -247,8 +249,6 @@ int model_reduce(clbm_ctx *c, int kind, double *out)
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "reduce", __FILE__, __LINE__);
     }
-    cudaFree(tmp);
-    cudaFree(partial);
     if (rc) return rc;
     const double nglob = (double)g.nx_global * (double)g.ny * (double)g.nz;
     if (kind == CLBM_REDUCE_MASS) *out = c->red_host[0];
@@ -285,6 +285,22 @@ static int phase0_fields(const clbm_ctx *c, HaloField *hf)
     return 0;
 }
 
+// All halo buffers of a context live in ONE allocation, the "mailbox": [phase][side][send, recv] blocks (256-byte aligned)
+// followed by a page of flag words.  One allocation = one cudaIpcMemHandle, and the block offsets depend only on the plane size
+// and the model, so a ring neighbour can address our receive blocks and flags through its mapping of the mailbox
+// (slab_comm.cu: the peer-memory ring packs straight into the neighbour's receive block).
+size_t halo_block_offset(const clbm_ctx *c, int phase, int side, int recv)
+{
+    size_t off = 0;
+    for (int ph = 0; ph < 3; ++ph)
+        for (int sd = 0; sd < 2; ++sd)
+            for (int r = 0; r < 2; ++r) {
+                if (ph == phase && sd == side && r == recv) return off;
+                off += (c->halo_bytes[ph] + 255) / 256 * 256;
+            }
+    return off;   // (3, 0, 0): the flag page
+}
+
 int halo_alloc(clbm_ctx *c)
 {
     const Geom &g = c->geo;
@@ -295,13 +311,22 @@ int halo_alloc(clbm_ctx *c)
     c->halo_bytes[0] = planes0 * g.plane * sizeof(double);
     c->halo_bytes[1] = (size_t)n_cross(c) * c->sets * g.plane * sizeof(double);
     c->halo_bytes[2] = (size_t)g.G * g.plane;
+    c->mailbox_flags_off = halo_block_offset(c, 3, 0, 0);
+    c->mailbox_bytes = c->mailbox_flags_off + 4096;
+    if (cudaMalloc(&c->mailbox, c->mailbox_bytes) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (halo buffers)"); return CLBM_ENOMEM; }
+    cudaMemsetAsync(c->mailbox, 0, c->mailbox_bytes, c->stream);
     for (int ph = 0; ph < 3; ++ph)
         for (int side = 0; side < 2; ++side)
-            for (int r = 0; r < 2; ++r) {
-                if (cudaMalloc(&c->halo[ph][side][r], c->halo_bytes[ph]) != cudaSuccess) { set_error("out of device memory (halo buffers)"); return CLBM_ENOMEM; }
-                cudaMemsetAsync(c->halo[ph][side][r], 0, c->halo_bytes[ph], c->stream);
-            }
+            for (int r = 0; r < 2; ++r) c->halo[ph][side][r] = (char *)c->mailbox + halo_block_offset(c, ph, side, r);
     return 0;
+}
+
+// where pack writes what travels towards `side`: our own send block, or -- on a peer-memory ring -- the receive block of
+// that neighbour (its block of the OPPOSITE side) through the mapping of its mailbox
+void *halo_send_ptr(const clbm_ctx *c, int phase, int side)
+{
+    if (c->peer_mode && c->peer_base[side]) return (char *)c->peer_base[side] + halo_block_offset(c, phase, 1 - side, 1);
+    return c->halo[phase][side][0];
 }
 
 // One launch for all (side, set, direction) slots: blockIdx.y enumerates them.
@@ -351,7 +376,7 @@ static CrossTable cross_table(clbm_ctx *c)
     for (int s = 0; s < 2; ++s) T.pop[s] = c->pop[s < c->sets ? s : 0][c->parity];
     for (int side = 0; side < 2; ++side) {
         T.recv[side] = (const double *)c->halo[1][side][1];
-        T.send[side] = (double *)c->halo[1][side][0];
+        T.send[side] = (double *)halo_send_ptr(c, 1, side);
         cross_dirs(c, side, T.ks[side]);
     }
     return T;
@@ -366,7 +391,7 @@ int halo_pack(clbm_ctx *c, int phase)
         HaloField hf[8];
         const int nf = phase0_fields(c, hf);
         for (int side = 0; side < 2; ++side) {
-            double *dst = (double *)c->halo[0][side][0];
+            double *dst = (double *)halo_send_ptr(c, 0, side);
             for (int i = 0; i < nf; ++i) {
                 const int d = hf[i].depth;
                 const int x0 = side ? g.nx - d : 0;
@@ -387,7 +412,7 @@ int halo_pack(clbm_ctx *c, int phase)
     if (phase == 2) {
         for (int side = 0; side < 2; ++side) {
             const int x0 = side ? g.nx - g.G : 0;
-            CLBM_CUDA(cudaMemcpyAsync(c->halo[2][side][0], c->flag + (size_t)(x0 + g.G) * pl, (size_t)g.G * pl, cudaMemcpyDeviceToDevice, c->stream));
+            CLBM_CUDA(cudaMemcpyAsync(halo_send_ptr(c, 2, side), c->flag + (size_t)(x0 + g.G) * pl, (size_t)g.G * pl, cudaMemcpyDeviceToDevice, c->stream));
         }
         return 0;
     }
@@ -435,6 +460,29 @@ int halo_unpack(clbm_ctx *c, int phase)
     }
     set_error("bad halo phase %d", phase);
     return CLBM_EINVAL;
+}
+
+// ---- clbm_upload: populations of bounce_back nodes in the buffer the caller did NOT select -------------------------
+// Only bounce_back nodes keep what they were initialised with (every slot of a bulk node is rewritten by each step), so the
+// reference's second buffer matters exactly there (PF/apps/twoLayeredFlow2D.h:184-187 fills both buffers at init).
+__global__ void __launch_bounds__(256)
+scatter_nodes_kernel(double *__restrict__ pop, const long long *__restrict__ idx, const double *__restrict__ vals, long long nn, int Q, long long ncs)
+{
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nn) return;
+    const long long i = idx[j];
+    for (int k = 0; k < Q; ++k) pop[(size_t)k * ncs + i] = vals[(size_t)k * nn + j];
+}
+
+// vals: [sets][Q][nn] host-ordered values of the nodes idx[] (storage cell indices) for device buffer `buffer`
+int scatter_node_pops(clbm_ctx *c, int buffer, const long long *idx_dev, const double *vals_dev, long long nn)
+{
+    for (int s = 0; s < c->sets; ++s) {
+        LaunchScope ls(c, "upload_scatter_nodes");
+        scatter_nodes_kernel<<<grid_for(nn, 256), 256, 0, c->stream>>>(c->pop[s][buffer], idx_dev, vals_dev + (size_t)s * c->Q * nn, nn, c->Q, c->geo.ncs);
+        CLBM_CUDA(cudaGetLastError());
+    }
+    return 0;
 }
 
 }  // namespace clbm

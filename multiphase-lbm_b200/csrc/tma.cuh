@@ -7,6 +7,9 @@
 
 #include <cstdint>
 
+#include <cstring>
+
+#include "clbm_internal.h"
 #include "lattice.cuh"
 
 namespace clbm {
@@ -60,5 +63,33 @@ inline EncodeTiledFn get_encode()
     return fn;
 }
 
+// tensor map of the [Q][nx+2G][ny][nz] fp64 population array at `base` with the given box, encoded once per
+// (buffer, box, promotion) and kept in the context (the two parities of a population set alternate between two entries)
+inline int cached_tmap(clbm_ctx *c, const void *base, const cuuint32_t box[4], CUtensorMapL2promotion promo, CUtensorMap *out)
+{
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+    for (const TmapEntry &e : c->tmaps)
+        if (e.base == base && e.promo == (int)promo && e.box[0] == box[0] && e.box[1] == box[1] && e.box[2] == box[2] && e.box[3] == box[3]) {
+            memcpy(out, e.map, sizeof(CUtensorMap));
+            return 0;
+        }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return CLBM_ECUDA; }
+    const Geom &g = c->geo;
+    const cuuint64_t dims[4] = {(cuuint64_t)g.nz, (cuuint64_t)g.ny, (cuuint64_t)(g.nx + 2 * g.G), (cuuint64_t)c->Q};
+    const cuuint64_t strides[3] = {(cuuint64_t)g.nz * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.ncs * 8};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return CLBM_ECUDA; }
+    if (c->tmaps.size() >= 64) c->tmaps.clear();
+    TmapEntry e;
+    e.base = base;
+    for (int i = 0; i < 4; ++i) e.box[i] = box[i];
+    e.promo = (int)promo;
+    memcpy(e.map, out, sizeof(CUtensorMap));
+    c->tmaps.push_back(e);
+    return 0;
+}
 
 }  // namespace clbm

@@ -10,9 +10,12 @@ One time step of a slab is
     exchange phase 1
     stage 2 : unpack the crossing populations into the boundary planes     (clbm_step_stage(2))
 
-The exchange itself is plumbing: `LocalRing` moves the buffers between several contexts living in one
-process (single-GPU emulation of R ranks, used by the GPU tests), `DistRing` uses torch.distributed
-point-to-point operations (NCCL on GPUs; gloo in the CPU tests with host buffers).
+The exchange itself is plumbing.  On GPUs the default is the library's own peer-memory ring (csrc/slab_comm.cu: the pack
+writes straight into the neighbour's mailbox over NVLink, flag signal / wait kernels, two steps per CUDA-graph launch;
+`clbm_slab_step`), for which this module only moves the 128-byte mailbox handles once.  `LocalRing` runs several contexts
+in one process (single-GPU emulation of R ranks, used by the GPU tests; copies between the buffers, or the same peer
+ring), `DistRing` is one rank per process; its "torch" transport moves the buffers with torch.distributed point-to-point
+operations (NCCL on GPUs; gloo in the CPU tests with host buffers).
 """
 import os
 
@@ -61,13 +64,19 @@ def as_torch(ptr, nbytes, device):
 class LocalRing:
     """R slab contexts in one process; the exchange is a device-to-device copy per neighbour pair."""
 
-    def __init__(self, lattices):
+    def __init__(self, lattices, peer=False):
+        """peer=True: the library's own peer-memory ring (clbm_peer_connect_local + clbm_slab_step: packs straight into the
+        neighbour's mailbox, flag signal / wait kernels, CUDA-graph replay) instead of the copies below"""
         import torch
         self.lats = lattices
         self.torch = torch
         self.R = len(lattices)
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self._views = {}
+        self.peer = bool(peer) and self.R > 1
+        if self.peer:
+            for r, lat in enumerate(lattices):
+                lat.peer_connect_local(lattices[(r - 1) % self.R], lattices[(r + 1) % self.R])
 
     def _view(self, r, phase, side, recv):
         key = (r, phase, side, recv)
@@ -87,6 +96,12 @@ class LocalRing:
         self.torch.cuda.synchronize()
 
     def exchange_flags(self):
+        if self.peer:
+            for lat in self.lats:
+                lat.slab_exchange(2)
+            for lat in self.lats:
+                lat.sync()
+            return
         for lat in self.lats:
             lat.halo_pack(2)
         self.exchange(2)
@@ -94,9 +109,19 @@ class LocalRing:
             lat.halo_unpack(2)
             lat.sync()
 
-    def step(self, n=1, overlap=None):
+    def step(self, n=1, overlap=None, chunk=2):
         """overlap: use the boundary-first protocol (stages 10-12) where the contexts support it; here the exchange is
-        still a synchronous copy, so this only checks the protocol's results, not its timing"""
+        still a synchronous copy, so this only checks the protocol's results, not its timing.
+        Peer ring: every context enqueues `chunk` steps at a time (its wait kernels spin until the neighbours' signals, which
+        this one host thread enqueues right after, so the chunks stay short)."""
+        if self.peer:
+            done = 0
+            while done < n:
+                m = min(chunk, n - done)
+                for lat in self.lats:
+                    lat.slab_step(m)
+                done += m
+            return
         if overlap is None:
             overlap = all(lat.overlap_supported() for lat in self.lats)
         s0, s1, s2 = (10, 11, 12) if overlap else (0, 1, 2)
@@ -112,6 +137,14 @@ class LocalRing:
 
     def refresh_moment_halo(self):
         """make the moment ghosts valid for the current populations (needed before fields())"""
+        if self.peer:
+            for lat in self.lats:
+                lat.step_stage(0)
+            for lat in self.lats:
+                lat.slab_exchange(0)
+            for lat in self.lats:
+                lat.sync()
+            return
         for lat in self.lats:
             lat.step_stage(0)
         self.exchange(0)
@@ -146,7 +179,7 @@ class DistRing:
     DEVICE: `req.wait()` on an NCCL work object makes the current stream wait, not the host.  A slab step therefore
     never synchronises with the host; the step loop runs ahead of the GPU like the single-slab one."""
 
-    def __init__(self, lattice, rank, nranks, device, native=None):
+    def __init__(self, lattice, rank, nranks, device, native=None, transport=None):
         import torch
         import torch.distributed as dist
         self.lat, self.rank, self.R, self.dist, self.torch = lattice, rank, nranks, dist, torch
@@ -158,6 +191,30 @@ class DistRing:
             native = os.environ.get("CLBM_SLAB_NATIVE", "0") == "1"
         self.native = bool(native) and device.type == "cuda" and nranks > 1
         self.dev = device
+        # transport of the ghost exchange: "peer" (default on GPUs: the library's peer-memory ring over CUDA IPC, packs
+        # straight into the neighbour's mailbox, CUDA-graph replay of the slab step), "nccl" (library-driven ncclSend/Recv),
+        # "torch" (torch.distributed batch_isend_irecv issued from Python, the round-1 path; the only one on CPU / gloo)
+        want = transport or os.environ.get("CLBM_SLAB_TRANSPORT", "") or ("nccl" if self.native else "peer")
+        if device.type != "cuda" or nranks < 2:
+            want = "torch"
+        self.transport = want
+        if want == "peer":
+            try:
+                self._init_peer()
+            except Exception as e:   # noqa: BLE001  (IPC not permitted in this container, ...): say so and fall back
+                import sys
+                print("clbm: peer-memory ring unavailable (%s); falling back to torch.distributed P2P" % e, file=sys.stderr)
+                self.transport = "torch"
+                ok = 0
+            else:
+                ok = 1
+            # every rank must agree on the transport
+            t = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0 and self.transport == "peer":
+                lattice.peer_disconnect()
+                self.transport = "torch"
+        self.native = self.transport == "nccl"
         self._v = {}
         for phase in range(3):
             for side in range(2):
@@ -172,7 +229,7 @@ class DistRing:
         # behind the thousands of pending CTAs of the interior launch and the "overlapped" exchange only starts when the
         # interior kernel drains; a group whose NCCL streams are high priority gets the next SM slot that frees up.
         self.group = None
-        if self.overlap and nranks > 1:
+        if self.overlap and nranks > 1 and self.transport == "torch":
             try:
                 opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
                 self.group = dist.new_group(list(range(nranks)), pg_options=opts)
@@ -196,10 +253,24 @@ class DistRing:
         return ev
 
     def exchange_flags(self):
+        if self.transport == "peer":
+            self.lat.slab_exchange(2)
+            self.lat.sync()
+            return
         self.lat.halo_pack(2)
         self.exchange(2)
         self.lat.halo_unpack(2)
         self.lat.sync()
+
+    def _init_peer(self):
+        """all-gather the 128-byte mailbox handles, map both ring neighbours (clbm_peer_connect), barrier"""
+        torch, dist = self.torch, self.dist
+        mine = torch.frombuffer(bytearray(self.lat.peer_export()), dtype=torch.uint8).to(self.dev)
+        every = [torch.empty_like(mine) for _ in range(self.R)]
+        dist.all_gather(every, mine)
+        left, right = (self.rank - 1) % self.R, (self.rank + 1) % self.R
+        self.lat.peer_connect(every[left].cpu().numpy().tobytes(), every[right].cpu().numpy().tobytes())
+        dist.barrier()
 
     def _init_native(self):
         torch, dist = self.torch, self.dist
@@ -212,6 +283,9 @@ class DistRing:
         self._native_ready = True
 
     def step(self, n=1, overlap=None):
+        if self.transport == "peer":
+            self.lat.slab_step(n)
+            return
         if self.native and overlap is None:
             if not getattr(self, "_native_ready", False):
                 self._init_native()
@@ -234,6 +308,11 @@ class DistRing:
                 self.lat.step_stage(2)
 
     def refresh_moment_halo(self):
+        if self.transport == "peer":
+            self.lat.step_stage(0)
+            self.lat.slab_exchange(0)
+            self.lat.sync()
+            return
         self.lat.step_stage(0)
         self.exchange(0)
         self.lat.halo_unpack(0)
