@@ -352,6 +352,10 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->scratch = nullptr;
     c->scratch_bytes = 0;
     c->stream_u = nullptr;
+    memset(c->mom, 0, sizeof(c->mom));
+    memset(c->mome, 0, sizeof(c->mome));
+    c->mom_src = c->mom_valid = 0;
+    c->walls_known = c->has_walls = 0;
     read_env_knobs(c->env);
     for (auto &s : c->pop) for (auto &b : s) b = nullptr;
     for (auto &f : c->fld) f = nullptr;
@@ -412,6 +416,10 @@ int clbm_destroy(clbm_ctx *c)
     if (c->red_host) cudaFreeHost(c->red_host);
     if (c->stage) cudaFreeHost(c->stage);
     if (c->scratch) cudaFree(c->scratch);
+    for (int m = 0; m < 5; ++m) {
+        if (c->mom[1][m]) cudaFree(c->mom[1][m]);      // mom[0] aliases fld[0..4]
+        for (int s = 0; s < 2; ++s) if (c->mome[s][m]) cudaFree(c->mome[s][m]);
+    }
     if (c->mailbox) cudaFree(c->mailbox);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -495,6 +503,8 @@ int clbm_upload2(clbm_ctx *c, const double *lattice, const uint8_t *flag, int pa
     CLBM_CUDA(cudaStreamSynchronize(c->stream));
     c->host_parity0 = parity;   // download returns (uploaded parity + steps taken) & 1, like the reference's *parity
     c->steps_taken = 0;
+    c->mom_valid = 0;
+    c->walls_known = 0;
     return CLBM_OK;
 }
 
@@ -580,6 +590,8 @@ int clbm_init_case(clbm_ctx *c, int case_id, const double *args, int nargs)
     if (rc) return rc;
     c->host_parity0 = 0;
     c->steps_taken = 0;
+    c->mom_valid = 0;
+    c->walls_known = 0;
     CLBM_CUDA(cudaStreamSynchronize(c->stream));
     return CLBM_OK;
 }

