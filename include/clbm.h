@@ -207,7 +207,8 @@ int  clbm_diag_interface_heights(clbm_ctx *ctx, double phi_mid, int *y_at_x0, in
 int  clbm_halo_buffer(clbm_ctx *ctx, int phase, int side, int recv, void **dev_ptr, size_t *bytes);
 int  clbm_halo_pack(clbm_ctx *ctx, int phase);
 int  clbm_halo_unpack(clbm_ctx *ctx, int phase);
-/* one time step split around the two exchanges:
+/* one time step split around the two exchanges (stage 20 = stage 0 with every moment rebuilt from the populations: the
+ * call a driver makes before clbm_download_fields on a slab):
  *   stage 0: moments of the local slab + pack phase 0
  *   stage 1: unpack phase 0 + collide/stream + pack phase 1
  *   stage 2: unpack phase 1, flip parity                                         */

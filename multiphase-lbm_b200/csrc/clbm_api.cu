@@ -78,7 +78,7 @@ int hcz2d_stage0(clbm_ctx *c);
 int hcz2d_stage1(clbm_ctx *c);
 bool hcz2d_fused_eligible(const clbm_ctx *c);                      // hcz2d_fused.cu
 int hcz2d_fused_range(clbm_ctx *c, int x_begin, int x_end);
-int hcz3d_moments(clbm_ctx *c);
+int hcz3d_stage0(clbm_ctx *c, bool rebuild);
 int hcz3d_stage1(clbm_ctx *c);
 
 static int model_step(clbm_ctx *c)
@@ -196,10 +196,10 @@ int model_stage(clbm_ctx *c, int stage)
 {
     int rc = 0;
     const int m = c->prm.model;
-    if (stage == 0) {
+    if (stage == 0 || stage == 20) {   // 20: stage 0 with every moment rebuilt from the populations (before a field download)
         if (m == CLBM_MODEL_SC_D2Q9 || m == CLBM_MODEL_SC_D3Q19) rc = c->prm.fused ? sc_psi_boundary(c) : sc_psi_all(c);
         else if (m == CLBM_MODEL_HCZ_D2Q9) rc = hcz2d_stage0(c);
-        else if (m == CLBM_MODEL_HCZ_D3Q19) rc = hcz3d_moments(c);
+        else if (m == CLBM_MODEL_HCZ_D3Q19) rc = hcz3d_stage0(c, stage == 20);
         else rc = CLBM_EINVAL;
         if (rc) return rc;
         return halo_pack(c, 0);
@@ -354,7 +354,7 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->stream_u = nullptr;
     memset(c->mom, 0, sizeof(c->mom));
     memset(c->mome, 0, sizeof(c->mome));
-    c->mom_src = c->mom_valid = 0;
+    c->mom_src = c->mom_valid = c->sweep_active = 0;
     c->walls_known = c->has_walls = 0;
     read_env_knobs(c->env);
     for (auto &s : c->pop) for (auto &b : s) b = nullptr;

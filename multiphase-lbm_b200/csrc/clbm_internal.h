@@ -148,6 +148,7 @@ struct clbm_ctx {
     // direct moments pass or a step of another kernel path invalidates it: the next step then rebuilds it from the populations)
     double *mom[2][5], *mome[2][5];
     int mom_src, mom_valid;
+    int sweep_active;             // x-slab only: the current step runs the sweep kernel, the moment halo comes from mom[mom_src] (+ edges)
     int walls_known, has_walls;   // result of the one-time scan for bounce_back nodes (the sweep kernel is wall-free only)
     // reduction scratch
     double *red_dev;
@@ -221,6 +222,10 @@ int halo_pack(clbm_ctx *c, int phase);
 int halo_unpack(clbm_ctx *c, int phase);
 int field_scratch(clbm_ctx *c, size_t bytes, double **out);   // persistent device scratch of the downloads / reductions
 int halo_alloc(clbm_ctx *c);
+// HCZ D3Q19: node array of moment m the halo exchange reads / fills (the sweep kernel's current set, else fld[m]), and the
+// pack of the phi halo with the sweep kernel's edge sums folded in (hcz3d_sweep.cu)
+double *hcz3d_moment_array(const clbm_ctx *c, int m);
+int hcz3d_pack_phi_merged(clbm_ctx *c, double *dst, int x0, int nplanes);
 size_t halo_block_offset(const clbm_ctx *c, int phase, int side, int recv);
 void *halo_send_ptr(const clbm_ctx *c, int phase, int side);
 int scatter_node_pops(clbm_ctx *c, int buffer, const long long *idx_dev, const double *vals_dev, long long nn);

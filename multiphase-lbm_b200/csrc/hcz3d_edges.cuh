@@ -72,7 +72,10 @@ CLBM_HD int ring_slot(const EdgeGeom &g, int y0, int z0, int dy, int dz)
 // populations [38][TY][TZ].  jx needs no sums of its own: it is +P_term(A) - P_term(C).
 struct PushSums { double ph[3], pt[3], jy[3], jz[3]; };
 
-template <int TY, int TZ>
+// FY / FZ: the only c_y / c_z whose source node can lie inside the tile (2 = any).  A cell of the ring row below the tile
+// (dy = -1) is reached from the tile's first row by c_y = -1 only, and so on: the filter drops the other directions at
+// compile time (they would be predicated off at run time: same sums, a quarter of the instructions).
+template <int TY, int TZ, int FY = 2, int FZ = 2>
 CLBM_D void gather_pushes(const double *S, int dy, int dz, PushSums &o)
 {
     constexpr int NT = TY * TZ;
@@ -85,6 +88,7 @@ CLBM_D void gather_pushes(const double *S, int dy, int dz, PushSums &o)
 #pragma unroll
     for (int k = 0; k < 19; ++k) {
         const int cx = D3Q19::cx(k), cy = D3Q19::cy(k), cz = D3Q19::cz(k);
+        if ((FY != 2 && cy != FY) || (FZ != 2 && cz != FZ)) continue;
         const int grp = cx > 0 ? 0 : (cx == 0 ? 1 : 2);
         const bool ok = vy[cy + 1] && vz[cz + 1];
         const int src = base - cy * TZ - cz;

@@ -222,9 +222,22 @@ static FieldPtrs8 fld8(clbm_ctx *c)
 int hcz3d_moments(clbm_ctx *c)
 {
     c->mom_valid = 0;   // fld[0..4] now hold plain sums: whatever the sweep kernel carried (edge sums, the other set) is stale
+    c->sweep_active = 0;
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "hcz3d_moments");
     hcz3d_moments_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[1][c->parity], fld8(c), c->geo, 0, n);
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// plain sums of the planes [x0, x0 + np) into moment set `set` of the sweep kernel
+static int hcz3d_moments_planes(clbm_ctx *c, int set, int x0, int np)
+{
+    FieldPtrs8 F = fld8(c);
+    for (int m = 0; m < 5; ++m) F.p[m] = c->mom[set][m];
+    const long long n = (long long)np * c->geo.plane;
+    LaunchScope ls(c, "hcz3d_moments_planes");
+    hcz3d_moments_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[1][c->parity], F, c->geo, x0, n);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -246,6 +259,7 @@ int hcz3d_level2(clbm_ctx *c)
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
+int hcz3d_sweep_launch(clbm_ctx *c, int src);    // hcz3d_sweep.cu
 bool hcz3d_march_eligible(const clbm_ctx *c);   // hcz3d_march.cu
 int hcz3d_march_collide(clbm_ctx *c);
 
@@ -264,6 +278,14 @@ static bool use_fused3d(const clbm_ctx *c)
 // everything after the moments: stage 1 of the slab protocol
 int hcz3d_stage1(clbm_ctx *c)
 {
+    if (c->sweep_active) {   // decided in stage 0 of this step
+        int rc = hcz3d_sweep_launch(c, c->mom_src);
+        if (rc) return rc;
+        c->mom_src = 1 - c->mom_src;
+        c->mom_valid = 1;
+        return 0;
+    }
+    c->mom_valid = 0;
     if (use_fused3d(c)) {
         int v = c->prm.fused;
         if (c->env.hcz_tile >= 0) v = c->env.hcz_tile;
@@ -327,7 +349,7 @@ static int hcz3d_has_walls(clbm_ctx *c, bool *walls)
 static int hcz3d_use_sweep(clbm_ctx *c, bool *use)
 {
     *use = false;
-    if (c->multi || c->env.hcz3d_sweep == 0 || c->profiling) return 0;
+    if (c->env.hcz3d_sweep == 0 || c->profiling) return 0;
     int v = c->prm.fused;
     if (c->env.hcz_tile >= 0) v = c->env.hcz_tile;
     if (v != 1 || !hcz3d_fused_eligible(c) || !hcz3d_sweep_shape_ok(c)) return 0;
@@ -352,6 +374,37 @@ static int hcz3d_sweep_alloc(clbm_ctx *c)
             CLBM_CUDA(cudaMemsetAsync(c->mome[s][m], 0, eb, c->stream));
         }
     }
+    return 0;
+}
+
+double *hcz3d_moment_array(const clbm_ctx *c, int m) { return (c->sweep_active && c->mom[1][0]) ? c->mom[c->mom_src][m] : c->fld[m]; }
+
+// stage 0 of an x-slab step: complete moments of the local planes + (by the caller) the pack of the moment halo.
+// Sweep path: the interior planes come from the previous sweep; planes 0 and nx-1 are rebuilt from the populations, which
+// the crossing populations of the neighbours changed after the sweep (their edge sums are therefore zero).
+int hcz3d_stage0(clbm_ctx *c, bool rebuild)
+{
+    int rc;
+    bool sweep = false;
+    if (rebuild) c->mom_valid = 0;
+    if ((rc = hcz3d_use_sweep(c, &sweep))) return rc;
+    if (!sweep || rebuild) return hcz3d_moments(c);   // plain sums of every plane into fld[0..4] (= set 0)
+    if ((rc = hcz3d_sweep_alloc(c))) return rc;
+    const Geom &g = c->geo;
+    const long long ep = hcz3d_sweep_edge_doubles(c) / g.nx;
+    if (!c->mom_valid) {
+        if ((rc = hcz3d_moments(c))) return rc;
+        for (int m = 0; m < 5; ++m) CLBM_CUDA(cudaMemsetAsync(c->mome[0][m], 0, (size_t)ep * g.nx * sizeof(double), c->stream));
+        c->mom_src = 0;
+    } else {
+        if ((rc = hcz3d_moments_planes(c, c->mom_src, 0, 1))) return rc;
+        if ((rc = hcz3d_moments_planes(c, c->mom_src, g.nx - 1, 1))) return rc;
+        for (int m = 0; m < 5; ++m) {
+            CLBM_CUDA(cudaMemsetAsync(c->mome[c->mom_src][m], 0, (size_t)ep * sizeof(double), c->stream));
+            CLBM_CUDA(cudaMemsetAsync(c->mome[c->mom_src][m] + (size_t)ep * (g.nx - 1), 0, (size_t)ep * sizeof(double), c->stream));
+        }
+    }
+    c->sweep_active = 1;
     return 0;
 }
 

@@ -198,50 +198,69 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     auto xs_of = [&](int xg) { return g.wx(xg) + G; };
     auto has_edges = [&](int xg) { return wrapx || (xg >= 0 && xg < nx); };
 
-    // registers that run one plane ahead of their use
-    double phi_n[3] = {0., 0., 0.};
+    // ---- phi: registers that run one plane ahead of their use.  The edge sums of a border node stay RAW in registers and are
+    //      added when the plane is stored one iteration later: an add right behind the loads would wait for them every plane
+    //      (measured: the kernel ran at half speed that way) ----
+    double phi_n[3] = {0., 0., 0.}, phi_e[3] = {0., 0., 0.};
     auto load_phi = [&](int xg) {
         const int base = xs_of(xg) * plane;
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
+        for (int j = 0; j < 3; ++j)
             if (w_idx[j] >= 0) phi_n[j] = Min.m[0][base + w_yz[j]];
-        if (w_idx[2] >= 0) {
-            double v = Min.m[0][base + w_yz[2]];
-            if (has_edges(xg)) {
-                const double *E = Min.e[0] + (size_t)g.wx(xg) * eg.eplane;
-                const double e0 = w_e[0] >= 0 ? E[w_e[0]] : 0.0, e1 = w_e[1] >= 0 ? E[w_e[1]] : 0.0, e2 = w_e[2] >= 0 ? E[w_e[2]] : 0.0;
-                v = ((v + e0) + e1) + e2;
-            }
-            phi_n[2] = v;
+        if (w_idx[2] >= 0 && has_edges(xg)) {
+            const double *E = Min.e[0] + (size_t)g.wx(xg) * eg.eplane;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) phi_e[q] = w_e[q] >= 0 ? E[w_e[q]] : 0.0;
+        } else {
+            phi_e[0] = phi_e[1] = phi_e[2] = 0.0;
         }
     };
-    // P_term and raw momentum of the own node and of the ring cell (moments 1..4), edge sums included
-    double mo_n[4] = {0., 0., 0., 0.}, mh_n[4] = {0., 0., 0., 0.}, mo_c[4], mh_c[4];
+    // ---- P_term and raw momentum (moments 1..4) of the own node and of the ring cell: loaded RAW (node array + edge slots) at
+    //      the top of the iteration that uses them and merged after the gather phase, i.e. with a phase of independent work
+    //      between load and use; one iteration earlier the same addresses are prefetched into L2, so those loads are L2 hits.
+    //      (Holding the raw values across the collide phase instead would cost 32 more registers there.) ----
+    double mo_r[4][4], mh_r[4][4], mo_c[4], mh_c[4];
+    auto pf_l2 = [](const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
+    auto prefetch_mom = [&](int xg) {
+        const int base = xs_of(xg) * plane;
+        const bool ed = has_edges(xg);
+        const size_t eb = (size_t)g.wx(xg) * eg.eplane;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            pf_l2(Min.m[m + 1] + base + yz);
+            if (h_warp) pf_l2(Min.m[m + 1] + base + h1_yz);
+            if (ed) {
+                const double *E = Min.e[m + 1] + eb;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (own_e[q] >= 0) pf_l2(E + own_e[q]);
+                    if (h_warp && h1_e[q] >= 0) pf_l2(E + h1_e[q]);
+                }
+            }
+        }
+    };
     auto load_mom = [&](int xg) {
         const int base = xs_of(xg) * plane;
         const bool ed = has_edges(xg);
         const size_t eb = (size_t)g.wx(xg) * eg.eplane;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            double v = Min.m[m + 1][base + yz];
-            if (ed) {
-                const double *E = Min.e[m + 1] + eb;
-                const double e0 = own_e[0] >= 0 ? E[own_e[0]] : 0.0, e1 = own_e[1] >= 0 ? E[own_e[1]] : 0.0, e2 = own_e[2] >= 0 ? E[own_e[2]] : 0.0;
-                v = ((v + e0) + e1) + e2;
-            }
-            mo_n[m] = v;
-        }
-        if (h_warp) {
+            const double *E = Min.e[m + 1] + eb;
+            mo_r[m][0] = Min.m[m + 1][base + yz];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                double v = Min.m[m + 1][base + h1_yz];
-                if (ed) {
-                    const double *E = Min.e[m + 1] + eb;
-                    const double e0 = h1_e[0] >= 0 ? E[h1_e[0]] : 0.0, e1 = h1_e[1] >= 0 ? E[h1_e[1]] : 0.0, e2 = h1_e[2] >= 0 ? E[h1_e[2]] : 0.0;
-                    v = ((v + e0) + e1) + e2;
-                }
-                mh_n[m] = v;
+            for (int q = 0; q < 3; ++q) mo_r[m][q + 1] = (ed && own_e[q] >= 0) ? E[own_e[q]] : 0.0;
+            if (h_warp) {
+                mh_r[m][0] = Min.m[m + 1][base + h1_yz];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) mh_r[m][q + 1] = (ed && h1_e[q] >= 0) ? E[h1_e[q]] : 0.0;
             }
+        }
+    };
+    auto merge_mom = [&]() {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            mo_c[m] = ((mo_r[m][0] + mo_r[m][1]) + mo_r[m][2]) + mo_r[m][3];
+            if (h_warp) mh_c[m] = ((mh_r[m][0] + mh_r[m][1]) + mh_r[m][2]) + mh_r[m][3];
         }
     };
 
@@ -344,9 +363,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
 
     // S5 for one cell: `slot` = its accumulator slot, (dy, dz) = its tile coordinates, xsrc = the plane whose pushes are in S.
     // Completes plane xsrc-1 and hands it to `store(plane, values[5])`.
-    auto accumulate = [&](const double *S, int slot, int dy, int dz, int xsrc, auto store) {
-        PushSums s;
-        gather_pushes<TY, TZ>(S, dy, dz, s);
+    auto accumulate = [&](const PushSums &s, int slot, int xsrc, auto store) {
         double *Ts = acc + slot, *As = acc + 5 * C::NACC + slot;    // Ts[j * NACC], As[j * NACC]
         double T[5], A[4], v[5];
 #pragma unroll
@@ -373,27 +390,43 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     };
 
     load_phi(-3);
+    prefetch_mom(-1);
     // x = plane being collided; the first six iterations only fill the pipeline, the last one only gathers plane nx-1
     for (int x = -6; x <= nx; ++x) {
-        // ---- S1: phi of plane x+3 from the registers, then prefetch the next plane's ----
+        // ---- S1: phi of plane x+3 from the registers (edge sums added now), then prefetch the next plane's; raw moments of
+        //      plane x+1 for S3 of THIS iteration, L2 prefetch of plane x+2's ----
+        const bool s3_on = x + 1 >= -1 && x < nx;
         if (x < nx) {
             double *dst = r_phi + ((x + 3) & 3) * C::R3;
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
+            for (int j = 0; j < 2; ++j)
                 if (w_idx[j] >= 0) dst[w_idx[j]] = phi_n[j];
+            if (w_idx[2] >= 0) dst[w_idx[2]] = ((phi_n[2] + phi_e[0]) + phi_e[1]) + phi_e[2];
             if (x + 1 < nx) load_phi(x + 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { mo_c[j] = mo_n[j]; mh_c[j] = mh_n[j]; }
-            if (x + 2 >= -1 && x + 1 < nx) load_mom(x + 2);   // consumed by S3 of the next iteration
+            if (s3_on) {
+                load_mom(x + 1);
+                if (x + 1 < nx) prefetch_mom(x + 2);
+            }
         }
         __syncthreads();
 
         // ---- S5: what plane x-1 pushed (its post-collision values are in its stage) ----
         if (x >= 1) {
             const double *S = reinterpret_cast<const double *>(smem_raw + ((x - 1) & 1) * C::STAGE_BYTES);
-            accumulate(S, tid, ty, tz, x - 1, store_own);
-            if (h_act) accumulate(S, NT + tid, h1y - 1, h1z - 1, x - 1, store_ring);
+            PushSums ps;
+            gather_pushes<TY, TZ>(S, ty, tz, ps);
+            accumulate(ps, tid, x - 1, store_own);
+            if (h_act) {
+                // ring cell: only the directions leaving the tile through that side can contribute
+                const int dy = h1y - 1, dz = h1z - 1;
+                if (tid < C::Z1) gather_pushes<TY, TZ, -1, 2>(S, dy, dz, ps);              // row below the tile
+                else if (tid < 2 * C::Z1) gather_pushes<TY, TZ, 1, 2>(S, dy, dz, ps);      // row above
+                else if ((tid - 2 * C::Z1) & 1) gather_pushes<TY, TZ, 2, 1>(S, dy, dz, ps);   // column behind the last one
+                else gather_pushes<TY, TZ, 2, -1>(S, dy, dz, ps);                          // column before the first one
+                accumulate(ps, NT + tid, x - 1, store_ring);
+            }
         }
+        if (s3_on) merge_mom();   // the loads of S1 have had the whole gather phase to land
         // ---- S2: lap(phi), psi(phi) of plane x+2 on tile + halo 2 ----
         if (x + 2 >= -2 && x < nx) {
             const int p = x + 2;
@@ -434,7 +467,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         }
 
         // ---- S3: level 2 of plane x+1 on tile + halo 1 ----
-        if (x + 1 >= -1 && x < nx) {
+        if (s3_on) {
             double *pr = r_pr + ((x + 1) & 3) * C::R1;
             if (h_warp) {
                 SweepLocal tmp;
@@ -521,6 +554,31 @@ int hcz3d_sweep_launch(clbm_ctx *c, int src)
     dim3 grid(g.nz / SW_TZ, g.ny / SW_TY, 1);
     LaunchScope ls(c, "hcz3d_sweep_collide_stream_moments", true);
     kern<<<grid, C::NT, C::SMEM, c->stream>>>(tm[0], tm[1], P, Min, Mout, g, c->mp, hcz3d_sweep_edge_geom(c));
+    CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// phi of the planes [x0, x0 + np) with the edge sums folded in, densely into dst (the moment-halo pack of an x-slab)
+__global__ void __launch_bounds__(256)
+pack_phi_merged_kernel(const double *__restrict__ M, const double *__restrict__ E, double *__restrict__ dst, Geom g, EdgeGeom eg, int x0, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int xp = x0 + (int)(t / g.plane), r = (int)(t % g.plane);
+    const int yy = r / g.nz, zz = r % g.nz;
+    int e[3];
+    edge_offsets<SW_TY, SW_TZ>(eg, yy, zz, e);
+    const double *Ep = E + (size_t)xp * eg.eplane;
+    const double e0 = e[0] >= 0 ? Ep[e[0]] : 0.0, e1 = e[1] >= 0 ? Ep[e[1]] : 0.0, e2 = e[2] >= 0 ? Ep[e[2]] : 0.0;
+    dst[t] = ((M[(size_t)(xp + g.G) * g.plane + r] + e0) + e1) + e2;
+}
+
+int hcz3d_pack_phi_merged(clbm_ctx *c, double *dst, int x0, int nplanes)
+{
+    const long long n = (long long)nplanes * c->geo.plane;
+    LaunchScope ls(c, "pack_phi_merged");
+    pack_phi_merged_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->mom[c->mom_src][0], c->mome[c->mom_src][0], dst, c->geo, hcz3d_sweep_edge_geom(c), x0, n);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -37,7 +37,7 @@ template <class L> struct PopTable {
 // GUO = true: the Rayleigh-Taylor variant (SC/apps/RayleighTaylor2D.h; psi = 1 - exp(-rho), a wall neighbour
 // contributes the psi of the opposite neighbour, Guo forcing) -- a compile-time flag, the Yuan-CS code is unchanged.
 // MRT = true: CLBM_COLLISION_MRT for D2Q9 (sc_collide_mrt), likewise a compile-time flag.
-template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false>
+template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false, int PF = 2>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const double *__restrict__ psi_g, Geom g,
                 ModelParams mp, int xchunk)
@@ -132,6 +132,17 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
     for (int x = xa; x < xb; ++x) {
         const int xp = g.wx(x + 1), xm = g.wx(x - 1);
         fill(xp + G, (x + 1) & 3, fn, psn, gpn);
+        // The loads of fill() are consumed at once (psi needs the density), so every plane pays a full memory latency with
+        // only 16 warps per SM to hide it (ncu at 8192^2, D2Q9: DRAM at 47 %, top stall long_scoreboard).  Pull the plane
+        // two further on into L2 now: those loads then wait for an L2 hit instead of HBM.  No registers, no shared memory.
+        if (PF > 0 && inside) {
+            const int xq = g.wrapx ? g.wx(g.wx(x + 1) + PF) : x + 1 + PF;
+            if (xq + G < g.nx + 2 * G) {
+                const int i = (xq + G) * plane + yz;
+#pragma unroll
+                for (int k = 0; k < L::Q; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.in[k] + i));
+            }
+        }
         __syncthreads();
 
         const int sm = (x + 3) & 3, s0 = x & 3, sp = (x + 1) & 3;

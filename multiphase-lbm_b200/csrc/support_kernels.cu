@@ -390,12 +390,19 @@ int halo_pack(clbm_ctx *c, int phase)
     if (phase == 0) {
         HaloField hf[8];
         const int nf = phase0_fields(c, hf);
+        const bool hcz3 = c->prm.model == CLBM_MODEL_HCZ_D3Q19;
         for (int side = 0; side < 2; ++side) {
             double *dst = (double *)halo_send_ptr(c, 0, side);
             for (int i = 0; i < nf; ++i) {
                 const int d = hf[i].depth;
                 const int x0 = side ? g.nx - d : 0;
-                CLBM_CUDA(cudaMemcpyAsync(dst, c->fld[hf[i].fld] + (size_t)(x0 + g.G) * pl, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                if (hcz3 && c->sweep_active && hf[i].fld == 0) {
+                    // phi of the sweep kernel = node array + edge sums: folded while packing (the neighbour's ghost planes hold plain values)
+                    if (int rc = hcz3d_pack_phi_merged(c, dst, x0, d)) return rc;
+                } else {
+                    const double *src = hcz3 ? hcz3d_moment_array(c, hf[i].fld) : c->fld[hf[i].fld];
+                    CLBM_CUDA(cudaMemcpyAsync(dst, src + (size_t)(x0 + g.G) * pl, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                }
                 dst += d * pl;
             }
         }
@@ -435,7 +442,8 @@ int halo_unpack(clbm_ctx *c, int phase)
             for (int i = 0; i < nf; ++i) {
                 const int d = hf[i].depth;
                 const int x0 = side ? g.nx : -d;   // ghost planes on that side
-                CLBM_CUDA(cudaMemcpyAsync(c->fld[hf[i].fld] + (size_t)(x0 + g.G) * pl, src, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                double *dstf = c->prm.model == CLBM_MODEL_HCZ_D3Q19 ? hcz3d_moment_array(c, hf[i].fld) : c->fld[hf[i].fld];
+                CLBM_CUDA(cudaMemcpyAsync(dstf + (size_t)(x0 + g.G) * pl, src, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
                 src += d * pl;
             }
         }

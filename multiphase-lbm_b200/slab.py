@@ -136,17 +136,18 @@ class LocalRing:
                 lat.step_stage(s2)
 
     def refresh_moment_halo(self):
-        """make the moment ghosts valid for the current populations (needed before fields())"""
+        """make the moments and their ghosts valid for the current populations (needed before fields()); stage 20 = stage 0
+        with every moment rebuilt from the populations (the sweep kernel of HCZ D3Q19 keeps its moments split in partial sums)"""
         if self.peer:
             for lat in self.lats:
-                lat.step_stage(0)
+                lat.step_stage(20)
             for lat in self.lats:
                 lat.slab_exchange(0)
             for lat in self.lats:
                 lat.sync()
             return
         for lat in self.lats:
-            lat.step_stage(0)
+            lat.step_stage(20)
         self.exchange(0)
         for lat in self.lats:
             lat.halo_unpack(0)
@@ -309,11 +310,11 @@ class DistRing:
 
     def refresh_moment_halo(self):
         if self.transport == "peer":
-            self.lat.step_stage(0)
+            self.lat.step_stage(20)
             self.lat.slab_exchange(0)
             self.lat.sync()
             return
-        self.lat.step_stage(0)
+        self.lat.step_stage(20)
         self.exchange(0)
         self.lat.halo_unpack(0)
         self.lat.sync()

@@ -138,3 +138,50 @@ def test_sweep_production_size_mass_and_speed():
     print("\nHCZ D3Q19 512^3 single sweep: %.2f ms/step, %.0f MLUPS" % (ms / 10, 512 ** 3 * 10 / ms / 1e3))
     assert np.isfinite(m1) and abs(m1 - m0) / abs(m0) < 1e-12
     assert np.isfinite(umax) and umax < 0.2
+
+
+@pytest.mark.parametrize("peer", [False, True])
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_sweep_on_x_slabs(nranks, peer):
+    """x-slabs running the sweep kernel: interior moments carried by the kernel, the two boundary planes of every slab rebuilt
+    from the populations after the crossing populations arrived, phi halo packed with the edge sums folded in.  Against the
+    single-slab sweep to round-off (the boundary planes are summed in a different order) and against the oracle at 1e-10."""
+    slab = pkg.slab
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 8 * nranks, 16, 64, ulb=0.01, N=24, Re=6.0, kappa=5e-4, gravity=-1e-5)
+    ora = OracleSim(prm).init_case(P.CASE_HCZ_LAPLACE3D, ())
+    steps = 41
+    with make(prm, 1) as single:
+        single.upload(ora.lattice, ora.flag, 0)
+        single.step(steps)
+        ref_pops, ref_fields = single.in_pops(), single.fields()
+    lats = []
+    with sweep_env(1):
+        for r in range(nranks):
+            lat = pkg.clbm.Lattice(slab.slab_params(prm, r, nranks))
+            l, f = slab.slice_host_state(prm, ora.lattice, ora.flag, r, nranks)
+            lat.upload(l, f, 0)
+            lats.append(lat)
+    ring = slab.LocalRing(lats, peer=peer)
+    ring.exchange_flags()
+    l0 = [lat.launch_count() for lat in lats]
+    if peer:
+        ring.step(steps, chunk=5)
+    else:
+        ring.step(steps)
+    per_step = [(lat.launch_count() - a) / steps for lat, a in zip(lats, l0)]
+    ring.refresh_moment_halo()
+    pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
+    fields = {k: np.concatenate([lat.fields()[k] for lat in lats]) for k in ("s0", "s1", "s2", "ux", "uy", "uz")}
+    ring.step(2)                                      # and on: the moments are rebuilt after the field download
+    pops2 = np.concatenate([lat.in_pops() for lat in lats], axis=2)
+    for lat in lats:
+        lat.close()
+    assert _cases.rel_linf(pops, ref_pops) < 1e-12
+    for k in ("s0", "s1", "s2"):
+        assert _cases.rel_linf(fields[k], ref_fields[k]) < 1e-11, k
+    assert vec_err(fields, ref_fields) < 1e-10
+    ora.step(steps)
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
+    ora.step(2)
+    assert _cases.rel_linf(pops2, ora.in_pops()) < TOL
+    assert max(per_step) < 14, per_step               # sweep + 2 boundary-plane moments + packs / unpacks (+ signal / wait), not 2 full passes

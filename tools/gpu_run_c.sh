@@ -1,0 +1,16 @@
+#!/bin/bash
+# round-2 GPU run C: sweep kernel with deferred edge merges, slab-mode sweep, D2Q9 L2 prefetch
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_zt_hcz3d_sweep.py tests/test_gpu_zv_peer_ring.py tests/test_gpu_slab.py -m gpu -q --timeout 600 -p no:cacheprovider -s -x > gpurun_out/r2c_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2c_pytest.log
+tail -15 gpurun_out/r2c_pytest.log
+timeout 300 python bench.py --workload c4_hcz_d3q19_512 --steps 20 --warmup 5 --no-extras --no-cpu > gpurun_out/r2c_bench_hcz3d.json 2> gpurun_out/r2c_bench_hcz3d.err
+echo "bench hcz3d rc=$?"; tail -3 gpurun_out/r2c_bench_hcz3d.err
+timeout 300 python bench.py --workload sc_d2q9_8192 --steps 30 --warmup 5 --no-extras --no-cpu --no-e2e > gpurun_out/r2c_bench_sc2d.json 2> gpurun_out/r2c_bench_sc2d.err
+echo "bench sc2d rc=$?"
+timeout 300 python bench.py --workload c1_sc_d2q9_256 --steps 2000 --warmup 50 --no-extras --no-cpu --no-e2e > gpurun_out/r2c_bench_c1.json 2> gpurun_out/r2c_bench_c1.err
+timeout 300 python bench.py --workload c2_hcz_d2q9_256 --steps 1000 --warmup 50 --no-extras --no-cpu --no-e2e > gpurun_out/r2c_bench_c2.json 2> gpurun_out/r2c_bench_c2.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:hcz3d_sweep --launch-skip 2 -c 1 -f -o gpurun_out/r2c_hcz3d_sweep_512 \
+    python bench.py --workload c4_hcz_d3q19_512 --steps 2 --warmup 3 --no-e2e --no-cpu --no-extras > gpurun_out/r2c_ncu.log 2>&1
+ncu -i gpurun_out/r2c_hcz3d_sweep_512.ncu-rep --page details > gpurun_out/r2c_hcz3d_sweep_512_ncu_full.txt 2>&1
+echo done
