@@ -259,6 +259,11 @@ int  clbm_ring_kind(const clbm_ctx *ctx);
 /* pack + exchange + unpack of ONE halo phase on the launching stream, through whichever ring the context has
  * (phase 2: the node mask after clbm_upload; phase 0 after stage 0: the moment ghosts a field download needs) */
 int  clbm_slab_exchange(clbm_ctx *ctx, int phase);
+/* the two halves of an exchange on a peer ring, for a caller that issues the stages itself: clbm_slab_signal after the stage
+ * that packed `phase`, clbm_slab_wait before the stage that unpacks it; boundary != 0: on the boundary stream (overlap
+ * protocol).  Contexts of one process that share a GPU must issue all signals of a phase before any wait of it. */
+int  clbm_slab_signal(clbm_ctx *ctx, int phase, int boundary);
+int  clbm_slab_wait(clbm_ctx *ctx, int phase, int boundary);
 
 /* ---- compliant-vessel case (CLBM_MODEL_PULSATILE) ---------------------------------------------------
  * Replaces the whole iteration body of PulsatileBloodFlow2D() ("Abbashub LBM/apps/PulsatileBloodFlow2D.h":764-790):

@@ -20,7 +20,7 @@ EXPORTS = [
     "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_diag_contact_angle", "clbm_diag_interface_heights", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
     "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_comm_unique_id", "clbm_comm_init", "clbm_slab_step", "clbm_comm_destroy",
-    "clbm_peer_export", "clbm_peer_connect", "clbm_peer_connect_local", "clbm_peer_disconnect", "clbm_ring_kind", "clbm_slab_exchange", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
+    "clbm_peer_export", "clbm_peer_connect", "clbm_peer_connect_local", "clbm_peer_disconnect", "clbm_ring_kind", "clbm_slab_exchange", "clbm_slab_signal", "clbm_slab_wait", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
     "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
     "clbm_pulsatile_kernel_timing_begin", "clbm_pulsatile_kernel_timing_end", "clbm_pulsatile_download_fields",
@@ -89,6 +89,8 @@ def load_library(path=None):
     lib.clbm_peer_disconnect.argtypes = [vp]
     lib.clbm_ring_kind.argtypes = [vp]
     lib.clbm_slab_exchange.argtypes = [vp, ctypes.c_int]
+    lib.clbm_slab_signal.argtypes = [vp, ctypes.c_int, ctypes.c_int]
+    lib.clbm_slab_wait.argtypes = [vp, ctypes.c_int, ctypes.c_int]
     ip, fp = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float)
     lib.clbm_pulsatile_create.argtypes = [ctypes.POINTER(P.PulsatileParams), ctypes.POINTER(vp)]
     lib.clbm_pulsatile_destroy.argtypes = [vp]
@@ -320,6 +322,12 @@ class Lattice:
 
     def slab_exchange(self, phase):
         self._check(self.lib.clbm_slab_exchange(self._h, int(phase)))
+
+    def slab_signal(self, phase, boundary=False):
+        self._check(self.lib.clbm_slab_signal(self._h, int(phase), 1 if boundary else 0))
+
+    def slab_wait(self, phase, boundary=False):
+        self._check(self.lib.clbm_slab_wait(self._h, int(phase), 1 if boundary else 0))
 
     def overlap_supported(self):
         return bool(self.lib.clbm_overlap_supported(self._h))

@@ -326,7 +326,7 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->device = dev;
     c->Q = is3d ? 19 : 9;
     c->sets = (p->model == CLBM_MODEL_HCZ_D2Q9 || p->model == CLBM_MODEL_HCZ_D3Q19) ? 2 : 1;
-    c->multi = p->nx != p->nx_global;
+    c->multi = p->nx != p->nx_global || env_int("CLBM_FORCE_SLAB") == 1;
     c->parity = 0;
     c->host_parity0 = 0;
     c->steps_taken = 0;

@@ -313,6 +313,7 @@ int hcz3d_collide(clbm_ctx *c)
 bool hcz3d_sweep_shape_ok(const clbm_ctx *c);
 int hcz3d_sweep_launch(clbm_ctx *c, int src);
 long long hcz3d_sweep_edge_doubles(const clbm_ctx *c);
+int hcz3d_sweep_zero_edges(clbm_ctx *c, int set, int x0, int np);
 
 __global__ void __launch_bounds__(256) count_walls_kernel(const uint8_t *__restrict__ flag, long long n, int *out)
 {
@@ -369,10 +370,15 @@ static int hcz3d_sweep_alloc(clbm_ctx *c)
         c->mom[0][m] = c->fld[m];
         if (cudaMalloc(&c->mom[1][m], nb) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (second moment set)"); return CLBM_ENOMEM; }
         CLBM_CUDA(cudaMemsetAsync(c->mom[1][m], 0, nb, c->stream));
-        for (int s = 0; s < 2; ++s) {
-            if (cudaMalloc(&c->mome[s][m], eb) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (edge sums)"); return CLBM_ENOMEM; }
-            CLBM_CUDA(cudaMemsetAsync(c->mome[s][m], 0, eb, c->stream));
+    }
+    for (int s = 0; s < 2; ++s) {
+        // mome[s][0]: edge sums of phi [nx][eplane]; mome[s][1]: of P_term, jx, jy, jz interleaved [nx][eplane][4]
+        if (cudaMalloc(&c->mome[s][0], eb) != cudaSuccess || cudaMalloc(&c->mome[s][1], 4 * eb) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("out of device memory (edge sums)");
+            return CLBM_ENOMEM;
         }
+        if (int rc = hcz3d_sweep_zero_edges(c, s, 0, c->geo.nx)) return rc;
     }
     return 0;
 }
@@ -391,18 +397,15 @@ int hcz3d_stage0(clbm_ctx *c, bool rebuild)
     if (!sweep || rebuild) return hcz3d_moments(c);   // plain sums of every plane into fld[0..4] (= set 0)
     if ((rc = hcz3d_sweep_alloc(c))) return rc;
     const Geom &g = c->geo;
-    const long long ep = hcz3d_sweep_edge_doubles(c) / g.nx;
     if (!c->mom_valid) {
         if ((rc = hcz3d_moments(c))) return rc;
-        for (int m = 0; m < 5; ++m) CLBM_CUDA(cudaMemsetAsync(c->mome[0][m], 0, (size_t)ep * g.nx * sizeof(double), c->stream));
+        if ((rc = hcz3d_sweep_zero_edges(c, 0, 0, g.nx))) return rc;
         c->mom_src = 0;
     } else {
         if ((rc = hcz3d_moments_planes(c, c->mom_src, 0, 1))) return rc;
         if ((rc = hcz3d_moments_planes(c, c->mom_src, g.nx - 1, 1))) return rc;
-        for (int m = 0; m < 5; ++m) {
-            CLBM_CUDA(cudaMemsetAsync(c->mome[c->mom_src][m], 0, (size_t)ep * sizeof(double), c->stream));
-            CLBM_CUDA(cudaMemsetAsync(c->mome[c->mom_src][m] + (size_t)ep * (g.nx - 1), 0, (size_t)ep * sizeof(double), c->stream));
-        }
+        if ((rc = hcz3d_sweep_zero_edges(c, c->mom_src, 0, 1))) return rc;
+        if ((rc = hcz3d_sweep_zero_edges(c, c->mom_src, g.nx - 1, 1))) return rc;
     }
     c->sweep_active = 1;
     return 0;
@@ -418,8 +421,7 @@ int hcz3d_step(clbm_ctx *c)
         if (!c->mom_valid) {
             // first step on this state: plain sums into set 0 (= fld[0..4]), whose edge sums are therefore zero
             if ((rc = hcz3d_moments(c))) return rc;
-            const size_t eb = (size_t)hcz3d_sweep_edge_doubles(c) * sizeof(double);
-            for (int m = 0; m < 5; ++m) CLBM_CUDA(cudaMemsetAsync(c->mome[0][m], 0, eb, c->stream));
+            if ((rc = hcz3d_sweep_zero_edges(c, 0, 0, c->geo.nx))) return rc;
             c->mom_src = 0;
         }
         if ((rc = hcz3d_sweep_launch(c, c->mom_src))) return rc;

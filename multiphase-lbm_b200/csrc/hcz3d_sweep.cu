@@ -35,7 +35,9 @@ struct SweepOut {
     double *fout[19];
     double *gout[19];
 };
-struct SweepMom { double *m[5]; double *e[5]; };   // phi, P_term, jx, jy, jz: node arrays [ncs] and edge arrays [nx][eplane]
+// phi, P_term, jx, jy, jz: node arrays m[5] of [ncs]; edge sums of phi in ephi[nx][eplane]; edge sums of the other four
+// moments INTERLEAVED in e4[nx][eplane][4] (one address, four consecutive loads / two 16-byte stores per slot)
+struct SweepMom { double *m[5]; double *ephi; double *e4; };
 
 template <int TY, int TZ>
 struct SweepCfg {
@@ -208,9 +210,11 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         for (int j = 0; j < 3; ++j)
             if (w_idx[j] >= 0) phi_n[j] = Min.m[0][base + w_yz[j]];
         if (w_idx[2] >= 0 && has_edges(xg)) {
-            const double *E = Min.e[0] + (size_t)g.wx(xg) * eg.eplane;
+            const double *E = Min.ephi + (size_t)g.wx(xg) * eg.eplane;
+            phi_e[0] = phi_e[1] = phi_e[2] = 0.0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) phi_e[q] = w_e[q] >= 0 ? E[w_e[q]] : 0.0;
+            for (int q = 0; q < 3; ++q)
+                if (w_e[q] >= 0) phi_e[q] = E[w_e[q]];      // (an if, not a ?: -- the select of a ?: waits for the load at once)
         } else {
             phi_e[0] = phi_e[1] = phi_e[2] = 0.0;
         }
@@ -223,37 +227,46 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     auto pf_l2 = [](const double *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); };
     auto prefetch_mom = [&](int xg) {
         const int base = xs_of(xg) * plane;
-        const bool ed = has_edges(xg);
-        const size_t eb = (size_t)g.wx(xg) * eg.eplane;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             pf_l2(Min.m[m + 1] + base + yz);
             if (h_warp) pf_l2(Min.m[m + 1] + base + h1_yz);
-            if (ed) {
-                const double *E = Min.e[m + 1] + eb;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (own_e[q] >= 0) pf_l2(E + own_e[q]);
-                    if (h_warp && h1_e[q] >= 0) pf_l2(E + h1_e[q]);
-                }
-            }
+        }
+        if (has_edges(xg)) {   // the row slots (every lane of the first / last row of the tile, most ring cells); the rest are two lanes per warp
+            const double *E = Min.e4 + (size_t)g.wx(xg) * eg.eplane * 4;
+            if (own_e[0] >= 0) pf_l2(E + (size_t)own_e[0] * 4);
+            if (h_warp && h1_e[0] >= 0) pf_l2(E + (size_t)h1_e[0] * 4);
         }
     };
     auto load_mom = [&](int xg) {
         const int base = xs_of(xg) * plane;
         const bool ed = has_edges(xg);
-        const size_t eb = (size_t)g.wx(xg) * eg.eplane;
+        const double *E = Min.e4 + (size_t)g.wx(xg) * eg.eplane * 4;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-            const double *E = Min.e[m + 1] + eb;
             mo_r[m][0] = Min.m[m + 1][base + yz];
+            mo_r[m][1] = mo_r[m][2] = mo_r[m][3] = 0.0;
+        }
 #pragma unroll
-            for (int q = 0; q < 3; ++q) mo_r[m][q + 1] = (ed && own_e[q] >= 0) ? E[own_e[q]] : 0.0;
-            if (h_warp) {
-                mh_r[m][0] = Min.m[m + 1][base + h1_yz];
+        for (int q = 0; q < 3; ++q)
+            if (ed && own_e[q] >= 0) {
+                const double *Eq = E + (size_t)own_e[q] * 4;
 #pragma unroll
-                for (int q = 0; q < 3; ++q) mh_r[m][q + 1] = (ed && h1_e[q] >= 0) ? E[h1_e[q]] : 0.0;
+                for (int m = 0; m < 4; ++m) mo_r[m][q + 1] = Eq[m];
             }
+        if (h_warp) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                mh_r[m][0] = Min.m[m + 1][base + h1_yz];
+                mh_r[m][1] = mh_r[m][2] = mh_r[m][3] = 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (ed && h1_e[q] >= 0) {
+                    const double *Eq = E + (size_t)h1_e[q] * 4;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) mh_r[m][q + 1] = Eq[m];
+                }
         }
     };
     auto merge_mom = [&]() {
@@ -385,8 +398,10 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     };
     auto store_ring = [&](int xp, const double *v) {
         const size_t i = (size_t)xp * eg.eplane + ring_e;
-#pragma unroll
-        for (int m = 0; m < 5; ++m) Mout.e[m][i] = v[m];
+        Mout.ephi[i] = v[0];
+        double2 *q = reinterpret_cast<double2 *>(Mout.e4 + i * 4);
+        q[0] = make_double2(v[1], v[2]);
+        q[1] = make_double2(v[3], v[4]);
     };
 
     load_phi(-3);
@@ -492,7 +507,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     // ---- x wraps inside the CTA: plane nx-1 still lacks the C group of plane 0 (parked in its slot at the start), plane 0
     //      the A group of plane nx-1 (in the accumulators now).  Same thread wrote those slots: a plain read-modify-write. ----
     if (wrapx) {
-        auto finish = [&](int slot, double *const *arr, size_t i_last, size_t i_first) {
+        auto finish = [&](int slot, auto ref) {   // ref(m, last) -> reference to moment m of the cell in plane nx-1 (last) / plane 0
             const double *Ts = acc + slot, *As = acc + 5 * C::NACC + slot;
             double T[5], A[4];
 #pragma unroll
@@ -501,12 +516,17 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             for (int j = 0; j < 4; ++j) A[j] = As[j * C::NACC];
 #pragma unroll
             for (int m = 0; m < 5; ++m) {
-                arr[m][i_last] = finish_last(T, m, arr[m][i_last]);
-                arr[m][i_first] = finish_first(A, m, arr[m][i_first]);
+                double &l = ref(m, true), &f = ref(m, false);
+                l = finish_last(T, m, l);
+                f = finish_first(A, m, f);
             }
         };
-        finish(tid, Mout.m, (size_t)(nx - 1 + G) * plane + yz, (size_t)G * plane + yz);
-        if (h_act) finish(NT + tid, Mout.e, (size_t)(nx - 1) * eg.eplane + ring_e, (size_t)ring_e);
+        finish(tid, [&](int m, bool last) -> double & { return Mout.m[m][(size_t)((last ? nx - 1 : 0) + G) * plane + yz]; });
+        if (h_act)
+            finish(NT + tid, [&](int m, bool last) -> double & {
+                const size_t i = (size_t)(last ? nx - 1 : 0) * eg.eplane + ring_e;
+                return m == 0 ? Mout.ephi[i] : Mout.e4[i * 4 + (m - 1)];
+            });
     }
 }
 
@@ -541,10 +561,12 @@ int hcz3d_sweep_launch(clbm_ctx *c, int src)
     SweepMom Min, Mout;
     for (int m = 0; m < 5; ++m) {
         Min.m[m] = c->mom[src][m];
-        Min.e[m] = c->mome[src][m];
         Mout.m[m] = c->mom[1 - src][m];
-        Mout.e[m] = c->mome[1 - src][m];
     }
+    Min.ephi = c->mome[src][0];
+    Min.e4 = c->mome[src][1];
+    Mout.ephi = c->mome[1 - src][0];
+    Mout.e4 = c->mome[1 - src][1];
     auto kern = hcz3d_sweep_kernel<SW_TY, SW_TZ>;
     static PerDeviceOnce attr;
     if (attr.need(c->device)) {
@@ -558,6 +580,15 @@ int hcz3d_sweep_launch(clbm_ctx *c, int src)
     return 0;
 }
 
+
+// edge sums of the planes [x0, x0 + np) of set `set` <- 0 (those planes' node arrays hold complete sums)
+int hcz3d_sweep_zero_edges(clbm_ctx *c, int set, int x0, int np)
+{
+    const size_t ep = (size_t)hcz3d_sweep_edge_geom(c).eplane;
+    CLBM_CUDA(cudaMemsetAsync(c->mome[set][0] + ep * x0, 0, ep * np * sizeof(double), c->stream));
+    CLBM_CUDA(cudaMemsetAsync(c->mome[set][1] + 4 * ep * x0, 0, 4 * ep * np * sizeof(double), c->stream));
+    return 0;
+}
 
 // phi of the planes [x0, x0 + np) with the edge sums folded in, densely into dst (the moment-halo pack of an x-slab)
 __global__ void __launch_bounds__(256)

@@ -403,6 +403,36 @@ int clbm_peer_disconnect(clbm_ctx *c)
     return CLBM_OK;
 }
 
+// the two halves of an exchange on a peer ring, for callers that drive the stages themselves: SIGNAL after the pack of the
+// phase, WAIT before its unpack, both on the stream the protocol uses (boundary != 0: the boundary stream of the overlap protocol).
+// Several contexts of ONE process sharing a GPU must issue every signal of a phase before any wait of that phase: a spinning
+// wait kernel may sit in front of another context's signal in a hardware queue the two streams happen to share.
+int clbm_slab_signal(clbm_ctx *c, int phase, int boundary)
+{
+    if (!c || phase < 0 || phase > 2) { set_error("bad argument to clbm_slab_signal"); return CLBM_EINVAL; }
+    if (!c->multi || !c->peer_mode) { set_error("clbm_slab_signal needs an x-slab context on a peer-memory ring"); return CLBM_ESTATE; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = boundary ? (cudaStream_t)clbm_boundary_stream(c) : c->stream;
+    if (!st) { set_error("no boundary stream on this context"); return CLBM_ESTATE; }
+    LaunchScope ls(c, "peer_signal");
+    peer_signal_kernel<<<1, 1, 0, st>>>(flags_of(c->mailbox, c), flags_of(c->peer_base[0], c), flags_of(c->peer_base[1], c), phase);
+    CLBM_CUDA(cudaGetLastError());
+    return CLBM_OK;
+}
+
+int clbm_slab_wait(clbm_ctx *c, int phase, int boundary)
+{
+    if (!c || phase < 0 || phase > 2) { set_error("bad argument to clbm_slab_wait"); return CLBM_EINVAL; }
+    if (!c->multi || !c->peer_mode) { set_error("clbm_slab_wait needs an x-slab context on a peer-memory ring"); return CLBM_ESTATE; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = boundary ? (cudaStream_t)clbm_boundary_stream(c) : c->stream;
+    if (!st) { set_error("no boundary stream on this context"); return CLBM_ESTATE; }
+    LaunchScope ls(c, "peer_wait");
+    peer_wait_kernel<<<1, 1, 0, st>>>(flags_of(c->mailbox, c), phase, peer_timeout_ns(), c->peer_err);
+    CLBM_CUDA(cudaGetLastError());
+    return CLBM_OK;
+}
+
 int clbm_ring_kind(const clbm_ctx *c) { return !c ? 0 : (c->peer_mode ? 2 : (c->comm ? 1 : 0)); }
 
 // pack + exchange + unpack of one halo phase on the launching stream (phase 2: the node mask after an upload; phase 0 after

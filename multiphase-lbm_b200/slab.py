@@ -95,11 +95,23 @@ class LocalRing:
             self._view(right, phase, 0, True).copy_(self._view(r, phase, 1, False))
         self.torch.cuda.synchronize()
 
+    def _peer_phase(self, phase, boundary):
+        """one exchange of the peer ring for all contexts: EVERY signal before ANY wait.  The contexts share one GPU here, and
+        a spinning wait kernel of one context may sit in front of another context's signal in a hardware queue the two
+        streams happen to share; with all signals submitted first no wait can starve (one context per GPU has no such issue:
+        clbm_slab_step then runs whole steps, two per CUDA-graph launch)."""
+        for lat in self.lats:
+            lat.slab_signal(phase, boundary)
+        for lat in self.lats:
+            lat.slab_wait(phase, boundary)
+
     def exchange_flags(self):
         if self.peer:
             for lat in self.lats:
-                lat.slab_exchange(2)
+                lat.halo_pack(2)
+            self._peer_phase(2, False)
             for lat in self.lats:
+                lat.halo_unpack(2)
                 lat.sync()
             return
         for lat in self.lats:
@@ -109,18 +121,23 @@ class LocalRing:
             lat.halo_unpack(2)
             lat.sync()
 
-    def step(self, n=1, overlap=None, chunk=2):
-        """overlap: use the boundary-first protocol (stages 10-12) where the contexts support it; here the exchange is
-        still a synchronous copy, so this only checks the protocol's results, not its timing.
-        Peer ring: every context enqueues `chunk` steps at a time (its wait kernels spin until the neighbours' signals, which
-        this one host thread enqueues right after, so the chunks stay short)."""
+    def step(self, n=1, overlap=None):
+        """overlap: use the boundary-first protocol (stages 10-12) where the contexts support it.  Copy ring: the exchange is a
+        synchronous copy, so this only checks the protocol's results, not its timing.  Peer ring: the stages of all contexts
+        are interleaved with the signal / wait kernels (no host synchronisation anywhere; see _peer_phase for the order)."""
         if self.peer:
-            done = 0
-            while done < n:
-                m = min(chunk, n - done)
+            if overlap is None:
+                overlap = all(lat.overlap_supported() for lat in self.lats)
+            s0, s1, s2 = (10, 11, 12) if overlap else (0, 1, 2)
+            for _ in range(n):
                 for lat in self.lats:
-                    lat.slab_step(m)
-                done += m
+                    lat.step_stage(s0)
+                self._peer_phase(0, overlap)
+                for lat in self.lats:
+                    lat.step_stage(s1)
+                self._peer_phase(1, overlap)
+                for lat in self.lats:
+                    lat.step_stage(s2)
             return
         if overlap is None:
             overlap = all(lat.overlap_supported() for lat in self.lats)
@@ -141,9 +158,9 @@ class LocalRing:
         if self.peer:
             for lat in self.lats:
                 lat.step_stage(20)
+            self._peer_phase(0, False)
             for lat in self.lats:
-                lat.slab_exchange(0)
-            for lat in self.lats:
+                lat.halo_unpack(0)
                 lat.sync()
             return
         for lat in self.lats:

@@ -164,10 +164,7 @@ def test_sweep_on_x_slabs(nranks, peer):
     ring = slab.LocalRing(lats, peer=peer)
     ring.exchange_flags()
     l0 = [lat.launch_count() for lat in lats]
-    if peer:
-        ring.step(steps, chunk=5)
-    else:
-        ring.step(steps)
+    ring.step(steps)
     per_step = [(lat.launch_count() - a) / steps for lat, a in zip(lats, l0)]
     ring.refresh_moment_halo()
     pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)

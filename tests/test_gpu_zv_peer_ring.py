@@ -1,7 +1,7 @@
-"""The library-driven peer-memory ring (csrc/slab_comm.cu) on ONE GPU: R slab contexts of this process are connected with
-clbm_peer_connect_local, so every pack writes straight into the neighbour's mailbox, the exchanges are the flag signal / wait
-kernels, and clbm_slab_step replays two captured steps per CUDA-graph launch -- exactly the code path of a multi-GPU run,
-minus the IPC mapping.  Results must equal the single slab bit for bit."""
+"""The peer-memory ring (csrc/slab_comm.cu) on ONE GPU.  Contexts of this process are connected with clbm_peer_connect_local,
+so every pack writes straight into the neighbour's mailbox and the exchanges are the flag signal / wait kernels -- the code
+path of a multi-GPU run minus the IPC mapping (tools/slab_check.py and bench.py's slab_bit_identical cover that under
+torchrun).  Results must equal the single slab bit for bit."""
 import os
 
 import numpy as np
@@ -41,43 +41,73 @@ def make_ring(prm, case, args, nranks):
     return lats, ring
 
 
-@pytest.mark.parametrize("graph", [1, 0])
 @pytest.mark.parametrize("nranks", [2, 3])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_peer_ring_matches_single_slab(name, nranks, graph):
+def test_peer_ring_matches_single_slab(name, nranks):
+    """R contexts of this process on a peer ring: packs into the neighbours' mailboxes, flag signal / wait kernels, no host
+    synchronisation (the stages of the contexts are interleaved by LocalRing: all signals of a phase before any wait)"""
     mk, case, args, steps = CASES[name]
     prm = mk()
     ref_pops, ref_fields = single_run(prm, case, args, steps)
-    old = os.environ.get("CLBM_SLAB_GRAPH")
-    os.environ["CLBM_SLAB_GRAPH"] = str(graph)          # read once per context, in clbm_create
-    try:
-        lats, ring = make_ring(prm, case, args, nranks)
-    finally:
-        if old is None:
-            os.environ.pop("CLBM_SLAB_GRAPH", None)
-        else:
-            os.environ["CLBM_SLAB_GRAPH"] = old
-    # odd step count, chunks of 7: eager first steps, graph replays (two steps each) and an eager odd step all occur
-    ring.step(steps, chunk=7)
+    lats, ring = make_ring(prm, case, args, nranks)
+    ring.step(steps)
     ring.refresh_moment_halo()
     pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
     fields = {k: np.concatenate([lat.fields()[k] for lat in lats]) for k in ("s0", "ux", "uy", "uz")}
     for lat in lats:
         lat.close()
-    # HCZ D3Q19: the single-sweep kernel sums the moments of an x-boundary plane in a different order than the slab's
-    # boundary-plane pass; everything else is bit-identical
-    if name == "hcz3d_drop":
-        assert _cases.rel_linf(pops, ref_pops) < 1e-13
-        for k in fields:
-            assert _cases.rel_linf(fields[k], ref_fields[k]) < 1e-12, k
-        return
     np.testing.assert_array_equal(pops, ref_pops)
     for k in fields:
         np.testing.assert_array_equal(fields[k], ref_fields[k])
 
 
+class env:
+    def __init__(self, **kw):
+        self.kw = kw
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kw}
+        os.environ.update({k: str(v) for k, v in self.kw.items()})
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("graph", [1, 0])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_self_ring_graph_replay_matches_single_slab(name, graph):
+    """clbm_slab_step itself -- whole steps issued by the library, two steps per CUDA-graph launch from the third step on --
+    on a ring of ONE context that is its own neighbour (CLBM_FORCE_SLAB=1: the full-width lattice runs in x-slab mode, its
+    ghost planes filled through its own mailbox).  This is the code path of a one-GPU-per-process run, without a second
+    context on the GPU whose signal a spinning wait could starve.  Bit-identical to the plain single-slab run."""
+    mk, case, args, steps = CASES[name]
+    prm = mk()
+    ref_pops, ref_fields = single_run(prm, case, args, steps)
+    with env(CLBM_FORCE_SLAB=1, CLBM_SLAB_GRAPH=graph):       # both read once, in clbm_create
+        lat = pkg.clbm.Lattice(prm)
+    lat.init_case(case, args)
+    lat.peer_connect_local(lat, lat)
+    assert lat.ring_kind() == 2
+    l0 = lat.launch_count()
+    for n in (1, 7, 2, 9, steps - 19):          # eager first steps, graph replays, odd leftovers, both parities
+        lat.slab_step(n)
+    per_step = (lat.launch_count() - l0) / steps
+    lat.step_stage(20)
+    lat.slab_exchange(0)
+    pops, fields = lat.in_pops(), lat.fields()
+    lat.close()
+    np.testing.assert_array_equal(pops, ref_pops)
+    for k in ("s0", "ux", "uy", "uz"):
+        np.testing.assert_array_equal(fields[k], ref_fields[k])
+    assert 3 <= per_step <= 16, per_step       # replayed launches are counted too
+
+
 def test_protocols_mix_without_host_synchronisation():
-    """a step of the sequential protocol (stages 0-2 on the launching stream) between steps of the overlap protocol (stages
+    """steps of the sequential protocol (stages 0-2 on the launching stream) between steps of the overlap protocol (stages
     10-12, boundary stream), every call asynchronous: the cross-stream ordering must come from events, not from a host sync
     (the boundary stream has to wait for what the launching stream ran last)"""
     prm = P.sc_params(P.MODEL_SC_D3Q19, 32, 24, 36, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
@@ -85,21 +115,11 @@ def test_protocols_mix_without_host_synchronisation():
     ref_pops, _ = single_run(prm, case, args, 30)
     lats, ring = make_ring(prm, case, args, 2)
     assert all(lat.overlap_supported() for lat in lats)
-
-    def sequential_step():
-        for st, ph in ((0, 0), (1, 1)):
-            for lat in lats:
-                lat.step_stage(st)
-            for lat in lats:
-                lat.slab_exchange(ph)
-        for lat in lats:
-            lat.step_stage(2)
-
     for _ in range(5):
-        ring.step(3, chunk=3)          # overlap protocol (graph replays from the third step on)
-        sequential_step()
-        ring.step(1)
-        sequential_step()
+        ring.step(3, overlap=True)
+        ring.step(1, overlap=False)
+        ring.step(1, overlap=True)
+        ring.step(1, overlap=False)
     pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
     for lat in lats:
         lat.close()
@@ -107,12 +127,12 @@ def test_protocols_mix_without_host_synchronisation():
 
 
 def test_peer_ring_full_plane_slabs_hcz2d_config3_shape():
-    """BASELINE configs[2] plane shape: 4 slabs of 16 columns x 8194 rows, overlap protocol + graph replay, against the single
-    64 x 8194 slab, bit for bit"""
+    """BASELINE configs[2] plane shape: 4 slabs of 16 columns x 8194 rows, overlap protocol, against the single 64 x 8194 slab,
+    bit for bit"""
     prm = P.hcz_params(P.MODEL_HCZ_D2Q9, 64, 8194, 1, ulb=0.04, N=2048, Re=3000.0)
     ref_pops, _ = single_run(prm, P.CASE_HCZ_RT2D, (), 12)
     lats, ring = make_ring(prm, P.CASE_HCZ_RT2D, (), 4)
-    ring.step(12, chunk=4)
+    ring.step(12)
     pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
     for lat in lats:
         lat.close()

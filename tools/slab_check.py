@@ -2,8 +2,8 @@
 """Multi-GPU slab check (run under torchrun, one rank per GPU):
 every rank advances its x-slab over NCCL (DistRing); rank 0 also advances the whole lattice on its own GPU and
 compares the gathered populations bit-for-bit.   torchrun --nproc-per-node N tools/slab_check.py [--native]
---native: the ring driven from the library (clbm_slab_step, csrc/slab_comm.cu) instead of slab.DistRing's Python loop;
-also prints the device time per step of both so that the host-overhead difference is visible."""
+--transport=peer|nccl|torch: the ghost exchange (default peer: the library's peer-memory ring over CUDA IPC with CUDA-graph
+replay; nccl = --native: library-driven ncclSend/ncclRecv; torch: batch_isend_irecv issued from Python)."""
 import os
 import sys
 
@@ -37,7 +37,11 @@ def main():
         sp.device = lr
         lat = clbm.Lattice(sp)
         lat.init_case(case, args)
-        ring = slab.DistRing(lat, rank, world, dev, native="--native" in sys.argv)
+        transport = None
+        for a in sys.argv[1:]:
+            if a.startswith("--transport="):
+                transport = a.split("=", 1)[1]
+        ring = slab.DistRing(lat, rank, world, dev, native="--native" in sys.argv, transport=transport)
         ring.step(steps)
         pops = torch.from_numpy(lat.in_pops()).to(dev)          # [sets, Q, nelem_local]
         sizes = [b[1] - b[0] for b in slab.slab_bounds(prm.nx_global, world)]
@@ -54,7 +58,7 @@ def main():
             single.close()
             same = np.array_equal(full, ref)
             err = np.max(np.abs(full - ref)) / np.max(np.abs(ref))
-            print("%-6s world=%d  bit-identical=%s  rel Linf=%.3e" % (name, world, same, err), flush=True)
+            print("%-6s world=%d  transport=%s  bit-identical=%s  rel Linf=%.3e" % (name, world, ring.transport, same, err), flush=True)
             ok_all = ok_all and same
     dist.barrier()
     dist.destroy_process_group()
