@@ -193,7 +193,17 @@ int  clbm_reduce(clbm_ctx *ctx, int kind, double *out);
  *   height = length of the run of fluid nodes with rho > rho_cut on column nx/2 from base_y up (:499-505).
  * The caller forms theta = atan((b/2)/(R-h)), R = (4h^2+b^2)/(8h) (:513-517).  NULL outputs are skipped. */
 int  clbm_diag_contact_angle(clbm_ctx *ctx, double rho_cut, int *base_y, int *base, int *height);
-/* findInterfaceHeights' scans (PF/apps/rayleighTaylor2D.h:668-708) on the device, HCZ D2Q9, single slab: the largest y in
+/* the same scans on an x-slab, in global x, combined by the caller (two calls on every rank of the ring):
+ *   1. base_y_in = -1:  out4[0] = base_y where this slab owns x = 0, ny elsewhere            -> MIN over the ranks
+ *   2. base_y_in = that minimum: out4[1] = largest x < nx_global/2 on row base_y with rho <= rho_cut here (-1: none)  -> MAX
+ *                                out4[2] = smallest x > nx_global/2 with rho <= rho_cut here (nx_global: none)          -> MIN
+ *                                out4[3] = first y >= base_y on column nx_global/2 that ends the height run (ny where
+ *                                          the slab does not own that column)                                          -> MIN
+ *   base = max(0, out4[2] - out4[1] - 1), height = out4[3] - base_y; base_y >= ny-1: no fluid row, base = height = 0.
+ * (clbm_diag_interface_heights needs no second form: a slab answers 0 for a column it does not own -> MAX over the ranks.) */
+int  clbm_diag_contact_angle_slab(clbm_ctx *ctx, double rho_cut, int base_y_in, int *out4);
+/* findInterfaceHeights' scans (PF/apps/rayleighTaylor2D.h:668-708) on the device, HCZ D2Q9 (on an x-slab: 0 for a column the
+ * slab does not own, combine the ranks with MAX): the largest y in
  * [1, ny-2] with phi <= phi_mid on column x = 0 (the reference stores it in `bubble_y`) and on column x = nx/2 (`spike_y`);
  * 0 when the column has none (the reference initialises both ints from +-0.05). */
 int  clbm_diag_interface_heights(clbm_ctx *ctx, double phi_mid, int *y_at_x0, int *y_at_xmid);

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libclbm.so")
 EXPORTS = [
     "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_upload2", "clbm_download_lattice",
     "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
-    "clbm_profile_step", "clbm_reduce", "clbm_diag_contact_angle", "clbm_diag_interface_heights", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
+    "clbm_profile_step", "clbm_reduce", "clbm_diag_contact_angle", "clbm_diag_contact_angle_slab", "clbm_diag_interface_heights", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
     "clbm_stream", "clbm_overlap_supported", "clbm_boundary_stream", "clbm_comm_unique_id", "clbm_comm_init", "clbm_slab_step", "clbm_comm_destroy",
     "clbm_peer_export", "clbm_peer_connect", "clbm_peer_connect_local", "clbm_peer_disconnect", "clbm_ring_kind", "clbm_slab_exchange", "clbm_slab_signal", "clbm_slab_wait", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
@@ -63,6 +63,7 @@ def load_library(path=None):
     lib.clbm_profile_step.argtypes = [vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float), ctypes.c_int]
     lib.clbm_reduce.argtypes = [vp, ctypes.c_int, dp]
     lib.clbm_diag_contact_angle.argtypes = [vp, ctypes.c_double] + [ctypes.POINTER(ctypes.c_int)] * 3
+    lib.clbm_diag_contact_angle_slab.argtypes = [vp, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     lib.clbm_diag_interface_heights.argtypes = [vp, ctypes.c_double] + [ctypes.POINTER(ctypes.c_int)] * 2
     lib.clbm_halo_buffer.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp),
                                      ctypes.POINTER(ctypes.c_size_t)]
@@ -257,6 +258,12 @@ class Lattice:
         v = [ctypes.c_int(0) for _ in range(3)]
         self._check(self.lib.clbm_diag_contact_angle(self._h, ctypes.c_double(rho_cut), *[ctypes.byref(x) for x in v]))
         return tuple(x.value for x in v)
+
+    def contact_angle_scan_slab(self, rho_cut, base_y_in=-1):
+        """the partial scan of one x-slab in global x (clbm_diag_contact_angle_slab) -> [base_y, lstop, rstop, hstop]"""
+        out = (ctypes.c_int * 4)()
+        self._check(self.lib.clbm_diag_contact_angle_slab(self._h, ctypes.c_double(rho_cut), int(base_y_in), out))
+        return list(out)
 
     def interface_heights(self, phi_mid):
         """device-side scans of findInterfaceHeights (PF/apps/rayleighTaylor2D.h:668-708) -> (y at x = 0, y at x = nx/2)"""

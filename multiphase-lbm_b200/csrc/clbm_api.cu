@@ -66,6 +66,7 @@ LaunchScope::~LaunchScope()
 int sc_fields(clbm_ctx *c, double *s0, double *s1, double *ux, double *uy, double *uz);
 int sc_force_field(clbm_ctx *c, double *fx, double *fy, double *fz);
 int diag_contact_angle(clbm_ctx *c, double rho_cut, int *base_y, int *base, int *height);          // diag_kernels.cu
+int diag_contact_angle_raw(clbm_ctx *c, double rho_cut, int base_y_in, int out[4]);
 int diag_interface_heights(clbm_ctx *c, double phi_mid, int *y_x0, int *y_xmid);
 int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
@@ -733,6 +734,13 @@ int clbm_diag_contact_angle(clbm_ctx *c, double rho_cut, int *base_y, int *base,
     if (!c) { set_error("bad argument to clbm_diag_contact_angle"); return CLBM_EINVAL; }
     CLBM_CUDA(cudaSetDevice(c->device));
     return diag_contact_angle(c, rho_cut, base_y, base, height);
+}
+
+int clbm_diag_contact_angle_slab(clbm_ctx *c, double rho_cut, int base_y_in, int *out4)
+{
+    if (!c || !out4) { set_error("bad argument to clbm_diag_contact_angle_slab"); return CLBM_EINVAL; }
+    CLBM_CUDA(cudaSetDevice(c->device));
+    return diag_contact_angle_raw(c, rho_cut, base_y_in, out4);
 }
 
 int clbm_diag_interface_heights(clbm_ctx *c, double phi_mid, int *y_at_x0, int *y_at_xmid)

@@ -234,27 +234,4 @@ int scatter_node_pops(clbm_ctx *c, int buffer, const long long *idx_dev, const d
 
 inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 
-// x-chunk length of a plane-marching kernel on a SHORT slab (strong scaling: 64 planes, 256 columns per GPU).  The CTAs
-// (tiles x chunks) run in waves of `slots` resident CTAs and every chunk pays `prologue` extra planes, so the step costs about
-// ceil(tiles * chunks / slots) * (chunk + prologue) plane-times: the default chunk, tuned on lattices with dozens of waves
-// (L2 sharing of the halo rows), can land just past a wave boundary here (64 planes in chunks of 24: 11 waves of 26 planes
-// where chunks of 32 need 7 waves of 34).  With many waves the quantisation is noise and the tuned default stays.
-inline int pick_xchunk(int n, long long tiles, long long slots, int prologue, int lo, int hi, int dflt)
-{
-    if (n <= lo) return n;
-    const long long nch_d = (n + dflt - 1) / dflt;
-    if (tiles * nch_d >= 16 * slots) return dflt < n ? dflt : n;
-    long long best = -1;
-    int pick = dflt < n ? dflt : n;
-    for (int nch = 1; nch <= n; ++nch) {
-        const int xc = (n + nch - 1) / nch;          // balanced chunks
-        if (xc > hi) continue;
-        if (xc < lo) break;
-        const long long waves = (tiles * nch + slots - 1) / slots;
-        const long long cost = waves * (xc + prologue);
-        if (best < 0 || cost < best) { best = cost; pick = xc; }
-    }
-    return pick;
-}
-
 }  // namespace clbm

@@ -381,10 +381,7 @@ static int launch_hcz2d_fused(clbm_ctx *c, int x_begin, int x_end)
     // CTAs per SM slot, down to 4 columns (tools/small_lattice_chunks.py at 256 x 1026, bit-identical populations: 29.9 us per
     // step at 8 columns, 24.5 at 4, 26.4 at 2, 31.9 at 1 -- the 4-column prologue of this kernel costs more than the SC one)
     const long long want = 2LL * 148 * MINB;
-    if ((long long)segs * ((ncol + xchunk - 1) / xchunk) < want && (long long)segs * ncol >= 4 * want)
-        xchunk = pick_xchunk(ncol, segs, 148LL * MINB, 4, 8, 64, 48);   // a strong-scaling slab (hundreds of columns): mind the wave boundaries
-    else
-        while (xchunk > 4 && (long long)segs * ((ncol + xchunk - 1) / xchunk) < want) xchunk = xchunk / 2 > 4 ? xchunk / 2 : 4;
+    while (xchunk > 4 && (long long)segs * ((ncol + xchunk - 1) / xchunk) < want) xchunk = xchunk / 2 > 4 ? xchunk / 2 : 4;
     if (c->env.hcz2d_xchunk > 0) xchunk = c->env.hcz2d_xchunk < ncol ? c->env.hcz2d_xchunk : ncol;
     dim3 grid(segs, (ncol + xchunk - 1) / xchunk);
     Hcz2dTables P;

@@ -31,9 +31,11 @@ namespace clbm {
 
 using L19s = D3Q19;
 
+// out buffers of the two population sets: direction k starts at k * ncs.  (An array of 38 pointers in the parameter block costs
+// a constant-bank load per store -- they cannot all stay in registers -- and the store then waits on that load: ncu showed
+// the long-scoreboard stalls of this kernel sitting on exactly those address computations.)
 struct SweepOut {
-    double *fout[19];
-    double *gout[19];
+    double *f, *g;
 };
 // phi, P_term, jx, jy, jz: node arrays m[5] of [ncs]; edge sums of phi in ephi[nx][eplane]; edge sums of the other four
 // moments INTERLEAVED in e4[nx][eplane][4] (one address, four consecutive loads / two 16-byte stores per slot)
@@ -53,11 +55,11 @@ struct SweepCfg {
     static constexpr int SET_BYTES = 19 * NT * 8;
     static constexpr int STAGE_BYTES = 2 * SET_BYTES;
     static constexpr int OFF_PHI = 2 * STAGE_BYTES;                // [4][R3]
-    static constexpr int OFF_LAP = OFF_PHI + 4 * R3 * 8;           // [4][R2]
-    static constexpr int OFF_PP = OFF_LAP + 4 * R2 * 8;            // [4][R2]
-    static constexpr int OFF_PR = OFF_PP + 4 * R2 * 8;             // [3][R1]
-    static constexpr int OFF_ACC = OFF_PR + 3 * R1 * 8;            // [8][NACC]  (the ninth running sum lives in a register)
-    static constexpr int OFF_BAR = ((OFF_ACC + 8 * NACC * 8 + 15) / 16) * 16;
+    static constexpr int OFF_LAP = OFF_PHI + 4 * R3 * 8;           // [3][R2]
+    static constexpr int OFF_PP = OFF_LAP + 3 * R2 * 8;            // [3][R2]
+    static constexpr int OFF_PR = OFF_PP + 3 * R2 * 8;             // [4][R1]
+    static constexpr int OFF_ACC = OFF_PR + 4 * R1 * 8;            // [9][NACC]
+    static constexpr int OFF_BAR = ((OFF_ACC + 9 * NACC * 8 + 15) / 16) * 16;
     static constexpr int SMEM = OFF_BAR + 32;
     static_assert(NH1 <= NT, "one ring cell per thread");
     static_assert(NSPEC <= NT && NPLAIN <= 2 * NT, "window cells per thread");
@@ -103,10 +105,10 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t stage_a = smem_u32(smem_raw);
     double *r_phi = reinterpret_cast<double *>(smem_raw + C::OFF_PHI);   // [4][R3]
-    double *r_lap = reinterpret_cast<double *>(smem_raw + C::OFF_LAP);   // [4][R2]
-    double *r_pp = reinterpret_cast<double *>(smem_raw + C::OFF_PP);     // [4][R2]
-    double *r_pr = reinterpret_cast<double *>(smem_raw + C::OFF_PR);     // [3][R1]
-    double *acc = reinterpret_cast<double *>(smem_raw + C::OFF_ACC);     // [8][NACC]: T0, T1, T3, T4 then A (4), thread-private slots
+    double *r_lap = reinterpret_cast<double *>(smem_raw + C::OFF_LAP);   // [3][R2]
+    double *r_pp = reinterpret_cast<double *>(smem_raw + C::OFF_PP);     // [3][R2]
+    double *r_pr = reinterpret_cast<double *>(smem_raw + C::OFF_PR);     // [4][R1]
+    double *acc = reinterpret_cast<double *>(smem_raw + C::OFF_ACC);     // [9][NACC]: T (5) then A (4), thread-private slots
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
 
     const int tid = threadIdx.x;
@@ -127,7 +129,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         auto plain_col = [](int ci) { return ci < 2 ? ci : (ci < TZ ? ci + 2 : ci + 4); };
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const int n = j == 0 ? tid : NT + (NT - 1 - tid);   // the second round goes to the LAST threads: the first warps own the ring cells
+            const int n = tid + j * NT;
             w_idx[j] = -1;
             w_yz[j] = 0;
             if (n < C::NPLAIN) {
@@ -180,7 +182,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     }
     // accumulators start from zero (group A of the plane before the first one does not exist yet)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 9; ++j) {
         acc[j * C::NACC + tid] = 0.0;
         if (h_act) acc[j * C::NACC + NT + tid] = 0.0;
     }
@@ -221,7 +223,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     };
     // ---- P_term and raw momentum (moments 1..4) of the own node and of the ring cell: loaded RAW (node array + edge slots) at
     //      the top of the iteration that uses them and merged after the gather phase, i.e. with a phase of independent work
-    //      between load and use; (an L2 prefetch one plane earlier was tried: its instructions cost more than the latency they saved.)
+    //      between load and use; (an L2 prefetch one plane earlier was tried: its instructions and LSU queue stalls cost more than the latency saved).
     //      (Holding the raw values across the collide phase instead would cost 32 more registers there.) ----
     double mo_r[4][4], mh_r[4][4], mo_c[4], mh_c[4];
     auto load_mom = [&](int xg) {
@@ -266,7 +268,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     // level 2 of the node at halo-1 position (a1, b1) of plane p; returns psi_rho, fills the node's local set
     auto level2 = [&](int p, int a1, int b1, const double *mo, SweepLocal &o) -> double {
         const int q3 = (a1 + 2) * C::Z3 + (b1 + 2), q2 = (a1 + 1) * C::Z2 + (b1 + 1);
-        const int sm = ((p - 1) & 3) * C::R2, s0 = (p & 3) * C::R2, sp = ((p + 1) & 3) * C::R2;
+        const int sm = mod3(p - 1) * C::R2, s0 = mod3(p) * C::R2, sp = mod3(p + 1) * C::R2;
         double gl[3];
         grad19s<C::Z2>(r_lap + sm, r_lap + s0, r_lap + sp, q2, gl);
         grad19s<C::Z2>(r_pp + sm, r_pp + s0, r_pp + sp, q2, o.gp);
@@ -298,9 +300,8 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     bool c2_on[C::N2];
 #pragma unroll
     for (int j = 0; j < C::N2; ++j) {
-        // round 0: cell tid; later rounds are handed out from the LAST thread down (the first warps own the ring cells)
-        int h = j == 0 ? tid : j * NT + (NT - 1 - tid);
-        c2_on[j] = j == 0 ? true : (j * NT + (NT - 1 - (tid | 31))) < C::R2;   // warp-uniform: does any lane of this warp have a cell
+        int h = tid + j * NT;
+        c2_on[j] = ((tid & ~31) + j * NT) < C::R2;   // warp-uniform
         if (h >= C::R2) h = tid;
         const int a2 = h / C::Z2, b2 = h % C::Z2;
         c2_q2[j] = h;
@@ -311,7 +312,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     auto collide = [&](int x, double *sf) {
         const int q1 = (ty + 1) * C::Z1 + tz + 1;
         double ge[3];
-        grad19s<C::Z1>(r_pr + mod3(x - 1) * C::R1, r_pr + mod3(x) * C::R1, r_pr + mod3(x + 1) * C::R1, q1, ge);
+        grad19s<C::Z1>(r_pr + ((x - 1) & 3) * C::R1, r_pr + (x & 3) * C::R1, r_pr + ((x + 1) & 3) * C::R1, q1, ge);
         const double phi = cur.phi, rho = cur.rho;
         const double u0 = cur.u0, u1 = cur.u1, u2 = cur.u2, Pt = cur.Pt;
         const double usqr = 1.5 * (u0 * u0 + u1 * u1 + u2 * u2);
@@ -329,6 +330,8 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         const int xp = g.wx(x + 1), xm = g.wx(x - 1);
         const int i = (x + G) * plane + yz;
         const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
+        double *const fo = P.f, *const go = P.g;
+        const size_t ncs = (size_t)g.ncs;
 #pragma unroll
         for (int k = 0; k < 19; ++k) {
             const double fk = sf[k * NT];
@@ -339,8 +342,8 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const double Gam = fma(-t, usqr, t);
                 pf = fma(Gam, opg, om1 * fk);
                 pg = fma(om1, gk, (omega * t) * fma(-rho3, usqr, Pt)) - fma(Gam, uD, t * uE);
-                P.fout[k][i] = pf;
-                P.gout[k][i] = pg;
+                fo[(size_t)k * ncs + i] = pf;
+                go[(size_t)k * ncs + i] = pg;
             } else {
                 const bool axis = (L19s::cx(k) != 0) + (L19s::cy(k) != 0) + (L19s::cz(k) != 0) == 1;
                 const double cu = cdot<L19s>(k, u0, u1, u2);
@@ -353,8 +356,8 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 pg = fma(t, dE, fma(Gam, dD, fma(om1, gk, fma(axis ? Ba : Bd, poly, axis ? Aa : Ad))));
                 const int off = (L19s::cx(k) < 0 ? oxm : (L19s::cx(k) > 0 ? oxp : 0)) + (L19s::cy(k) < 0 ? oym : (L19s::cy(k) > 0 ? oyp : 0)) +
                                 (L19s::cz(k) < 0 ? ozm : (L19s::cz(k) > 0 ? ozp : 0));
-                P.fout[k][i + off] = pf;
-                P.gout[k][i + off] = pg;
+                fo[(size_t)k * ncs + (i + off)] = pf;
+                go[(size_t)k * ncs + (i + off)] = pg;
             }
             sf[k * NT] = pf;             // the gather of the next iteration reads these
             sf[(19 + k) * NT] = pg;
@@ -363,17 +366,18 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
 
     // S5 for one cell: `slot` = its accumulator slot, (dy, dz) = its tile coordinates, xsrc = the plane whose pushes are in S.
     // Completes plane xsrc-1 and hands it to `store(plane, values[5])`.
-    double tpa_own = 0.0, tpa_ring = 0.0;   // the ninth running sum of a cell (P_term of group A, for jx): a register each
-    auto accumulate = [&](const PushSums &s, int slot, double &tpa, int xsrc, auto store) {
-        double *Ts = acc + slot, *As = acc + 4 * C::NACC + slot;    // Ts[j * NACC] = T0, T1, T3, T4; As[j * NACC] = A0..A3
+    auto accumulate = [&](const PushSums &s, int slot, int xsrc, auto store) {
+        double *Ts = acc + slot, *As = acc + 5 * C::NACC + slot;    // Ts[j * NACC], As[j * NACC]
         double T[5], A[4], v[5];
-        T[0] = Ts[0]; T[1] = Ts[C::NACC]; T[2] = tpa; T[3] = Ts[2 * C::NACC]; T[4] = Ts[3 * C::NACC];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) T[j] = Ts[j * C::NACC];
 #pragma unroll
         for (int j = 0; j < 4; ++j) A[j] = As[j * C::NACC];
         fold_pushes(T, A, s, xsrc == 0, v);
         if (xsrc >= 1) store(xsrc - 1, v);
         else if (wrapx) store(nx - 1, v);      // parked: completed after the march
-        Ts[0] = T[0]; Ts[C::NACC] = T[1]; tpa = T[2]; Ts[2 * C::NACC] = T[3]; Ts[3 * C::NACC] = T[4];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) Ts[j * C::NACC] = T[j];
 #pragma unroll
         for (int j = 0; j < 4; ++j) As[j * C::NACC] = A[j];
     };
@@ -391,23 +395,22 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     };
 
     load_phi(-3);
-    // x = plane being collided; the first seven iterations only fill the pipeline, the last one only gathers plane nx-1.
-    // Two barriers per plane: between them S5, S2 and S3 are independent of each other (S3 reads the lap / psi planes S2
-    // wrote in EARLIER iterations), so the warps with ring cells overlap their extra work with the others' instead of
-    // holding them at a third barrier.
-    for (int x = -7; x <= nx; ++x) {
-        // ---- S1: phi of plane x+4 from the registers (edge sums added now), then the loads of plane x+5; raw moments of
-        //      plane x+1 for S3 of THIS iteration ----
-        const bool s3_on = x >= -2 && x < nx;
-        if (x + 4 <= nx + 2) {
-            double *dst = r_phi + ((x + 4) & 3) * C::R3;
+    // x = plane being collided; the first six iterations only fill the pipeline, the last one only gathers plane nx-1
+    for (int x = -6; x <= nx; ++x) {
+        // ---- S1: phi of plane x+3 from the registers (edge sums added now), then prefetch the next plane's; raw moments of
+        //      plane x+1 for S3 of THIS iteration, L2 prefetch of plane x+2's ----
+        const bool s3_on = x + 1 >= -1 && x < nx;
+        if (x < nx) {
+            double *dst = r_phi + ((x + 3) & 3) * C::R3;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 if (w_idx[j] >= 0) dst[w_idx[j]] = phi_n[j];
             if (w_idx[2] >= 0) dst[w_idx[2]] = ((phi_n[2] + phi_e[0]) + phi_e[1]) + phi_e[2];
-            if (x + 5 <= nx + 2) load_phi(x + 5);
+            if (x + 1 < nx) load_phi(x + 4);
+            if (s3_on) {
+                load_mom(x + 1);
+            }
         }
-        if (s3_on) load_mom(x + 1);
         __syncthreads();
 
         // ---- S5: what plane x-1 pushed (its post-collision values are in its stage) ----
@@ -415,7 +418,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             const double *S = reinterpret_cast<const double *>(smem_raw + ((x - 1) & 1) * C::STAGE_BYTES);
             PushSums ps;
             gather_pushes<TY, TZ>(S, ty, tz, ps);
-            accumulate(ps, tid, tpa_own, x - 1, store_own);
+            accumulate(ps, tid, x - 1, store_own);
             if (h_act) {
                 // ring cell: only the directions leaving the tile through that side can contribute
                 const int dy = h1y - 1, dz = h1z - 1;
@@ -423,12 +426,13 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 else if (tid < 2 * C::Z1) gather_pushes<TY, TZ, 1, 2>(S, dy, dz, ps);      // row above
                 else if ((tid - 2 * C::Z1) & 1) gather_pushes<TY, TZ, 2, 1>(S, dy, dz, ps);   // column behind the last one
                 else gather_pushes<TY, TZ, 2, -1>(S, dy, dz, ps);                          // column before the first one
-                accumulate(ps, NT + tid, tpa_ring, x - 1, store_ring);
+                accumulate(ps, NT + tid, x - 1, store_ring);
             }
         }
-        // ---- S2: lap(phi), psi(phi) of plane x+3 on tile + halo 2 (used by S3 from the NEXT iteration on) ----
-        if (x + 3 >= -2 && x + 3 <= nx + 1) {
-            const int p = x + 3;
+        if (s3_on) merge_mom();   // the loads of S1 have had the whole gather phase to land
+        // ---- S2: lap(phi), psi(phi) of plane x+2 on tile + halo 2 ----
+        if (x + 2 >= -2 && x < nx) {
+            const int p = x + 2;
             const double *Pm = r_phi + ((p - 1) & 3) * C::R3, *P0 = r_phi + (p & 3) * C::R3, *Pp = r_phi + ((p + 1) & 3) * C::R3;
             double lap_v[C::N2], pp_v[C::N2];
 #pragma unroll
@@ -450,7 +454,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 lap_v[j] = 6.0 * ((1. / 18.) * (sa[0] + sa[1]) + (1. / 36.) * (sd[0] + sd[1]) - (2. / 3.) * phi_c);
                 pp_v[j] = hcz_psi1(phi_c, mp.a, mp.b);
             }
-            const int sl = (p & 3) * C::R2;
+            const int sl = mod3(p) * C::R2;
 #pragma unroll
             for (int j = 0; j < C::N2; ++j) {
                 if (!c2_on[j]) continue;
@@ -458,10 +462,16 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 r_pp[sl + c2_q2[j]] = pp_v[j];
             }
         }
-        // ---- S3: level 2 of plane x+1 on tile + halo 1 (the moment loads of S1 have had S5 and S2 to land) ----
+        __syncthreads();
+        // the stage of plane x-1 has been gathered: refill it with plane x+1 (generic-proxy accesses before the async write)
+        if (tid == 0 && x >= 1 && x + 1 < nx) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(x + 1);
+        }
+
+        // ---- S3: level 2 of plane x+1 on tile + halo 1 ----
         if (s3_on) {
-            merge_mom();
-            double *pr = r_pr + mod3(x + 1) * C::R1;
+            double *pr = r_pr + ((x + 1) & 3) * C::R1;
             if (h_warp) {
                 SweepLocal tmp;
                 const double a = level2(x + 1, ty + 1, tz + 1, mo_c, nxt);
@@ -473,11 +483,6 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             }
         }
         __syncthreads();
-        // the stage of plane x-1 has been gathered: refill it with plane x+1 (generic-proxy accesses before the async write)
-        if (tid == 0 && x >= 1 && x + 1 < nx) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(x + 1);
-        }
 
         // ---- S4: collide + push plane x ----
         if (x >= 0 && x < nx) {
@@ -490,10 +495,11 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     // ---- x wraps inside the CTA: plane nx-1 still lacks the C group of plane 0 (parked in its slot at the start), plane 0
     //      the A group of plane nx-1 (in the accumulators now).  Same thread wrote those slots: a plain read-modify-write. ----
     if (wrapx) {
-        auto finish = [&](int slot, double tpa, auto ref) {   // ref(m, last) -> moment m of the cell in plane nx-1 (last) / plane 0
-            const double *Ts = acc + slot, *As = acc + 4 * C::NACC + slot;
-            const double T[5] = {Ts[0], Ts[C::NACC], tpa, Ts[2 * C::NACC], Ts[3 * C::NACC]};
-            double A[4];
+        auto finish = [&](int slot, auto ref) {   // ref(m, last) -> reference to moment m of the cell in plane nx-1 (last) / plane 0
+            const double *Ts = acc + slot, *As = acc + 5 * C::NACC + slot;
+            double T[5], A[4];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) T[j] = Ts[j * C::NACC];
 #pragma unroll
             for (int j = 0; j < 4; ++j) A[j] = As[j * C::NACC];
 #pragma unroll
@@ -503,9 +509,9 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 f = finish_first(A, m, f);
             }
         };
-        finish(tid, tpa_own, [&](int m, bool last) -> double & { return Mout.m[m][(size_t)((last ? nx - 1 : 0) + G) * plane + yz]; });
+        finish(tid, [&](int m, bool last) -> double & { return Mout.m[m][(size_t)((last ? nx - 1 : 0) + G) * plane + yz]; });
         if (h_act)
-            finish(NT + tid, tpa_ring, [&](int m, bool last) -> double & {
+            finish(NT + tid, [&](int m, bool last) -> double & {
                 const size_t i = (size_t)(last ? nx - 1 : 0) * eg.eplane + ring_e;
                 return m == 0 ? Mout.ephi[i] : Mout.e4[i * 4 + (m - 1)];
             });
@@ -535,11 +541,7 @@ int hcz3d_sweep_launch(clbm_ctx *c, int src)
     const cuuint32_t box[4] = {(cuuint32_t)SW_TZ, (cuuint32_t)SW_TY, 1, 19};
     for (int s = 0; s < 2; ++s)
         if (int rc = cached_tmap(c, c->pop[s][c->parity], box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, &tm[s])) return rc;
-    SweepOut P;
-    for (int k = 0; k < 19; ++k) {
-        P.fout[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
-        P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
-    }
+    const SweepOut P = {c->pop[0][1 - c->parity], c->pop[1][1 - c->parity]};
     SweepMom Min, Mout;
     for (int m = 0; m < 5; ++m) {
         Min.m[m] = c->mom[src][m];

@@ -293,7 +293,6 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
     // profiles/README.md).  (tiles is only used to keep at least one full wave of CTAs.)
     int xchunk = nxr < 24 ? nxr : 24;
     if ((long long)tiles * ((nxr + xchunk - 1) / xchunk) < 148LL * MINB && nxr > 8) xchunk = 8;
-    else xchunk = pick_xchunk(nxr, tiles, 148LL * MINB, 2, 8, 64, 24);   // short slabs: mind the wave boundaries
     if (c->env.sc_xchunk > 0) xchunk = c->env.sc_xchunk < nxr ? c->env.sc_xchunk : nxr;
     const int nch1 = (nxr + xchunk - 1) / xchunk, nch2 = x2_end > x2_begin ? (x2_end - x2_begin + xchunk - 1) / xchunk : 0;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, nch1 + nch2);

@@ -61,6 +61,16 @@ def as_torch(ptr, nbytes, device):
     return torch.as_tensor(CudaBuffer(ptr, nbytes), device=device)
 
 
+def combine_contact_angle(ny, first, second):
+    """the two rounds of clbm_diag_contact_angle_slab of all slabs -> (base_y, base, height) of calculateContactAngle
+    (SC/apps/contactAngle2D.h:465-505); `second` is None when the first round found no fluid row"""
+    base_y = min(r[0] for r in first)
+    if base_y >= ny - 1 or second is None:
+        return base_y, 0, 0
+    lstop, rstop, hstop = max(r[1] for r in second), min(r[2] for r in second), min(r[3] for r in second)
+    return base_y, max(0, rstop - lstop - 1), hstop - base_y
+
+
 class LocalRing:
     """R slab contexts in one process; the exchange is a device-to-device copy per neighbour pair."""
 
@@ -151,6 +161,19 @@ class LocalRing:
             self.exchange(1)
             for lat in self.lats:
                 lat.step_stage(s2)
+
+    def contact_angle_scan(self, rho_cut):
+        """calculateContactAngle's scans over all slabs (two rounds per slab, combined here)"""
+        ny = self.lats[0].p.ny
+        first = [lat.contact_angle_scan_slab(rho_cut, -1) for lat in self.lats]
+        base_y = min(r[0] for r in first)
+        second = [lat.contact_angle_scan_slab(rho_cut, base_y) for lat in self.lats] if base_y < ny - 1 else None
+        return combine_contact_angle(ny, first, second)
+
+    def interface_heights(self, phi_mid):
+        """findInterfaceHeights over all slabs: a slab answers 0 for a column it does not own"""
+        r = [lat.interface_heights(phi_mid) for lat in self.lats]
+        return max(v[0] for v in r), max(v[1] for v in r)
 
     def refresh_moment_halo(self):
         """make the moments and their ghosts valid for the current populations (needed before fields()); stage 20 = stage 0
@@ -279,6 +302,31 @@ class DistRing:
         self.exchange(2)
         self.lat.halo_unpack(2)
         self.lat.sync()
+
+    def contact_angle_scan(self, rho_cut):
+        """calculateContactAngle's scans over the ring: two rounds on every rank, MIN / MAX all-reduces in between"""
+        torch, dist = self.torch, self.dist
+        ny = self.lat.p.ny
+        first = self.lat.contact_angle_scan_slab(rho_cut, -1)
+        t = torch.tensor([first[0]], dtype=torch.int64, device=self.dev)
+        if self.R > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        base_y = int(t.item())
+        if base_y >= ny - 1:
+            return base_y, 0, 0
+        r = self.lat.contact_angle_scan_slab(rho_cut, base_y)
+        t = torch.tensor([r[1], -r[2], -r[3]], dtype=torch.int64, device=self.dev)      # one MAX for max / min / min
+        if self.R > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lstop, rstop, hstop = int(t[0]), -int(t[1]), -int(t[2])
+        return base_y, max(0, rstop - lstop - 1), hstop - base_y
+
+    def interface_heights(self, phi_mid):
+        torch, dist = self.torch, self.dist
+        t = torch.tensor(list(self.lat.interface_heights(phi_mid)), dtype=torch.int64, device=self.dev)
+        if self.R > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t[0]), int(t[1])
 
     def _init_peer(self):
         """all-gather the 128-byte mailbox handles, map both ring neighbours (clbm_peer_connect), barrier"""

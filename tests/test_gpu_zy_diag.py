@@ -167,3 +167,45 @@ def test_driver_sc_rayleigh_taylor_energy_matches_oracle(tmp_path):
     e_drv = np.loadtxt(tmp_path / "energy.dat")[1, 1]
     assert np.isfinite(e_ref) and e_ref > 0
     assert abs(e_drv - e_ref) <= 2e-7 * abs(e_ref)       # energy.dat holds 8 significant digits
+
+
+@pytest.mark.parametrize("nranks", [2, 3, 5])
+def test_scans_on_x_slabs_equal_the_single_slab_scans(nranks):
+    """the slab forms of both scans (partial integers per slab in global x, MIN / MAX combined by the caller) against the
+    single-slab scans of the same state: the droplet base straddles slab borders, the centre column lies in one slab"""
+    slab = pkg.slab
+    nx, ny = 120, 48
+    prm = P.sc_params(P.MODEL_SC_D2Q9, nx, ny, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    args = (0.265, 0.038, 22.0)
+    cut = 0.5 * (0.265 + 0.038)
+    with pkg.clbm.Lattice(prm) as single:
+        single.init_case(P.CASE_SC_CONTACT2D, args)
+        single.step(60)
+        ref = [single.contact_angle_scan(c) for c in (cut, 0.01, 1.0)]
+    lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, nranks)) for r in range(nranks)]
+    for lat in lats:
+        lat.init_case(P.CASE_SC_CONTACT2D, args)
+    ring = slab.LocalRing(lats)
+    ring.step(60)
+    got = [ring.contact_angle_scan(c) for c in (cut, 0.01, 1.0)]
+    with pytest.raises(pkg.clbm.ClbmError):
+        lats[0].contact_angle_scan(cut)            # the one-call form is for a single slab
+    for lat in lats:
+        lat.close()
+    assert got == ref and ref[0][1] > 30
+
+    prm = P.hcz_params(P.MODEL_HCZ_D2Q9, 60, 242, N=60)
+    mid = 0.5 * (prm.phi_l + prm.phi_g)
+    with pkg.clbm.Lattice(prm) as single:
+        single.init_case(P.CASE_HCZ_RT2D, ())
+        single.step(100)
+        ref = single.interface_heights(mid)
+    lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, nranks)) for r in range(nranks)]
+    for lat in lats:
+        lat.init_case(P.CASE_HCZ_RT2D, ())
+    ring = slab.LocalRing(lats)
+    ring.step(100)
+    got = ring.interface_heights(mid)
+    for lat in lats:
+        lat.close()
+    assert got == ref and ref[0] > 0 and ref[1] > 0
