@@ -159,18 +159,14 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     }
     // ---- the ring cell of this thread (first NH1 threads), in halo-1 coordinates; its edge slot; the edge slots of the
     //      P_term / momentum reads of the own node and of the ring cell ----
-    // ring cell number rq of the LAST threads (rq = 0 is thread NT-1): the first warps already carry the border nodes of the
-    // phi window and the second round of S2, so the ring duties (extra level-2 evaluation, extra gather, extra loads) go to
-    // the other end of the CTA
-    const int rq = NT - 1 - tid;
-    const bool h_act = rq < C::NH1;
+    const bool h_act = tid < C::NH1;
     int h1y = 0, h1z = 0;
     if (h_act) {
-        if (rq < C::Z1) { h1y = 0; h1z = rq; }
-        else if (rq < 2 * C::Z1) { h1y = C::Y1 - 1; h1z = rq - C::Z1; }
-        else { const int q = rq - 2 * C::Z1; h1y = 1 + (q >> 1); h1z = (q & 1) ? C::Z1 - 1 : 0; }
+        if (tid < C::Z1) { h1y = 0; h1z = tid; }
+        else if (tid < 2 * C::Z1) { h1y = C::Y1 - 1; h1z = tid - C::Z1; }
+        else { const int q = tid - 2 * C::Z1; h1y = 1 + (q >> 1); h1z = (q & 1) ? C::Z1 - 1 : 0; }
     }
-    const bool h_warp = (tid >> 5) >= ((NT - C::NH1) >> 5);
+    const bool h_warp = (tid >> 5) <= ((C::NH1 - 1) >> 5);
     if (h_warp && !h_act) { h1y = ty + 1; h1z = tz + 1; }
     const int h1_yy = wrapn(y0 + h1y - 1, ny), h1_zz = wrapn(z0 + h1z - 1, nz);
     const int h1_yz = h1_yy * nz + h1_zz;
@@ -188,7 +184,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
         acc[j * C::NACC + tid] = 0.0;
-        if (h_act) acc[j * C::NACC + NT + rq] = 0.0;
+        if (h_act) acc[j * C::NACC + NT + tid] = 0.0;
     }
     __syncthreads();
     auto issue = [&](int x) {   // populations of plane x (both sets) into stage x & 1
@@ -426,11 +422,11 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             if (h_act) {
                 // ring cell: only the directions leaving the tile through that side can contribute
                 const int dy = h1y - 1, dz = h1z - 1;
-                if (rq < C::Z1) gather_pushes<TY, TZ, -1, 2>(S, dy, dz, ps);              // row below the tile
-                else if (rq < 2 * C::Z1) gather_pushes<TY, TZ, 1, 2>(S, dy, dz, ps);      // row above
-                else if ((rq - 2 * C::Z1) & 1) gather_pushes<TY, TZ, 2, 1>(S, dy, dz, ps);   // column behind the last one
+                if (tid < C::Z1) gather_pushes<TY, TZ, -1, 2>(S, dy, dz, ps);              // row below the tile
+                else if (tid < 2 * C::Z1) gather_pushes<TY, TZ, 1, 2>(S, dy, dz, ps);      // row above
+                else if ((tid - 2 * C::Z1) & 1) gather_pushes<TY, TZ, 2, 1>(S, dy, dz, ps);   // column behind the last one
                 else gather_pushes<TY, TZ, 2, -1>(S, dy, dz, ps);                          // column before the first one
-                accumulate(ps, NT + rq, x - 1, store_ring);
+                accumulate(ps, NT + tid, x - 1, store_ring);
             }
         }
         if (s3_on) merge_mom();   // the loads of S1 have had the whole gather phase to land
@@ -515,7 +511,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         };
         finish(tid, [&](int m, bool last) -> double & { return Mout.m[m][(size_t)((last ? nx - 1 : 0) + G) * plane + yz]; });
         if (h_act)
-            finish(NT + rq, [&](int m, bool last) -> double & {
+            finish(NT + tid, [&](int m, bool last) -> double & {
                 const size_t i = (size_t)(last ? nx - 1 : 0) * eg.eplane + ring_e;
                 return m == 0 ? Mout.ephi[i] : Mout.e4[i * 4 + (m - 1)];
             });
