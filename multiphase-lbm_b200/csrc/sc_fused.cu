@@ -37,9 +37,7 @@ template <class L> struct PopTable {
 // GUO = true: the Rayleigh-Taylor variant (SC/apps/RayleighTaylor2D.h; psi = 1 - exp(-rho), a wall neighbour
 // contributes the psi of the opposite neighbour, Guo forcing) -- a compile-time flag, the Yuan-CS code is unchanged.
 // MRT = true: CLBM_COLLISION_MRT for D2Q9 (sc_collide_mrt), likewise a compile-time flag.
-// DEEP = true: the own populations of plane x+2 are loaded into a third register set one iteration BEFORE their density is
-// needed (fill() consumes its loads at once: with 16 warps per SM every plane then waits for memory).  Nine more registers.
-template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false, int PF = 2, bool DEEP = false>
+template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false, int PF = 2>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const double *__restrict__ psi_g, Geom g,
                 ModelParams mp, int xchunk)
@@ -65,7 +63,7 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
 
     // psi (or -1 for a wall) of storage plane xs into ring slot `slot`.  The thread's own populations stay in
     // fk, its own psi / G1 branch in ps / gp (used when that plane is collided one iteration later).
-    auto fill = [&](int xs, int slot, double *fk, double &ps, bool &gp, bool preloaded = false) {
+    auto fill = [&](int xs, int slot, double *fk, double &ps, bool &gp) {
         if (!g.wrapx && (xs < G || xs >= g.nx + G)) {
             // x-slab mode: ghost plane of the neighbour slab -> psi from the exchanged moment halo, mask from flag[]
             if (inside) {
@@ -87,10 +85,8 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
         }
         if (inside) {
             const int i = xs * plane + yz;
-            if (!preloaded) {
 #pragma unroll
-                for (int k = 0; k < L::Q; ++k) fk[k] = P.in[k][i];
-            }
+            for (int k = 0; k < L::Q; ++k) fk[k] = P.in[k][i];
             double v = -1.0;
             ps = 0.0;
             gp = true;
@@ -133,26 +129,9 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
     const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
     const int ozm = g.wz(z - 1) - z, ozp = g.wz(z + 1) - z;
 
-    // DEEP: raw own populations of the plane after next (no use until the next iteration)
-    double fnn[DEEP ? L::Q : 1];
-    auto own_plane_loadable = [&](int xs) { return inside && (g.wrapx || (xs >= G && xs < g.nx + G)); };
-    auto load_own = [&](int xs, double *fk) {
-        if (own_plane_loadable(xs)) {
-            const int i = xs * plane + yz;
-#pragma unroll
-            for (int k = 0; k < L::Q; ++k) fk[k] = P.in[k][i];
-        }
-    };
-    if constexpr (DEEP) load_own(g.wx(xa + 1) + G, fn);
-
     for (int x = xa; x < xb; ++x) {
         const int xp = g.wx(x + 1), xm = g.wx(x - 1);
-        if constexpr (DEEP) {
-            fill(xp + G, (x + 1) & 3, fn, psn, gpn, own_plane_loadable(xp + G));   // fn was loaded one iteration ago
-            load_own(g.wx(xp + 1) + G, fnn);
-        } else {
-            fill(xp + G, (x + 1) & 3, fn, psn, gpn);
-        }
+        fill(xp + G, (x + 1) & 3, fn, psn, gpn);
         // The loads of fill() are consumed at once (psi needs the density), so every plane pays a full memory latency with
         // only 16 warps per SM to hide it (ncu at 8192^2, D2Q9: DRAM at 47 %, top stall long_scoreboard).  Pull the plane
         // two further on into L2 now: those loads then wait for an L2 hit instead of HBM.  No registers, no shared memory.
@@ -202,10 +181,6 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
         }
 #pragma unroll
         for (int k = 0; k < L::Q; ++k) fc[k] = fn[k];
-        if constexpr (DEEP) {
-#pragma unroll
-            for (int k = 0; k < L::Q; ++k) fn[k] = fnn[k];
-        }
         psc = psn;
         gpc = gpn;
     }
@@ -213,7 +188,7 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
 
 struct FusedChoice { int ty, tz; };
 
-template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false, bool DEEP = false>
+template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false>
 static int launch_fused(clbm_ctx *c)
 {
     const Geom &g = c->geo;
@@ -241,7 +216,7 @@ static int launch_fused(clbm_ctx *c)
         P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "sc_fused_collide_stream", true);
-    sc_fused_kernel<L, TY, TZ, MINB, GUO, MRT, 2, DEEP><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
+    sc_fused_kernel<L, TY, TZ, MINB, GUO, MRT><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -283,8 +258,7 @@ int sc_fused_launch(clbm_ctx *c)
         switch (variant) {
         case 1: rc = launch_fused<D2Q9, 256, 1, 2>(c); break;
         case 2: rc = launch_fused<D2Q9, 64, 1, 8>(c); break;
-        case 3: rc = launch_fused<D2Q9, 128, 1, 4>(c); break;                      // round-1 default: two register sets
-        default: rc = launch_fused<D2Q9, 128, 1, 3, false, false, true>(c); break;   // three register sets (DEEP)
+        default: rc = launch_fused<D2Q9, 128, 1, 4>(c); break;
         }
     } else {
         switch (variant) {
