@@ -314,6 +314,7 @@ bool hcz3d_sweep_shape_ok(const clbm_ctx *c);
 int hcz3d_sweep_launch(clbm_ctx *c, int src);
 long long hcz3d_sweep_edge_doubles(const clbm_ctx *c);
 int hcz3d_sweep_zero_edges(clbm_ctx *c, int set, int x0, int np);
+int hcz3d_sweep_zero_edge_planes(clbm_ctx *c, int set, int xa, int xb);
 
 __global__ void __launch_bounds__(256) count_walls_kernel(const uint8_t *__restrict__ flag, long long n, int *out)
 {
@@ -404,8 +405,7 @@ int hcz3d_stage0(clbm_ctx *c, bool rebuild)
     } else {
         if ((rc = hcz3d_moments_planes(c, c->mom_src, 0, 1))) return rc;
         if ((rc = hcz3d_moments_planes(c, c->mom_src, g.nx - 1, 1))) return rc;
-        if ((rc = hcz3d_sweep_zero_edges(c, c->mom_src, 0, 1))) return rc;
-        if ((rc = hcz3d_sweep_zero_edges(c, c->mom_src, g.nx - 1, 1))) return rc;
+        if ((rc = hcz3d_sweep_zero_edge_planes(c, c->mom_src, 0, g.nx - 1))) return rc;
     }
     c->sweep_active = 1;
     return 0;

@@ -566,11 +566,32 @@ int hcz3d_sweep_launch(clbm_ctx *c, int src)
 
 
 // edge sums of the planes [x0, x0 + np) of set `set` <- 0 (those planes' node arrays hold complete sums)
+__global__ void __launch_bounds__(256) zero_edges_kernel(double *ephi, double *e4, long long ep, int xa, int xb, int np)
+{
+    // blockIdx.y: 0 = planes [xa, xa + np), 1 = planes [xb, xb + np)
+    const long long x0 = blockIdx.y ? xb : xa;
+    const long long n1 = ep * np, n4 = 4 * ep * np;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        if (i < n1) ephi[ep * x0 + i] = 0.0;
+        e4[4 * ep * x0 + i] = 0.0;
+    }
+}
+
 int hcz3d_sweep_zero_edges(clbm_ctx *c, int set, int x0, int np)
 {
     const size_t ep = (size_t)hcz3d_sweep_edge_geom(c).eplane;
     CLBM_CUDA(cudaMemsetAsync(c->mome[set][0] + ep * x0, 0, ep * np * sizeof(double), c->stream));
     CLBM_CUDA(cudaMemsetAsync(c->mome[set][1] + 4 * ep * x0, 0, 4 * ep * np * sizeof(double), c->stream));
+    return 0;
+}
+
+// the same for the two boundary planes of a slab in one launch (stage 0 of every slab step)
+int hcz3d_sweep_zero_edge_planes(clbm_ctx *c, int set, int xa, int xb)
+{
+    const long long ep = hcz3d_sweep_edge_geom(c).eplane;
+    LaunchScope ls(c, "zero_edge_planes");
+    zero_edges_kernel<<<dim3(64, 2), 256, 0, c->stream>>>(c->mome[set][0], c->mome[set][1], ep, xa, xb, 1);
+    CLBM_CUDA(cudaGetLastError());
     return 0;
 }
 

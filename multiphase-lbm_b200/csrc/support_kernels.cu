@@ -382,6 +382,64 @@ static CrossTable cross_table(clbm_ctx *c)
     return T;
 }
 
+// Up to 16 (dst, src, bytes) segments copied -- or, src == nullptr, zero-filled -- by ONE launch (blockIdx.y = segment).  The
+// moment halo of a slab step is 2 (Shan-Chen) to 20 (HCZ D3Q19: five fields, two sides, pack and unpack) plane copies; as
+// separate cudaMemcpyAsync nodes each costs several microseconds of copy-engine set-up on the step's critical path, and the
+// peer-memory ring wants them as stores anyway (the destination may be the neighbour's mailbox).
+struct SegTable {
+    void *dst[16];
+    const void *src[16];
+    unsigned long long bytes[16];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) copy_segments_kernel(SegTable T)
+{
+    const int sgm = blockIdx.y;
+    if (sgm >= T.n) return;
+    char *d = (char *)T.dst[sgm];
+    const char *s = (const char *)T.src[sgm];
+    const unsigned long long nb = T.bytes[sgm];
+    const unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+    const bool a16 = (((unsigned long long)d | (unsigned long long)s | nb) & 15ull) == 0;
+    if (a16) {
+        const unsigned long long n16 = nb >> 4;
+        const int4 z = make_int4(0, 0, 0, 0);
+        for (unsigned long long i = t0; i < n16; i += stride) ((int4 *)d)[i] = s ? ((const int4 *)s)[i] : z;
+    } else if ((((unsigned long long)d | (unsigned long long)s | nb) & 7ull) == 0) {   // fp64 planes of an odd row count
+        const unsigned long long n8 = nb >> 3;
+        for (unsigned long long i = t0; i < n8; i += stride) ((long long *)d)[i] = s ? ((const long long *)s)[i] : 0ll;
+    } else {
+        for (unsigned long long i = t0; i < nb; i += stride) d[i] = s ? s[i] : (char)0;
+    }
+}
+
+struct SegList {
+    SegTable T;
+    SegList() { T.n = 0; }
+    // a full table is flushed by the caller through launch(); returns false when there is no room
+    bool add(void *dst, const void *src, size_t bytes)
+    {
+        if (T.n >= 16) return false;
+        T.dst[T.n] = dst; T.src[T.n] = src; T.bytes[T.n] = bytes; ++T.n;
+        return true;
+    }
+    int launch(clbm_ctx *c, const char *name)
+    {
+        if (T.n == 0) return 0;
+        unsigned long long mx = 0;
+        for (int i = 0; i < T.n; ++i) mx = T.bytes[i] > mx ? T.bytes[i] : mx;
+        long long blocks = (long long)((mx / 16 + 255) / 256);
+        if (blocks < 1) blocks = 1;
+        if (blocks > 148) blocks = 148;          // a grid-stride loop: one block per SM and segment is plenty for a few MB
+        LaunchScope ls(c, name);
+        copy_segments_kernel<<<dim3((unsigned)blocks, T.n), 256, 0, c->stream>>>(T);
+        CLBM_CUDA(cudaGetLastError());
+        T.n = 0;
+        return 0;
+    }
+};
+
 int halo_pack(clbm_ctx *c, int phase)
 {
     const Geom &g = c->geo;
@@ -391,6 +449,7 @@ int halo_pack(clbm_ctx *c, int phase)
         HaloField hf[8];
         const int nf = phase0_fields(c, hf);
         const bool hcz3 = c->prm.model == CLBM_MODEL_HCZ_D3Q19;
+        SegList L;
         for (int side = 0; side < 2; ++side) {
             double *dst = (double *)halo_send_ptr(c, 0, side);
             for (int i = 0; i < nf; ++i) {
@@ -401,12 +460,12 @@ int halo_pack(clbm_ctx *c, int phase)
                     if (int rc = hcz3d_pack_phi_merged(c, dst, x0, d)) return rc;
                 } else {
                     const double *src = hcz3 ? hcz3d_moment_array(c, hf[i].fld) : c->fld[hf[i].fld];
-                    CLBM_CUDA(cudaMemcpyAsync(dst, src + (size_t)(x0 + g.G) * pl, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                    if (!L.add(dst, src + (size_t)(x0 + g.G) * pl, d * pl * sizeof(double))) { set_error("halo segment table full"); return CLBM_ESTATE; }
                 }
                 dst += d * pl;
             }
         }
-        return 0;
+        return L.launch(c, "pack_moment_halo");
     }
     if (phase == 1) {
         LaunchScope ls(c, "pack_cross");
@@ -417,11 +476,12 @@ int halo_pack(clbm_ctx *c, int phase)
         return 0;
     }
     if (phase == 2) {
+        SegList L;
         for (int side = 0; side < 2; ++side) {
             const int x0 = side ? g.nx - g.G : 0;
-            CLBM_CUDA(cudaMemcpyAsync(halo_send_ptr(c, 2, side), c->flag + (size_t)(x0 + g.G) * pl, (size_t)g.G * pl, cudaMemcpyDeviceToDevice, c->stream));
+            L.add(halo_send_ptr(c, 2, side), c->flag + (size_t)(x0 + g.G) * pl, (size_t)g.G * pl);
         }
-        return 0;
+        return L.launch(c, "pack_mask_halo");
     }
     set_error("bad halo phase %d", phase);
     return CLBM_EINVAL;
@@ -437,17 +497,18 @@ int halo_unpack(clbm_ctx *c, int phase)
     if (phase == 0) {
         HaloField hf[8];
         const int nf = phase0_fields(c, hf);
+        SegList L;
         for (int side = 0; side < 2; ++side) {
             const double *src = (const double *)c->halo[0][side][1];
             for (int i = 0; i < nf; ++i) {
                 const int d = hf[i].depth;
                 const int x0 = side ? g.nx : -d;   // ghost planes on that side
                 double *dstf = c->prm.model == CLBM_MODEL_HCZ_D3Q19 ? hcz3d_moment_array(c, hf[i].fld) : c->fld[hf[i].fld];
-                CLBM_CUDA(cudaMemcpyAsync(dstf + (size_t)(x0 + g.G) * pl, src, d * pl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+                if (!L.add(dstf + (size_t)(x0 + g.G) * pl, src, d * pl * sizeof(double))) { set_error("halo segment table full"); return CLBM_ESTATE; }
                 src += d * pl;
             }
         }
-        return 0;
+        return L.launch(c, "unpack_moment_halo");
     }
     if (phase == 1) {
         // data received from the side-0 neighbour moves in +x (c_x = +1) into plane 0, and vice versa
@@ -460,11 +521,12 @@ int halo_unpack(clbm_ctx *c, int phase)
         return 0;
     }
     if (phase == 2) {
+        SegList L;
         for (int side = 0; side < 2; ++side) {
             const int x0 = side ? g.nx : -g.G;
-            CLBM_CUDA(cudaMemcpyAsync(c->flag + (size_t)(x0 + g.G) * pl, c->halo[2][side][1], (size_t)g.G * pl, cudaMemcpyDeviceToDevice, c->stream));
+            L.add(c->flag + (size_t)(x0 + g.G) * pl, c->halo[2][side][1], (size_t)g.G * pl);
         }
-        return 0;
+        return L.launch(c, "unpack_mask_halo");
     }
     set_error("bad halo phase %d", phase);
     return CLBM_EINVAL;
