@@ -333,13 +333,16 @@ def measure(cx, workload, scaling, steps, warmup, fused=1, size="", solo=False, 
         mass = cx.allreduce([mass], "sum")[0]     # the whole lattice's mass, not this slab's
     blu = P.MODEL_BYTES_PER_LU[prm.model]
     peak, peak_src = measured_peak_gbs()
-    achieved = (blu * prm.nelem / (kms * 1e-3) / 1e9) if kms > 0 else None
+    # lattice updates of the launch the kernel timing sampled: the whole slab, or -- overlap protocol of a ring -- the interior
+    # planes (the boundary chunks are collided by a launch of their own ahead of it)
+    lu_launch = prm.nelem if ring is None else (nxl - 2 * lat.overlap_width()) * ny * nz
+    achieved = (blu * lu_launch / (kms * 1e-3) / 1e9) if kms > 0 else None
     res = {"workload": workload, "description": desc, "scaling": scaling if world > 1 else "single", "n_gpus": world,
            "lattice_per_gpu": [nxl, ny, nz], "lattice_global": [nx_global, ny, nz], "steps": steps, "ms_per_step": ms / steps,
            "mlups": value, "mass": mass, "gpu_launches": launches,
            "transport": (ring.transport if ring is not None else None),
            "kernel": kname, "kernel_ms": kms, "kernel_launches_sampled": kcount,
-           "algorithmic_bytes_per_lu": blu, "achieved_gbs": achieved, "peak_gbs": peak, "peak_source": peak_src,
+           "algorithmic_bytes_per_lu": blu, "lattice_updates_per_launch": lu_launch, "achieved_gbs": achieved, "peak_gbs": peak, "peak_source": peak_src,
            "frac": (achieved / peak) if achieved else None,
            "step_frac_of_peak": blu * nelem_total / world * steps / (ms * 1e-3) / 1e9 / peak,
            "bytes_per_gpu": prm.lattice_size * 8, "clocks": clocks}
@@ -431,9 +434,9 @@ def main():
     traffic, traffic_src = ncu_traffic(tkey) if tkey else (None, None)
     roofline = {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": head["peak_gbs"], "unit": "GB/s", "frac": head["frac"],
                 "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": head["algorithmic_bytes_per_lu"] * prm.nelem,
+                "algorithmic_bytes_per_launch": head["algorithmic_bytes_per_lu"] * head["lattice_updates_per_launch"],
                 "kernel": head["kernel"], "kernel_ms": head["kernel_ms"], "kernel_launches_sampled": head["kernel_launches_sampled"],
-                "algorithmic_bytes_per_lu": head["algorithmic_bytes_per_lu"], "lattice_updates_per_launch": prm.nelem,
+                "algorithmic_bytes_per_lu": head["algorithmic_bytes_per_lu"], "lattice_updates_per_launch": head["lattice_updates_per_launch"],
                 "peak_source": head["peak_source"], "step_frac_of_peak": head["step_frac_of_peak"]}
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------

@@ -147,40 +147,47 @@ struct BoundaryStream {
     ~BoundaryStream() { c->stream = saved; }
 };
 
-// Overlap protocol of one slab step (stages 10, 11, 12; include/clbm.h): the interior planes [D, nx-D) need nothing
-// from the neighbours (their stencils read the slab's own populations: D = 1 for the psi stencil, 2 for the phi chain of
-// HCZ D2Q9), so they are collided on the launching stream while the boundary stream moves the moment halo, collides the
-// 2 D boundary planes and moves the crossing populations.  Interior and boundary launches write disjoint (node, direction)
-// slots of the out buffer.
+// Overlap protocol of one slab step (stages 10, 11, 12; include/clbm.h), second form (round 2).
+//
+// Round 1 collided the interior planes WHILE the boundary stream ran the moment exchange and the two boundary planes.  With the
+// peer-memory ring the moment exchange costs ~15 us, and the measurement on a 64-plane slab (tools/self_ring_bench.py) showed
+// what the concurrency cost: the interior launch takes 1007 us alone and 1220 us with the high-priority boundary-plane CTAs of
+// the same kernel cutting into its waves (they break the L2 sharing of neighbouring planes that the short x-chunks live on).
+// So the moment halo is now exchanged FIRST, on the launching stream (stage 10 + exchange 0), then the boundary planes -- a
+// chunk of Bw planes on each side, not one plane, so that their two-plane prologue is amortised -- are collided, and only
+// then the interior; what overlaps with the interior is the exchange of the crossing populations (pack, signal, wait,
+// unpack on the boundary stream), which is the larger message and the one whose latency would otherwise sit between two steps.
+static int overlap_width(const clbm_ctx *c)
+{
+    const int nx = c->geo.nx, D = overlap_depth(c);
+    int bw = c->prm.model == CLBM_MODEL_HCZ_D2Q9 ? 16 : 8;
+    if (bw > nx / 4) bw = nx / 4;
+    return bw < D ? D : bw;
+}
+
 static int overlap_stage(clbm_ctx *c, int stage)
 {
     if (!overlap_supported(c)) { set_error("overlap protocol not available for this context (use stages 0-2)"); return CLBM_ESTATE; }
     int rc;
-    const int nx = c->geo.nx, D = overlap_depth(c);
+    const int nx = c->geo.nx, Bw = overlap_width(c);
     if ((rc = ensure_boundary_stream(c))) return rc;
-    if (stage == 10) {
-        {   // the boundary planes of the "in" buffer were completed by the launching stream: by the previous step's interior
-            // launch, or -- after a step of the sequential protocol, an upload or a device-side init -- by whatever that stream
-            // ran last.  Recording here (not only after the interior launch) orders ALL of it before the boundary stream.
-            CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
-            CLBM_CUDA(cudaStreamWaitEvent(c->stream_b, c->ev_main, 0));
-            BoundaryStream bs(c);
-            if ((rc = overlap_moments(c))) return rc;
-            if ((rc = halo_pack(c, 0))) return rc;
-            // the interior launch fills every SM for the rest of the step: let these two small kernels through first
-            // (they run in ~20 us on the idle GPU; behind the interior's first wave they took 350 us)
-            CLBM_CUDA(cudaEventRecord(c->ev_b, c->stream_b));
-        }
-        CLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
-        if ((rc = overlap_collide(c, D, nx - D, 0, 0))) return rc;
-        CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
-        return 0;
+    if (stage == 10) {   // launching stream: moments of the boundary planes + pack of the moment halo (exchange 0 follows on this stream)
+        if ((rc = overlap_moments(c))) return rc;
+        return halo_pack(c, 0);
     }
     if (stage == 11) {
-        BoundaryStream bs(c);
         if ((rc = halo_unpack(c, 0))) return rc;
-        if ((rc = overlap_collide(c, 0, D, nx - D, nx))) return rc;   // SC: both boundary planes in one launch
+        if (nx <= 2 * Bw) {
+            if ((rc = overlap_collide(c, 0, nx, 0, 0))) return rc;              // a slab this thin has no interior worth a launch
+            CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
+        } else {
+            if ((rc = overlap_collide(c, 0, Bw, nx - Bw, nx))) return rc;       // both boundary chunks in one launch
+            CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));                  // the ghost planes hold what crossed the faces
+            if ((rc = overlap_collide(c, Bw, nx - Bw, 0, 0))) return rc;        // interior: overlaps with exchange 1
+        }
         c->parity = 1 - c->parity;
+        CLBM_CUDA(cudaStreamWaitEvent(c->stream_b, c->ev_main, 0));
+        BoundaryStream bs(c);
         return halo_pack(c, 1);
     }
     {
@@ -622,6 +629,7 @@ int clbm_step_stage(clbm_ctx *c, int stage)
 }
 
 int clbm_overlap_supported(const clbm_ctx *c) { return c && overlap_supported(c) ? 1 : 0; }
+int clbm_overlap_width(const clbm_ctx *c) { return c && overlap_supported(c) ? (c->geo.nx <= 2 * overlap_width(c) ? 0 : overlap_width(c)) : 0; }
 
 int clbm_sync(clbm_ctx *c)
 {
