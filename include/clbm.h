@@ -225,19 +225,28 @@ int  clbm_halo_unpack(clbm_ctx *ctx, int phase);
 int  clbm_step_stage(clbm_ctx *ctx, int stage);
 /* raw stream handle (cudaStream_t) so the caller can order its copies after ours */
 void *clbm_stream(clbm_ctx *ctx);
-/* Overlap protocol, available when clbm_overlap_supported() returns 1:
- *   stage 10: launching stream: moments of the boundary planes + pack phase 0
- *   (caller exchanges phase 0 ON THE LAUNCHING STREAM: ~two planes of doubles per side, microseconds over NVLink)
- *   stage 11: launching stream: unpack phase 0, collide/stream of a chunk of boundary planes on each side, then of the
- *             interior planes; boundary stream (after the boundary chunks): pack phase 1
- *   (caller exchanges phase 1 ON THE BOUNDARY STREAM: it overlaps with the interior launch)
- *   stage 12: boundary stream: unpack phase 1; the launching stream then waits for the boundary stream
- * (Round 1 ran the interior concurrently with the moment exchange and the boundary planes; measured on the B200 the
- * boundary-plane CTAs cut 20 % off the interior launch's throughput, more than the exchange they hid: DESIGN.md section 4.)
+/* Overlap protocol, available when clbm_overlap_supported() returns 1.  Two forms, clbm_overlap_variant():
+ *  1 "interior first" ("boundary planes first on a high-priority stream -> start exchange -> interior on the main
+ *    stream -> join"):
+ *      stage 10: boundary stream: moments of the boundary planes + pack phase 0;  launching stream: collide/stream of the
+ *                interior planes, which need nothing from the neighbours
+ *      (caller exchanges phase 0 ON THE BOUNDARY STREAM)
+ *      stage 11: boundary stream: unpack phase 0, collide/stream of the boundary planes, pack phase 1
+ *      (caller exchanges phase 1 on the boundary stream)
+ *      stage 12: boundary stream: unpack phase 1; the launching stream then waits for the boundary stream
+ *  2 "halo first":
+ *      stage 10: launching stream: moments of the boundary planes + pack phase 0
+ *      (caller exchanges phase 0 ON THE LAUNCHING STREAM)
+ *      stage 11: launching stream: unpack phase 0, collide/stream of a chunk of boundary planes per side, then of the interior;
+ *                boundary stream (after the boundary chunks): pack phase 1
+ *      (caller exchanges phase 1 on the boundary stream: it overlaps with the interior launch)
+ *      stage 12: as above
+ * CLBM_SLAB_OVERLAP = 0 / 1 / 2 (environment, read in clbm_create) turns the protocol off / forces a form.
  * clbm_boundary_stream returns the boundary stream (cudaStream_t), NULL when the protocol is not available. */
 int  clbm_overlap_supported(const clbm_ctx *ctx);
-/* planes per side that stage 11 collides ahead of the interior launch (0: no separate interior launch); the interior launch,
- * which the kernel timing samples, therefore covers nx - 2 * width planes */
+int  clbm_overlap_variant(const clbm_ctx *ctx);
+/* planes per side collided by the boundary launch (0: no separate interior launch): the interior launch, which the kernel
+ * timing samples, covers nx - 2 * width planes */
 int  clbm_overlap_width(const clbm_ctx *ctx);
 void *clbm_boundary_stream(clbm_ctx *ctx);
 

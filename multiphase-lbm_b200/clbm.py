@@ -19,7 +19,7 @@ EXPORTS = [
     "clbm_create", "clbm_destroy", "clbm_last_error", "clbm_abi_version", "clbm_upload", "clbm_upload2", "clbm_download_lattice",
     "clbm_download_fields", "clbm_download_force", "clbm_init_case", "clbm_step", "clbm_sync", "clbm_step_timed", "clbm_launch_count",
     "clbm_profile_step", "clbm_reduce", "clbm_diag_contact_angle", "clbm_diag_contact_angle_slab", "clbm_diag_interface_heights", "clbm_halo_buffer", "clbm_halo_pack", "clbm_halo_unpack", "clbm_step_stage",
-    "clbm_stream", "clbm_overlap_supported", "clbm_overlap_width", "clbm_boundary_stream", "clbm_comm_unique_id", "clbm_comm_init", "clbm_slab_step", "clbm_comm_destroy",
+    "clbm_stream", "clbm_overlap_supported", "clbm_overlap_variant", "clbm_overlap_width", "clbm_boundary_stream", "clbm_comm_unique_id", "clbm_comm_init", "clbm_slab_step", "clbm_comm_destroy",
     "clbm_peer_export", "clbm_peer_connect", "clbm_peer_connect_local", "clbm_peer_disconnect", "clbm_ring_kind", "clbm_slab_exchange", "clbm_slab_signal", "clbm_slab_wait", "clbm_kernel_timing_begin", "clbm_kernel_timing_end", "clbm_alloc_host", "clbm_free_host",
     "clbm_pulsatile_create", "clbm_pulsatile_destroy", "clbm_pulsatile_info", "clbm_pulsatile_step",
     "clbm_pulsatile_step_timed", "clbm_pulsatile_sync", "clbm_pulsatile_launch_count",
@@ -81,6 +81,7 @@ def load_library(path=None):
     lib.clbm_boundary_stream.restype = vp
     lib.clbm_overlap_supported.argtypes = [vp]
     lib.clbm_overlap_width.argtypes = [vp]
+    lib.clbm_overlap_variant.argtypes = [vp]
     lib.clbm_comm_unique_id.argtypes = [vp]
     lib.clbm_comm_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
     lib.clbm_slab_step.argtypes = [vp, ctypes.c_int]
@@ -336,6 +337,10 @@ class Lattice:
 
     def slab_wait(self, phase, boundary=False):
         self._check(self.lib.clbm_slab_wait(self._h, int(phase), 1 if boundary else 0))
+
+    def overlap_variant(self):
+        """0: sequential protocol, 1: interior-first overlap, 2: halo-first overlap (clbm_overlap_variant)"""
+        return int(self.lib.clbm_overlap_variant(self._h))
 
     def overlap_width(self):
         return int(self.lib.clbm_overlap_width(self._h))

@@ -108,7 +108,10 @@ int model_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
 // The overlap protocol needs x-range launches of the collide kernel: the TMA Shan-Chen kernel and the fused HCZ D2Q9 kernel
 // have them.  D = number of boundary planes per side whose stencils reach into the neighbour slab (= the halo depth of the
 // moment exchange: psi depth 1, phi depth 2).
-static bool overlap_supported(const clbm_ctx *c)
+// default form per model, from the measurements of DESIGN.md section 4
+#define OVERLAP_DEFAULT(c) 1
+
+static bool overlap_possible(const clbm_ctx *c)
 {
     const int m = c->prm.model;
     if (!c->multi) return false;
@@ -116,6 +119,20 @@ static bool overlap_supported(const clbm_ctx *c)
     if (m == CLBM_MODEL_HCZ_D2Q9) return c->geo.nx >= 4 && c->prm.fused && hcz2d_fused_eligible(c);
     return false;
 }
+// Which form of the overlap protocol a slab step uses (0: none, the sequential stages 0-2).  Two forms exist because neither
+// wins everywhere (tools/self_ring_bench.py):
+//   1  interior first: the interior planes are collided on the launching stream WHILE the boundary stream exchanges the moment
+//      halo, collides the boundary planes and exchanges the crossing populations;
+//   2  halo first: moment halo exchanged on the launching stream, a chunk of boundary planes per side collided, then the
+//      interior, which overlaps with the exchange of the crossing populations only.
+// CLBM_SLAB_OVERLAP = 0 / 1 / 2 forces one (read in clbm_create).
+static int overlap_variant(const clbm_ctx *c)
+{
+    if (!overlap_possible(c)) return 0;
+    if (c->env.slab_overlap >= 0) return c->env.slab_overlap > 2 ? 2 : c->env.slab_overlap;
+    return OVERLAP_DEFAULT(c);
+}
+static bool overlap_supported(const clbm_ctx *c) { return overlap_variant(c) != 0; }
 static int overlap_depth(const clbm_ctx *c) { return c->prm.model == CLBM_MODEL_HCZ_D2Q9 ? 2 : 1; }
 static int overlap_moments(clbm_ctx *c) { return c->prm.model == CLBM_MODEL_HCZ_D2Q9 ? hcz2d_stage0(c) : sc_psi_boundary(c); }
 // collide + push of [x_begin, x_end) and, when non-empty, [x2_begin, x2_end)
@@ -165,7 +182,50 @@ static int overlap_width(const clbm_ctx *c)
     return bw < D ? D : bw;
 }
 
-static int overlap_stage(clbm_ctx *c, int stage)
+// form 1 (round 1): see overlap_variant
+static int overlap_stage_interior_first(clbm_ctx *c, int stage)
+{
+    if (!overlap_supported(c)) { set_error("overlap protocol not available for this context (use stages 0-2)"); return CLBM_ESTATE; }
+    int rc;
+    const int nx = c->geo.nx, D = overlap_depth(c);
+    if ((rc = ensure_boundary_stream(c))) return rc;
+    if (stage == 10) {
+        {   // the boundary planes of the "in" buffer were completed by the launching stream: by the previous step's interior
+            // launch, or -- after a step of the sequential protocol, an upload or a device-side init -- by whatever that stream
+            // ran last.  Recording here (not only after the interior launch) orders ALL of it before the boundary stream.
+            CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
+            CLBM_CUDA(cudaStreamWaitEvent(c->stream_b, c->ev_main, 0));
+            BoundaryStream bs(c);
+            if ((rc = overlap_moments(c))) return rc;
+            if ((rc = halo_pack(c, 0))) return rc;
+            // the interior launch fills every SM for the rest of the step: let these two small kernels through first
+            // (they run in ~20 us on the idle GPU; behind the interior's first wave they took 350 us)
+            CLBM_CUDA(cudaEventRecord(c->ev_b, c->stream_b));
+        }
+        CLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+        if ((rc = overlap_collide(c, D, nx - D, 0, 0))) return rc;
+        CLBM_CUDA(cudaEventRecord(c->ev_main, c->stream));
+        return 0;
+    }
+    if (stage == 11) {
+        BoundaryStream bs(c);
+        if ((rc = halo_unpack(c, 0))) return rc;
+        if ((rc = overlap_collide(c, 0, D, nx - D, nx))) return rc;   // SC: both boundary planes in one launch
+        c->parity = 1 - c->parity;
+        return halo_pack(c, 1);
+    }
+    {
+        BoundaryStream bs(c);
+        if ((rc = halo_unpack(c, 1))) return rc;
+    }
+    CLBM_CUDA(cudaEventRecord(c->ev_b, c->stream_b));
+    CLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+    return 0;
+}
+
+
+// form 2
+static int overlap_stage_halo_first(clbm_ctx *c, int stage)
 {
     if (!overlap_supported(c)) { set_error("overlap protocol not available for this context (use stages 0-2)"); return CLBM_ESTATE; }
     int rc;
@@ -197,6 +257,11 @@ static int overlap_stage(clbm_ctx *c, int stage)
     CLBM_CUDA(cudaEventRecord(c->ev_b, c->stream_b));
     CLBM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
     return 0;
+}
+
+static int overlap_stage(clbm_ctx *c, int stage)
+{
+    return overlap_variant(c) == 2 ? overlap_stage_halo_first(c, stage) : overlap_stage_interior_first(c, stage);
 }
 
 // slab protocol: see include/clbm.h (clbm_step_stage)
@@ -629,7 +694,15 @@ int clbm_step_stage(clbm_ctx *c, int stage)
 }
 
 int clbm_overlap_supported(const clbm_ctx *c) { return c && overlap_supported(c) ? 1 : 0; }
-int clbm_overlap_width(const clbm_ctx *c) { return c && overlap_supported(c) ? (c->geo.nx <= 2 * overlap_width(c) ? 0 : overlap_width(c)) : 0; }
+int clbm_overlap_variant(const clbm_ctx *c) { return c ? overlap_variant(c) : 0; }
+int clbm_overlap_width(const clbm_ctx *c)
+{
+    if (!c) return 0;
+    const int v = overlap_variant(c);
+    if (v == 1) return overlap_depth(c);
+    if (v == 2) return c->geo.nx <= 2 * overlap_width(c) ? 0 : overlap_width(c);
+    return 0;
+}
 
 int clbm_sync(clbm_ctx *c)
 {

@@ -81,6 +81,7 @@ struct EnvKnobs {
     int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
     int slab_graph;    // 0: never capture the slab step in a CUDA graph
     int persist;       // 0: never use the persistent multi-step kernels of the L2-resident lattices
+    int slab_overlap;  // 0: sequential slab protocol only; 1: interior-first overlap; 2: halo-first overlap (default: per model, clbm_api.cu)
     int force_slab;    // 1: treat a full-width lattice as an x-slab (a ring of ONE context, its own neighbour: tests of the ring code)
 };
 inline int env_int(const char *name, int unset = -1)
@@ -101,6 +102,7 @@ inline void read_env_knobs(EnvKnobs &k)
     k.hcz3d_sweep = env_int("CLBM_HCZ3D_SWEEP");
     k.slab_graph = env_int("CLBM_SLAB_GRAPH");
     k.persist = env_int("CLBM_PERSIST");
+    k.slab_overlap = env_int("CLBM_SLAB_OVERLAP");
     k.force_slab = env_int("CLBM_FORCE_SLAB");
 }
 

@@ -224,7 +224,7 @@ static int slab_step_eager(clbm_ctx *c)
     const int s0 = overlap ? 10 : 0;
     int rc;
     if ((rc = clbm_step_stage(c, s0))) return rc;
-    if ((rc = ring_exchange(c, 0, c->stream))) return rc;   // the moment halo always travels on the launching stream
+    if ((rc = ring_exchange(c, 0, clbm_overlap_variant(c) == 1 ? xs : c->stream))) return rc;   // form 1 moves the moment halo on the boundary stream
     if ((rc = clbm_step_stage(c, s0 + 1))) return rc;
     if ((rc = ring_exchange(c, 1, xs))) return rc;
     return clbm_step_stage(c, s0 + 2);

@@ -142,7 +142,7 @@ class LocalRing:
             for _ in range(n):
                 for lat in self.lats:
                     lat.step_stage(s0)
-                self._peer_phase(0, False)          # the moment halo travels on the launching stream in both protocols
+                self._peer_phase(0, overlap and self.lats[0].overlap_variant() == 1)   # form 1 moves the moment halo on the boundary stream
                 for lat in self.lats:
                     lat.step_stage(s1)
                 self._peer_phase(1, overlap)
@@ -360,8 +360,8 @@ class DistRing:
         if self.overlap if overlap is None else (overlap and self.overlap):
             for _ in range(n):
                 self.lat.step_stage(10)         # boundary moments + pack (launching stream)
-                self.exchange(0, boundary=False)
-                self.lat.step_stage(11)         # unpack, boundary chunks, interior | boundary stream: pack of the crossing populations
+                self.exchange(0, boundary=self.lat.overlap_variant() == 1)
+                self.lat.step_stage(11)         # boundary planes (form 2: then the interior) | boundary stream: pack of the crossing populations
                 self.exchange(1, boundary=True)
                 self.lat.step_stage(12)         # unpack, join
             return

@@ -16,10 +16,14 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def run(key, size, steps, force_slab, graph):
+def run(key, size, steps, force_slab, graph, overlap=-1):
     import torch
     os.environ["CLBM_FORCE_SLAB"] = "1" if force_slab else "0"
     os.environ["CLBM_SLAB_GRAPH"] = str(graph)
+    if overlap >= 0:
+        os.environ["CLBM_SLAB_OVERLAP"] = str(overlap)
+    else:
+        os.environ.pop("CLBM_SLAB_OVERLAP", None)
     prm, case, args = bench.build_params(P, key, *size, size[0], 0, 1)
     if key == "sc3d":
         args = (0.265, 0.038, 0.2 * size[1], 5.0)
@@ -55,9 +59,11 @@ def main():
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 200
     size = {"sc3d": (nx, 512, 512), "hcz3d": (nx, 512, 512), "hcz2d": (nx, 8194, 1), "sc2d": (nx, 8192, 1)}[key]
     nelem = size[0] * size[1] * size[2]
-    for name, fs, gr in (("single slab (clbm_step)", 0, 0), ("self ring, call by call", 1, 0), ("self ring, graph replay", 1, 1)):
-        ms, launches, kms, kname = run(key, size, steps, fs, gr)
-        print("%-5s %dx%dx%d  %-26s %8.1f us/step  %7.0f MLUPS  %5.1f launches/step  dominant kernel %s %.1f us"
+    for name, fs, gr, ov in (("single slab (clbm_step)", 0, 0, -1), ("self ring, sequential, eager", 1, 0, 0),
+                             ("self ring, sequential, graph", 1, 1, 0), ("self ring, interior first, graph", 1, 1, 1),
+                             ("self ring, halo first, graph", 1, 1, 2)):
+        ms, launches, kms, kname = run(key, size, steps, fs, gr, ov)
+        print("%-5s %dx%dx%d  %-34s %8.1f us/step  %7.0f MLUPS  %5.1f launches/step  dominant kernel %s %.1f us"
               % (key, size[0], size[1], size[2], name, ms * 1e3, nelem / ms / 1e3, launches, kname, kms * 1e3), flush=True)
 
 
