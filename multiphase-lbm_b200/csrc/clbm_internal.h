@@ -81,6 +81,7 @@ struct EnvKnobs {
     int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
     int slab_graph;    // 0: never capture the slab step in a CUDA graph
     int persist;       // 0: never use the persistent multi-step kernels of the L2-resident lattices
+    int ring_fuse;     // 0: separate signal / wait kernels on the peer ring (default: fused into the pack / unpack kernels)
     int slab_overlap;  // 0: sequential slab protocol only; 1: interior-first overlap; 2: halo-first overlap (default: per model, clbm_api.cu)
     int force_slab;    // 1: treat a full-width lattice as an x-slab (a ring of ONE context, its own neighbour: tests of the ring code)
 };
@@ -102,6 +103,7 @@ inline void read_env_knobs(EnvKnobs &k)
     k.hcz3d_sweep = env_int("CLBM_HCZ3D_SWEEP");
     k.slab_graph = env_int("CLBM_SLAB_GRAPH");
     k.persist = env_int("CLBM_PERSIST");
+    k.ring_fuse = env_int("CLBM_RING_FUSE");
     k.slab_overlap = env_int("CLBM_SLAB_OVERLAP");
     k.force_slab = env_int("CLBM_FORCE_SLAB");
 }
@@ -170,6 +172,7 @@ struct clbm_ctx {
     int peer_mode;
     void *peer_base[2];
     int *peer_err;              // pinned + mapped: a wait kernel that timed out writes its phase + 1 here
+    int ring_fuse;              // 1 while clbm_slab_step issues stages whose pack / unpack kernels carry the signal / wait themselves
     void *slab_graph[2];        // cudaGraphExec_t of two consecutive slab steps starting at parity 0 / 1
     int64_t slab_graph_launches[2];   // kernels one replay launches (counted while capturing)
     int slab_graph_failed;

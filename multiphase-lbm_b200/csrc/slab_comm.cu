@@ -29,6 +29,7 @@
 #include <mutex>
 
 #include "clbm_internal.h"
+#include "ring_sync.cuh"
 
 namespace clbm {
 
@@ -112,51 +113,37 @@ static int nccl_exchange(clbm_ctx *c, int phase, cudaStream_t st)
 }
 
 // ---- peer-memory ring -------------------------------------------------------------------------------------------
-struct MailFlags {
-    unsigned arrive[3][2];   // [phase][side]: sequence number of the last block the neighbour on `side` completed in our mailbox
-    unsigned seq[3];         // signals this context has sent, per phase
-    unsigned expect[3];      // waits this context has done, per phase
-};
-
 static MailFlags *flags_of(void *mailbox, const clbm_ctx *c) { return (MailFlags *)((char *)mailbox + c->mailbox_flags_off); }
 
-__global__ void peer_signal_kernel(MailFlags *mine, MailFlags *left, MailFlags *right, int phase)
-{
-    const unsigned v = mine->seq[phase] + 1u;
-    mine->seq[phase] = v;
-    __threadfence_system();   // everything the pack wrote into the neighbours' mailboxes (earlier in this stream) is ordered before the flags
-    *(volatile unsigned *)&left->arrive[phase][1] = v;    // we are the side-1 neighbour of our left neighbour
-    *(volatile unsigned *)&right->arrive[phase][0] = v;
-}
-
-__device__ __forceinline__ unsigned long long gtimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
+__global__ void peer_signal_kernel(MailFlags *mine, MailFlags *left, MailFlags *right, int phase) { ring_send(mine, left, right, phase); }
 
 __global__ void peer_wait_kernel(MailFlags *mine, int phase, unsigned long long timeout_ns, int *err)
 {
     const unsigned v = mine->expect[phase] + 1u;
     mine->expect[phase] = v;
-    const unsigned long long t0 = gtimer_ns();
-    volatile unsigned *a0 = &mine->arrive[phase][0], *a1 = &mine->arrive[phase][1];
-    unsigned spins = 0;
-    while ((int)(*a0 - v) < 0 || (int)(*a1 - v) < 0) {
-        if ((++spins & 1023u) == 0 && gtimer_ns() - t0 > timeout_ns) {   // a neighbour died or never joined: report, do not hang the GPU
-            *err = phase + 1;
-            break;
-        }
-        __nanosleep(64);
-    }
-    __threadfence_system();
+    ring_spin(mine, phase, v, timeout_ns, err);
 }
 
-static unsigned long long peer_timeout_ns()
+unsigned long long peer_timeout_ns()
 {
     static const int ms = env_int("CLBM_PEER_TIMEOUT_MS", 20000);
     return (unsigned long long)(ms > 0 ? ms : 20000) * 1000000ull;
+}
+
+// what a fused pack (mode 1) / unpack (mode 2) kernel of `phase` needs; mode 0 when the context's ring is not fused right now
+RingSync ring_sync_for(const clbm_ctx *c, int phase, int mode, unsigned nblocks)
+{
+    RingSync r = {};
+    if (!c->ring_fuse || !c->peer_mode) return r;
+    r.mine = flags_of(c->mailbox, c);
+    r.left = flags_of(c->peer_base[0], c);
+    r.right = flags_of(c->peer_base[1], c);
+    r.mode = mode;
+    r.phase = phase;
+    r.nblocks = nblocks;
+    r.timeout_ns = peer_timeout_ns();
+    r.err = c->peer_err;
+    return r;
 }
 
 static int peer_exchange(clbm_ctx *c, int phase, cudaStream_t st)
@@ -223,6 +210,15 @@ static int slab_step_eager(clbm_ctx *c)
     }
     const int s0 = overlap ? 10 : 0;
     int rc;
+    if (c->peer_mode && c->env.ring_fuse != 0) {
+        // the signal rides on the last block of every pack kernel, the wait on the first instruction of every unpack kernel
+        c->ring_fuse = 1;
+        rc = clbm_step_stage(c, s0);
+        if (!rc) rc = clbm_step_stage(c, s0 + 1);
+        if (!rc) rc = clbm_step_stage(c, s0 + 2);
+        c->ring_fuse = 0;
+        return rc;
+    }
     if ((rc = clbm_step_stage(c, s0))) return rc;
     if ((rc = ring_exchange(c, 0, clbm_overlap_variant(c) == 1 ? xs : c->stream))) return rc;   // form 1 moves the moment halo on the boundary stream
     if ((rc = clbm_step_stage(c, s0 + 1))) return rc;

@@ -2,9 +2,12 @@
 // (iniLattice + inigeom of each case), warp-shuffle reductions for the mass / energy diagnostics,
 // and the ghost-plane pack / unpack of the x-slab decomposition.
 #include "clbm_internal.h"
+#include "ring_sync.cuh"
 #include "moments.cuh"
 
 namespace clbm {
+
+RingSync ring_sync_for(const clbm_ctx *c, int phase, int mode, unsigned nblocks);   // slab_comm.cu
 
 // ============================================================================================
 // initial conditions.  One thread per storage cell INCLUDING ghost planes so that ghost flags are
@@ -340,32 +343,37 @@ struct CrossTable {
 
 template <class L>
 __global__ void __launch_bounds__(256)
-unpack_cross_kernel(CrossTable T, const uint8_t *__restrict__ flag, Geom g)
+unpack_cross_kernel(CrossTable T, const uint8_t *__restrict__ flag, Geom g, RingSync rs)
 {
+    ring_kernel_begin(rs);   // fused ring: the neighbours' crossing populations have arrived
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= g.plane) return;
-    const int per_side = T.ncross * T.sets;
-    const int side = blockIdx.y / per_side, slot = blockIdx.y % per_side;
-    const int s = slot / T.ncross, k = T.ks[1 - side][slot % T.ncross];
-    const int y = (int)(r / g.nz), z = (int)(r % g.nz);
-    const int xb = side ? g.nx - 1 : 0;   // boundary plane that receives
-    const long long j = g.idx(xb, y, z);
-    if (flag[j] == CELL_BB) return;
-    const long long src = g.idx(xb - L::cx(k), g.wy(y - L::cy(k)), g.wz(z - L::cz(k)));
-    if (flag[src] == CELL_BB) return;
-    T.pop[s][(size_t)k * g.ncs + j] = T.recv[side][(size_t)slot * g.plane + r];
+    if (r < g.plane) {
+        const int per_side = T.ncross * T.sets;
+        const int side = blockIdx.y / per_side, slot = blockIdx.y % per_side;
+        const int s = slot / T.ncross, k = T.ks[1 - side][slot % T.ncross];
+        const int y = (int)(r / g.nz), z = (int)(r % g.nz);
+        const int xb = side ? g.nx - 1 : 0;   // boundary plane that receives
+        const long long j = g.idx(xb, y, z);
+        if (flag[j] != CELL_BB) {
+            const long long src = g.idx(xb - L::cx(k), g.wy(y - L::cy(k)), g.wz(z - L::cz(k)));
+            if (flag[src] != CELL_BB) T.pop[s][(size_t)k * g.ncs + j] = T.recv[side][(size_t)slot * g.plane + r];
+        }
+    }
+    ring_kernel_end(rs);
 }
 
 // ghost-plane populations (what the push wrote across the slab face) -> send buffers, all slots in one launch
-__global__ void __launch_bounds__(256) pack_cross_kernel(CrossTable T, Geom g)
+__global__ void __launch_bounds__(256) pack_cross_kernel(CrossTable T, Geom g, RingSync rs)
 {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= g.plane) return;
-    const int per_side = T.ncross * T.sets;
-    const int side = blockIdx.y / per_side, slot = blockIdx.y % per_side;
-    const int s = slot / T.ncross, k = T.ks[side][slot % T.ncross];
-    const int xg = side ? g.nx : -1;
-    T.send[side][(size_t)slot * g.plane + r] = T.pop[s][(size_t)k * g.ncs + (size_t)(xg + g.G) * g.plane + r];
+    if (r < g.plane) {
+        const int per_side = T.ncross * T.sets;
+        const int side = blockIdx.y / per_side, slot = blockIdx.y % per_side;
+        const int s = slot / T.ncross, k = T.ks[side][slot % T.ncross];
+        const int xg = side ? g.nx : -1;
+        T.send[side][(size_t)slot * g.plane + r] = T.pop[s][(size_t)k * g.ncs + (size_t)(xg + g.G) * g.plane + r];
+    }
+    ring_kernel_end(rs);     // fused ring: the last block tells both neighbours
 }
 
 static CrossTable cross_table(clbm_ctx *c)
@@ -393,25 +401,27 @@ struct SegTable {
     int n;
 };
 
-__global__ void __launch_bounds__(256) copy_segments_kernel(SegTable T)
+__global__ void __launch_bounds__(256) copy_segments_kernel(SegTable T, RingSync rs)
 {
+    ring_kernel_begin(rs);
     const int sgm = blockIdx.y;
-    if (sgm >= T.n) return;
-    char *d = (char *)T.dst[sgm];
-    const char *s = (const char *)T.src[sgm];
-    const unsigned long long nb = T.bytes[sgm];
-    const unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
-    const bool a16 = (((unsigned long long)d | (unsigned long long)s | nb) & 15ull) == 0;
-    if (a16) {
-        const unsigned long long n16 = nb >> 4;
-        const int4 z = make_int4(0, 0, 0, 0);
-        for (unsigned long long i = t0; i < n16; i += stride) ((int4 *)d)[i] = s ? ((const int4 *)s)[i] : z;
-    } else if ((((unsigned long long)d | (unsigned long long)s | nb) & 7ull) == 0) {   // fp64 planes of an odd row count
-        const unsigned long long n8 = nb >> 3;
-        for (unsigned long long i = t0; i < n8; i += stride) ((long long *)d)[i] = s ? ((const long long *)s)[i] : 0ll;
-    } else {
-        for (unsigned long long i = t0; i < nb; i += stride) d[i] = s ? s[i] : (char)0;
+    if (sgm < T.n) {
+        char *d = (char *)T.dst[sgm];
+        const char *s = (const char *)T.src[sgm];
+        const unsigned long long nb = T.bytes[sgm];
+        const unsigned long long t0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (unsigned long long)gridDim.x * blockDim.x;
+        if ((((unsigned long long)d | (unsigned long long)s | nb) & 15ull) == 0) {
+            const unsigned long long n16 = nb >> 4;
+            const int4 z = make_int4(0, 0, 0, 0);
+            for (unsigned long long i = t0; i < n16; i += stride) ((int4 *)d)[i] = s ? ((const int4 *)s)[i] : z;
+        } else if ((((unsigned long long)d | (unsigned long long)s | nb) & 7ull) == 0) {   // fp64 planes of an odd row count
+            const unsigned long long n8 = nb >> 3;
+            for (unsigned long long i = t0; i < n8; i += stride) ((long long *)d)[i] = s ? ((const long long *)s)[i] : 0ll;
+        } else {
+            for (unsigned long long i = t0; i < nb; i += stride) d[i] = s ? s[i] : (char)0;
+        }
     }
+    ring_kernel_end(rs);
 }
 
 struct SegList {
@@ -424,7 +434,8 @@ struct SegList {
         T.dst[T.n] = dst; T.src[T.n] = src; T.bytes[T.n] = bytes; ++T.n;
         return true;
     }
-    int launch(clbm_ctx *c, const char *name)
+    // sync_mode 1: the pack of `phase` (signal when done), 2: its unpack (wait first); only honoured while the ring is fused
+    int launch(clbm_ctx *c, const char *name, int phase = 0, int sync_mode = 0)
     {
         if (T.n == 0) return 0;
         unsigned long long mx = 0;
@@ -433,7 +444,8 @@ struct SegList {
         if (blocks < 1) blocks = 1;
         if (blocks > 148) blocks = 148;          // a grid-stride loop: one block per SM and segment is plenty for a few MB
         LaunchScope ls(c, name);
-        copy_segments_kernel<<<dim3((unsigned)blocks, T.n), 256, 0, c->stream>>>(T);
+        const RingSync rs = ring_sync_for(c, phase, sync_mode, (unsigned)(blocks * T.n));
+        copy_segments_kernel<<<dim3((unsigned)blocks, T.n), 256, 0, c->stream>>>(T, rs);
         CLBM_CUDA(cudaGetLastError());
         T.n = 0;
         return 0;
@@ -465,13 +477,13 @@ int halo_pack(clbm_ctx *c, int phase)
                 dst += d * pl;
             }
         }
-        return L.launch(c, "pack_moment_halo");
+        return L.launch(c, "pack_moment_halo", 0, 1);
     }
     if (phase == 1) {
         LaunchScope ls(c, "pack_cross");
         const CrossTable T = cross_table(c);
         dim3 grid(grid_for(g.plane, 256), 2 * T.ncross * T.sets);
-        pack_cross_kernel<<<grid, 256, 0, c->stream>>>(T, g);
+        pack_cross_kernel<<<grid, 256, 0, c->stream>>>(T, g, ring_sync_for(c, 1, 1, grid.x * grid.y));
         CLBM_CUDA(cudaGetLastError());
         return 0;
     }
@@ -481,7 +493,7 @@ int halo_pack(clbm_ctx *c, int phase)
             const int x0 = side ? g.nx - g.G : 0;
             L.add(halo_send_ptr(c, 2, side), c->flag + (size_t)(x0 + g.G) * pl, (size_t)g.G * pl);
         }
-        return L.launch(c, "pack_mask_halo");
+        return L.launch(c, "pack_mask_halo", 2, 1);
     }
     set_error("bad halo phase %d", phase);
     return CLBM_EINVAL;
@@ -508,15 +520,16 @@ int halo_unpack(clbm_ctx *c, int phase)
                 src += d * pl;
             }
         }
-        return L.launch(c, "unpack_moment_halo");
+        return L.launch(c, "unpack_moment_halo", 0, 2);
     }
     if (phase == 1) {
         // data received from the side-0 neighbour moves in +x (c_x = +1) into plane 0, and vice versa
         LaunchScope ls(c, "unpack_cross");
         const CrossTable T = cross_table(c);
         dim3 grid(grid_for(g.plane, 256), 2 * T.ncross * T.sets);
-        if (c->Q == 9) unpack_cross_kernel<D2Q9><<<grid, 256, 0, c->stream>>>(T, c->flag, g);
-        else unpack_cross_kernel<D3Q19><<<grid, 256, 0, c->stream>>>(T, c->flag, g);
+        const RingSync rs = ring_sync_for(c, 1, 2, grid.x * grid.y);
+        if (c->Q == 9) unpack_cross_kernel<D2Q9><<<grid, 256, 0, c->stream>>>(T, c->flag, g, rs);
+        else unpack_cross_kernel<D3Q19><<<grid, 256, 0, c->stream>>>(T, c->flag, g, rs);
         CLBM_CUDA(cudaGetLastError());
         return 0;
     }
@@ -526,7 +539,7 @@ int halo_unpack(clbm_ctx *c, int phase)
             const int x0 = side ? g.nx : -g.G;
             L.add(c->flag + (size_t)(x0 + g.G) * pl, c->halo[2][side][1], (size_t)g.G * pl);
         }
-        return L.launch(c, "unpack_mask_halo");
+        return L.launch(c, "unpack_mask_halo", 2, 2);
     }
     set_error("bad halo phase %d", phase);
     return CLBM_EINVAL;
