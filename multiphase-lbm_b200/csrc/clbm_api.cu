@@ -108,8 +108,12 @@ int model_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
 // The overlap protocol needs x-range launches of the collide kernel: the TMA Shan-Chen kernel and the fused HCZ D2Q9 kernel
 // have them.  D = number of boundary planes per side whose stencils reach into the neighbour slab (= the halo depth of the
 // moment exchange: psi depth 1, phi depth 2).
-// default form per model, from the measurements of DESIGN.md section 4
-#define OVERLAP_DEFAULT(c) 1
+// Default per model, from the measurements of DESIGN.md section 4 (tools/self_ring_bench.py, peer ring, graph replay):
+//   Shan-Chen (TMA kernel): the SEQUENTIAL protocol.  64-plane slab 1225 us per step against 1243 (interior first) / 1226 (halo
+//   first); 512-plane slab 8377 / 8412 / 8388.  With the peer ring an exchange is ~15 us; the boundary-plane launches of the
+//   overlap forms cost the full-SM kernel more than that (the interior launch: 1007 us alone, 1220 us with them in its waves).
+//   HCZ D2Q9: interior first.  256-column slab 162 us against 174 (sequential) / 184 (halo first); 2048 columns 1039 / 1058 / 1076.
+#define OVERLAP_DEFAULT(c) ((c)->prm.model == CLBM_MODEL_HCZ_D2Q9 ? 1 : 0)
 
 static bool overlap_possible(const clbm_ctx *c)
 {

@@ -210,8 +210,9 @@ static int slab_step_eager(clbm_ctx *c)
     }
     const int s0 = overlap ? 10 : 0;
     int rc;
-    if (c->peer_mode && c->env.ring_fuse != 0) {
-        // the signal rides on the last block of every pack kernel, the wait on the first instruction of every unpack kernel
+    if (c->peer_mode && c->env.ring_fuse == 1) {
+        // CLBM_RING_FUSE=1 (an experiment that stays off: measured SLOWER): the signal rides on the last
+        // block of every pack kernel, the wait on the first instruction of every unpack kernel
         c->ring_fuse = 1;
         rc = clbm_step_stage(c, s0);
         if (!rc) rc = clbm_step_stage(c, s0 + 1);

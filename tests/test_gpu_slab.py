@@ -75,10 +75,31 @@ def test_slab_device_init_has_consistent_ghost_flags():
     np.testing.assert_array_equal(pops, ref)
 
 
+class overlap_env:
+    """CLBM_SLAB_OVERLAP (read once per context in clbm_create): 0 sequential only, 1 interior-first, 2 halo-first overlap"""
+
+    def __init__(self, form):
+        self.form = form
+
+    def __enter__(self):
+        import os
+        self.old = os.environ.get("CLBM_SLAB_OVERLAP")
+        os.environ["CLBM_SLAB_OVERLAP"] = str(self.form)
+
+    def __exit__(self, *a):
+        import os
+        if self.old is None:
+            os.environ.pop("CLBM_SLAB_OVERLAP", None)
+        else:
+            os.environ["CLBM_SLAB_OVERLAP"] = self.old
+
+
+@pytest.mark.parametrize("form", [1, 2])
 @pytest.mark.parametrize("nranks", [2, 4])
-def test_overlap_protocol_is_bit_identical(nranks):
-    """boundary-first overlap protocol (clbm_step_stage 10-12: interior planes on the launching stream, boundary planes
-    + both exchanges on the boundary stream) against the sequential protocol (stages 0-2) and the single slab"""
+def test_overlap_protocol_is_bit_identical(nranks, form):
+    """both forms of the overlap protocol (clbm_step_stage 10-12; 1: interior planes on the launching stream while the boundary
+    stream runs both exchanges and the boundary planes, 2: moment halo first, boundary chunks, interior overlapping the
+    population exchange) against the sequential protocol (stages 0-2, the Shan-Chen default) and the single slab"""
     prm = P.sc_params(P.MODEL_SC_D3Q19, 32, 24, 36, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
     args = (0.265, 0.038, 8.0, 5.0)
     with pkg.clbm.Lattice(prm) as single:
@@ -87,8 +108,9 @@ def test_overlap_protocol_is_bit_identical(nranks):
         ref = single.in_pops()
     out = {}
     for overlap in (False, True):
-        lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, nranks)) for r in range(nranks)]
-        assert all(lat.overlap_supported() for lat in lats)
+        with overlap_env(form):
+            lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, nranks)) for r in range(nranks)]
+        assert all(lat.overlap_supported() and lat.overlap_variant() == form for lat in lats)
         for lat in lats:
             lat.init_case(P.CASE_SC_DROPLET3D, args)
         ring = slab.LocalRing(lats)
@@ -101,16 +123,19 @@ def test_overlap_protocol_is_bit_identical(nranks):
     np.testing.assert_array_equal(out[True], ref)
 
 
-def test_full_plane_slabs_match_single_slab():
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_full_plane_slabs_match_single_slab(form):
     """four slabs of 8 planes at the production plane size 512 x 512 (real tile grid, TMA boxes, 24-plane chunk logic) against
-    the single 32 x 512 x 512 slab, bit for bit, with the overlap protocol"""
+    the single 32 x 512 x 512 slab, bit for bit, with the sequential protocol and both forms of the overlap protocol"""
     prm = P.sc_params(P.MODEL_SC_D3Q19, 32, 512, 512, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
     args = (0.265, 0.038, 12.0, 5.0)
     with pkg.clbm.Lattice(prm) as single:
         single.init_case(P.CASE_SC_DROPLET3D, args)
         single.step(6)
         ref = single.in_pops()
-    lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, 4)) for r in range(4)]
+    with overlap_env(form):
+        lats = [pkg.clbm.Lattice(slab.slab_params(prm, r, 4)) for r in range(4)]
+    assert all(lat.overlap_variant() == form for lat in lats)
     for lat in lats:
         lat.init_case(P.CASE_SC_DROPLET3D, args)
     ring = slab.LocalRing(lats)

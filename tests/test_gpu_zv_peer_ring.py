@@ -77,9 +77,10 @@ class env:
                 os.environ[k] = v
 
 
+@pytest.mark.parametrize("overlap", [-1, 0, 1, 2])
 @pytest.mark.parametrize("graph", [1, 0])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_self_ring_graph_replay_matches_single_slab(name, graph):
+def test_self_ring_graph_replay_matches_single_slab(name, graph, overlap):
     """clbm_slab_step itself -- whole steps issued by the library, two steps per CUDA-graph launch from the third step on --
     on a ring of ONE context that is its own neighbour (CLBM_FORCE_SLAB=1: the full-width lattice runs in x-slab mode, its
     ghost planes filled through its own mailbox).  This is the code path of a one-GPU-per-process run, without a second
@@ -87,11 +88,18 @@ def test_self_ring_graph_replay_matches_single_slab(name, graph):
     mk, case, args, steps = CASES[name]
     prm = mk()
     ref_pops, ref_fields = single_run(prm, case, args, steps)
-    with env(CLBM_FORCE_SLAB=1, CLBM_SLAB_GRAPH=graph):       # both read once, in clbm_create
+    if overlap > 0 and name in ("sc2d_contact", "hcz3d_drop"):
+        pytest.skip("no overlap protocol for this kernel")
+    kw = dict(CLBM_FORCE_SLAB=1, CLBM_SLAB_GRAPH=graph)       # read once, in clbm_create
+    if overlap >= 0:
+        kw["CLBM_SLAB_OVERLAP"] = overlap                        # -1: the model's default protocol
+    with env(**kw):
         lat = pkg.clbm.Lattice(prm)
     lat.init_case(case, args)
     lat.peer_connect_local(lat, lat)
     assert lat.ring_kind() == 2
+    if overlap >= 0:
+        assert lat.overlap_variant() == overlap
     l0 = lat.launch_count()
     for n in (1, 7, 2, 9, steps - 19):          # eager first steps, graph replays, odd leftovers, both parities
         lat.slab_step(n)
@@ -106,15 +114,17 @@ def test_self_ring_graph_replay_matches_single_slab(name, graph):
     assert 3 <= per_step <= 16, per_step       # replayed launches are counted too
 
 
-def test_protocols_mix_without_host_synchronisation():
+@pytest.mark.parametrize("form", [1, 2])
+def test_protocols_mix_without_host_synchronisation(form):
     """steps of the sequential protocol (stages 0-2 on the launching stream) between steps of the overlap protocol (stages
     10-12, boundary stream), every call asynchronous: the cross-stream ordering must come from events, not from a host sync
     (the boundary stream has to wait for what the launching stream ran last)"""
     prm = P.sc_params(P.MODEL_SC_D3Q19, 32, 24, 36, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
     case, args = P.CASE_SC_DROPLET3D, (0.265, 0.038, 8.0, 5.0)
     ref_pops, _ = single_run(prm, case, args, 30)
-    lats, ring = make_ring(prm, case, args, 2)
-    assert all(lat.overlap_supported() for lat in lats)
+    with env(CLBM_SLAB_OVERLAP=form):            # the Shan-Chen default is the sequential protocol
+        lats, ring = make_ring(prm, case, args, 2)
+    assert all(lat.overlap_supported() and lat.overlap_variant() == form for lat in lats)
     for _ in range(5):
         ring.step(3, overlap=True)
         ring.step(1, overlap=False)
