@@ -420,6 +420,7 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->peer_base[0] = c->peer_base[1] = nullptr;
     c->peer_err = nullptr;
     c->ring_fuse = 0;
+    c->halo0_packed = 0;
     c->slab_graph[0] = c->slab_graph[1] = nullptr;
     c->slab_graph_launches[0] = c->slab_graph_launches[1] = 0;
     c->slab_graph_failed = 0;

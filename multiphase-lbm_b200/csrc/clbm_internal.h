@@ -172,6 +172,7 @@ struct clbm_ctx {
     int peer_mode;
     void *peer_base[2];
     int *peer_err;              // pinned + mapped: a wait kernel that timed out writes its phase + 1 here
+    int halo0_packed;           // the moment kernels of this stage wrote the phase-0 send blocks themselves (Shan-Chen boundary psi)
     int ring_fuse;              // 1 while clbm_slab_step issues stages whose pack / unpack kernels carry the signal / wait themselves
     void *slab_graph[2];        // cudaGraphExec_t of two consecutive slab steps starting at parity 0 / 1
     int64_t slab_graph_launches[2];   // kernels one replay launches (counted while capturing)

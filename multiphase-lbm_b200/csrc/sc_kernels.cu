@@ -34,6 +34,35 @@ sc_psi_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, 
     psi[i] = v;
 }
 
+// psi of the two boundary planes of a slab in ONE launch (blockIdx.y = side), written to the psi field AND straight into the
+// send block of that side -- on a peer ring the neighbour's mailbox -- so that the moment halo of a Shan-Chen slab step needs
+// no pack launch of its own (two of the ten small dependent kernels of a sequential step)
+template <class L, bool GUO = false>
+__global__ void __launch_bounds__(256)
+sc_psi_boundary_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, double *__restrict__ psi, Geom g, ModelParams mp,
+                       double *__restrict__ send0, double *__restrict__ send1)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= g.plane) return;
+    const int side = blockIdx.y;
+    const long long i = (long long)((side ? g.nx - 1 : 0) + g.G) * g.plane + t;
+    double f[L::Q];
+#pragma unroll
+    for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + i];
+    double v = 0.0;
+    if (flag[i] != CELL_BB) {
+        if constexpr (GUO) {
+            v = scrt_psi(Mom<L>::sum(f));
+        } else {
+            bool g1_pos;
+            const double ps = sc_psi_g1(mp, Mom<L>::sum(f), g1_pos);
+            v = g1_pos ? ps : -ps;
+        }
+    }
+    psi[i] = v;
+    (side ? send1 : send0)[t] = v;
+}
+
 template <class L, bool GUO = false, bool MRT = false>
 __global__ void __launch_bounds__(256, 2)
 sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const uint8_t *__restrict__ flag,
@@ -136,10 +165,16 @@ int sc_collide_all(clbm_ctx *c);
 // psi of the two boundary planes only (what the neighbours need as moment halo when the fused kernel runs)
 int sc_psi_boundary(clbm_ctx *c)
 {
-    const int nx = c->geo.nx;
-    int rc = c->Q == 9 ? sc_psi_range<D2Q9>(c, 0, 1) : sc_psi_range<D3Q19>(c, 0, 1);
-    if (rc || nx == 1) return rc;
-    return c->Q == 9 ? sc_psi_range<D2Q9>(c, nx - 1, nx) : sc_psi_range<D3Q19>(c, nx - 1, nx);
+    const Geom &g = c->geo;
+    double *s0 = (double *)halo_send_ptr(c, 0, 0), *s1 = (double *)halo_send_ptr(c, 0, 1);
+    const dim3 grid(grid_for(g.plane, 256), 2);
+    LaunchScope ls(c, "sc_psi_boundary");
+    if (c->Q == 9 && is_guo(c)) sc_psi_boundary_kernel<D2Q9, true><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1);
+    else if (c->Q == 9) sc_psi_boundary_kernel<D2Q9><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1);
+    else sc_psi_boundary_kernel<D3Q19><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1);
+    CLBM_CUDA(cudaGetLastError());
+    c->halo0_packed = 1;   // the halo_pack(0) that follows has nothing left to copy
+    return 0;
 }
 // collide + stream of the local planes in slab mode (ghost psi planes already unpacked); no parity flip
 int sc_collide_slab(clbm_ctx *c)

@@ -461,6 +461,10 @@ int halo_pack(clbm_ctx *c, int phase)
         HaloField hf[8];
         const int nf = phase0_fields(c, hf);
         const bool hcz3 = c->prm.model == CLBM_MODEL_HCZ_D3Q19;
+        if (c->halo0_packed) {   // the boundary-moment kernel of this stage stored into the send blocks itself
+            c->halo0_packed = 0;
+            if (!c->ring_fuse) return 0;     // (a fused ring still needs a kernel whose last block signals)
+        }
         SegList L;
         for (int side = 0; side < 2; ++side) {
             double *dst = (double *)halo_send_ptr(c, 0, side);

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_slab.py tests/test_gpu_zv_peer_ring.py tests/test_gpu_zz_sc_rt2d.py -m gpu -q --timeout 600 -p no:cacheprovider > gpurun_out/r2q_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2q_pytest.log
+tail -4 gpurun_out/r2q_pytest.log
+for k in "sc3d 64" "sc3d 512"; do timeout 300 python tools/self_ring_bench.py $k 100 2>&1 | grep -v Warning; done > gpurun_out/r2q_self_ring.txt
+cat gpurun_out/r2q_self_ring.txt
+echo done
