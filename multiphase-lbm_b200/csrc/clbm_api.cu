@@ -421,6 +421,10 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->peer_err = nullptr;
     c->ring_fuse = 0;
     c->halo0_packed = 0;
+    c->fld0_in_mailbox = 0;
+    c->mailbox_psi_off = 0;
+    c->halo0_direct = 0;
+    c->peer_nx[0] = c->peer_nx[1] = 0;
     c->slab_graph[0] = c->slab_graph[1] = nullptr;
     c->slab_graph_launches[0] = c->slab_graph_launches[1] = 0;
     c->slab_graph_failed = 0;
@@ -467,7 +471,9 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     if (cudaMalloc(&c->flag, (size_t)g.ncs) != cudaSuccess) { set_error("out of device memory (flag)"); return fail(CLBM_ENOMEM); }
     cudaMemsetAsync(c->flag, CELL_BULK, (size_t)g.ncs, c->stream);
     c->nfld = (p->model == CLBM_MODEL_HCZ_D3Q19) ? 8 : (p->model == CLBM_MODEL_HCZ_D2Q9 ? 5 : 1);
-    for (int i = 0; i < c->nfld; ++i) {
+    // (the psi field of a Shan-Chen x-slab is placed inside the halo mailbox by halo_alloc below)
+    c->fld0_in_mailbox = c->multi && (p->model == CLBM_MODEL_SC_D2Q9 || p->model == CLBM_MODEL_SC_D3Q19);
+    for (int i = c->fld0_in_mailbox ? 1 : 0; i < c->nfld; ++i) {
         if (cudaMalloc(&c->fld[i], (size_t)g.ncs * sizeof(double)) != cudaSuccess) { set_error("out of device memory (field %d)", i); return fail(CLBM_ENOMEM); }
         cudaMemsetAsync(c->fld[i], 0, (size_t)g.ncs * sizeof(double), c->stream);
     }
@@ -489,6 +495,7 @@ int clbm_destroy(clbm_ctx *c)
     clbm_peer_disconnect(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &s : c->pop) for (auto &b : s) if (b) cudaFree(b);
+    if (c->fld0_in_mailbox) c->fld[0] = nullptr;   // part of the mailbox allocation
     for (auto &f : c->fld) if (f) cudaFree(f);
     if (c->flag) cudaFree(c->flag);
     if (c->red_dev) cudaFree(c->red_dev);

@@ -172,6 +172,12 @@ struct clbm_ctx {
     int peer_mode;
     void *peer_base[2];
     int *peer_err;              // pinned + mapped: a wait kernel that timed out writes its phase + 1 here
+    // Shan-Chen x-slabs: the psi field lives INSIDE the mailbox allocation, so that on a peer ring a neighbour stores its boundary
+    // psi plane straight into our ghost plane (no receive block, no unpack launch for the moment halo)
+    int fld0_in_mailbox;
+    size_t mailbox_psi_off;     // byte offset of fld[0] in the mailbox (0: not there)
+    int halo0_direct;           // peer ring connected with direct ghost planes: halo_send_ptr(0, side) is the neighbour's ghost plane
+    int peer_nx[2];             // local plane count of the neighbour on each side (its right ghost plane is plane nx + G of its storage)
     int halo0_packed;           // the moment kernels of this stage wrote the phase-0 send blocks themselves (Shan-Chen boundary psi)
     int ring_fuse;              // 1 while clbm_slab_step issues stages whose pack / unpack kernels carry the signal / wait themselves
     void *slab_graph[2];        // cudaGraphExec_t of two consecutive slab steps starting at parity 0 / 1

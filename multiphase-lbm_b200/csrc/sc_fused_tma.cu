@@ -26,7 +26,13 @@ namespace clbm {
 
 using L3 = D3Q19;
 
-struct OutTable { double *out[19]; };
+// out buffer: direction k starts at k * ncs (one base pointer instead of 19 parameter-block pointers, whose constant-bank loads
+// the stores then wait on; the same change in the HCZ D3Q19 sweep kernel halved its long-scoreboard stalls)
+struct OutTable {
+    double *base;
+    size_t ncs;
+    CLBM_D double *at(int k) const { return base + (size_t)k * ncs; }
+};
 
 template <int TY, int TZ>
 struct TmaCfg {
@@ -227,7 +233,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
                 for (int k = 0; k < 19; ++k) {
                     const int off = (L3::cx(k) < 0 ? oxm : (L3::cx(k) > 0 ? oxp : 0)) + (L3::cy(k) < 0 ? oym : (L3::cy(k) > 0 ? oyp : 0)) +
                                     (L3::cz(k) < 0 ? ozm : (L3::cz(k) > 0 ? ozp : 0));
-                    P.out[k][i + off] = out[k];
+                    P.at(k)[i + off] = out[k];
                 }
             }
         } else if (inside && ring[s0][ty + 1][tz + 1] >= 0.0) {
@@ -248,11 +254,11 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
             const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
 #pragma unroll
             for (int k = 0; k < 19; ++k) {
-                if (k == L3::REST) { P.out[k][i] = out[k]; continue; }
+                if (k == L3::REST) { P.at(k)[i] = out[k]; continue; }
                 const int off = (L3::cx(k) < 0 ? oxm : (L3::cx(k) > 0 ? oxp : 0)) + (L3::cy(k) < 0 ? oym : (L3::cy(k) > 0 ? oyp : 0)) +
                                 (L3::cz(k) < 0 ? ozm : (L3::cz(k) > 0 ? ozp : 0));
-                if (s.wall & (1u << k)) P.out[L3::opp(k)][i] = out[k];
-                else P.out[k][i + off] = out[k];
+                if (s.wall & (1u << k)) P.at(L3::opp(k))[i] = out[k];
+                else P.at(k)[i + off] = out[k];
             }
         }
         psc = psn;
@@ -296,8 +302,7 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
     if (c->env.sc_xchunk > 0) xchunk = c->env.sc_xchunk < nxr ? c->env.sc_xchunk : nxr;
     const int nch1 = (nxr + xchunk - 1) / xchunk, nch2 = x2_end > x2_begin ? (x2_end - x2_begin + xchunk - 1) / xchunk : 0;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, nch1 + nch2);
-    OutTable P;
-    for (int k = 0; k < 19; ++k) P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+    const OutTable P = {c->pop[0][1 - c->parity], (size_t)g.ncs};
     auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY>;
     static PerDeviceOnce attr;
     if (attr.need(c->device)) {

@@ -172,9 +172,9 @@ static int ring_exchange(clbm_ctx *c, int phase, cudaStream_t st)
 
 struct PeerHandle {                // what clbm_peer_export writes: CLBM_PEER_HANDLE_BYTES
     cudaIpcMemHandle_t mem;        // 64 bytes
-    unsigned long long magic, bytes, flags_off;
-    int pid, device;
-    char pad[CLBM_PEER_HANDLE_BYTES - 64 - 3 * 8 - 2 * 4];
+    unsigned long long magic, bytes, flags_off, psi_off;
+    int pid, device, nx, model;
+    char pad[CLBM_PEER_HANDLE_BYTES - 64 - 4 * 8 - 4 * 4];
 };
 static_assert(sizeof(PeerHandle) == CLBM_PEER_HANDLE_BYTES, "handle size");
 static const unsigned long long PEER_MAGIC = 0x434c424d50454552ull;   // "CLBMPEER"
@@ -314,8 +314,11 @@ int clbm_peer_export(clbm_ctx *c, void *handle)
     h.magic = PEER_MAGIC;
     h.bytes = c->mailbox_bytes;
     h.flags_off = c->mailbox_flags_off;
+    h.psi_off = c->mailbox_psi_off;
     h.pid = (int)getpid();
     h.device = c->device;
+    h.nx = c->geo.nx;
+    h.model = c->prm.model;
     memcpy(handle, &h, sizeof(h));
     return CLBM_OK;
 }
@@ -331,8 +334,8 @@ int clbm_peer_connect(clbm_ctx *c, const void *left_handle, const void *right_ha
     memcpy(&h[1], right_handle, sizeof(PeerHandle));
     for (int s = 0; s < 2; ++s) {
         if (h[s].magic != PEER_MAGIC) { set_error("not a clbm_peer_export handle"); return CLBM_EINVAL; }
-        if (h[s].bytes != c->mailbox_bytes || h[s].flags_off != c->mailbox_flags_off) {
-            set_error("neighbour mailbox layout differs (%llu / %llu bytes): ring members must share the model and the y, z extents", h[s].bytes, (unsigned long long)c->mailbox_bytes);
+        if (h[s].flags_off != c->mailbox_flags_off || h[s].psi_off != c->mailbox_psi_off || h[s].model != c->prm.model) {
+            set_error("neighbour mailbox layout differs (flag page at %llu / %llu): ring members must share the model and the y, z extents", h[s].flags_off, (unsigned long long)c->mailbox_flags_off);
             return CLBM_EINVAL;
         }
         if (h[s].pid == (int)getpid()) { set_error("neighbour lives in this process: use clbm_peer_connect_local"); return CLBM_EINVAL; }
@@ -349,6 +352,9 @@ int clbm_peer_connect(clbm_ctx *c, const void *left_handle, const void *right_ha
     if (rc) { cudaIpcCloseMemHandle(base[0]); if (base[1] != base[0]) cudaIpcCloseMemHandle(base[1]); return rc; }
     c->peer_base[0] = base[0];
     c->peer_base[1] = base[1];
+    c->peer_nx[0] = h[0].nx;
+    c->peer_nx[1] = h[1].nx;
+    c->halo0_direct = c->fld0_in_mailbox;
     c->peer_mode = 1;
     drop_graphs(c);
     return CLBM_OK;
@@ -362,7 +368,7 @@ int clbm_peer_connect_local(clbm_ctx *c, clbm_ctx *left, clbm_ctx *right)
     clbm_ctx *nb[2] = {left, right};
     CLBM_CUDA(cudaSetDevice(c->device));
     for (int s = 0; s < 2; ++s) {
-        if (nb[s]->mailbox_bytes != c->mailbox_bytes || nb[s]->mailbox_flags_off != c->mailbox_flags_off) { set_error("neighbour mailbox layout differs"); return CLBM_EINVAL; }
+        if (nb[s]->mailbox_flags_off != c->mailbox_flags_off || nb[s]->mailbox_psi_off != c->mailbox_psi_off || nb[s]->prm.model != c->prm.model) { set_error("neighbour mailbox layout differs"); return CLBM_EINVAL; }
         if (nb[s]->device != c->device) {
             int can = 0;
             CLBM_CUDA(cudaDeviceCanAccessPeer(&can, c->device, nb[s]->device));
@@ -376,6 +382,9 @@ int clbm_peer_connect_local(clbm_ctx *c, clbm_ctx *left, clbm_ctx *right)
     if (rc) return rc;
     c->peer_base[0] = left->mailbox;
     c->peer_base[1] = right->mailbox;
+    c->peer_nx[0] = left->geo.nx;
+    c->peer_nx[1] = right->geo.nx;
+    c->halo0_direct = c->fld0_in_mailbox;
     c->peer_mode = 2;
     drop_graphs(c);
     return CLBM_OK;
@@ -395,6 +404,7 @@ int clbm_peer_disconnect(clbm_ctx *c)
         }
         c->peer_base[0] = c->peer_base[1] = nullptr;
         c->peer_mode = 0;
+        c->halo0_direct = 0;
     }
     if (c->peer_err) { cudaFreeHost(c->peer_err); c->peer_err = nullptr; }
     return CLBM_OK;

@@ -316,8 +316,13 @@ int halo_alloc(clbm_ctx *c)
     c->halo_bytes[2] = (size_t)g.G * g.plane;
     c->mailbox_flags_off = halo_block_offset(c, 3, 0, 0);
     c->mailbox_bytes = c->mailbox_flags_off + 4096;
+    if (c->fld0_in_mailbox) {   // Shan-Chen: the psi field behind the flag page (see clbm_internal.h)
+        c->mailbox_psi_off = c->mailbox_bytes;
+        c->mailbox_bytes += (size_t)g.ncs * sizeof(double);
+    }
     if (cudaMalloc(&c->mailbox, c->mailbox_bytes) != cudaSuccess) { cudaGetLastError(); set_error("out of device memory (halo buffers)"); return CLBM_ENOMEM; }
     cudaMemsetAsync(c->mailbox, 0, c->mailbox_bytes, c->stream);
+    if (c->fld0_in_mailbox) c->fld[0] = (double *)((char *)c->mailbox + c->mailbox_psi_off);
     for (int ph = 0; ph < 3; ++ph)
         for (int side = 0; side < 2; ++side)
             for (int r = 0; r < 2; ++r) c->halo[ph][side][r] = (char *)c->mailbox + halo_block_offset(c, ph, side, r);
@@ -328,6 +333,13 @@ int halo_alloc(clbm_ctx *c)
 // that neighbour (its block of the OPPOSITE side) through the mapping of its mailbox
 void *halo_send_ptr(const clbm_ctx *c, int phase, int side)
 {
+    if (phase == 0 && c->halo0_direct) {
+        // Shan-Chen on a peer ring: our boundary psi plane goes straight into the neighbour's ghost plane -- its RIGHT ghost
+        // plane (storage plane nx + G of ITS slab) for what we send to the left, its left ghost plane (storage plane G - 1) to the right
+        const size_t pl = (size_t)c->geo.plane * sizeof(double);
+        const size_t plane_idx = side == 0 ? (size_t)(c->peer_nx[0] + c->geo.G) : (size_t)(c->geo.G - 1);
+        return (char *)c->peer_base[side] + c->mailbox_psi_off + plane_idx * pl;
+    }
     if (c->peer_mode && c->peer_base[side]) return (char *)c->peer_base[side] + halo_block_offset(c, phase, 1 - side, 1);
     return c->halo[phase][side][0];
 }
@@ -511,6 +523,7 @@ int halo_unpack(clbm_ctx *c, int phase)
     const Geom &g = c->geo;
     const size_t pl = (size_t)g.plane;
     if (phase == 0) {
+        if (c->halo0_direct && !c->ring_fuse) return 0;   // the neighbours stored into our ghost planes themselves
         HaloField hf[8];
         const int nf = phase0_fields(c, hf);
         SegList L;
