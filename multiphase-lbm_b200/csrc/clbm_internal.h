@@ -81,7 +81,7 @@ struct EnvKnobs {
     int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
     int slab_graph;    // 0: never capture the slab step in a CUDA graph
     int persist;       // 0: never use the persistent multi-step kernels of the L2-resident lattices
-    int ring_fuse;     // 1: signal / wait fused into the pack / unpack kernels of the peer ring (default off: measured slower)
+    int ring_fuse;     // peer ring: 0 separate signal / wait kernels, 1 both fused into the pack / unpack kernels (measured slower), default (2): signals fused only
     int slab_overlap;  // 0: sequential slab protocol only; 1: interior-first overlap; 2: halo-first overlap (default: per model, clbm_api.cu)
     int force_slab;    // 1: treat a full-width lattice as an x-slab (a ring of ONE context, its own neighbour: tests of the ring code)
 };

@@ -79,7 +79,10 @@ __device__ __forceinline__ void ring_kernel_begin(const RingSync &r)
 __device__ __forceinline__ void ring_kernel_end(const RingSync &r)
 {
     if (r.mode == 0) return;
-    __threadfence_system();   // this thread's stores, possibly into a neighbour's mailbox
+    // this thread's stores (possibly into a neighbour's mailbox) before the block's ticket: a device-scope fence per thread; the
+    // last block adds the system-scope fence in ring_send, which is cumulative over everything the tickets made visible to it
+    // (a system-scope fence in every thread of a 10 000-block pack kernel is what made the first fused form slow)
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
         unsigned *t = &r.mine->ticket[r.phase][r.mode - 1];

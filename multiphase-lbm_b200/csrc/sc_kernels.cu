@@ -3,9 +3,12 @@
 //   sc_collide_kernel : force from the psi stencil, BGK collision, push streaming with
 //                       half-way bounce-back (SC/apps/laplace2D.h:285-306, :260-270)
 // The fused plane-marching form lives in sc_fused.cu; both share sc_cell.cuh.
+#include "ring_sync.cuh"
 #include "sc_cell.cuh"
 
 namespace clbm {
+
+RingSync ring_sync_for(const clbm_ctx *c, int phase, int mode, unsigned nblocks);   // slab_comm.cu
 
 template <class L, bool GUO = false>
 __global__ void __launch_bounds__(256)
@@ -40,27 +43,29 @@ sc_psi_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, 
 template <class L, bool GUO = false>
 __global__ void __launch_bounds__(256)
 sc_psi_boundary_kernel(const double *__restrict__ fin, const uint8_t *__restrict__ flag, double *__restrict__ psi, Geom g, ModelParams mp,
-                       double *__restrict__ send0, double *__restrict__ send1)
+                       double *__restrict__ send0, double *__restrict__ send1, RingSync rs)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= g.plane) return;
-    const int side = blockIdx.y;
-    const long long i = (long long)((side ? g.nx - 1 : 0) + g.G) * g.plane + t;
-    double f[L::Q];
+    if (t < g.plane) {
+        const int side = blockIdx.y;
+        const long long i = (long long)((side ? g.nx - 1 : 0) + g.G) * g.plane + t;
+        double f[L::Q];
 #pragma unroll
-    for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + i];
-    double v = 0.0;
-    if (flag[i] != CELL_BB) {
-        if constexpr (GUO) {
-            v = scrt_psi(Mom<L>::sum(f));
-        } else {
-            bool g1_pos;
-            const double ps = sc_psi_g1(mp, Mom<L>::sum(f), g1_pos);
-            v = g1_pos ? ps : -ps;
+        for (int k = 0; k < L::Q; ++k) f[k] = fin[(size_t)k * g.ncs + i];
+        double v = 0.0;
+        if (flag[i] != CELL_BB) {
+            if constexpr (GUO) {
+                v = scrt_psi(Mom<L>::sum(f));
+            } else {
+                bool g1_pos;
+                const double ps = sc_psi_g1(mp, Mom<L>::sum(f), g1_pos);
+                v = g1_pos ? ps : -ps;
+            }
         }
+        psi[i] = v;
+        (side ? send1 : send0)[t] = v;
     }
-    psi[i] = v;
-    (side ? send1 : send0)[t] = v;
+    ring_kernel_end(rs);   // fused ring: the last block tells both neighbours that their ghost psi planes are complete
 }
 
 template <class L, bool GUO = false, bool MRT = false>
@@ -169,11 +174,12 @@ int sc_psi_boundary(clbm_ctx *c)
     double *s0 = (double *)halo_send_ptr(c, 0, 0), *s1 = (double *)halo_send_ptr(c, 0, 1);
     const dim3 grid(grid_for(g.plane, 256), 2);
     LaunchScope ls(c, "sc_psi_boundary");
-    if (c->Q == 9 && is_guo(c)) sc_psi_boundary_kernel<D2Q9, true><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1);
-    else if (c->Q == 9) sc_psi_boundary_kernel<D2Q9><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1);
-    else sc_psi_boundary_kernel<D3Q19><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1);
+    const RingSync rs = ring_sync_for(c, 0, 1, grid.x * grid.y);
+    if (c->Q == 9 && is_guo(c)) sc_psi_boundary_kernel<D2Q9, true><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1, rs);
+    else if (c->Q == 9) sc_psi_boundary_kernel<D2Q9><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1, rs);
+    else sc_psi_boundary_kernel<D3Q19><<<grid, 256, 0, c->stream>>>(c->pop[0][c->parity], c->flag, c->fld[0], g, c->mp, s0, s1, rs);
     CLBM_CUDA(cudaGetLastError());
-    c->halo0_packed = 1;   // the halo_pack(0) that follows has nothing left to copy
+    c->halo0_packed = rs.mode ? 2 : 1;   // the halo_pack(0) that follows has nothing left to copy (2: nor to signal)
     return 0;
 }
 // collide + stream of the local planes in slab mode (ghost psi planes already unpacked); no parity flip

@@ -135,6 +135,7 @@ RingSync ring_sync_for(const clbm_ctx *c, int phase, int mode, unsigned nblocks)
 {
     RingSync r = {};
     if (!c->ring_fuse || !c->peer_mode) return r;
+    if (c->ring_fuse == 2 && mode == 2) return r;   // signals fused, waits as separate kernels
     r.mine = flags_of(c->mailbox, c);
     r.left = flags_of(c->peer_base[0], c);
     r.right = flags_of(c->peer_base[1], c);
@@ -210,6 +211,25 @@ static int slab_step_eager(clbm_ctx *c)
     }
     const int s0 = overlap ? 10 : 0;
     int rc;
+    if (c->peer_mode && c->env.ring_fuse != 0 && c->env.ring_fuse != 1) {
+        // default on a peer ring: the SIGNAL of a phase rides on the last block of its pack kernel (two launches less per step);
+        // the waits stay one-thread kernels (hundreds of polling blocks in the unpack kernels measured slower)
+        cudaStream_t w0 = clbm_overlap_variant(c) == 1 ? xs : c->stream;
+        auto wait = [&](int phase, cudaStream_t st) -> int {
+            LaunchScope ls(c, "peer_wait");
+            peer_wait_kernel<<<1, 1, 0, st>>>(flags_of(c->mailbox, c), phase, peer_timeout_ns(), c->peer_err);
+            CLBM_CUDA(cudaGetLastError());
+            return 0;
+        };
+        c->ring_fuse = 2;
+        rc = clbm_step_stage(c, s0);
+        if (!rc) rc = wait(0, w0);
+        if (!rc) rc = clbm_step_stage(c, s0 + 1);
+        if (!rc) rc = wait(1, xs);
+        if (!rc) rc = clbm_step_stage(c, s0 + 2);
+        c->ring_fuse = 0;
+        return rc;
+    }
     if (c->peer_mode && c->env.ring_fuse == 1) {
         // CLBM_RING_FUSE=1 (an experiment that stays off: measured SLOWER): the signal rides on the last
         // block of every pack kernel, the wait on the first instruction of every unpack kernel

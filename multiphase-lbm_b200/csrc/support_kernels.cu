@@ -474,8 +474,9 @@ int halo_pack(clbm_ctx *c, int phase)
         const int nf = phase0_fields(c, hf);
         const bool hcz3 = c->prm.model == CLBM_MODEL_HCZ_D3Q19;
         if (c->halo0_packed) {   // the boundary-moment kernel of this stage stored into the send blocks itself
+            const int how = c->halo0_packed;
             c->halo0_packed = 0;
-            if (!c->ring_fuse) return 0;     // (a fused ring still needs a kernel whose last block signals)
+            if (how == 2 || !c->ring_fuse) return 0;     // (a fused ring needs a kernel whose last block signals: that kernel, or the copy below)
         }
         SegList L;
         for (int side = 0; side < 2; ++side) {
@@ -523,7 +524,7 @@ int halo_unpack(clbm_ctx *c, int phase)
     const Geom &g = c->geo;
     const size_t pl = (size_t)g.plane;
     if (phase == 0) {
-        if (c->halo0_direct && !c->ring_fuse) return 0;   // the neighbours stored into our ghost planes themselves
+        if (c->halo0_direct && c->ring_fuse != 1) return 0;   // the neighbours stored into our ghost planes themselves
         HaloField hf[8];
         const int nf = phase0_fields(c, hf);
         SegList L;
