@@ -34,40 +34,80 @@ struct OutTable {
     CLBM_D double *at(int k) const { return base + (size_t)k * ncs; }
 };
 
-template <int TY, int TZ>
+template <int TY, int TZ, int NS = 2, int SPY = 1, int SPZ = 1>
 struct TmaCfg {
     static constexpr int NT = TY * TZ, SY = TY + 2, SZ = TZ + 2;
     // the innermost TMA coordinate must be 16-byte aligned (odd z faults on sm_100a, tools/tma_probe.cu), so the
     // box spans z0-2 .. z0+TZ+1: BZ = TZ+4 columns, of which column 0 and TZ+3 are padding
     static constexpr int BZ = TZ + 4;
-    static constexpr int NH = 2 * SZ + 2 * TY;                 // halo ring cells
+    // SPY x SPZ groups of GY rows x GZ columns, each with its own psi ring (the cells next to a neighbouring group are recomputed)
+    static constexpr int SPLIT = SPY * SPZ, GY = TY / SPY, GZ = TZ / SPZ, GT = NT / SPLIT, RY = GY + 2, RZ = GZ + 2;
+    static constexpr int NH = 2 * RZ + 2 * GY;                 // halo ring cells of a group
     static constexpr int BOX = 19 * SY * BZ;                   // doubles per staged box
     static_assert(TZ % 2 == 0, "box rows must be a multiple of 16 bytes");
+    static_assert(TY % SPY == 0 && TZ % SPZ == 0 && GT % 32 == 0, "groups are whole warps");
     static constexpr int STAGE_BYTES = ((BOX * 8 + 127) / 128) * 128;
-    static constexpr int RING_BYTES = 4 * SY * SZ * 8;
-    static constexpr int SMEM = 2 * STAGE_BYTES + RING_BYTES + 64;
-    static_assert(NH <= NT, "one halo cell per thread");
+    static constexpr int RING_BYTES = SPLIT * 4 * RY * RZ * 8;
+    static constexpr int SMEM = NS * STAGE_BYTES + RING_BYTES + 256;   // NS full + NS empty mbarriers + NS counters behind the rings
+    static_assert(NH <= GT, "one halo cell per thread");
+    static_assert(NS >= 2 && NS <= 8, "2 to 8 stages");
 };
+
+// barrier + OR over the threads of one group (named barrier `id`, `nthreads` threads; id 0 = the whole CTA)
+template <int SPLIT, int GT>
+CLBM_D int group_sync_or(int pred, int id)
+{
+    if (SPLIT == 1) return __syncthreads_or(pred);
+    int res;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.s32 q, %1, 0;\n\t"
+        "bar.red.or.pred p, %2, %3, q;\n\t"
+        "selp.s32 %0, 1, 0, p;\n\t}"
+        : "=r"(res) : "r"(pred), "r"(id), "r"(GT) : "memory");
+    return res;
+}
 
 // CY > 1: the kernel is launched in thread-block clusters of CY tiles along y that cross a cluster barrier once per
 // plane.  Nothing is exchanged through it -- it only keeps y-neighbouring tiles on the same plane, so that the halo
 // rows they share (box rows y0-1 / y0+TY of one tile are own rows of the next) are fetched from HBM once and hit in
 // L2 the second time.  Without it tiles drift apart by several planes and the rows are evicted in between (ncu at
 // 512^3: 31.6 GB read for 20.4 GB of populations).
-template <int TY, int TZ, int MINB, int CY>
+//
+// NS stages; plane r of a chunk lives in stage r % NS.  EARLY = 0: a stage is refilled (plane r + NS) once plane r + 1 has arrived
+// and the own populations of plane r have been read -- with NS = 2 its box is then in flight only while plane r is collided and
+// stored, and a fifth of the warp time is spent waiting for it (profiles/r1_sc_d3q19_512_ncu_full_f.txt: the mbarrier wait holds
+// 20 % of the samples).  EARLY >= 1: the own populations of plane r are read FIRST and the stage is handed back before the wait for
+// plane r + 1, so that two boxes are in flight while psi of plane r + 1 is built (1: __syncthreads; 2: an "empty" mbarrier the
+// warps arrive on, only the issuing thread waits; 3: a shared-memory counter, the LAST warp to arrive issues the refill and nobody
+// waits).
+//
+// SPLIT = 2: the CTA is two independent groups of TY / 2 rows that share nothing but the staged boxes: each has its own psi ring
+// (the row next to the other group is recomputed rather than exchanged) and its own named barrier, so that the groups drift
+// apart by up to a plane and the shared-memory, FP64 and store phases of one overlap those of the other -- what a second CTA per
+// SM would give, without a second set of boxes (two 4 x 64 CTAs would need 2 x 124 KB and re-fetch the rows between them).
+template <int TY, int TZ, int MINB, int CY, int NS, int EARLY, int SPY, int SPZ>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, const uint8_t *__restrict__ flag,
                     const double *__restrict__ fin, const double *__restrict__ psi_g, Geom g, ModelParams mp, int xchunk,
                     int x_begin, int x_end, int nch1, int x2_begin, int x2_end)
 {
-    using C = TmaCfg<TY, TZ>;
+    using C = TmaCfg<TY, TZ, NS, SPY, SPZ>;
+    constexpr int SPLIT = SPY * SPZ;
+    static_assert(SPLIT == 1 || EARLY == 3, "independent groups need the waiting-free refill");
+    static_assert(SPLIT == 1 || CY == 1, "no lock-step clusters of split CTAs");
+    constexpr int NWARP = (TY * TZ + 31) / 32, GY = C::GY, GZ = C::GZ, GT = C::GT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t stage_a = smem_u32(smem_raw);   // shared-window address of stage 0 (stage 1 follows)
-    double (*ring)[C::SY][C::SZ] = reinterpret_cast<double (*)[C::SY][C::SZ]>(smem_raw + 2 * C::STAGE_BYTES);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + 2 * C::STAGE_BYTES + C::RING_BYTES);
-
+    const uint32_t stage_a = smem_u32(smem_raw);   // shared-window address of stage 0 (the others follow)
     const int tid = threadIdx.x;
-    const int tz = tid % TZ, ty = tid / TZ;
+    const int gq = SPLIT == 1 ? 0 : tid / GT, lt = SPLIT == 1 ? tid : tid % GT;   // group, thread within the group
+    double (*ring)[C::RY][C::RZ] = reinterpret_cast<double (*)[C::RY][C::RZ]>(smem_raw + NS * C::STAGE_BYTES) + gq * 4;
+    const int gy0 = (gq / SPZ) * GY, gz0 = (gq % SPZ) * GZ;   // first row / column of the group within the tile
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + NS * C::STAGE_BYTES + C::RING_BYTES);
+    uint64_t *mbar_empty = mbar + NS;
+    int *refill_cnt = reinterpret_cast<int *>(mbar_empty + NS);
+
+    const int tzl = lt % GZ, tyl = lt / GZ, ty = gy0 + tyl, tz = gz0 + tzl;   // position within the group, within the tile
     const int y0 = blockIdx.y * TY, z0 = blockIdx.x * TZ;
     const int y = y0 + ty, z = z0 + tz;
     const bool inside = (y < g.ny) && (z < g.nz);
@@ -77,48 +117,81 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     const int xa = second ? x2_begin + ((int)blockIdx.z - nch1) * xchunk : x_begin + (int)blockIdx.z * xchunk;
     const int nplanes = min(second ? x2_end : x_end, xa + xchunk) - xa;
     const int plane = (int)g.plane, nz = g.nz, G = g.G;
-    const int ty_n = min(TY, g.ny - y0), tz_n = min(TZ, g.nz - z0);
-    const int nrow = tz_n + 2, nhalo = 2 * nrow + 2 * ty_n;
+    const int ty_n = max(0, min(GY, g.ny - (y0 + gy0))), tz_n = max(0, min(GZ, g.nz - (z0 + gz0)));   // rows / columns of the group inside the lattice
+    const int nrow = tz_n + 2, nhalo = (ty_n > 0 && tz_n > 0) ? 2 * nrow + 2 * ty_n : 0;
     const int yz = y * nz + z;
     const int own_s = (ty + 1) * C::BZ + (tz + 2);   // own cell inside a staged k-slab (box column = ring column + 1)
 
-    // this thread's halo cell (if any): position in the box, wrapped lattice position, whether TMA could not fetch it
-    const bool h_act = tid < nhalo;
+    // this thread's halo cell (if any): position in the group's ring, in the box, wrapped lattice position, whether TMA
+    // could not fetch it
+    const bool h_act = lt < nhalo;
     int hsy = 0, hsz = 0;
     if (h_act) {
-        if (tid < nrow) { hsy = 0; hsz = tid; }
-        else if (tid < 2 * nrow) { hsy = ty_n + 1; hsz = tid - nrow; }
-        else { const int q = tid - 2 * nrow; hsy = 1 + (q >> 1); hsz = (q & 1) ? tz_n + 1 : 0; }
+        if (lt < nrow) { hsy = 0; hsz = lt; }
+        else if (lt < 2 * nrow) { hsy = ty_n + 1; hsz = lt - nrow; }
+        else { const int q = lt - 2 * nrow; hsy = 1 + (q >> 1); hsz = (q & 1) ? tz_n + 1 : 0; }
     }
-    const int hy_raw = y0 + hsy - 1, hz_raw = z0 + hsz - 1;
+    const int hy_raw = y0 + gy0 + hsy - 1, hz_raw = z0 + gz0 + hsz - 1;
     const bool h_wrapped = (hy_raw < 0) || (hy_raw >= g.ny) || (hz_raw < 0) || (hz_raw >= g.nz);
     const int hyz = g.wy(hy_raw) * nz + g.wz(hz_raw);
-    const int h_s = hsy * C::BZ + (hsz + 1);
+    const int h_s = (gy0 + hsy) * C::BZ + (gz0 + hsz + 1);
 
     if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&mbar[s], 1);
+            mbar_init(&mbar_empty[s], NWARP);
+            refill_cnt[s] = 0;
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // r = 0 .. nplanes+1 enumerates the planes xa-1 .. xa+nplanes; plane r lives in stage r&1, ring slot r&3
+    // r = 0 .. nplanes+1 enumerates the planes xa-1 .. xa+nplanes; plane r lives in stage r % NS, ring slot r&3
     auto xs_of = [&](int r) { return g.wx(xa - 1 + r) + G; };   // storage plane
     auto issue = [&](int r) {
-        mbar_expect_tx(&mbar[r & 1], (uint32_t)(C::BOX * 8));
-        tma_load_4d(stage_a + (r & 1) * C::STAGE_BYTES, &tmap, &mbar[r & 1], z0 - 2, y0 - 1, xs_of(r), 0);
+        mbar_expect_tx(&mbar[r % NS], (uint32_t)(C::BOX * 8));
+        tma_load_4d(stage_a + (r % NS) * C::STAGE_BYTES, &tmap, &mbar[r % NS], z0 - 2, y0 - 1, xs_of(r), 0);
+    };
+    auto wait_full = [&](int r) { mbar_wait(&mbar[r % NS], (uint32_t)((r / NS) & 1)); };
+    // this thread is done with the stage of plane r; once every thread is, the stage is refilled with plane r + NS
+    auto release_and_refill = [&](int r) {
+        if (EARLY == 3) {
+            __syncwarp();
+            if ((tid & 31) == 0) {
+                __threadfence_block();
+                const int old = atomicAdd(&refill_cnt[r % NS], 1);
+                if (old == NWARP - 1) {
+                    // last warp out: the counter is next touched after the refill has landed, so a plain reset is safe
+                    refill_cnt[r % NS] = 0;
+                    __threadfence_block();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if (r + NS <= nplanes + 1) issue(r + NS);
+                }
+            }
+        } else if (EARLY == 2) {
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&mbar_empty[r % NS]);
+            if (tid == 0 && r + NS <= nplanes + 1) {
+                mbar_wait(&mbar_empty[r % NS], (uint32_t)((r / NS) & 1));
+                issue(r + NS);
+            }
+        } else {
+            __syncthreads();
+            if (tid == 0 && r + NS <= nplanes + 1) issue(r + NS);
+        }
     };
     double psn = 0.0, rhn = 0.0;
     bool gpn = true;
-    // psi of plane r (tile + halo ring) from its staged box into the ring; keeps the own psi / G1 branch
+    // psi of plane r (rows of the group + halo ring) from its staged box into the group's ring; keeps the own psi / G1 branch
     auto make_psi = [&](int r, uint8_t fl_own, uint8_t fl_halo) {
-        const uint32_t st = stage_a + (r & 1) * C::STAGE_BYTES;
+        const uint32_t st = stage_a + (r % NS) * C::STAGE_BYTES;
         const int xg = xa - 1 + r;
         if (!g.wrapx && (xg < 0 || xg >= g.nx)) {
             // x-slab mode: planes -1 and nx belong to the neighbour slab; their psi arrived with the moment halo
             // exchange (|value| = psi, see sc_psi_kernel) and their mask sits in the ghost planes of flag[]
             const int xs = xg + G;
-            if (inside) ring[r & 3][ty + 1][tz + 1] = (fl_own == CELL_BB) ? -1.0 : fabs(psi_g[xs * plane + yz]);
+            if (inside) ring[r & 3][tyl + 1][tzl + 1] = (fl_own == CELL_BB) ? -1.0 : fabs(psi_g[xs * plane + yz]);
             if (h_act) ring[r & 3][hsy][hsz] = (fl_halo == CELL_BB) ? -1.0 : fabs(psi_g[xs * plane + hyz]);
             return;
         }
@@ -135,7 +208,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
                 psn = sc_psi_g1(mp, rhn, gpn);
                 v = psn;
             }
-            ring[r & 3][ty + 1][tz + 1] = v;
+            ring[r & 3][tyl + 1][tzl + 1] = v;
         }
         if (h_act) {
             double v = -1.0;
@@ -161,27 +234,32 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
         fh = h_act ? flag[xs * plane + hyz] : CELL_BB;
     };
 
-    if (tid == 0) { issue(0); issue(1); }
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < NS; ++r)
+            if (r <= nplanes + 1) issue(r);
+    }
     uint8_t fo, fh;
-    // wmask bit (r & 3): plane r has a bounce_back node inside this CTA's tile + halo ring (CTA-uniform).  Planes
+    // wmask bit (r & 3): plane r has a bounce_back node inside this group's rows + halo ring (group-uniform).  Planes
     // without walls around take the branch-free force sums and unconditional pushes below.
     unsigned wmask = 0;
     auto has_wall = [&](uint8_t fl_own, uint8_t fl_halo) { return (int)((inside && fl_own == CELL_BB) || (h_act && fl_halo == CELL_BB)); };
     flags_of(0, fo, fh);
     int w0 = has_wall(fo, fh);
-    mbar_wait(&mbar[0], 0);
+    wait_full(0);
     make_psi(0, fo, fh);
+    if (EARLY) release_and_refill(0);   // plane 0 only feeds psi: its stage goes back at once
     flags_of(1, fo, fh);
     const int w1 = has_wall(fo, fh);
-    mbar_wait(&mbar[1], 0);
+    wait_full(1);
     make_psi(1, fo, fh);
     double psc = psn, rhc = rhn;
     bool gpc = gpn;
     flags_of(2, fo, fh);        // the node mask runs one plane ahead of its use so that its latency never shows
-    w0 = __syncthreads_or(w0 | (w1 << 1));
+    w0 = group_sync_or<SPLIT, GT>(w0 | (w1 << 1), 1 + gq);
     wmask = (unsigned)w0 & 3u;   // an OR over both prologue planes: conservative (bit set where either plane has a wall)
     if (wmask) wmask = 3u;
-    if (tid == 0 && nplanes + 1 >= 2) issue(2);
+    if (!EARLY && tid == 0 && NS <= nplanes + 1) issue(NS);
 
     const int oym = (g.wy(y - 1) - y) * nz, oyp = (g.wy(y + 1) - y) * nz;
     const int ozm = g.wz(z - 1) - z, ozp = g.wz(z + 1) - z;
@@ -189,25 +267,29 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
     for (int r = 1; r <= nplanes; ++r) {
         const uint8_t fo_now = fo, fh_now = fh;
         if (r + 2 <= nplanes + 1) flags_of(r + 2, fo, fh);
-        mbar_wait(&mbar[(r + 1) & 1], ((r + 1) >> 1) & 1);
-        make_psi(r + 1, fo_now, fh_now);
-
         // own populations of plane r out of its stage before the stage is recycled
         double fc[19];
-        {
-            const uint32_t st = stage_a + (r & 1) * C::STAGE_BYTES;
+        auto load_own = [&]() {
+            const uint32_t st = stage_a + (r % NS) * C::STAGE_BYTES;
 #pragma unroll
             for (int k = 0; k < 19; ++k) fc[k] = lds_f64(st + (k * (C::SY * C::BZ) + own_s) * 8);
+        };
+        if (EARLY) {
+            load_own();
+            release_and_refill(r);
         }
+        wait_full(r + 1);
+        make_psi(r + 1, fo_now, fh_now);
+        if (!EARLY) load_own();
         {
             const unsigned bit = 1u << ((r + 1) & 3);
-            wmask = __syncthreads_or(has_wall(fo_now, fh_now)) ? (wmask | bit) : (wmask & ~bit);
+            wmask = group_sync_or<SPLIT, GT>(has_wall(fo_now, fh_now), 1 + gq) ? (wmask | bit) : (wmask & ~bit);
         }
         if (CY > 1) {
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         }
-        if (tid == 0 && r + 2 <= nplanes + 1) issue(r + 2);
+        if (!EARLY && tid == 0 && r + NS <= nplanes + 1) issue(r + NS);
 
         const int sm = (r + 3) & 3, s0 = r & 3, sp = (r + 1) & 3;
         const bool walls = (wmask & ((1u << sm) | (1u << s0) | (1u << sp))) != 0u;
@@ -219,7 +301,7 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
                 for (int k = 0; k < 19; ++k) {
                     if (k == L3::REST) continue;
                     const int slot = L3::cx(k) < 0 ? sm : (L3::cx(k) > 0 ? sp : s0);
-                    const double v = ring[slot][ty + 1 + L3::cy(k)][tz + 1 + L3::cz(k)];
+                    const double v = ring[slot][tyl + 1 + L3::cy(k)][tzl + 1 + L3::cz(k)];
                     if (L3::cx(k)) s.ff[0] += L3::t(k) * L3::cx(k) * v;
                     if (L3::cy(k)) s.ff[1] += L3::t(k) * L3::cy(k) * v;
                     if (L3::cz(k)) s.ff[2] += L3::t(k) * L3::cz(k) * v;
@@ -236,13 +318,13 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
                     P.at(k)[i + off] = out[k];
                 }
             }
-        } else if (inside && ring[s0][ty + 1][tz + 1] >= 0.0) {
+        } else if (inside && ring[s0][tyl + 1][tzl + 1] >= 0.0) {
             ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
 #pragma unroll
             for (int k = 0; k < 19; ++k) {
                 if (k == L3::REST) continue;
                 const int slot = L3::cx(k) < 0 ? sm : (L3::cx(k) > 0 ? sp : s0);
-                const double v = ring[slot][ty + 1 + L3::cy(k)][tz + 1 + L3::cz(k)];
+                const double v = ring[slot][tyl + 1 + L3::cy(k)][tzl + 1 + L3::cz(k)];
                 sc_force_add<L3>(s, k, v < 0.0, v);
             }
             double out[19];
@@ -274,10 +356,11 @@ bool sc_tma_eligible(const clbm_ctx *c)
     return c->Q == 19 && (g.nz % 2 == 0) && g.ncs < (1LL << 31) && get_encode() != nullptr;
 }
 
-template <int TY, int TZ, int MINB, int CY>
+template <int TY, int TZ, int MINB, int CY, int NS = 2, int EARLY = 0, int SPY = 1, int SPZ = 1>
 static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
-    using C = TmaCfg<TY, TZ>;
+    using C = TmaCfg<TY, TZ, NS, SPY, SPZ>;
+    static_assert(C::SMEM <= 232448, "stages + psi ring must fit the 227 KB a CTA may opt in to");
     const Geom &g = c->geo;
     CUtensorMap tmap;
     const cuuint32_t box[4] = {(cuuint32_t)C::BZ, (cuuint32_t)C::SY, 1, 19};
@@ -303,7 +386,7 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
     const int nch1 = (nxr + xchunk - 1) / xchunk, nch2 = x2_end > x2_begin ? (x2_end - x2_begin + xchunk - 1) / xchunk : 0;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, nch1 + nch2);
     const OutTable P = {c->pop[0][1 - c->parity], (size_t)g.ncs};
-    auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY>;
+    auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY, NS, EARLY, SPY, SPZ>;
     static PerDeviceOnce attr;
     if (attr.need(c->device)) {
         CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -335,9 +418,10 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
 
 // lock-step clusters along y are an experiment (CLBM_SC_CLUSTER = 2 / 4): measured SLOWER at 512^3 (12.8 / 11.8 vs 14.8
 // GLUPS) -- waiting for the slower partner costs more than the shared halo rows save -- so the default is 1
-template <int TY, int TZ, int MINB>
+template <int TY, int TZ, int MINB, int NS = 2, int EARLY = 0, int SPY = 1, int SPZ = 1>
 static int launch_tma(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
+    if (NS != 2 || EARLY != 0) return launch_tma_c<TY, TZ, MINB, 1, NS, EARLY, SPY, SPZ>(c, x_begin, x_end, x2_begin, x2_end);
     const int cy = c->env.sc_cluster > 0 ? c->env.sc_cluster : 1;
     const int ytiles = (c->geo.ny + TY - 1) / TY;
     if (MINB == 1 && cy >= 4 && ytiles % 4 == 0) return launch_tma_c<TY, TZ, MINB, 4>(c, x_begin, x_end, x2_begin, x2_end);
@@ -356,6 +440,14 @@ int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_
     case 14: rc = launch_tma<4, 32, 3>(c, x_begin, x_end, x2_begin, x2_end); break;
     case 15: rc = launch_tma<8, 16, 3>(c, x_begin, x_end, x2_begin, x2_end); break;
     case 16: rc = launch_tma<8, 32, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 21: rc = launch_tma<8, 64, 1, 2, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 22: rc = launch_tma<8, 64, 1, 2, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 23: rc = launch_tma<8, 64, 1, 2, 3>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 24: rc = launch_tma<8, 64, 1, 2, 3, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 25: rc = launch_tma<8, 64, 1, 2, 3, 1, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 26: rc = launch_tma<8, 64, 1, 2, 3, 1, 4>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 27: rc = launch_tma<16, 32, 1, 2, 3, 2, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 28: rc = launch_tma<16, 32, 1, 2, 3, 4, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
     default: rc = launch_tma<6, 32, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
     }
     return rc;
