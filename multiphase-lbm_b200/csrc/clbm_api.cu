@@ -70,6 +70,7 @@ int diag_contact_angle_raw(clbm_ctx *c, double rho_cut, int base_y_in, int out[4
 int diag_interface_heights(clbm_ctx *c, double phi_mid, int *y_x0, int *y_xmid);
 int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
+int slab_step_for_profile(clbm_ctx *c);   // slab_comm.cu
 int sc_psi_all(clbm_ctx *c);
 int sc_psi_boundary(clbm_ctx *c);
 bool sc_range_supported(const clbm_ctx *c);
@@ -749,15 +750,17 @@ int64_t clbm_launch_count(const clbm_ctx *c) { return c ? c->launches : -1; }
 int clbm_profile_step(clbm_ctx *c, const char **names, float *ms, int cap)
 {
     if (!c || !names || !ms || cap <= 0) { set_error("bad argument to clbm_profile_step"); return CLBM_EINVAL; }
-    if (c->multi) { set_error("profile a single-slab context"); return CLBM_ESTATE; }
+    // an x-slab context can be profiled on a ring inside ONE process (every launch is followed by a host synchronisation, which
+    // a ring across processes would not survive): the self ring of tools/self_ring_bench.py
+    if (c->multi && !c->peer_mode) { set_error("profile a single-slab context or a context on a same-process peer ring"); return CLBM_ESTATE; }
     CLBM_CUDA(cudaSetDevice(c->device));
     CLBM_CUDA(cudaStreamSynchronize(c->stream));
     c->prof.clear();
     c->profiling = true;
-    int rc = model_step(c);
+    int rc = c->multi ? slab_step_for_profile(c) : model_step(c);
     c->profiling = false;
     if (rc) return rc;
-    count_step(c);
+    if (!c->multi) count_step(c);
     int n = 0;
     for (auto &k : c->prof) {
         if (n >= cap) break;

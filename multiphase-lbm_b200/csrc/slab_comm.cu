@@ -269,6 +269,9 @@ static int capture_two_steps(clbm_ctx *c, cudaGraphExec_t *out, int64_t *launche
     return 0;
 }
 
+// one call-by-call slab step for clbm_profile_step (every launch bracketed by events, host-synchronised: a ring of one process)
+int slab_step_for_profile(clbm_ctx *c) { return slab_step_eager(c); }
+
 }  // namespace clbm
 
 using namespace clbm;
