@@ -232,9 +232,9 @@ static int sc_tma_variant(const clbm_ctx *c)
     // clbm_params.fused: 1 = default fused kernel, >1 = explicit tile variant (tuning / tests); env overrides
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (c->env.sc_tile >= 0) variant = c->env.sc_tile;
-    // D3Q19 default: the TMA-staged kernel with 8 x 64 tiles as two independent 4-row groups, early stage release (variant 24: best of
+    // D3Q19 default: the TMA-staged kernel with 8 x 64 tiles as two independent 4-row groups, early stage release (variant 29, = 24 with 32-bit store indices: best of
     // the sweeps in profiles/README.md)
-    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 24;
+    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 29;
     return (variant >= 10 && sc_tma_eligible(c)) ? variant : 0;
 }
 
@@ -250,7 +250,7 @@ int sc_fused_launch(clbm_ctx *c)
     int rc;
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (c->env.sc_tile >= 0) variant = c->env.sc_tile;
-    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 24;
+    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 29;
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;
     if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO) return launch_fused<D2Q9, 128, 1, 4, true>(c);   // D2Q9 only (clbm_create)

@@ -31,6 +31,7 @@ using L3 = D3Q19;
 struct OutTable {
     double *base;
     size_t ncs;
+    unsigned kn[19];   // k * ncs as 32-bit element offsets (valid while 19 * ncs < 2^32: IDX32 kernels)
     CLBM_D double *at(int k) const { return base + (size_t)k * ncs; }
 };
 
@@ -86,7 +87,11 @@ CLBM_D int group_sync_or(int pred, int id)
 // (the row next to the other group is recomputed rather than exchanged) and its own named barrier, so that the groups drift
 // apart by up to a plane and the shared-memory, FP64 and store phases of one overlap those of the other -- what a second CTA per
 // SM would give, without a second set of boxes (two 4 x 64 CTAs would need 2 x 124 KB and re-fetch the rows between them).
-template <int TY, int TZ, int MINB, int CY, int NS, int EARLY, int SPY, int SPZ>
+//
+// IDX32: the whole "out" buffer is addressed with unsigned 32-bit element indices from one base pointer (19 * ncs < 2^32).  The
+// general form spends seven integer instructions per store on k * ncs + i + offset in 64 bits (133 of 747 per node in
+// profiles/r2_sc_d3q19_512_ncu_full_g.txt); this one two or three.
+template <int TY, int TZ, int MINB, int CY, int NS, int EARLY, int SPY, int SPZ, int IDX32>
 __global__ void __launch_bounds__(TY *TZ, MINB)
 sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, const uint8_t *__restrict__ flag,
                     const double *__restrict__ fin, const double *__restrict__ psi_g, Geom g, ModelParams mp, int xchunk,
@@ -311,11 +316,22 @@ sc_fused_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable P, 
                 const int x = xa - 1 + r;
                 const int i = (x + G) * plane + yz;
                 const int oxm = (g.wx(x - 1) - x) * plane, oxp = (g.wx(x + 1) - x) * plane;
+                if (IDX32) {
+                    const unsigned i0 = (unsigned)i, im = (unsigned)(i + oxm), ip = (unsigned)(i + oxp);
 #pragma unroll
-                for (int k = 0; k < 19; ++k) {
-                    const int off = (L3::cx(k) < 0 ? oxm : (L3::cx(k) > 0 ? oxp : 0)) + (L3::cy(k) < 0 ? oym : (L3::cy(k) > 0 ? oyp : 0)) +
-                                    (L3::cz(k) < 0 ? ozm : (L3::cz(k) > 0 ? ozp : 0));
-                    P.at(k)[i + off] = out[k];
+                    for (int k = 0; k < 19; ++k) {
+                        unsigned idx = (L3::cx(k) < 0 ? im : (L3::cx(k) > 0 ? ip : i0)) + P.kn[k];
+                        if (L3::cy(k)) idx += (unsigned)(L3::cy(k) < 0 ? oym : oyp);
+                        if (L3::cz(k)) idx += (unsigned)(L3::cz(k) < 0 ? ozm : ozp);
+                        P.base[idx] = out[k];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 19; ++k) {
+                        const int off = (L3::cx(k) < 0 ? oxm : (L3::cx(k) > 0 ? oxp : 0)) + (L3::cy(k) < 0 ? oym : (L3::cy(k) > 0 ? oyp : 0)) +
+                                        (L3::cz(k) < 0 ? ozm : (L3::cz(k) > 0 ? ozp : 0));
+                        P.at(k)[i + off] = out[k];
+                    }
                 }
             }
         } else if (inside && ring[s0][tyl + 1][tzl + 1] >= 0.0) {
@@ -356,9 +372,11 @@ bool sc_tma_eligible(const clbm_ctx *c)
     return c->Q == 19 && (g.nz % 2 == 0) && g.ncs < (1LL << 31) && get_encode() != nullptr;
 }
 
-template <int TY, int TZ, int MINB, int CY, int NS = 2, int EARLY = 0, int SPY = 1, int SPZ = 1>
+template <int TY, int TZ, int MINB, int CY, int NS = 2, int EARLY = 0, int SPY = 1, int SPZ = 1, int IDX32 = 0>
 static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
+    if (IDX32 && 19ull * (unsigned long long)c->geo.ncs >= (1ull << 32))   // too large for 32-bit element indices: the general form
+        return launch_tma_c<TY, TZ, MINB, CY, NS, EARLY, SPY, SPZ, 0>(c, x_begin, x_end, x2_begin, x2_end);
     using C = TmaCfg<TY, TZ, NS, SPY, SPZ>;
     static_assert(C::SMEM <= 232448, "stages + psi ring must fit the 227 KB a CTA may opt in to");
     const Geom &g = c->geo;
@@ -385,8 +403,9 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
     if (c->env.sc_xchunk > 0) xchunk = c->env.sc_xchunk < nxr ? c->env.sc_xchunk : nxr;
     const int nch1 = (nxr + xchunk - 1) / xchunk, nch2 = x2_end > x2_begin ? (x2_end - x2_begin + xchunk - 1) / xchunk : 0;
     dim3 grid((g.nz + TZ - 1) / TZ, (g.ny + TY - 1) / TY, nch1 + nch2);
-    const OutTable P = {c->pop[0][1 - c->parity], (size_t)g.ncs};
-    auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY, NS, EARLY, SPY, SPZ>;
+    OutTable P = {c->pop[0][1 - c->parity], (size_t)g.ncs, {0}};
+    for (int k = 0; k < 19; ++k) P.kn[k] = (unsigned)((unsigned long long)k * (unsigned long long)g.ncs);
+    auto kern = sc_fused_tma_kernel<TY, TZ, MINB, CY, NS, EARLY, SPY, SPZ, IDX32>;
     static PerDeviceOnce attr;
     if (attr.need(c->device)) {
         CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -418,10 +437,10 @@ static int launch_tma_c(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x
 
 // lock-step clusters along y are an experiment (CLBM_SC_CLUSTER = 2 / 4): measured SLOWER at 512^3 (12.8 / 11.8 vs 14.8
 // GLUPS) -- waiting for the slower partner costs more than the shared halo rows save -- so the default is 1
-template <int TY, int TZ, int MINB, int NS = 2, int EARLY = 0, int SPY = 1, int SPZ = 1>
+template <int TY, int TZ, int MINB, int NS = 2, int EARLY = 0, int SPY = 1, int SPZ = 1, int IDX32 = 0>
 static int launch_tma(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
-    if (NS != 2 || EARLY != 0) return launch_tma_c<TY, TZ, MINB, 1, NS, EARLY, SPY, SPZ>(c, x_begin, x_end, x2_begin, x2_end);
+    if (NS != 2 || EARLY != 0) return launch_tma_c<TY, TZ, MINB, 1, NS, EARLY, SPY, SPZ, IDX32>(c, x_begin, x_end, x2_begin, x2_end);
     const int cy = c->env.sc_cluster > 0 ? c->env.sc_cluster : 1;
     const int ytiles = (c->geo.ny + TY - 1) / TY;
     if (MINB == 1 && cy >= 4 && ytiles % 4 == 0) return launch_tma_c<TY, TZ, MINB, 4>(c, x_begin, x_end, x2_begin, x2_end);
@@ -446,6 +465,7 @@ int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_
     case 24: rc = launch_tma<8, 64, 1, 2, 3, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
     case 25: rc = launch_tma<8, 64, 1, 2, 3, 1, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
     case 26: rc = launch_tma<8, 64, 1, 2, 3, 1, 4>(c, x_begin, x_end, x2_begin, x2_end); break;
+    case 29: rc = launch_tma<8, 64, 1, 2, 3, 2, 1, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
     case 27: rc = launch_tma<16, 32, 1, 2, 3, 2, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
     case 28: rc = launch_tma<16, 32, 1, 2, 3, 4, 1>(c, x_begin, x_end, x2_begin, x2_end); break;
     default: rc = launch_tma<6, 32, 2>(c, x_begin, x_end, x2_begin, x2_end); break;
