@@ -435,6 +435,9 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->nfld = 0;
     c->scratch = nullptr;
     c->scratch_bytes = 0;
+    c->sc_queue = nullptr;
+    c->sc_queue_next = 0;
+    c->sm_count = 0;
     c->stream_u = nullptr;
     memset(c->mom, 0, sizeof(c->mom));
     memset(c->mome, 0, sizeof(c->mome));
@@ -503,6 +506,7 @@ int clbm_destroy(clbm_ctx *c)
     if (c->red_host) cudaFreeHost(c->red_host);
     if (c->stage) cudaFreeHost(c->stage);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->sc_queue) cudaFree(c->sc_queue);
     for (int m = 0; m < 5; ++m) {
         if (c->mom[1][m]) cudaFree(c->mom[1][m]);      // mom[0] aliases fld[0..4]
         for (int s = 0; s < 2; ++s) if (c->mome[s][m]) cudaFree(c->mome[s][m]);

@@ -196,6 +196,11 @@ struct clbm_ctx {
     std::vector<clbm::KernelTiming> prof;
     clbm::EnvKnobs env;
     std::vector<clbm::TmapEntry> tmaps;
+    // work queues of the persistent Shan-Chen D3Q19 kernel (sc_fused_tma_persist.cu): 8 x {next item, CTAs done}, one pair per
+    // launch in rotation (two launches of the overlap protocol may run at the same time); each returns to zero by itself
+    int *sc_queue;
+    int sc_queue_next;
+    int sm_count;
     // persistent device scratch of clbm_download_fields / clbm_download_force (grown on demand, freed in clbm_destroy)
     double *scratch;
     size_t scratch_bytes;

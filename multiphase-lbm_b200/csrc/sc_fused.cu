@@ -224,6 +224,7 @@ static int launch_fused(clbm_ctx *c)
 bool sc_tma_eligible(const clbm_ctx *c);            // sc_fused_tma.cu
 int sc_fused_tma_step(clbm_ctx *c, int variant);
 int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_begin, int x2_end);
+int sc_fused_tma_persist_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_begin, int x2_end);   // sc_fused_tma_persist.cu
 
 // one fused collide-stream sweep over the local planes; does NOT flip the parity
 // tile variant of the TMA kernel this context would run, 0 when it runs one of the register-pipelined kernels
@@ -238,11 +239,29 @@ static int sc_tma_variant(const clbm_ctx *c)
     return (variant >= 10 && sc_tma_eligible(c)) ? variant : 0;
 }
 
+// the work queue of the next launch of the persistent kernel (allocated and zeroed on first use)
+int sc_persist_queue(clbm_ctx *c, int **q)
+{
+    if (!c->sc_queue) {
+        CLBM_CUDA(cudaMalloc(&c->sc_queue, 16 * sizeof(int)));
+        CLBM_CUDA(cudaMemsetAsync(c->sc_queue, 0, 16 * sizeof(int), c->stream));
+        if (c->stream_b) {   // the boundary stream may launch the kernel too: order the memset before anything it does
+            CLBM_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, c->device) == cudaSuccess) c->sm_count = n;
+    }
+    *q = c->sc_queue + 2 * (c->sc_queue_next++ & 7);
+    return 0;
+}
+
 // x-range launches (overlap protocol of the slab exchange) exist for the TMA kernel
 bool sc_range_supported(const clbm_ctx *c) { return c->prm.fused && sc_tma_variant(c) != 0; }
 int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end, int x2_begin, int x2_end)
 {
-    return sc_fused_tma_range(c, sc_tma_variant(c), x_begin, x_end, x2_begin, x2_end);
+    const int v = sc_tma_variant(c);
+    if (v >= 40) return sc_fused_tma_persist_range(c, v, x_begin, x_end, x2_begin, x2_end);
+    return sc_fused_tma_range(c, v, x_begin, x_end, x2_begin, x2_end);
 }
 
 int sc_fused_launch(clbm_ctx *c)
@@ -251,6 +270,7 @@ int sc_fused_launch(clbm_ctx *c)
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (c->env.sc_tile >= 0) variant = c->env.sc_tile;
     if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 29;
+    if (variant >= 40 && sc_tma_eligible(c)) return sc_fused_tma_persist_range(c, variant, 0, c->geo.nx, 0, 0);
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;
     if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO) return launch_fused<D2Q9, 128, 1, 4, true>(c);   // D2Q9 only (clbm_create)

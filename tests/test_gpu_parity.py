@@ -80,7 +80,7 @@ def test_sc_contact2d_walls_1000_steps(fused):
     check_fields(ora.fields(), got, ("s0", "s1", "ux", "uy"))
 
 
-@pytest.mark.parametrize("fused", [0, 1, 2, 5, 9, 10, 11, 12, 13, 14, 15, 16, 21, 22, 23, 24, 25, 26, 27, 28, 29])
+@pytest.mark.parametrize("fused", [0, 1, 2, 5, 9, 10, 11, 12, 13, 14, 15, 16, 21, 22, 23, 24, 25, 26, 27, 28, 29, 41])
 def test_sc_d3q19_sessile_droplet(fused):
     """config 4 physics at a size the oracle finishes: walls y=0,ny-1, contact-angle force"""
     prm = P.sc_params(P.MODEL_SC_D3Q19, 40, 24, 36, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)

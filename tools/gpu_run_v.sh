@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/sc3d_variants.py 512 20 > gpurun_out/r2v_sc3d_variants.txt 2>&1
-CLBM_TMA_PROMO=2 timeout 600 python tools/sc3d_variants.py 512 20 24 29 2>&1 | sed 's/^variant/promo128 variant/' >> gpurun_out/r2v_sc3d_variants.txt
-CLBM_TMA_PROMO=0 timeout 600 python tools/sc3d_variants.py 512 20 24 29 2>&1 | sed 's/^variant/promo0 variant/' >> gpurun_out/r2v_sc3d_variants.txt
+timeout 300 python tools/sc3d_variants.py 512 20 29 41 > gpurun_out/r2v_sc3d_variants.txt 2>&1
+CLBM_SC_PERSIST_STATIC=1 timeout 300 python tools/sc3d_variants.py 512 20 41 2>&1 | sed 's/^variant/static variant/' >> gpurun_out/r2v_sc3d_variants.txt
 cat gpurun_out/r2v_sc3d_variants.txt
 echo done

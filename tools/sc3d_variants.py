@@ -15,7 +15,7 @@ pkg = entry.load_package()
 P = pkg.params
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-variants = [int(v) for v in sys.argv[3:]] or [11, 24, 29]
+variants = [int(v) for v in sys.argv[3:]] or [11, 29, 41]
 t_start = time.time()
 
 
@@ -44,7 +44,7 @@ for v in variants:
     ok = np.array_equal(got, base)
     diff = float(np.max(np.abs(got - base)) / np.max(np.abs(base)))
     out = []
-    for xc in (None, 20, 28, 32):
+    for xc in (None, 16, 32, 48):
         with lattice(nx, v, xc) as lat:
             lat.step(5)
             lat.sync()
