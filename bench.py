@@ -189,8 +189,9 @@ def run_reference_arm(a, rank):
     print(json.dumps(line))
 
 
-def reference_functor_baseline(key):
-    """the UNTOUCHED reference functor (oracle/_ref harness binary), all host threads, small sample"""
+def reference_functor_baseline(key, same_lattice=None):
+    """the UNTOUCHED reference functor (oracle/_ref harness binary), all host threads, small sample.
+    same_lattice = (nx, ny, steps): time it on exactly the GPU arm's lattice (the L2-resident BASELINE configs[0-1])."""
     from _oracle import ref_binary
     spec = {"sc2d": ("ref_sc_laplace2d", ["nx=512", "ny=512", "steps=40"]),
             "sc2d_tau1": ("ref_sc_laplace2d", ["nx=512", "ny=512", "steps=40", "omega=1.0"]),
@@ -199,11 +200,13 @@ def reference_functor_baseline(key):
             "hcz3d": ("ref_hcz_laplace3d", ["nx=16", "ny=16", "nz=16", "steps=2"])}.get(key)
     if not spec or not ref_binary(spec[0]):
         return None
+    if same_lattice:
+        spec = (spec[0], ["nx=%d" % same_lattice[0], "ny=%d" % same_lattice[1], "steps=%d" % same_lattice[2]] + [a for a in spec[1] if a.startswith("omega")])
     thr = host_threads()
     try:
         out = subprocess.check_output([ref_binary(spec[0])] + spec[1] + ["threads=%d" % thr], timeout=600).decode()
         r = json.loads(out.strip().splitlines()[0])
-        return {"value": r["mlups"], "unit": "MLUPS", "cores": thr, "kind": "reference",
+        return {"value": r["mlups"], "unit": "MLUPS", "cores": thr, "kind": "reference", "same_lattice_as_gpu": bool(same_lattice),
                 "sample": "%s %s (reference header compiled unmodified, index range sharded over std::threads)" % (spec[0], " ".join(spec[1]))}
     except Exception as e:  # noqa: BLE001
         return {"error": str(e)}
@@ -252,7 +255,7 @@ def l2_policy_text(bytes_per_gpu):
            "lattice every step), the HBM roofline fraction is not meaningful for this configuration" % (bytes_per_gpu / 1e6)
 
 
-def measure(cx, workload, scaling, steps, warmup, fused=1, size="", solo=False, sample_clocks=False, keep=False):
+def measure(cx, workload, scaling, steps, warmup, fused=1, size="", solo=False, sample_clocks=False, keep=False, ktiming=True):
     """device-resident timing of one workload.  solo: this rank runs the WHOLE lattice alone (the 1-GPU reference of a strong
     pass).  Returns a dict (timings identical on every rank after the all-reduce) and, with keep, the live objects."""
     torch = cx.torch
@@ -295,7 +298,7 @@ def measure(cx, workload, scaling, steps, warmup, fused=1, size="", solo=False, 
     if sampler:
         sampler.start()
     l0 = lat.launch_count()
-    if ring is None:
+    if ring is None and ktiming:
         lat.kernel_timing_begin(min(steps, 512))
     if not solo:
         cx.barrier()
@@ -312,7 +315,9 @@ def measure(cx, workload, scaling, steps, warmup, fused=1, size="", solo=False, 
     if not solo:
         cx.barrier()
     launches = lat.launch_count() - l0
-    if ring is None:
+    if ring is None and not ktiming:
+        kms, kcount, kname = 0.0, 0, None     # L2-resident lattices: event pairs around every launch would be a third of the step
+    elif ring is None:
         kms, kcount, kname = lat.kernel_timing_end()
     else:
         # dominant-kernel time on a ring: event pairs around the launches cannot live inside a replayed graph, so a few
@@ -463,6 +468,16 @@ def main():
             t, tsrc = ncu_traffic("c3_hcz_d2q9_2048x8194" if wl == "c3_hcz_d2q9_full" else wl)
             r["traffic"], r["traffic_source"] = t, tsrc
             r["l2_policy"] = l2_policy_text(r["bytes_per_gpu"])
+            also[wl] = r
+        # BASELINE configs[0] and configs[1]: L2-resident lattices, latency per step is the figure; the UNTOUCHED reference functor
+        # is timed on the very same lattice (the one configuration where that is possible within seconds)
+        for wl, ref_steps in (("c1_sc_d2q9_256", 300), ("c2_hcz_d2q9_256", 12)):
+            r = measure(cx, wl, "weak", 2000, a.warmup, ktiming=False)
+            r["us_per_step"] = r["ms_per_step"] * 1e3
+            r["l2_policy"] = l2_policy_text(r["bytes_per_gpu"])
+            if not a.no_cpu:
+                key, sz, _ = WORKLOADS[wl]
+                r["cpu_baseline_reference"] = reference_functor_baseline(key, same_lattice=(sz[0], sz[1], ref_steps))
             also[wl] = r
         roofline["also"] = also
     if default_run and world > 1:

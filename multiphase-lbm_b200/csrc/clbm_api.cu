@@ -370,9 +370,8 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
         return CLBM_EINVAL;
     }
     if (p->collision != CLBM_COLLISION_BGK) {
-        const bool sc2_yuan = p->model == CLBM_MODEL_SC_D2Q9 && p->sc_force != CLBM_SC_FORCE_EXPGUO;
-        if (p->collision != CLBM_COLLISION_MRT || !(p->model == CLBM_MODEL_HCZ_D2Q9 || sc2_yuan)) {
-            set_error("collision operator %d: only BGK (0) everywhere and MRT (1) for HCZ D2Q9 and Yuan-CS Shan-Chen D2Q9 exist", p->collision);
+        if (p->collision != CLBM_COLLISION_MRT) {
+            set_error("collision operator %d: BGK (0) and MRT (1) exist", p->collision);
             return CLBM_EINVAL;
         }
         const double r[3] = {p->s_e, p->s_eps, p->s_q};
@@ -401,6 +400,8 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     if (!c) return CLBM_ENOMEM;
     memset((void *)&c->prm, 0, sizeof(c->prm));
     c->prm = *p;
+    // the MRT operator of the HCZ D3Q19 model lives in the staged collide kernel only
+    if (p->model == CLBM_MODEL_HCZ_D3Q19 && p->collision == CLBM_COLLISION_MRT) c->prm.fused = 0;
     c->device = dev;
     c->Q = is3d ? 19 : 9;
     c->sets = (p->model == CLBM_MODEL_HCZ_D2Q9 || p->model == CLBM_MODEL_HCZ_D3Q19) ? 2 : 1;

@@ -120,7 +120,11 @@ hcz3d_level2_kernel(const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g, Mode
     F.p[7][n.i] = o.P - o.rho / 3.0;
 }
 
-__global__ void __launch_bounds__(256, 2)
+// MRT = true: CLBM_COLLISION_MRT: out = in + F - M^-1 S M (in - eq + F/2) with the equilibria and forcing terms of collideBgk, the
+// forcing without its (1 - omega/2) factor, in the D3Q19 moment basis of mrt.cuh (S = omega I is collideBgk again; the reference has
+// no D3Q19 MRT operator: parity unpinned).  Runs on the staged path only (clbm_create clears `fused` for it).
+template <bool MRT>
+__global__ void __launch_bounds__(256, MRT ? 1 : 2)
 hcz3d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, const double *__restrict__ gin,
                      double *__restrict__ gout, const uint8_t *__restrict__ flag, FieldPtrs8 F, Geom g,
                      ModelParams mp, int x0, long long ncell)
@@ -150,6 +154,39 @@ hcz3d_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, 
     for (int k = 0; k < 19; ++k)
         if (k != 9 && flag[n.at<L19>(k)] == CELL_BB) wall |= 1u << k;
 
+    if constexpr (MRT) {
+        double Ff[19], Fg[19], vf[19], vg[19], wv[19];
+#pragma unroll
+        for (int k = 0; k < 19; ++k) {
+            const double ck_u = L19::cx(k) * u0 + L19::cy(k) * u1 + L19::cz(k) * u2;
+            const double poly = 3 * ck_u + 4.5 * ck_u * ck_u - usqr;
+            const double eqf = phi * L19::t(k) * (1 + poly);
+            const double eqg = L19::t(k) * (P + (rho / 3.0) * poly);
+            const double ex = L19::cx(k) - u0, ey = L19::cy(k) - u1, ez = L19::cz(k) - u2;
+            Fg[k] = (ex * forcex + ey * forcey + ez * forcez) * eqf * inv_phi + ((ex * -1 * E.x) + (ey * -1 * E.y) + (ez * -1 * E.z)) * (eqf * inv_phi - L19::t(k));
+            Ff[k] = ((ex * -1 * o.gpsiphi.x) + (ey * -1 * o.gpsiphi.y) + (ez * -1 * o.gpsiphi.z)) * 3. * eqf * inv_rho;
+            vf[k] = fin[(size_t)k * g.ncs + n.i] - eqf + 0.5 * Ff[k];
+            vg[k] = gin[(size_t)k * g.ncs + n.i] - eqg + 0.5 * Fg[k];
+        }
+        const MrtRates S = {omega, mp.s_e, mp.s_eps, mp.s_q, omega};
+        mrt19_relax(vf, S, wv);
+#pragma unroll
+        for (int k = 0; k < 19; ++k) {
+            const double pf = fin[(size_t)k * g.ncs + n.i] + Ff[k] - wv[k];
+            if (k == 9) fout[(size_t)9 * g.ncs + n.i] = pf;
+            else if (wall & (1u << k)) fout[(size_t)L19::opp(k) * g.ncs + n.i] = pf;
+            else fout[(size_t)k * g.ncs + n.at<L19>(k)] = pf;
+        }
+        mrt19_relax(vg, S, wv);
+#pragma unroll
+        for (int k = 0; k < 19; ++k) {
+            const double pg = gin[(size_t)k * g.ncs + n.i] + Fg[k] - wv[k];
+            if (k == 9) gout[(size_t)9 * g.ncs + n.i] = pg;
+            else if (wall & (1u << k)) gout[(size_t)L19::opp(k) * g.ncs + n.i] = pg;
+            else gout[(size_t)k * g.ncs + n.at<L19>(k)] = pg;
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 19; ++k) {
         const double fk = fin[(size_t)k * g.ncs + n.i];
@@ -302,9 +339,14 @@ int hcz3d_collide(clbm_ctx *c)
     if (c->prm.fused && hcz3d_march_eligible(c)) return hcz3d_march_collide(c);
     const long long n = (long long)c->geo.nx * c->geo.plane;
     LaunchScope ls(c, "hcz3d_collide_stream", true);
-    hcz3d_collide_kernel<<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
-                                                                c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
-                                                                fld8(c), c->geo, c->mp, 0, n);
+    if (c->prm.collision == CLBM_COLLISION_MRT)
+        hcz3d_collide_kernel<true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
+                                                                          c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
+                                                                          fld8(c), c->geo, c->mp, 0, n);
+    else
+        hcz3d_collide_kernel<false><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity],
+                                                                           c->pop[1][c->parity], c->pop[1][1 - c->parity], c->flag,
+                                                                           fld8(c), c->geo, c->mp, 0, n);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -48,4 +48,78 @@ CLBM_D void mrt9_relax(const double *v, const MrtRates &S, double *w)
     w[3] = ed - n8 - (px - py);
 }
 
+// ---- D3Q19: w = M^-1 S M v in the orthogonal basis of d'Humieres et al. (Phil. Trans. R. Soc. A 360, 2002) evaluated at the c_k of
+// the PF laplace3D.h ordering (oracle/clbm_oracle.c: mrt19_rows, same rows, same order):
+//   rho | e = 19 c^2 - 30 | eps = (21 c^4 - 53 c^2 + 24)/2 | j_a = c_a, q_a = (5 c^2 - 9) c_a | 3 p_xx, 3 pi_xx = (3 c^2 - 5) 3 p_xx |
+//   p_ww = c_y^2 - c_z^2, pi_ww | p_xy, p_yz, p_xz | m_x, m_y, m_z.
+// Rates by moment order, carried over from the D2Q9 assignment: conserved + stress moments omega, e: s_e, eps and pi: s_eps,
+// q and m: s_q.  The rows are compile-time constants: after unrolling only the non-zero products remain (about 230 of 361 per
+// direction of the transform), in the oracle's k = 0..18 / j = 0..18 summation order.  The reference has no D3Q19 MRT operator:
+// parity unpinned, pinned at S = omega I to the BGK kernels.
+struct Mrt19 {
+    CLBM_HD static constexpr double row(int j, int k)
+    {
+        const double cx = D3Q19::cx(k), cy = D3Q19::cy(k), cz = D3Q19::cz(k), c2 = cx * cx + cy * cy + cz * cz;
+        switch (j) {
+        case 0: return 1.0;
+        case 1: return 19.0 * c2 - 30.0;
+        case 2: return (21.0 * c2 * c2 - 53.0 * c2 + 24.0) / 2.0;
+        case 3: return cx;
+        case 4: return (5.0 * c2 - 9.0) * cx;
+        case 5: return cy;
+        case 6: return (5.0 * c2 - 9.0) * cy;
+        case 7: return cz;
+        case 8: return (5.0 * c2 - 9.0) * cz;
+        case 9: return 3.0 * cx * cx - c2;
+        case 10: return (3.0 * c2 - 5.0) * (3.0 * cx * cx - c2);
+        case 11: return cy * cy - cz * cz;
+        case 12: return (3.0 * c2 - 5.0) * (cy * cy - cz * cz);
+        case 13: return cx * cy;
+        case 14: return cy * cz;
+        case 15: return cx * cz;
+        case 16: return (cy * cy - cz * cz) * cx;
+        case 17: return (cz * cz - cx * cx) * cy;
+        default: return (cx * cx - cy * cy) * cz;
+        }
+    }
+    CLBM_HD static constexpr double norm2(int j)
+    {
+        double s = 0.0;
+        for (int k = 0; k < 19; ++k) s += row(j, k) * row(j, k);
+        return s;
+    }
+    // which of the five rates a moment relaxes with: 0 omega, 1 s_e, 2 s_eps, 3 s_q
+    CLBM_HD static constexpr int rate(int j)
+    {
+        constexpr int r[19] = {0, 1, 2, 0, 3, 0, 3, 0, 3, 0, 2, 0, 2, 0, 0, 0, 3, 3, 3};
+        return r[j];
+    }
+};
+
+CLBM_D void mrt19_relax(const double *v, const MrtRates &S, double *w)
+{
+    double m[19];
+#pragma unroll
+    for (int j = 0; j < 19; ++j) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 19; ++k) {
+            const double c = Mrt19::row(j, k);
+            if (c != 0.0) a += c * v[k];
+        }
+        const int r = Mrt19::rate(j);
+        m[j] = (r == 0 ? S.s_c : (r == 1 ? S.s_e : (r == 2 ? S.s_eps : S.s_q))) * a;
+    }
+#pragma unroll
+    for (int k = 0; k < 19; ++k) {
+        double a = 0.0;
+#pragma unroll
+        for (int j = 0; j < 19; ++j) {
+            const double c = Mrt19::row(j, k) / Mrt19::norm2(j);
+            if (c != 0.0) a += c * m[j];
+        }
+        w[k] = a;
+    }
+}
+
 }  // namespace clbm

@@ -160,7 +160,6 @@ CLBM_D void sc_collide(const ModelParams &mp, const double *f, ScForceSums &s, d
 template <class L>
 CLBM_D void sc_collide_mrt(const ModelParams &mp, const double *f, ScForceSums &s, double rho_raw, double psi_c, bool g1_pos, double *out)
 {
-    static_assert(L::Q == 9, "the MRT operator exists for D2Q9");
     const double rho = fmax(rho_raw, 1e-14);
     const double inv = fast_rcp(rho);
     double jx, jy, jz, F[3];
@@ -168,17 +167,19 @@ CLBM_D void sc_collide_mrt(const ModelParams &mp, const double *f, ScForceSums &
     sc_force<L>(mp, s, rho_raw, psi_c, g1_pos, F);
     const double ux = (jx + mp.tau * F[0]) * inv;
     const double uy = (jy + mp.tau * F[1]) * inv;
-    const double base = 1.0 - 1.5 * (ux * ux + uy * uy);
-    double v[9], w[9];
+    const double uz = (L::D == 3) ? (jz + mp.tau * F[2]) * inv : 0.0;
+    const double base = 1.0 - 1.5 * (ux * ux + uy * uy + uz * uz);
+    double v[L::Q], w[L::Q];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-        const double cu = cdot<L>(k, ux, uy, 0.0);
+    for (int k = 0; k < L::Q; ++k) {
+        const double cu = cdot<L>(k, ux, uy, uz);
         v[k] = f[k] - rho * L::t(k) * (base + 3.0 * cu + 4.5 * cu * cu);
     }
     const MrtRates S = {mp.omega, mp.s_e, mp.s_eps, mp.s_q, mp.omega};
-    mrt9_relax(v, S, w);
+    if constexpr (L::Q == 9) mrt9_relax(v, S, w);
+    else mrt19_relax(v, S, w);   // D3Q19: the basis of mrt.cuh / oracle mrt19_rows (no reference operator: parity unpinned)
 #pragma unroll
-    for (int k = 0; k < 9; ++k) out[k] = f[k] - w[k];
+    for (int k = 0; k < L::Q; ++k) out[k] = f[k] - w[k];
 }
 
 // output fields of one bulk node: pressure_node (laplace2D.h:308-315) and u_actual (:252-257)
@@ -250,6 +251,36 @@ CLBM_D void scrt_collide(const ModelParams &mp, const double *f, const ScForceSu
         out[L::opp(k)] = om1 * f[L::opp(k)] + (even - odd);
     }
     out[L::REST] = om1 * f[L::REST] + L::t(L::REST) * (A * base - uF3);
+}
+
+// CLBM_COLLISION_MRT for the Rayleigh-Taylor / Guo variant (D2Q9): out = f + F - M^-1 S M (f - eq + F/2) with
+//   F_k = t_k [3 (c_k - u) + 9 (c_k.u) c_k] . F,  F_rest = -3 t_rest u.F   (the terms above without their (1 - omega/2) factor;
+// oracle scrt_step).  S = omega I is scrt_collide.  The reference functor is BGK: parity unpinned.
+template <class L>
+CLBM_D void scrt_collide_mrt(const ModelParams &mp, const double *f, const ScForceSums &s, double rho_raw, double psi_c, double *out)
+{
+    static_assert(L::Q == 9, "the Rayleigh-Taylor variant is D2Q9");
+    const double rho = fmax(rho_raw, 1e-14);
+    const double inv = fast_rcp(rho);
+    double jx, jy, jz, F[3];
+    Mom<L>::first(f, jx, jy, jz);
+    scrt_force<L>(mp, s, rho_raw, psi_c, F);
+    const double ux = (jx + 0.5 * F[0]) * inv;
+    const double uy = (jy + 0.5 * F[1]) * inv;
+    const double base = 1.0 - 1.5 * (ux * ux + uy * uy);
+    const double uF = ux * F[0] + uy * F[1];
+    double Fk[9], v[9], w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const double cu = cdot<L>(k, ux, uy, 0.0);
+        const double cF = cdot<L>(k, F[0], F[1], 0.0);
+        Fk[k] = (k == L::REST) ? L::t(k) * (-3.0 * uF) : L::t(k) * (3.0 * (cF - uF) + 9.0 * cu * cF);
+        v[k] = f[k] - rho * L::t(k) * (base + 3.0 * cu + 4.5 * cu * cu) + 0.5 * Fk[k];
+    }
+    const MrtRates S = {mp.omega, mp.s_e, mp.s_eps, mp.s_q, mp.omega};
+    mrt9_relax(v, S, w);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k] = f[k] + Fk[k] - w[k];
 }
 
 // output fields of one bulk node: density, P_eos (:200-208, the Carnahan-Starling pressure with rt = b rho / 4),

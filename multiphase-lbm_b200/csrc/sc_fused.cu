@@ -164,7 +164,8 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
                 }
             }
             double out[L::Q];
-            if constexpr (GUO) scrt_collide<L>(mp, fc, s, Mom<L>::sum(fc), psc, out);
+            if constexpr (GUO && MRT) scrt_collide_mrt<L>(mp, fc, s, Mom<L>::sum(fc), psc, out);
+            else if constexpr (GUO) scrt_collide<L>(mp, fc, s, Mom<L>::sum(fc), psc, out);
             else if constexpr (MRT) sc_collide_mrt<L>(mp, fc, s, Mom<L>::sum(fc), psc, gpc, out);
             else sc_collide<L>(mp, fc, s, psc, gpc, out);
 
@@ -231,6 +232,7 @@ int sc_fused_tma_persist_range(clbm_ctx *c, int variant, int x_begin, int x_end,
 static int sc_tma_variant(const clbm_ctx *c)
 {
     // clbm_params.fused: 1 = default fused kernel, >1 = explicit tile variant (tuning / tests); env overrides
+    if (c->prm.collision == CLBM_COLLISION_MRT) return 0;   // the MRT operator lives in the register-pipelined and the staged kernels
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (c->env.sc_tile >= 0) variant = c->env.sc_tile;
     // D3Q19 default: the TMA-staged kernel with 8 x 64 tiles as two independent 4-row groups, early stage release (variant 29, = 24 with 32-bit store indices: best of
@@ -267,14 +269,18 @@ int sc_collide_range_fused(clbm_ctx *c, int x_begin, int x_end, int x2_begin, in
 int sc_fused_launch(clbm_ctx *c)
 {
     int rc;
+    const bool mrt = c->prm.collision == CLBM_COLLISION_MRT;
     int variant = c->prm.fused > 1 ? c->prm.fused : 0;
     if (c->env.sc_tile >= 0) variant = c->env.sc_tile;
-    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c)) variant = 29;
+    if (mrt) variant = 0;
+    if (variant == 0 && c->Q == 19 && sc_tma_eligible(c) && !mrt) variant = 29;
     if (variant >= 40 && sc_tma_eligible(c)) return sc_fused_tma_persist_range(c, variant, 0, c->geo.nx, 0, 0);
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;
+    if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO && mrt) return launch_fused<D2Q9, 128, 1, 3, true, true>(c);
     if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO) return launch_fused<D2Q9, 128, 1, 4, true>(c);   // D2Q9 only (clbm_create)
-    if (c->prm.collision == CLBM_COLLISION_MRT) return launch_fused<D2Q9, 128, 1, 3, false, true>(c);   // D2Q9 only (clbm_create)
+    if (mrt && c->Q == 9) return launch_fused<D2Q9, 128, 1, 3, false, true>(c);
+    if (mrt) return launch_fused<D3Q19, 4, 64, 1, false, true>(c);   // D3Q19 MRT: one CTA per SM, up to 255 registers for the 19 x 19 transforms
     if (c->Q == 9) {
         switch (variant) {
         case 1: rc = launch_fused<D2Q9, 256, 1, 2>(c); break;

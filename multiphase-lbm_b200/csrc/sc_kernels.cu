@@ -88,7 +88,8 @@ sc_collide_kernel(const double *__restrict__ fin, double *__restrict__ fout, con
     ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
     sc_gather_force<L, GUO>(s, n, flag, psi);
     const double pc = psi[n.i];
-    if constexpr (GUO) scrt_collide<L>(mp, f, s, Mom<L>::sum(f), pc, out);
+    if constexpr (GUO && MRT) scrt_collide_mrt<L>(mp, f, s, Mom<L>::sum(f), pc, out);
+    else if constexpr (GUO) scrt_collide<L>(mp, f, s, Mom<L>::sum(f), pc, out);
     else if constexpr (MRT) sc_collide_mrt<L>(mp, f, s, Mom<L>::sum(f), fabs(pc), !signbit(pc), out);
     else sc_collide<L>(mp, f, s, fabs(pc), !signbit(pc), out);
 
@@ -150,8 +151,11 @@ template <class L> static int sc_collide_range(clbm_ctx *c, int x0, int x1)
     const long long n = (long long)(x1 - x0) * c->geo.plane;
     if (n <= 0) return 0;
     LaunchScope ls(c, "sc_collide_stream", true);
-    if (L::D == 2 && c->prm.collision == CLBM_COLLISION_MRT)
-        sc_collide_kernel<D2Q9, false, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
+    if (L::D == 2 && c->prm.collision == CLBM_COLLISION_MRT && is_guo(c))
+        sc_collide_kernel<D2Q9, true, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
+                                                                                    c->fld[0], c->geo, c->mp, x0, n);
+    else if (c->prm.collision == CLBM_COLLISION_MRT)
+        sc_collide_kernel<L, false, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,
                                                                                      c->fld[0], c->geo, c->mp, x0, n);
     else if (L::D == 2 && is_guo(c))
         sc_collide_kernel<D2Q9, true><<<grid_for(n, 256), 256, 0, c->stream>>>(c->pop[0][c->parity], c->pop[0][1 - c->parity], c->flag,

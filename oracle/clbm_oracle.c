@@ -232,6 +232,8 @@ static void sc_psi_field(const clbm_params *p, const sc_eos *e, int D, const dou
 }
 
 static void mrt9_relax(const double v[9], const double S[9], double w[9]);   /* defined with the HCZ D2Q9 model below */
+static void mrt19_relax(const double v[19], const double S[19], double w[19]);
+static void mrt19_rates(const clbm_params *p, double S[19]);
 
 /* one Shan-Chen step: operator() of SC/apps/laplace2D.h:285-306 / contactAngle2D.h:333-355 */
 static void sc_step(const clbm_params *p, int D, const double *fin, double *fout, const uint8_t *flag)
@@ -278,6 +280,25 @@ static void sc_step(const clbm_params *p, int D, const double *fin, double *fout
                 int x2 = (iX + C9[k][0] + nx) % nx, y2 = (iY + C9[k][1] + ny) % ny;
                 size_t nb = (size_t)y2 + (size_t)ny * x2;
                 if (flag[nb] == BB) fout[(size_t)OPP9[k] * ne + i] = pop_out; else fout[(size_t)k * ne + nb] = pop_out;
+            }
+            continue;
+        }
+        if (D == 3 && p->collision == CLBM_COLLISION_MRT) {
+            /* D3Q19: the same construction in the moment basis of mrt19_rows() below -- out = f - M^-1 S M (f - eq), S = omega I is collideBgk.
+             * No reference implementation (the reference has neither a D3Q19 Shan-Chen functor nor a D3Q19 MRT basis): parity unpinned. */
+            double S[19], v[19], w[19];
+            mrt19_rates(p, S);
+            for (int k = 0; k < 19; ++k) {
+                const double ck_u = C19[k][0] * ueq[0] + C19[k][1] * ueq[1] + C19[k][2] * ueq[2];
+                v[k] = fin[(size_t)k * ne + i] - rho * T19[k] * (1. + 3. * ck_u + 4.5 * ck_u * ck_u - usqr);
+            }
+            mrt19_relax(v, S, w);
+            for (int k = 0; k < 19; ++k) {
+                const double pop_out = fin[(size_t)k * ne + i] - w[k];
+                if (k == 9) { fout[(size_t)k * ne + i] = pop_out; continue; }
+                int x2 = (iX + C19[k][0] + nx) % nx, y2 = (iY + C19[k][1] + ny) % ny, z2 = (iZ + C19[k][2] + nz) % nz;
+                size_t nb = (size_t)z2 + (size_t)nz * ((size_t)y2 + (size_t)ny * x2);
+                if (flag[nb] == BB) fout[(size_t)OPP19[k] * ne + i] = pop_out; else fout[(size_t)k * ne + nb] = pop_out;
             }
             continue;
         }
@@ -461,6 +482,30 @@ static void scrt_step(const clbm_params *p, const double *fin, double *fout, con
         scrt_force_fw(p, psi, flag, i, iX, iY, FW);
         scrt_ueq(u, FF, FW, rho, ueq);
         double usqreq = 1.5 * (ueq[0] * ueq[0] + ueq[1] * ueq[1]);
+        if (p->collision == CLBM_COLLISION_MRT) {
+            /* MRT with Guo's forcing: out = f + F - M^-1 S M (f - eq + F/2), F_k = t_k [3 (c_k - u) + 9 (c_k.u) c_k] . FF  (the term of
+             * :370-405 without its (1 - omega/2) factor; rest population as the reference writes it, with FW + FF); S = omega I is the
+             * collideBgk below.  Parity unpinned (the reference functor is BGK). */
+            const double S[9] = {omega, p->s_e, p->s_eps, omega, p->s_q, omega, p->s_q, omega, omega};
+            double Fk[9], v[9], w[9];
+            for (int k = 0; k < 9; ++k) {
+                double ck_ueq = C9[k][0] * ueq[0] + C9[k][1] * ueq[1];
+                double eq_f = rho * T9[k] * (1. + 3. * ck_ueq + 4.5 * ck_ueq * ck_ueq - usqreq);
+                double e_u_x = C9[k][0] - ueq[0], e_u_y = C9[k][1] - ueq[1];
+                if (k == 4) Fk[k] = T9[k] * ((-3. * ueq[0] * (FW[0] + FF[0])) + (-3. * ueq[1] * (FW[1] + FF[1])));
+                else Fk[k] = T9[k] * ((3 * e_u_x + 9 * ck_ueq * C9[k][0]) * FF[0] + (3 * e_u_y + 9 * ck_ueq * C9[k][1]) * FF[1]);
+                v[k] = fin[(size_t)k * ne + i] - eq_f + 0.5 * Fk[k];
+            }
+            mrt9_relax(v, S, w);
+            for (int k = 0; k < 9; ++k) {
+                const double pop_out = fin[(size_t)k * ne + i] + Fk[k] - w[k];
+                if (k == 4) { fout[(size_t)k * ne + i] = pop_out; continue; }
+                int x2 = (iX + C9[k][0] + nx) % nx, y2 = iY + C9[k][1];
+                size_t nb = (size_t)y2 + (size_t)ny * x2;
+                if (flag[nb] == BB) fout[(size_t)OPP9[k] * ne + i] = pop_out; else fout[(size_t)k * ne + nb] = pop_out;
+            }
+            continue;
+        }
         for (int k = 0; k < 4; ++k) {
             const int ko = OPP9[k];
             double F_x = FF[0], F_y = FF[1];
@@ -669,6 +714,72 @@ static void mrt9_relax(const double v[9], const double S[9], double w[9])
         w[k] = 0.0;
         for (int j = 0; j < 9; ++j) w[k] += M[j][k] / n2[j] * m[j];   /* back to population space (:2445-2449) */
     }
+}
+
+/* ---- D3Q19: the orthogonal moment basis of d'Humieres, Ginzburg, Krafczyk, Lallemand, Luo (Phil. Trans. R. Soc. A 360, 2002), rows
+ * evaluated at the c_k of the PF laplace3D.h ordering:
+ *   rho | e = 19 c^2 - 30 | eps = (21 c^4 - 53 c^2 + 24) / 2 | j_a = c_a, q_a = (5 c^2 - 9) c_a  (a = x, y, z) |
+ *   3 p_xx = 3 c_x^2 - c^2, 3 pi_xx = (3 c^2 - 5)(3 c_x^2 - c^2) | p_ww = c_y^2 - c_z^2, pi_ww = (3 c^2 - 5)(c_y^2 - c_z^2) |
+ *   p_xy, p_yz, p_xz | m_x = (c_y^2 - c_z^2) c_x, m_y = (c_z^2 - c_x^2) c_y, m_z = (c_x^2 - c_y^2) c_z.
+ * Rates: conserved moments and the stress moments (3 p_xx, p_ww, p_ab) relax with omega (they set the viscosity and keep the
+ * BGK hydrodynamics), e with s_e, eps and the fourth-order pi moments with s_eps, the third-order q and m moments with s_q --
+ * the D2Q9 assignment (omega, s_e, s_eps, omega, s_q, ...) of CooLBM_MRT_combustion.cpp:339 carried over by moment order.
+ * The reference has no D3Q19 MRT: PARITY UNPINNED, pinned only at S = omega I (= collideBgk). */
+static void mrt19_rows(double M[19][19], double norm2[19])
+{
+    for (int k = 0; k < 19; ++k) {
+        const double cx = C19[k][0], cy = C19[k][1], cz = C19[k][2], c2 = cx * cx + cy * cy + cz * cz;
+        M[0][k] = 1.0;
+        M[1][k] = 19.0 * c2 - 30.0;
+        M[2][k] = (21.0 * c2 * c2 - 53.0 * c2 + 24.0) / 2.0;
+        M[3][k] = cx;
+        M[4][k] = (5.0 * c2 - 9.0) * cx;
+        M[5][k] = cy;
+        M[6][k] = (5.0 * c2 - 9.0) * cy;
+        M[7][k] = cz;
+        M[8][k] = (5.0 * c2 - 9.0) * cz;
+        M[9][k] = 3.0 * cx * cx - c2;
+        M[10][k] = (3.0 * c2 - 5.0) * (3.0 * cx * cx - c2);
+        M[11][k] = cy * cy - cz * cz;
+        M[12][k] = (3.0 * c2 - 5.0) * (cy * cy - cz * cz);
+        M[13][k] = cx * cy;
+        M[14][k] = cy * cz;
+        M[15][k] = cx * cz;
+        M[16][k] = (cy * cy - cz * cz) * cx;
+        M[17][k] = (cz * cz - cx * cx) * cy;
+        M[18][k] = (cx * cx - cy * cy) * cz;
+    }
+    for (int j = 0; j < 19; ++j) {
+        norm2[j] = 0.0;
+        for (int k = 0; k < 19; ++k) norm2[j] += M[j][k] * M[j][k];
+    }
+}
+static void mrt19_rates(const clbm_params *p, double S[19])
+{
+    const double o = p->omega, e = p->s_e, eps = p->s_eps, q = p->s_q;
+    const double r[19] = {o, e, eps, o, q, o, q, o, q, o, eps, o, eps, o, o, o, q, q, q};
+    for (int j = 0; j < 19; ++j) S[j] = r[j];
+}
+static void mrt19_relax(const double v[19], const double S[19], double w[19])
+{
+    double M[19][19], n2[19], m[19];
+    mrt19_rows(M, n2);
+    for (int j = 0; j < 19; ++j) {
+        m[j] = 0.0;
+        for (int k = 0; k < 19; ++k) m[j] += M[j][k] * v[k];
+        m[j] = S[j] * m[j];
+    }
+    for (int k = 0; k < 19; ++k) {
+        w[k] = 0.0;
+        for (int j = 0; j < 19; ++j) w[k] += M[j][k] / n2[j] * m[j];
+    }
+}
+/* exported for the tests: the rows and their squared norms (orthogonality, M^-1 = M^T diag(1/norm2)) */
+void oracle_mrt19_rows(double *M361, double *norm2_19)
+{
+    double M[19][19];
+    mrt19_rows(M, norm2_19);
+    for (int j = 0; j < 19; ++j) for (int k = 0; k < 19; ++k) M361[j * 19 + k] = M[j][k];
 }
 
 /* velocity :316-337 and total_P :452-460 of one bulk node */
@@ -981,6 +1092,34 @@ static void hcz3_step(const clbm_params *p, const double *fin, double *fout, con
         double Ex = grad_psi_rho[0], Ey = grad_psi_rho[1], Ez = grad_psi_rho[2];
         double usqr = 1.5 * (u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
 
+        if (p->collision == CLBM_COLLISION_MRT) {
+            /* the equilibria and forcing terms of collideBgk below without the (1 - omega/2) factor, relaxed in the D3Q19 moment basis:
+             *   out = in + F - M^-1 S M (in - eq + F/2);  S = omega I gives collideBgk back.  Parity unpinned (see mrt19_rows). */
+            double S[19], Ff[19], Fg[19], vf[19], vg[19], wf[19], wg[19];
+            mrt19_rates(p, S);
+            for (int k = 0; k < 19; ++k) {
+                double ck_u = C19[k][0] * u[0] + C19[k][1] * u[1] + C19[k][2] * u[2];
+                double eqf = phi * T19[k] * (1 + 3 * ck_u + 4.5 * ck_u * ck_u - usqr);
+                double eqg = T19[k] * (P + (rho / 3.0) * (3 * ck_u + 4.5 * ck_u * ck_u - usqr));
+                double e_u_x = C19[k][0] - u[0], e_u_y = C19[k][1] - u[1], e_u_z = C19[k][2] - u[2];
+                Fg[k] = (e_u_x * forcex + e_u_y * forcey + e_u_z * forcez) * eqf / phi
+                      + ((e_u_x * -1 * Ex) + (e_u_y * -1 * Ey) + (e_u_z * -1 * Ez)) * (eqf / phi - T19[k]);
+                Ff[k] = ((e_u_x * -1 * grad_psi_phi[0]) + (e_u_y * -1 * grad_psi_phi[1]) + (e_u_z * -1 * grad_psi_phi[2])) * 3. * eqf / rho;
+                vf[k] = fin[(size_t)k * ne + i] - eqf + 0.5 * Ff[k];
+                vg[k] = gin[(size_t)k * ne + i] - eqg + 0.5 * Fg[k];
+            }
+            mrt19_relax(vf, S, wf);
+            mrt19_relax(vg, S, wg);
+            for (int k = 0; k < 19; ++k) {
+                double pf = fin[(size_t)k * ne + i] + Ff[k] - wf[k];
+                double pg = gin[(size_t)k * ne + i] + Fg[k] - wg[k];
+                if (k == 9) { fout[(size_t)k * ne + i] = pf; gout[(size_t)k * ne + i] = pg; continue; }
+                size_t nb = hcz3_nbidx(p, iX, iY, iZ, k);
+                if (flag[nb] == BB) { fout[(size_t)OPP19[k] * ne + i] = pf; gout[(size_t)OPP19[k] * ne + i] = pg; }
+                else { fout[(size_t)k * ne + nb] = pf; gout[(size_t)k * ne + nb] = pg; }
+            }
+            continue;
+        }
         for (int k = 0; k < 9; ++k) { /* collideBgk :562-624 */
             const int ko = OPP19[k];
             double ck_u = C19[k][0] * u[0] + C19[k][1] * u[1] + C19[k][2] * u[2];

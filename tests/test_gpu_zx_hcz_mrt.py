@@ -106,9 +106,9 @@ def test_mrt_slab_ring_matches_single_slab(fused):
     np.testing.assert_array_equal(pops, ref_pops)
 
 
-def test_mrt_is_rejected_where_it_does_not_exist():
-    for prm in (P.sc_params(P.MODEL_SC_D3Q19, 8, 8, 8).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=1.0),
-                P.hcz_params(P.MODEL_HCZ_D3Q19, 8, 8, 8).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=1.0),
+def test_mrt_rates_outside_the_stable_range_and_unknown_operators_are_rejected():
+    for prm in (P.hcz_params(P.MODEL_HCZ_D3Q19, 8, 8, 8).copy(collision=2, s_e=1.0, s_eps=1.0, s_q=1.0),
+                P.sc_params(P.MODEL_SC_D3Q19, 8, 8, 8).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=2.0),
                 P.hcz_mrt_params(16, 66, s_e=2.5), P.hcz_mrt_params(16, 66, s_q=0.0).copy(s_q=0.0)):
         with pytest.raises(pkg.clbm.ClbmError):
             pkg.clbm.Lattice(prm)

@@ -1,0 +1,111 @@
+"""GPU parity of the MRT collision operators of the D3Q19 models and of the Shan-Chen Rayleigh-Taylor (Guo) variant -- through the C ABI.
+
+No reference implementation exists (the reference's SC / HCZ functors are BGK, its only MRT basis is D2Q9): parity unpinned against the
+reference; pinned to the BGK kernels at S = omega I and to the oracle's matrix-form operator (oracle/clbm_oracle.c: mrt19_rows,
+d'Humieres et al. 2002) at free rates, 1e-10 after 1000 steps on the small lattices, and slab == single slab bit for bit."""
+import numpy as np
+import pytest
+
+import _cases
+from _cases import rel_linf
+from _oracle import OracleSim
+
+pytestmark = pytest.mark.gpu
+
+pkg = _cases.pkg
+P = pkg.params
+TOL = 1e-10
+
+SC3 = (lambda: P.sc_params(P.MODEL_SC_D3Q19, 28, 20, 24, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT), P.CASE_SC_DROPLET3D, (0.265, 0.038, 7.0, 5.0))
+SC3P = (lambda: P.sc_params(P.MODEL_SC_D3Q19, 20, 22, 24, omega=1.3, gravity=-2e-5, sc_force=P.SC_FORCE_LAPLACE), P.CASE_SC_DROPLET3D_PER, (0.265, 0.038, 6.0))
+HCZ3 = (lambda: P.hcz_params(P.MODEL_HCZ_D3Q19, 20, 16, 24, ulb=0.01, N=20, Re=6.0, kappa=5e-4, gravity=-1e-5), P.CASE_HCZ_LAPLACE3D, ())
+SCRT = (lambda: P.sc_rt_params(32, 130, omega=1.3), P.CASE_SC_RT2D, (1.2, 0.4))
+CASES = {"sc3_walls": SC3, "sc3_periodic": SC3P, "hcz3": HCZ3, "sc_rt": SCRT}
+
+
+def _mrt(p, **r):
+    om = p.omega
+    return p.copy(collision=P.COLLISION_MRT, s_e=r.get("s_e", om), s_eps=r.get("s_eps", om), s_q=r.get("s_q", om))
+
+
+def _gpu(prm, case, args, steps, fused):
+    with pkg.clbm.Lattice(prm.copy(fused=fused)) as lat:
+        lat.init_case(case, args)
+        lat.step(steps)
+        return lat.fields(), lat.in_pops(), lat.flags()
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_equal_rates_reproduce_the_bgk_kernels(name, fused):
+    mk, case, args = CASES[name]
+    steps = 100 if name == "sc_rt" else 300     # the Rayleigh-Taylor model amplifies one-ulp differences (test_gpu_zz_sc_rt2d.py)
+    _, pa, fl = _gpu(mk(), case, args, steps, fused)
+    _, pb, _ = _gpu(_mrt(mk()), case, args, steps, fused)
+    bulk = fl == 1
+    assert np.isfinite(pa[..., bulk]).all()
+    assert rel_linf(pb[..., bulk], pa[..., bulk]) < 1e-11
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_free_rates_match_the_oracle(name, fused):
+    mk, case, args = CASES[name]
+    prm = _mrt(mk(), s_e=1.15, s_eps=1.25, s_q=1.45)
+    steps = 200 if name == "sc_rt" else 1000
+    got, pops, flags = _gpu(prm, case, args, steps, fused)
+    ora = OracleSim(prm).init_case(case, args).step(steps)
+    np.testing.assert_array_equal(flags, ora.flag)
+    ref = ora.fields()
+    for k in ("s0", "s1", "ux", "uy", "uz"):
+        if np.max(np.abs(ref[k])) > 1e-14:
+            assert rel_linf(got[k], ref[k]) < TOL, k
+    bulk = flags == 1
+    assert rel_linf(pops[..., bulk], ora.in_pops()[..., bulk]) < TOL
+    # the operator is not a no-op: the BGK run differs
+    bgk = OracleSim(mk()).init_case(case, args).step(steps)
+    assert rel_linf(bgk.in_pops()[..., bulk], ora.in_pops()[..., bulk]) > 1e-8
+
+
+@pytest.mark.parametrize("name", ["sc3_walls", "hcz3"])
+def test_slab_ring_matches_single_slab(name):
+    slab = pkg.slab
+    mk, case, args = CASES[name]
+    prm = _mrt(mk(), s_e=1.15, s_eps=1.25, s_q=1.45)
+    ora = OracleSim(prm).init_case(case, args)
+    with pkg.clbm.Lattice(prm) as single:
+        single.upload(ora.lattice, ora.flag, 0)
+        single.step(40)
+        ref_pops = single.in_pops()
+    lats = []
+    for r in range(2):
+        lat = pkg.clbm.Lattice(slab.slab_params(prm, r, 2))
+        l, f = slab.slice_host_state(prm, ora.lattice, ora.flag, r, 2)
+        lat.upload(l, f, 0)
+        lats.append(lat)
+    ring = slab.LocalRing(lats)
+    ring.exchange_flags()
+    ring.step(40)
+    pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
+    for lat in lats:
+        lat.close()
+    np.testing.assert_array_equal(pops, ref_pops)
+
+
+def test_mrt19_speed_line(capsys):
+    """not a parity check: MLUPS of the D3Q19 MRT kernels next to BGK at 256^3 for DESIGN.md"""
+    out = []
+    for name, prm, case, args in (
+            ("SC D3Q19 bgk", P.sc_params(P.MODEL_SC_D3Q19, 256, 256, 256, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT), P.CASE_SC_DROPLET3D, (0.265, 0.038, 50.0, 5.0)),
+            ("SC D3Q19 mrt", _mrt(P.sc_params(P.MODEL_SC_D3Q19, 256, 256, 256, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT), s_e=1.1, s_eps=1.2, s_q=1.3), P.CASE_SC_DROPLET3D, (0.265, 0.038, 50.0, 5.0)),
+            ("HCZ D3Q19 bgk", P.hcz_params(P.MODEL_HCZ_D3Q19, 256, 256, 256, ulb=0.01, N=256, Re=6.0, kappa=5e-4, gravity=0.0), P.CASE_HCZ_LAPLACE3D, ()),
+            ("HCZ D3Q19 mrt", _mrt(P.hcz_params(P.MODEL_HCZ_D3Q19, 256, 256, 256, ulb=0.01, N=256, Re=6.0, kappa=5e-4, gravity=0.0), s_e=1.1, s_eps=1.2, s_q=1.3), P.CASE_HCZ_LAPLACE3D, ())):
+        with pkg.clbm.Lattice(prm) as lat:
+            lat.init_case(case, args)
+            lat.step(3)
+            lat.sync()
+            ms = lat.step_timed(10)
+            assert np.isfinite(lat.reduce(P.REDUCE_MASS))
+        out.append("%s %.0f MLUPS" % (name, prm.nelem * 10 / (ms * 1e3)))
+    with capsys.disabled():
+        print("\n256^3: " + ", ".join(out))
