@@ -83,8 +83,9 @@ def test_sc_mrt_slab_ring_matches_single_slab():
     np.testing.assert_array_equal(pops, ref_pops)
 
 
-def test_sc_mrt_is_rejected_where_it_does_not_exist():
+def test_sc_mrt_exists_for_every_shan_chen_variant_now():
+    """round 2 added the D3Q19 operator and the Rayleigh-Taylor / Guo one (tests/test_gpu_zzzz_mrt19.py)"""
     for prm in (P.sc_params(P.MODEL_SC_D3Q19, 8, 8, 8).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=1.0),
                 P.sc_rt_params(16, 66).copy(collision=P.COLLISION_MRT, s_e=1.0, s_eps=1.0, s_q=1.0)):
-        with pytest.raises(pkg.clbm.ClbmError):
-            pkg.clbm.Lattice(prm)
+        with pkg.clbm.Lattice(prm) as lat:
+            assert lat is not None

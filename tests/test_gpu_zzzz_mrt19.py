@@ -52,14 +52,21 @@ def test_equal_rates_reproduce_the_bgk_kernels(name, fused):
 def test_free_rates_match_the_oracle(name, fused):
     mk, case, args = CASES[name]
     prm = _mrt(mk(), s_e=1.15, s_eps=1.25, s_q=1.45)
-    steps = 200 if name == "sc_rt" else 1000
+    # 1000 steps, except: the Rayleigh-Taylor model amplifies one-ulp differences (200), and the wall-bounded droplet is at rest by
+    # then -- its velocity is the 4e-8 spurious current, whose 1e-10 is below the round-off of the momentum sums (400, the horizon of
+    # the BGK test of the same case in test_gpu_parity.py)
+    steps = {"sc_rt": 200, "sc3_walls": 400}.get(name, 1000)
     got, pops, flags = _gpu(prm, case, args, steps, fused)
     ora = OracleSim(prm).init_case(case, args).step(steps)
     np.testing.assert_array_equal(flags, ora.flag)
     ref = ora.fields()
-    for k in ("s0", "s1", "ux", "uy", "uz"):
-        if np.max(np.abs(ref[k])) > 1e-14:
-            assert rel_linf(got[k], ref[k]) < TOL, k
+    for k in ("s0", "s1"):
+        assert rel_linf(got[k], ref[k]) < TOL, k
+    # the velocity as a vector (a component that vanishes by symmetry has no scale of its own)
+    uref = np.stack([ref[k] for k in ("ux", "uy", "uz")])
+    ugot = np.stack([got[k] for k in ("ux", "uy", "uz")])
+    assert np.max(np.abs(uref)) > 1e-7
+    assert rel_linf(ugot, uref) < TOL
     bulk = flags == 1
     assert rel_linf(pops[..., bulk], ora.in_pops()[..., bulk]) < TOL
     # the operator is not a no-op: the BGK run differs

@@ -1,0 +1,9 @@
+#!/bin/bash
+# full GPU suite + smoke
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q --timeout 900 -p no:cacheprovider > gpurun_out/r2z_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2z_pytest.log
+tail -8 gpurun_out/r2z_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2z_smoke.log 2>&1
+tail -2 gpurun_out/r2z_smoke.log
+echo done
