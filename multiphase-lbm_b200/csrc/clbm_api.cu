@@ -71,6 +71,7 @@ int diag_interface_heights(clbm_ctx *c, double phi_mid, int *y_x0, int *y_xmid);
 int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int slab_step_for_profile(clbm_ctx *c);   // slab_comm.cu
+int sc_fused_multi_step(clbm_ctx *c, int nsteps, int *done);   // sc_fused.cu
 int sc_psi_all(clbm_ctx *c);
 int sc_psi_boundary(clbm_ctx *c);
 bool sc_range_supported(const clbm_ctx *c);
@@ -437,6 +438,8 @@ int clbm_create(const clbm_params *p, clbm_ctx **out)
     c->scratch = nullptr;
     c->scratch_bytes = 0;
     c->sc_queue = nullptr;
+    c->resident_progress = nullptr;
+    c->resident_epoch = 0;
     c->sc_queue_next = 0;
     c->sm_count = 0;
     c->stream_u = nullptr;
@@ -508,6 +511,7 @@ int clbm_destroy(clbm_ctx *c)
     if (c->stage) cudaFreeHost(c->stage);
     if (c->scratch) cudaFree(c->scratch);
     if (c->sc_queue) cudaFree(c->sc_queue);
+    if (c->resident_progress) cudaFree(c->resident_progress);
     for (int m = 0; m < 5; ++m) {
         if (c->mom[1][m]) cudaFree(c->mom[1][m]);      // mom[0] aliases fld[0..4]
         for (int s = 0; s < 2; ++s) if (c->mome[s][m]) cudaFree(c->mome[s][m]);
@@ -693,6 +697,12 @@ int clbm_step(clbm_ctx *c, int nsteps)
     if (!c || nsteps < 0) { set_error("bad argument to clbm_step"); return CLBM_EINVAL; }
     if (c->multi) { set_error("clbm_step on an x-slab: drive it with clbm_step_stage + halo exchange"); return CLBM_ESTATE; }
     CLBM_CUDA(cudaSetDevice(c->device));
+    if (c->prm.model == CLBM_MODEL_SC_D2Q9 && nsteps >= 2) {
+        // L2-resident D2Q9 lattices: all the steps in one cooperative launch (sc_fused.cu)
+        int done = 0;
+        if (int rc = sc_fused_multi_step(c, nsteps, &done)) return rc;
+        if (done) { c->steps_taken += nsteps; return CLBM_OK; }
+    }
     for (int s = 0; s < nsteps; ++s) {
         int rc = model_step(c);
         if (rc) return rc;

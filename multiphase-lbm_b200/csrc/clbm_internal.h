@@ -76,7 +76,7 @@ struct KernelTiming {
 
 // tuning knobs from the environment, read ONCE per context in clbm_create (-1 = not set): the launch paths never call getenv
 struct EnvKnobs {
-    int sc_xchunk, sc_tile, sc_cluster, tma_promo;
+    int sc_xchunk, sc_tile, sc_cluster, tma_promo, sc_multi;
     int hcz_tile, hcz_xchunk, hcz2d_tile, hcz2d_xchunk;
     int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
     int slab_graph;    // 0: never capture the slab step in a CUDA graph
@@ -95,6 +95,7 @@ inline void read_env_knobs(EnvKnobs &k)
     k.sc_xchunk = env_int("CLBM_SC_XCHUNK");
     k.sc_tile = env_int("CLBM_SC_TILE");
     k.sc_cluster = env_int("CLBM_SC_CLUSTER");
+    k.sc_multi = env_int("CLBM_SC_MULTI");
     k.tma_promo = env_int("CLBM_TMA_PROMO");
     k.hcz_tile = env_int("CLBM_HCZ_TILE");
     k.hcz_xchunk = env_int("CLBM_HCZ_XCHUNK");
@@ -201,6 +202,10 @@ struct clbm_ctx {
     int *sc_queue;
     int sc_queue_next;
     int sm_count;
+    // column-resident multi-step kernel of the L2-resident D2Q9 lattices (sc_fused.cu): steps completed per column, counting
+    // across launches
+    int *resident_progress;
+    int resident_epoch;
     // persistent device scratch of clbm_download_fields / clbm_download_force (grown on demand, freed in clbm_destroy)
     double *scratch;
     size_t scratch_bytes;

@@ -14,6 +14,8 @@
 //
 // Physics per cell: sc_cell.cuh (force, tau-shifted BGK; SC/apps/laplace2D.h:198-306,
 // SC/apps/contactAngle2D.h:248-355).
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "sc_cell.cuh"
@@ -37,11 +39,26 @@ template <class L> struct PopTable {
 // GUO = true: the Rayleigh-Taylor variant (SC/apps/RayleighTaylor2D.h; psi = 1 - exp(-rho), a wall neighbour
 // contributes the psi of the opposite neighbour, Guo forcing) -- a compile-time flag, the Yuan-CS code is unchanged.
 // MRT = true: CLBM_COLLISION_MRT for D2Q9 (sc_collide_mrt), likewise a compile-time flag.
-template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false, int PF = 2>
+//
+// MULTI = true: the whole grid is resident (cooperative launch) and runs `nsteps` time steps in ONE launch, a grid barrier and a
+// swap of the two population buffers between them.  For lattices that live in L2 (BASELINE configs[0]: 256 x 256, 4.7 MB per
+// buffer) a step is a few microseconds of latency and the kernel boundary is most of it: 8.2 us per step launch by launch.
+template <class L, int TY, int TZ, int MINB, bool GUO = false, bool MRT = false, int PF = 2, bool MULTI = false>
 __global__ void __launch_bounds__(TY *TZ, MINB)
-sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const double *__restrict__ psi_g, Geom g,
-                ModelParams mp, int xchunk)
+sc_fused_kernel(const PopTable<L> P0, const uint8_t *__restrict__ flag, const double *__restrict__ psi_g, Geom g,
+                ModelParams mp, int xchunk, int nsteps)
 {
+  for (int step = 0; step < (MULTI ? nsteps : 1); ++step) {
+    // population tables of this step: the buffers swap roles every step (the stores of the previous step are visible behind the
+    // grid barrier; the loads below are plain loads, never the non-coherent path, because `in` was written by this very kernel)
+    PopTable<L> P;
+    if (MULTI && (step & 1)) {
+#pragma unroll
+        for (int k = 0; k < L::Q; ++k) { P.in[k] = P0.out[k]; P.out[k] = const_cast<double *>(P0.in[k]); }
+    } else {
+#pragma unroll
+        for (int k = 0; k < L::Q; ++k) { P.in[k] = P0.in[k]; P.out[k] = P0.out[k]; }
+    }
     using C = FusedCfg<L, TY, TZ>;
     __shared__ double psi_s[4][C::SY][C::SZ];
 
@@ -86,7 +103,7 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
         if (inside) {
             const int i = xs * plane + yz;
 #pragma unroll
-            for (int k = 0; k < L::Q; ++k) fk[k] = P.in[k][i];
+            for (int k = 0; k < L::Q; ++k) fk[k] = MULTI ? __ldcg(P.in[k] + i) : P.in[k][i];
             double v = -1.0;
             ps = 0.0;
             gp = true;
@@ -110,7 +127,7 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
             if (flag[i] != CELL_BB) {
                 double fh[L::Q];
 #pragma unroll
-                for (int k = 0; k < L::Q; ++k) fh[k] = P.in[k][i];
+                for (int k = 0; k < L::Q; ++k) fh[k] = MULTI ? __ldcg(P.in[k] + i) : P.in[k][i];
                 bool gph;
                 if constexpr (GUO) v = scrt_psi(Mom<L>::sum(fh));
                 else v = sc_psi_g1(mp, Mom<L>::sum(fh), gph);
@@ -185,6 +202,8 @@ sc_fused_kernel(const PopTable<L> P, const uint8_t *__restrict__ flag, const dou
         psc = psn;
         gpc = gpn;
     }
+    if (MULTI && step + 1 < nsteps) cooperative_groups::this_grid().sync();
+  }
 }
 
 struct FusedChoice { int ty, tz; };
@@ -217,8 +236,68 @@ static int launch_fused(clbm_ctx *c)
         P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "sc_fused_collide_stream", true);
-    sc_fused_kernel<L, TY, TZ, MINB, GUO, MRT><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk);
+    sc_fused_kernel<L, TY, TZ, MINB, GUO, MRT><<<grid, TY * TZ, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk, 1);
     CLBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// nsteps steps of a small D2Q9 lattice in one cooperative launch (MULTI form of the kernel); *done = 0 when the lattice does not
+// qualify (the caller then steps launch by launch).  The parity advances by nsteps.
+template <int TY, int MINB>
+static int launch_fused_multi(clbm_ctx *c, int nsteps, int xchunk, int *done)
+{
+    const Geom &g = c->geo;
+    auto kern = sc_fused_kernel<D2Q9, TY, 1, MINB, false, false, 0, true>;
+    int per_sm = 0;
+    CLBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TY, 0));
+    int sms = 0;
+    CLBM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    dim3 grid(1, (g.ny + TY - 1) / TY, (g.nx + xchunk - 1) / xchunk);
+    if ((long long)grid.y * grid.z > (long long)per_sm * sms) return 0;   // not co-resident: no grid barrier
+    PopTable<D2Q9> P;
+    for (int k = 0; k < 9; ++k) {
+        P.in[k] = c->pop[0][c->parity] + (size_t)k * g.ncs;
+        P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+    }
+    const uint8_t *fl = c->flag;
+    const double *psi = c->fld[0];
+    Geom gg = g;
+    ModelParams mp = c->mp;
+    void *args[] = {&P, &fl, &psi, &gg, &mp, &xchunk, &nsteps};
+    LaunchScope ls(c, "sc_fused_multi_step", true);
+    CLBM_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(TY, 1, 1), args, 0, c->stream));
+    if (nsteps & 1) c->parity = 1 - c->parity;
+    *done = 1;
+    return 0;
+}
+
+int sc2d_resident_multi_step(clbm_ctx *c, int nsteps, int *done);
+
+// Yuan-CS BGK Shan-Chen D2Q9 on a single slab that fits in L2: several steps per launch (CLBM_SC_MULTI=0 turns it off)
+int sc_fused_multi_step(clbm_ctx *c, int nsteps, int *done)
+{
+    *done = 0;
+    const Geom &g = c->geo;
+    if (c->Q != 9 || c->multi || !c->prm.fused || c->prm.fused > 1 || c->env.sc_tile >= 0 || c->prm.collision != CLBM_COLLISION_BGK ||
+        c->mp.sc_force == CLBM_SC_FORCE_EXPGUO || c->profiling || c->ktiming || nsteps < 2)
+        return 0;
+    if (c->env.sc_multi == 0) return 0;
+    if ((size_t)g.ncs * 9 * sizeof(double) * 2 > 64u << 20) return 0;   // both buffers well inside the L2
+    if (c->env.sc_multi < 0 || c->env.sc_multi >= 4) {   // default: the column-resident kernel below, where the lattice qualifies
+        if (int rc = sc2d_resident_multi_step(c, nsteps, done)) return rc;
+        if (*done) return 0;
+    }
+    if (c->env.sc_multi == 1 || c->env.sc_multi == 3) {   // tile-height experiments of the plane-marching form
+        const int xchunk = c->env.sc_xchunk > 0 ? (c->env.sc_xchunk < g.nx ? c->env.sc_xchunk : g.nx) : 1;
+        if (c->env.sc_multi == 3) return launch_fused_multi<64, 8>(c, nsteps, xchunk, done);
+        return launch_fused_multi<128, 4>(c, nsteps, xchunk, done);
+    }
+    // too many columns to keep one CTA per column resident: the plane-marching form with the shortest x-chunks that still fit
+    // (512 x 256: 7.1 us per step at 2 columns per CTA against 14.3 launch by launch)
+    for (int xchunk = c->env.sc_xchunk > 0 ? c->env.sc_xchunk : 1; xchunk <= 8 && xchunk <= g.nx; xchunk *= 2) {
+        if (int rc = launch_fused_multi<256, 2>(c, nsteps, xchunk, done)) return rc;
+        if (*done || c->env.sc_xchunk > 0) return 0;
+    }
     return 0;
 }
 
@@ -308,6 +387,164 @@ int sc_fused_step(clbm_ctx *c)
     int rc = sc_fused_launch(c);
     if (rc) return rc;
     c->parity = 1 - c->parity;
+    return 0;
+}
+
+}  // namespace clbm
+
+// ---- L2-resident D2Q9 lattices: one CTA per lattice column, one thread per node, every step of a clbm_step(n) call in ONE
+// cooperative launch.  BASELINE configs[0] (256 x 256) is 4.7 MB per buffer: it never leaves L2, and a step is a chain of
+// latencies -- launch, three dependent load / psi rounds of the plane-marching kernel, the stores.  Here a thread issues the 27
+// loads of its node in the three columns x-1, x, x+1 at once (plain L2 loads: the data was written by this kernel one step
+// earlier), builds the three psi values, meets its column in shared memory, collides and pushes; a grid barrier ends the
+// step.  The node masks of the three columns are read once, before the first step.  Same per-cell functions, same summation
+// order as sc_fused_kernel: the populations are bit-identical (tools/small_lattice_multi.py).
+namespace clbm {
+
+//
+// P2P = true: no grid barrier.  Column x of step t + 1 depends on what the CTAs x-2 .. x+2 did in step t (its three input columns
+// are written by x-2 .. x+2, and the columns it overwrites are still being read by them), so every CTA publishes the number of
+// steps it has completed and waits for those four neighbours only: one flag round trip through L2 instead of an atomic on a
+// word that all CTAs hammer.  The flags keep counting across launches (`epoch` = steps completed before this launch).
+template <int NT, bool P2P>
+__global__ void __launch_bounds__(NT)
+sc2d_resident_kernel(const PopTable<D2Q9> P0, const uint8_t *__restrict__ flag, Geom g, ModelParams mp, int nsteps, int *progress, int epoch)
+{
+    using L = D2Q9;
+    extern __shared__ double psi_col[];          // [3][ny + 2]: psi (or -1 for a wall) of columns x-1, x, x+1 with the periodic rows
+    const int ny = g.ny, G = g.G, plane = (int)g.plane;
+    const int x = blockIdx.x, y = threadIdx.x;
+    const bool act = y < ny;
+    const int xm = g.wx(x - 1), xp = g.wx(x + 1);
+    const int im = (xm + G) * plane + y, ic = (x + G) * plane + y, ip = (xp + G) * plane + y;
+    uint8_t flm = CELL_BB, flc = CELL_BB, flp = CELL_BB;
+    if (act) { flm = flag[im]; flc = flag[ic]; flp = flag[ip]; }
+    double *pm = psi_col, *pc = psi_col + (ny + 2), *pp = psi_col + 2 * (ny + 2);
+    const int oym = g.wy(y - 1) - y, oyp = g.wy(y + 1) - y;
+    const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
+    auto put = [&](double *col, double v) {
+        col[y + 1] = v;
+        if (y == ny - 1) col[0] = v;        // periodic rows (walls are mask rows: a bulk node never reads across them)
+        if (y == 0) col[ny + 1] = v;
+    };
+
+    for (int step = 0; step < nsteps; ++step) {
+        const bool odd = step & 1;
+        double fc[9];
+        double psc = 0.0;
+        bool gpc = true;
+        if (act) {
+            double fm[9], fp[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double *src = odd ? P0.out[k] : P0.in[k];
+                fm[k] = __ldcg(src + im);
+                fc[k] = __ldcg(src + ic);
+                fp[k] = __ldcg(src + ip);
+            }
+            bool gpx;
+            put(pm, flm == CELL_BB ? -1.0 : sc_psi_g1(mp, Mom<L>::sum(fm), gpx));
+            put(pp, flp == CELL_BB ? -1.0 : sc_psi_g1(mp, Mom<L>::sum(fp), gpx));
+            if (flc != CELL_BB) psc = sc_psi_g1(mp, Mom<L>::sum(fc), gpc);
+            put(pc, flc == CELL_BB ? -1.0 : psc);
+        }
+        __syncthreads();
+        {
+            if (act && flc != CELL_BB) {
+                ScForceSums s = {{0., 0., 0.}, {0., 0., 0.}, 0u};
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    if (k == L::REST) continue;
+                    const double *col = L::cx(k) < 0 ? pm : (L::cx(k) > 0 ? pp : pc);
+                    const double v = col[y + 1 + L::cy(k)];
+                    sc_force_add<L>(s, k, v < 0.0, v);
+                }
+                double out[9];
+                sc_collide<L>(mp, fc, s, psc, gpc, out);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    double *dst = odd ? const_cast<double *>(P0.in[k]) : P0.out[k];
+                    double *dopp = odd ? const_cast<double *>(P0.in[L::opp(k)]) : P0.out[L::opp(k)];
+                    if (k == L::REST) { dst[ic] = out[k]; continue; }
+                    const int off = (L::cx(k) < 0 ? oxm : (L::cx(k) > 0 ? oxp : 0)) + (L::cy(k) < 0 ? oym : (L::cy(k) > 0 ? oyp : 0));
+                    if (s.wall & (1u << k)) dopp[ic] = out[k];   // half-way bounce-back
+                    else dst[ic + off] = out[k];
+                }
+            }
+        }
+        if (P2P) {
+            __syncthreads();                                    // every store of this CTA's step is issued
+            if (y == 0) {
+                __threadfence();
+                *(volatile int *)&progress[x] = epoch + step + 1;
+            }
+            if (step + 1 < nsteps) {
+                if (y < 4) {
+                    const int d = y < 2 ? y - 2 : y - 1;          // -2, -1, +1, +2
+                    int xn = x + d;
+                    xn = xn < 0 ? xn + g.nx : (xn >= g.nx ? xn - g.nx : xn);
+                    const volatile int *pf = &progress[xn];
+                    while (*pf - (epoch + step + 1) < 0) { }
+                    __threadfence();
+                }
+                __syncthreads();
+            }
+        } else if (step + 1 < nsteps) {
+            cooperative_groups::this_grid().sync();
+        }
+    }
+}
+
+template <int NT, bool P2P>
+static int launch_resident(clbm_ctx *c, int nsteps, int *done)
+{
+    const Geom &g = c->geo;
+    auto kern = sc2d_resident_kernel<NT, P2P>;
+    if (P2P && g.nx < 5) return 0;
+    if (P2P && !c->resident_progress) {
+        CLBM_CUDA(cudaMalloc(&c->resident_progress, (size_t)g.nx * sizeof(int)));
+        CLBM_CUDA(cudaMemsetAsync(c->resident_progress, 0, (size_t)g.nx * sizeof(int), c->stream));
+        c->resident_epoch = 0;
+    }
+    const size_t smem = 3 * (size_t)(g.ny + 2) * sizeof(double);
+    int per_sm = 0, sms = 0;
+    CLBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    CLBM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    if ((long long)g.nx > (long long)per_sm * sms) return 0;   // not co-resident: no grid barrier
+    PopTable<D2Q9> P;
+    for (int k = 0; k < 9; ++k) {
+        P.in[k] = c->pop[0][c->parity] + (size_t)k * g.ncs;
+        P.out[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+    }
+    const uint8_t *fl = c->flag;
+    Geom gg = g;
+    ModelParams mp = c->mp;
+    int *prog = c->resident_progress;
+    int epoch = c->resident_epoch;
+    void *args[] = {&P, &fl, &gg, &mp, &nsteps, &prog, &epoch};
+    LaunchScope ls(c, "sc2d_resident_multi_step", true);
+    CLBM_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(g.nx), dim3(NT), args, smem, c->stream));
+    if (P2P) c->resident_epoch += nsteps;
+    if (nsteps & 1) c->parity = 1 - c->parity;
+    *done = 1;
+    return 0;
+}
+
+int sc2d_resident_multi_step(clbm_ctx *c, int nsteps, int *done)
+{
+    const int ny = c->geo.ny;
+    if (c->env.sc_multi == 6) {   // neighbour flags instead of the grid barrier: measured SLOWER (8.5 against 4.5 us per step at 256 x 256:
+                                  // every step waits for the slowest of four neighbours, and a flag is seen one poll round trip late)
+        if (ny <= 128) return launch_resident<128, true>(c, nsteps, done);
+        if (ny <= 256) return launch_resident<256, true>(c, nsteps, done);
+        if (ny <= 512) return launch_resident<512, true>(c, nsteps, done);
+        if (ny <= 1024) return launch_resident<1024, true>(c, nsteps, done);
+        return 0;
+    }
+    if (ny <= 128) return launch_resident<128, false>(c, nsteps, done);
+    if (ny <= 256) return launch_resident<256, false>(c, nsteps, done);
+    if (ny <= 512) return launch_resident<512, false>(c, nsteps, done);
+    if (ny <= 1024) return launch_resident<1024, false>(c, nsteps, done);
     return 0;
 }
 
