@@ -122,10 +122,12 @@ typedef struct clbm_params {
     /* HCZ layered variant (LBM_twoLayeredPF2D members gx, Gx_const, PF/apps/twoLayeredFlow2D.h:127-128); gx is shared */
     double gx_const;
     /* collision operator (appended in ABI version 3; zero-initialised = BGK, the only operator the reference's SC / HCZ
-     * functors have).  CLBM_COLLISION_MRT, HCZ D2Q9 and Shan-Chen D2Q9: relaxation in the moment basis of CooLBM_MRT_combustion.cpp:313-323
+     * functors have).  CLBM_COLLISION_MRT, D2Q9 models: relaxation in the moment basis of CooLBM_MRT_combustion.cpp:313-323
      * (rho, e, eps, jx, qx, jy, qy, pxx, pxy), rates S = (omega, s_e, s_eps, omega, s_q, omega, s_q, omega, omega) for BOTH
-     * population sets, HCZ forcing term relaxed with (I - S/2) (the form of :2441, :2466); Shan-Chen keeps its tau-shifted
-     * equilibrium velocity (tau = 1/omega) and relaxes f - f_eq.  s_e = s_eps = s_q = omega is BGK. */
+     * population sets, HCZ / Guo forcing term relaxed with (I - S/2) (the form of :2441, :2466); Yuan-CS Shan-Chen keeps its
+     * tau-shifted equilibrium velocity (tau = 1/omega) and relaxes f - f_eq.  D3Q19 models (the reference has no D3Q19 basis):
+     * the orthogonal basis of d'Humieres et al. 2002 (rho, e, eps, j_a, q_a, 3p_xx, 3pi_xx, p_ww, pi_ww, p_xy, p_yz, p_xz, m_a),
+     * conserved and stress moments at omega, e at s_e, eps and pi at s_eps, q and m at s_q.  s_e = s_eps = s_q = omega is BGK. */
     double s_e, s_eps, s_q;
     int32_t collision;      /* CLBM_COLLISION_* */
     int32_t reserved0;

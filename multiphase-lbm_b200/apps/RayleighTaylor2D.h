@@ -20,7 +20,7 @@ inline void RayleighTaylor2D(const std::string &config_dir)
     const double Re = cfg.d("Re", 0), ulb = cfg.d("ulb", 0), max_t = cfg.d("max_t", 0), rhol = cfg.d("rhol", 0), rhog = cfg.d("rhog", 0),
                  rhow = cfg.d("rhow", 0), g = cfg.d("g", 0), a = cfg.d("a", 0), b = cfg.d("b", 0), gravity = cfg.d("gravity", 0);
     const int N = cfg.i("N", 0), out_freq = cfg.i("out_freq", 0), vtk_freq = cfg.i("vtk_freq", 0);
-    cfg.warn_unknown();
+    const bool has_collision = cfg.has("collision");
     const int nx = N, ny = 4 * N + 2;
 
     const auto lb = lb_parameters(ulb, N, Re);
@@ -33,6 +33,8 @@ inline void RayleighTaylor2D(const std::string &config_dir)
     clbm_params prm = default_params(CLBM_MODEL_SC_D2Q9, nx, ny, 1);
     prm.omega = lb.omega; prm.gravity = gravity; prm.rho_w = rhow; prm.a = a; prm.b = b; prm.G = g;
     prm.sc_force = CLBM_SC_FORCE_EXPGUO;
+    if (has_collision) apply_collision_keys(cfg, prm, lb.omega);   // optional keys of this library
+    cfg.warn_unknown();
     DeviceLattice lat(prm);
     lat.init_case(CLBM_CASE_SC_RT2D, {rhol, rhog});
 

@@ -58,7 +58,7 @@ struct Config {
 };
 
 // Optional keys of this library, absent from the reference's config files: `collision MRT` selects the moment-space
-// collision operator (include/clbm.h, CLBM_COLLISION_MRT: HCZ D2Q9 and Yuan-CS Shan-Chen D2Q9), `s_e`, `s_eps`, `s_q` are
+// collision operator (include/clbm.h, CLBM_COLLISION_MRT: every Shan-Chen and HCZ model), `s_e`, `s_eps`, `s_q` are
 // its free rates (default: omega, which is the BGK operator evaluated in moment space).
 inline void apply_collision_keys(Config &cfg, clbm_params &p, double omega)
 {
