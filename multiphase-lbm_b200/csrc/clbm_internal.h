@@ -76,7 +76,7 @@ struct KernelTiming {
 
 // tuning knobs from the environment, read ONCE per context in clbm_create (-1 = not set): the launch paths never call getenv
 struct EnvKnobs {
-    int sc_xchunk, sc_tile, sc_cluster, tma_promo, sc_multi;
+    int sc_xchunk, sc_tile, sc_cluster, tma_promo, sc_multi, sc2d_tma;
     int hcz_tile, hcz_xchunk, hcz2d_tile, hcz2d_xchunk;
     int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
     int slab_graph;    // 0: never capture the slab step in a CUDA graph
@@ -96,6 +96,7 @@ inline void read_env_knobs(EnvKnobs &k)
     k.sc_tile = env_int("CLBM_SC_TILE");
     k.sc_cluster = env_int("CLBM_SC_CLUSTER");
     k.sc_multi = env_int("CLBM_SC_MULTI");
+    k.sc2d_tma = env_int("CLBM_SC2D_TMA");   // 0: off, 1: force the default shape, 2..7: other tile / stage shapes
     k.tma_promo = env_int("CLBM_TMA_PROMO");
     k.hcz_tile = env_int("CLBM_HCZ_TILE");
     k.hcz_xchunk = env_int("CLBM_HCZ_XCHUNK");

@@ -36,6 +36,8 @@ using L19s = D3Q19;
 // the long-scoreboard stalls of this kernel sitting on exactly those address computations.)
 struct SweepOut {
     double *f, *g;
+    unsigned kn[19];   // k * ncs as unsigned 32-bit element offsets (hcz3d_sweep_shape_ok: 19 * ncs < 2^32): the 38 stores of a node
+                       // cost two or three integer instructions each instead of seven for k * ncs + i + offset in 64 bits
 };
 // phi, P_term, jx, jy, jz: node arrays m[5] of [ncs]; edge sums of phi in ephi[nx][eplane]; edge sums of the other four
 // moments INTERLEAVED in e4[nx][eplane][4] (one address, four consecutive loads / two 16-byte stores per slot)
@@ -331,7 +333,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         const int i = (x + G) * plane + yz;
         const int oxm = (xm - x) * plane, oxp = (xp - x) * plane;
         double *const fo = P.f, *const go = P.g;
-        const size_t ncs = (size_t)g.ncs;
+        const unsigned i0 = (unsigned)i, im = (unsigned)(i + oxm), ip = (unsigned)(i + oxp);
 #pragma unroll
         for (int k = 0; k < 19; ++k) {
             const double fk = sf[k * NT];
@@ -342,8 +344,8 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const double Gam = fma(-t, usqr, t);
                 pf = fma(Gam, opg, om1 * fk);
                 pg = fma(om1, gk, (omega * t) * fma(-rho3, usqr, Pt)) - fma(Gam, uD, t * uE);
-                fo[(size_t)k * ncs + i] = pf;
-                go[(size_t)k * ncs + i] = pg;
+                fo[i0 + P.kn[k]] = pf;
+                go[i0 + P.kn[k]] = pg;
             } else {
                 const bool axis = (L19s::cx(k) != 0) + (L19s::cy(k) != 0) + (L19s::cz(k) != 0) == 1;
                 const double cu = cdot<L19s>(k, u0, u1, u2);
@@ -354,10 +356,11 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const double dG = cdot<L19s>(k, G0, G1, G2) + opg;
                 pf = fma(Gam, dG, om1 * fk);
                 pg = fma(t, dE, fma(Gam, dD, fma(om1, gk, fma(axis ? Ba : Bd, poly, axis ? Aa : Ad))));
-                const int off = (L19s::cx(k) < 0 ? oxm : (L19s::cx(k) > 0 ? oxp : 0)) + (L19s::cy(k) < 0 ? oym : (L19s::cy(k) > 0 ? oyp : 0)) +
-                                (L19s::cz(k) < 0 ? ozm : (L19s::cz(k) > 0 ? ozp : 0));
-                fo[(size_t)k * ncs + (i + off)] = pf;
-                go[(size_t)k * ncs + (i + off)] = pg;
+                unsigned idx = (L19s::cx(k) < 0 ? im : (L19s::cx(k) > 0 ? ip : i0)) + P.kn[k];
+                if (L19s::cy(k)) idx += (unsigned)(L19s::cy(k) < 0 ? oym : oyp);
+                if (L19s::cz(k)) idx += (unsigned)(L19s::cz(k) < 0 ? ozm : ozp);
+                fo[idx] = pf;
+                go[idx] = pg;
             }
             sf[k * NT] = pf;             // the gather of the next iteration reads these
             sf[(19 + k) * NT] = pg;
@@ -529,7 +532,7 @@ bool hcz3d_sweep_shape_ok(const clbm_ctx *c)
 {
     const Geom &g = c->geo;
     return c->prm.model == CLBM_MODEL_HCZ_D3Q19 && g.ny % SW_TY == 0 && g.nz % SW_TZ == 0 && g.nx >= 4 && g.ny >= SW_TY && g.nz >= SW_TZ &&
-           g.ncs < (1LL << 31) && (long long)g.nx * make_edge_geom<SW_TY, SW_TZ>(g.ny, g.nz).eplane < (1LL << 31) && get_encode() != nullptr;
+           g.ncs < (1LL << 31) && 19ull * (unsigned long long)g.ncs < (1ull << 32) && (long long)g.nx * make_edge_geom<SW_TY, SW_TZ>(g.ny, g.nz).eplane < (1LL << 31) && get_encode() != nullptr;
 }
 
 // one sweep: populations pop[*][parity] -> pop[*][1 - parity], moments mom[src] (+ edges) -> mom[1 - src] (+ edges)
@@ -541,7 +544,8 @@ int hcz3d_sweep_launch(clbm_ctx *c, int src)
     const cuuint32_t box[4] = {(cuuint32_t)SW_TZ, (cuuint32_t)SW_TY, 1, 19};
     for (int s = 0; s < 2; ++s)
         if (int rc = cached_tmap(c, c->pop[s][c->parity], box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, &tm[s])) return rc;
-    const SweepOut P = {c->pop[0][1 - c->parity], c->pop[1][1 - c->parity]};
+    SweepOut P = {c->pop[0][1 - c->parity], c->pop[1][1 - c->parity], {0}};
+    for (int k = 0; k < 19; ++k) P.kn[k] = (unsigned)((unsigned long long)k * (unsigned long long)g.ncs);
     SweepMom Min, Mout;
     for (int m = 0; m < 5; ++m) {
         Min.m[m] = c->mom[src][m];

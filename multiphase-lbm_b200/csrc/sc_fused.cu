@@ -305,6 +305,8 @@ bool sc_tma_eligible(const clbm_ctx *c);            // sc_fused_tma.cu
 int sc_fused_tma_step(clbm_ctx *c, int variant);
 int sc_fused_tma_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_begin, int x2_end);
 int sc_fused_tma_persist_range(clbm_ctx *c, int variant, int x_begin, int x_end, int x2_begin, int x2_end);   // sc_fused_tma_persist.cu
+bool sc2d_tma_eligible(const clbm_ctx *c);          // sc2d_tma.cu
+int sc2d_tma_step(clbm_ctx *c, int variant);
 
 // one fused collide-stream sweep over the local planes; does NOT flip the parity
 // tile variant of the TMA kernel this context would run, 0 when it runs one of the register-pipelined kernels
@@ -356,6 +358,11 @@ int sc_fused_launch(clbm_ctx *c)
     if (variant >= 40 && sc_tma_eligible(c)) return sc_fused_tma_persist_range(c, variant, 0, c->geo.nx, 0, 0);
     if (variant >= 10 && sc_tma_eligible(c)) return sc_fused_tma_step(c, variant);
     if (variant >= 10) variant = 0;
+    // D2Q9 at HBM size: the TMA-staged column kernel (sc2d_tma.cu; bit-identical populations).  L2-resident lattices keep the
+    // register-pipelined kernel with its one-column chunks (and clbm_step(n >= 2) the multi-step launches below).
+    if (c->Q == 9 && variant == 0 && !mrt && c->env.sc2d_tma != 0 && sc2d_tma_eligible(c) &&
+        (c->env.sc2d_tma > 0 || (size_t)c->geo.ncs * 9 * sizeof(double) * 2 > (size_t)256 << 20))
+        return sc2d_tma_step(c, c->env.sc2d_tma > 1 ? c->env.sc2d_tma : 0);
     if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO && mrt) return launch_fused<D2Q9, 128, 1, 3, true, true>(c);
     if (c->mp.sc_force == CLBM_SC_FORCE_EXPGUO) return launch_fused<D2Q9, 128, 1, 4, true>(c);   // D2Q9 only (clbm_create)
     if (mrt && c->Q == 9) return launch_fused<D2Q9, 128, 1, 3, false, true>(c);
