@@ -108,15 +108,27 @@ sc2d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable2 P, con
     };
     double psn = 0.0;
     bool gpn = true;
+    // node masks of the column whose psi is built next, fetched ONE COLUMN AHEAD: the populations arrive through TMA, and a mask
+    // byte loaded at its point of use was the only global load left in the loop -- every column paid its latency (ncu at 8192^2:
+    // 27 % of the stall samples on the compare behind that load, 25 % at the barrier waiting for the warps stalled there)
+    uint8_t fl_n = CELL_BULK, flh_n = CELL_BULK;
+    auto fetch_flags = [&](int r) {
+        if (r > nplanes + 1) return;
+        const int xs = xs_of(r);
+        if (inside) fl_n = flag[xs * ny + y];
+        if (h_act) flh_n = flag[xs * ny + hy];
+    };
     // psi of column r (own rows + the two halo rows) from its staged box into the ring; keeps the own psi / G1 branch
     auto make_psi = [&](int r) {
         const uint32_t st = stage_a + (r % NS) * C::STAGE_BYTES;
         const int xs = xs_of(r);
+        const uint8_t fl_own = fl_n, fl_halo = flh_n;
+        fetch_flags(r + 1);
         if (inside) {
             double v = -1.0;
             psn = 0.0;
             gpn = true;
-            if (flag[xs * ny + y] != CELL_BB) {
+            if (fl_own != CELL_BB) {
                 double f[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) f[k] = lds_f64(st + (k * C::BY + own_box) * 8);
@@ -129,7 +141,7 @@ sc2d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable2 P, con
         if (h_act) {
             double v = -1.0;
             const int i = xs * ny + hy;
-            if (flag[i] != CELL_BB) {
+            if (fl_halo != CELL_BB) {
                 double f[9];
                 if (h_wrapped) {
 #pragma unroll
@@ -151,6 +163,7 @@ sc2d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable2 P, con
         for (int r = 0; r < NS; ++r)
             if (r <= nplanes + 1) issue(r);
     }
+    fetch_flags(0);
     wait_full(0);
     make_psi(0);
     release_and_refill(0);      // column xa-1 only feeds psi
