@@ -72,6 +72,7 @@ int hcz2d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, do
 int hcz3d_fields(clbm_ctx *c, double *s0, double *s1, double *s2, double *ux, double *uy, double *uz);
 int slab_step_for_profile(clbm_ctx *c);   // slab_comm.cu
 int sc_fused_multi_step(clbm_ctx *c, int nsteps, int *done);   // sc_fused.cu
+int hcz2d_fused_multi_step(clbm_ctx *c, int nsteps, int *done);   // hcz2d_fused.cu
 int sc_psi_all(clbm_ctx *c);
 int sc_psi_boundary(clbm_ctx *c);
 bool sc_range_supported(const clbm_ctx *c);
@@ -701,6 +702,12 @@ int clbm_step(clbm_ctx *c, int nsteps)
         // L2-resident D2Q9 lattices: all the steps in one cooperative launch (sc_fused.cu)
         int done = 0;
         if (int rc = sc_fused_multi_step(c, nsteps, &done)) return rc;
+        if (done) { c->steps_taken += nsteps; return CLBM_OK; }
+    }
+    if (c->prm.model == CLBM_MODEL_HCZ_D2Q9 && nsteps >= 2) {
+        // HCZ D2Q9, opt-in (CLBM_HCZ2D_MULTI=1; hcz2d_fused.cu, MULTI form)
+        int done = 0;
+        if (int rc = hcz2d_fused_multi_step(c, nsteps, &done)) return rc;
         if (done) { c->steps_taken += nsteps; return CLBM_OK; }
     }
     for (int s = 0; s < nsteps; ++s) {

@@ -77,7 +77,7 @@ struct KernelTiming {
 // tuning knobs from the environment, read ONCE per context in clbm_create (-1 = not set): the launch paths never call getenv
 struct EnvKnobs {
     int sc_xchunk, sc_tile, sc_cluster, tma_promo, sc_multi, sc2d_tma;
-    int hcz_tile, hcz_xchunk, hcz2d_tile, hcz2d_xchunk;
+    int hcz_tile, hcz_xchunk, hcz2d_tile, hcz2d_xchunk, hcz2d_multi;
     int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
     int slab_graph;    // 0: never capture the slab step in a CUDA graph
     int persist;       // 0: never use the persistent multi-step kernels of the L2-resident lattices
@@ -100,6 +100,7 @@ inline void read_env_knobs(EnvKnobs &k)
     k.tma_promo = env_int("CLBM_TMA_PROMO");
     k.hcz_tile = env_int("CLBM_HCZ_TILE");
     k.hcz_xchunk = env_int("CLBM_HCZ_XCHUNK");
+    k.hcz2d_multi = env_int("CLBM_HCZ2D_MULTI");   // 1: clbm_step(n >= 2) of an HCZ D2Q9 lattice as one cooperative launch (opt-in: measured slower at configs[1])
     k.hcz2d_tile = env_int("CLBM_HCZ2D_TILE");
     k.hcz2d_xchunk = env_int("CLBM_HCZ2D_XCHUNK");
     k.hcz3d_sweep = env_int("CLBM_HCZ3D_SWEEP");

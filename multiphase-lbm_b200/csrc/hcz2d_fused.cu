@@ -20,6 +20,8 @@
 // The per-node arithmetic is the staged kernel's with the divisions by constants turned into multiplications and the
 // quotients shared (4 FP64 divisions per node instead of 13; they were a third of the instruction stream): fused and
 // staged agree to O(1 ulp) per step, both within 1e-10 of the oracle.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 #include <type_traits>
 
@@ -82,10 +84,25 @@ CLBM_D void ring_grad(const double (*R)[NT], const uint8_t (*FL)[NT], unsigned w
 
 // MRT = true: CLBM_COLLISION_MRT (include/clbm.h, mrt.cuh) -- a compile-time variant of the collide phase only; the BGK
 // instantiations are unchanged.
-template <int NT, int MINB, bool MRT = false>
+//
+// MULTI = true: L2-resident lattices (BASELINE configs[1], 256 x 1026: 75.6 MB for both buffers), `nsteps` time steps in ONE
+// cooperative launch.  Launch by launch such a lattice is latency bound and half of a CTA's work is its prologue: a 4-column chunk
+// reads the populations of 8 columns for phi.  Here a step is two phases separated by grid barriers:
+//   A  every CTA sums phi of ITS OWN nodes into a scalar field (9 loads + 1 store per node, L2 to L2);
+//   B  the march above with phi of EVERY column taken from that field (the path the ghost columns of an x-slab take): the
+//      prologue is 4 doubles per thread instead of 36, the populations are read once, all of them issued at the top of the column
+//      iteration (registers) so that the ring phases and barriers of the iteration cover their L2 latency.
+// The buffers swap roles every step.  Same cell functions, same summation order; the compiler contracts a few products of the BGK
+// collide differently in this instantiation, so the populations agree with the launch-per-step form to O(1 ulp) per step (MRT:
+// bit for bit) -- tests/test_gpu_zq_hcz2d_multistep.py.
+// MEASURED (tools/hcz2d_multi.py, B200): 256 x 1026 31.3 us per step against 24.6 launch by launch, MRT 36.7 against 30.8,
+// 128 x 514 15.8 against 18.4.  A column iteration costs ~3.4 us whoever issues it (16 warps per SM, FP64 dependency chains: the
+// rate the kernel also runs at from HBM, 17.9 cycles per node and SM, puts configs[1] at 16 us per step at best), so the phi pass and
+// the two grid barriers cost more than the prologue they save.  The form is therefore OPT-IN (CLBM_HCZ2D_MULTI=1), not a default.
+template <int NT, int MINB, bool MRT = false, bool MULTI = false>
 __global__ void __launch_bounds__(NT, MINB)
 hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const double *__restrict__ phi_g, Geom g,
-                   ModelParams mp, int xchunk, int x_begin, int x_end)
+                   ModelParams mp, int xchunk, int x_begin, int x_end, int nsteps, double *phi_w)
 {
     constexpr int NS = HCZ2D_NS;
     __shared__ double r_phi[NS][NT], r_rho[NS][NT], r_pp[NS][NT], r_pr[NS][NT], r_lap[NS][NT];
@@ -94,6 +111,8 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
     // (no registers, no stall at the point of use: long_scoreboard was the second stall reason); a thread only ever reads
     // the slots it filled itself, so the copies need no barrier, only cp.async.wait_group
     __shared__ double st_g[2][9][NT];     // g only: the second read of f hits L1/L2 (it was read two columns earlier for phi)
+    extern __shared__ double st_f_raw[];          // MULTI reads f once: [9][NT] doubles of dynamic shared memory, staged at the top of
+    double (*st_f)[NT] = reinterpret_cast<double (*)[NT]>(st_f_raw);   // its own column's iteration (static + dynamic > 48 KB)
 
     const int tid = threadIdx.x;
     const int ny = g.ny, G = g.G;
@@ -106,6 +125,16 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
     // interior) -- a column is collided by exactly one launch, and a (node, direction) slot is written by exactly one column
     const int xa = x_begin + blockIdx.y * xchunk;
     const int xb = min(x_end, xa + xchunk);
+
+    // MULTI: the buffers swap roles every step, so the four population sets are addressed as base + k * ncs (four pointers in
+    // registers) instead of through the 36 pointers of the parameter block
+    const double *fin_b = P.fin[0], *gin_b = P.gin[0];
+    double *fout_b = P.fout[0], *gout_b = P.gout[0];
+    const size_t ncs_ = (size_t)g.ncs;
+    auto FIN = [&](int k) -> const double * { if constexpr (MULTI) return fin_b + k * ncs_; else return P.fin[k]; };
+    auto GIN = [&](int k) -> const double * { if constexpr (MULTI) return gin_b + k * ncs_; else return P.gin[k]; };
+    auto FOUT = [&](int k) -> double * { if constexpr (MULTI) return fout_b + k * ncs_; else return P.fout[k]; };
+    auto GOUT = [&](int k) -> double * { if constexpr (MULTI) return gout_b + k * ncs_; else return P.gout[k]; };
 
     auto slot_of = [](int xg) { return (xg + 2 * NS) % NS; };
     auto col_of = [&](int xg) { return (g.wx(xg) + G) * ny + yw; };   // storage index of (xg, this row)
@@ -124,12 +153,13 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
     auto load_f = [&](int xg, double *f) {
         const int i = col_of(xg);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) f[k] = P.fin[k][i];
+        for (int k = 0; k < 9; ++k) f[k] = MULTI ? __ldcg(FIN(k) + i) : FIN(k)[i];
     };
     auto fill_direct = [&](int xg) -> bool {   // true: the cell is a bounce_back node
         if (!has_phi) return false;
         const int i = col_of(xg);
         const uint8_t fl = flag[i];
+        if constexpr (MULTI) { put_phi(xg, __ldcg(phi_w + i), fl); return fl == CELL_BB; }
         if (is_ghost(xg)) { put_phi(xg, phi_g[i], fl); return fl == CELL_BB; }
         double f[9];
         load_f(xg, f);
@@ -161,16 +191,44 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         r_lap[s0][tid] = 6.0 * sum;
     };
 
+  for (int step = 0; step < (MULTI ? nsteps : 1); ++step) {
+    if constexpr (MULTI) {
+        if (step & 1) {
+            fin_b = P.fout[0]; gin_b = P.gout[0];
+            fout_b = const_cast<double *>(P.fin[0]); gout_b = const_cast<double *>(P.gin[0]);
+        } else {
+            fin_b = P.fin[0]; gin_b = P.gin[0];
+            fout_b = P.fout[0]; gout_b = P.gout[0];
+        }
+        // ---- phase A: phi of the own nodes of this CTA's columns into the scalar field ----
+        if (own) {
+            for (int x0 = xa; x0 < xb; x0 += 2) {      // two columns at a time: 18 loads in flight (four spilled)
+                double fa[2][9];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (x0 + j < xb) load_f(x0 + j, fa[j]);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (x0 + j < xb) __stcg(phi_w + col_of(x0 + j), Mom<L9f>::sum(fa[j]));
+            }
+        }
+        cooperative_groups::this_grid().sync();
+    }
     // ---- prologue: phi of columns xa-2 .. xa+1, lap of columns xa-1, xa ----
     int pw = fill_direct(xa - 2);
     pw |= (int)fill_direct(xa - 1);
     pw |= (int)fill_direct(xa);
     pw |= (int)fill_direct(xa + 1);
     double fn[9];
+    double phin = 0.0;    // MULTI: phi of the column after next, fetched one iteration ahead like fn
     uint8_t fln = CELL_BULK;
     bool ghost_n = is_ghost(xa + 2);
-    if (has_phi && !ghost_n) { load_f(xa + 2, fn); fln = flag[col_of(xa + 2)]; }
-    if (__syncthreads_or(pw)) wmask = 0xffu;   // conservative for the four prologue columns; the ring corrects itself as it advances
+    if constexpr (MULTI) {
+        if (has_phi) { const int i = col_of(xa + 2); phin = __ldcg(phi_w + i); fln = flag[i]; }
+    } else {
+        if (has_phi && !ghost_n) { load_f(xa + 2, fn); fln = flag[col_of(xa + 2)]; }
+    }
+    wmask = __syncthreads_or(pw) ? 0xffu : 0u;   // conservative for the four prologue columns; the ring corrects itself as it advances
     make_lap(xa - 1);
     make_lap(xa);
 
@@ -181,7 +239,7 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
             const int i = (xg + G) * ny + yy;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&st_g[xg & 1][k][tid])), "l"(P.gin[k] + i) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&st_g[xg & 1][k][tid])), "l"(GIN(k) + i) : "memory");
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -189,18 +247,32 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
     stage_pops(xa);
 
     for (int x = xa; x < xb; ++x) {
+        if constexpr (MULTI) {      // f of this column rides in the group of the next column's g; the collide waits for both
+            if (own) {
+                const int i = (x + G) * ny + yy;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(&st_f[k][tid])), "l"(FIN(k) + i) : "memory");
+                }
+            }
+        }
         if (x + 1 < xb) stage_pops(x + 1);
         else asm volatile("cp.async.commit_group;" ::: "memory");   // keep one group per iteration so wait_group 1 means "column x is here"
         // 1. column x+2: phi from the prefetched populations (or the exchanged ghost field)
         int anyw = 0;
         if (has_phi) {
-            if (ghost_n) { const int i = col_of(x + 2); fln = flag[i]; put_phi(x + 2, phi_g[i], fln); }
+            if constexpr (MULTI) put_phi(x + 2, phin, fln);
+            else if (ghost_n) { const int i = col_of(x + 2); fln = flag[i]; put_phi(x + 2, phi_g[i], fln); }
             else put_phi(x + 2, Mom<L9f>::sum(fn), fln);
             anyw = fln == CELL_BB;
         }
         // prefetch column x+3 for the next iteration
         ghost_n = is_ghost(x + 3);
-        if (x + 1 < xb && has_phi && !ghost_n) { load_f(x + 3, fn); fln = flag[col_of(x + 3)]; }
+        if constexpr (MULTI) {
+            if (x + 1 < xb && has_phi) { const int i = col_of(x + 3); phin = __ldcg(phi_w + i); fln = flag[i]; }
+        } else {
+            if (x + 1 < xb && has_phi && !ghost_n) { load_f(x + 3, fn); fln = flag[col_of(x + 3)]; }
+        }
         {
             const unsigned bit = 1u << ((x + 2) & 7);
             wmask = __syncthreads_or(anyw) ? (wmask | bit) : (wmask & ~bit);
@@ -216,9 +288,15 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         constexpr bool W = decltype(wtag)::value;
         const int i = (x + G) * ny + yy;
         double f[9], gg[9];
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        if constexpr (MULTI) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { gg[k] = st_g[x & 1][k][tid]; f[k] = P.fin[k][i]; }
+            for (int k = 0; k < 9; ++k) { gg[k] = st_g[x & 1][k][tid]; f[k] = st_f[k][tid]; }
+        } else {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { gg[k] = st_g[x & 1][k][tid]; f[k] = FIN(k)[i]; }
+        }
 
         unsigned wall = 0;
         if constexpr (W) {
@@ -271,12 +349,12 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         const double Ad = (omega * (1. / 36.)) * Pp, Bd = (omega * (1. / 36.)) * rho3;
         auto push = [&](int k, double pf, double pg) {
             if (W && (wall & (1u << k))) {
-                P.fout[L9f::opp(k)][i] = pf;
-                P.gout[L9f::opp(k)][i] = pg;
+                FOUT(L9f::opp(k))[i] = pf;
+                GOUT(L9f::opp(k))[i] = pg;
             } else {
                 const int off = (L9f::cx(k) < 0 ? oxm : (L9f::cx(k) > 0 ? oxp : 0)) + (L9f::cy(k) < 0 ? oym : (L9f::cy(k) > 0 ? oyp : 0));
-                P.fout[k][i + off] = pf;
-                P.gout[k][i + off] = pg;
+                FOUT(k)[i + off] = pf;
+                GOUT(k)[i + off] = pg;
             }
         };
         if constexpr (MRT) {
@@ -317,8 +395,8 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
                 vv[k] = gg[k] - eqg + 0.5 * Fg;
             }
             mrt9_relax(vv, S, wv);
-            P.fout[4][i] = of[4];
-            P.gout[4][i] = sv[4] - wv[4];
+            FOUT(4)[i] = of[4];
+            GOUT(4)[i] = sv[4] - wv[4];
 #pragma unroll
             for (int k = 0; k < 9; ++k)
                 if (k != 4) push(k, of[k], sv[k] - wv[k]);
@@ -338,8 +416,8 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
             }
             const double fg0 = hw * (-uF0 * Gam - uE * (Gam - t));     // (u.(-E)) as the reference writes it
             const double ff0 = hw3 * uG * Gam;
-            P.fout[4][i] = om1 * f[4] + op * Gam + ff0;
-            P.gout[4][i] = om1 * gg[4] + omega * eqg0 + fg0;
+            FOUT(4)[i] = om1 * f[4] + op * Gam + ff0;
+            GOUT(4)[i] = om1 * gg[4] + omega * eqg0 + fg0;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -365,6 +443,8 @@ hcz2d_fused_kernel(const Hcz2dTables P, const uint8_t *__restrict__ flag, const 
         };
         if (walls_near(x)) collide(std::true_type{}); else collide(std::false_type{});
     }
+    if (MULTI && step + 1 < nsteps) cooperative_groups::this_grid().sync();
+  }
 }
 
 template <int NT, int MINB, bool MRT = false>
@@ -392,12 +472,63 @@ static int launch_hcz2d_fused(clbm_ctx *c, int x_begin, int x_end)
         P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
     }
     LaunchScope ls(c, "hcz2d_fused_collide_stream", ncol * 2 >= g.nx);   // the boundary-column launches of the overlap protocol are not the dominant kernel
-    hcz2d_fused_kernel<NT, MINB, MRT><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk, x_begin, x_end);
+    hcz2d_fused_kernel<NT, MINB, MRT><<<grid, NT, 0, c->stream>>>(P, c->flag, c->fld[0], g, c->mp, xchunk, x_begin, x_end, 1, nullptr);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }
 
 bool hcz2d_fused_eligible(const clbm_ctx *c) { return c->geo.ny >= 4 && c->geo.ncs < (1LL << 31); }
+
+// nsteps steps in one cooperative launch (MULTI form); *done stays 0 when the lattice does not qualify: the grid must be
+// co-resident (grid barrier) and both population buffers should live in L2 -- at HBM size the launch-per-step kernel with its
+// 48-column chunks is the faster one (no phi pass, no barriers)
+template <int NT, int MINB, bool MRT>
+static int launch_hcz2d_multi(clbm_ctx *c, int nsteps, int *done)
+{
+    const Geom &g = c->geo;
+    auto kern = hcz2d_fused_kernel<NT, MINB, MRT, true>;
+    int per_sm = 0, sms = 0;
+    const size_t smem = 9 * (size_t)NT * sizeof(double);
+    CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CLBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    CLBM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    const int segs = (g.ny + (NT - 4) - 1) / (NT - 4);
+    const int max_chunks = per_sm * sms / segs;
+    if (max_chunks < 1) return 0;
+    int xchunk = (g.nx + max_chunks - 1) / max_chunks;
+    if (xchunk < 2) xchunk = 2;
+    if (c->env.hcz2d_xchunk > 0 && c->env.hcz2d_xchunk >= xchunk) xchunk = c->env.hcz2d_xchunk < g.nx ? c->env.hcz2d_xchunk : g.nx;
+    dim3 grid(segs, (g.nx + xchunk - 1) / xchunk);
+    Hcz2dTables P;
+    for (int k = 0; k < 9; ++k) {
+        P.fin[k] = c->pop[0][c->parity] + (size_t)k * g.ncs;
+        P.gin[k] = c->pop[1][c->parity] + (size_t)k * g.ncs;
+        P.fout[k] = c->pop[0][1 - c->parity] + (size_t)k * g.ncs;
+        P.gout[k] = c->pop[1][1 - c->parity] + (size_t)k * g.ncs;
+    }
+    const uint8_t *fl = c->flag;
+    const double *phi_g = c->fld[0];
+    double *phi_w = c->fld[0];
+    Geom gg = g;
+    ModelParams mp = c->mp;
+    int x_begin = 0, x_end = g.nx;
+    void *args[] = {&P, &fl, &phi_g, &gg, &mp, &xchunk, &x_begin, &x_end, &nsteps, &phi_w};
+    LaunchScope ls(c, "hcz2d_fused_multi_step", true);
+    CLBM_CUDA(cudaLaunchCooperativeKernel((const void *)kern, grid, dim3(NT), args, smem, c->stream));
+    if (nsteps & 1) c->parity = 1 - c->parity;
+    *done = 1;
+    return 0;
+}
+
+// HCZ D2Q9 on a single slab: all the steps of a clbm_step(n >= 2) call in one launch, only with CLBM_HCZ2D_MULTI=1 (measured slower
+// than the launch-per-step path at BASELINE configs[1], see the kernel's header)
+int hcz2d_fused_multi_step(clbm_ctx *c, int nsteps, int *done)
+{
+    *done = 0;
+    if (nsteps < 2 || c->multi || c->prm.fused != 1 || c->env.hcz2d_tile >= 0 || !hcz2d_fused_eligible(c) || c->env.hcz2d_multi != 1) return 0;
+    if (c->prm.collision == CLBM_COLLISION_MRT) return launch_hcz2d_multi<128, 3, true>(c, nsteps, done);
+    return launch_hcz2d_multi<128, 4, false>(c, nsteps, done);
+}
 
 // collide + push of the columns [x_begin, x_end) of this slab (the whole slab, or a range of the overlap protocol)
 int hcz2d_fused_range(clbm_ctx *c, int x_begin, int x_end)
