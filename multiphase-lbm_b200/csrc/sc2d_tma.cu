@@ -42,7 +42,12 @@ struct Tma2Cfg {
     static constexpr int RING_BYTES = 4 * (T + 2) * 8;
     static constexpr int SMEM = NS * STAGE_BYTES + RING_BYTES + 128;   // NS mbarriers + NS counters behind the ring
     static_assert(T % 32 == 0 && NS >= 2 && NS <= 8, "whole warps, 2 to 8 stages");
-    static_assert(BY / 2 <= 256, "a TMA box dimension holds at most 256 elements (the rows are described as pairs, see cached_tmap_2d)");
+    // a TMA box dimension holds at most 256 elements: a column box of up to 256 rows is described as it is -- (BY rows, 1 column, 9
+    // directions), innermost extent BY * 8 bytes -- and a taller one with its rows as PAIRS (2, BY / 2, 1, 9).  The pair form makes
+    // the innermost extent 16 bytes, and the TMA unit fetches a box row by row of that extent: measured on the 128-row default,
+    // 17 % of the stall samples sat on the mbarrier wait for a box issued two columns (6 us) earlier (cached_tmap_2d).
+    static constexpr bool PAIRS = BY > 256;
+    static_assert(BY / 2 <= 256, "a TMA box dimension holds at most 256 elements");
 };
 
 // GUO = true: the Rayleigh-Taylor variant (psi = 1 - exp(-rho), a wall neighbour contributes the psi of the opposite neighbour, Guo
@@ -90,7 +95,8 @@ sc2d_tma_kernel(const __grid_constant__ CUtensorMap tmap, const OutTable2 P, con
     auto xs_of = [&](int r) { return g.wx(xa - 1 + r) + G; };
     auto issue = [&](int r) {
         mbar_expect_tx(&mbar[r % NS], (uint32_t)(C::BOX * 8));
-        tma_load_4d(stage_a + (r % NS) * C::STAGE_BYTES, &tmap, &mbar[r % NS], 0, (y0 - 2) / 2, xs_of(r), 0);   // y0 - 2 is even, also for tile 0 (-2 / 2 = -1)
+        if constexpr (C::PAIRS) tma_load_4d(stage_a + (r % NS) * C::STAGE_BYTES, &tmap, &mbar[r % NS], 0, (y0 - 2) / 2, xs_of(r), 0);   // y0 - 2 is even, also for tile 0 (-2 / 2 = -1)
+        else tma_load_3d(stage_a + (r % NS) * C::STAGE_BYTES, &tmap, &mbar[r % NS], y0 - 2, xs_of(r), 0);
     };
     auto wait_full = [&](int r) { mbar_wait(&mbar[r % NS], (uint32_t)((r / NS) & 1)); };
     auto release_and_refill = [&](int r) {
@@ -234,29 +240,39 @@ bool sc2d_tma_eligible(const clbm_ctx *c)
 // tensor map of the [9][nx + 2G][ny] population array, its rows described as ny / 2 PAIRS of doubles -- dims (2, ny / 2, nx + 2G, 9) --
 // because a box dimension is limited to 256 elements and a column box has T + 4 rows; the bytes land in shared memory in the
 // same order.  Cached per buffer like the 3-D lattice's maps (promo = -2 marks this form).
-static int cached_tmap_2d(clbm_ctx *c, const void *base, int box_rows, CUtensorMap *out)
+static int cached_tmap_2d(clbm_ctx *c, const void *base, int box_rows, bool pairs, CUtensorMap *out)
 {
-    const unsigned bx[4] = {2u, (unsigned)box_rows / 2u, 1u, 9u};
+    const unsigned bx[4] = {pairs ? 2u : (unsigned)box_rows, pairs ? (unsigned)box_rows / 2u : 1u, pairs ? 1u : 9u, pairs ? 9u : 0u};
+    const int tag = pairs ? -2 : -3;
     for (const TmapEntry &e : c->tmaps)
-        if (e.base == base && e.promo == -2 && e.box[0] == bx[0] && e.box[1] == bx[1] && e.box[2] == bx[2] && e.box[3] == bx[3]) {
+        if (e.base == base && e.promo == tag && e.box[0] == bx[0] && e.box[1] == bx[1] && e.box[2] == bx[2] && e.box[3] == bx[3]) {
             memcpy(out, e.map, sizeof(CUtensorMap));
             return 0;
         }
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return CLBM_ECUDA; }
     const Geom &g = c->geo;
-    const cuuint64_t dims[4] = {2, (cuuint64_t)g.ny / 2, (cuuint64_t)(g.nx + 2 * g.G), 9};
-    const cuuint64_t strides[3] = {16, (cuuint64_t)g.ny * 8, (cuuint64_t)g.ncs * 8};
-    const cuuint32_t box[4] = {2, (cuuint32_t)box_rows / 2, 1, 9};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r;
+    if (pairs) {
+        const cuuint64_t dims[4] = {2, (cuuint64_t)g.ny / 2, (cuuint64_t)(g.nx + 2 * g.G), 9};
+        const cuuint64_t strides[3] = {16, (cuuint64_t)g.ny * 8, (cuuint64_t)g.ncs * 8};
+        const cuuint32_t box[4] = {2, (cuuint32_t)box_rows / 2, 1, 9};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.ny, (cuuint64_t)(g.nx + 2 * g.G), 9};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.ny * 8, (cuuint64_t)g.ncs * 8};
+        const cuuint32_t box[3] = {(cuuint32_t)box_rows, 1, 9};
+        r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (2-D lattice) failed (%d)", (int)r); return CLBM_ECUDA; }
     if (c->tmaps.size() >= 64) c->tmaps.clear();
     TmapEntry e;
     e.base = base;
     for (int i = 0; i < 4; ++i) e.box[i] = bx[i];
-    e.promo = -2;
+    e.promo = tag;
     memcpy(e.map, out, sizeof(CUtensorMap));
     c->tmaps.push_back(e);
     return 0;
@@ -268,7 +284,7 @@ static int launch_sc2d_tma_g(clbm_ctx *c)
     using C = Tma2Cfg<T, NS>;
     const Geom &g = c->geo;
     CUtensorMap tmap;
-    if (int rc = cached_tmap_2d(c, c->pop[0][c->parity], C::BY, &tmap)) return rc;
+    if (int rc = cached_tmap_2d(c, c->pop[0][c->parity], C::BY, C::PAIRS, &tmap)) return rc;
     const int tiles = (g.ny + T - 1) / T;
     // short x-chunks keep concurrently resident CTAs on neighbouring columns (their halo rows meet in L2) and give the tail of the
     // grid something to balance with; 32 columns was the optimum of the register-pipelined kernel at 8192^2
@@ -311,6 +327,9 @@ int sc2d_tma_step(clbm_ctx *c, int variant)
     case 10: return launch_sc2d_tma<256, 3, 4>(c);
     case 11: return launch_sc2d_tma<128, 3, 7>(c);
     case 12: return launch_sc2d_tma<64, 3, 12>(c);
+    case 13: return launch_sc2d_tma<224, 3, 3>(c);   // the tallest tiles whose box (228, 196 rows) still fits one TMA dimension
+    case 14: return launch_sc2d_tma<192, 3, 4>(c);
+    case 15: return launch_sc2d_tma<128, 2, 6>(c);
     default: return launch_sc2d_tma<128, 3, 6>(c);
     }
 }

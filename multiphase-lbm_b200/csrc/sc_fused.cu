@@ -124,10 +124,13 @@ sc_fused_kernel(const PopTable<L> P0, const uint8_t *__restrict__ flag, const do
             const int yy = g.wy(y0 + sy - 1), zz = (L::D == 3) ? g.wz(z0 + sz - 1) : 0;
             const int i = xs * plane + yy * nz + zz;
             double v = -1.0;
-            if (flag[i] != CELL_BB) {
-                double fh[L::Q];
+            // populations fetched whatever the mask says (a bounce_back cell's are valid memory, just unused): with the loads behind
+            // the mask test a halo thread paid two memory latencies in a row while its whole CTA waited at the barrier
+            const uint8_t flh = flag[i];
+            double fh[L::Q];
 #pragma unroll
-                for (int k = 0; k < L::Q; ++k) fh[k] = MULTI ? __ldcg(P.in[k] + i) : P.in[k][i];
+            for (int k = 0; k < L::Q; ++k) fh[k] = MULTI ? __ldcg(P.in[k] + i) : P.in[k][i];
+            if (flh != CELL_BB) {
                 bool gph;
                 if constexpr (GUO) v = scrt_psi(Mom<L>::sum(fh));
                 else v = sc_psi_g1(mp, Mom<L>::sum(fh), gph);

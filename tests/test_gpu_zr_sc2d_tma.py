@@ -44,7 +44,7 @@ def _run(prm, case, args, steps, tma, xchunk=None):
 def test_tma_kernel_is_bit_identical_to_the_register_pipelined_kernel(name):
     prm, case, args = CASES[name]
     ref, _ = _run(prm, case, args, 150, 0)
-    for shape in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):
+    for shape in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15):
         got, _ = _run(prm, case, args, 150, shape)
         np.testing.assert_array_equal(got, ref, err_msg="shape %d" % shape)
     for xchunk in (1, 3, 7):

@@ -11,9 +11,9 @@ pkg = entry.load_package()
 P = pkg.params
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 os.environ["CLBM_SC_MULTI"] = "0"
-for tma in (0, 6, 7, 8, 9, 10, 11, 12):
+for tma in (0, 1, 5, 7, 8, 9, 11, 12, 13, 14, 15):
     out = []
-    for xc in (None, 24, 48):
+    for xc in (None, 64):
         os.environ["CLBM_SC2D_TMA"] = str(tma)
         if xc:
             os.environ["CLBM_SC_XCHUNK"] = str(xc)
