@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "clbm_internal.h"
+#include "tma.cuh"
 
 namespace clbm {
 namespace puls {
@@ -237,6 +238,144 @@ __global__ void __launch_bounds__(NT) puls_fused(const double *__restrict__ A, d
                                   (F[sm][tid - 1] & F[sm][tid] & F[sm][tid + 1] & F[s0][tid - 1] & F[s0][tid] & F[s0][tid + 1] &
                                    F[sp][tid - 1] & F[sp][tid] & F[sp][tid + 1]) != 0;
             intr[Y + (long long)g.ny * X] = interior ? 1 : 0;      // puls_stream skips these nodes (one coalesced byte per node)
+            if (interior) {
+                double gk[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) gk[k] = R[ckx(k) > 0 ? sm : (ckx(k) < 0 ? sp : s0)][k][tid - cky(k)];   // source (X - cx, Y - cy)
+                double pp = 0.0, ux = 0.0, uy = 0.0;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) pp += gk[k];
+#pragma unroll
+                for (int k = 1; k < 9; ++k) { ux += gk[k] * ckx(k); uy += gk[k] * cky(k); }
+                const long long i = Y + (long long)g.ny * X;
+                Pn[i] = pp;
+                Uxn[i] = (mp.Rho0 == 1.0) ? 3.0 * ux : 3.0 * ux / mp.Rho0;
+                Uyn[i] = (mp.Rho0 == 1.0) ? 3.0 * uy : 3.0 * uy / mp.Rho0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- puls_fused with its inputs staged by TMA (opt-in, CLBM_PULS_TMA) ------------------------------------------------------
+// An experiment with a negative result, kept because it is bit-exact and documents where the kernel stands.  ncu at N = 1024 shows
+// 44 % of puls_fused's stall samples as long-scoreboard waits, which is what TMA staging cured in the D2Q9 Shan-Chen kernel.  Not
+// here: measured 361 us (2 stages) / 351 us (3 stages) against 351 us -- puls_fused already moves 1.05 GB + 0.96 GB per launch,
+// 5.75 TB/s, 0.88 of the measured HBM peak; the waits are the DRAM queue, not exposed latency.  What is left of the iteration is the
+// 100 us of one-thread-per-column wall kernels behind it.
+// The 12 input columns of a tile -- 9 populations, P, Ux, Uy -- arrive
+// as four cp.async.bulk.tensor boxes per column in an NS-stage shared-memory pipeline with mbarrier completion: no load instruction,
+// no address arithmetic and no registers are spent on data in flight, and NS - 1 whole columns are always on their way.  The box starts
+// one row in front of the tile's first halo row (an even row: the innermost TMA coordinate has to be 16-byte aligned) and is NT + 2
+// rows tall; rows and columns outside the lattice are zero-filled by the TMA unit and never used (their mask is 0).  Solid nodes are
+// fetched too (a box cannot skip them).  Arithmetic, ring and stores are those of puls_fused: the results are bit-identical.
+template <int NT, int NS>
+struct PulsTmaCfg {
+    static constexpr int BY = NT + 2;
+    static constexpr int A_BYTES = 9 * BY * 8, F_BYTES = BY * 8;
+    static constexpr int A_PITCH = ((A_BYTES + 127) / 128) * 128, F_PITCH = ((F_BYTES + 127) / 128) * 128;
+    static constexpr int STAGE_BYTES = A_PITCH + 3 * F_PITCH;
+    static constexpr int TX = A_BYTES + 3 * F_BYTES;
+    static constexpr int OFF_R = NS * STAGE_BYTES;            // R[3][9][NT]
+    static constexpr int OFF_F = OFF_R + 3 * 9 * NT * 8;      // F[3][NT]
+    static constexpr int OFF_BAR = ((OFF_F + 3 * NT + 15) / 16) * 16;
+    static constexpr int SMEM = OFF_BAR + NS * 8;
+    static_assert(NT % 2 == 0 && BY <= 256, "even tile height (16-byte rows), one TMA box dimension");
+};
+
+template <int NT, int NS>
+__global__ void __launch_bounds__(NT) puls_fused_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmP,
+                                                     const __grid_constant__ CUtensorMap tmUx, const __grid_constant__ CUtensorMap tmUy,
+                                                     double *__restrict__ B, const uint8_t *__restrict__ flag, double *__restrict__ Pn,
+                                                     double *__restrict__ Uxn, double *__restrict__ Uyn, uint8_t *__restrict__ intr, Geo g, Par mp,
+                                                     int xchunk)
+{
+    using C = PulsTmaCfg<NT, NS>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t stage_a = smem_u32(smem_raw);
+    double (*R)[9][NT] = reinterpret_cast<double (*)[9][NT]>(smem_raw + C::OFF_R);
+    uint8_t (*F)[NT] = reinterpret_cast<uint8_t (*)[NT]>(smem_raw + C::OFF_F);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
+    const int tid = threadIdx.x;
+    const int Y = (int)blockIdx.x * (NT - 2) - 1 + tid;          // rows tid = 0 and NT-1 are halo rows
+    const int Ys = (int)blockIdx.x * (NT - 2) - 2;               // first row of the boxes: thread tid reads box row tid + 1
+    const bool row_ok = Y >= 0 && Y < g.ny;
+    const bool own = tid >= 1 && tid < NT - 1 && row_ok;
+    const int xa = blockIdx.y * xchunk, xb = min(g.nx, xa + xchunk);
+    const int ncols = xb - xa + 2;                               // r = 0 .. ncols-1 enumerates the columns xa-1 .. xb
+    auto slot_of = [](int X) { return (X + 3) % 3; };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int r) {                                    // thread 0: the four boxes of column r into stage r % NS
+        const int X = xa - 1 + r;
+        uint64_t *bar = &mbar[r % NS];
+        const uint32_t st = stage_a + (r % NS) * C::STAGE_BYTES;
+        mbar_expect_tx(bar, (uint32_t)C::TX);
+        tma_load_3d(st, &tmA, bar, Ys, X, 0);
+        tma_load_2d(st + C::A_PITCH, &tmP, bar, Ys, X);
+        tma_load_2d(st + C::A_PITCH + C::F_PITCH, &tmUx, bar, Ys, X);
+        tma_load_2d(st + C::A_PITCH + 2 * C::F_PITCH, &tmUy, bar, Ys, X);
+    };
+    // stage r % NS is free once every thread has its column-r inputs in registers: the caller has a barrier behind collide_col
+    auto refill = [&](int r) {
+        if (tid == 0 && r + NS < ncols) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(r + NS);
+        }
+    };
+    auto flag_of = [&](int X) -> uint8_t { return (row_ok && X >= 0 && X < g.nx) ? flag[Y + (long long)g.ny * X] : (uint8_t)0; };
+    uint8_t f0, f1;          // node masks of the next two columns to be collided: plain loads, two columns ahead of their use
+    auto collide_col = [&](int r, bool write) {
+        const int X = xa - 1 + r;
+        const int s = slot_of(X);
+        const uint8_t fl = f0;
+        f0 = f1;
+        f1 = (r + 2 < ncols) ? flag_of(X + 2) : (uint8_t)0;
+        F[s][tid] = fl;
+        mbar_wait(&mbar[r % NS], (uint32_t)((r / NS) & 1));
+        if (!fl) return;
+        const uint32_t st = stage_a + (r % NS) * C::STAGE_BYTES + (tid + 1) * 8;
+        double gin[9], post[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) gin[k] = lds_f64(st + k * (C::BY * 8));
+        const double p0 = lds_f64(st + C::A_PITCH), u0 = lds_f64(st + C::A_PITCH + C::F_PITCH), v0 = lds_f64(st + C::A_PITCH + 2 * C::F_PITCH);
+        mrt_post(mp, gin, p0, u0, v0, post);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[s][k][tid] = post[k];
+        if (write && own) {
+            const long long i = Y + (long long)g.ny * X;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) B[k * g.nelem + i] = post[k];
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < NS; ++r)
+            if (r < ncols) issue(r);
+    }
+    f0 = flag_of(xa - 1);
+    f1 = flag_of(xa);
+    collide_col(0, false);
+    __syncthreads();
+    refill(0);
+    collide_col(1, true);
+    __syncthreads();
+    refill(1);
+    for (int X = xa; X < xb; ++X) {
+        const int r = X - xa + 2;                                // column X + 1
+        collide_col(r, X + 1 < xb);
+        __syncthreads();
+        refill(r);
+        if (own) {
+            const int sm = slot_of(X - 1), s0 = slot_of(X), sp = slot_of(X + 1);
+            const bool interior = X >= 1 && X <= g.nx - 2 && Y >= 1 && Y <= g.ny - 2 &&
+                                  (F[sm][tid - 1] & F[sm][tid] & F[sm][tid + 1] & F[s0][tid - 1] & F[s0][tid] & F[s0][tid + 1] &
+                                   F[sp][tid - 1] & F[sp][tid] & F[sp][tid + 1]) != 0;
+            intr[Y + (long long)g.ny * X] = interior ? 1 : 0;
             if (interior) {
                 double gk[9];
 #pragma unroll
@@ -725,6 +864,11 @@ struct clbm_pulsatile {
     uint8_t *intr;            // fused step: 1 where puls_fused streamed the node (interior), written every step
     double *P2, *Ux2, *Uy2;   // fused step: the set the running step writes (swapped with P, Ux, Uy afterwards)
     int fused;                // 1: puls_fused + puls_stream on the remaining nodes (default), 0: puls_collide + puls_stream
+    int tma;                  // fused step through puls_fused_tma: 0 off (CLBM_PULS_TMA=0, odd N, no driver entry point), else the stage count
+    int xchunk_env, nt_env;   // CLBM_PULS_XCHUNK / CLBM_PULS_NT, read once in clbm_pulsatile_create
+    int tma_xchunk;           // chunk length of the TMA kernel, chosen at its first launch (0 = not yet)
+    struct TmapSlot { const void *base; int rank, rows; CUtensorMap map; };
+    std::vector<TmapSlot> tmaps;   // tensor maps of the two lattice buffers and the six field arrays, encoded on first use
     bool in_complete;         // the last step's in buffer holds the streamed populations of ALL nodes (see puls_materialise)
     int *err_dev, *err_host;
     double *pre;          // pre-fill populations of this step's fresh nodes
@@ -803,6 +947,64 @@ int initial_state(clbm_pulsatile *c, std::vector<double> &gin, std::vector<uint8
     return CLBM_OK;
 }
 
+// tensor map of one lattice buffer ([9][nx][ny], rank 3) or one field array ([nx][ny], rank 2) with a (rows, 1[, 9]) box
+int puls_tmap(clbm_pulsatile *c, const void *base, int rank, int rows, CUtensorMap *out)
+{
+    for (const auto &e : c->tmaps)
+        if (e.base == base && e.rank == rank && e.rows == rows) { memcpy(out, &e.map, sizeof(CUtensorMap)); return CLBM_OK; }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available"); return CLBM_ECUDA; }
+    const Geo &g = c->g;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.ny, (cuuint64_t)g.nx, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.ny * 8, (cuuint64_t)g.nelem * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)rows, 1, 9};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    clbm_pulsatile::TmapSlot e;
+    CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (pulsatile, rank %d) failed (%d)", rank, (int)r); return CLBM_ECUDA; }
+    e.base = base; e.rank = rank; e.rows = rows;
+    c->tmaps.push_back(e);
+    memcpy(out, &e.map, sizeof(CUtensorMap));
+    return CLBM_OK;
+}
+
+template <int NT, int NS>
+int launch_fused_tma(clbm_pulsatile *c, const double *A, double *B, double *Pw, double *Uxw, double *Uyw)
+{
+    using C = PulsTmaCfg<NT, NS>;
+    const Geo &g = c->g;
+    CUtensorMap tA, tP, tUx, tUy;
+    int rc;
+    if ((rc = puls_tmap(c, A, 3, C::BY, &tA)) || (rc = puls_tmap(c, c->P, 2, C::BY, &tP)) || (rc = puls_tmap(c, c->Ux, 2, C::BY, &tUx)) ||
+        (rc = puls_tmap(c, c->Uy, 2, C::BY, &tUy)))
+        return rc;
+    auto kern = puls_fused_tma<NT, NS>;
+    const int segs = (g.ny + (NT - 2) - 1) / (NT - 2);
+    int xchunk = c->xchunk_env;
+    if (c->tma_xchunk == 0) {       // first launch of this context: opt in to the dynamic shared memory, choose the chunk length
+        CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        // whole waves: the CTAs of a launch all take the same time, so a last wave that is half empty costs a sixth of the launch
+        int per_sm = 0, sms = 0;
+        CLBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, C::SMEM));
+        CLBM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        const long long slots = (long long)(per_sm > 0 ? per_sm : 1) * sms;
+        const long long want = (long long)segs * ((g.nx + 63) / 64);           // CTAs at the 64-column chunks of puls_fused
+        const long long waves = (want + slots - 1) / slots;
+        long long chunks = waves * slots / segs;
+        if (chunks < 1) chunks = 1;
+        xchunk = (int)((g.nx + chunks - 1) / chunks);
+        if (xchunk < 8) xchunk = g.nx < 8 ? g.nx : 8;
+        if (c->xchunk_env > 0) xchunk = c->xchunk_env;
+        if (xchunk > g.nx) xchunk = g.nx;
+        c->tma_xchunk = xchunk;
+    }
+    xchunk = c->tma_xchunk;
+    dim3 grid(segs, (g.nx + xchunk - 1) / xchunk);
+    kern<<<grid, NT, C::SMEM, c->stream>>>(tA, tP, tUx, tUy, B, c->flag, Pw, Uxw, Uyw, c->intr, g, c->mp, xchunk);
+    return CLBM_OK;
+}
+
 int one_step(clbm_pulsatile *c)
 {
     const Geo &g = c->g;
@@ -817,10 +1019,16 @@ int one_step(clbm_pulsatile *c)
         cudaEventRecord(e, c->stream);
     }
     double *Pw = c->fused ? c->P2 : c->P, *Uxw = c->fused ? c->Ux2 : c->Ux, *Uyw = c->fused ? c->Uy2 : c->Uy;   // this step's P, Ux, Uy
-    if (c->fused) {
-        int xchunk = g.nx < 64 ? g.nx : 64, nt = 128;
-        if (const char *e = getenv("CLBM_PULS_XCHUNK")) { const int v = atoi(e); if (v > 0) xchunk = v < g.nx ? v : g.nx; }
-        if (const char *e = getenv("CLBM_PULS_NT")) nt = atoi(e);
+    if (c->fused && c->tma) {
+        int rc;
+        if (c->tma == 3) rc = launch_fused_tma<128, 3>(c, A, B, Pw, Uxw, Uyw);
+        else if (c->tma == 4) rc = launch_fused_tma<64, 3>(c, A, B, Pw, Uxw, Uyw);
+        else if (c->tma == 5) rc = launch_fused_tma<254, 2>(c, A, B, Pw, Uxw, Uyw);
+        else rc = launch_fused_tma<128, 2>(c, A, B, Pw, Uxw, Uyw);
+        if (rc) return rc;
+    } else if (c->fused) {
+        int xchunk = g.nx < 64 ? g.nx : 64, nt = c->nt_env > 0 ? c->nt_env : 128;
+        if (c->xchunk_env > 0) xchunk = c->xchunk_env < g.nx ? c->xchunk_env : g.nx;
         if (nt == 64) {
             dim3 grid((g.ny + 62 - 1) / 62, (g.nx + xchunk - 1) / xchunk);
             puls_fused<64><<<grid, 64, 0, c->stream>>>(A, B, c->flag, c->P, c->Ux, c->Uy, Pw, Uxw, Uyw, c->intr, g, c->mp, xchunk);
@@ -932,6 +1140,16 @@ int clbm_pulsatile_create(const clbm_pulsatile_params *p, clbm_pulsatile **out)
     if ((e = cudaMalloc(&c->intr, (size_t)g.nelem)) != cudaSuccess) return fail(e, "cudaMalloc intr");
     c->fused = 1;
     if (const char *e = getenv("CLBM_PULS_FUSED")) c->fused = atoi(e) != 0;
+    c->tma_xchunk = 0;
+    c->xchunk_env = getenv("CLBM_PULS_XCHUNK") ? atoi(getenv("CLBM_PULS_XCHUNK")) : 0;
+    c->nt_env = getenv("CLBM_PULS_NT") ? atoi(getenv("CLBM_PULS_NT")) : 0;
+    // TMA-staged fused step, OPT-IN (measured equal or slower, see puls_fused_tma): CLBM_PULS_TMA = 2 / 3 pick the stage count of the
+    // 128-row tile, 4 the 64-row tile, 5 the 254-row tile; needs 16-byte aligned rows and buffers (even N) and the driver's encoder
+    c->tma = 0;
+    if (const char *e = getenv("CLBM_PULS_TMA")) {
+        const int v = atoi(e);
+        if (v >= 2 && v <= 5 && g.ny % 2 == 0 && g.ny >= 8 && get_encode() != nullptr) c->tma = v;
+    }
     c->in_complete = true;
     double **fl[6] = {&c->P, &c->Ux, &c->Uy, &c->P2, &c->Ux2, &c->Uy2};
     for (auto f : fl) if ((e = cudaMalloc(f, nd)) != cudaSuccess) return fail(e, "cudaMalloc field");

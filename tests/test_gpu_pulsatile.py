@@ -108,3 +108,21 @@ def test_pulsatile_gpu_open_vessel_vs_oracle(N, steps, margin):
         f = dev.fields()
         assert np.isfinite(f["P"]).all() and 0.5 < f["flag"].mean() < 1.0
     o.close()
+
+
+@pytest.mark.parametrize("variant", [2, 3, 4, 5])
+def test_pulsatile_tma_staged_fused_step_is_bit_exact(variant):
+    """CLBM_PULS_TMA (opt-in): puls_fused with its 12 input columns staged by cp.async.bulk.tensor boxes; same arithmetic, so the
+    state must equal the oracle bit for bit -- moving walls, fresh nodes and both Zou/He ends included (N = 64, the reference's own
+    start, 600 iterations, several tiles in y at the 64-row shape)"""
+    os.environ["CLBM_PULS_TMA"] = str(variant)
+    try:
+        o = PulsatileOracle(N=64)
+        with clbm.Pulsatile(N=64) as dev:
+            for chunk in (1, 2, 297, 300):
+                o.step(chunk)
+                dev.step(chunk)
+                _compare(dev, o.fields(), o.lattice(), o.parity, "variant %d" % variant)
+        o.close()
+    finally:
+        os.environ.pop("CLBM_PULS_TMA", None)
