@@ -476,8 +476,8 @@ def main():
             r["us_per_step"] = r["ms_per_step"] * 1e3
             r["l2_policy"] = l2_policy_text(r["bytes_per_gpu"])
             if not a.no_cpu:
-                key, sz, _ = WORKLOADS[wl]
-                r["cpu_baseline_reference"] = reference_functor_baseline(key, same_lattice=(sz[0], sz[1], ref_steps))
+                wl_key, sz, _ = WORKLOADS[wl]     # (not `key`: that is the headline workload's, used for its CPU arm below)
+                r["cpu_baseline_reference"] = reference_functor_baseline(wl_key, same_lattice=(sz[0], sz[1], ref_steps))
             also[wl] = r
         roofline["also"] = also
     if default_run and world > 1:
