@@ -79,6 +79,8 @@ struct EnvKnobs {
     int sc_xchunk, sc_tile, sc_cluster, tma_promo, sc_multi, sc2d_tma;
     int hcz_tile, hcz_xchunk, hcz2d_tile, hcz2d_xchunk, hcz2d_multi;
     int hcz3d_sweep;   // 1 / 0: force / forbid the single-sweep HCZ D3Q19 kernel (default: where eligible)
+    int hcz3d_sweep_var;   // load-issue variant of that kernel (hcz3d_sweep.cu, bit-identical results)
+    int hcz3d_sweep_ko;    // knock-out bits for timing experiments (WRONG results when set; tools/hcz3d_sweep_variants.py)
     int slab_graph;    // 0: never capture the slab step in a CUDA graph
     int persist;       // 0: never use the persistent multi-step kernels of the L2-resident lattices
     int ring_fuse;     // peer ring: 0 separate signal / wait kernels, 1 both fused into the pack / unpack kernels (measured slower), default (2): signals fused only
@@ -104,6 +106,8 @@ inline void read_env_knobs(EnvKnobs &k)
     k.hcz2d_tile = env_int("CLBM_HCZ2D_TILE");
     k.hcz2d_xchunk = env_int("CLBM_HCZ2D_XCHUNK");
     k.hcz3d_sweep = env_int("CLBM_HCZ3D_SWEEP");
+    k.hcz3d_sweep_var = env_int("CLBM_HCZ3D_SWEEP_VAR");
+    k.hcz3d_sweep_ko = env_int("CLBM_HCZ3D_SWEEP_KO");
     k.slab_graph = env_int("CLBM_SLAB_GRAPH");
     k.persist = env_int("CLBM_PERSIST");
     k.ring_fuse = env_int("CLBM_RING_FUSE");

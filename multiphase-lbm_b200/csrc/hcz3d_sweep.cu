@@ -97,13 +97,29 @@ struct SweepLocal {
     double phi, rho, Fx, Fy, Fz, gp[3], u0, u1, u2, Pt;
 };
 
-template <int TY, int TZ>
+// VAR (CLBM_HCZ3D_SWEEP_VAR, bit-identical results): bit 0 = the four interleaved edge moments of a slot as two 16-byte loads
+// instead of four 8-byte ones (the ring warps issue 38 scattered loads per plane in S1 and sat in the LSU queue there: `lg`
+// throttle on exactly those lines); bit 1 = the raw moments (needed after the gather phase) are requested BEFORE phi of plane
+// x+4 (needed an iteration later); bit 2 = the push of the nine directions with c_z = 0 as TMA box stores: S4 writes the post-collision values back
+// into the stage anyway (S5 gathers them there), so one thread stores the tile of such a direction to its shifted position with
+// cp.async.bulk.tensor shared -> global boxes (18 per plane) instead of a st.global per thread and direction (the knock-out timing
+// of tools/hcz3d_sweep_ko.py: 4.8 of 22.3 ms per step went with the thread-level stores).  Only c_z = 0: a box STORE traps with
+// "illegal instruction" on this device unless its start is 16-byte aligned in global memory and its coordinates are non-negative
+// (tools/probe/tma_store_probe.cu; box LOADS have neither restriction), and z0 +- 1 is an odd number of doubles.  Tiles in the
+// first / last tile row (y0 - 1 < 0, or a clipped box) keep the thread-level stores for every direction.
+template <int TY, int TZ, int VAR = 0, bool KO = false>
 __global__ void __launch_bounds__(TY *TZ, 1)
-hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_g, const SweepOut P,
-                   const SweepMom Min, const SweepMom Mout, Geom g, ModelParams mp, EdgeGeom eg)
+hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_g,
+                   const __grid_constant__ CUtensorMap tmap_fo, const __grid_constant__ CUtensorMap tmap_go, const SweepOut P,
+                   const SweepMom Min, const SweepMom Mout, Geom g, ModelParams mp, EdgeGeom eg, int ko_arg)
 {
+    // ko: knock-out bits of tools/hcz3d_sweep_ko.py (CLBM_HCZ3D_SWEEP_KO) -- TIMING EXPERIMENTS ONLY, results are wrong when set; only the
+    // KO = true instantiation looks at them, in the production kernels the constant 0 removes every test
+    const int ko = KO ? ko_arg : 0;
     using C = SweepCfg<TY, TZ>;
     constexpr int NT = C::NT;
+    constexpr bool TS = (VAR & 4) != 0;             // TMA stores
+    constexpr int TMA_TID = TS ? NT - 32 : 0;       // the thread that talks to the TMA unit (TS: first lane of the last warp, which has no ring cells)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t stage_a = smem_u32(smem_raw);
     double *r_phi = reinterpret_cast<double *>(smem_raw + C::OFF_PHI);   // [4][R3]
@@ -195,10 +211,12 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         tma_load_4d(stage_a + s * C::STAGE_BYTES, &tmap_f, &mbar[s], z0, y0, x + G, 0);
         tma_load_4d(stage_a + s * C::STAGE_BYTES + C::SET_BYTES, &tmap_g, &mbar[s], z0, y0, x + G, 0);
     };
-    if (tid == 0) {
+    if (tid == TMA_TID) {
         issue(0);
         if (1 < nx) issue(1);
     }
+    // TS: tiles of the first / last tile row keep thread-level stores for every direction
+    const bool edge_cta = TS && (y0 == 0 || y0 + TY == ny);
 
     // storage plane of slab plane xg, and whether that plane has edge sums (ghost planes of an x-slab carry merged values)
     auto xs_of = [&](int xg) { return g.wx(xg) + G; };
@@ -213,7 +231,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 3; ++j)
             if (w_idx[j] >= 0) phi_n[j] = Min.m[0][base + w_yz[j]];
-        if (w_idx[2] >= 0 && has_edges(xg)) {
+        if (w_idx[2] >= 0 && has_edges(xg) && !(ko & 64)) {
             const double *E = Min.ephi + (size_t)g.wx(xg) * eg.eplane;
             phi_e[0] = phi_e[1] = phi_e[2] = 0.0;
 #pragma unroll
@@ -230,7 +248,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
     double mo_r[4][4], mh_r[4][4], mo_c[4], mh_c[4];
     auto load_mom = [&](int xg) {
         const int base = xs_of(xg) * plane;
-        const bool ed = has_edges(xg);
+        const bool ed = has_edges(xg) && !(ko & 64);
         const double *E = Min.e4 + (size_t)g.wx(xg) * eg.eplane * 4;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
@@ -241,10 +259,15 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         for (int q = 0; q < 3; ++q)
             if (ed && own_e[q] >= 0) {
                 const double *Eq = E + (size_t)own_e[q] * 4;
+                if constexpr (VAR & 1) {
+                    const double2 a = reinterpret_cast<const double2 *>(Eq)[0], b = reinterpret_cast<const double2 *>(Eq)[1];
+                    mo_r[0][q + 1] = a.x; mo_r[1][q + 1] = a.y; mo_r[2][q + 1] = b.x; mo_r[3][q + 1] = b.y;
+                } else {
 #pragma unroll
-                for (int m = 0; m < 4; ++m) mo_r[m][q + 1] = Eq[m];
+                    for (int m = 0; m < 4; ++m) mo_r[m][q + 1] = Eq[m];
+                }
             }
-        if (h_warp) {
+        if (h_warp && !(ko & 8)) {
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
                 mh_r[m][0] = Min.m[m + 1][base + h1_yz];
@@ -254,8 +277,13 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             for (int q = 0; q < 3; ++q)
                 if (ed && h1_e[q] >= 0) {
                     const double *Eq = E + (size_t)h1_e[q] * 4;
+                    if constexpr (VAR & 1) {
+                        const double2 a = reinterpret_cast<const double2 *>(Eq)[0], b = reinterpret_cast<const double2 *>(Eq)[1];
+                        mh_r[0][q + 1] = a.x; mh_r[1][q + 1] = a.y; mh_r[2][q + 1] = b.x; mh_r[3][q + 1] = b.y;
+                    } else {
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) mh_r[m][q + 1] = Eq[m];
+                        for (int m = 0; m < 4; ++m) mh_r[m][q + 1] = Eq[m];
+                    }
                 }
         }
     };
@@ -344,8 +372,10 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const double Gam = fma(-t, usqr, t);
                 pf = fma(Gam, opg, om1 * fk);
                 pg = fma(om1, gk, (omega * t) * fma(-rho3, usqr, Pt)) - fma(Gam, uD, t * uE);
-                fo[i0 + P.kn[k]] = pf;
-                go[i0 + P.kn[k]] = pg;
+                if ((!TS || edge_cta) && !(ko & 16)) {
+                    fo[i0 + P.kn[k]] = pf;
+                    go[i0 + P.kn[k]] = pg;
+                }
             } else {
                 const bool axis = (L19s::cx(k) != 0) + (L19s::cy(k) != 0) + (L19s::cz(k) != 0) == 1;
                 const double cu = cdot<L19s>(k, u0, u1, u2);
@@ -356,11 +386,15 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const double dG = cdot<L19s>(k, G0, G1, G2) + opg;
                 pf = fma(Gam, dG, om1 * fk);
                 pg = fma(t, dE, fma(Gam, dD, fma(om1, gk, fma(axis ? Ba : Bd, poly, axis ? Aa : Ad))));
-                unsigned idx = (L19s::cx(k) < 0 ? im : (L19s::cx(k) > 0 ? ip : i0)) + P.kn[k];
-                if (L19s::cy(k)) idx += (unsigned)(L19s::cy(k) < 0 ? oym : oyp);
-                if (L19s::cz(k)) idx += (unsigned)(L19s::cz(k) < 0 ? ozm : ozp);
-                fo[idx] = pf;
-                go[idx] = pg;
+                if (!(TS && L19s::cz(k) == 0) || edge_cta) {
+                    unsigned idx = (L19s::cx(k) < 0 ? im : (L19s::cx(k) > 0 ? ip : i0)) + P.kn[k];
+                    if (L19s::cy(k)) idx += (unsigned)(L19s::cy(k) < 0 ? oym : oyp);
+                    if (L19s::cz(k)) idx += (unsigned)(L19s::cz(k) < 0 ? ozm : ozp);
+                    if (!(ko & 16)) {
+                        fo[idx] = pf;
+                        go[idx] = pg;
+                    }
+                }
             }
             sf[k * NT] = pf;             // the gather of the next iteration reads these
             sf[(19 + k) * NT] = pg;
@@ -409,20 +443,39 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
             for (int j = 0; j < 2; ++j)
                 if (w_idx[j] >= 0) dst[w_idx[j]] = phi_n[j];
             if (w_idx[2] >= 0) dst[w_idx[2]] = ((phi_n[2] + phi_e[0]) + phi_e[1]) + phi_e[2];
-            if (x + 1 < nx) load_phi(x + 4);
-            if (s3_on) {
-                load_mom(x + 1);
+            if constexpr (VAR & 2) {
+                if (s3_on) load_mom(x + 1);
+                if (x + 1 < nx) load_phi(x + 4);
+            } else {
+                if (x + 1 < nx) load_phi(x + 4);
+                if (s3_on) load_mom(x + 1);
             }
         }
         __syncthreads();
+        if constexpr (TS) {
+            // push of plane x-1: its post-collision tile of every direction, shifted by c_k, straight from the stage
+            if (tid == TMA_TID && x >= 1 && !(ko & 1024) && !edge_cta) {
+                const int xq = x - 1;
+                const uint32_t src = stage_a + (xq & 1) * C::STAGE_BYTES;
+                const int xs0 = xq + G, xsm = g.wx(xq - 1) + G, xsp = g.wx(xq + 1) + G;
+#pragma unroll
+                for (int k = 0; k < 19; ++k) {
+                    if (L19s::cz(k) != 0) continue;
+                    const int xs = L19s::cx(k) < 0 ? xsm : (L19s::cx(k) > 0 ? xsp : xs0);
+                    tma_store_4d(&tmap_fo, src + k * NT * 8, z0, y0 + L19s::cy(k), xs, k);
+                    tma_store_4d(&tmap_go, src + C::SET_BYTES + k * NT * 8, z0, y0 + L19s::cy(k), xs, k);
+                }
+                bulk_commit();
+            }
+        }
 
         // ---- S5: what plane x-1 pushed (its post-collision values are in its stage) ----
-        if (x >= 1) {
+        if (x >= 1 && !(ko & 2)) {
             const double *S = reinterpret_cast<const double *>(smem_raw + ((x - 1) & 1) * C::STAGE_BYTES);
             PushSums ps;
             gather_pushes<TY, TZ>(S, ty, tz, ps);
             accumulate(ps, tid, x - 1, store_own);
-            if (h_act) {
+            if (h_act && !(ko & 1)) {
                 // ring cell: only the directions leaving the tile through that side can contribute
                 const int dy = h1y - 1, dz = h1z - 1;
                 if (tid < C::Z1) gather_pushes<TY, TZ, -1, 2>(S, dy, dz, ps);              // row below the tile
@@ -432,9 +485,9 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 accumulate(ps, NT + tid, x - 1, store_ring);
             }
         }
-        if (s3_on) merge_mom();   // the loads of S1 have had the whole gather phase to land
+        if (s3_on) merge_mom();   // the loads of S1 have had the whole gather phase to land (merging after S2 instead: no change, 21.75 vs 21.72 ms)
         // ---- S2: lap(phi), psi(phi) of plane x+2 on tile + halo 2 ----
-        if (x + 2 >= -2 && x < nx) {
+        if (x + 2 >= -2 && x < nx && !(ko & 32)) {
             const int p = x + 2;
             const double *Pm = r_phi + ((p - 1) & 3) * C::R3, *P0 = r_phi + (p & 3) * C::R3, *Pp = r_phi + ((p + 1) & 3) * C::R3;
             double lap_v[C::N2], pp_v[C::N2];
@@ -467,15 +520,16 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         }
         __syncthreads();
         // the stage of plane x-1 has been gathered: refill it with plane x+1 (generic-proxy accesses before the async write)
-        if (tid == 0 && x >= 1 && x + 1 < nx) {
+        if (tid == TMA_TID && x >= 1 && x + 1 < nx) {
+            if constexpr (TS) bulk_wait_read_all();    // the box stores of plane x-1 have read the stage
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             issue(x + 1);
         }
 
         // ---- S3: level 2 of plane x+1 on tile + halo 1 ----
-        if (s3_on) {
+        if (s3_on && !(ko & 256)) {
             double *pr = r_pr + ((x + 1) & 3) * C::R1;
-            if (h_warp) {
+            if (h_warp && !(ko & 4)) {
                 SweepLocal tmp;
                 const double a = level2(x + 1, ty + 1, tz + 1, mo_c, nxt);
                 const double b = level2(x + 1, h1y, h1z, mh_c, tmp);
@@ -490,11 +544,15 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         // ---- S4: collide + push plane x ----
         if (x >= 0 && x < nx) {
             mbar_wait(&mbar[x & 1], (x >> 1) & 1);
-            collide(x, reinterpret_cast<double *>(smem_raw + (x & 1) * C::STAGE_BYTES) + tid);
+            if (!(ko & 128)) collide(x, reinterpret_cast<double *>(smem_raw + (x & 1) * C::STAGE_BYTES) + tid);
+            if constexpr (TS) fence_proxy_async_smem();   // the stage as the box stores (async proxy) must see it, before the next barrier
         }
         cur = nxt;
     }
 
+    if constexpr (TS) {
+        if (tid == TMA_TID) bulk_wait_all();
+    }
     // ---- x wraps inside the CTA: plane nx-1 still lacks the C group of plane 0 (parked in its slot at the start), plane 0
     //      the A group of plane nx-1 (in the accumulators now).  Same thread wrote those slots: a plain read-modify-write. ----
     if (wrapx) {
@@ -523,6 +581,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 static constexpr int SW_TY = 8, SW_TZ = 32;
+static constexpr int SW_VAR_DEFAULT = 5;   // CLBM_HCZ3D_SWEEP_VAR overrides (kernel header)
 
 EdgeGeom hcz3d_sweep_edge_geom(const clbm_ctx *c) { return make_edge_geom<SW_TY, SW_TZ>(c->geo.ny, c->geo.nz); }
 long long hcz3d_sweep_edge_doubles(const clbm_ctx *c) { return (long long)c->geo.nx * hcz3d_sweep_edge_geom(c).eplane; }
@@ -555,15 +614,27 @@ int hcz3d_sweep_launch(clbm_ctx *c, int src)
     Min.e4 = c->mome[src][1];
     Mout.ephi = c->mome[1 - src][0];
     Mout.e4 = c->mome[1 - src][1];
-    auto kern = hcz3d_sweep_kernel<SW_TY, SW_TZ>;
-    static PerDeviceOnce attr;
-    if (attr.need(c->device)) {
+    const int var_env = c->env.hcz3d_sweep_var >= 0 ? c->env.hcz3d_sweep_var : SW_VAR_DEFAULT;
+    const int ko = c->env.hcz3d_sweep_ko > 0 ? c->env.hcz3d_sweep_ko : 0;
+    const int var = ko ? 3 : ((var_env & 4) ? 2 : (var_env & 1));       // kernel table slot: VAR 0, 1, 5, and 5 with the knock-out tests compiled in
+    using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const SweepOut, const SweepMom, const SweepMom,
+                          Geom, ModelParams, EdgeGeom, int);
+    static const Kern kerns[4] = {hcz3d_sweep_kernel<SW_TY, SW_TZ, 0>, hcz3d_sweep_kernel<SW_TY, SW_TZ, 1>, hcz3d_sweep_kernel<SW_TY, SW_TZ, 5>,
+                                  hcz3d_sweep_kernel<SW_TY, SW_TZ, 5, true>};
+    const Kern kern = kerns[var];
+    static PerDeviceOnce attr[4];
+    if (attr[var].need(c->device)) {
         CLBM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        attr.mark(c->device);
+        attr[var].mark(c->device);
     }
+    // output boxes of the TMA-store form: one direction's tile
+    CUtensorMap tmo[2];
+    const cuuint32_t obox[4] = {(cuuint32_t)SW_TZ, (cuuint32_t)SW_TY, 1, 1};
+    for (int s = 0; s < 2; ++s)
+        if (int rc = cached_tmap(c, c->pop[s][1 - c->parity], obox, CU_TENSOR_MAP_L2_PROMOTION_NONE, &tmo[s])) return rc;
     dim3 grid(g.nz / SW_TZ, g.ny / SW_TY, 1);
     LaunchScope ls(c, "hcz3d_sweep_collide_stream_moments", true);
-    kern<<<grid, C::NT, C::SMEM, c->stream>>>(tm[0], tm[1], P, Min, Mout, g, c->mp, hcz3d_sweep_edge_geom(c));
+    kern<<<grid, C::NT, C::SMEM, c->stream>>>(tm[0], tm[1], tmo[0], tmo[1], P, Min, Mout, g, c->mp, hcz3d_sweep_edge_geom(c), ko);
     CLBM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -65,6 +65,17 @@ CLBM_D void tma_load_2d(uint32_t dst, const CUtensorMap *tmap, uint64_t *bar, in
         ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 
+// shared -> global box store (bulk async-group of the issuing thread) and its bookkeeping
+CLBM_D void tma_store_4d(const CUtensorMap *tmap, uint32_t src, int c0, int c1, int c2, int c3)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+CLBM_D void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+CLBM_D void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // the sources may be overwritten
+CLBM_D void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+CLBM_D void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }  // generic-proxy smem writes -> async proxy
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -182,3 +182,67 @@ def test_sweep_on_x_slabs(nranks, peer):
     ora.step(2)
     assert _cases.rel_linf(pops2, ora.in_pops()) < TOL
     assert max(per_step) < 14, per_step               # sweep + 2 boundary-plane moments + packs / unpacks (+ signal / wait), not 2 full passes
+
+
+class var_env(sweep_env):
+    """CLBM_HCZ3D_SWEEP_VAR: load / store variant of the sweep kernel (read once per context)"""
+
+    def __enter__(self):
+        self.old_var = os.environ.get("CLBM_HCZ3D_SWEEP_VAR")
+        if self.v is None:
+            os.environ.pop("CLBM_HCZ3D_SWEEP_VAR", None)
+        else:
+            os.environ["CLBM_HCZ3D_SWEEP_VAR"] = str(self.v)
+
+    def __exit__(self, *a):
+        if self.old_var is None:
+            os.environ.pop("CLBM_HCZ3D_SWEEP_VAR", None)
+        else:
+            os.environ["CLBM_HCZ3D_SWEEP_VAR"] = self.old_var
+
+
+@pytest.mark.parametrize("var", [0, 1])
+def test_sweep_kernel_variants_are_bit_identical(var):
+    """the default kernel (16-byte edge loads, the nine c_z = 0 directions pushed as TMA box stores from the stage) against the
+    scalar-load and the thread-store forms: same arithmetic, so the populations must be IDENTICAL.  ny = 40 gives tile rows that
+    are not on the lattice border (only those issue box stores) next to the first / last row (thread-level stores)."""
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 10, 40, 64, ulb=0.01, N=10, Re=6.0, kappa=5e-4, gravity=-1e-5)
+    out = []
+    for v in (None, var):
+        with var_env(v), make(prm, 1) as lat:
+            lat.init_case(P.CASE_HCZ_LAPLACE3D, ())
+            lat.step(25)
+            out.append((lat.in_pops(), lat.fields()))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("s0", "s1", "ux", "uy", "uz"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+def test_sweep_box_stores_on_x_slabs_with_interior_tile_rows():
+    """x-slabs whose planes have tile rows away from the lattice border: the box stores of the c_x = +-1 directions land in the
+    ghost planes the ring ships to the neighbours.  Against the single slab (round-off of the two rebuilt planes) and the oracle."""
+    slab = pkg.slab
+    nranks = 2
+    prm = P.hcz_params(P.MODEL_HCZ_D3Q19, 8 * nranks, 40, 64, ulb=0.01, N=16, Re=6.0, kappa=5e-4, gravity=-1e-5)
+    ora = OracleSim(prm).init_case(P.CASE_HCZ_LAPLACE3D, ())
+    steps = 30
+    with make(prm, 1) as single:
+        single.upload(ora.lattice, ora.flag, 0)
+        single.step(steps)
+        ref_pops = single.in_pops()
+    lats = []
+    with sweep_env(1):
+        for r in range(nranks):
+            lat = pkg.clbm.Lattice(slab.slab_params(prm, r, nranks))
+            l, f = slab.slice_host_state(prm, ora.lattice, ora.flag, r, nranks)
+            lat.upload(l, f, 0)
+            lats.append(lat)
+    ring = slab.LocalRing(lats, peer=True)
+    ring.exchange_flags()
+    ring.step(steps)
+    pops = np.concatenate([lat.in_pops() for lat in lats], axis=2)
+    for lat in lats:
+        lat.close()
+    assert _cases.rel_linf(pops, ref_pops) < 1e-12
+    ora.step(steps)
+    assert _cases.rel_linf(pops, ora.in_pops()) < TOL
