@@ -67,6 +67,18 @@ CLBM_HD int ring_slot(const EdgeGeom &g, int y0, int z0, int dy, int dz)
     return (ys && zs) ? e[2] : (ys ? e[0] : e[1]);
 }
 
+// ---- the push of a tile's post-collision plane as TMA box stores (hcz3d_sweep.cu, VAR bit 2) ----
+// A box store needs a start that is 16-byte aligned in global memory and has no negative coordinate (the device traps otherwise,
+// tools/probe/tma_store_probe.cu); z is the fastest index, so only the directions with c_z = 0 qualify (z0 is a multiple of TZ,
+// TZ is even), and only in tiles whose shifted box stays inside [0, ny): not the first / last tile row.  Everything else is
+// pushed by the threads, with the periodic wrap.  Kernel and CPU emulation (tests/test_hcz3d_edges.py) share this rule.
+template <int TY, int TZ>
+CLBM_HD bool push_by_box(int y0, int ny, int cz) { return cz == 0 && y0 > 0 && y0 + TY < ny; }
+// start of that box in (y, z) for a direction with c_z = 0
+struct PushBox { int y, z; };
+template <int TY, int TZ>
+CLBM_HD PushBox push_box_start(int y0, int z0, int cy) { return PushBox{y0 + cy, z0}; }
+
 // what the nodes of ONE plane of the tile push into the cell (dy, dz) (tile coordinates; ring cells have dy = -1 / TY or
 // dz = -1 / TZ), grouped by c_x: index 0 = A (c_x = +1), 1 = B (c_x = 0), 2 = C (c_x = -1).  S = the plane's post-collision
 // populations [38][TY][TZ].  jx needs no sums of its own: it is +P_term(A) - P_term(C).

@@ -216,7 +216,7 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
         if (1 < nx) issue(1);
     }
     // TS: tiles of the first / last tile row keep thread-level stores for every direction
-    const bool edge_cta = TS && (y0 == 0 || y0 + TY == ny);
+    const bool edge_cta = TS && !push_by_box<TY, TZ>(y0, ny, 0);
 
     // storage plane of slab plane xg, and whether that plane has edge sums (ghost planes of an x-slab carry merged values)
     auto xs_of = [&](int xg) { return g.wx(xg) + G; };
@@ -460,10 +460,11 @@ hcz3d_sweep_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_cons
                 const int xs0 = xq + G, xsm = g.wx(xq - 1) + G, xsp = g.wx(xq + 1) + G;
 #pragma unroll
                 for (int k = 0; k < 19; ++k) {
-                    if (L19s::cz(k) != 0) continue;
+                    if (L19s::cz(k) != 0) continue;      // push_by_box: the rest of the rule is edge_cta
                     const int xs = L19s::cx(k) < 0 ? xsm : (L19s::cx(k) > 0 ? xsp : xs0);
-                    tma_store_4d(&tmap_fo, src + k * NT * 8, z0, y0 + L19s::cy(k), xs, k);
-                    tma_store_4d(&tmap_go, src + C::SET_BYTES + k * NT * 8, z0, y0 + L19s::cy(k), xs, k);
+                    const PushBox b = push_box_start<TY, TZ>(y0, z0, L19s::cy(k));
+                    tma_store_4d(&tmap_fo, src + k * NT * 8, b.z, b.y, xs, k);
+                    tma_store_4d(&tmap_go, src + C::SET_BYTES + k * NT * 8, b.z, b.y, xs, k);
                 }
                 bulk_commit();
             }

@@ -95,3 +95,58 @@ extern "C" int host_check_hcz3d_edges(int ty, int tz, int nx, int ny, int nz, co
     if (ty == 4 && tz == 8) return run<4, 8>(nx, ny, nz, post, out, wrap);
     return -2;
 }
+
+// ---- the push of one plane as the kernel does it with VAR bit 2: box stores where push_by_box() says so (emulated with the TMA
+//      unit's clipping of out-of-range elements), thread-level stores with the periodic wrap everywhere else.
+//      post / out: [19][ny][nz]; writes[k][y][z] counts the stores a slot received.  Returns a non-zero code when a box would
+//      break the device's rule for box stores (negative or 16-byte-unaligned start) or would be clipped.
+template <int TY, int TZ>
+static int run_push(int ny, int nz, const double *post, double *out, int *writes)
+{
+    if (ny % TY || nz % TZ) return -1;
+    const size_t plane = (size_t)ny * nz;
+    for (int y0 = 0; y0 < ny; y0 += TY)
+        for (int z0 = 0; z0 < nz; z0 += TZ)
+            for (int k = 0; k < 19; ++k) {
+                const int cy = D3Q19::cy(k), cz = D3Q19::cz(k);
+                if (push_by_box<TY, TZ>(y0, ny, cz)) {
+                    const PushBox b = push_box_start<TY, TZ>(y0, z0, cy);
+                    if (b.y < 0 || b.z < 0) return 1;                       // negative start: traps
+                    if ((b.z * 8) % 16) return 2;                           // unaligned start: traps
+                    if (b.y + TY > ny || b.z + TZ > nz) return 3;           // would be clipped: elements lost
+                    for (int r = 0; r < TY; ++r)
+                        for (int c = 0; c < TZ; ++c) {
+                            const int yy = b.y + r, zz = b.z + c;
+                            if (yy < 0 || yy >= ny || zz < 0 || zz >= nz) continue;
+                            out[k * plane + (size_t)yy * nz + zz] = post[k * plane + (size_t)(y0 + r) * nz + (z0 + c)];
+                            ++writes[k * plane + (size_t)yy * nz + zz];
+                        }
+                } else {
+                    for (int r = 0; r < TY; ++r)
+                        for (int c = 0; c < TZ; ++c) {
+                            const int yy = (y0 + r + cy + ny) % ny, zz = (z0 + c + cz + nz) % nz;
+                            out[k * plane + (size_t)yy * nz + zz] = post[k * plane + (size_t)(y0 + r) * nz + (z0 + c)];
+                            ++writes[k * plane + (size_t)yy * nz + zz];
+                        }
+                }
+            }
+    return 0;
+}
+
+extern "C" int host_check_hcz3d_box_push(int ty, int tz, int ny, int nz, const double *post, double *out, int *writes)
+{
+    if (ty == 8 && tz == 32) return run_push<8, 32>(ny, nz, post, out, writes);
+    if (ty == 4 && tz == 8) return run_push<4, 8>(ny, nz, post, out, writes);
+    return -2;
+}
+
+// how many (tile, direction) pushes leave as boxes
+extern "C" int host_check_hcz3d_box_count(int ty, int tz, int ny, int nz)
+{
+    int n = 0;
+    for (int y0 = 0; y0 < ny; y0 += ty)
+        for (int z0 = 0; z0 < nz; z0 += tz)
+            for (int k = 0; k < 19; ++k)
+                n += (ty == 8 ? push_by_box<8, 32>(y0, ny, D3Q19::cz(k)) : push_by_box<4, 8>(y0, ny, D3Q19::cz(k))) ? 1 : 0;
+    return n;
+}

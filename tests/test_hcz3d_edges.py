@@ -113,3 +113,25 @@ def test_every_edge_slot_has_exactly_one_writer_and_one_reader():
     assert len(set(writers)) == len(writers)          # one writer per slot
     assert set(writers) == readers                    # every slot that is read is written, and nothing else
     assert len(readers) == eplane                     # the arrays have no unused slot
+
+
+@pytest.mark.parametrize("ty,tz,ny,nz", [(8, 32, 40, 64), (8, 32, 16, 32), (8, 32, 8, 32), (4, 8, 20, 24)])
+def test_box_stores_plus_thread_stores_are_the_periodic_push(ty, tz, ny, nz):
+    """hcz3d_sweep.cu, VAR bit 2: the c_z = 0 directions of the tiles away from the first / last tile row leave as TMA box stores,
+    everything else as thread-level stores with the periodic wrap.  With the rule the kernel uses (push_by_box / push_box_start):
+    no box breaks the device's rule for box stores (non-negative, 16-byte aligned start) or is clipped, every (node, direction)
+    slot is written exactly once, and the result is the periodic push."""
+    rng = np.random.default_rng(ny * 100 + nz)
+    post = rng.random((19, ny, nz))
+    out = np.full((19, ny, nz), np.nan)
+    writes = np.zeros((19, ny, nz), dtype=np.int32)
+    dp = ctypes.POINTER(ctypes.c_double)
+    L = _lib()
+    rc = L.host_check_hcz3d_box_push(ty, tz, ny, nz, post.ctypes.data_as(dp), out.ctypes.data_as(dp), writes.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+    assert rc == 0
+    assert np.all(writes == 1)
+    for k, (cx, cy, cz) in enumerate(C19):
+        assert np.array_equal(out[k], np.roll(post[k], (cy, cz), axis=(0, 1))), k
+    # the boxes are really used: 9 directions with c_z = 0 in every tile of the interior tile rows
+    rows = max(ny // ty - 2, 0)
+    assert L.host_check_hcz3d_box_count(ty, tz, ny, nz) == 9 * rows * (nz // tz)
