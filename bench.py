@@ -137,6 +137,28 @@ CPU_SAMPLE = {"sc3d": (96, 96, 96), "hcz3d": (64, 64, 64), "sc2d": (1024, 1024, 
               "sc_rt2d": (256, 1026, 1)}
 
 
+def static_config(pkg, a, world):
+    """the `config` of the JSON line: what the workload IS, computed from the arguments alone, so that the GPU arm and the
+    --impl reference arm print the identical dict (the reference arm times a bounded sample OF this configuration and says so
+    in cpu_baseline.sample).  Everything measured or chosen at run time (transport, strong pass, bit-identity check) lives
+    in `roofline`, which the driver also keeps verbatim."""
+    P, slab = pkg.params, pkg.slab
+    key, sz, desc = WORKLOADS[a.workload]
+    if a.size:
+        sz = tuple(int(v) for v in a.size.split("x"))
+        sz = sz + (1,) * (3 - len(sz))
+    nxl, ny, nz = sz
+    if a.scaling == "weak" or world == 1:
+        nx_global = nxl * world
+    else:
+        nx_global = nxl
+        b = slab.slab_bounds(nx_global, world)[0]
+        nxl = b[1] - b[0]
+    prm, _, _ = build_params(P, key, nxl, ny, nz, nx_global, 0, int(a.fused))
+    return {"workload": a.workload, "description": desc, "lattice_per_gpu": [nxl, ny, nz], "lattice_global": [nx_global, ny, nz],
+            "parallelism": "x-slab ring x%d" % world, "l2_policy": l2_policy_text(prm.lattice_size * 8)}
+
+
 def cpu_baseline(P, key, threads=0, target_s=12.0):
     """time the CPU oracle port on a bounded sample of the same workload (rank 0)"""
     from _oracle import OracleSim
@@ -166,26 +188,30 @@ def run_reference_arm(a, rank):
     pkg = entry.load_package()
     P = pkg.params
     key = WORKLOADS[a.workload][0]
-    vals = []
+    vals, secs = [], []
     cb = None
     for _ in range(max(1, min(a.steps, 3))):
+        t0 = time.perf_counter()
         cb = cpu_baseline(P, key, target_s=8.0)
+        secs.append(time.perf_counter() - t0)
         vals.append(cb["value"])
     v = float(np.mean(vals))
     cb["value"] = v
+    cb["sample_lattice"] = list(CPU_SAMPLE[key])
+    cb["samples_timed"] = len(vals)
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
     line = {"impl": "reference", "metric": "fp64 MLUPS (D3Q19 Shan-Chen/HCZ)", "value": v, "unit": "MLUPS", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": a.scaling,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": a.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": a.workload, "description": WORKLOADS[a.workload][2],
-                       "cpu_sample_lattice": list(CPU_SAMPLE[key]), "cpu_threads": cb["cores"]},
+            "config": static_config(pkg, a, world),         # the GPU arm's config, key for key
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     ref = reference_functor_baseline(key)
     if ref:
         line["cpu_baseline_reference"] = ref
     # the other half of the metric (HCZ D3Q19), whose CPU arm IS the untouched reference functor
     if a.workload == "c4_sc_d3q19_512":
-        line["config"]["also"] = {"c4_hcz_d3q19_512": {"cpu_baseline": cpu_baseline(P, "hcz3d", target_s=6.0),
-                                                       "cpu_baseline_reference": reference_functor_baseline("hcz3d")}}
+        cb["also"] = {"c4_hcz_d3q19_512": {"cpu_baseline": cpu_baseline(P, "hcz3d", target_s=6.0),
+                                           "cpu_baseline_reference": reference_functor_baseline("hcz3d")}}
     print(json.dumps(line))
 
 
@@ -455,9 +481,10 @@ def main():
     lat.close()
     del lat, ring
 
-    config = {"workload": a.workload, "description": head["description"], "lattice_per_gpu": head["lattice_per_gpu"],
-              "lattice_global": head["lattice_global"], "parallelism": "x-slab ring x%d" % world,
-              "transport": head["transport"], "fused": int(a.fused), "l2_policy": l2_policy_text(head["bytes_per_gpu"])}
+    config = static_config(cx.pkg, a, world)
+    if (config["lattice_per_gpu"], config["lattice_global"]) != (head["lattice_per_gpu"], head["lattice_global"]):
+        config.update(lattice_per_gpu=head["lattice_per_gpu"], lattice_global=head["lattice_global"])   # what ran wins
+    roofline["transport"], roofline["fused"] = head["transport"], int(a.fused)
 
     # ---- the rest of the metric, in the dicts the driver keeps verbatim ---------------------------------
     default_run = a.workload == "c4_sc_d3q19_512" and not a.size and not a.no_extras and a.scaling == "weak"
@@ -497,8 +524,8 @@ def main():
                 r["single_gpu_ms_per_step"] = solo["ms_per_step"]
                 r["strong_efficiency"] = r["mlups"] / (world * solo["mlups"])
             strong[wl] = r
-        config["strong_scaling"] = strong
-        config["slab_bit_identical"] = slab_bit_identical(cx)
+        roofline["strong_scaling"] = strong
+        roofline["slab_bit_identical"] = slab_bit_identical(cx)
 
     cb = cbr = None
     if rank == 0 and not a.no_cpu:

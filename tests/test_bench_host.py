@@ -1,0 +1,80 @@
+"""bench.py, host side (no GPU): the --impl reference arm prints a line the driver can pair with the GPU arm's --
+same metric, unit, direction and, key for key, the same `config` -- and `static_config` reproduces the `config` the GPU arm
+printed on the B200 boxes (committed driver-format lines under profiles/).  The CPU arm times oracle/ (allowed: it is the
+reference arm of the bench, never the product path)."""
+import json
+import os
+import sys
+import types
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402
+
+MOVED = ("transport", "fused", "strong_scaling", "slab_bit_identical")     # run-time keys, now under `roofline`
+
+
+def _args(**kw):
+    a = dict(workload="c4_sc_d3q19_512", size="", scaling="weak", fused=1, gpus=1, steps=1, warmup=3)
+    a.update(kw)
+    return types.SimpleNamespace(**a)
+
+
+def _committed_line(name):
+    for ln in open(os.path.join(ROOT, "profiles", name)):
+        if ln.startswith('{"metric'):
+            return json.loads(ln)
+    raise AssertionError("no bench line in " + name)
+
+
+@pytest.mark.parametrize("name,world", [("bench_r2_final3_n1.json", 1), ("bench_r2_final2_n2.json", 2), ("bench_r2_final2_n8.json", 8)])
+def test_static_config_is_what_the_gpu_arm_printed(name, world):
+    pkg = bench.entry.load_package()
+    printed = {k: v for k, v in _committed_line(name)["config"].items() if k not in MOVED}
+    assert bench.static_config(pkg, _args(gpus=world), world) == printed
+
+
+def test_static_config_strong_and_size():
+    pkg = bench.entry.load_package()
+    c = bench.static_config(pkg, _args(scaling="strong", gpus=8), 8)
+    assert c["lattice_global"] == [512, 512, 512] and c["lattice_per_gpu"] == [64, 512, 512]
+    c = bench.static_config(pkg, _args(workload="c3_hcz_d2q9_full", scaling="strong", gpus=8), 8)
+    assert c["lattice_global"] == [2048, 8194, 1] and c["lattice_per_gpu"] == [256, 8194, 1]
+    c = bench.static_config(pkg, _args(size="128x64"), 1)
+    assert c["lattice_per_gpu"] == [128, 64, 1] and c["lattice_global"] == [128, 64, 1]
+    c = bench.static_config(pkg, _args(workload="c1_sc_d2q9_256"), 1)
+    assert "FITS in the 126 MB L2" in c["l2_policy"]
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 0), (2, 1)])
+def test_reference_arm_line(monkeypatch, capsys, world, rank):
+    real = bench.cpu_baseline
+    monkeypatch.setattr(bench, "cpu_baseline", lambda P, key, threads=0, target_s=0.0: real(P, key, threads, target_s=0.2))
+    monkeypatch.setattr(bench, "reference_functor_baseline", lambda key, same_lattice=None: None)   # timed in its own tests
+    monkeypatch.setenv("WORLD_SIZE", str(world))
+    a = _args(gpus=world)
+    bench.run_reference_arm(a, rank)
+    out = capsys.readouterr().out.strip()
+    if rank != 0:
+        assert out == ""            # the other ranks exit without work
+        return
+    line = json.loads(out)
+    gpu = _committed_line("bench_r2_final3_n1.json")
+    for k in ("metric", "unit", "higher_is_better", "dtype", "data", "scaling"):
+        assert line[k] == gpu[k], k
+    assert line["impl"] == "reference" and line["n_gpus"] == world and line["steps"] == 1
+    assert line["config"] == bench.static_config(bench.entry.load_package(), a, world)
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == bench.host_threads() and cb["value"] == line["value"]
+    assert cb["sample_lattice"] == [96, 96, 96] and "96x96x96" in cb["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "c4_hcz_d3q19_512" in cb["also"]
+
+
+def test_host_threads_ignores_omp_num_threads(monkeypatch):
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")      # what torchrun exports to every rank
+    assert bench.host_threads() == len(os.sched_getaffinity(0))
