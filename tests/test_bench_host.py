@@ -78,3 +78,68 @@ def test_reference_arm_line(monkeypatch, capsys, world, rank):
 def test_host_threads_ignores_omp_num_threads(monkeypatch):
     monkeypatch.setenv("OMP_NUM_THREADS", "1")      # what torchrun exports to every rank
     assert bench.host_threads() == len(os.sched_getaffinity(0))
+
+
+class _FakeLat:
+    def close(self):
+        pass
+
+
+class _FakeCtx:
+    """stands in for bench.Ctx so that main()'s assembly of the JSON line runs without a device"""
+    world, rank = 1, 0
+
+    def __init__(self, a):
+        self.rank, self.local_rank = type(self).rank, 0
+        self.world = type(self).world
+        self.pkg = bench.entry.load_package()
+        self.dev = types.SimpleNamespace(index=0)
+        self.dist = types.SimpleNamespace(destroy_process_group=lambda: None)
+
+    def barrier(self):
+        pass
+
+
+def _fake_measure(cx, workload, scaling, steps, warmup, fused=1, size="", solo=False, sample_clocks=False, keep=False, ktiming=True):
+    key, sz, desc = bench.WORKLOADS[workload]
+    world = 1 if solo else cx.world
+    nxl, ny, nz = sz
+    nxg = nxl * world if (scaling == "weak" or world == 1) else nxl
+    if nxg == nxl and world > 1:
+        nxl = nxl // world
+    res = {"workload": workload, "description": desc, "scaling": scaling, "n_gpus": world, "lattice_per_gpu": [nxl, ny, nz],
+           "lattice_global": [nxg, ny, nz], "steps": steps, "ms_per_step": 1.0, "mlups": 1000.0 * world, "mass": 1.0, "gpu_launches": steps,
+           "transport": "peer" if world > 1 else None, "kernel": "k", "kernel_ms": 1.0, "kernel_launches_sampled": steps,
+           "algorithmic_bytes_per_lu": 305, "lattice_updates_per_launch": nxl * ny * nz, "achieved_gbs": 5000.0, "peak_gbs": 6545.0,
+           "peak_source": "test", "frac": 0.76, "step_frac_of_peak": 0.75, "bytes_per_gpu": nxl * ny * nz * 39 * 8, "clocks": None}
+    return (res, _FakeLat(), None, None) if keep else res
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_gpu_arm_line_assembly(monkeypatch, capsys, world):
+    """main() with the device work stubbed out: the line parses, `config` is static_config (so equal to the reference arm's),
+    the run-time keys sit under `roofline`."""
+    _FakeCtx.world = world
+    monkeypatch.setattr(bench, "Ctx", _FakeCtx)
+    monkeypatch.setattr(bench, "measure", _fake_measure)
+    monkeypatch.setattr(bench, "run_e2e", lambda *a, **k: {"value": 1.0, "unit": "MLUPS", "h2d_bytes_per_step": 1, "d2h_bytes_per_step": 1})
+    monkeypatch.setattr(bench, "slab_bit_identical", lambda cx: {"sc_d3q19": {"bit_identical": True}})
+    monkeypatch.setattr(bench, "cpu_baseline", lambda *a, **k: {"value": 1.0, "kind": "port"})
+    monkeypatch.setattr(bench, "reference_functor_baseline", lambda *a, **k: None)
+    monkeypatch.setattr(bench, "pulsatile_extra", lambda *a, **k: {"mlups": 1.0})
+    monkeypatch.setenv("WORLD_SIZE", str(world))
+    monkeypatch.setenv("RANK", "0")
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", str(world), "--steps", "20", "--warmup", "5"])
+    bench.main()
+    line = json.loads(capsys.readouterr().out.strip())
+    assert line["config"] == bench.static_config(bench.entry.load_package(), _args(gpus=world), world)
+    assert line["n_gpus"] == world and line["value"] == 1000.0 * world
+    rf = line["roofline"]
+    assert rf["fused"] == 1 and rf["transport"] == ("peer" if world > 1 else None)
+    if world == 1:
+        assert set(rf["also"]) == {"c4_hcz_d3q19_512", "c3_hcz_d2q9_full", "sc_d2q9_8192", "c1_sc_d2q9_256", "c2_hcz_d2q9_256", "c5_pulsatile_1024"}
+    else:
+        assert set(rf["strong_scaling"]) == {"c4_sc_d3q19_512", "c4_hcz_d3q19_512", "c3_hcz_d2q9_full"}
+        assert all(abs(v["strong_efficiency"] - 1.0) < 1e-12 for v in rf["strong_scaling"].values())
+        assert rf["slab_bit_identical"]["sc_d3q19"]["bit_identical"] is True
+    assert not any(k in line["config"] for k in MOVED)
