@@ -608,6 +608,21 @@ def pulsatile_extra(cx, steps, warmup, with_cpu):
     return out
 
 
+def pulsatile_config(a, world, N):
+    """`config` of the Pulsatile lines, the same dict in both arms (nx = 1 + 10 (N - 2), AB/apps/PulsatileBloodFlow2D.h:740-751)"""
+    nx = 1 + 10 * (N - 2)
+    return {"workload": a.workload, "description": WORKLOADS[a.workload][2], "lattice_per_gpu": [nx, N, 1],
+            "parallelism": "replicas only x%d (global per-column wall recurrence)" % world,
+            "initial_state": "open vessel at rest, margin 6 rows (pulsatile_cases.open_vessel_at_rest), uploaded through the C ABI",
+            "l2_policy": "working set %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (2 * 9 * nx * N * 8 / 1e9)}
+
+
+def yl2d_config(a, world, N):
+    return {"workload": a.workload, "description": WORKLOADS[a.workload][2], "lattice_per_gpu": [N, N, 1],
+            "parallelism": "replicas only x%d" % world,
+            "l2_policy": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (36 * N * N * 8 / 1e9)}
+
+
 def run_pulsatile(a, rank, world, local_rank):
     """BASELINE configs[4]: the compliant-vessel case.  The wall update is a global per-column recurrence fed by the
     centre-line pressure and the path has no periodic x: replicas only (each rank runs its own vessel)."""
@@ -622,7 +637,7 @@ def run_pulsatile(a, rank, world, local_rank):
         print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "MLUPS", "n_gpus": a.gpus,
                           "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": a.workload, "description": WORKLOADS[a.workload][2]}, "cpu_baseline": cb,
+                          "config": pulsatile_config(a, world, N), "cpu_baseline": cb,
                           "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     import torch
@@ -719,10 +734,7 @@ def run_pulsatile(a, rank, world, local_rank):
         print(json.dumps({"metric": metric, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic",
-                          "config": {"workload": a.workload, "description": WORKLOADS[a.workload][2], "lattice_per_gpu": [sim.nx, sim.ny, 1],
-                                     "parallelism": "replicas only x%d (global per-column wall recurrence)" % world,
-                                     "initial_state": "open vessel at rest, margin 6 rows (pulsatile_cases.open_vessel_at_rest), uploaded through the C ABI",
-                                     "l2_policy": "working set %.2f GB per GPU >> 126 MB L2 (no flush needed)" % (2 * 9 * nelem * 8 / 1e9)},
+                          "config": pulsatile_config(a, world, N),
                           "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
     sim.close()
     if world > 1:
@@ -759,7 +771,7 @@ def run_yl2d(a, rank, world, local_rank):
         cb = yl2d_cpu_baseline(512, target_s=8.0 * max(1, min(a.steps, 3)))
         print(json.dumps({"impl": "reference", "metric": metric, "value": cb["value"], "unit": "MLUPS", "n_gpus": a.gpus, "steps": a.steps,
                           "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f64", "data": "synthetic", "config": {"workload": a.workload, "description": WORKLOADS[a.workload][2]},
+                          "dtype": "f64", "data": "synthetic", "config": yl2d_config(a, world, N),
                           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
     import torch
@@ -835,9 +847,7 @@ def run_yl2d(a, rank, world, local_rank):
         print(json.dumps({"metric": metric, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic",
-                          "config": {"workload": a.workload, "description": WORKLOADS[a.workload][2], "lattice_per_gpu": [N, N, 1],
-                                     "parallelism": "replicas only x%d" % world,
-                                     "l2_policy": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (36 * nelem * 8 / 1e9)},
+                          "config": yl2d_config(a, world, N),
                           "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
     sim.close()
     if world > 1:

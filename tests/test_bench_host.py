@@ -143,3 +143,10 @@ def test_gpu_arm_line_assembly(monkeypatch, capsys, world):
         assert all(abs(v["strong_efficiency"] - 1.0) < 1e-12 for v in rf["strong_scaling"].values())
         assert rf["slab_bit_identical"]["sc_d3q19"]["bit_identical"] is True
     assert not any(k in line["config"] for k in MOVED)
+
+
+def test_pulsatile_and_yl2d_configs_are_what_the_gpu_arm_printed():
+    a = _args(workload="c5_pulsatile_1024")
+    assert bench.pulsatile_config(a, 1, 1024) == _committed_line("bench_r2_puls_1024.json")["config"]
+    c = bench.yl2d_config(_args(workload="yl2d_8192"), 1, 8192)
+    assert c["lattice_per_gpu"] == [8192, 8192, 1] and "19.3 GB" in c["l2_policy"]
