@@ -80,3 +80,32 @@ def test_library_driven_ring_entry_points_fail_cleanly():
     assert lib.clbm_slab_step(None, 1) == -1
     assert lib.clbm_comm_init(None, buf, 0, 2) == -1
     assert lib.clbm_comm_destroy(None) == 0
+
+
+def test_every_entry_point_survives_null_arguments():
+    """nothing crosses the ABI as a crash: every export called with a null context / null pointers / zeros returns an error code
+    (or a benign 0 / NULL for the destroy, query and stream getters) -- on a box without a device as well"""
+    lib = pkg.clbm.load_library()
+    benign_zero = {"clbm_destroy", "clbm_comm_destroy", "clbm_peer_disconnect", "clbm_pulsatile_destroy", "clbm_yl2d_destroy",
+                   "clbm_overlap_supported", "clbm_overlap_variant", "clbm_overlap_width", "clbm_ring_kind",
+                   "clbm_pulsatile_launch_count", "clbm_yl2d_launch_count"}
+    not_swept = {"clbm_last_error", "clbm_abi_version", "clbm_alloc_host", "clbm_free_host", "clbm_comm_unique_id"}
+    swept = 0
+    for name in sorted(pkg.clbm.EXPORTS):
+        if name in not_swept:
+            continue
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None, name + " has no ctypes signature"
+        args = [0 if t in (ctypes.c_int, ctypes.c_int64, ctypes.c_size_t) else 0.0 if t in (ctypes.c_double, ctypes.c_float) else None
+                for t in fn.argtypes]
+        rc = fn(*args)
+        swept += 1
+        if name in ("clbm_stream", "clbm_boundary_stream"):
+            assert rc is None, name
+        elif name in benign_zero:
+            assert rc == 0, (name, rc)
+        else:
+            assert rc < 0, (name, rc)
+            assert lib.clbm_last_error(), name
+    assert swept >= 55
+    assert lib.clbm_free_host(None) == 0 and lib.clbm_alloc_host(64, None) == -1      # free(NULL) is a no-op, as in C
