@@ -21,8 +21,12 @@
  * Parity status:
  *   SC D2Q9 (laplace2D.h, contactAngle2D.h, twoLayeredFlow2D.h, RayleighTaylor2D.h), HCZ D2Q9 (rayleighTaylor2D.h, twoLayeredFlow2D.h),
  *   HCZ D3Q19 (laplace3D.h): PINNED against the reference functor (golden fixtures).
- *   SC D3Q19: the reference has no such functor -> "parity unpinned" against the
- *   reference; pinned indirectly by the z-uniform D3Q19 == D2Q9 consistency test.
+ *   SC D3Q19: the reference has no such C++ functor -> no functor fixtures.  Pinned instead (tests/test_sc3d_oracle_symmetry.py,
+ *   CPU suite) to the reference's only 3-D Shan-Chen code, the Fortran D3Q19 listing SC/apps/fortran (no Fortran compiler
+ *   here: restated in numpy with its own direction ordering): the force of calcu_Fxy (:945-1150) with walls at 1e-13, and
+ *   the whole stream / getuv / calcu_Fxy / collision loop on a periodic lattice, populations at 1e-12 after 1000 steps
+ *   (the listing's on-node bounce-back differs from the case files' half-way rule, so walls are pinned through the
+ *   z-uniform and x-uniform D3Q19 == D2Q9 projections onto the functor-pinned contactAngle2D model instead).
  */
 #include <math.h>
 #include <stdint.h>
