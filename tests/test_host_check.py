@@ -130,6 +130,18 @@ def test_mrt9_factorised_form_equals_the_matrix_form():
     perm = [ref_order.index((int(a), int(b))) for a, b in c]
     np.testing.assert_array_equal(M, Mref[:, perm])
     Minv = np.linalg.inv(M)
+    # ... and its inverse is the reference's literal M_inv table (CooLBM_MRT_combustion.cpp:326-336), rows permuted the same way
+    Minv_ref = np.array([[1 / 9., -1 / 9., 1 / 9., 0, 0, 0, 0, 0, 0],
+                         [1 / 9., -1 / 36., -1 / 18., 1 / 6., -1 / 6., 0, 0, 1 / 4., 0],
+                         [1 / 9., -1 / 36., -1 / 18., 0, 0, 1 / 6., -1 / 6., -1 / 4., 0],
+                         [1 / 9., -1 / 36., -1 / 18., -1 / 6., 1 / 6., 0, 0, 1 / 4., 0],
+                         [1 / 9., -1 / 36., -1 / 18., 0, 0, -1 / 6., 1 / 6., -1 / 4., 0],
+                         [1 / 9., 1 / 18., 1 / 36., 1 / 6., 1 / 12., 1 / 6., 1 / 12., 0, 1 / 4.],
+                         [1 / 9., 1 / 18., 1 / 36., -1 / 6., -1 / 12., 1 / 6., 1 / 12., 0, -1 / 4.],
+                         [1 / 9., 1 / 18., 1 / 36., -1 / 6., -1 / 12., -1 / 6., -1 / 12., 0, 1 / 4.],
+                         [1 / 9., 1 / 18., 1 / 36., 1 / 6., 1 / 12., -1 / 6., -1 / 12., 0, -1 / 4.]])
+    np.testing.assert_allclose(Minv_ref @ Mref, np.eye(9), atol=2e-16)
+    np.testing.assert_allclose(Minv, Minv_ref[perm, :], atol=2e-16)
     L = _lib()
     rng = np.random.default_rng(1)
     for rates in ([1.3, 1.3, 1.3, 1.3, 1.3], [1.7, 1.1, 1.2, 0.9, 1.7], [1.0, 0.5, 1.9, 1.4, 1.96]):
