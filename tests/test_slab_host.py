@@ -78,3 +78,122 @@ def test_ring_exchange_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Slab-aware diagnostics: DistRing.contact_angle_scan / interface_heights combine the per-slab integers of the device scans
+# (csrc/diag_kernels.cu:43-50) with MIN / MAX all-reduces.  Here every rank holds a numpy stand-in for its slab's device scan
+# (same contract, global x) and the ring's result must equal the reference's SERIAL scan of the whole lattice
+# (SC/apps/contactAngle2D.h:465-505, restated below) -- over gloo at world_size 2 and 3, uneven slabs included.
+# ---------------------------------------------------------------------------------------------------------------------------
+def _serial_contact_angle(rho, flag, rho_cut):
+    """calculateContactAngle's integers (base_y, Base, Height) on the whole lattice, rho/flag as [nx][ny]"""
+    nx, ny = rho.shape
+    base_y = 2
+    while base_y < ny and flag[0, base_y] == 0:
+        base_y += 1
+    if base_y >= ny - 1:
+        return base_y, 0, 0
+    xmid = nx // 2
+    left = right = xmid
+    while left > 0 and rho[(left - 1) % nx, base_y] > rho_cut:
+        left -= 1
+    while right < nx - 1 and rho[(right + 1) % nx, base_y] > rho_cut:
+        right += 1
+    base = max(0, right - left + 1)
+    height = 0
+    for y in range(base_y, ny):
+        if flag[xmid, y] == 0 or not rho[xmid, y] > rho_cut:
+            break
+        height += 1
+    return base_y, base, height
+
+
+class _SlabScanStandIn:
+    """what clbm_diag_contact_angle_slab returns for the columns [x0, x1) of the global lattice"""
+
+    def __init__(self, rho, flag, x0, x1):
+        self.rho, self.flag, self.x0, self.x1 = rho, flag, x0, x1
+        self.p = type("p", (), {"ny": rho.shape[1]})()
+
+    def contact_angle_scan_slab(self, rho_cut, base_y_in):
+        nxg, ny = self.rho.shape
+        xmid = nxg // 2
+        base_y = base_y_in
+        if base_y_in < 0:
+            base_y = ny
+            if self.x0 == 0:
+                base_y = 2
+                while base_y < ny and self.flag[0, base_y] == 0:
+                    base_y += 1
+            return [base_y, -1, nxg, ny]
+        lstop, rstop, hstop = -1, nxg, ny
+        for x in range(self.x0, self.x1):
+            if not self.rho[x, base_y] > rho_cut:
+                if x < xmid:
+                    lstop = max(lstop, x)
+                elif x > xmid:
+                    rstop = min(rstop, x)
+        if self.x0 <= xmid < self.x1:
+            hstop = next((y for y in range(base_y, ny) if self.flag[xmid, y] == 0 or not self.rho[xmid, y] > rho_cut), ny)
+        return [base_y, lstop, rstop, hstop]
+
+
+def _sessile_droplet(nx, ny, radius, wall_rows):
+    import numpy as np
+    x, y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    r = np.sqrt((x - nx / 2 + 0.3) ** 2 + (y - wall_rows) ** 2)
+    rho = 0.1515 - 0.1135 * np.tanh((r - radius) / 1.5)
+    flag = np.ones((nx, ny), dtype=np.uint8)
+    flag[:, :wall_rows] = 0
+    flag[:, ny - 1] = 0
+    return rho, flag
+
+
+def _diag_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = []
+        for nx, ny, radius, wall_rows in ((37, 24, 9.0, 1), (40, 30, 12.5, 3), (16, 12, 40.0, 1), (12, 6, 3.0, 5)):
+            rho, flag = _sessile_droplet(nx, ny, radius, wall_rows)
+            x0, x1 = slab.slab_bounds(nx, world)[rank]
+            ring = object.__new__(slab.DistRing)          # the reduction logic only: no device, no halo buffers
+            ring.torch, ring.dist, ring.R, ring.rank, ring.dev = torch, dist, world, rank, torch.device("cpu")
+            ring.lat = _SlabScanStandIn(rho, flag, x0, x1)
+            out.append(tuple(ring.contact_angle_scan(0.1515)))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_contact_angle_reduction_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_diag_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    want = [_serial_contact_angle(*_sessile_droplet(nx, ny, radius, wall_rows), 0.1515)
+            for nx, ny, radius, wall_rows in ((37, 24, 9.0, 1), (40, 30, 12.5, 3), (16, 12, 40.0, 1), (12, 6, 3.0, 5))]
+    assert want[0][1] > 5 and want[0][2] > 3            # a droplet is found ...
+    assert want[2][1] == 16                              # ... a liquid film spans the whole row (no stop on either side) ...
+    assert want[3][1:] == (0, 0)                         # ... and a lattice without a fluid row above the wall
+    for r in range(world):
+        assert res[r] == want, (r, res[r], want)        # every rank holds the serial scan's integers
+    # the in-process combine used by LocalRing (same contract)
+    for (nx, ny, radius, wall_rows), w in zip(((37, 24, 9.0, 1), (40, 30, 12.5, 3), (16, 12, 40.0, 1), (12, 6, 3.0, 5)), want):
+        rho, flag = _sessile_droplet(nx, ny, radius, wall_rows)
+        slabs = [_SlabScanStandIn(rho, flag, *b) for b in slab.slab_bounds(nx, world)]
+        first = [s.contact_angle_scan_slab(0.1515, -1) for s in slabs]
+        base_y = min(f[0] for f in first)
+        second = [s.contact_angle_scan_slab(0.1515, base_y) for s in slabs] if base_y < ny - 1 else None
+        assert slab.combine_contact_angle(ny, first, second) == w
