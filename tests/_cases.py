@@ -28,10 +28,13 @@ pkg = load_package()
 P = pkg.params
 
 
-def golden_names(prefix=""):
-    """multiphase fixtures (clbm_oracle.c); the Pulsatile fixtures have their own loader (pulsatile_golden_names)"""
+def golden_names(prefix="", long_horizon=False):
+    """multiphase fixtures (clbm_oracle.c); the Pulsatile fixtures have their own loader (pulsatile_golden_names).
+    `*_long` fixtures (hundreds to 1000 steps of the untouched functor) pin the ORACLE in the CPU suite only
+    (long_horizon=True); the device meets that horizon against the oracle in test_gpu_parity.py."""
     return sorted(f[:-4] for f in os.listdir(GOLDEN)
-                  if f.endswith(".npz") and f.startswith(prefix) and not f.startswith(("pulsatile_", "yl2d_")))
+                  if f.endswith(".npz") and f.startswith(prefix) and not f.startswith(("pulsatile_", "yl2d_"))
+                  and (long_horizon or not f.endswith("_long.npz")))
 
 
 def pulsatile_golden_names():

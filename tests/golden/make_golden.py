@@ -55,6 +55,19 @@ CASES = {
     "hcz_laplace3d_8x8x8_s4": ("ref_hcz_laplace3d", dict(nx=8, ny=8, nz=8, steps=4, omega=0.5617977528089888,
                                phi_l=0.251, phi_g=0.024, rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=5e-4, gravity=0.0),
                                2, 19, ["phi", "P", "rho", "ux", "uy", "uz"]),
+    # the north_star horizon against the untouched functor itself (CPU suite only: tests/test_oracle_vs_reference.py)
+    "sc_laplace2d_32x32_s1000_long": ("ref_sc_laplace2d", dict(nx=32, ny=32, steps=1000, omega=0.5617977528089888,
+                                      rhol=0.265, rhog=0.038, rho_w=0.12, a=1.0, b=4.0, R=1.0, TT0=0.875, gravity=0.0),
+                                      1, 9, ["rho", "pressure", "ux", "uy"]),
+    "sc_contact2d_48x24_s1000_long": ("ref_sc_contact2d", dict(nx=48, ny=24, steps=1000, omega=1.0, rhol=0.265, rhog=0.038,
+                                      rho_w=0.2, a=1.0, b=4.0, R=1.0, TT0=0.875, RR=8.0),
+                                      1, 9, ["rho", "pressure", "ux", "uy"]),
+    "hcz_rt2d_16x66_s1000_long": ("ref_hcz_rt2d", dict(nx=16, ny=66, steps=1000, omega=1.9598595172738, phi_l=0.251, phi_g=0.024,
+                                  rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-6.25e-6),
+                                  2, 9, ["phi", "P", "rho", "ux", "uy"]),
+    "hcz_laplace3d_10x8x12_s400_long": ("ref_hcz_laplace3d", dict(nx=10, ny=8, nz=12, steps=400, omega=1.3,
+                                        phi_l=0.251, phi_g=0.024, rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=5e-4, gravity=-1e-5),
+                                        2, 19, ["phi", "P", "rho", "ux", "uy", "uz"]),
     "hcz_laplace3d_10x6x12_s3": ("ref_hcz_laplace3d", dict(nx=10, ny=6, nz=12, steps=3, omega=1.3,
                                  phi_l=0.251, phi_g=0.024, rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=5e-4, gravity=-1e-5),
                                  2, 19, ["phi", "P", "rho", "ux", "uy", "uz"]),

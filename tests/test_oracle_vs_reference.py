@@ -11,7 +11,7 @@ import pytest
 import _cases
 from _oracle import OracleSim
 
-NAMES = _cases.golden_names()
+NAMES = _cases.golden_names(long_horizon=True)
 
 
 @pytest.mark.parametrize("name", NAMES)
