@@ -119,7 +119,10 @@ def ncu_traffic(key):
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         e = json.load(open(path)).get(key)
-        return (e["traffic"], "profiles/" + e["report"].replace(".ncu-rep", "") + " (ncu --set full, one launch)") if e else (None, None)
+        if not e:
+            return None, None
+        src = "profiles/%s" % e["summary"] if e.get("summary") else e["report"]      # the committed text summary of that report
+        return e["traffic"], "%s (ncu --set full of %s, one launch)" % (src, e["report"])
     except Exception:
         return None, None
 

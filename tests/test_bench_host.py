@@ -150,3 +150,12 @@ def test_pulsatile_and_yl2d_configs_are_what_the_gpu_arm_printed():
     assert bench.pulsatile_config(a, 1, 1024) == _committed_line("bench_r2_puls_1024.json")["config"]
     c = bench.yl2d_config(_args(workload="yl2d_8192"), 1, 8192)
     assert c["lattice_per_gpu"] == [8192, 8192, 1] and "19.3 GB" in c["l2_policy"]
+
+
+def test_traffic_sources_cite_committed_summaries():
+    table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    for key, e in table.items():
+        traffic, src = bench.ncu_traffic(key)
+        assert traffic == e["dram_bytes_read"] + e["dram_bytes_write"]
+        assert os.path.exists(os.path.join(ROOT, src.split(" ")[0])), src       # the file the line points the reader to exists
+    assert bench.ncu_traffic("no_such_workload") == (None, None)
