@@ -2,6 +2,7 @@
 // with N a parameter (the reference hard-codes N = 64); the loop body is the reference's :764-790.
 //   N=64 steps=2755 vtk=1 dir=/tmp/x  -> writes the reference's own sol_%07d.vtk files every tf/100 steps into dir
 //   N=.. steps=.. out=dump.bin dump_at=a,b,c -> binary fp64 P,Ux,Uy,yr1,yr2 + u8 flag + the full lattice at those steps
+//   state=FILE -> start from a caller-made state (open vessel at rest of the large-N tests / bench.py), see below
 #include "harness_common.h"
 #include <unistd.h>
 #include <set>
@@ -40,6 +41,25 @@ int main(int argc, char** argv)
     lbm.Initialize_Fobj_for_Vessel_Walls();
     lbm.Find_or_Update_Boundary_Nodes();
     lbm.Initialize_P_U_g();
+
+    // state=FILE: start from a caller-made state instead of Initialize_P_U_g (what clbm_pulsatile_upload / the oracle's
+    // pulsatile_set_state do): lattice[2*9*nelem], P, Ux, Uy [nelem], yr1, yr2 [nx] as raw doubles; the mask, Fobj and the
+    // border lists are re-derived from the wall positions by the REFERENCE's own functions (:275-285, :294-382)
+    std::string state = A.s("state", "");
+    if (!state.empty()) {
+        FILE* f = std::fopen(state.c_str(), "rb");
+        if (!f) { std::perror("state"); return 2; }
+        auto rd = [&](double* dst, size_t n) { if (std::fread(dst, sizeof(double), n, f) != n) { std::fprintf(stderr, "short state file\n"); std::exit(2); } };
+        rd(lattice, lattice_vect.size());
+        rd(lbm.P.data(), dim.nelem); rd(lbm.Ux.data(), dim.nelem); rd(lbm.Uy.data(), dim.nelem);
+        rd(lbm.yr1.data(), dim.nx); rd(lbm.yr2.data(), dim.nx);
+        std::fclose(f);
+        lbm.y1new = lbm.yr1; lbm.y2new = lbm.yr2;
+        std::fill(lbm.Vw1.begin(), lbm.Vw1.end(), 0.0); std::fill(lbm.Vw2.begin(), lbm.Vw2.end(), 0.0);
+        lbm.Initialize_Fobj_for_Vessel_Walls();
+        lbm.Find_or_Update_Boundary_Nodes();
+        *parity = 0;
+    }
 
     int tf = lbm.t_beat + 2 * lbm.t_propagation;
     int step = max(1, tf / 100);

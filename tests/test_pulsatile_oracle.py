@@ -58,3 +58,32 @@ def test_pulsatile_initial_wall_out_of_bounds():
     """AB/apps/PulsatileBloodFlow2D.h:181 throws runtime_error("Initial wall location out of bounds.")"""
     with pytest.raises(RuntimeError):
         PulsatileOracle(N=16, p0_in=0.1, p0_out=0.5, alpha=0.01, is_severed=0)
+
+
+@pytest.mark.parametrize("name", ["open_N128_m6", "open_N256_m6"])
+def test_pulsatile_oracle_bit_exact_vs_reference_from_the_open_vessel(name):
+    """the start state of the large-N device tests and of bench.py's N = 1024 line (pulsatile_cases.open_vessel_at_rest) handed
+    to the UNTOUCHED reference header at N = 128 / 256 (tests/golden/make_golden_pulsatile_open.py): the oracle must make of it
+    exactly what the reference does -- walls dilating from the inlet, fresh nodes, both Zou/He ends -- SHA-256 of every array."""
+    rec = json.load(open(os.path.join(_cases.GOLDEN, "pulsatile_open_sha256.json")))[name]
+    N = rec["N"]
+    st = _cases.pkg.pulsatile_cases.open_vessel_at_rest(N, margin=rec["margin"])
+    o = PulsatileOracle(N=N)
+    o.set_state(st["lattice"], st["P"], st["Ux"], st["Uy"], st["yr1"], st["yr2"], 0, 0)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    assert int((o.fields()["flag"] == 1).sum()) == rec["initial_bulk_nodes"]
+    t = 0
+    for d in rec["dumps"]:
+        o.step(d - t)
+        t = d
+        want = rec["steps"][str(d)]
+        f = o.fields()
+        assert int((f["flag"] == 1).sum()) == want["bulk_nodes"]
+        assert sha(f["flag"]) == want["flag"]
+        for k in ("yr1", "yr2", "P", "Ux", "Uy"):
+            assert sha(f[k]) == want[k], (name, d, k)
+        assert sha(o.lattice()) == want["lattice"], (name, d)
+        assert o.parity == want["parity"]
+    last = rec["steps"][str(rec["dumps"][-1])]
+    assert last["bulk_nodes"] > rec["initial_bulk_nodes"] and last["yr2_min_max"][1] - last["yr2_min_max"][0] > 5.0   # the walls moved
+    o.close()
