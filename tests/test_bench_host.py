@@ -159,3 +159,11 @@ def test_traffic_sources_cite_committed_summaries():
         assert traffic == e["dram_bytes_read"] + e["dram_bytes_write"]
         assert os.path.exists(os.path.join(ROOT, src.split(" ")[0])), src       # the file the line points the reader to exists
     assert bench.ncu_traffic("no_such_workload") == (None, None)
+
+
+def test_pulsatile_cpu_arm_is_the_untouched_reference_from_the_open_vessel():
+    from _oracle import ref_binary
+    if not ref_binary("ref_pulsatile"):
+        pytest.skip("oracle/_ref/ref_pulsatile not built (no /root/reference here)")
+    cb = bench.pulsatile_cpu_baseline(64, target_s=0.2)
+    assert cb["kind"] == "reference" and cb["cores"] == 1 and cb["value"] > 0 and "open vessel" in cb["sample"]
