@@ -23,9 +23,11 @@ THREADS = max(1, len(os.sched_getaffinity(0)))
 
 RUNS = [
     ("dropin_sc_contact2d", ["nx=96", "ny=48", "steps=1000", "omega=1.0", "RR=14"]),
-    ("dropin_sc_contact2d", ["nx=64", "ny=40", "steps=301", "omega=1.25", "RR=10"]),
     ("dropin_hcz_laplace3d", ["nx=10", "ny=8", "nz=12", "steps=40", "omega=1.3", "gravity=-1e-5"]),
     ("dropin_hcz_laplace3d", ["nx=12", "steps=100", "omega=0.5617977528089888"]),     # the shipped config's relaxation rate (ulb .01, Re 6)
+    # last: an ODD step count with walls -- the downloaded buffer is then the one the caller did not upload, whose bounce_back
+    # nodes must still hold the reference's value-initialised zeros (a combination no earlier Shan-Chen test compares node by node)
+    ("dropin_sc_contact2d", ["nx=64", "ny=40", "steps=301", "omega=1.25", "RR=10"]),
 ]
 
 
