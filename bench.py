@@ -6,12 +6,16 @@
 
 Default workload = BASELINE.json configs[3], the configuration the metric is quoted on:
 Shan-Chen D3Q19 droplet on a wall (contact-angle bounce-back planes y=0, ny-1), 512^3 fp64 per GPU.
-A "step" is one lattice time step over the whole lattice.  N>1: x-slab ring over NCCL, weak scaling
+A "step" is one lattice time step over the whole lattice.  N>1: x-slab ring, weak scaling
 (512 x-planes per GPU, nx_global = 512 N) unless --scaling strong.
 
 One JSON line on stdout (rank 0).  value = all lattice updates of all ranks / device time (max over
 ranks) with the state resident in HBM; e2e = the same through the C ABI with HOST buffers: upload of the
 reference-layout lattice from pinned host memory + K steps + download of rho, ux, uy, uz, all timed.
+`config` (static_config) is what the workload IS, computed from the arguments alone and therefore identical in both arms;
+what is measured or chosen at run time -- transport, the N = 1 extras (`also`), the N > 1 strong pass and slab bit-identity
+check -- sits in `roofline`.  N>1: the ghost exchange is the library's peer-memory ring (CUDA IPC over NVLink), NCCL only
+carries the timing all-reduces.
 """
 import argparse
 import json
