@@ -40,3 +40,33 @@ def test_oracle_thread_count_invariant(name):
     a = OracleSim(p).init_case(case_id, args).step(min(steps, 10), threads=1)
     b = OracleSim(p).init_case(case_id, args).step(min(steps, 10), threads=4)
     np.testing.assert_array_equal(a.lattice, b.lattice)
+
+
+@pytest.mark.parametrize("name", ["c1_sc_d2q9_256", "c2_hcz_d2q9_256"])
+def test_oracle_bit_exact_vs_reference_on_full_baseline_configs(name):
+    """BASELINE.json configs[0] (Shan-Chen 256 x 256) and configs[1] (HCZ Rayleigh-Taylor 256 x 1026) in full -- size, shipped
+    parameters, 1000 steps -- through the UNTOUCHED functors (tests/golden/make_golden_baseline_configs.py; SHA-256 of the
+    populations, every field and the mask, the arrays being tens of MB).  The GPU suite holds the device to the oracle on exactly
+    these two configurations (test_sc_laplace2d_256_1000_steps, the 256 x 1026 1000-step test)."""
+    import hashlib
+    import json
+    import os
+    rec = json.load(open(os.path.join(_cases.GOLDEN, "baseline_configs_sha256.json")))[name]
+    kw = rec["params"]
+    P = _cases.P
+    if name.startswith("c1"):
+        p = P.sc_params(P.MODEL_SC_D2Q9, 256, 256, ulb=0.01, N=256, Re=6.0)            # as test_gpu_parity.py builds configs[0]
+        case_id, args, fmap = P.CASE_SC_LAPLACE2D, (kw["rhol"], kw["rhog"], 10.0), {"rho": "s0", "pressure": "s1", "ux": "ux", "uy": "uy"}
+    else:
+        p = P.hcz_params(P.MODEL_HCZ_D2Q9, 256, 1026, N=256)                            # as test_gpu_parity.py builds configs[1]
+        case_id, args, fmap = P.CASE_HCZ_RT2D, (), {"phi": "s0", "P": "s1", "rho": "s2", "ux": "ux", "uy": "uy"}
+    assert (p.nx, p.ny, p.omega) == (kw["nx"], kw["ny"], kw["omega"])
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    sim = OracleSim(p).init_case(case_id, args)
+    assert sha(sim.flag) == rec["sha256"]["flag"] and int((sim.flag == 1).sum()) == rec["bulk_nodes"]
+    sim.step(kw["steps"])                                  # all host threads: the thread count does not change a bit (test above)
+    assert sha(sim.in_pops()) == rec["sha256"]["pops"]
+    f = sim.fields()
+    for gname, slot in fmap.items():
+        assert float(np.abs(f[slot]).max()) == rec["max_abs"][gname], gname
+        assert sha(f[slot]) == rec["sha256"][gname], gname
