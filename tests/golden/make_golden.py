@@ -62,6 +62,14 @@ CASES = {
     "sc_contact2d_48x24_s1000_long": ("ref_sc_contact2d", dict(nx=48, ny=24, steps=1000, omega=1.0, rhol=0.265, rhog=0.038,
                                       rho_w=0.2, a=1.0, b=4.0, R=1.0, TT0=0.875, RR=8.0),
                                       1, 9, ["rho", "pressure", "ux", "uy"]),
+    "sc_layered2d_10x41_s1000_long": ("ref_sc_layered2d", dict(nx=10, ny=41, steps=1000, omega=1.0, rhol=0.21, rhog=0.067, rho_w=0.067,
+                                      a=1.0, b=4.0, R=1.0, TT0=0.95, gx=1e-6, gy=0.0, G=-1.0, h_lower=0.3, w_int=4),
+                                      1, 9, ["rho", "pressure", "ux", "uy"]),
+    "sc_rt2d_16x66_s1000_long": ("ref_sc_rt2d", dict(nx=16, ny=66, steps=1000, omega=1.0, rhol=1.2, rhog=0.4, rhow=0.2, g=-5.0, a=1.0, b=4.0,
+                                 gravity=-1.25e-5), 1, 9, ["rho", "pressure", "ux", "uy", "fx", "fy"]),
+    "hcz_layered2d_10x41_s1000_long": ("ref_hcz_layered2d", dict(nx=10, ny=41, steps=1000, omega=1.0, phi_l=0.251, phi_g=0.024, rho_l=0.12,
+                                       rho_g=0.04, a=4.0, b=4.0, kappa=0.001, gx=0.0, gx_const=1e-6, h_lower=0.3, w_int=2),
+                                       2, 9, ["phi", "P", "rho", "ux", "uy"]),
     "hcz_rt2d_16x66_s1000_long": ("ref_hcz_rt2d", dict(nx=16, ny=66, steps=1000, omega=1.9598595172738, phi_l=0.251, phi_g=0.024,
                                   rho_l=0.12, rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-6.25e-6),
                                   2, 9, ["phi", "P", "rho", "ux", "uy"]),
