@@ -180,3 +180,39 @@ def test_host_cell_functions_sc_mrt(case):
     assert np.isfinite(f["ux"]).all()
     c = OracleSim(free).init_case(cid, args).step(steps)
     assert rel_linf(c.in_pops(), a.in_pops()) > 1e-8        # the free rates do change the solution
+
+
+def test_host_cell_functions_sc_d3q19_equal_the_reference_fortran_listing():
+    """the DEVICE's per-cell Shan-Chen D3Q19 arithmetic (sc_cell.cuh compiled for the host) against the numpy restatement of the
+    reference's Fortran D3Q19 listing (SC/apps/fortran) with no oracle in between -- the CPU-side twin of
+    tests/test_gpu_zzzzz_sc3d_listing.py, same lattice, state and step count (periodic, no solid nodes: see there)."""
+    from test_sc3d_oracle_symmetry import C19, FTK, FXC, FYC, FZC, _fortran_iteration, _fortran_stream
+    nx, ny, nz, steps, tau = 24, 28, 32, 200, 1.0
+    p = P.sc_params(P.MODEL_SC_D3Q19, nx, ny, nz, tau=tau, sc_force=P.SC_FORCE_LAPLACE)
+    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    r = np.sqrt((x - 11.4) ** 2 + (y - 13.2) ** 2 + (z - 15.7) ** 2)
+    rho0 = 0.1515 - 0.1135 * np.tanh((r - 9.0) / 1.5) + 0.003 * np.cos(0.7 * x - 0.4 * y + 1.1 * z)
+    ff = FTK[:, None, None, None] * rho0[None]
+    to19 = [int(np.where((C19 == (FXC[k], FYC[k], FZC[k])).all(axis=1))[0][0]) for k in range(19)]
+
+    def layout(ff_post):
+        s = _fortran_stream(ff_post)
+        out = np.empty((19, nx * ny * nz))
+        for k in range(19):
+            out[to19[k]] = s[k].reshape(-1)
+        return out
+
+    host = OracleSim(p)                       # holder of the reference-layout arrays only; the oracle never steps here
+    host.lattice[:19 * p.nelem] = layout(ff).reshape(-1)
+    h = HostSim(host).step(steps)
+    for _ in range(steps):
+        ff, rho, u, F = _fortran_iteration(ff, tau, p.TT)
+    assert h.parity.value == 0
+    assert rel_linf(h.in_pops(), layout(ff).reshape(-1)) < TOL
+    _, rho, u, F = _fortran_iteration(ff, tau, p.TT)
+    up = u + F / 2.0 / rho
+    fh = h.fields()
+    assert rho.max() - rho.min() > 0.15
+    assert rel_linf(fh["s0"], rho.reshape(-1)) < TOL
+    assert rel_linf_vec([fh[k] for k in ("ux", "uy", "uz")], list(up.reshape(3, -1))) < TOL
+    assert rel_linf_vec([fh[k] for k in ("fx", "fy", "fz")], list(F.reshape(3, -1))) < TOL
