@@ -216,3 +216,22 @@ def test_host_cell_functions_sc_d3q19_equal_the_reference_fortran_listing():
     assert rel_linf(fh["s0"], rho.reshape(-1)) < TOL
     assert rel_linf_vec([fh[k] for k in ("ux", "uy", "uz")], list(up.reshape(3, -1))) < TOL
     assert rel_linf_vec([fh[k] for k in ("fx", "fy", "fz")], list(F.reshape(3, -1))) < TOL
+
+
+def test_host_cell_force_sc_d3q19_walls_equals_the_reference_fortran_listing():
+    """the device's force gathering (sc_gather_force + the wall term of the contact-angle variant, host-compiled) against
+    `calcu_Fxy` of the Fortran listing on a 3-D state with the two wall planes and a solid block in the bulk"""
+    from test_sc3d_oracle_symmetry import T19, _fortran_calcu_Fxy
+    nx, ny, nz = 14, 12, 10
+    p = P.sc_params(P.MODEL_SC_D3Q19, nx, ny, nz, tau=1.0, rho_w=0.2, sc_force=P.SC_FORCE_CONTACT)
+    o = OracleSim(p)
+    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    r = np.sqrt((x - 6.3) ** 2 + (y - 3.1) ** 2 + (z - 4.6) ** 2)
+    rho = 0.1515 - 0.1135 * np.tanh((r - 3.7) / 1.3) + 0.004 * np.sin(0.9 * x + 0.5 * y - 1.3 * z)
+    solid = (y == 0) | (y == ny - 1) | ((x >= 9) & (x <= 10) & (y >= 5) & (y <= 7) & (z >= 2) & (z <= 4))
+    o.flag[:] = np.where(solid, 0, 1).reshape(-1).astype(np.uint8)
+    o.lattice[:19 * p.nelem] = (T19[:, None] * rho.reshape(-1)[None, :]).reshape(-1)
+    fh = HostSim(o).fields()
+    got = np.stack([fh["fx"], fh["fy"], fh["fz"]], axis=-1).reshape(nx, ny, nz, 3)
+    ref, _ = _fortran_calcu_Fxy(rho, solid, p.rho_w, p.TT)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-13
