@@ -29,11 +29,15 @@ THREADS = max(1, len(os.sched_getaffinity(0)))
 
 OM_C1 = P.lb_parameters(0.01, 256, 6.0)[1]
 OM_C2 = P.lb_parameters(0.04, 256, 3000.0)[1]
+OM_C3 = P.lb_parameters(0.04, 2048, 3000.0)[1]
 CASES = {
     "c1_sc_d2q9_256": ("ref_sc_laplace2d", dict(nx=256, ny=256, steps=1000, omega=OM_C1, rhol=0.265, rhog=0.038, rho_w=0.12,
                                                a=1.0, b=4.0, R=1.0, TT0=0.875, gravity=0.0), 1, 9, ["rho", "pressure", "ux", "uy"]),
     "c2_hcz_d2q9_256": ("ref_hcz_rt2d", dict(nx=256, ny=1026, steps=1000, omega=OM_C2, phi_l=0.251, phi_g=0.024, rho_l=0.12,
                                             rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-6.25e-6), 2, 9, ["phi", "P", "rho", "ux", "uy"]),
+    # configs[2] (2048 x 8194) is 36 h of the functor: its COLUMN shape and parameters on 16 columns, 100 steps, as the GPU suite runs it
+    "c3_shape_16x8194": ("ref_hcz_rt2d", dict(nx=16, ny=8194, steps=100, omega=OM_C3, phi_l=0.251, phi_g=0.024, rho_l=0.12,
+                                             rho_g=0.04, a=4.0, b=4.0, kappa=0.01, gravity=-6.25e-6), 2, 9, ["phi", "P", "rho", "ux", "uy"]),
 }
 
 
@@ -42,8 +46,11 @@ def sha(a):
 
 
 def main():
-    out = {}
+    path = os.path.join(HERE, "baseline_configs_sha256.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
     for name, (binary, kw, sets, Q, fields) in CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
         with tempfile.TemporaryDirectory() as td:
             dump = os.path.join(td, "dump.bin")
             log = subprocess.check_output([os.path.join(REF, binary)] + ["%s=%r" % kv for kv in kw.items()] +

@@ -42,10 +42,11 @@ def test_oracle_thread_count_invariant(name):
     np.testing.assert_array_equal(a.lattice, b.lattice)
 
 
-@pytest.mark.parametrize("name", ["c1_sc_d2q9_256", "c2_hcz_d2q9_256"])
+@pytest.mark.parametrize("name", ["c1_sc_d2q9_256", "c2_hcz_d2q9_256", "c3_shape_16x8194"])
 def test_oracle_bit_exact_vs_reference_on_full_baseline_configs(name):
     """BASELINE.json configs[0] (Shan-Chen 256 x 256) and configs[1] (HCZ Rayleigh-Taylor 256 x 1026) in full -- size, shipped
-    parameters, 1000 steps -- through the UNTOUCHED functors (tests/golden/make_golden_baseline_configs.py; SHA-256 of the
+    parameters, 1000 steps -- and the column shape of configs[2] (8194 rows, N = 2048 parameters, 16 columns, 100 steps; the
+    whole 2048 x 8194 lattice is 36 h of the functor) through the UNTOUCHED functors (tests/golden/make_golden_baseline_configs.py; SHA-256 of the
     populations, every field and the mask, the arrays being tens of MB).  The GPU suite holds the device to the oracle on exactly
     these two configurations (test_sc_laplace2d_256_1000_steps, the 256 x 1026 1000-step test)."""
     import hashlib
@@ -58,7 +59,8 @@ def test_oracle_bit_exact_vs_reference_on_full_baseline_configs(name):
         p = P.sc_params(P.MODEL_SC_D2Q9, 256, 256, ulb=0.01, N=256, Re=6.0)            # as test_gpu_parity.py builds configs[0]
         case_id, args, fmap = P.CASE_SC_LAPLACE2D, (kw["rhol"], kw["rhog"], 10.0), {"rho": "s0", "pressure": "s1", "ux": "ux", "uy": "uy"}
     else:
-        p = P.hcz_params(P.MODEL_HCZ_D2Q9, 256, 1026, N=256)                            # as test_gpu_parity.py builds configs[1]
+        p = P.hcz_params(P.MODEL_HCZ_D2Q9, 256, 1026, N=256) if name.startswith("c2") else \
+            P.hcz_params(P.MODEL_HCZ_D2Q9, 16, 8194, 1, ulb=0.04, N=2048, Re=3000.0)    # as test_gpu_parity.py builds configs[1] / the configs[2] column shape
         case_id, args, fmap = P.CASE_HCZ_RT2D, (), {"phi": "s0", "P": "s1", "rho": "s2", "ux": "ux", "uy": "uy"}
     assert (p.nx, p.ny, p.omega) == (kw["nx"], kw["ny"], kw["omega"])
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
