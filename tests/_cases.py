@@ -41,8 +41,9 @@ def pulsatile_golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("pulsatile_"))
 
 
-def yl2d_golden_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("yl2d_"))
+def yl2d_golden_names(long_horizon=False):
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f.startswith("yl2d_")
+                  and (long_horizon or not f.endswith("_long.npz")))
 
 
 def load_yl2d_golden(name):

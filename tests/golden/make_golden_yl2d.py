@@ -14,6 +14,7 @@ EXE = os.path.join(ROOT, "oracle", "_ref", "ref_yl2d")
 
 CASES = {
     "yl2d_32x32_s200": dict(nx=32, ny=32, steps=200),                                             # config defaults
+    "yl2d_32x32_s1000_long": dict(nx=32, ny=32, steps=1000),                                      # north_star horizon (CPU suite only)
     "yl2d_40x24_s150": dict(nx=40, ny=24, steps=150, Sigma=0.02, W=3.0, M=0.05, RhoL=0.01, RhoH=1.0, tau=0.7),
 }
 
@@ -38,5 +39,6 @@ def run_case(name):
 
 
 if __name__ == "__main__":
-    for n in CASES:
+    import sys
+    for n in (sys.argv[1:] or CASES):
         run_case(n)

@@ -8,7 +8,7 @@ import _cases
 from _oracle import YL2DOracle
 
 
-@pytest.mark.parametrize("name", _cases.yl2d_golden_names())
+@pytest.mark.parametrize("name", _cases.yl2d_golden_names(long_horizon=True))
 def test_yl2d_oracle_bit_exact_vs_reference(name):
     z, kw = _cases.load_yl2d_golden(name)
     steps = kw.pop("steps")
