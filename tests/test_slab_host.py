@@ -139,6 +139,42 @@ class _SlabScanStandIn:
         return [base_y, lstop, rstop, hstop]
 
 
+def _serial_interface_heights(phi, phi_mid):
+    """findInterfaceHeights (PF/apps/rayleighTaylor2D.h:668-708): walking down from y = ny-2 to 1 on the columns x = 0 and
+    x = nx/2, the first y with phi <= phi_mid; both outputs start from int(+-0.05) = 0"""
+    nx, ny = phi.shape
+    out = []
+    for x in (0, nx // 2):
+        out.append(next((y for y in range(ny - 2, 0, -1) if phi[x, y] <= phi_mid), 0))
+    return tuple(out)
+
+
+class _SlabHeightsStandIn:
+    """what clbm_diag_interface_heights returns on the columns [x0, x1): 0 for a column this slab does not own"""
+
+    def __init__(self, phi, x0, x1):
+        self.phi, self.x0, self.x1 = phi, x0, x1
+
+    def interface_heights(self, phi_mid):
+        nxg, ny = self.phi.shape
+        out = []
+        for x in (0, nxg // 2):
+            c = 0
+            if self.x0 <= x < self.x1:
+                for y in range(1, ny - 1):
+                    if self.phi[x, y] <= phi_mid:
+                        c = y
+            out.append(c)
+        return out
+
+
+def _rt_interface(nx, ny, amp):
+    import numpy as np
+    x, y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    h = ny / 2 + amp * nx * np.cos(2 * np.pi * x / (nx - 1))
+    return 0.1375 + 0.1135 * np.tanh((y - h) / 1.25)       # heavy (phi_l) above, light below
+
+
 def _sessile_droplet(nx, ny, radius, wall_rows):
     import numpy as np
     x, y = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
@@ -165,7 +201,14 @@ def _diag_worker(rank, world, port, q):
             ring.torch, ring.dist, ring.R, ring.rank, ring.dev = torch, dist, world, rank, torch.device("cpu")
             ring.lat = _SlabScanStandIn(rho, flag, x0, x1)
             out.append(tuple(ring.contact_angle_scan(0.1515)))
-        q.put((rank, out))
+        heights = []
+        for nx, ny, amp in ((24, 98, 0.1), (33, 70, 0.25), (16, 40, 0.0)):
+            phi = _rt_interface(nx, ny, amp)
+            ring = object.__new__(slab.DistRing)
+            ring.torch, ring.dist, ring.R, ring.rank, ring.dev = torch, dist, world, rank, torch.device("cpu")
+            ring.lat = _SlabHeightsStandIn(phi, *slab.slab_bounds(nx, world)[rank])
+            heights.append(tuple(ring.interface_heights(0.1375)))
+        q.put((rank, (out, heights)))
     finally:
         dist.destroy_process_group()
 
@@ -187,8 +230,11 @@ def test_slab_contact_angle_reduction_gloo(world):
     assert want[0][1] > 5 and want[0][2] > 3            # a droplet is found ...
     assert want[2][1] == 16                              # ... a liquid film spans the whole row (no stop on either side) ...
     assert want[3][1:] == (0, 0)                         # ... and a lattice without a fluid row above the wall
+    want_h = [_serial_interface_heights(_rt_interface(nx, ny, amp), 0.1375) for nx, ny, amp in ((24, 98, 0.1), (33, 70, 0.25), (16, 40, 0.0))]
+    assert want_h[0][0] != want_h[0][1] and min(want_h[0]) > 10      # the perturbed interface sits at different heights on the two columns
     for r in range(world):
-        assert res[r] == want, (r, res[r], want)        # every rank holds the serial scan's integers
+        assert res[r][0] == want, (r, res[r][0], want)        # every rank holds the serial scan's integers
+        assert res[r][1] == want_h, (r, res[r][1], want_h)    # spike / bubble heights (findInterfaceHeights)
     # the in-process combine used by LocalRing (same contract)
     for (nx, ny, radius, wall_rows), w in zip(((37, 24, 9.0, 1), (40, 30, 12.5, 3), (16, 12, 40.0, 1), (12, 6, 3.0, 5)), want):
         rho, flag = _sessile_droplet(nx, ny, radius, wall_rows)
