@@ -109,3 +109,17 @@ def test_every_entry_point_survives_null_arguments():
             assert lib.clbm_last_error(), name
     assert swept >= 55
     assert lib.clbm_free_host(None) == 0 and lib.clbm_alloc_host(64, None) == -1      # free(NULL) is a no-op, as in C
+
+
+def test_every_environment_knob_is_documented():
+    """INTEGRATION.md's tuning-knob table lists every CLBM_* / COOLBM_* variable the sources read"""
+    import glob
+    names = set()
+    pkgdir = os.path.join(ROOT, "multiphase-lbm_b200")
+    for pat in ("csrc/*.cu", "csrc/*.cuh", "csrc/*.h", "apps/*.h", "apps/*.cpp", "*.py"):
+        for f in glob.glob(os.path.join(pkgdir, pat)):
+            names |= set(re.findall(r'"((?:CLBM|COOLBM)_[A-Z0-9_]+)"', open(f, errors="replace").read()))
+    assert len(names) >= 25
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read() + open(os.path.join(ROOT, "README.md")).read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
